@@ -1,0 +1,380 @@
+"""ctypes wrapper of the CPU oracle (oracle/dspsr_oracle.cpp, oracle/orc_fft.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product (dspsr_b200/) never imports this.
+Parity is UNPINNED: the reference ships no golden vectors for the path.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+
+
+def build(force=False):
+    """Compile the oracle with the committed Makefile (g++ only)."""
+    if force or not os.path.exists(_LIB_PATH):
+        subprocess.check_call(["make", "-C", _HERE, "-j4"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+class DedispParams(C.Structure):
+    _fields_ = [
+        ("centre_frequency", C.c_double),
+        ("bandwidth", C.c_double),
+        ("dispersion_measure", C.c_double),
+        ("doppler_shift", C.c_double),
+        ("input_nchan", C.c_uint),
+        ("nchan", C.c_uint),
+        ("input_dual_sideband", C.c_int),
+        ("input_dc_centred", C.c_int),
+        ("input_swap", C.c_int),
+        ("frequency_resolution", C.c_uint),
+        ("impulse_pos", C.c_uint),
+        ("impulse_neg", C.c_uint),
+        ("ndat", C.c_uint),
+        ("unsupported_channels", C.c_uint),
+    ]
+
+
+class FB(C.Structure):
+    _fields_ = [
+        ("input_real", C.c_int),
+        ("input_nchan", C.c_uint),
+        ("npol", C.c_uint),
+        ("nchan", C.c_uint),
+        ("freq_res", C.c_uint),
+        ("nfilt_pos", C.c_uint),
+        ("nfilt_neg", C.c_uint),
+        ("nchan_subband", C.c_uint),
+        ("n_fft", C.c_uint),
+        ("nsamp_fft", C.c_uint),
+        ("nsamp_overlap", C.c_uint),
+        ("nsamp_step", C.c_uint),
+        ("nkeep", C.c_uint),
+    ]
+
+
+class Conv(C.Structure):
+    _fields_ = [
+        ("input_real", C.c_int),
+        ("nchan", C.c_uint),
+        ("npol", C.c_uint),
+        ("n_fft", C.c_uint),
+        ("nfilt_pos", C.c_uint),
+        ("nfilt_neg", C.c_uint),
+        ("nsamp_fft", C.c_uint),
+        ("nsamp_overlap", C.c_uint),
+        ("nsamp_step", C.c_uint),
+    ]
+
+
+class Polyco(C.Structure):
+    _fields_ = [
+        ("tmid_day", C.c_int),
+        ("tmid_sec", C.c_double),
+        ("rphase_int", C.c_double),
+        ("rphase_frac", C.c_double),
+        ("f0", C.c_double),
+        ("span_min", C.c_double),
+        ("obsfreq", C.c_double),
+        ("dm", C.c_double),
+        ("ncoef", C.c_int),
+        ("coef", C.c_double * 32),
+    ]
+
+
+class Pipe(C.Structure):
+    _fields_ = [
+        ("unpack_fmt", C.c_int),
+        ("input_nchan", C.c_uint),
+        ("npol", C.c_uint),
+        ("ndim", C.c_uint),
+        ("lut", C.c_void_p),
+        ("scale", C.c_float),
+        ("use_filterbank", C.c_int),
+        ("fb", FB),
+        ("conv", Conv),
+        ("H", C.c_void_p),
+        ("detect_state", C.c_int),
+        ("detect_ndim", C.c_uint),
+        ("nbin", C.c_uint),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.orc_ja98_optimal_spacing.restype = C.c_double
+        L.orc_ja98_optimal_spacing.argtypes = [C.c_uint]
+        L.orc_normal_cdf.restype = C.c_double
+        L.orc_normal_cdf.argtypes = [C.c_double]
+        L.orc_bittable_unique_values.restype = C.c_double
+        L.orc_bittable_unique_values.argtypes = [C.c_uint, C.c_int, C.c_void_p]
+        L.orc_bittable8.restype = C.c_double
+        L.orc_bittable8.argtypes = [C.c_int, C.c_void_p]
+        L.orc_optimal_fft_length.restype = C.c_int64
+        L.orc_optimal_fft_length.argtypes = [C.c_uint64, C.c_uint64]
+        L.orc_dedisp_prepare.restype = C.c_int
+        L.orc_dedisp_build.restype = C.c_int
+        L.orc_fb_npart.restype = C.c_uint64
+        L.orc_fb_npart.argtypes = [C.c_void_p, C.c_uint64]
+        L.orc_conv_npart.restype = C.c_uint64
+        L.orc_conv_npart.argtypes = [C.c_void_p, C.c_uint64]
+        L.orc_fold_plan.restype = C.c_uint64
+        L.orc_fold_plan.argtypes = [C.c_double, C.c_double, C.c_uint, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_polyco_parse.restype = C.c_int
+        L.orc_polyco_phase.restype = C.c_double
+        L.orc_polyco_phase.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]
+        L.orc_polyco_frequency.restype = C.c_double
+        L.orc_polyco_frequency.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ----------------------------------------------------------------------------- a1
+def bittable8(twos_complement=True):
+    lut = np.zeros(256, np.float32)
+    scale = lib().orc_bittable8(int(twos_complement), _p(lut))
+    return lut, scale
+
+
+def bittable_values(nbit, twos_complement):
+    v = np.zeros(1 << nbit, np.float32)
+    scale = lib().orc_bittable_unique_values(nbit, int(twos_complement), _p(v))
+    return v, scale
+
+
+# ----------------------------------------------------------------------------- a2-a5
+def unpack_caspsr(raw, ndat, lut):
+    out = np.zeros((1, 2, ndat), np.float32)
+    lib().orc_unpack_caspsr(_p(raw), C.c_uint64(ndat), _p(lut), _p(out), C.c_uint64(ndat))
+    return out
+
+
+def unpack_generic8(raw, ndat, nchan, npol, ndim, lut):
+    out = np.zeros((nchan, npol, ndat * ndim), np.float32)
+    lib().orc_unpack_generic8(_p(raw), C.c_uint64(ndat), nchan, npol, ndim, _p(lut), _p(out),
+                              C.c_uint64(ndat * ndim), None)
+    return out
+
+
+def unpack_meerkat(raw, ndat, nchan, npol, scale, sample_swap=1):
+    out = np.zeros((nchan, npol, ndat * 2), np.float32)
+    lib().orc_unpack_meerkat(_p(raw), C.c_uint64(ndat), nchan, npol, C.c_float(scale), sample_swap, _p(out),
+                             C.c_uint64(ndat * 2))
+    return out
+
+
+def unpack_uwb(raw, ndat, npol):
+    out = np.zeros((1, npol, ndat * 2), np.float32)
+    lib().orc_unpack_uwb(_p(raw), C.c_uint64(ndat), npol, _p(out), C.c_uint64(ndat * 2))
+    return out
+
+
+# ----------------------------------------------------------------------------- a7-a9
+def optimal_fft_length(nbad, nfft_max=0):
+    return lib().orc_optimal_fft_length(nbad, nfft_max)
+
+
+def dedispersion(centre_frequency, bandwidth, dm, input_nchan, nchan, input_real, frequency_resolution=0,
+                 dual_sideband=None, dc_centred=False, swap=False, build=True):
+    """Dedispersion::prepare + build + match.  Returns (params, H[nchan, ndat] complex64 or None)."""
+    d = DedispParams()
+    d.centre_frequency = centre_frequency
+    d.bandwidth = bandwidth
+    d.dispersion_measure = dm
+    d.doppler_shift = 1.0
+    d.input_nchan = input_nchan
+    d.nchan = nchan
+    d.input_dual_sideband = int((not input_real) if dual_sideband is None else dual_sideband)
+    d.input_dc_centred = int(dc_centred)
+    d.input_swap = int(swap)
+    d.frequency_resolution = frequency_resolution
+    rc = lib().orc_dedisp_prepare(C.byref(d))
+    if rc != 0:
+        raise ValueError("orc_dedisp_prepare failed rc=%d" % rc)
+    H = None
+    if build:
+        H = np.zeros((nchan, d.ndat), np.complex64)
+        lib().orc_dedisp_build(C.byref(d), _p(H))
+    return d, H
+
+
+# ----------------------------------------------------------------------------- FFT
+def fcc1d(x):
+    x = np.ascontiguousarray(x, np.complex64)
+    out = np.zeros_like(x)
+    lib().orc_fft_fcc1d(x.size, _p(out), _p(x))
+    return out
+
+
+def bcc1d(x):
+    x = np.ascontiguousarray(x, np.complex64)
+    out = np.zeros_like(x)
+    lib().orc_fft_bcc1d(x.size, _p(out), _p(x))
+    return out
+
+
+def frc1d(x):
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros(x.size // 2 + 1, np.complex64)
+    lib().orc_fft_frc1d(x.size, _p(out), _p(x))
+    return out
+
+
+# ----------------------------------------------------------------------------- a10/a11
+def fb_sizes(input_real, input_nchan, npol, nchan, freq_res, nfilt_pos, nfilt_neg):
+    f = FB()
+    f.input_real = int(input_real)
+    f.input_nchan, f.npol, f.nchan, f.freq_res = input_nchan, npol, nchan, freq_res
+    f.nfilt_pos, f.nfilt_neg = nfilt_pos, nfilt_neg
+    lib().orc_fb_sizes(C.byref(f))
+    return f
+
+
+def filterbank(f, x, H):
+    """x: [input_nchan, npol, ndat*ndim] float32 -> [nchan, npol, npart*nkeep] complex64."""
+    x = np.ascontiguousarray(x, np.float32)
+    ndim = 1 if f.input_real else 2
+    ndat = x.shape[2] // ndim
+    npart = lib().orc_fb_npart(C.byref(f), ndat)
+    out = np.zeros((f.nchan, f.npol, npart * f.nkeep), np.complex64)
+    if npart:
+        Hp = _p(np.ascontiguousarray(H, np.complex64)) if H is not None else None
+        lib().orc_filterbank_parts(C.byref(f), _p(x), C.c_uint64(x.shape[2]), Hp, _p(out),
+                                   C.c_uint64(2 * npart * f.nkeep), C.c_uint64(0), C.c_uint64(npart))
+    return out
+
+
+def conv_sizes(input_real, nchan, npol, n_fft, nfilt_pos, nfilt_neg):
+    c = Conv()
+    c.input_real = int(input_real)
+    c.nchan, c.npol, c.n_fft, c.nfilt_pos, c.nfilt_neg = nchan, npol, n_fft, nfilt_pos, nfilt_neg
+    lib().orc_conv_sizes(C.byref(c))
+    return c
+
+
+def convolution(c, x, H):
+    x = np.ascontiguousarray(x, np.float32)
+    ndim = 1 if c.input_real else 2
+    ndat = x.shape[2] // ndim
+    npart = lib().orc_conv_npart(C.byref(c), ndat)
+    nkeep = c.n_fft - c.nfilt_pos - c.nfilt_neg
+    out = np.zeros((c.nchan, c.npol, npart * nkeep), np.complex64)
+    if npart:
+        Hh = np.ascontiguousarray(H, np.complex64)
+        lib().orc_convolution_parts(C.byref(c), _p(x), C.c_uint64(x.shape[2]), _p(Hh), _p(out),
+                                    C.c_uint64(2 * npart * nkeep), C.c_uint64(0), C.c_uint64(npart))
+    return out
+
+
+# ----------------------------------------------------------------------------- a12
+STATE = {"Intensity": 0, "PPQQ": 1, "Coherence": 2, "Stokes": 3}
+
+
+def detect_shape(state, ndim_out):
+    s = STATE[state] if isinstance(state, str) else state
+    if s >= 2:
+        return 4 // ndim_out, ndim_out
+    return (2, 1) if s == 1 else (1, 1)
+
+
+def detect(state, ndim_out, v):
+    """v: [nchan, 2, ndat] complex64 -> [nchan, npol', ndat*ndim'] float32."""
+    s = STATE[state] if isinstance(state, str) else state
+    v = np.ascontiguousarray(v, np.complex64)
+    nchan, npol, ndat = v.shape
+    onpol, ondim = detect_shape(s, ndim_out)
+    out = np.zeros((nchan, onpol, ndat * ondim), np.float32)
+    lib().orc_detect(s, ondim, _p(v), C.c_uint64(2 * ndat), nchan, npol, C.c_uint64(ndat), _p(out),
+                     C.c_uint64(ndat * ondim))
+    return out
+
+
+# ----------------------------------------------------------------------------- a13
+def fold_plan(phi, pps, nbin, ndat):
+    binplan = np.zeros(ndat, np.uint32)
+    hits = np.zeros(nbin, np.uint32)
+    phi_out = C.c_double(0)
+    n = lib().orc_fold_plan(phi, pps, nbin, ndat, _p(binplan), _p(hits), C.byref(phi_out))
+    return binplan, hits, n, phi_out.value
+
+
+def fold(x, ndim, binplan, nbin, profile=None, idat_start=0):
+    """x: [nchan, npol, ndat*ndim] float32; returns profile [nchan, npol, nbin*ndim] (+=)."""
+    x = np.ascontiguousarray(x, np.float32)
+    nchan, npol, n = x.shape
+    if profile is None:
+        profile = np.zeros((nchan, npol, nbin * ndim), np.float32)
+    lib().orc_fold(_p(x), C.c_uint64(n), nchan, npol, ndim, C.c_uint64(idat_start), C.c_uint64(binplan.size),
+                   _p(binplan), nbin, _p(profile))
+    return profile
+
+
+# ----------------------------------------------------------------------------- a16
+def polyco_parse(text):
+    pc = Polyco()
+    rc = lib().orc_polyco_parse(text.encode(), C.byref(pc))
+    if rc != 0:
+        raise ValueError("orc_polyco_parse rc=%d" % rc)
+    return pc
+
+
+def polyco_phase(pc, day, sec, frac):
+    turns = C.c_double(0)
+    f = lib().orc_polyco_phase(C.byref(pc), day, sec, frac, C.byref(turns))
+    return f, turns.value
+
+
+def polyco_frequency(pc, day, sec, frac):
+    return lib().orc_polyco_frequency(C.byref(pc), day, sec, frac)
+
+
+# ----------------------------------------------------------------------------- whole path
+def make_pipe(unpack_fmt, input_nchan, npol, ndim, lut, scale, fb, conv, H, detect_state, detect_ndim, nbin):
+    p = Pipe()
+    p.unpack_fmt = unpack_fmt
+    p.input_nchan, p.npol, p.ndim = input_nchan, npol, ndim
+    p._keep = (lut, H)
+    p.lut = lut.ctypes.data if lut is not None else None
+    p.scale = scale
+    p.use_filterbank = int(fb is not None)
+    if fb is not None:
+        p.fb = fb
+    if conv is not None:
+        p.conv = conv
+    p.H = H.ctypes.data if H is not None else None
+    p.detect_state = STATE[detect_state] if isinstance(detect_state, str) else detect_state
+    p.detect_ndim = detect_ndim
+    p.nbin = nbin
+    return p
+
+
+def pipe_profile_shape(p):
+    out_nchan = p.fb.nchan if p.use_filterbank else p.conv.nchan
+    onpol, ondim = detect_shape(p.detect_state, p.detect_ndim)
+    return out_nchan, onpol, p.nbin * ondim
+
+
+def pipe_run(p, raw, nblock, parts_per_block, phi, pps, nthread=1):
+    shape = pipe_profile_shape(p)
+    profile = np.zeros(shape, np.float32)
+    hits = np.zeros(p.nbin, np.uint32)
+    phi = np.ascontiguousarray(phi, np.float64)
+    pps = np.ascontiguousarray(pps, np.float64)
+    lib().orc_pipe_run(C.byref(p), _p(raw), C.c_uint64(nblock), C.c_uint64(parts_per_block), _p(phi), _p(pps),
+                       C.c_uint(nthread), _p(profile), _p(hits))
+    return profile, hits
