@@ -1,0 +1,153 @@
+"""ctypes binding of libb200dsp.so (include/b200dsp.h).  No CPU fallback: a missing library or a
+missing GPU is an error, never a silent detour."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200dsp.so")
+
+OK = 0
+FMT_CASPSR8, FMT_GENERIC8, FMT_MEERKAT8, FMT_UWB16, FMT_FLOAT32 = range(5)
+INTENSITY, PPQQ, COHERENCE, STOKES = range(4)
+STATE = {"Intensity": INTENSITY, "PPQQ": PPQQ, "Coherence": COHERENCE, "Stokes": STOKES}
+
+
+class UnpackDesc(C.Structure):
+    _fields_ = [
+        ("format", C.c_int),
+        ("nchan", C.c_uint),
+        ("npol", C.c_uint),
+        ("ndim", C.c_uint),
+        ("lut", C.c_float * 256),
+        ("scale", C.c_float),
+        ("sample_swap", C.c_uint),
+    ]
+
+
+class FbDesc(C.Structure):
+    _fields_ = [
+        ("input_real", C.c_int),
+        ("input_nchan", C.c_uint),
+        ("npol", C.c_uint),
+        ("nchan_subband", C.c_uint),
+        ("freq_res", C.c_uint),
+        ("nfilt_pos", C.c_uint),
+        ("nfilt_neg", C.c_uint),
+        ("h_response", C.c_void_p),
+        ("max_npart", C.c_uint),
+    ]
+
+
+class FbInfo(C.Structure):
+    _fields_ = [
+        ("n_fft", C.c_uint),
+        ("nsamp_fft", C.c_uint),
+        ("nsamp_overlap", C.c_uint),
+        ("nsamp_step", C.c_uint),
+        ("nkeep", C.c_uint),
+        ("fft_rows", C.c_uint),
+        ("fft_cols", C.c_uint),
+        ("batch_npart", C.c_uint),
+        ("scratch_bytes", C.c_uint64),
+    ]
+
+
+class PipelineDesc(C.Structure):
+    _fields_ = [
+        ("unpack", UnpackDesc),
+        ("fb", FbDesc),
+        ("detect_state", C.c_int),
+        ("detect_ndim", C.c_uint),
+        ("nbin", C.c_uint),
+    ]
+
+
+class PhaseSegment(C.Structure):
+    _fields_ = [
+        ("start", C.c_uint64),
+        ("count", C.c_uint64),
+        ("a0", C.c_uint64),
+        ("step", C.c_uint64),
+        ("scale_exp", C.c_int),
+        ("pad", C.c_int),
+    ]
+
+
+_vp, _u64, _u, _i, _d = C.c_void_p, C.c_uint64, C.c_uint, C.c_int, C.c_double
+_pvp = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); every symbol include/b200dsp.h declares
+SIGNATURES = {
+    "b200_version": (_i, []),
+    "b200_last_error": (C.c_char_p, []),
+    "b200_context_create": (_i, [_i, _vp, _pvp]),
+    "b200_context_destroy": (_i, [_vp]),
+    "b200_context_synchronize": (_i, [_vp]),
+    "b200_context_launch_count": (C.c_ulonglong, [_vp]),
+    "b200_context_stream": (_vp, [_vp]),
+    "b200_malloc": (_i, [_vp, _u64, _pvp]),
+    "b200_free": (_i, [_vp, _vp]),
+    "b200_malloc_host": (_i, [_vp, _u64, _pvp]),
+    "b200_free_host": (_i, [_vp, _vp]),
+    "b200_memset": (_i, [_vp, _vp, _i, _u64]),
+    "b200_memcpy_h2d": (_i, [_vp, _vp, _vp, _u64]),
+    "b200_memcpy_d2h": (_i, [_vp, _vp, _vp, _u64]),
+    "b200_unpack": (_i, [_vp, C.POINTER(UnpackDesc), _vp, _u64, _vp, _u64]),
+    "b200_fb_plan_create": (_i, [_vp, C.POINTER(FbDesc), _pvp]),
+    "b200_fb_plan_info": (_i, [_vp, C.POINTER(FbInfo)]),
+    "b200_fb_plan_destroy": (_i, [_vp]),
+    "b200_fb_perform": (_i, [_vp, _vp, _u64, _vp, _u64, _u64, _u64, _u64]),
+    "b200_detect": (_i, [_vp, _i, _u, _vp, _u64, _u, _u, _u64, _vp, _u64]),
+    "b200_fold_create": (_i, [_vp, _u, _u, _u, _u, _pvp]),
+    "b200_fold_destroy": (_i, [_vp]),
+    "b200_fold_set_bins": (_i, [_vp, _d, _d, _u64, _u64, C.POINTER(_u64)]),
+    "b200_fold_get_bin_hits": (_i, [_vp, _vp]),
+    "b200_fold_fold": (_i, [_vp, _vp, _u64]),
+    "b200_fold_synch": (_i, [_vp, _vp]),
+    "b200_fold_get_hits": (_i, [_vp, _vp, C.POINTER(_u64)]),
+    "b200_fold_zero": (_i, [_vp]),
+    "b200_fold_device_profile": (_vp, [_vp]),
+    "b200_fold_device_hits": (_vp, [_vp]),
+    "b200_pipeline_create": (_i, [_vp, C.POINTER(PipelineDesc), _pvp]),
+    "b200_pipeline_destroy": (_i, [_vp]),
+    "b200_pipeline_info": (_i, [_vp, C.POINTER(FbInfo)]),
+    "b200_pipeline_execute": (_i, [_vp, _vp, _u64, _u64, _u64, _d, _d, _vp, _u64]),
+    "b200_pipeline_execute_host": (_i, [_vp, _vp, _u64, _u64, _u64, _d, _d]),
+    "b200_pipeline_synch": (_i, [_vp, _vp, _vp, C.POINTER(_u64)]),
+    "b200_pipeline_zero": (_i, [_vp]),
+    "b200_pipeline_fold": (_vp, [_vp]),
+    "b200_phase_segments": (C.c_int64, [_d, _d, _u64, C.POINTER(PhaseSegment), _u64, C.POINTER(_d)]),
+    "b200_phase_bins_sequential": (None, [_d, _d, _u, _u64, _vp, C.POINTER(_d)]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libb200dsp.so; raises if it has not been built (python __graft_entry__.py / make)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libb200dsp.so is not built (%s). Run `make -C dspsr_b200/csrc` or "
+                "`python -c 'import __graft_entry__ as g; g.build()'`. There is no CPU fallback." % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)   # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class B200Error(RuntimeError):
+    """Mirror of the reference's `Error` exceptions (status + message of b200_last_error)."""
+
+    def __init__(self, status, message):
+        super().__init__("b200 status %d: %s" % (status, message))
+        self.status = status
+
+
+def check(status):
+    if status != OK:
+        raise B200Error(status, load().b200_last_error().decode(errors="replace"))

@@ -1,0 +1,123 @@
+// common.cuh -- shared device helpers and host-side error plumbing for libb200dsp.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/b200dsp.h"
+#include "fft_core.cuh"
+
+namespace b200 {
+
+// ---- host-side error handling: no exceptions cross the C ABI --------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define B200_CUDA(call)                                                        \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) return b200::cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define B200_REQUIRE(cond, ...)               \
+  do {                                        \
+    if (!(cond)) {                            \
+      b200::set_error(__VA_ARGS__);           \
+      return B200_ERR_INVALID;                \
+    }                                         \
+  } while (0)
+
+struct Context {
+  int device;
+  cudaStream_t stream;
+  int sm_count;
+  int max_smem_optin;
+  unsigned long long launches;   // kernels launched through this context (bench's gpu_launches)
+};
+
+static inline unsigned ilog2(uint64_t x) {
+  unsigned l = 0;
+  while ((1ull << (l + 1)) <= x) l++;
+  return l;
+}
+static inline bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
+
+// Device twiddle tables owned by a plan
+struct TwiddleTable {
+  float2* tw = nullptr;   // exp(-2 pi i m / n), m < n
+  unsigned n = 0;
+};
+// two-level table for big transforms: W_n^m = hi[m >> 11] * lo[m & 2047]
+struct BigTwiddle {
+  float2* lo = nullptr;
+  float2* hi = nullptr;
+  unsigned nlo = 0, nhi = 0;
+  uint64_t n = 0;
+};
+int make_twiddle(TwiddleTable& t, unsigned n, cudaStream_t s);
+int make_big_twiddle(BigTwiddle& t, uint64_t n, cudaStream_t s);
+void free_twiddle(TwiddleTable& t);
+void free_big_twiddle(BigTwiddle& t);
+
+#ifdef __CUDACC__
+
+// W_n^m from the two-level table (forward sign); one complex multiply (<= 1.5 ulp)
+template <bool INV>
+__device__ __forceinline__ float2 big_twiddle(const float2* __restrict__ lo, const float2* __restrict__ hi,
+                                              unsigned m) {
+  float2 a = __ldg(lo + (m & 2047u));
+  float2 b = __ldg(hi + (m >> 11));
+  float2 w = cmul(a, b);
+  return INV ? cconj(w) : w;
+}
+
+// Block-cooperative FFT.  Every thread of the CTA must call it (it contains __syncthreads()).
+//   N      transform length (power of two, >= EPT unless EPT == N)
+//   j, T   this thread's index within its transform and threads per transform (N / EPT)
+//   map    shared-memory index map of this thread's transform
+//   load   load(idx)  -> float2      called EPT times for idx = j + e*T
+//   store  store(idx, value)         called EPT times with natural-order output indices
+template <int EPT, bool INV, typename Map, typename LoadF, typename StoreF>
+__device__ __forceinline__ void block_fft(unsigned N, unsigned j, unsigned T, const Map& map, float2* smem,
+                                          const float2* __restrict__ tw, unsigned NT, LoadF load,
+                                          StoreF store) {
+  float2 v[EPT];
+#pragma unroll
+  for (int e = 0; e < EPT; e++) v[e] = load(j + e * T);
+  unsigned Ns = 1, rem = N;
+#pragma unroll 1
+  while (rem > 1) {
+    const unsigned R = rem >= (unsigned)EPT ? (unsigned)EPT : rem;
+    const bool last = (rem == R);
+#define B200_STAGE(RR)                                                                   \
+  {                                                                                      \
+    stage_compute<EPT, RR, INV>(v, j, T, Ns, tw, NT);                                    \
+    constexpr int NB = EPT / RR;                                                         \
+    if (last) {                                                                          \
+      _Pragma("unroll") for (int q = 0; q < NB; q++)                                     \
+        _Pragma("unroll") for (int r = 0; r < RR; r++)                                   \
+          store(stage_dest<EPT, RR>(j, T, Ns, q, r), v[q + r * NB]);                     \
+    } else {                                                                             \
+      __syncthreads();                                                                   \
+      _Pragma("unroll") for (int q = 0; q < NB; q++)                                     \
+        _Pragma("unroll") for (int r = 0; r < RR; r++)                                   \
+          smem[map(stage_dest<EPT, RR>(j, T, Ns, q, r))] = v[q + r * NB];                \
+      __syncthreads();                                                                   \
+      _Pragma("unroll") for (int e = 0; e < EPT; e++) v[e] = smem[map(j + e * T)];       \
+    }                                                                                    \
+  }
+    if (R == (unsigned)EPT) B200_STAGE(EPT)
+    else if (EPT > 16 && R == 16) B200_STAGE((EPT > 16 ? 16 : EPT))
+    else if (EPT > 8 && R == 8) B200_STAGE((EPT > 8 ? 8 : EPT))
+    else if (EPT > 4 && R == 4) B200_STAGE((EPT > 4 ? 4 : EPT))
+    else if (EPT > 2 && R == 2) B200_STAGE((EPT > 2 ? 2 : EPT))
+#undef B200_STAGE
+    Ns *= R;
+    rem /= R;
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace b200

@@ -1,0 +1,60 @@
+// engine.cuh -- internal interface between the filterbank engine (filterbank.cu), the fold
+// engine (fold.cu) and the fused pipeline (pipeline.cu).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+enum SrcKind { SRC_F32 = 0, SRC_CASPSR8 = 1 };
+enum Epilogue { EPI_VOLT = 0, EPI_DETECT = 1, EPI_FOLD = 2 };
+
+// where the forward transform reads its samples
+struct FbSource {
+  int kind;                 // SrcKind
+  const void* ptr;          // float planes (SRC_F32) or raw bytes (SRC_CASPSR8)
+  uint64_t span;            // SRC_F32: floats between (chan,pol) planes
+  uint64_t step;            // SRC_F32: floats between parts; raw: SAMPLES between parts
+  const float* d_lut;       // raw 8-bit formats: device copy of the 256-entry table
+};
+
+// what the last kernel does with the dedispersed samples
+struct FbSink {
+  int kind;                 // Epilogue
+  // EPI_VOLT: complex voltages, Filterbank::Engine::perform's output TimeSeries
+  float* volt;
+  uint64_t volt_span;       // floats between (chan,pol) planes
+  uint64_t volt_step;       // floats between parts (nkeep*2)
+  // EPI_DETECT / EPI_FOLD
+  int state;                // b200_state
+  unsigned dndim;           // output ndim (1,2,4); npol' = nprod/dndim
+  float* det;               // EPI_DETECT: detected planes
+  uint64_t det_span;
+  // EPI_FOLD
+  const unsigned* bins;     // bin of every output sample of the block (npart*nkeep)
+  unsigned nbin;
+  float* profile;           // [chan][npol'][nbin][dndim]
+};
+
+}  // namespace b200
+
+struct b200_fb_plan {
+  b200::Context* ctx;
+  b200_fb_desc desc;
+  // derived sizes (Filterbank.C:68-155,409)
+  unsigned C, F, Nc, nsamp_fft, nsamp_overlap, nsamp_step, nkeep, nchan_out;
+  // forward factorisation
+  unsigned P, Q, lbB, G;
+  bool conv_path;           // large single-channel transforms: inverse also two-pass
+  unsigned batch;           // parts per internal batch
+  b200::TwiddleTable twP, twQ, twF;
+  b200::BigTwiddle bigN, big2N;
+  float2* d_response;       // nchan_in*Nc complex or null
+  float2* scratchA;         // batch*nblk*Nc
+  float2* scratchZ;         // batch*nblk*Nc (unused on the conv path)
+  uint64_t scratch_bytes;
+};
+
+namespace b200 {
+// Runs the engine over npart parts: source -> (K1, K2, K3) -> sink.
+int fb_run(b200_fb_plan* plan, const FbSource& src, const FbSink& sink, uint64_t npart);
+}

@@ -1,0 +1,815 @@
+// filterbank.cu -- overlap-save coherent filterbank / convolution engine (sm_100a).
+//
+// Replaces the inner loops of dsp::Filterbank::filterbank (Signal/General/Filterbank.C:563-660)
+// and dsp::Convolution::transformation (Convolution.C:389-458) -- forward FFT, multiply by the
+// dsp::Response, inverse FFT per output channel, discard the wrap-around -- with three kernels
+// around ONE spectrum round trip each:
+//
+//   K1 k_cols_fwd   raw bytes | float samples -> P-point column FFTs (n = Q*n1 + n2), times
+//                   W_N^(n2*k1)                                   -> A[k1][n2]
+//   K2 k_rows       Q-point row FFTs (-> k = k1 + P*k2), real-input split (mirror rows are
+//                   co-resident), response multiply               -> Z[k] natural order
+//                   (convolution path: + inverse Q-point row FFT, twiddle, in place)
+//   K3 k_chan_inv   per output channel: inverse F-point FFT of both polarisations in shared
+//                   memory, discard nfilt_pos/nfilt_neg, then voltages | detect | detect+fold
+//      k_cols_inv   (convolution path, F = N > 8192) inverse P-point column FFTs + same epilogues
+//
+// No cuFFT.  FFTs are hand-written radix-16/8/4/2 Stockham stages on registers (fft_core.cuh)
+// exchanged through shared memory.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "engine.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ float2 ld_nc_f2(const float2* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: forward column pass
+// ------------------------------------------------------------------------------------------
+struct ColsArgs {
+  const void* src;
+  uint64_t span, step;
+  const float* lut;
+  float2* dst;
+  const float2* twP;
+  const float2* blo;
+  const float2* bhi;
+  unsigned P, Q, lb, npol, nchan_in, Nc;
+  uint64_t part0;
+};
+
+template <int SRC>
+__global__ void __launch_bounds__(1024, 1) k_cols_fwd(ColsArgs a) {
+  extern __shared__ float2 smem[];
+  __shared__ float s_lut[256];
+  const unsigned B = 1u << a.lb;
+  const unsigned b = threadIdx.x & (B - 1);
+  const unsigned j = threadIdx.x >> a.lb;
+  const unsigned T = a.P >> 4;
+  const unsigned n2 = blockIdx.x * B + b;
+  const unsigned blk = blockIdx.y;
+  const unsigned pol = blk % a.npol;
+  const unsigned ic = (blk / a.npol) % a.nchan_in;
+  const uint64_t part = a.part0 + blk / (a.npol * a.nchan_in);
+  if (SRC == SRC_CASPSR8) {
+    for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = a.lut[i];
+    __syncthreads();
+  }
+  const float2* fsrc = nullptr;
+  const unsigned char* raw = nullptr;
+  uint64_t samp0 = 0;
+  if (SRC == SRC_F32)
+    fsrc = reinterpret_cast<const float2*>(static_cast<const float*>(a.src) + (uint64_t(ic) * a.npol + pol) * a.span +
+                                           part * a.step) + n2;
+  else {
+    raw = static_cast<const unsigned char*>(a.src);
+    samp0 = part * a.step + 2ull * n2;
+  }
+  MapCols map{b, a.lb, 4};
+  auto load = [&](unsigned n1) -> float2 {
+    if (SRC == SRC_F32) {
+      return ld_nc_f2(fsrc + uint64_t(n1) * a.Q);
+    } else {
+      // CASPSR: byte 8*(i/4) + 4*pol + i%4 (CASPSRUnpacker.C:141-187); samples 2n, 2n+1 are adjacent
+      uint64_t i0 = samp0 + 2ull * uint64_t(n1) * a.Q;
+      uint64_t off = 8ull * (i0 >> 2) + 4u * pol + (i0 & 3ull);
+      unsigned short w = __ldg(reinterpret_cast<const unsigned short*>(raw + off));
+      return make_float2(s_lut[w & 255u], s_lut[w >> 8]);
+    }
+  };
+  float2* dst = a.dst + uint64_t(blk) * a.Nc + n2;
+  auto store = [&](unsigned k1, float2 v) {
+    if (a.Q > 1) v = cmul(v, big_twiddle<false>(a.blo, a.bhi, n2 * k1));
+    dst[uint64_t(k1) * a.Q] = v;
+  };
+  block_fft<16, false>(a.P, j, T, map, smem, a.twP, a.P, load, store);
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: row pass (+ real split, response multiply; convolution path: + inverse row pass)
+// ------------------------------------------------------------------------------------------
+struct RowsArgs {
+  float2* A;
+  float2* Z;
+  const float2* H;
+  const float2* twQ;
+  const float2* blo;
+  const float2* bhi;
+  const float2* b2lo;
+  const float2* b2hi;
+  unsigned P, Q, G, Nc, npol, nchan_in;
+};
+
+template <bool SPLIT, bool CONV, int EPT>
+__global__ void __launch_bounds__(1024, 1) k_rows(RowsArgs a) {
+  extern __shared__ float2 smem[];
+  const unsigned T = EPT ? a.Q / (EPT ? EPT : 1) : 1;
+  const unsigned slot = threadIdx.x / T;
+  const unsigned j = threadIdx.x % T;
+  const unsigned G = a.G;
+  const unsigned tile = blockIdx.x;
+  const unsigned blk = blockIdx.y;
+  const unsigned ic = (blk / a.npol) % a.nchan_in;
+  const unsigned P = a.P, Q = a.Q, Nc = a.Nc;
+  const unsigned nslots = SPLIT ? 2 * G : G;
+
+  auto slot_row = [&](unsigned s) -> unsigned {
+    unsigned g = s % G;
+    unsigned low = tile * G + g;
+    if (!SPLIT || s < G) return low;
+    return (low == 0) ? P / 2 : P - low;
+  };
+  auto smap = [&](unsigned s, unsigned idx) -> unsigned {
+    if (!EPT) return s;
+    return s * Q + ((idx ^ ((idx >> 4) & 15u)) ^ (((s % G) * 2u) & 15u));
+  };
+
+  const unsigned row = slot_row(slot);
+  float2* Ablk = a.A + uint64_t(blk) * Nc;
+
+  // ---- phase 1: forward row FFT into shared memory (natural order) ----
+  if (EPT) {
+    MapRows map{slot * Q, 4, ((slot % G) * 2u) & 15u};
+    const float2* src = Ablk + uint64_t(row) * Q;
+    auto load = [&](unsigned idx) -> float2 { return src[idx]; };
+    auto store = [&](unsigned idx, float2 v) { smem[map(idx)] = v; };
+    block_fft<(EPT ? EPT : 2), false>(Q, j, T, map, smem, a.twQ, Q, load, store);
+  } else {
+    smem[slot] = Ablk[row];
+  }
+  __syncthreads();
+
+  // ---- phase 2: split / response ----
+  const float2* H = a.H ? a.H + uint64_t(ic) * Nc : nullptr;
+  float2* Zblk = CONV ? nullptr : a.Z + uint64_t(blk) * Nc;
+
+  if (SPLIT) {
+    auto do_pair = [&](unsigned sA, unsigned iA, unsigned sB, unsigned iB, unsigned k) {
+      const unsigned pa = smap(sA, iA), pb = smap(sB, iB);
+      const bool same = (pa == pb);
+      float2 zk = smem[pa], zm = cconj(smem[pb]);
+      float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y + zm.y));
+      float2 d = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y - zm.y));
+      float2 o = make_float2(d.y, -d.x);   // -i * d
+      float2 t = cmul(o, big_twiddle<false>(a.b2lo, a.b2hi, k));
+      float2 xk = cadd(e, t);
+      float2 xm = cconj(csub(e, t));
+      if (H) {
+        xk = cmul(xk, __ldg(H + k));
+        if (!same) xm = cmul(xm, __ldg(H + (Nc - k)));
+      }
+      if (CONV) {
+        smem[pa] = xk;
+        if (!same) smem[pb] = xm;
+      } else {
+        Zblk[k] = xk;
+        if (!same) Zblk[Nc - k] = xm;
+      }
+    };
+    const unsigned njobs = G * Q;
+    for (unsigned it = threadIdx.x; it < njobs; it += blockDim.x) {
+      const unsigned g = it % G, k2 = it / G;
+      const unsigned low = tile * G + g;
+      if (low != 0) {
+        do_pair(g, k2, G + g, Q - 1 - k2, low + P * k2);
+      } else if (k2 <= Q / 2) {
+        do_pair(0, k2, 0, (Q - k2) % Q, P * k2);                       // row 0 pairs with itself
+      } else {
+        const unsigned kk = k2 - Q / 2 - 1;                            // row P/2 pairs with itself
+        do_pair(G, kk, G, Q - 1 - kk, P / 2 + P * kk);
+      }
+    }
+    if (tile == 0 && threadIdx.x == 0) {
+      const unsigned kk = (Q / 2 ? Q / 2 : 1) - 1;                     // the one row-P/2 job not covered above
+      do_pair(G, kk, G, Q - 1 - kk, P / 2 + P * kk);
+    }
+  } else {
+    const unsigned njobs = G * Q;
+    for (unsigned it = threadIdx.x; it < njobs; it += blockDim.x) {
+      const unsigned g = it % G, k2 = it / G;
+      const unsigned k = tile * G + g + P * k2;
+      const unsigned pa = smap(g, k2);
+      float2 x = smem[pa];
+      if (H) x = cmul(x, __ldg(H + k));
+      if (CONV) smem[pa] = x;
+      else Zblk[k] = x;
+    }
+  }
+
+  // ---- phase 3 (convolution path): inverse row FFT, twiddle, store in place ----
+  if (CONV) {
+    __syncthreads();
+    float2* dst = Ablk + uint64_t(row) * Q;
+    if (EPT) {
+      MapRows map{slot * Q, 4, ((slot % G) * 2u) & 15u};
+      auto load = [&](unsigned idx) -> float2 { return smem[map(idx)]; };
+      auto store = [&](unsigned m2, float2 v) {
+        dst[m2] = cmul(v, big_twiddle<true>(a.blo, a.bhi, row * m2));
+      };
+      block_fft<(EPT ? EPT : 2), true>(Q, j, T, map, smem, a.twQ, Q, load, store);
+    } else {
+      dst[0] = smem[slot];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// detection products (cross_detect.ic:25-41, stokes_detect.ic:21-44, Detection.C:264-301);
+// explicit _rn intrinsics: no FMA contraction, bit-identical to the CPU loops.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int detect_products(int state, float2 p, float2 q, float* r) {
+  float pp = __fadd_rn(__fmul_rn(p.x, p.x), __fmul_rn(p.y, p.y));
+  float qq = __fadd_rn(__fmul_rn(q.x, q.x), __fmul_rn(q.y, q.y));
+  if (state == B200_INTENSITY) {
+    r[0] = __fadd_rn(pp, qq);
+    return 1;
+  }
+  if (state == B200_PPQQ) {
+    r[0] = pp;
+    r[1] = qq;
+    return 2;
+  }
+  float re = __fadd_rn(__fmul_rn(p.x, q.x), __fmul_rn(p.y, q.y));
+  float im = __fsub_rn(__fmul_rn(p.x, q.y), __fmul_rn(p.y, q.x));
+  if (state == B200_COHERENCE) {
+    r[0] = pp; r[1] = qq; r[2] = re; r[3] = im;
+  } else {
+    r[0] = __fadd_rn(pp, qq); r[1] = __fsub_rn(pp, qq); r[2] = __fmul_rn(2.f, re); r[3] = __fmul_rn(2.f, im);
+  }
+  return 4;
+}
+
+__host__ __device__ inline unsigned state_nprod(int state, unsigned npol) {
+  if (state == B200_INTENSITY) return 1;
+  if (state == B200_PPQQ) return npol;
+  return 4;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: per-channel inverse FFT + discard + epilogue
+// ------------------------------------------------------------------------------------------
+struct ChanArgs {
+  const float2* Z;
+  const float2* twF;
+  unsigned F, C, Nc, npol, nchan_in, CB, npol_cta;
+  unsigned nfilt_pos, nkeep;
+  uint64_t part0;
+  FbSink sink;
+  unsigned smem_bins;   // 1: phase bins accumulate in shared memory (CB*nbin*nprod floats)
+};
+
+template <int EPT, int EPI>
+__global__ void __launch_bounds__(1024, 1) k_chan_inv(ChanArgs a) {
+  extern __shared__ float2 smem[];
+  const unsigned F = a.F;
+  const unsigned T = EPT ? F / (EPT ? EPT : 1) : 1;
+  const unsigned f = threadIdx.x / T;              // transform within the CTA
+  const unsigned j = threadIdx.x % T;
+  const unsigned NF = a.CB * a.npol_cta;
+  const unsigned cb = f / a.npol_cta;
+  const unsigned pol = blockIdx.z * a.npol_cta + f % a.npol_cta;
+  const unsigned ch0 = blockIdx.x * a.CB;          // first output channel of this CTA
+  const unsigned ch = ch0 + cb;
+  const unsigned ic = ch / a.C, csub = ch % a.C;
+  const unsigned partl = blockIdx.y;
+  const uint64_t part = a.part0 + partl;
+  const unsigned blk = (partl * a.nchan_in + ic) * a.npol + pol;
+  const unsigned sh = 4;
+  auto fmap = [&](unsigned ff, unsigned idx) -> unsigned {
+    if (!EPT) return ff;
+    if (F < 16) return ff * F + idx;
+    return ff * F + (idx ^ ((idx >> sh) & 15u));
+  };
+
+  float* bins = reinterpret_cast<float*>(smem + uint64_t(NF) * F);
+  const unsigned nprod = (EPI == EPI_VOLT) ? 0 : state_nprod(a.sink.state, a.npol);
+  if (EPI == EPI_FOLD && a.smem_bins) {
+    const unsigned nb = a.CB * a.sink.nbin * nprod;
+    for (unsigned i = threadIdx.x; i < nb; i += blockDim.x) bins[i] = 0.f;
+  }
+
+  const float2* src = a.Z + uint64_t(blk) * a.Nc + uint64_t(csub) * F;
+  if (EPT) {
+    if (F >= 16) {
+      MapRows map{f * F, sh, 0};
+      auto load = [&](unsigned idx) -> float2 { return ld_nc_f2(src + idx); };
+      auto store = [&](unsigned idx, float2 v) { smem[map(idx)] = v; };
+      block_fft<(EPT ? EPT : 2), true>(F, j, T, map, smem, a.twF, F, load, store);
+    } else {
+      // F = 2, 4, 8: one thread per transform, no shared-memory exchange needed
+      MapRows map{f * F, 0, 0};
+      auto load = [&](unsigned idx) -> float2 { return ld_nc_f2(src + idx); };
+      auto store = [&](unsigned idx, float2 v) { smem[f * F + idx] = v; };
+      block_fft<(EPT ? EPT : 2), true>(F, j, T, map, smem, a.twF, F, load, store);
+    }
+  } else {
+    smem[f] = ld_nc_f2(src);   // freq_res == 1: no inverse transform (Filterbank.C:621-631)
+  }
+  __syncthreads();
+
+  const unsigned nkeep = a.nkeep, np0 = a.nfilt_pos;
+  if (EPI == EPI_VOLT) {
+    const unsigned total = NF * nkeep;
+    for (unsigned it = threadIdx.x; it < total; it += blockDim.x) {
+      const unsigned ff = it / nkeep, m = it % nkeep;
+      const unsigned c2 = ch0 + ff / a.npol_cta, p2 = blockIdx.z * a.npol_cta + ff % a.npol_cta;
+      float2* out = reinterpret_cast<float2*>(a.sink.volt + (uint64_t(c2) * a.npol + p2) * a.sink.volt_span +
+                                              part * a.sink.volt_step);
+      out[m] = smem[fmap(ff, np0 + m)];
+    }
+    return;
+  }
+
+  // detected epilogues need both polarisations in this CTA (npol_cta == npol)
+  const unsigned dndim = a.sink.dndim;
+  const unsigned dnpol = nprod / dndim;
+  if (EPI == EPI_DETECT) {
+    const unsigned total = a.CB * nkeep;
+    for (unsigned it = threadIdx.x; it < total; it += blockDim.x) {
+      const unsigned c = it / nkeep, m = it % nkeep;
+      float2 p = smem[fmap(c * a.npol, np0 + m)];
+      float2 q = a.npol > 1 ? smem[fmap(c * a.npol + 1, np0 + m)] : make_float2(0.f, 0.f);
+      float r[4];
+      detect_products(a.sink.state, p, q, r);
+      const uint64_t osamp = part * nkeep + m;
+      for (unsigned pr = 0; pr < nprod; pr++) {
+        float* out = a.sink.det + (uint64_t(ch0 + c) * dnpol + pr / dndim) * a.sink.det_span;
+        out[osamp * dndim + pr % dndim] = r[pr];
+      }
+    }
+    return;
+  }
+
+  // EPI_FOLD: every thread walks L consecutive samples, summing while the bin is unchanged
+  // (same order as the reference's per-bin sequential +=, Fold.C:844-852), then adds the run
+  // to the CTA's shared bins (or straight to the global profile when they do not fit).
+  {
+    const unsigned L = 8;
+    const unsigned nchunk = (nkeep + L - 1) / L;
+    const unsigned total = a.CB * nchunk;
+    const unsigned nbin = a.sink.nbin;
+    const unsigned* plan = a.sink.bins + partl * uint64_t(nkeep);
+    for (unsigned it = threadIdx.x; it < total; it += blockDim.x) {
+      const unsigned c = it / nchunk, m0 = (it % nchunk) * L;
+      const unsigned m1 = min(nkeep, m0 + L);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      unsigned cur = 0xffffffffu;
+      float* dstbase = a.smem_bins ? bins + uint64_t(c) * nbin * nprod
+                                   : a.sink.profile + uint64_t(ch0 + c) * nbin * nprod;
+      auto flush = [&]() {
+        if (cur == 0xffffffffu) return;
+        for (unsigned pr = 0; pr < nprod; pr++) {
+          // profile layout [npol'][nbin][ndim']
+          float* d = dstbase + (uint64_t(pr / dndim) * nbin + cur) * dndim + pr % dndim;
+          atomicAdd(d, acc[pr]);
+        }
+      };
+      for (unsigned m = m0; m < m1; m++) {
+        const unsigned bin = __ldg(plan + m);
+        float2 p = smem[fmap(c * a.npol, np0 + m)];
+        float2 q = a.npol > 1 ? smem[fmap(c * a.npol + 1, np0 + m)] : make_float2(0.f, 0.f);
+        float r[4] = {0.f, 0.f, 0.f, 0.f};
+        detect_products(a.sink.state, p, q, r);
+        if (bin != cur) {
+          flush();
+          cur = bin;
+          for (int pr = 0; pr < 4; pr++) acc[pr] = r[pr];
+        } else {
+          for (int pr = 0; pr < 4; pr++) acc[pr] += r[pr];
+        }
+      }
+      flush();
+    }
+    if (a.smem_bins) {
+      __syncthreads();
+      const unsigned nb = a.CB * nbin * nprod;
+      float* prof = a.sink.profile + uint64_t(ch0) * nbin * nprod;
+      for (unsigned i = threadIdx.x; i < nb; i += blockDim.x) {
+        float v = bins[i];
+        if (v != 0.f) atomicAdd(prof + i, v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3' (convolution path): inverse column pass + discard + epilogue
+// ------------------------------------------------------------------------------------------
+struct ColsInvArgs {
+  const float2* A;          // B[k1][m2] after K2<CONV>
+  const float2* twP;
+  unsigned P, Q, lb, npol, nchan_in, Nc;
+  unsigned nfilt_pos, nkeep;
+  uint64_t part0;
+  FbSink sink;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(1024, 1) k_cols_inv(ColsInvArgs a) {
+  extern __shared__ float2 smem[];
+  const unsigned B = 1u << a.lb;
+  const unsigned T = a.P >> 4;
+  const unsigned per_pol = T * B;
+  const unsigned pol = threadIdx.x / per_pol;
+  const unsigned t = threadIdx.x % per_pol;
+  const unsigned b = t & (B - 1);
+  const unsigned j = t >> a.lb;
+  const unsigned m2 = blockIdx.x * B + b;
+  const unsigned partl = blockIdx.y / a.nchan_in;
+  const unsigned ic = blockIdx.y % a.nchan_in;
+  const uint64_t part = a.part0 + partl;
+  const unsigned blk = (partl * a.nchan_in + ic) * a.npol + pol;
+  float2* spol = smem + uint64_t(pol) * a.P * B;
+  MapCols map{b, a.lb, 4};
+  const float2* src = a.A + uint64_t(blk) * a.Nc + m2;
+  auto load = [&](unsigned k1) -> float2 { return ld_nc_f2(src + uint64_t(k1) * a.Q); };
+  const unsigned np0 = a.nfilt_pos, nkeep = a.nkeep;
+
+  if (EPI == EPI_VOLT) {
+    float2* out = reinterpret_cast<float2*>(a.sink.volt + (uint64_t(ic) * a.npol + pol) * a.sink.volt_span +
+                                            part * a.sink.volt_step);
+    auto store = [&](unsigned m1, float2 v) {
+      const unsigned m = m1 * a.Q + m2;
+      if (m >= np0 && m < np0 + nkeep) out[m - np0] = v;
+    };
+    block_fft<16, true>(a.P, j, T, map, spol, a.twP, a.P, load, store);
+    return;
+  }
+
+  const unsigned nprod = state_nprod(a.sink.state, a.npol);
+  const unsigned dndim = a.sink.dndim, dnpol = nprod / dndim;
+  const unsigned nbin = a.sink.nbin;
+  float* bins = reinterpret_cast<float*>(smem + uint64_t(a.npol) * a.P * B);
+  if (EPI == EPI_FOLD)
+    for (unsigned i = threadIdx.x; i < nbin * nprod; i += blockDim.x) bins[i] = 0.f;
+
+  {
+    auto store = [&](unsigned m1, float2 v) { spol[map(m1)] = v; };
+    block_fft<16, true>(a.P, j, T, map, spol, a.twP, a.P, load, store);
+  }
+  __syncthreads();
+
+  // items (m1, b): lanes span b, so a group of B lanes holds B consecutive time samples
+  const unsigned total = a.P * B;
+  const unsigned* plan = (EPI == EPI_FOLD) ? a.sink.bins + partl * uint64_t(nkeep) : nullptr;
+  for (unsigned it0 = 0; it0 < total; it0 += blockDim.x) {
+    const unsigned it = it0 + threadIdx.x;
+    const bool in_range = it < total;
+    const unsigned m1 = in_range ? it >> a.lb : 0, bb = it & (B - 1);
+    const unsigned m = m1 * a.Q + blockIdx.x * B + bb;
+    const bool valid = in_range && m >= np0 && m < np0 + nkeep;
+    float r[4] = {0.f, 0.f, 0.f, 0.f};
+    if (valid) {
+      MapCols mp{bb, a.lb, 4};
+      float2 p = smem[mp(m1)];
+      float2 q = a.npol > 1 ? smem[uint64_t(a.P) * B + mp(m1)] : make_float2(0.f, 0.f);
+      detect_products(a.sink.state, p, q, r);
+    }
+    if (EPI == EPI_DETECT) {
+      if (valid) {
+        const uint64_t osamp = part * nkeep + (m - np0);
+        for (unsigned pr = 0; pr < nprod; pr++) {
+          float* out = a.sink.det + (uint64_t(ic) * dnpol + pr / dndim) * a.sink.det_span;
+          out[osamp * dndim + pr % dndim] = r[pr];
+        }
+      }
+    } else {
+      if (valid) {
+        const unsigned bin = __ldg(plan + (m - np0));
+        for (unsigned pr = 0; pr < nprod; pr++)
+          atomicAdd(bins + (uint64_t(pr / dndim) * nbin + bin) * dndim + pr % dndim, r[pr]);
+      }
+    }
+  }
+  if (EPI == EPI_FOLD) {
+    __syncthreads();
+    float* prof = a.sink.profile + uint64_t(ic) * nbin * nprod;
+    for (unsigned i = threadIdx.x; i < nbin * nprod; i += blockDim.x) {
+      float v = bins[i];
+      if (v != 0.f) atomicAdd(prof + i, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+  B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return B200_OK;
+}
+
+static const size_t SMEM_TILE = 128 * 1024;   // FFT tile budget per CTA (elements * 8 B)
+
+int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t npart) {
+  Context* ctx = pl->ctx;
+  cudaStream_t st = ctx->stream;
+  const unsigned npol = pl->desc.npol, nchan_in = pl->desc.input_nchan;
+  const unsigned nblk1 = nchan_in * npol;
+  const unsigned B = 1u << pl->lbB;
+  const unsigned nprod = sink.kind == EPI_VOLT ? 0 : state_nprod(sink.state, npol);
+
+  if (sink.kind != EPI_VOLT) {
+    B200_REQUIRE(sink.state >= 0 && sink.state <= 3, "invalid detection state %d", sink.state);
+    if (sink.state >= B200_COHERENCE) {
+      B200_REQUIRE(npol == 2, "Coherence/Stokes detection requires npol == 2 (Detection.C:476-489)");
+      B200_REQUIRE(sink.dndim == 1 || sink.dndim == 2 || sink.dndim == 4, "invalid detection ndim %u", sink.dndim);
+    } else {
+      B200_REQUIRE(sink.dndim == 1, "Intensity/PPQQ detection has ndim 1");
+    }
+  }
+
+  for (uint64_t part0 = 0; part0 < npart; part0 += pl->batch) {
+    const unsigned nb = (unsigned)std::min<uint64_t>(pl->batch, npart - part0);
+    // ---- K1 ----
+    {
+      ColsArgs a;
+      a.src = src.ptr; a.span = src.span; a.step = src.step; a.lut = src.d_lut;
+      a.dst = pl->scratchA; a.twP = pl->twP.tw; a.blo = pl->bigN.lo; a.bhi = pl->bigN.hi;
+      a.P = pl->P; a.Q = pl->Q; a.lb = pl->lbB; a.npol = npol; a.nchan_in = nchan_in; a.Nc = pl->Nc;
+      a.part0 = part0;
+      dim3 grid(pl->Q / B, nb * nblk1);
+      dim3 block((pl->P / 16) * B);
+      size_t smem = size_t(pl->P) * B * sizeof(float2);
+      if (src.kind == SRC_F32) k_cols_fwd<SRC_F32><<<grid, block, smem, st>>>(a);
+      else k_cols_fwd<SRC_CASPSR8><<<grid, block, smem, st>>>(a);
+      ctx->launches++;
+    }
+    // ---- K2 ----
+    {
+      RowsArgs a;
+      a.A = pl->scratchA; a.Z = pl->scratchZ; a.H = pl->d_response; a.twQ = pl->twQ.tw;
+      a.blo = pl->bigN.lo; a.bhi = pl->bigN.hi; a.b2lo = pl->big2N.lo; a.b2hi = pl->big2N.hi;
+      a.P = pl->P; a.Q = pl->Q; a.G = pl->G; a.Nc = pl->Nc; a.npol = npol; a.nchan_in = nchan_in;
+      const bool split = pl->desc.input_real;
+      const unsigned nslots = split ? 2 * pl->G : pl->G;
+      const unsigned T = pl->Q >= 16 ? pl->Q / 16 : 1;
+      dim3 grid(split ? (pl->P / 2) / pl->G : pl->P / pl->G, nb * nblk1);
+      dim3 block(nslots * T);
+      size_t smem = size_t(nslots) * pl->Q * sizeof(float2);
+      if (pl->Q >= 16) {
+        if (split) {
+          if (pl->conv_path) k_rows<true, true, 16><<<grid, block, smem, st>>>(a);
+          else k_rows<true, false, 16><<<grid, block, smem, st>>>(a);
+        } else {
+          if (pl->conv_path) k_rows<false, true, 16><<<grid, block, smem, st>>>(a);
+          else k_rows<false, false, 16><<<grid, block, smem, st>>>(a);
+        }
+      } else {
+        if (split) k_rows<true, false, 0><<<grid, block, smem, st>>>(a);
+        else k_rows<false, false, 0><<<grid, block, smem, st>>>(a);
+      }
+      ctx->launches++;
+    }
+    // ---- K3 ----
+    FbSink sk = sink;
+    if (sk.kind == EPI_FOLD) sk.bins = sink.bins + part0 * pl->nkeep;
+    if (pl->conv_path) {
+      ColsInvArgs a;
+      a.A = pl->scratchA; a.twP = pl->twP.tw;
+      a.P = pl->P; a.Q = pl->Q; a.npol = npol; a.nchan_in = nchan_in; a.Nc = pl->Nc;
+      a.nfilt_pos = pl->desc.nfilt_pos; a.nkeep = pl->nkeep; a.part0 = part0; a.sink = sk;
+      // both polarisations share the CTA: halve the column tile if needed
+      unsigned lb = pl->lbB;
+      while (lb > 0 && size_t(npol) * pl->P * (1u << lb) * sizeof(float2) > SMEM_TILE) lb--;
+      while (lb > 0 && npol * (pl->P / 16) * (1u << lb) > 1024) lb--;
+      a.lb = lb;
+      const unsigned Bi = 1u << lb;
+      dim3 grid(pl->Q / Bi, nb * nchan_in);
+      dim3 block(npol * (pl->P / 16) * Bi);
+      size_t smem = size_t(npol) * pl->P * Bi * sizeof(float2) + (sk.kind == EPI_FOLD ? size_t(sk.nbin) * nprod * 4 : 0);
+      if (sk.kind == EPI_VOLT) k_cols_inv<EPI_VOLT><<<grid, block, smem, st>>>(a);
+      else if (sk.kind == EPI_DETECT) k_cols_inv<EPI_DETECT><<<grid, block, smem, st>>>(a);
+      else k_cols_inv<EPI_FOLD><<<grid, block, smem, st>>>(a);
+      ctx->launches++;
+    } else {
+      ChanArgs a;
+      a.Z = pl->scratchZ; a.twF = pl->twF.tw;
+      a.F = pl->F; a.C = pl->C; a.Nc = pl->Nc; a.npol = npol; a.nchan_in = nchan_in;
+      a.nfilt_pos = pl->desc.nfilt_pos; a.nkeep = pl->nkeep; a.part0 = part0; a.sink = sk;
+      const unsigned F = pl->F;
+      const unsigned ept = F >= 16 ? 16 : F;       // 16, 8, 4, 2, 1
+      const unsigned T = F >= 16 ? F / 16 : 1;
+      // transforms per CTA: both polarisations of CB channels
+      unsigned npol_cta = npol;
+      if (size_t(npol) * F * sizeof(float2) > SMEM_TILE || npol * T > 1024) {
+        B200_REQUIRE(sk.kind == EPI_VOLT,
+                     "freq_res=%u: detection/fold fused epilogues need both polarisations on one SM "
+                     "(freq_res <= 8192); use the voltage output + b200_detect/b200_fold", F);
+        npol_cta = 1;
+      }
+      unsigned CB = 1;
+      while (CB * 2 <= pl->C && size_t(CB) * 2 * npol_cta * F * sizeof(float2) <= SMEM_TILE / 2 &&
+             CB * 2 * npol_cta * T <= 512)
+        CB *= 2;
+      a.CB = CB; a.npol_cta = npol_cta;
+      size_t smem = size_t(CB) * npol_cta * F * sizeof(float2);
+      a.smem_bins = 0;
+      if (sk.kind == EPI_FOLD) {
+        size_t bins_bytes = size_t(CB) * sk.nbin * nprod * sizeof(float);
+        if (smem + bins_bytes <= size_t(ctx->max_smem_optin) - 1024 && bins_bytes <= 64 * 1024) {
+          a.smem_bins = 1;
+          smem += bins_bytes;
+        }
+      }
+      dim3 grid(pl->nchan_out / CB, nb, npol / npol_cta);
+      dim3 block(CB * npol_cta * T);
+#define B200_K3(E)                                                                          \
+  if (sk.kind == EPI_VOLT) k_chan_inv<E, EPI_VOLT><<<grid, block, smem, st>>>(a);            \
+  else if (sk.kind == EPI_DETECT) k_chan_inv<E, EPI_DETECT><<<grid, block, smem, st>>>(a);   \
+  else k_chan_inv<E, EPI_FOLD><<<grid, block, smem, st>>>(a);
+      switch (ept) {
+        case 16: B200_K3(16) break;
+        case 8: B200_K3(8) break;
+        case 4: B200_K3(4) break;
+        case 2: B200_K3(2) break;
+        default: B200_K3(0) break;
+      }
+#undef B200_K3
+      ctx->launches++;
+    }
+    B200_CUDA(cudaGetLastError());
+  }
+  return B200_OK;
+}
+
+static int plan_set_attributes(size_t maxs) {
+  int rc;
+#define SET(k) if ((rc = set_smem(k, maxs)) != B200_OK) return rc;
+  SET(k_cols_fwd<SRC_F32>) SET(k_cols_fwd<SRC_CASPSR8>)
+  SET((k_rows<true, true, 16>)) SET((k_rows<true, false, 16>)) SET((k_rows<false, true, 16>))
+  SET((k_rows<false, false, 16>)) SET((k_rows<true, false, 0>)) SET((k_rows<false, false, 0>))
+  SET(k_cols_inv<EPI_VOLT>) SET(k_cols_inv<EPI_DETECT>) SET(k_cols_inv<EPI_FOLD>)
+  SET((k_chan_inv<16, EPI_VOLT>)) SET((k_chan_inv<16, EPI_DETECT>)) SET((k_chan_inv<16, EPI_FOLD>))
+  SET((k_chan_inv<8, EPI_VOLT>)) SET((k_chan_inv<8, EPI_DETECT>)) SET((k_chan_inv<8, EPI_FOLD>))
+  SET((k_chan_inv<4, EPI_VOLT>)) SET((k_chan_inv<4, EPI_DETECT>)) SET((k_chan_inv<4, EPI_FOLD>))
+  SET((k_chan_inv<2, EPI_VOLT>)) SET((k_chan_inv<2, EPI_DETECT>)) SET((k_chan_inv<2, EPI_FOLD>))
+  SET((k_chan_inv<0, EPI_VOLT>)) SET((k_chan_inv<0, EPI_DETECT>)) SET((k_chan_inv<0, EPI_FOLD>))
+#undef SET
+  return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_fb_plan_create(b200_context* cctx, const b200_fb_desc* d, b200_fb_plan** out) {
+  B200_REQUIRE(cctx && d && out, "b200_fb_plan_create: null argument");
+  Context* ctx = reinterpret_cast<Context*>(cctx);
+  B200_REQUIRE(d->npol == 1 || d->npol == 2, "npol=%u unsupported (1 or 2)", d->npol);
+  B200_REQUIRE(d->input_nchan >= 1 && d->nchan_subband >= 1 && d->freq_res >= 1, "invalid channelisation");
+  B200_REQUIRE(is_pow2(d->nchan_subband) && is_pow2(d->freq_res),
+               "nchan_subband=%u and freq_res=%u must be powers of two", d->nchan_subband, d->freq_res);
+  const uint64_t Nc64 = uint64_t(d->nchan_subband) * d->freq_res;
+  B200_REQUIRE(Nc64 >= 16 && Nc64 <= (1ull << 22), "forward transform of %llu complex points unsupported (16..2^22)",
+               (unsigned long long)Nc64);
+  B200_REQUIRE(d->nfilt_pos + d->nfilt_neg < d->freq_res || (d->freq_res == 1 && d->nfilt_pos + d->nfilt_neg == 0),
+               "nfilt_pos+nfilt_neg=%u must be smaller than freq_res=%u", d->nfilt_pos + d->nfilt_neg, d->freq_res);
+  B200_CUDA(cudaSetDevice(ctx->device));
+
+  b200_fb_plan* pl = new b200_fb_plan();
+  memset(pl, 0, sizeof(*pl));
+  pl->ctx = ctx;
+  pl->desc = *d;
+  pl->desc.h_response = nullptr;
+  pl->C = d->nchan_subband;
+  pl->F = d->freq_res;
+  pl->Nc = (unsigned)Nc64;
+  const unsigned nfilt_tot = d->nfilt_pos + d->nfilt_neg;
+  if (d->input_real) {                       // Filterbank.C:139-148
+    pl->nsamp_fft = 2 * pl->Nc;
+    pl->nsamp_overlap = 2 * nfilt_tot * pl->C;
+  } else {
+    pl->nsamp_fft = pl->Nc;
+    pl->nsamp_overlap = nfilt_tot * pl->C;
+  }
+  pl->nsamp_step = pl->nsamp_fft - pl->nsamp_overlap;   // :155
+  pl->nkeep = pl->F - nfilt_tot;                        // :409
+  pl->nchan_out = d->input_nchan * pl->C;
+
+  // ---- factorisation of the forward transform ----
+  pl->conv_path = (pl->C == 1 && pl->F > 8192);
+  if (pl->F > 16384 && !pl->conv_path) {
+    set_error("freq_res=%u with nchan_subband=%u: per-channel inverse transforms above 16384 points are not built yet",
+              pl->F, pl->C);
+    delete pl;
+    return B200_ERR_UNSUPPORTED;
+  }
+  const unsigned lgN = ilog2(pl->Nc);
+  if (pl->Nc <= 8192 && !pl->conv_path) {
+    pl->P = pl->Nc;
+    pl->Q = 1;
+  } else {
+    unsigned lgP = (lgN + 1) / 2;
+    if (lgP > 11) lgP = 11;
+    pl->P = 1u << lgP;
+    pl->Q = pl->Nc / pl->P;
+  }
+  // column tile: B columns, P*B elements <= 16384, (P/16)*B threads <= 1024
+  {
+    unsigned lb = 0;
+    while ((2u << lb) <= pl->Q && size_t(pl->P) * (2u << lb) * sizeof(float2) <= SMEM_TILE &&
+           (pl->P / 16) * (2u << lb) <= 1024 && (2u << lb) <= 16)
+      lb++;
+    pl->lbB = lb;
+  }
+  // row tile: G (+G mirror) rows of Q points
+  {
+    const unsigned mult = d->input_real ? 2 : 1;
+    const unsigned T = pl->Q >= 16 ? pl->Q / 16 : 1;
+    const unsigned rows_avail = d->input_real ? pl->P / 2 : pl->P;
+    unsigned G = 1;
+    while (G * 2 <= rows_avail && size_t(G) * 2 * mult * pl->Q * sizeof(float2) <= SMEM_TILE &&
+           G * 2 * mult * T <= 1024 && G * 2 <= 8)
+      G *= 2;
+    pl->G = G;
+  }
+  pl->batch = d->max_npart ? d->max_npart : 4;
+
+  int rc = plan_set_attributes(size_t(ctx->max_smem_optin));
+  if (rc == B200_OK) rc = make_twiddle(pl->twP, pl->P, ctx->stream);
+  if (rc == B200_OK) rc = make_twiddle(pl->twQ, pl->Q, ctx->stream);
+  if (rc == B200_OK) rc = make_twiddle(pl->twF, pl->F, ctx->stream);
+  if (rc == B200_OK) rc = make_big_twiddle(pl->bigN, pl->Nc, ctx->stream);
+  if (rc == B200_OK) rc = make_big_twiddle(pl->big2N, 2ull * pl->Nc, ctx->stream);
+  if (rc != B200_OK) { b200_fb_plan_destroy(pl); return rc; }
+
+  const uint64_t nblk = uint64_t(pl->batch) * d->input_nchan * d->npol;
+  const uint64_t sbytes = nblk * pl->Nc * sizeof(float2);
+  cudaError_t e = cudaMalloc(&pl->scratchA, sbytes);
+  if (e == cudaSuccess && !pl->conv_path) e = cudaMalloc(&pl->scratchZ, sbytes);
+  if (e == cudaSuccess && d->h_response) {
+    const uint64_t rbytes = uint64_t(d->input_nchan) * pl->Nc * sizeof(float2);
+    e = cudaMalloc(&pl->d_response, rbytes);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pl->d_response, d->h_response, rbytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  if (e != cudaSuccess) {
+    b200_fb_plan_destroy(pl);
+    return cuda_fail(e, "plan allocation", __FILE__, __LINE__);
+  }
+  pl->scratch_bytes = sbytes * (pl->conv_path ? 1 : 2);
+  *out = pl;
+  return B200_OK;
+}
+
+int b200_fb_plan_info(const b200_fb_plan* pl, b200_fb_info* info) {
+  B200_REQUIRE(pl && info, "b200_fb_plan_info: null argument");
+  info->n_fft = pl->Nc;
+  info->nsamp_fft = pl->nsamp_fft;
+  info->nsamp_overlap = pl->nsamp_overlap;
+  info->nsamp_step = pl->nsamp_step;
+  info->nkeep = pl->nkeep;
+  info->fft_rows = pl->P;
+  info->fft_cols = pl->Q;
+  info->batch_npart = pl->batch;
+  info->scratch_bytes = pl->scratch_bytes;
+  return B200_OK;
+}
+
+int b200_fb_plan_destroy(b200_fb_plan* pl) {
+  if (!pl) return B200_OK;
+  free_twiddle(pl->twP);
+  free_twiddle(pl->twQ);
+  free_twiddle(pl->twF);
+  free_big_twiddle(pl->bigN);
+  free_big_twiddle(pl->big2N);
+  if (pl->d_response) cudaFree(pl->d_response);
+  if (pl->scratchA) cudaFree(pl->scratchA);
+  if (pl->scratchZ) cudaFree(pl->scratchZ);
+  delete pl;
+  return B200_OK;
+}
+
+int b200_fb_perform(b200_fb_plan* pl, const float* d_in, uint64_t in_span, float* d_out, uint64_t out_span,
+                    uint64_t npart, uint64_t in_step, uint64_t out_step) {
+  B200_REQUIRE(pl && d_in && d_out, "b200_fb_perform: null argument");
+  if (npart == 0) return B200_OK;
+  const unsigned ndim = pl->desc.input_real ? 1 : 2;
+  B200_REQUIRE(in_step == uint64_t(pl->nsamp_step) * ndim, "in_step=%llu != nsamp_step*ndim=%llu (Filterbank.C:517)",
+               (unsigned long long)in_step, (unsigned long long)(uint64_t(pl->nsamp_step) * ndim));
+  B200_REQUIRE(out_step == uint64_t(pl->nkeep) * 2, "out_step=%llu != nkeep*2=%llu (Filterbank.C:523)",
+               (unsigned long long)out_step, (unsigned long long)(uint64_t(pl->nkeep) * 2));
+  B200_REQUIRE(in_span % 2 == 0 && out_span % 2 == 0 && (reinterpret_cast<uintptr_t>(d_in) & 7) == 0 &&
+                   (reinterpret_cast<uintptr_t>(d_out) & 7) == 0,
+               "time series planes must be 8-byte aligned with even spans");
+  B200_REQUIRE(in_step % 2 == 0, "nsamp_step must be even for real input");
+  FbSource src;
+  src.kind = SRC_F32; src.ptr = d_in; src.span = in_span; src.step = in_step; src.d_lut = nullptr;
+  FbSink sink;
+  memset(&sink, 0, sizeof(sink));
+  sink.kind = EPI_VOLT; sink.volt = d_out; sink.volt_span = out_span; sink.volt_step = out_step;
+  return fb_run(pl, src, sink, npart);
+}
+
+}  // extern "C"

@@ -1,0 +1,503 @@
+// fold.cu -- stand-alone unpack, detection and fold engines + the bin-plan expansion kernel.
+//
+//   b200_unpack   <- Unpacker device hook (CASPSR / generic 8-bit / MeerKAT / UWB)
+//   b200_detect   <- dsp::Detection::Engine (Signal/General/dsp/Detection.h:98-106)
+//   b200_fold_*   <- dsp::Fold::Engine      (Signal/Pulsar/dsp/Fold.h:249-312)
+#include <cstring>
+#include <vector>
+
+#include "engine.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------
+// unpack kernels: one thread per output (chan,pol) sample group; writes are coalesced along
+// time, reads gather through the read-only path.
+// ------------------------------------------------------------------------------------------
+struct UnpackArgs {
+  const unsigned char* raw;
+  float* out;
+  uint64_t span, ndat;
+  unsigned nchan, npol, ndim;
+  float scale;
+  unsigned sample_swap;
+};
+
+// CASPSR: 4 samples of pol0 then 4 samples of pol1 (CASPSRUnpacker.C:141-187); LUT in smem.
+__global__ void k_unpack_caspsr(UnpackArgs a, const float* __restrict__ lut) {
+  __shared__ float s_lut[256];
+  for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = lut[i];
+  __syncthreads();
+  // each thread converts one 8-byte group: 4 floats to each polarisation plane
+  const uint64_t ngroup = a.ndat / 4;
+  for (uint64_t g = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; g < ngroup; g += uint64_t(gridDim.x) * blockDim.x) {
+    uint2 w = __ldg(reinterpret_cast<const uint2*>(a.raw) + g);
+    float4 p0 = make_float4(s_lut[w.x & 255u], s_lut[(w.x >> 8) & 255u], s_lut[(w.x >> 16) & 255u], s_lut[w.x >> 24]);
+    float4 p1 = make_float4(s_lut[w.y & 255u], s_lut[(w.y >> 8) & 255u], s_lut[(w.y >> 16) & 255u], s_lut[w.y >> 24]);
+    reinterpret_cast<float4*>(a.out)[g] = p0;
+    reinterpret_cast<float4*>(a.out + a.span)[g] = p1;
+  }
+}
+
+// generic TFP 8-bit (BitUnpacker.C:56-75): byte idat*(nchan*npol*ndim) + ndim*(npol*ichan+ipol)+idim
+__global__ void k_unpack_generic8(UnpackArgs a, const float* __restrict__ lut) {
+  __shared__ float s_lut[256];
+  for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = lut[i];
+  __syncthreads();
+  const unsigned nplane = a.nchan * a.npol;
+  const unsigned nskip = nplane * a.ndim;
+  const uint64_t total = a.ndat * nskip;
+  // consecutive threads read consecutive bytes (coalesced); the scattered 4-byte writes land in
+  // nskip different planes and are merged by L2.
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < total; i += uint64_t(gridDim.x) * blockDim.x) {
+    const uint64_t idat = i / nskip;
+    const unsigned off = unsigned(i % nskip);
+    const unsigned plane = off / a.ndim, idim = off % a.ndim;
+    a.out[uint64_t(plane) * a.span + idat * a.ndim + idim] = s_lut[__ldg(a.raw + i)];
+  }
+}
+
+// MeerKAT (MeerKATUnpacker.C:196-229): heaps of 256 samples, [heap][pol][chan][256 x (re,im) int8]
+__global__ void k_unpack_meerkat(UnpackArgs a) {
+  const uint64_t total = a.ndat * a.nchan * a.npol;   // complex samples
+  const char2* from = reinterpret_cast<const char2*>(a.raw);
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < total; i += uint64_t(gridDim.x) * blockDim.x) {
+    const unsigned isamp = unsigned(i & 255u);
+    uint64_t r = i >> 8;
+    const unsigned ichan = unsigned(r % a.nchan); r /= a.nchan;
+    const unsigned ipol = unsigned(r % a.npol);
+    const uint64_t iheap = r / a.npol;
+    // sample_swap == 2 (MKBFRo) exchanges odd and even samples (MeerKATUnpacker.C:211-222)
+    const unsigned osamp = (a.sample_swap == 2) ? (isamp ^ 1u) : isamp;
+    char2 v = from[i];
+    float2 o;
+    o.x = __fmul_rn(float(v.x) + 0.5f, a.scale);
+    o.y = __fmul_rn(float(v.y) + 0.5f, a.scale);
+    float2* into = reinterpret_cast<float2*>(a.out + (uint64_t(ichan) * a.npol + ipol) * a.span) + iheap * 256 + osamp;
+    *into = o;
+  }
+}
+
+// UWB (UWBUnpacker.C:177-218): blocks of 2048 complex int16 samples per pol, offset binary
+__global__ void k_unpack_uwb(UnpackArgs a) {
+  const uint64_t total = a.ndat * a.npol;   // complex samples
+  const short2* from = reinterpret_cast<const short2*>(a.raw);
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < total; i += uint64_t(gridDim.x) * blockDim.x) {
+    const unsigned isamp = unsigned(i & 2047u);
+    uint64_t r = i >> 11;
+    const unsigned ipol = unsigned(r % a.npol);
+    const uint64_t iblock = r / a.npol;
+    short2 v = from[i];
+    float2 o;
+    o.x = float(short(v.x ^ short(0x8000)));
+    o.y = float(short(v.y ^ short(0x8000)));
+    reinterpret_cast<float2*>(a.out + uint64_t(ipol) * a.span)[iblock * 2048 + isamp] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// stand-alone detection (Detection.C:218-320,322-421)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void detect4(int state, float2 p, float2 q, float* r) {
+  float pp = __fadd_rn(__fmul_rn(p.x, p.x), __fmul_rn(p.y, p.y));
+  float qq = __fadd_rn(__fmul_rn(q.x, q.x), __fmul_rn(q.y, q.y));
+  float re = __fadd_rn(__fmul_rn(p.x, q.x), __fmul_rn(p.y, q.y));
+  float im = __fsub_rn(__fmul_rn(p.x, q.y), __fmul_rn(p.y, q.x));
+  if (state == B200_INTENSITY) { r[0] = __fadd_rn(pp, qq); }
+  else if (state == B200_PPQQ) { r[0] = pp; r[1] = qq; }
+  else if (state == B200_COHERENCE) { r[0] = pp; r[1] = qq; r[2] = re; r[3] = im; }
+  else { r[0] = __fadd_rn(pp, qq); r[1] = __fsub_rn(pp, qq); r[2] = __fmul_rn(2.f, re); r[3] = __fmul_rn(2.f, im); }
+}
+
+struct DetectArgs {
+  const float* in;
+  float* out;
+  uint64_t in_span, out_span, ndat;
+  unsigned nchan, npol, ndim_out, nprod;
+  int state;
+};
+
+__global__ void k_detect(DetectArgs a) {
+  const unsigned ichan = blockIdx.y;
+  const float2* p = reinterpret_cast<const float2*>(a.in + uint64_t(ichan) * a.npol * a.in_span);
+  const float2* q = a.npol > 1 ? reinterpret_cast<const float2*>(a.in + (uint64_t(ichan) * a.npol + 1) * a.in_span) : p;
+  const unsigned dnpol = a.nprod / a.ndim_out;
+  float* obase = a.out + uint64_t(ichan) * dnpol * a.out_span;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < a.ndat; i += uint64_t(gridDim.x) * blockDim.x) {
+    float2 pv = p[i];
+    float2 qv = a.npol > 1 ? q[i] : make_float2(0.f, 0.f);
+    float r[4];
+    detect4(a.state, pv, qv, r);
+    // both reads happen before any write of this sample: safe in place for ndim_out == 2
+    if (a.ndim_out == 4) {
+      reinterpret_cast<float4*>(obase)[i] = make_float4(r[0], r[1], r[2], r[3]);
+    } else if (a.ndim_out == 2) {
+      reinterpret_cast<float2*>(obase)[i] = make_float2(r[0], r[1]);
+      reinterpret_cast<float2*>(obase + a.out_span)[i] = make_float2(r[2], r[3]);
+    } else {
+      for (unsigned pr = 0; pr < a.nprod; pr++) obase[uint64_t(pr) * a.out_span + i] = r[pr];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// bin-plan expansion: segments -> bin of every sample (+ hits).  Exact integer arithmetic.
+// ------------------------------------------------------------------------------------------
+__global__ void k_expand_bins(const b200_phase_segment* __restrict__ seg, unsigned nseg, uint64_t ndat, unsigned nbin,
+                              unsigned* __restrict__ bins, unsigned* __restrict__ hits_last,
+                              unsigned* __restrict__ hits_total) {
+  const double double_nbin = double(nbin);
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < ndat; i += uint64_t(gridDim.x) * blockDim.x) {
+    // binary search for the segment containing sample i
+    unsigned lo = 0, hi = nseg - 1;
+    while (lo < hi) {
+      unsigned mid = (lo + hi + 1) >> 1;
+      if (seg[mid].start <= i) lo = mid;
+      else hi = mid - 1;
+    }
+    const b200_phase_segment s = seg[lo];
+    const uint64_t a = s.a0 + (i - s.start) * s.step;            // < 2^53: exact in double
+    const double phi = ldexp(double(a), s.scale_exp);            // exact scaling
+    const double double_ibin = __dmul_rn(phi, double_nbin);      // Fold.C:766
+    const unsigned ibin = unsigned(double_ibin);                 // Fold.C:767 (truncation)
+    bins[i] = ibin;
+    atomicAdd(hits_last + ibin, 1u);
+    atomicAdd(hits_total + ibin, 1u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// stand-alone fold (Fold.C:835-873): one CTA per (chan, pol, time slab); per-thread runs of
+// consecutive samples summed sequentially, then added to shared bins, then to the profile.
+// ------------------------------------------------------------------------------------------
+struct FoldArgs {
+  const float* in;
+  uint64_t in_span, idat_start, ndat;
+  const unsigned* bins;
+  float* profile;
+  unsigned nchan, npol, ndim, nbin, slab;
+  unsigned smem_bins;
+};
+
+template <int NDIM>
+__global__ void k_fold(FoldArgs a) {
+  extern __shared__ float sbins[];
+  const unsigned plane = blockIdx.y;               // ichan*npol + ipol
+  const uint64_t s0 = uint64_t(blockIdx.x) * a.slab;
+  const uint64_t s1 = min(a.ndat, s0 + a.slab);
+  const float* tp = a.in + uint64_t(plane) * a.in_span + a.idat_start * NDIM;
+  float* prof = a.profile + uint64_t(plane) * a.nbin * NDIM;
+  if (a.smem_bins) {
+    for (unsigned i = threadIdx.x; i < a.nbin * NDIM; i += blockDim.x) sbins[i] = 0.f;
+    __syncthreads();
+  }
+  float* dst = a.smem_bins ? sbins : prof;
+  const unsigned L = 16;
+  for (uint64_t c0 = s0 + uint64_t(threadIdx.x) * L; c0 < s1; c0 += uint64_t(blockDim.x) * L) {
+    const uint64_t c1 = min(s1, c0 + L);
+    float acc[NDIM];
+    unsigned cur = 0xffffffffu;
+    for (uint64_t i = c0; i < c1; i++) {
+      const unsigned bin = __ldg(a.bins + i);
+      float v[NDIM];
+      if (NDIM == 4) {
+        float4 t = reinterpret_cast<const float4*>(tp)[i];
+        v[0] = t.x; v[1 % NDIM] = t.y; v[2 % NDIM] = t.z; v[3 % NDIM] = t.w;
+      } else if (NDIM == 2) {
+        float2 t = reinterpret_cast<const float2*>(tp)[i];
+        v[0] = t.x; v[1 % NDIM] = t.y;
+      } else {
+        v[0] = tp[i];
+      }
+      if (bin != cur) {
+        if (cur != 0xffffffffu)
+          for (int d = 0; d < NDIM; d++) atomicAdd(dst + uint64_t(cur) * NDIM + d, acc[d]);
+        cur = bin;
+        for (int d = 0; d < NDIM; d++) acc[d] = v[d];
+      } else {
+        for (int d = 0; d < NDIM; d++) acc[d] += v[d];
+      }
+    }
+    if (cur != 0xffffffffu)
+      for (int d = 0; d < NDIM; d++) atomicAdd(dst + uint64_t(cur) * NDIM + d, acc[d]);
+  }
+  if (a.smem_bins) {
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < a.nbin * NDIM; i += blockDim.x) {
+      float v = sbins[i];
+      if (v != 0.f) atomicAdd(prof + i, v);
+    }
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_fold {
+  Context* ctx;
+  unsigned nchan, npol, ndim, nbin;
+  float* d_profile;
+  unsigned* d_hits_total;
+  unsigned* d_hits_last;
+  unsigned* d_bins;
+  uint64_t bins_capacity;
+  b200_phase_segment* d_seg;
+  b200_phase_segment* h_seg;     // pinned
+  uint64_t seg_capacity;
+  uint64_t ndat, idat_start;     // of the last set_bins
+  uint64_t ndat_total;
+  cudaEvent_t seg_free;          // the pinned segment buffer may be rewritten after this event
+  bool seg_pending;
+};
+
+extern "C" {
+
+int b200_unpack(b200_context* cctx, const b200_unpack_desc* d, const void* d_raw, uint64_t ndat, float* d_out,
+                uint64_t out_span) {
+  B200_REQUIRE(cctx && d && d_raw && d_out, "b200_unpack: null argument");
+  Context* ctx = reinterpret_cast<Context*>(cctx);
+  if (ndat == 0) return B200_OK;
+  UnpackArgs a;
+  a.raw = static_cast<const unsigned char*>(d_raw);
+  a.out = d_out; a.span = out_span; a.ndat = ndat;
+  a.nchan = d->nchan; a.npol = d->npol; a.ndim = d->ndim;
+  a.scale = d->scale; a.sample_swap = d->sample_swap ? d->sample_swap : 1;
+  const unsigned threads = 256;
+  const unsigned maxgrid = ctx->sm_count * 16;
+  float* d_lut = nullptr;
+  if (d->format == B200_FMT_CASPSR8 || d->format == B200_FMT_GENERIC8) {
+    // the table travels with the call; 1 KiB async copy from a staging copy owned by the stream order
+    B200_CUDA(cudaMallocAsync(&d_lut, 256 * sizeof(float), ctx->stream));
+    B200_CUDA(cudaMemcpyAsync(d_lut, d->lut, 256 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  switch (d->format) {
+    case B200_FMT_CASPSR8: {
+      B200_REQUIRE(d->nchan == 1 && d->npol == 2 && d->ndim == 1, "CASPSR unpacker: nchan=1 npol=2 ndim=1 only");
+      B200_REQUIRE(ndat % 4 == 0 && out_span % 4 == 0, "CASPSR unpacker: ndat and span must be multiples of 4");
+      uint64_t ng = ndat / 4;
+      unsigned grid = (unsigned)std::min<uint64_t>((ng + threads - 1) / threads, maxgrid);
+      k_unpack_caspsr<<<grid, threads, 0, ctx->stream>>>(a, d_lut);
+      break;
+    }
+    case B200_FMT_GENERIC8: {
+      uint64_t total = ndat * d->nchan * d->npol * d->ndim;
+      unsigned grid = (unsigned)std::min<uint64_t>((total + threads - 1) / threads, maxgrid);
+      k_unpack_generic8<<<grid, threads, 0, ctx->stream>>>(a, d_lut);
+      break;
+    }
+    case B200_FMT_MEERKAT8: {
+      B200_REQUIRE(d->ndim == 2, "MeerKAT unpacker: ndim=2 only (MeerKATUnpacker.C:137-144)");
+      B200_REQUIRE(ndat % 256 == 0 && out_span % 2 == 0, "MeerKAT unpacker: ndat must be a multiple of the 256-sample heap");
+      uint64_t total = ndat * d->nchan * d->npol;
+      unsigned grid = (unsigned)std::min<uint64_t>((total + threads - 1) / threads, maxgrid);
+      k_unpack_meerkat<<<grid, threads, 0, ctx->stream>>>(a);
+      break;
+    }
+    case B200_FMT_UWB16: {
+      B200_REQUIRE(d->nchan == 1 && d->ndim == 2, "UWB unpacker: nchan=1 ndim=2 only (UWBUnpacker.C:140-147)");
+      B200_REQUIRE(ndat % 2048 == 0 && out_span % 2 == 0, "UWB unpacker: ndat must be a multiple of the 2048-sample block");
+      uint64_t total = ndat * d->npol;
+      unsigned grid = (unsigned)std::min<uint64_t>((total + threads - 1) / threads, maxgrid);
+      k_unpack_uwb<<<grid, threads, 0, ctx->stream>>>(a);
+      break;
+    }
+    default:
+      set_error("b200_unpack: unknown format %d", d->format);
+      return B200_ERR_INVALID;
+  }
+  ctx->launches++;
+  if (d_lut) B200_CUDA(cudaFreeAsync(d_lut, ctx->stream));
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_detect(b200_context* cctx, int state, unsigned ndim_out, const float* d_in, uint64_t in_span, unsigned nchan,
+                unsigned npol, uint64_t ndat, float* d_out, uint64_t out_span) {
+  B200_REQUIRE(cctx && d_in && d_out, "b200_detect: null argument");
+  Context* ctx = reinterpret_cast<Context*>(cctx);
+  B200_REQUIRE(state >= 0 && state <= 3, "b200_detect: invalid state %d", state);
+  if (state >= B200_COHERENCE) {
+    // Detection::checks (Detection.C:476-489)
+    B200_REQUIRE(npol == 2, "b200_detect: Coherence/Stokes need npol == 2, have %u", npol);
+    B200_REQUIRE(ndim_out == 1 || ndim_out == 2 || ndim_out == 4, "b200_detect: invalid ndim=%u", ndim_out);
+  } else {
+    B200_REQUIRE(npol == 1 || npol == 2, "b200_detect: npol=%u", npol);
+    ndim_out = 1;
+  }
+  B200_REQUIRE(!(d_in == d_out) || (state >= B200_COHERENCE && ndim_out == 2),
+               "b200_detect: in-place detection only for ndim == 2 (Detection.C:358-361)");
+  B200_REQUIRE(in_span % 2 == 0, "b200_detect: odd input span");
+  if (ndat == 0) return B200_OK;
+  DetectArgs a;
+  a.in = d_in; a.out = d_out; a.in_span = in_span; a.out_span = out_span; a.ndat = ndat;
+  a.nchan = nchan; a.npol = npol; a.ndim_out = ndim_out; a.state = state;
+  a.nprod = state == B200_INTENSITY ? 1 : state == B200_PPQQ ? npol : 4;
+  const unsigned threads = 256;
+  unsigned gx = (unsigned)std::min<uint64_t>((ndat + threads - 1) / threads, 4096);
+  k_detect<<<dim3(gx, nchan), threads, 0, ctx->stream>>>(a);
+  ctx->launches++;
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_fold_create(b200_context* cctx, unsigned nchan, unsigned npol, unsigned ndim, unsigned nbin, b200_fold** out) {
+  B200_REQUIRE(cctx && out, "b200_fold_create: null argument");
+  B200_REQUIRE(nchan && npol && nbin && (ndim == 1 || ndim == 2 || ndim == 4), "b200_fold_create: invalid shape");
+  Context* ctx = reinterpret_cast<Context*>(cctx);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  b200_fold* f = new b200_fold();
+  memset(f, 0, sizeof(*f));
+  f->ctx = ctx; f->nchan = nchan; f->npol = npol; f->ndim = ndim; f->nbin = nbin;
+  const uint64_t nfloat = uint64_t(nchan) * npol * ndim * nbin;
+  cudaError_t e = cudaMalloc(&f->d_profile, nfloat * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_hits_total, nbin * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_hits_last, nbin * sizeof(unsigned));
+  f->seg_capacity = 1 << 16;
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_seg, f->seg_capacity * sizeof(b200_phase_segment));
+  if (e == cudaSuccess) e = cudaMallocHost(&f->h_seg, f->seg_capacity * sizeof(b200_phase_segment));
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->seg_free, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaMemsetAsync(f->d_profile, 0, nfloat * sizeof(float), ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(f->d_hits_total, 0, nbin * sizeof(unsigned), ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(f->d_hits_last, 0, nbin * sizeof(unsigned), ctx->stream);
+  if (e != cudaSuccess) {
+    b200_fold_destroy(f);
+    return cuda_fail(e, "b200_fold_create", __FILE__, __LINE__);
+  }
+  *out = f;
+  return B200_OK;
+}
+
+int b200_fold_destroy(b200_fold* f) {
+  if (!f) return B200_OK;
+  if (f->d_profile) cudaFree(f->d_profile);
+  if (f->d_hits_total) cudaFree(f->d_hits_total);
+  if (f->d_hits_last) cudaFree(f->d_hits_last);
+  if (f->d_bins) cudaFree(f->d_bins);
+  if (f->d_seg) cudaFree(f->d_seg);
+  if (f->h_seg) cudaFreeHost(f->h_seg);
+  if (f->seg_free) cudaEventDestroy(f->seg_free);
+  delete f;
+  return B200_OK;
+}
+
+int b200_fold_set_bins(b200_fold* f, double phi, double pps, uint64_t ndat, uint64_t idat_start, uint64_t* ndat_folded) {
+  B200_REQUIRE(f, "b200_fold_set_bins: null fold");
+  Context* ctx = f->ctx;
+  f->ndat = ndat;
+  f->idat_start = idat_start;
+  if (ndat_folded) *ndat_folded = ndat;
+  if (ndat == 0) return B200_OK;
+  if (ndat > f->bins_capacity) {
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (f->d_bins) cudaFree(f->d_bins);
+    f->d_bins = nullptr;
+    f->bins_capacity = ndat + ndat / 4 + 1024;
+    B200_CUDA(cudaMalloc(&f->d_bins, f->bins_capacity * sizeof(unsigned)));
+  }
+  if (f->seg_pending) {   // previous upload may still be reading the pinned buffer
+    B200_CUDA(cudaEventSynchronize(f->seg_free));
+    f->seg_pending = false;
+  }
+  int64_t nseg = b200_phase_segments(phi, pps, ndat, f->h_seg, f->seg_capacity, nullptr);
+  if (nseg < 0) {
+    // pathological phase_per_sample (a pulse period of a few samples): more binade segments than
+    // the staging buffer holds.  Run the reference recurrence on the host and upload the bins.
+    std::vector<unsigned> hb(ndat), hh(f->nbin, 0u), ht(f->nbin);
+    b200_phase_bins_sequential(phi, pps, f->nbin, ndat, hb.data(), nullptr);
+    for (uint64_t i = 0; i < ndat; i++) hh[hb[i]]++;
+    B200_CUDA(cudaMemcpyAsync(ht.data(), f->d_hits_total, f->nbin * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (unsigned b = 0; b < f->nbin; b++) ht[b] += hh[b];
+    B200_CUDA(cudaMemcpyAsync(f->d_bins, hb.data(), ndat * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    B200_CUDA(cudaMemcpyAsync(f->d_hits_last, hh.data(), f->nbin * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    B200_CUDA(cudaMemcpyAsync(f->d_hits_total, ht.data(), f->nbin * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    f->ndat_total += ndat;
+    return B200_OK;
+  }
+  B200_CUDA(cudaMemcpyAsync(f->d_seg, f->h_seg, nseg * sizeof(b200_phase_segment), cudaMemcpyHostToDevice, ctx->stream));
+  B200_CUDA(cudaEventRecord(f->seg_free, ctx->stream));
+  f->seg_pending = true;
+  B200_CUDA(cudaMemsetAsync(f->d_hits_last, 0, f->nbin * sizeof(unsigned), ctx->stream));
+  const unsigned threads = 256;
+  unsigned grid = (unsigned)std::min<uint64_t>((ndat + threads - 1) / threads, ctx->sm_count * 8);
+  k_expand_bins<<<grid, threads, 0, ctx->stream>>>(f->d_seg, (unsigned)nseg, ndat, f->nbin, f->d_bins, f->d_hits_last,
+                                                  f->d_hits_total);
+  ctx->launches++;
+  f->ndat_total += ndat;
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_fold_get_bin_hits(b200_fold* f, unsigned* h_hits) {
+  B200_REQUIRE(f && h_hits, "b200_fold_get_bin_hits: null argument");
+  B200_CUDA(cudaMemcpyAsync(h_hits, f->d_hits_last, f->nbin * sizeof(unsigned), cudaMemcpyDeviceToHost, f->ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(f->ctx->stream));
+  return B200_OK;
+}
+
+int b200_fold_fold(b200_fold* f, const float* d_in, uint64_t in_span) {
+  B200_REQUIRE(f && d_in, "b200_fold_fold: null argument");
+  Context* ctx = f->ctx;
+  if (f->ndat == 0) return B200_OK;
+  B200_REQUIRE(f->d_bins, "b200_fold_fold: set_bins has not been called");
+  FoldArgs a;
+  a.in = d_in; a.in_span = in_span; a.idat_start = f->idat_start; a.ndat = f->ndat; a.bins = f->d_bins;
+  a.profile = f->d_profile; a.nchan = f->nchan; a.npol = f->npol; a.ndim = f->ndim; a.nbin = f->nbin;
+  const unsigned threads = 256;
+  const unsigned nplane = f->nchan * f->npol;
+  // slabs so that the grid fills the machine a few times over
+  uint64_t want = std::max<uint64_t>(1, uint64_t(ctx->sm_count) * 8 / nplane);
+  uint64_t slab = std::max<uint64_t>((f->ndat + want - 1) / want, uint64_t(threads) * 16);
+  a.slab = (unsigned)std::min<uint64_t>(slab, 1u << 30);
+  unsigned gx = (unsigned)((f->ndat + a.slab - 1) / a.slab);
+  size_t smem = size_t(f->nbin) * f->ndim * sizeof(float);
+  a.smem_bins = smem <= 48 * 1024 ? 1 : 0;
+  if (!a.smem_bins) smem = 0;
+  dim3 grid(gx, nplane);
+  if (f->ndim == 4) k_fold<4><<<grid, threads, smem, ctx->stream>>>(a);
+  else if (f->ndim == 2) k_fold<2><<<grid, threads, smem, ctx->stream>>>(a);
+  else k_fold<1><<<grid, threads, smem, ctx->stream>>>(a);
+  ctx->launches++;
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_fold_synch(b200_fold* f, float* h_profile) {
+  B200_REQUIRE(f && h_profile, "b200_fold_synch: null argument");
+  const uint64_t nfloat = uint64_t(f->nchan) * f->npol * f->ndim * f->nbin;
+  B200_CUDA(cudaMemcpyAsync(h_profile, f->d_profile, nfloat * sizeof(float), cudaMemcpyDeviceToHost, f->ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(f->ctx->stream));
+  return B200_OK;
+}
+
+int b200_fold_get_hits(b200_fold* f, unsigned* h_hits, uint64_t* ndat_total) {
+  B200_REQUIRE(f, "b200_fold_get_hits: null fold");
+  if (h_hits) {
+    B200_CUDA(cudaMemcpyAsync(h_hits, f->d_hits_total, f->nbin * sizeof(unsigned), cudaMemcpyDeviceToHost, f->ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(f->ctx->stream));
+  }
+  if (ndat_total) *ndat_total = f->ndat_total;
+  return B200_OK;
+}
+
+int b200_fold_zero(b200_fold* f) {
+  B200_REQUIRE(f, "b200_fold_zero: null fold");
+  const uint64_t nfloat = uint64_t(f->nchan) * f->npol * f->ndim * f->nbin;
+  B200_CUDA(cudaMemsetAsync(f->d_profile, 0, nfloat * sizeof(float), f->ctx->stream));
+  B200_CUDA(cudaMemsetAsync(f->d_hits_total, 0, f->nbin * sizeof(unsigned), f->ctx->stream));
+  B200_CUDA(cudaMemsetAsync(f->d_hits_last, 0, f->nbin * sizeof(unsigned), f->ctx->stream));
+  f->ndat_total = 0;
+  return B200_OK;
+}
+
+float* b200_fold_device_profile(b200_fold* f) { return f ? f->d_profile : nullptr; }
+unsigned* b200_fold_device_hits(b200_fold* f) { return f ? f->d_hits_total : nullptr; }
+
+}  // extern "C"
+
+// internal accessors for pipeline.cu
+namespace b200 {
+const unsigned* fold_bins(b200_fold* f) { return f->d_bins; }
+}

@@ -1,0 +1,146 @@
+// host_fft_emul.cu -- CPU emulation of the block FFT (fft_core.cuh) used by the CPU-only
+// test-suite: runs the very same __host__ __device__ stage code thread-by-thread with an
+// emulated shared memory, and compares against a double-precision DFT.
+// Build: nvcc -std=c++17 -O2 host_fft_emul.cu -o host_fft_emul   (no GPU needed to run)
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "fft_core.cuh"
+
+using namespace b200;
+
+template <int EPT, bool INV, typename Map>
+static void run_stage(int R, std::vector<float2>& regs, unsigned T, unsigned Ns, const float2* tw, unsigned NT,
+                      std::vector<float2>& smem, std::vector<Map>& maps, bool last, std::vector<float2>& out) {
+  for (unsigned j = 0; j < T; j++) {
+    float2* v = &regs[size_t(j) * EPT];
+    switch (R) {
+      case 2: if constexpr (EPT >= 2) stage_compute<EPT, 2, INV>(v, j, T, Ns, tw, NT); break;
+      case 4: if constexpr (EPT >= 4) stage_compute<EPT, 4, INV>(v, j, T, Ns, tw, NT); break;
+      case 8: if constexpr (EPT >= 8) stage_compute<EPT, 8, INV>(v, j, T, Ns, tw, NT); break;
+      case 16: if constexpr (EPT >= 16) stage_compute<EPT, 16, INV>(v, j, T, Ns, tw, NT); break;
+      case 32: if constexpr (EPT >= 32) stage_compute<EPT, 32, INV>(v, j, T, Ns, tw, NT); break;
+    }
+  }
+  // "syncthreads", then scatter
+  for (unsigned j = 0; j < T; j++) {
+    const int NB = EPT / R;
+    for (int q = 0; q < NB; q++)
+      for (int r = 0; r < R; r++) {
+        unsigned b = j + q * T, k = b & (Ns - 1);
+        unsigned d = (b - k) * R + k + r * Ns;
+        if (last) out[d] = regs[size_t(j) * EPT + q + r * NB];
+        else smem[maps[j](d)] = regs[size_t(j) * EPT + q + r * NB];
+      }
+  }
+  if (!last)
+    for (unsigned j = 0; j < T; j++)
+      for (int e = 0; e < EPT; e++) regs[size_t(j) * EPT + e] = smem[maps[j](j + e * T)];
+}
+
+template <int EPT, bool INV>
+static double test_one(unsigned N, int mapkind) {
+  const unsigned T = N / EPT;
+  std::vector<float2> tw(N);
+  for (unsigned m = 0; m < N; m++) {
+    double a = -2.0 * M_PI * m / N;
+    tw[m] = make_float2(float(cos(a)), float(sin(a)));
+  }
+  std::vector<std::complex<double>> x(N);
+  srand(N + EPT);
+  for (auto& z : x) z = {rand() / double(RAND_MAX) - 0.5, rand() / double(RAND_MAX) - 0.5};
+  std::vector<float2> regs(size_t(T) * EPT);
+  for (unsigned j = 0; j < T; j++)
+    for (int e = 0; e < EPT; e++) regs[size_t(j) * EPT + e] = make_float2(float(x[j + e * T].real()), float(x[j + e * T].imag()));
+  RadixPlan plan = make_radix_plan(N, EPT);
+  unsigned sh = 0;
+  while ((1u << sh) < (unsigned)plan.radix[0]) sh++;
+  std::vector<float2> out(N);
+  double err = 0;
+  if (mapkind == 0) {
+    std::vector<MapRows> maps(T);
+    for (auto& m : maps) m = MapRows{16, sh, 5};
+    std::vector<float2> smem(N + 64);
+    unsigned Ns = 1;
+    for (int s = 0; s < plan.nstage; s++) {
+      run_stage<EPT, INV>(plan.radix[s], regs, T, Ns, tw.data(), N, smem, maps, s == plan.nstage - 1, out);
+      Ns *= plan.radix[s];
+    }
+  } else {
+    // emulate B interleaved transforms, test transform b = 3 of B = 8
+    std::vector<MapCols> maps(T);
+    for (auto& m : maps) m = MapCols{3, 3, sh};
+    std::vector<float2> smem(size_t(N) * 8 + 64);
+    unsigned Ns = 1;
+    for (int s = 0; s < plan.nstage; s++) {
+      run_stage<EPT, INV>(plan.radix[s], regs, T, Ns, tw.data(), N, smem, maps, s == plan.nstage - 1, out);
+      Ns *= plan.radix[s];
+    }
+  }
+  // reference DFT (O(N^2) for small N, recursive split for large)
+  std::vector<std::complex<double>> X(N);
+  if (N <= 2048) {
+    for (unsigned k = 0; k < N; k++) {
+      std::complex<double> acc = 0;
+      for (unsigned n = 0; n < N; n++) {
+        double a = (INV ? 2.0 : -2.0) * M_PI * double((uint64_t(k) * n) % N) / N;
+        acc += x[n] * std::complex<double>(cos(a), sin(a));
+      }
+      X[k] = acc;
+    }
+  } else {
+    // iterative radix-2 in double
+    std::vector<std::complex<double>> a(x);
+    unsigned lg = 0;
+    while ((1u << lg) < N) lg++;
+    for (unsigned i = 0; i < N; i++) {
+      unsigned r = 0;
+      for (unsigned bit = 0; bit < lg; bit++) if (i & (1u << bit)) r |= 1u << (lg - 1 - bit);
+      if (r > i) std::swap(a[i], a[r]);
+    }
+    for (unsigned len = 2; len <= N; len <<= 1) {
+      double ang = (INV ? 2.0 : -2.0) * M_PI / len;
+      for (unsigned i = 0; i < N; i += len)
+        for (unsigned k = 0; k < len / 2; k++) {
+          std::complex<double> w(cos(ang * k), sin(ang * k));
+          auto u = a[i + k], t = a[i + k + len / 2] * w;
+          a[i + k] = u + t;
+          a[i + k + len / 2] = u - t;
+        }
+    }
+    X = a;
+  }
+  double rms = 0;
+  for (unsigned k = 0; k < N; k++) rms += std::norm(X[k]);
+  rms = sqrt(rms / N);
+  for (unsigned k = 0; k < N; k++) {
+    double e = std::abs(std::complex<double>(out[k].x, out[k].y) - X[k]) / rms;
+    if (e > err) err = e;
+  }
+  return err;
+}
+
+template <int EPT>
+static int sweep(unsigned nmin, unsigned nmax) {
+  int bad = 0;
+  for (unsigned N = nmin; N <= nmax; N <<= 1) {
+    double e0 = test_one<EPT, false>(N, 0), e1 = test_one<EPT, true>(N, 0), e2 = test_one<EPT, false>(N, 1);
+    printf("EPT=%d N=%u fwd %.3e inv %.3e cols %.3e\n", EPT, N, e0, e1, e2);
+    if (!(e0 < 2e-6 && e1 < 2e-6 && e2 < 2e-6)) bad++;
+  }
+  return bad;
+}
+
+int main() {
+  int bad = 0;
+  bad += sweep<2>(2, 2);
+  bad += sweep<4>(4, 64);
+  bad += sweep<8>(8, 512);
+  bad += sweep<16>(16, 16384);
+  bad += sweep<32>(32, 16384);
+  printf(bad ? "FAIL %d\n" : "OK\n", bad);
+  return bad ? 1 : 0;
+}

@@ -1,0 +1,204 @@
+// pipeline.cu -- fused path: raw bytes -> (K1, K2, K3 with detect+fold epilogue) -> PhaseSeries.
+// What dspsr computes with [IOManager(unpack), Filterbank|Convolution, Detection, Fold]
+// (Signal/Pulsar/LoadToFold1.C:117-599, SingleThread.C:405-431) when no operation sits between.
+#include <cstring>
+
+#include "engine.cuh"
+
+namespace b200 {
+const unsigned* fold_bins(b200_fold* f);
+}
+using namespace b200;
+
+struct b200_pipeline {
+  Context* ctx;
+  b200_pipeline_desc desc;
+  b200_fb_plan* fb;
+  b200_fold* fold;
+  float* d_lut;
+  // staging for execute_host
+  void* d_stage;
+  uint64_t stage_bytes;
+  // unpacked float series for formats whose unpack is not fused into K1
+  float* d_unpacked;
+  uint64_t unpacked_floats;
+  unsigned nprod, dnpol, dndim;
+};
+
+static unsigned fmt_resolution(int fmt) {
+  switch (fmt) {
+    case B200_FMT_CASPSR8: return 4;
+    case B200_FMT_MEERKAT8: return 256;
+    case B200_FMT_UWB16: return 2048;
+    default: return 1;
+  }
+}
+static unsigned fmt_nbit(int fmt) { return fmt == B200_FMT_UWB16 ? 16 : fmt == B200_FMT_FLOAT32 ? 32 : 8; }
+
+extern "C" {
+
+int b200_pipeline_create(b200_context* cctx, const b200_pipeline_desc* d, b200_pipeline** out) {
+  B200_REQUIRE(cctx && d && out, "b200_pipeline_create: null argument");
+  Context* ctx = reinterpret_cast<Context*>(cctx);
+  const int fmt = d->unpack.format;
+  B200_REQUIRE(fmt >= B200_FMT_CASPSR8 && fmt <= B200_FMT_FLOAT32, "unknown input format %d", fmt);
+  B200_REQUIRE(d->unpack.nchan == d->fb.input_nchan && d->unpack.npol == d->fb.npol,
+               "unpacker nchan/npol (%u,%u) != filterbank input (%u,%u)", d->unpack.nchan, d->unpack.npol,
+               d->fb.input_nchan, d->fb.npol);
+  B200_REQUIRE(d->unpack.ndim == (d->fb.input_real ? 1u : 2u), "unpacker ndim=%u inconsistent with input state",
+               d->unpack.ndim);
+  B200_REQUIRE(d->detect_state >= 0 && d->detect_state <= 3, "invalid detection state");
+  b200_pipeline* p = new b200_pipeline();
+  memset(p, 0, sizeof(*p));
+  p->ctx = ctx;
+  p->desc = *d;
+  p->desc.fb.h_response = nullptr;
+  if (d->detect_state >= B200_COHERENCE) {
+    p->nprod = 4;
+    p->dndim = d->detect_ndim;
+    if (!(p->dndim == 1 || p->dndim == 2 || p->dndim == 4)) {
+      delete p;
+      set_error("invalid detection ndim %u", d->detect_ndim);
+      return B200_ERR_INVALID;
+    }
+  } else {
+    p->nprod = d->detect_state == B200_PPQQ ? d->fb.npol : 1;
+    p->dndim = 1;
+  }
+  p->dnpol = p->nprod / p->dndim;
+  int rc = b200_fb_plan_create(cctx, &d->fb, &p->fb);
+  if (rc != B200_OK) { delete p; return rc; }
+  if (d->nbin) {
+    rc = b200_fold_create(cctx, p->fb->nchan_out, p->dnpol, p->dndim, d->nbin, &p->fold);
+    if (rc != B200_OK) { b200_pipeline_destroy(p); return rc; }
+  }
+  if (fmt == B200_FMT_CASPSR8 || fmt == B200_FMT_GENERIC8) {
+    cudaError_t e = cudaMalloc(&p->d_lut, 256 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_lut, d->unpack.lut, 256 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { b200_pipeline_destroy(p); return cuda_fail(e, "lut upload", __FILE__, __LINE__); }
+  }
+  *out = p;
+  return B200_OK;
+}
+
+int b200_pipeline_destroy(b200_pipeline* p) {
+  if (!p) return B200_OK;
+  if (p->fb) b200_fb_plan_destroy(p->fb);
+  if (p->fold) b200_fold_destroy(p->fold);
+  if (p->d_lut) cudaFree(p->d_lut);
+  if (p->d_stage) cudaFree(p->d_stage);
+  if (p->d_unpacked) cudaFree(p->d_unpacked);
+  delete p;
+  return B200_OK;
+}
+
+int b200_pipeline_info(const b200_pipeline* p, b200_fb_info* info) {
+  B200_REQUIRE(p, "null pipeline");
+  return b200_fb_plan_info(p->fb, info);
+}
+
+b200_fold* b200_pipeline_fold(b200_pipeline* p) { return p ? p->fold : nullptr; }
+
+int b200_pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t input_span, uint64_t first_sample,
+                          uint64_t npart, double phi, double pps, float* d_detected, uint64_t detected_span) {
+  B200_REQUIRE(p && d_input, "b200_pipeline_execute: null argument");
+  if (npart == 0) return B200_OK;
+  Context* ctx = p->ctx;
+  b200_fb_plan* fb = p->fb;
+  const int fmt = p->desc.unpack.format;
+  const unsigned ndim = p->desc.unpack.ndim;
+  const uint64_t ndat_out = npart * fb->nkeep;
+
+  FbSource src;
+  memset(&src, 0, sizeof(src));
+  if (fmt == B200_FMT_CASPSR8) {
+    B200_REQUIRE(first_sample % 2 == 0, "CASPSR input must start on an even sample");
+    src.kind = SRC_CASPSR8;
+    // fold the first-sample offset into whole 8-byte groups + a residual handled by the loader
+    src.ptr = static_cast<const unsigned char*>(d_input) + 8 * (first_sample / 4);
+    B200_REQUIRE(first_sample % 4 == 0, "CASPSR block must start on a 4-sample boundary");
+    src.step = fb->nsamp_step;
+    src.d_lut = p->d_lut;
+  } else if (fmt == B200_FMT_FLOAT32) {
+    src.kind = SRC_F32;
+    src.ptr = static_cast<const float*>(d_input) + first_sample * ndim;
+    src.span = input_span;
+    src.step = uint64_t(fb->nsamp_step) * ndim;
+    B200_REQUIRE(input_span % 2 == 0 && (first_sample * ndim) % 2 == 0, "float input planes must be 8-byte aligned");
+  } else {
+    // unpack the enclosing resolution-aligned range, then seek (Unpacker.C:82-111)
+    const unsigned res = fmt_resolution(fmt);
+    const uint64_t ndat_in = npart * fb->nsamp_step + fb->nsamp_overlap;
+    const uint64_t a0 = (first_sample / res) * res;
+    const uint64_t a1 = ((first_sample + ndat_in + res - 1) / res) * res;
+    const uint64_t span = (a1 - a0) * ndim;
+    const uint64_t need = span * p->desc.unpack.nchan * p->desc.unpack.npol;
+    if (need > p->unpacked_floats) {
+      B200_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (p->d_unpacked) cudaFree(p->d_unpacked);
+      p->d_unpacked = nullptr;
+      p->unpacked_floats = need + need / 8;
+      B200_CUDA(cudaMalloc(&p->d_unpacked, p->unpacked_floats * sizeof(float)));
+    }
+    const uint64_t bytes_per_sample = uint64_t(p->desc.unpack.nchan) * p->desc.unpack.npol * ndim * fmt_nbit(fmt) / 8;
+    int rc = b200_unpack(reinterpret_cast<b200_context*>(ctx), &p->desc.unpack,
+                         static_cast<const unsigned char*>(d_input) + a0 * bytes_per_sample, a1 - a0, p->d_unpacked, span);
+    if (rc != B200_OK) return rc;
+    src.kind = SRC_F32;
+    src.ptr = p->d_unpacked + (first_sample - a0) * ndim;
+    src.span = span;
+    src.step = uint64_t(fb->nsamp_step) * ndim;
+    B200_REQUIRE(((first_sample - a0) * ndim) % 2 == 0, "unaligned block start");
+  }
+
+  FbSink sink;
+  memset(&sink, 0, sizeof(sink));
+  sink.state = p->desc.detect_state;
+  sink.dndim = p->dndim;
+  if (p->desc.nbin) {
+    int rc = b200_fold_set_bins(p->fold, phi, pps, ndat_out, 0, nullptr);
+    if (rc != B200_OK) return rc;
+    sink.kind = EPI_FOLD;
+    sink.bins = fold_bins(p->fold);
+    sink.nbin = p->desc.nbin;
+    sink.profile = b200_fold_device_profile(p->fold);
+  } else {
+    B200_REQUIRE(d_detected, "b200_pipeline_execute: nbin == 0 needs an output buffer for the detected series");
+    sink.kind = EPI_DETECT;
+    sink.det = d_detected;
+    sink.det_span = detected_span;
+  }
+  return fb_run(fb, src, sink, npart);
+}
+
+int b200_pipeline_execute_host(b200_pipeline* p, const void* h_input, uint64_t nbytes, uint64_t first_sample,
+                               uint64_t npart, double phi, double pps) {
+  B200_REQUIRE(p && h_input, "b200_pipeline_execute_host: null argument");
+  B200_REQUIRE(p->desc.unpack.format != B200_FMT_FLOAT32, "execute_host takes raw bytes");
+  Context* ctx = p->ctx;
+  if (nbytes > p->stage_bytes) {
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (p->d_stage) cudaFree(p->d_stage);
+    p->d_stage = nullptr;
+    p->stage_bytes = nbytes;
+    B200_CUDA(cudaMalloc(&p->d_stage, p->stage_bytes));
+  }
+  B200_CUDA(cudaMemcpyAsync(p->d_stage, h_input, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+  return b200_pipeline_execute(p, p->d_stage, 0, first_sample, npart, phi, pps, nullptr, 0);
+}
+
+int b200_pipeline_synch(b200_pipeline* p, float* h_profile, unsigned* h_hits, uint64_t* ndat_total) {
+  B200_REQUIRE(p && p->fold, "b200_pipeline_synch: pipeline has no fold stage");
+  int rc = B200_OK;
+  if (h_profile) rc = b200_fold_synch(p->fold, h_profile);
+  if (rc == B200_OK) rc = b200_fold_get_hits(p->fold, h_hits, ndat_total);
+  return rc;
+}
+
+int b200_pipeline_zero(b200_pipeline* p) {
+  B200_REQUIRE(p && p->fold, "b200_pipeline_zero: pipeline has no fold stage");
+  return b200_fold_zero(p->fold);
+}
+
+}  // extern "C"

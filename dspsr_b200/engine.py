@@ -1,0 +1,308 @@
+"""Python handles on the C-ABI engines (one class per reference engine interface).
+
+These are thin: they own a handle, translate torch CUDA tensors into (pointer, span) pairs
+exactly like the C++ shims in dspsr_b200/host/ translate dsp::TimeSeries, and raise B200Error
+on a non-zero status (the shims `throw Error`).  torch is used for device memory and streams
+only; every computation happens in libb200dsp.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _need_cuda(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous()):
+        raise TypeError("%s must be a contiguous CUDA tensor" % name)
+
+
+class Context:
+    """One CUDA stream of one device (reference: one pipeline thread, SingleThread.C:237-244)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = L.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("dspsr_b200 needs a CUDA device (no CPU fallback)")
+        torch.cuda.set_device(device)
+        self.device = device
+        self.torch_stream = stream if stream is not None else torch.cuda.current_stream(device)
+        h = C.c_void_p()
+        L.check(self.lib.b200_context_create(device, C.c_void_p(self.torch_stream.cuda_stream), C.byref(h)))
+        self.h = h
+
+    def synchronize(self):
+        L.check(self.lib.b200_context_synchronize(self.h))
+
+    @property
+    def launches(self):
+        return int(self.lib.b200_context_launch_count(self.h))
+
+    def __del__(self):
+        try:
+            self.lib.b200_context_destroy(self.h)
+        except Exception:
+            pass
+
+
+def make_unpack_desc(fmt, nchan, npol, ndim, lut=None, scale=0.0, sample_swap=1):
+    d = L.UnpackDesc()
+    d.format, d.nchan, d.npol, d.ndim = fmt, nchan, npol, ndim
+    if lut is not None:
+        lut = np.ascontiguousarray(lut, np.float32)
+        C.memmove(d.lut, lut.ctypes.data, 1024)
+    d.scale = scale
+    d.sample_swap = sample_swap
+    return d
+
+
+def unpack(ctx, desc, raw, ndat):
+    """Unpacker device hook: raw uint8 CUDA tensor -> float32 [nchan, npol, ndat*ndim]."""
+    _need_cuda(raw, "raw")
+    out = torch.empty((desc.nchan, desc.npol, ndat * desc.ndim), dtype=torch.float32, device=raw.device)
+    L.check(ctx.lib.b200_unpack(ctx.h, C.byref(desc), _ptr(raw), ndat, _ptr(out), ndat * desc.ndim))
+    return out
+
+
+def make_fb_desc(input_real, input_nchan, npol, nchan_subband, freq_res, nfilt_pos, nfilt_neg, response=None,
+                 max_npart=0):
+    d = L.FbDesc()
+    d.input_real = int(input_real)
+    d.input_nchan, d.npol, d.nchan_subband, d.freq_res = input_nchan, npol, nchan_subband, freq_res
+    d.nfilt_pos, d.nfilt_neg = nfilt_pos, nfilt_neg
+    d.max_npart = max_npart
+    keep = None
+    if response is not None:
+        keep = np.ascontiguousarray(response, np.complex64)
+        assert keep.size == input_nchan * nchan_subband * freq_res, "response size"
+        d.h_response = keep.ctypes.data
+    return d, keep
+
+
+class FilterbankEngine:
+    """dsp::Filterbank::Engine / dsp::Convolution::Engine (FilterbankEngine.h:15-44, Convolution.h:158-167)."""
+
+    def __init__(self, ctx, input_real, input_nchan, npol, nchan_subband, freq_res, nfilt_pos, nfilt_neg,
+                 response=None, max_npart=0):
+        self.ctx = ctx
+        d, keep = make_fb_desc(input_real, input_nchan, npol, nchan_subband, freq_res, nfilt_pos, nfilt_neg,
+                               response, max_npart)
+        h = C.c_void_p()
+        L.check(ctx.lib.b200_fb_plan_create(ctx.h, C.byref(d), C.byref(h)))
+        self.h = h
+        self.desc = d
+        info = L.FbInfo()
+        L.check(ctx.lib.b200_fb_plan_info(h, C.byref(info)))
+        self.info = info
+        self.ndim = 1 if input_real else 2
+        self.nchan = input_nchan * nchan_subband
+
+    def npart(self, ndat):
+        # Filterbank::resize_output (Filterbank.C:401-402)
+        i = self.info
+        return (ndat - i.nsamp_overlap) // i.nsamp_step if ndat > i.nsamp_overlap else 0
+
+    def perform(self, x, npart=None):
+        """x: [input_nchan, npol, ndat*ndim] float32 CUDA -> [nchan, npol, npart*nkeep*2] float32."""
+        _need_cuda(x, "x")
+        i = self.info
+        ndat = x.shape[2] // self.ndim
+        if npart is None:
+            npart = self.npart(ndat)
+        out = torch.empty((self.nchan, self.desc.npol, npart * i.nkeep * 2), dtype=torch.float32, device=x.device)
+        L.check(self.ctx.lib.b200_fb_perform(self.h, _ptr(x), x.shape[2], _ptr(out), out.shape[2], npart,
+                                             i.nsamp_step * self.ndim, i.nkeep * 2))
+        return out
+
+    def __del__(self):
+        try:
+            self.ctx.lib.b200_fb_plan_destroy(self.h)
+        except Exception:
+            pass
+
+
+def detect(ctx, state, ndim_out, v, npol=2):
+    """dsp::Detection::Engine. v: [nchan, npol, ndat*2] float32 CUDA -> [nchan, npol', ndat*ndim']."""
+    _need_cuda(v, "v")
+    s = L.STATE[state] if isinstance(state, str) else state
+    nchan, npol, n2 = v.shape
+    ndat = n2 // 2
+    if s >= L.COHERENCE:
+        onpol, ondim = 4 // ndim_out, ndim_out
+    else:
+        onpol, ondim = (npol if s == L.PPQQ else 1), 1
+    out = torch.empty((nchan, onpol, ndat * ondim), dtype=torch.float32, device=v.device)
+    L.check(ctx.lib.b200_detect(ctx.h, s, ondim, _ptr(v), n2, nchan, npol, ndat, _ptr(out), ndat * ondim))
+    return out
+
+
+class FoldEngine:
+    """dsp::Fold::Engine (Fold.h:249-312): owns the accumulating device PhaseSeries."""
+
+    def __init__(self, ctx, nchan, npol, ndim, nbin, handle=None):
+        self.ctx = ctx
+        self.nchan, self.npol, self.ndim, self.nbin = nchan, npol, ndim, nbin
+        self.owned = handle is None
+        if handle is None:
+            handle = C.c_void_p()
+            L.check(ctx.lib.b200_fold_create(ctx.h, nchan, npol, ndim, nbin, C.byref(handle)))
+        self.h = handle
+
+    def set_bins(self, phi, phase_per_sample, ndat, idat_start=0):
+        n = C.c_uint64(0)
+        L.check(self.ctx.lib.b200_fold_set_bins(self.h, phi, phase_per_sample, ndat, idat_start, C.byref(n)))
+        return n.value
+
+    def get_bin_hits(self):
+        h = np.zeros(self.nbin, np.uint32)
+        L.check(self.ctx.lib.b200_fold_get_bin_hits(self.h, h.ctypes.data_as(C.c_void_p)))
+        return h
+
+    def fold(self, x):
+        _need_cuda(x, "x")
+        L.check(self.ctx.lib.b200_fold_fold(self.h, _ptr(x), x.shape[2]))
+
+    def synch(self):
+        p = np.zeros((self.nchan, self.npol, self.nbin * self.ndim), np.float32)
+        L.check(self.ctx.lib.b200_fold_synch(self.h, p.ctypes.data_as(C.c_void_p)))
+        return p
+
+    def hits(self):
+        h = np.zeros(self.nbin, np.uint32)
+        n = C.c_uint64(0)
+        L.check(self.ctx.lib.b200_fold_get_hits(self.h, h.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return h, n.value
+
+    def zero(self):
+        L.check(self.ctx.lib.b200_fold_zero(self.h))
+
+    def device_profile(self):
+        """torch view of the device profile (for NCCL reductions at sub-integration boundaries)."""
+        ptr = self.ctx.lib.b200_fold_device_profile(self.h)
+        n = self.nchan * self.npol * self.nbin * self.ndim
+        return _tensor_from_ptr(ptr, n, torch.float32, self.ctx.device)
+
+    def device_hits(self):
+        ptr = self.ctx.lib.b200_fold_device_hits(self.h)
+        return _tensor_from_ptr(ptr, self.nbin, torch.int32, self.ctx.device)
+
+    def __del__(self):
+        try:
+            if self.owned:
+                self.ctx.lib.b200_fold_destroy(self.h)
+        except Exception:
+            pass
+
+
+class _CudaArrayView:
+    def __init__(self, ptr, nbytes, typestr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def _tensor_from_ptr(ptr, n, dtype, device):
+    typestr = {torch.float32: "<f4", torch.int32: "<i4"}[dtype]
+    return torch.as_tensor(_CudaArrayView(ptr, n * 4, typestr, n), device="cuda:%d" % device)
+
+
+class Pipeline:
+    """Fused raw bytes -> PhaseSeries path (b200_pipeline_*)."""
+
+    def __init__(self, ctx, unpack_desc, fb_desc, response_keepalive, detect_state, detect_ndim, nbin):
+        self.ctx = ctx
+        d = L.PipelineDesc()
+        d.unpack = unpack_desc
+        d.fb = fb_desc
+        d.detect_state = L.STATE[detect_state] if isinstance(detect_state, str) else detect_state
+        d.detect_ndim = detect_ndim
+        d.nbin = nbin
+        self._keep = response_keepalive
+        h = C.c_void_p()
+        L.check(ctx.lib.b200_pipeline_create(ctx.h, C.byref(d), C.byref(h)))
+        self.h = h
+        self.desc = d
+        info = L.FbInfo()
+        L.check(ctx.lib.b200_pipeline_info(h, C.byref(info)))
+        self.info = info
+        self.nchan = fb_desc.input_nchan * fb_desc.nchan_subband
+        s = d.detect_state
+        if s >= L.COHERENCE:
+            self.dnpol, self.dndim = 4 // detect_ndim, detect_ndim
+        else:
+            self.dnpol, self.dndim = (fb_desc.npol if s == L.PPQQ else 1), 1
+        self.nbin = nbin
+        self.fold = None
+        if nbin:
+            fh = C.c_void_p(ctx.lib.b200_pipeline_fold(h))
+            self.fold = FoldEngine(ctx, self.nchan, self.dnpol, self.dndim, nbin, handle=fh)
+
+    def execute(self, d_input, npart, phi=0.0, pps=0.0, first_sample=0, input_span=0):
+        _need_cuda(d_input, "d_input")
+        det = None
+        dptr, dspan = None, 0
+        if not self.nbin:
+            dspan = npart * self.info.nkeep * self.dndim
+            det = torch.empty((self.nchan, self.dnpol, dspan), dtype=torch.float32, device=d_input.device)
+            dptr = _ptr(det)
+        L.check(self.ctx.lib.b200_pipeline_execute(self.h, _ptr(d_input), input_span, first_sample, npart, phi, pps,
+                                                   dptr, dspan))
+        return det
+
+    def execute_host(self, h_input, npart, phi=0.0, pps=0.0, first_sample=0):
+        """h_input: numpy uint8 array or pinned torch CPU tensor of raw bytes."""
+        if isinstance(h_input, torch.Tensor):
+            ptr, nbytes = h_input.data_ptr(), h_input.numel() * h_input.element_size()
+        else:
+            ptr, nbytes = h_input.ctypes.data, h_input.nbytes
+        L.check(self.ctx.lib.b200_pipeline_execute_host(self.h, C.c_void_p(ptr), nbytes, first_sample, npart, phi, pps))
+
+    def synch(self):
+        p = np.zeros((self.nchan, self.dnpol, self.nbin * self.dndim), np.float32)
+        h = np.zeros(self.nbin, np.uint32)
+        n = C.c_uint64(0)
+        L.check(self.ctx.lib.b200_pipeline_synch(self.h, p.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p),
+                                                 C.byref(n)))
+        return p, h, n.value
+
+    def zero(self):
+        L.check(self.ctx.lib.b200_pipeline_zero(self.h))
+
+    def __del__(self):
+        try:
+            self.ctx.lib.b200_pipeline_destroy(self.h)
+        except Exception:
+            pass
+
+
+# ---- host-only helpers (exact fold bin plan) -------------------------------------------------
+def phase_segments(phi, pps, ndat, max_segments=1 << 16):
+    lib = L.load()
+    seg = (L.PhaseSegment * max_segments)()
+    phi_end = C.c_double(0)
+    n = lib.b200_phase_segments(phi, pps, ndat, seg, max_segments, C.byref(phi_end))
+    if n < 0:
+        raise L.B200Error(1, "more than %d phase segments" % max_segments)
+    return [seg[i] for i in range(n)], phi_end.value
+
+
+def phase_bins_sequential(phi, pps, nbin, ndat):
+    lib = L.load()
+    bins = np.zeros(ndat, np.uint32)
+    phi_end = C.c_double(0)
+    lib.b200_phase_bins_sequential(phi, pps, nbin, ndat, bins.ctypes.data_as(C.c_void_p), C.byref(phi_end))
+    return bins, phi_end.value
+
+
+def expand_segments_numpy(segs, nbin, ndat):
+    """Host expansion of phase segments with the same exact arithmetic as k_expand_bins (tests)."""
+    bins = np.zeros(ndat, np.uint32)
+    for s in segs:
+        t = np.arange(s.count, dtype=np.uint64)
+        a = np.uint64(s.a0) + t * np.uint64(s.step)
+        phi = np.ldexp(a.astype(np.float64), s.scale_exp)
+        bins[s.start:s.start + s.count] = (phi * float(nbin)).astype(np.uint32)
+    return bins

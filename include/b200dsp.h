@@ -1,0 +1,235 @@
+/* b200dsp.h -- C ABI of libb200dsp.so: dspsr's baseband hot path on NVIDIA B200 (sm_100a).
+ *
+ * unpack -> overlap-save coherent dedispersion / filterbank -> detection -> fold
+ *
+ * Every entry point is extern "C", takes plain pointers and sizes, returns a b200_status
+ * (0 = success) and never throws; b200_last_error() holds the message of the last failure
+ * on the calling thread.  Pointers named d_* are device pointers, h_* host pointers.
+ * Nothing in execute-type calls allocates.  One b200_context == one CUDA stream == one dspsr
+ * pipeline thread (reference: Signal/General/SingleThread.C:237-244 creates exactly one
+ * stream per thread; engines obtain it from CUDA::DeviceMemory::get_stream()).
+ *
+ * Each group cites the reference interface it replaces (paths relative to demorest/dspsr).
+ * The precedent for a C struct + C function boundary under the C++ engines is the
+ * reference's own Signal/General/dsp/filterbank_engine.h:25-38 and
+ * dsp/filterbank_cuda.h:64-66 (filterbank_cuda_perform).
+ */
+#ifndef B200DSP_H
+#define B200DSP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  B200_OK = 0,
+  B200_ERR_INVALID = 1,     /* bad argument / state            (reference: Error(InvalidParam|InvalidState)) */
+  B200_ERR_CUDA = 2,        /* CUDA runtime failure            (reference: Kernel/Classes/check_error.C)    */
+  B200_ERR_UNSUPPORTED = 3, /* shape outside what is built                                                  */
+  B200_ERR_NOMEM = 4
+} b200_status;
+
+typedef struct b200_context b200_context;
+typedef struct b200_fb_plan b200_fb_plan;
+typedef struct b200_fold b200_fold;
+typedef struct b200_pipeline b200_pipeline;
+
+/* ---------------------------------------------------------------------------------------
+ * Library / context.  Replaces: CUDA::DeviceMemory(stream, device) and the cudaSetDevice /
+ * cudaStreamCreate block of Signal/General/SingleThread.C:237-244; dsp::Memory::do_allocate /
+ * do_free / do_zero / do_copy (Kernel/Classes/MemoryCUDA.C).
+ * ------------------------------------------------------------------------------------- */
+int b200_version(void);
+const char* b200_last_error(void);
+
+/* cuda_stream: a cudaStream_t to run on, or NULL to create a private non-blocking stream. */
+int b200_context_create(int device, void* cuda_stream, b200_context** ctx);
+int b200_context_destroy(b200_context* ctx);
+int b200_context_synchronize(b200_context* ctx);
+/* kernels launched through this context so far (bench.py's gpu_launches) */
+unsigned long long b200_context_launch_count(const b200_context* ctx);
+void* b200_context_stream(const b200_context* ctx);
+
+int b200_malloc(b200_context* ctx, uint64_t nbytes, void** d_ptr);
+int b200_free(b200_context* ctx, void* d_ptr);
+int b200_malloc_host(b200_context* ctx, uint64_t nbytes, void** h_ptr); /* pinned */
+int b200_free_host(b200_context* ctx, void* h_ptr);
+int b200_memset(b200_context* ctx, void* d_ptr, int value, uint64_t nbytes);
+int b200_memcpy_h2d(b200_context* ctx, void* d_dst, const void* h_src, uint64_t nbytes);
+int b200_memcpy_d2h(b200_context* ctx, void* h_dst, const void* d_src, uint64_t nbytes);
+
+/* ---------------------------------------------------------------------------------------
+ * Unpacker device hook.  Replaces: Unpacker::unpack() on a device (Kernel/Classes/dsp/
+ * Unpacker.h:57-61,100) for
+ *   B200_FMT_CASPSR8   CASPSRUnpacker::unpack          Kernel/Formats/caspsr/CASPSRUnpacker.C:132-187
+ *   B200_FMT_GENERIC8  BitUnpacker/EightBitUnpacker     Kernel/Classes/BitUnpacker.C:48-80
+ *   B200_FMT_MEERKAT8  MeerKATUnpacker::unpack (FPT)    Kernel/Formats/kat/MeerKATUnpacker.C:196-229
+ *   B200_FMT_UWB16     UWBUnpacker::unpack              Kernel/Formats/uwb/UWBUnpacker.C:177-218
+ * Output is a dsp::TimeSeries in FPT order: plane(ichan,ipol) = d_out + (ichan*npol+ipol)*out_span
+ * floats, element [idat*ndim + idim].  The 8-bit LUT formats index the HOST-BUILT 256-entry
+ * table of dsp::BitTable (BitTable.C:165-218) so results are bit-identical to the CPU path.
+ * ------------------------------------------------------------------------------------- */
+typedef enum {
+  B200_FMT_CASPSR8 = 0,
+  B200_FMT_GENERIC8 = 1,
+  B200_FMT_MEERKAT8 = 2,
+  B200_FMT_UWB16 = 3,
+  B200_FMT_FLOAT32 = 4 /* already a float TimeSeries (pipeline input only) */
+} b200_format;
+
+typedef struct {
+  int format;            /* b200_format */
+  unsigned nchan, npol, ndim;
+  float lut[256];        /* CASPSR8 / GENERIC8: BitTable::get_values() */
+  float scale;           /* MEERKAT8: float(BitTable::get_scale()) */
+  unsigned sample_swap;  /* MEERKAT8: 1 (MKBF) or 2 (MKBFRo) */
+} b200_unpack_desc;
+
+int b200_unpack(b200_context* ctx, const b200_unpack_desc* desc, const void* d_raw, uint64_t ndat,
+                float* d_out, uint64_t out_span);
+
+/* ---------------------------------------------------------------------------------------
+ * Filterbank / Convolution engine.  Replaces: dsp::Filterbank::Engine::{setup,set_scratch,
+ * perform,finish} (Signal/General/dsp/FilterbankEngine.h:15-44; reference implementation
+ * CUDA::FilterbankEngine, FilterbankCUDA.cu:60-304) and dsp::Convolution::Engine::{prepare,
+ * set_scratch,perform} (Signal/General/dsp/Convolution.h:158-167; ConvolutionCUDA.cu).
+ * Convolution is the nchan_subband = 1 case (freq_res = response ndat).
+ * The response is the finished, matched dsp::Response buffer (host float pairs,
+ * input_nchan*nchan_subband*freq_res complex) exactly as the reference hands it to its
+ * engines (FilterbankCUDA.cu:134-165); NULL = no response (plain filterbank).
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  int input_real;          /* 1: Signal::Nyquist (ndim 1), 0: Signal::Analytic (ndim 2) */
+  unsigned input_nchan;
+  unsigned npol;
+  unsigned nchan_subband;  /* output channels per input channel (Filterbank.C:68) */
+  unsigned freq_res;       /* points per output channel = Response::get_ndat() (Filterbank.C:93) */
+  unsigned nfilt_pos;      /* Response::get_impulse_pos() */
+  unsigned nfilt_neg;      /* Response::get_impulse_neg() */
+  const float* h_response; /* may be NULL */
+  unsigned max_npart;      /* parts per internal batch (scratch sizing); 0 = library default */
+} b200_fb_desc;
+
+typedef struct {
+  unsigned n_fft;          /* complex points of the forward transform (nchan_subband*freq_res) */
+  unsigned nsamp_fft, nsamp_overlap, nsamp_step, nkeep;   /* Filterbank.C:131-155,409 */
+  unsigned fft_rows, fft_cols;   /* two-pass factorisation P x Q of n_fft (Q = 1: single pass) */
+  unsigned batch_npart;
+  uint64_t scratch_bytes;
+} b200_fb_info;
+
+int b200_fb_plan_create(b200_context* ctx, const b200_fb_desc* desc, b200_fb_plan** plan);
+int b200_fb_plan_info(const b200_fb_plan* plan, b200_fb_info* info);
+int b200_fb_plan_destroy(b200_fb_plan* plan);
+
+/* Filterbank::Engine::perform (FilterbankEngine.h:29-33): d_in/d_out are get_datptr(0,0) of
+ * the device TimeSeries, *_span = floats between consecutive (chan,pol) planes
+ * (DataSeries::get_nfloat_span), in_step = nsamp_step*ndim floats, out_step = nkeep*2 floats
+ * (Filterbank.C:517-523).  For Convolution::Engine::perform pass the same quantities
+ * (Convolution.C:373,387). */
+int b200_fb_perform(b200_fb_plan* plan, const float* d_in, uint64_t in_span, float* d_out, uint64_t out_span,
+                    uint64_t npart, uint64_t in_step, uint64_t out_step);
+
+/* ---------------------------------------------------------------------------------------
+ * Detection engine.  Replaces: dsp::Detection::Engine::{polarimetry,square_law}
+ * (Signal/General/dsp/Detection.h:98-106; DetectionCUDA.cu:127-177,246-310).  Unlike the
+ * reference CUDA engine (ndim 2 only) every Detection::get_result_pointers layout
+ * (Detection.C:423-474, ndim 1|2|4) is produced.  In-place (d_in == d_out) is allowed for
+ * ndim_out == 2 only, as in the reference (Detection.C:358-361).
+ * ------------------------------------------------------------------------------------- */
+typedef enum { B200_INTENSITY = 0, B200_PPQQ = 1, B200_COHERENCE = 2, B200_STOKES = 3 } b200_state;
+
+int b200_detect(b200_context* ctx, int state, unsigned ndim_out, const float* d_in, uint64_t in_span,
+                unsigned nchan, unsigned npol, uint64_t ndat, float* d_out, uint64_t out_span);
+
+/* ---------------------------------------------------------------------------------------
+ * Fold engine.  Replaces: dsp::Fold::Engine::{set_nbin,set_ndat,set_bins,get_bin_hits,
+ * get_ndat_folded,fold,synch,zero} (Signal/Pulsar/dsp/Fold.h:249-312; CUDA::FoldEngine,
+ * FoldCUDA.cu:84-152,586-697).  The engine owns the accumulating device PhaseSeries
+ * [nchan][npol][nbin][ndim] floats (Fold.C:88-94).  set_bins reproduces the host's sequential
+ * double-precision recurrence of Fold.C:765-768 bit for bit (see DESIGN.md "bin plan").
+ * ------------------------------------------------------------------------------------- */
+int b200_fold_create(b200_context* ctx, unsigned nchan, unsigned npol, unsigned ndim, unsigned nbin,
+                     b200_fold** fold);
+int b200_fold_destroy(b200_fold* fold);
+/* Fold::Engine::set_bins(phi, phase_per_sample, ndat, idat_start) (Fold.h:261). */
+int b200_fold_set_bins(b200_fold* fold, double phi, double phase_per_sample, uint64_t ndat,
+                       uint64_t idat_start, uint64_t* ndat_folded);
+/* Fold::Engine::get_bin_hits for every bin of the last set_bins (Fold.C:731-735). */
+int b200_fold_get_bin_hits(b200_fold* fold, unsigned* h_hits);
+/* Fold::Engine::fold(): d_in = input->get_datptr(0,0), in_span = get_nfloat_span (Fold.C:989-990). */
+int b200_fold_fold(b200_fold* fold, const float* d_in, uint64_t in_span);
+/* Fold::Engine::synch(PhaseSeries*): copies the device profiles to the host (idempotent). */
+int b200_fold_synch(b200_fold* fold, float* h_profile);
+/* accumulated hits of every set_bins since the last zero (PhaseSeries::get_hits) */
+int b200_fold_get_hits(b200_fold* fold, unsigned* h_hits, uint64_t* ndat_total);
+int b200_fold_zero(b200_fold* fold);
+/* device pointer of the accumulating profile (for NCCL reductions at sub-integration ends) */
+float* b200_fold_device_profile(b200_fold* fold);
+unsigned* b200_fold_device_hits(b200_fold* fold);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused path: raw bytes -> folded profile without materialising the unpacked, filtered or
+ * detected time series (one spectrum round trip).  It is what the four engines above
+ * compute when dspsr wires [IOManager, Filterbank|Convolution, Detection, Fold]
+ * (Signal/Pulsar/LoadToFold1.C:117-599) with nothing in between.
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  b200_unpack_desc unpack; /* format FLOAT32: d_input is a float TimeSeries (span = input_span) */
+  b200_fb_desc fb;
+  int detect_state;        /* b200_state */
+  unsigned detect_ndim;    /* 1, 2 or 4 for COHERENCE / STOKES */
+  unsigned nbin;           /* 0: no fold -- detected series is written to d_detected */
+} b200_pipeline_desc;
+
+int b200_pipeline_create(b200_context* ctx, const b200_pipeline_desc* desc, b200_pipeline** pipe);
+int b200_pipeline_destroy(b200_pipeline* pipe);
+int b200_pipeline_info(const b200_pipeline* pipe, b200_fb_info* info);
+
+/* One block = one Fold::transformation call: npart overlap-save parts whose first sample is
+ * sample `first_sample` of d_input (d_input itself must start on a boundary of the format's
+ * resolution: 4 samples CASPSR, 256-sample heap MeerKAT, 2048-sample block UWB); phi /
+ * phase_per_sample as Fold::fold computes them (Fold.C:650-657,718-720) for the block's first
+ * OUTPUT sample.  input_span: floats between (chan,pol) planes when the format is FLOAT32,
+ * ignored for raw formats.  d_detected (nbin == 0 only): planes of npart*nkeep*ndim' floats
+ * with span detected_span. */
+int b200_pipeline_execute(b200_pipeline* pipe, const void* d_input, uint64_t input_span, uint64_t first_sample,
+                          uint64_t npart, double phi, double phase_per_sample, float* d_detected,
+                          uint64_t detected_span);
+/* Same, from HOST memory (pinned or pageable): copies nbytes to the device on the pipeline's
+ * stream first (File::load_bytes_device, Kernel/Classes/File.C:213-272). */
+int b200_pipeline_execute_host(b200_pipeline* pipe, const void* h_input, uint64_t nbytes, uint64_t first_sample,
+                               uint64_t npart, double phi, double phase_per_sample);
+int b200_pipeline_synch(b200_pipeline* pipe, float* h_profile, unsigned* h_hits, uint64_t* ndat_total);
+int b200_pipeline_zero(b200_pipeline* pipe);
+b200_fold* b200_pipeline_fold(b200_pipeline* pipe);
+
+/* ---------------------------------------------------------------------------------------
+ * Host-side helpers with no device work (exported so that hosts in any language share the
+ * exact arithmetic): the bin-plan recurrence and its closed form.
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  uint64_t start;      /* first sample of the segment */
+  uint64_t count;      /* samples in the segment */
+  uint64_t a0;         /* phase of the first sample in units of 2^scale_exp */
+  uint64_t step;       /* phase increment per sample in the same units */
+  int scale_exp;       /* phase = (a0 + i*step) * 2^scale_exp, exactly */
+  int pad;
+} b200_phase_segment;
+
+/* Splits the recurrence  phi -= floor(phi); ibin = unsigned(phi*nbin); phi += pps  (Fold.C:765-768)
+ * over ndat samples into segments inside which phi is an exact arithmetic progression.
+ * Returns the number of segments written (<= max_segments) or -1 if more are needed.
+ * phi_end receives phi after the last sample. */
+int64_t b200_phase_segments(double phi, double phase_per_sample, uint64_t ndat, b200_phase_segment* segments,
+                            uint64_t max_segments, double* phi_end);
+/* The plain sequential recurrence (reference behaviour), for hosts and tests. */
+void b200_phase_bins_sequential(double phi, double phase_per_sample, unsigned nbin, uint64_t ndat,
+                                unsigned* bins, double* phi_end);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DSP_H */

@@ -1,0 +1,282 @@
+"""GPU parity tests: every C-ABI engine against the CPU oracle on the same seeded inputs.
+Tolerances follow BASELINE.json north_star: unpack bit-exact; voltages and folded profiles
+<= 1e-5 relative (normalised to RMS); hits / ndat_total exact."""
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _E():
+    from dspsr_b200 import engine as E
+    return E
+
+
+def _L():
+    from dspsr_b200 import _lib as L
+    return L
+
+
+# ------------------------------------------------------------------------------------ unpack
+def test_unpack_caspsr_bitexact(ctx, oracle):
+    torch, E, L = _torch(), _E(), _L()
+    ndat = 1 << 16
+    raw = synth.caspsr_bytes(ndat)
+    lut, _ = oracle.bittable8()
+    ref = oracle.unpack_caspsr(raw, ndat, lut)
+    d = E.make_unpack_desc(L.FMT_CASPSR8, 1, 2, 1, lut)
+    out = E.unpack(ctx, d, torch.from_numpy(raw).cuda(), ndat).cpu().numpy()
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("nchan,npol,ndim", [(1, 2, 1), (4, 2, 2), (3, 1, 2), (16, 2, 1)])
+def test_unpack_generic8_bitexact(ctx, oracle, nchan, npol, ndim):
+    torch, E, L = _torch(), _E(), _L()
+    ndat = 5000
+    raw = synth.generic8_bytes(ndat, nchan, npol, ndim)
+    lut, _ = oracle.bittable8()
+    ref = oracle.unpack_generic8(raw, ndat, nchan, npol, ndim, lut)
+    d = E.make_unpack_desc(L.FMT_GENERIC8, nchan, npol, ndim, lut)
+    out = E.unpack(ctx, d, torch.from_numpy(raw).cuda(), ndat).cpu().numpy()
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("swap", [1, 2])
+def test_unpack_meerkat_bitexact(ctx, oracle, swap):
+    torch, E, L = _torch(), _E(), _L()
+    ndat, nchan, npol = 1024, 8, 2
+    raw = synth.meerkat_bytes(ndat, nchan, npol)
+    _, scale = oracle.bittable8()
+    scale = float(np.float32(scale))
+    ref = oracle.unpack_meerkat(raw, ndat, nchan, npol, scale, swap)
+    d = E.make_unpack_desc(L.FMT_MEERKAT8, nchan, npol, 2, None, scale, swap)
+    out = E.unpack(ctx, d, torch.from_numpy(raw).cuda(), ndat).cpu().numpy()
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("npol", [1, 2])
+def test_unpack_uwb_bitexact(ctx, oracle, npol):
+    torch, E, L = _torch(), _E(), _L()
+    ndat = 8192
+    raw = synth.uwb_bytes(ndat, npol)
+    ref = oracle.unpack_uwb(raw.view(np.int16), ndat, npol)
+    d = E.make_unpack_desc(L.FMT_UWB16, 1, npol, 2)
+    out = E.unpack(ctx, d, torch.from_numpy(raw).cuda(), ndat).cpu().numpy()
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+
+
+# ------------------------------------------------------------------------------------ filterbank
+def _fb_case(ctx, oracle, input_real, input_nchan, npol, C, F, npos, nneg, npart, with_response=True, seed=1,
+             max_npart=0):
+    torch, E = _torch(), _E()
+    rng = np.random.default_rng(seed)
+    nchan = input_nchan * C
+    f = oracle.fb_sizes(input_real, input_nchan, npol, nchan, F, npos, nneg)
+    ndim = 1 if input_real else 2
+    ndat = npart * f.nsamp_step + f.nsamp_overlap
+    x = rng.standard_normal((input_nchan, npol, ndat * ndim)).astype(np.float32)
+    H = None
+    if with_response:
+        ph = rng.uniform(-np.pi, np.pi, (nchan, F))
+        H = np.exp(1j * ph).astype(np.complex64)
+        H[0, 0] = 0
+    ref = oracle.filterbank(f, x, H)
+    eng = E.FilterbankEngine(ctx, input_real, input_nchan, npol, C, F, npos, nneg, H, max_npart)
+    assert eng.info.nsamp_step == f.nsamp_step and eng.info.nkeep == f.nkeep
+    out = eng.perform(torch.from_numpy(x).cuda()).cpu().numpy().view(np.complex64)
+    assert out.shape == ref.shape
+    return synth.relerr(out.view(np.float32), ref.view(np.float32)), eng
+
+
+@pytest.mark.parametrize("case", [
+    # (input_real, input_nchan, npol, C, F, nfilt_pos, nfilt_neg, npart)
+    (1, 1, 2, 16, 64, 5, 6, 5),          # single-pass forward (Nc = 1024)
+    (1, 1, 2, 64, 512, 30, 31, 3),       # two-pass forward (Nc = 32768)
+    (1, 1, 1, 8, 16, 2, 1, 7),           # single pol
+    (0, 1, 2, 32, 128, 9, 10, 4),        # complex input, single-pass
+    (0, 3, 2, 8, 256, 11, 13, 3),        # complex multi-channel input
+    (0, 1, 2, 128, 256, 20, 21, 3),      # complex two-pass (Nc = 32768)
+    (1, 1, 2, 4096, 8, 1, 1, 6),         # cfg2 shape: 4096 x 8
+    (1, 1, 2, 2, 8192, 457, 459, 2),     # F = 8192 inverse (cfg1's channel transform), Nc = 16384
+    (1, 1, 2, 64, 4, 1, 0, 9),           # tiny freq_res
+    (1, 1, 2, 64, 2, 0, 1, 9),
+])
+def test_filterbank_voltages(ctx, oracle, case):
+    err, _ = _fb_case(ctx, oracle, *case)
+    assert err <= TOL, err
+
+
+def test_filterbank_freq_res_1_no_response(ctx, oracle):
+    # freq_res == 1: spectrum copied straight to the output channels (Filterbank.C:621-631)
+    err, _ = _fb_case(ctx, oracle, 1, 1, 2, 64, 1, 0, 0, 20, with_response=False)
+    assert err <= TOL, err
+    err, _ = _fb_case(ctx, oracle, 0, 2, 2, 32, 1, 0, 0, 20, with_response=False)
+    assert err <= TOL, err
+
+
+def test_filterbank_batching_independent(ctx, oracle):
+    # more parts than the internal batch: results must not depend on the batch size
+    e1, _ = _fb_case(ctx, oracle, 1, 1, 2, 16, 64, 5, 6, 11, max_npart=3)
+    e2, _ = _fb_case(ctx, oracle, 1, 1, 2, 16, 64, 5, 6, 11, max_npart=16)
+    assert e1 <= TOL and e2 <= TOL
+
+
+def test_filterbank_cfg1_shape(ctx, oracle):
+    # BASELINE configs[0]: 256 x 8192, M = 457 + 459, r2c 4,194,304 (3 parts)
+    err, eng = _fb_case(ctx, oracle, 1, 1, 2, 256, 8192, 457, 459, 3)
+    assert (eng.info.fft_rows, eng.info.fft_cols) == (2048, 1024)
+    assert err <= TOL, err
+
+
+# ------------------------------------------------------------------------------------ convolution
+@pytest.mark.parametrize("case", [
+    (1, 1, 2, 1, 1024, 40, 41, 4),       # real, in-shared-memory transform
+    (0, 4, 2, 1, 4096, 100, 101, 3),     # complex multi-channel (cfg3-like, small)
+    (0, 1, 2, 1, 16384, 500, 501, 3),    # two-pass inverse (convolution path)
+    (1, 1, 2, 1, 32768, 900, 901, 2),    # real + two-pass inverse
+    (0, 2, 2, 1, 65536, 2536, 2543, 2),  # cfg3's per-channel transform
+])
+def test_convolution_voltages(ctx, oracle, case):
+    torch, E = _torch(), _E()
+    input_real, nchan, npol, _, F, npos, nneg, npart = case
+    rng = np.random.default_rng(3)
+    c = oracle.conv_sizes(input_real, nchan, npol, F, npos, nneg)
+    ndim = 1 if input_real else 2
+    ndat = npart * c.nsamp_step + c.nsamp_overlap
+    x = rng.standard_normal((nchan, npol, ndat * ndim)).astype(np.float32)
+    H = np.exp(1j * rng.uniform(-np.pi, np.pi, (nchan, F))).astype(np.complex64)
+    ref = oracle.convolution(c, x, H)
+    eng = E.FilterbankEngine(ctx, input_real, nchan, npol, 1, F, npos, nneg, H)
+    out = eng.perform(torch.from_numpy(x).cuda()).cpu().numpy().view(np.complex64)
+    assert out.shape == ref.shape
+    err = synth.relerr(out.view(np.float32), ref.view(np.float32))
+    assert err <= TOL, err
+
+
+# ------------------------------------------------------------------------------------ detection
+@pytest.mark.parametrize("state,ndim", [("Intensity", 1), ("PPQQ", 1), ("Coherence", 1), ("Coherence", 2),
+                                        ("Coherence", 4), ("Stokes", 1), ("Stokes", 2), ("Stokes", 4)])
+def test_detection_bitexact(ctx, oracle, state, ndim):
+    torch, E = _torch(), _E()
+    rng = np.random.default_rng(5)
+    nchan, ndat = 5, 3001
+    v = (rng.standard_normal((nchan, 2, ndat)) + 1j * rng.standard_normal((nchan, 2, ndat))).astype(np.complex64)
+    ref = oracle.detect(state, ndim, v)
+    out = E.detect(ctx, state, ndim, torch.from_numpy(v.view(np.float32)).cuda()).cpu().numpy()
+    assert out.shape == ref.shape
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+
+
+def test_detection_inplace_ndim2(ctx, oracle):
+    torch, E, L = _torch(), _E(), _L()
+    rng = np.random.default_rng(6)
+    nchan, ndat = 3, 1000
+    v = (rng.standard_normal((nchan, 2, ndat)) + 1j * rng.standard_normal((nchan, 2, ndat))).astype(np.complex64)
+    ref = oracle.detect("Coherence", 2, v)
+    t = torch.from_numpy(v.view(np.float32).copy()).cuda()
+    import ctypes as C
+    L.check(ctx.lib.b200_detect(ctx.h, L.COHERENCE, 2, C.c_void_p(t.data_ptr()), 2 * ndat, nchan, 2, ndat,
+                                C.c_void_p(t.data_ptr()), 2 * ndat))
+    assert np.array_equal(t.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+
+
+def test_detection_errors(ctx):
+    torch, E, L = _torch(), _E(), _L()
+    t = torch.zeros((1, 1, 64), device="cuda")
+    with pytest.raises(L.B200Error):
+        E.detect(ctx, "Coherence", 2, t)      # npol != 2 (Detection.C:476-489)
+
+
+# ------------------------------------------------------------------------------------ fold
+@pytest.mark.parametrize("ndim,npol", [(1, 1), (1, 4), (2, 2), (4, 1)])
+def test_fold_engine(ctx, oracle, ndim, npol):
+    torch, E = _torch(), _E()
+    rng = np.random.default_rng(7)
+    nchan, nbin, ndat = 6, 128, 40000
+    x = rng.standard_normal((nchan, npol, ndat * ndim)).astype(np.float32) + 3.0
+    phi, pps = 0.37, 1.0 / 777.7
+    fe = E.FoldEngine(ctx, nchan, npol, ndim, nbin)
+    n1 = fe.set_bins(phi, pps, ndat // 2, 0)
+    h1 = fe.get_bin_hits()
+    xt = torch.from_numpy(x).cuda()
+    fe.fold(xt)
+    bp1, hh1, _, phi_mid = oracle.fold_plan(phi, pps, nbin, ndat // 2)
+    assert n1 == ndat // 2 and np.array_equal(h1, hh1)
+    prof = oracle.fold(x, ndim, bp1, nbin)
+    # second call with idat_start (Subint-style slice) and its own phase
+    phi2 = 0.91
+    fe.set_bins(phi2, pps, ndat - ndat // 2, ndat // 2)
+    fe.fold(xt)
+    bp2, hh2, _, _ = oracle.fold_plan(phi2, pps, nbin, ndat - ndat // 2)
+    prof = oracle.fold(x, ndim, bp2, nbin, profile=prof, idat_start=ndat // 2)
+    out = fe.synch()
+    hits, ntot = fe.hits()
+    assert np.array_equal(hits, hh1 + hh2) and ntot == ndat and hits.sum() == ndat
+    assert synth.relerr(out, prof) <= TOL
+    fe.zero()
+    assert not fe.synch().any() and not fe.hits()[0].any()
+
+
+# ------------------------------------------------------------------------------------ fused path
+def _pipeline_case(ctx, oracle, C, F, npos, nneg, npart, state, dndim, nbin, nblock=2, pps=None, from_host=False):
+    torch, E, L = _torch(), _E(), _L()
+    lut, _ = oracle.bittable8()
+    f = oracle.fb_sizes(1, 1, 2, C, F, npos, nneg)
+    ndat = nblock * npart * f.nsamp_step + f.nsamp_overlap
+    ndat = (ndat + 3) // 4 * 4
+    raw = synth.caspsr_bytes(ndat, seed=11)
+    rng = np.random.default_rng(12)
+    H = np.exp(1j * rng.uniform(-np.pi, np.pi, (C, F))).astype(np.complex64)
+    H[0, 0] = 0
+    if pps is None:
+        pps = 1.0 / (0.37 * f.nkeep * npart)
+    phis = [0.123 + 0.31 * b for b in range(nblock)]
+    ppss = [pps * (1 + 1e-6 * b) for b in range(nblock)]
+    op = oracle.make_pipe(0, 1, 2, 1, lut, 0.0, f, None, H, state, dndim, nbin)
+    ref, ref_hits = oracle.pipe_run(op, raw, nblock, npart, phis, ppss, nthread=1)
+    ud = E.make_unpack_desc(L.FMT_CASPSR8, 1, 2, 1, lut)
+    fd, keep = E.make_fb_desc(1, 1, 2, C, F, npos, nneg, H)
+    pipe = E.Pipeline(ctx, ud, fd, keep, state, dndim, nbin)
+    d_raw = torch.from_numpy(raw).cuda()
+    for b in range(nblock):
+        first = b * npart * f.nsamp_step
+        if from_host:
+            nbytes = (npart * f.nsamp_step + f.nsamp_overlap) * 2
+            pipe.execute_host(raw[first * 2: first * 2 + nbytes], npart, phis[b], ppss[b], 0)
+        else:
+            pipe.execute(d_raw, npart, phis[b], ppss[b], first_sample=first)
+    prof, hits, ntot = pipe.synch()
+    assert np.array_equal(hits, ref_hits)
+    assert ntot == nblock * npart * f.nkeep == hits.sum()
+    return synth.relerr(prof, ref)
+
+
+@pytest.mark.parametrize("state,dndim", [("Coherence", 4), ("Coherence", 2), ("Coherence", 1), ("Stokes", 4),
+                                         ("PPQQ", 1), ("Intensity", 1)])
+def test_pipeline_small(ctx, oracle, state, dndim):
+    err = _pipeline_case(ctx, oracle, 16, 256, 20, 21, 5, state, dndim, 64)
+    assert err <= TOL, err
+
+
+def test_pipeline_many_channels_per_cta(ctx, oracle):
+    err = _pipeline_case(ctx, oracle, 256, 16, 2, 3, 8, "Coherence", 4, 32)
+    assert err <= TOL, err
+
+
+def test_pipeline_from_host(ctx, oracle):
+    err = _pipeline_case(ctx, oracle, 16, 256, 20, 21, 5, "Coherence", 4, 64, from_host=True)
+    assert err <= TOL, err
+
+
+def test_pipeline_cfg1(ctx, oracle):
+    # BASELINE configs[0] at full shape: 256 x 8192, 1024 bins, Coherence, 2 blocks x 2 parts
+    err = _pipeline_case(ctx, oracle, 256, 8192, 457, 459, 2, "Coherence", 4, 1024, nblock=2, pps=7.18e-6)
+    assert err <= TOL, err
