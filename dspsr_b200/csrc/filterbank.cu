@@ -503,7 +503,10 @@ __global__ void __launch_bounds__(1024, 1) k_cols_inv(ColsInvArgs a) {
 // ------------------------------------------------------------------------------------------
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
-  B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  cudaFuncAttributes fa;
+  B200_CUDA(cudaFuncGetAttributes(&fa, kernel));
+  B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(bytes - fa.sharedSizeBytes)));
   return B200_OK;
 }
 

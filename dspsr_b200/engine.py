@@ -33,7 +33,10 @@ class Context:
         self.device = device
         self.torch_stream = stream if stream is not None else torch.cuda.current_stream(device)
         h = C.c_void_p()
-        L.check(self.lib.b200_context_create(device, C.c_void_p(self.torch_stream.cuda_stream), C.byref(h)))
+        # torch's default stream has handle 0, which the C ABI reads as "create a private stream";
+        # cudaStreamLegacy (0x1) names the same default stream explicitly.
+        handle = self.torch_stream.cuda_stream or 1
+        L.check(self.lib.b200_context_create(device, C.c_void_p(handle), C.byref(h)))
         self.h = h
 
     def synchronize(self):
