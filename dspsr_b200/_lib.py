@@ -62,6 +62,38 @@ class PipelineDesc(C.Structure):
     ]
 
 
+class Dedispersion(C.Structure):
+    _fields_ = [
+        ("centre_frequency", C.c_double),
+        ("bandwidth", C.c_double),
+        ("dispersion_measure", C.c_double),
+        ("input_nchan", C.c_uint),
+        ("nchan", C.c_uint),
+        ("input_dual_sideband", C.c_int),
+        ("input_dc_centred", C.c_int),
+        ("input_swap", C.c_int),
+        ("frequency_resolution", C.c_uint),
+        ("impulse_pos", C.c_uint),
+        ("impulse_neg", C.c_uint),
+        ("ndat", C.c_uint),
+    ]
+
+
+class Polyco(C.Structure):
+    _fields_ = [
+        ("tmid_day", C.c_int),
+        ("tmid_sec", C.c_double),
+        ("rphase_int", C.c_double),
+        ("rphase_frac", C.c_double),
+        ("f0", C.c_double),
+        ("span_min", C.c_double),
+        ("obsfreq", C.c_double),
+        ("dm", C.c_double),
+        ("ncoef", C.c_int),
+        ("coef", C.c_double * 32),
+    ]
+
+
 class PhaseSegment(C.Structure):
     _fields_ = [
         ("start", C.c_uint64),
@@ -85,6 +117,8 @@ SIGNATURES = {
     "b200_context_synchronize": (_i, [_vp]),
     "b200_context_launch_count": (C.c_ulonglong, [_vp]),
     "b200_context_stream": (_vp, [_vp]),
+    "b200_context_set_timing": (_i, [_vp, _i]),
+    "b200_context_read_timing": (_i, [_vp, C.POINTER(_d), C.POINTER(C.c_ulonglong)]),
     "b200_malloc": (_i, [_vp, _u64, _pvp]),
     "b200_free": (_i, [_vp, _vp]),
     "b200_malloc_host": (_i, [_vp, _u64, _pvp]),
@@ -116,6 +150,13 @@ SIGNATURES = {
     "b200_pipeline_synch": (_i, [_vp, _vp, _vp, C.POINTER(_u64)]),
     "b200_pipeline_zero": (_i, [_vp]),
     "b200_pipeline_fold": (_vp, [_vp]),
+    "b200_bittable8": (_i, [_i, _vp, C.POINTER(_d)]),
+    "b200_dedispersion_prepare": (_i, [C.POINTER(Dedispersion)]),
+    "b200_dedispersion_build": (_i, [C.POINTER(Dedispersion), _vp]),
+    "b200_optimal_fft_length": (C.c_int64, [_u64, _u64]),
+    "b200_polyco_parse": (_i, [C.c_char_p, C.POINTER(Polyco)]),
+    "b200_polyco_phase": (_d, [C.POINTER(Polyco), _i, _i, _d, C.POINTER(_d)]),
+    "b200_polyco_frequency": (_d, [C.POINTER(Polyco), _i, _i, _d]),
     "b200_phase_segments": (C.c_int64, [_d, _d, _u64, C.POINTER(PhaseSegment), _u64, C.POINTER(_d)]),
     "b200_phase_bins_sequential": (None, [_d, _d, _u, _u64, _vp, C.POINTER(_d)]),
 }

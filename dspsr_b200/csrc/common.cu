@@ -92,6 +92,8 @@ int b200_context_create(int device, void* cuda_stream, b200_context** out) {
   b200_context* c = new b200_context();
   c->device = device;
   c->launches = 0;
+  c->timing = false;
+  c->timed = new std::vector<b200::TimedLaunch>();
   if (cuda_stream) {
     c->stream = (cudaStream_t)cuda_stream;
     c->own_stream = false;
@@ -108,6 +110,8 @@ int b200_context_create(int device, void* cuda_stream, b200_context** out) {
 int b200_context_destroy(b200_context* c) {
   if (!c) return B200_OK;
   if (c->own_stream) cudaStreamDestroy(c->stream);
+  for (auto& t : *c->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
+  delete c->timed;
   delete c;
   return B200_OK;
 }
@@ -115,6 +119,28 @@ int b200_context_destroy(b200_context* c) {
 int b200_context_synchronize(b200_context* c) {
   B200_REQUIRE(c, "null context");
   B200_CUDA(cudaStreamSynchronize(c->stream));
+  return B200_OK;
+}
+
+int b200_context_set_timing(b200_context* c, int enable) {
+  B200_REQUIRE(c, "null context");
+  c->timing = enable != 0;
+  return B200_OK;
+}
+
+int b200_context_read_timing(b200_context* c, double* ms, unsigned long long* count) {
+  B200_REQUIRE(c && ms && count, "b200_context_read_timing: null argument");
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < b200::KC_COUNT; k++) { ms[k] = 0.0; count[k] = 0; }
+  for (auto& t : *c->timed) {
+    float e = 0.f;
+    B200_CUDA(cudaEventElapsedTime(&e, t.start, t.stop));
+    ms[t.kc] += e;
+    count[t.kc]++;
+    cudaEventDestroy(t.start);
+    cudaEventDestroy(t.stop);
+  }
+  c->timed->clear();
   return B200_OK;
 }
 

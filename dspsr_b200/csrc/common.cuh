@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "../../include/b200dsp.h"
 #include "fft_core.cuh"
@@ -28,12 +29,42 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     }                                         \
   } while (0)
 
+// per-kernel-class device timing (bench.py's roofline): events are recorded around every launch
+// of a class while timing is enabled and summed at read time.
+enum KernelClass { KC_COLS_FWD = 0, KC_ROWS = 1, KC_INV = 2, KC_BINS = 3, KC_OTHER = 4, KC_COUNT = 5 };
+struct TimedLaunch {
+  int kc;
+  cudaEvent_t start, stop;
+};
 struct Context {
   int device;
   cudaStream_t stream;
   int sm_count;
   int max_smem_optin;
   unsigned long long launches;   // kernels launched through this context (bench's gpu_launches)
+  bool timing;
+  std::vector<TimedLaunch>* timed;
+};
+
+// RAII helper: brackets one kernel launch with events when timing is on, and counts it
+struct LaunchScope {
+  Context* c;
+  cudaEvent_t stop;
+  LaunchScope(Context* ctx, int kc) : c(ctx), stop(nullptr) {
+    c->launches++;
+    if (c->timing) {
+      TimedLaunch t;
+      t.kc = kc;
+      cudaEventCreate(&t.start);
+      cudaEventCreate(&t.stop);
+      cudaEventRecord(t.start, c->stream);
+      stop = t.stop;
+      c->timed->push_back(t);
+    }
+  }
+  ~LaunchScope() {
+    if (stop) cudaEventRecord(stop, c->stream);
+  }
 };
 
 static inline unsigned ilog2(uint64_t x) {

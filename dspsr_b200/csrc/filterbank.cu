@@ -542,9 +542,9 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
       dim3 grid(pl->Q / B, nb * nblk1);
       dim3 block((pl->P / 16) * B);
       size_t smem = size_t(pl->P) * B * sizeof(float2);
+      LaunchScope ls(ctx, KC_COLS_FWD);
       if (src.kind == SRC_F32) k_cols_fwd<SRC_F32><<<grid, block, smem, st>>>(a);
       else k_cols_fwd<SRC_CASPSR8><<<grid, block, smem, st>>>(a);
-      ctx->launches++;
     }
     // ---- K2 ----
     {
@@ -558,6 +558,7 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
       dim3 grid(split ? (pl->P / 2) / pl->G : pl->P / pl->G, nb * nblk1);
       dim3 block(nslots * T);
       size_t smem = size_t(nslots) * pl->Q * sizeof(float2);
+      LaunchScope ls(ctx, KC_ROWS);
       if (pl->Q >= 16) {
         if (split) {
           if (pl->conv_path) k_rows<true, true, 16><<<grid, block, smem, st>>>(a);
@@ -570,7 +571,6 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
         if (split) k_rows<true, false, 0><<<grid, block, smem, st>>>(a);
         else k_rows<false, false, 0><<<grid, block, smem, st>>>(a);
       }
-      ctx->launches++;
     }
     // ---- K3 ----
     FbSink sk = sink;
@@ -589,10 +589,10 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
       dim3 grid(pl->Q / Bi, nb * nchan_in);
       dim3 block(npol * (pl->P / 16) * Bi);
       size_t smem = size_t(npol) * pl->P * Bi * sizeof(float2) + (sk.kind == EPI_FOLD ? size_t(sk.nbin) * nprod * 4 : 0);
+      LaunchScope ls(ctx, KC_INV);
       if (sk.kind == EPI_VOLT) k_cols_inv<EPI_VOLT><<<grid, block, smem, st>>>(a);
       else if (sk.kind == EPI_DETECT) k_cols_inv<EPI_DETECT><<<grid, block, smem, st>>>(a);
       else k_cols_inv<EPI_FOLD><<<grid, block, smem, st>>>(a);
-      ctx->launches++;
     } else {
       ChanArgs a;
       a.Z = pl->scratchZ; a.twF = pl->twF.tw;
@@ -625,6 +625,7 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
       }
       dim3 grid(pl->nchan_out / CB, nb, npol / npol_cta);
       dim3 block(CB * npol_cta * T);
+      LaunchScope ls(ctx, KC_INV);
 #define B200_K3(E)                                                                          \
   if (sk.kind == EPI_VOLT) k_chan_inv<E, EPI_VOLT><<<grid, block, smem, st>>>(a);            \
   else if (sk.kind == EPI_DETECT) k_chan_inv<E, EPI_DETECT><<<grid, block, smem, st>>>(a);   \
@@ -637,7 +638,6 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
         default: B200_K3(0) break;
       }
 #undef B200_K3
-      ctx->launches++;
     }
     B200_CUDA(cudaGetLastError());
   }

@@ -271,6 +271,7 @@ int b200_unpack(b200_context* cctx, const b200_unpack_desc* d, const void* d_raw
     B200_CUDA(cudaMallocAsync(&d_lut, 256 * sizeof(float), ctx->stream));
     B200_CUDA(cudaMemcpyAsync(d_lut, d->lut, 256 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   }
+  LaunchScope ls(ctx, KC_OTHER);
   switch (d->format) {
     case B200_FMT_CASPSR8: {
       B200_REQUIRE(d->nchan == 1 && d->npol == 2 && d->ndim == 1, "CASPSR unpacker: nchan=1 npol=2 ndim=1 only");
@@ -306,7 +307,6 @@ int b200_unpack(b200_context* cctx, const b200_unpack_desc* d, const void* d_raw
       set_error("b200_unpack: unknown format %d", d->format);
       return B200_ERR_INVALID;
   }
-  ctx->launches++;
   if (d_lut) B200_CUDA(cudaFreeAsync(d_lut, ctx->stream));
   B200_CUDA(cudaGetLastError());
   return B200_OK;
@@ -335,8 +335,8 @@ int b200_detect(b200_context* cctx, int state, unsigned ndim_out, const float* d
   a.nprod = state == B200_INTENSITY ? 1 : state == B200_PPQQ ? npol : 4;
   const unsigned threads = 256;
   unsigned gx = (unsigned)std::min<uint64_t>((ndat + threads - 1) / threads, 4096);
+  LaunchScope ls(ctx, KC_OTHER);
   k_detect<<<dim3(gx, nchan), threads, 0, ctx->stream>>>(a);
-  ctx->launches++;
   B200_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -422,9 +422,11 @@ int b200_fold_set_bins(b200_fold* f, double phi, double pps, uint64_t ndat, uint
   B200_CUDA(cudaMemsetAsync(f->d_hits_last, 0, f->nbin * sizeof(unsigned), ctx->stream));
   const unsigned threads = 256;
   unsigned grid = (unsigned)std::min<uint64_t>((ndat + threads - 1) / threads, ctx->sm_count * 8);
-  k_expand_bins<<<grid, threads, 0, ctx->stream>>>(f->d_seg, (unsigned)nseg, ndat, f->nbin, f->d_bins, f->d_hits_last,
-                                                  f->d_hits_total);
-  ctx->launches++;
+  {
+    LaunchScope ls(ctx, KC_BINS);
+    k_expand_bins<<<grid, threads, 0, ctx->stream>>>(f->d_seg, (unsigned)nseg, ndat, f->nbin, f->d_bins, f->d_hits_last,
+                                                    f->d_hits_total);
+  }
   f->ndat_total += ndat;
   B200_CUDA(cudaGetLastError());
   return B200_OK;
@@ -456,10 +458,10 @@ int b200_fold_fold(b200_fold* f, const float* d_in, uint64_t in_span) {
   a.smem_bins = smem <= 48 * 1024 ? 1 : 0;
   if (!a.smem_bins) smem = 0;
   dim3 grid(gx, nplane);
+  LaunchScope ls(ctx, KC_OTHER);
   if (f->ndim == 4) k_fold<4><<<grid, threads, smem, ctx->stream>>>(a);
   else if (f->ndim == 2) k_fold<2><<<grid, threads, smem, ctx->stream>>>(a);
   else k_fold<1><<<grid, threads, smem, ctx->stream>>>(a);
-  ctx->launches++;
   B200_CUDA(cudaGetLastError());
   return B200_OK;
 }

@@ -42,6 +42,17 @@ class Context:
     def synchronize(self):
         L.check(self.lib.b200_context_synchronize(self.h))
 
+    def set_timing(self, enable):
+        L.check(self.lib.b200_context_set_timing(self.h, int(enable)))
+
+    def read_timing(self):
+        """-> ({class: ms}, {class: launches}) since the last read; synchronises the stream."""
+        ms = (C.c_double * 5)()
+        n = (C.c_ulonglong * 5)()
+        L.check(self.lib.b200_context_read_timing(self.h, ms, n))
+        names = ["cols_fwd", "rows", "inverse", "bins", "other"]
+        return {k: ms[i] for i, k in enumerate(names)}, {k: int(n[i]) for i, k in enumerate(names)}
+
     @property
     def launches(self):
         return int(self.lib.b200_context_launch_count(self.h))

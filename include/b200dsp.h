@@ -51,6 +51,12 @@ int b200_context_synchronize(b200_context* ctx);
 /* kernels launched through this context so far (bench.py's gpu_launches) */
 unsigned long long b200_context_launch_count(const b200_context* ctx);
 void* b200_context_stream(const b200_context* ctx);
+/* Per-kernel-class device timing for roofline reports: while enabled, every launch is bracketed
+ * by CUDA events on the context's stream.  read_timing synchronises and returns, per class
+ * (0 forward column pass, 1 row pass, 2 inverse pass + epilogue, 3 bin plan, 4 other), the summed
+ * milliseconds and launch counts since the last read (arrays of 5). */
+int b200_context_set_timing(b200_context* ctx, int enable);
+int b200_context_read_timing(b200_context* ctx, double* ms, unsigned long long* count);
 
 int b200_malloc(b200_context* ctx, uint64_t nbytes, void** d_ptr);
 int b200_free(b200_context* ctx, void* d_ptr);
@@ -228,6 +234,54 @@ int64_t b200_phase_segments(double phi, double phase_per_sample, uint64_t ndat, 
 /* The plain sequential recurrence (reference behaviour), for hosts and tests. */
 void b200_phase_bins_sequential(double phi, double phase_per_sample, unsigned nbin, uint64_t ndat,
                                 unsigned* bins, double* phi_end);
+
+/* ---------------------------------------------------------------------------------------
+ * Host-side restatements of what the reference computes on the CPU around the engines
+ * (no device work).  Inside a real dspsr tree these come from dspsr / PSRCHIVE; they are
+ * exported for stand-alone hosts (bench.py, the Python handles, host/b200_demo.cpp).
+ * ------------------------------------------------------------------------------------- */
+
+/* dsp::BitTable(8, TwosComplement|OffsetBinary): 256-entry value table and get_scale()
+ * (Kernel/Classes/BitTable.C:121-218). */
+int b200_bittable8(int twos_complement, float* lut256, double* scale);
+
+/* dsp::Dedispersion (Signal/General/Dedispersion.C) + Response::match (Response.C:132-181). */
+typedef struct {
+  double centre_frequency;       /* MHz */
+  double bandwidth;              /* MHz, signed */
+  double dispersion_measure;     /* pc cm^-3 */
+  unsigned input_nchan;          /* channels of the input Observation */
+  unsigned nchan;                /* channels of the response = output channels */
+  int input_dual_sideband;       /* Observation::get_dual_sideband (Observation.C:80-87) */
+  int input_dc_centred;
+  int input_swap;
+  unsigned frequency_resolution; /* 0: Response::set_optimal_ndat; else the -x nfft override */
+  /* filled by b200_dedispersion_prepare: */
+  unsigned impulse_pos, impulse_neg, ndat;
+} b200_dedispersion;
+
+/* Dedispersion::prepare (Dedispersion.C:216-248) and the ndat choice of Dedispersion::build
+ * (:296-308) via optimal_fft_length (optimize_fft.c:63-127). */
+int b200_dedispersion_prepare(b200_dedispersion* d);
+/* Dedispersion::build (:310-331,478-556) then Response::match and the DC zap (:278):
+ * h_response receives nchan*ndat complex floats in the order the FFT produces them. */
+int b200_dedispersion_build(const b200_dedispersion* d, float* h_response);
+int64_t b200_optimal_fft_length(uint64_t nbadperfft, uint64_t nfft_max);
+
+/* TEMPO polyco block (what Pulsar::Predictor::phase/frequency evaluate for Fold.C:943-958). */
+typedef struct {
+  int tmid_day;
+  double tmid_sec;
+  double rphase_int, rphase_frac;
+  double f0, span_min, obsfreq, dm;
+  int ncoef;
+  double coef[32];
+} b200_polyco;
+
+int b200_polyco_parse(const char* text, b200_polyco* pc);
+/* fractional turns in [0,1) at MJD (day, sec, frac); *turns (nullable) gets the integer part */
+double b200_polyco_phase(const b200_polyco* pc, int day, int sec, double frac, double* turns);
+double b200_polyco_frequency(const b200_polyco* pc, int day, int sec, double frac);
 
 #ifdef __cplusplus
 }
