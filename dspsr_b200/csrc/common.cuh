@@ -149,6 +149,51 @@ __device__ __forceinline__ void block_fft(unsigned N, unsigned j, unsigned T, co
   }
 }
 
+// Compile-time-sized block FFT: N, EPT and therefore every radix / stride are constants, the
+// stage loop is unrolled by template recursion.  Same contract as block_fft.
+template <int EPT, bool INV, unsigned N, unsigned NS, typename Map, typename StoreF>
+__device__ __forceinline__ void block_fft_ct_stages(float2* v, unsigned j, const Map& map, float2* smem,
+                                                    const float2* __restrict__ tw, StoreF store) {
+  constexpr unsigned T = N / EPT;
+  constexpr unsigned REM = N / NS;
+  constexpr int R = REM >= (unsigned)EPT ? EPT : (int)REM;
+  constexpr int NB = EPT / R;
+  constexpr bool last = (REM == (unsigned)R);
+  stage_compute_ct<EPT, R, INV, N, NS>(v, j, tw);
+  if constexpr (last) {
+#pragma unroll
+    for (int q = 0; q < NB; q++)
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const unsigned b = j + q * T, k = b & (NS - 1);
+        store((b - k) * R + k + r * NS, v[q + r * NB]);
+      }
+  } else {
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NB; q++)
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const unsigned b = j + q * T, k = b & (NS - 1);
+        smem[map((b - k) * R + k + r * NS)] = v[q + r * NB];
+      }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < EPT; e++) v[e] = smem[map(j + e * T)];
+    block_fft_ct_stages<EPT, INV, N, NS * R>(v, j, map, smem, tw, store);
+  }
+}
+
+template <int EPT, bool INV, unsigned N, typename Map, typename LoadF, typename StoreF>
+__device__ __forceinline__ void block_fft_ct(unsigned j, const Map& map, float2* smem,
+                                             const float2* __restrict__ tw, LoadF load, StoreF store) {
+  constexpr unsigned T = N / EPT;
+  float2 v[EPT];
+#pragma unroll
+  for (int e = 0; e < EPT; e++) v[e] = load(j + e * T);
+  block_fft_ct_stages<EPT, INV, N, 1>(v, j, map, smem, tw, store);
+}
+
 #endif  // __CUDACC__
 
 }  // namespace b200

@@ -235,6 +235,135 @@ B200_HD RadixPlan make_radix_plan(unsigned N, int EPT) {
   return p;
 }
 
+// ---- compile-time-sized variant ------------------------------------------------------------
+// multiply by W32^m (forward) / W32^-m (inverse); m is a compile-time constant after unrolling,
+// so the switch folds to one constant multiply (or a free rotation for m = 0, 8, 16, 24).
+template <bool INV> B200_HD float2 mul_w32(float2 a, int m) {
+  switch (m & 31) {
+    case 0: return a;
+    case 8: return crot<INV>(a);
+    case 16: return make_float2(-a.x, -a.y);
+    case 24: return crot<!INV>(a);
+    case 1: return cmulc<INV>(a, B200_COS_PI_16, B200_SIN_PI_16);
+    case 2: return cmulc<INV>(a, B200_COS_PI_8, B200_SIN_PI_8);
+    case 3: return cmulc<INV>(a, B200_COS_3PI_16, B200_SIN_3PI_16);
+    case 4: return cmulc<INV>(a, B200_SQRT1_2, B200_SQRT1_2);
+    case 5: return cmulc<INV>(a, B200_SIN_3PI_16, B200_COS_3PI_16);
+    case 6: return cmulc<INV>(a, B200_SIN_PI_8, B200_COS_PI_8);
+    case 7: return cmulc<INV>(a, B200_SIN_PI_16, B200_COS_PI_16);
+    case 9: return cmulc<INV>(a, -B200_SIN_PI_16, B200_COS_PI_16);
+    case 10: return cmulc<INV>(a, -B200_SIN_PI_8, B200_COS_PI_8);
+    case 11: return cmulc<INV>(a, -B200_SIN_3PI_16, B200_COS_3PI_16);
+    case 12: return cmulc<INV>(a, -B200_SQRT1_2, B200_SQRT1_2);
+    case 13: return cmulc<INV>(a, -B200_COS_3PI_16, B200_SIN_3PI_16);
+    case 14: return cmulc<INV>(a, -B200_COS_PI_8, B200_SIN_PI_8);
+    case 15: return cmulc<INV>(a, -B200_COS_PI_16, B200_SIN_PI_16);
+    case 17: return cmulc<INV>(a, -B200_COS_PI_16, -B200_SIN_PI_16);
+    case 18: return cmulc<INV>(a, -B200_COS_PI_8, -B200_SIN_PI_8);
+    case 19: return cmulc<INV>(a, -B200_COS_3PI_16, -B200_SIN_3PI_16);
+    case 20: return cmulc<INV>(a, -B200_SQRT1_2, -B200_SQRT1_2);
+    case 21: return cmulc<INV>(a, -B200_SIN_3PI_16, -B200_COS_3PI_16);
+    case 22: return cmulc<INV>(a, -B200_SIN_PI_8, -B200_COS_PI_8);
+    case 23: return cmulc<INV>(a, -B200_SIN_PI_16, -B200_COS_PI_16);
+    case 25: return cmulc<INV>(a, B200_SIN_PI_16, -B200_COS_PI_16);
+    case 26: return cmulc<INV>(a, B200_SIN_PI_8, -B200_COS_PI_8);
+    case 27: return cmulc<INV>(a, B200_SIN_3PI_16, -B200_COS_3PI_16);
+    case 28: return cmulc<INV>(a, B200_SQRT1_2, -B200_SQRT1_2);
+    case 29: return cmulc<INV>(a, B200_COS_3PI_16, -B200_SIN_3PI_16);
+    case 30: return cmulc<INV>(a, B200_COS_PI_8, -B200_SIN_PI_8);
+    default: return cmulc<INV>(a, B200_COS_PI_16, -B200_SIN_PI_16);   // 31
+  }
+}
+
+// Radix-R butterfly with the stage twiddles W^(r*k) folded into a (R/A) x A decomposition so
+// that only log-many runtime twiddles are live:  r = A*n1 + n2  (n1 < R/A... see below).
+//   R = 16: 4 x 4,  runtime twiddles w1,w2,w3 (on the second axis) and w4,w8,w12 (first axis)
+//   R = 32: 4 x 8,  runtime twiddles w1..w7 and w8,w16,w24
+// TW = false skips the runtime twiddles (first stage, Ns = 1).  tw[m] = exp(-2 pi i m / NT);
+// kk = k * NT/(Ns*R) is the table index of W^(1*k).
+template <int R, bool INV, bool TW>
+B200_HD void dft_tw(float2* u, const float2* __restrict__ tw, unsigned kk) {
+  if constexpr (R <= 8) {
+    if (TW) apply_stage_twiddles<R, INV>(u, tw, kk);
+    dftR<R, INV>(u);
+  } else {
+    constexpr int A = R / 4;        // second-axis length (4 or 8); first axis has 4 points
+    // first axis: r = A*n1 + n2, twiddle W^(A*n1*k)
+    float2 wa1, wa2, wa3;
+    if (TW) {
+      wa1 = tw_get<INV>(tw, A * kk);
+      wa2 = tw_get<INV>(tw, 2 * A * kk);
+      wa3 = cmul(wa1, wa2);
+    }
+#pragma unroll
+    for (int n2 = 0; n2 < A; n2++) {
+      float2 a = u[n2], b = u[A + n2], c = u[2 * A + n2], d = u[3 * A + n2];
+      if (TW) { b = cmul(b, wa1); c = cmul(c, wa2); d = cmul(d, wa3); }
+      dft4<INV>(a, b, c, d);
+      u[n2] = a; u[A + n2] = b; u[2 * A + n2] = c; u[3 * A + n2] = d;   // now y[n2][k1] at u[k1*A + n2]
+    }
+    // second axis twiddles: y[n2][k1] *= W^(n2*k) * W_R^(n2*k1)
+    float2 w[A];
+    if (TW) {
+      w[1] = tw_get<INV>(tw, kk);
+      w[2] = tw_get<INV>(tw, 2 * kk);
+      w[3] = cmul(w[1], w[2]);
+      if (A == 8) {
+        w[4] = tw_get<INV>(tw, 4 * kk);
+        w[5] = cmul(w[1], w[4]);
+        w[6] = cmul(w[2], w[4]);
+        w[7] = cmul(w[3], w[4]);
+      }
+    }
+#pragma unroll
+    for (int n2 = 1; n2 < A; n2++) {
+#pragma unroll
+      for (int k1 = 0; k1 < 4; k1++) {
+        float2 y = u[k1 * A + n2];
+        if (TW) y = cmul(y, w[n2]);
+        y = mul_w32<INV>(y, (32 / R) * n2 * k1);
+        u[k1 * A + n2] = y;
+      }
+    }
+    // second axis DFTs (length A) for every k1; output index k = k1 + 4*k2
+    float2 o[R];
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++) {
+      float2 t[A];
+#pragma unroll
+      for (int n2 = 0; n2 < A; n2++) t[n2] = u[k1 * A + n2];
+      dftR<A, INV>(t);
+#pragma unroll
+      for (int k2 = 0; k2 < A; k2++) o[k1 + 4 * k2] = t[k2];
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) u[r] = o[r];
+  }
+}
+
+// One Stockham stage with every size a compile-time constant (N points, EPT per thread,
+// sub-transform length NS): same contract as stage_compute.
+template <int EPT, int R, bool INV, unsigned N, unsigned NS>
+B200_HD void stage_compute_ct(float2* v, unsigned j, const float2* __restrict__ tw) {
+  constexpr int NB = EPT / R;
+  constexpr unsigned T = N / EPT;
+  constexpr unsigned stride = N / (NS * R);
+#pragma unroll
+  for (int q = 0; q < NB; q++) {
+    float2 u[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) u[r] = v[q + r * NB];
+    if (NS > 1) {
+      const unsigned k = (j + q * T) & (NS - 1);
+      dft_tw<R, INV, true>(u, tw, k * stride);
+    } else {
+      dft_tw<R, INV, false>(u, tw, 0);
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) v[q + r * NB] = u[r];
+  }
+}
+
 // ---- shared-memory index maps ----------------------------------------------------------------
 // ROWS: one array per transform, XOR swizzle keeps the stride-R writes of the first stage
 // conflict free for 64-bit accesses (16 lanes per phase).

@@ -30,6 +30,17 @@ __device__ __forceinline__ float2 ld_nc_f2(const float2* p) {
   return r;
 }
 
+// Block FFT of compile-time size NCT (fully unrolled stages, EPT points per thread) or, when
+// NCT == 0, of run-time size N (generic path).
+template <int EPT, bool INV, unsigned NCT, typename Map, typename LoadF, typename StoreF>
+__device__ __forceinline__ void fft_any(unsigned N, unsigned j, unsigned T, const Map& map, float2* smem,
+                                        const float2* __restrict__ tw, LoadF load, StoreF store) {
+  if constexpr (NCT != 0) block_fft_ct<EPT, INV, NCT>(j, map, smem, tw, load, store);
+  else block_fft<EPT, INV>(N, j, T, map, smem, tw, N, load, store);
+}
+// log2 of the first radix = swizzle shift of the shared-memory maps
+template <int EPT> struct SwzShift { static constexpr unsigned value = EPT == 32 ? 5 : 4; };
+
 // ------------------------------------------------------------------------------------------
 // K1: forward column pass
 // ------------------------------------------------------------------------------------------
@@ -45,14 +56,15 @@ struct ColsArgs {
   uint64_t part0;
 };
 
-template <int SRC>
-__global__ void __launch_bounds__(1024, 1) k_cols_fwd(ColsArgs a) {
+template <int SRC, int EPT, unsigned PCT>
+__global__ void __launch_bounds__(PCT ? 512 : 1024, 1) k_cols_fwd(ColsArgs a) {
   extern __shared__ float2 smem[];
   __shared__ float s_lut[256];
+  const unsigned P = PCT ? PCT : a.P;
   const unsigned B = 1u << a.lb;
   const unsigned b = threadIdx.x & (B - 1);
   const unsigned j = threadIdx.x >> a.lb;
-  const unsigned T = a.P >> 4;
+  const unsigned T = P / EPT;
   const unsigned n2 = blockIdx.x * B + b;
   const unsigned blk = blockIdx.y;
   const unsigned pol = blk % a.npol;
@@ -72,7 +84,7 @@ __global__ void __launch_bounds__(1024, 1) k_cols_fwd(ColsArgs a) {
     raw = static_cast<const unsigned char*>(a.src);
     samp0 = part * a.step + 2ull * n2;
   }
-  MapCols map{b, a.lb, 4};
+  MapCols map{b, a.lb, SwzShift<EPT>::value};
   auto load = [&](unsigned n1) -> float2 {
     if (SRC == SRC_F32) {
       return ld_nc_f2(fsrc + uint64_t(n1) * a.Q);
@@ -89,7 +101,7 @@ __global__ void __launch_bounds__(1024, 1) k_cols_fwd(ColsArgs a) {
     if (a.Q > 1) v = cmul(v, big_twiddle<false>(a.blo, a.bhi, n2 * k1));
     dst[uint64_t(k1) * a.Q] = v;
   };
-  block_fft<16, false>(a.P, j, T, map, smem, a.twP, a.P, load, store);
+  fft_any<EPT, false, PCT>(P, j, T, map, smem, a.twP, load, store);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -107,18 +119,19 @@ struct RowsArgs {
   unsigned P, Q, G, Nc, npol, nchan_in;
 };
 
-template <bool SPLIT, bool CONV, int EPT>
-__global__ void __launch_bounds__(1024, 1) k_rows(RowsArgs a) {
+template <bool SPLIT, bool CONV, int EPT, unsigned QCT>
+__global__ void __launch_bounds__(QCT ? 512 : 1024, 1) k_rows(RowsArgs a) {
   extern __shared__ float2 smem[];
-  const unsigned T = EPT ? a.Q / (EPT ? EPT : 1) : 1;
+  const unsigned Q = QCT ? QCT : a.Q;
+  const unsigned T = EPT ? Q / (EPT ? EPT : 1) : 1;
+  constexpr unsigned SH = SwzShift<EPT>::value;
   const unsigned slot = threadIdx.x / T;
   const unsigned j = threadIdx.x % T;
   const unsigned G = a.G;
   const unsigned tile = blockIdx.x;
   const unsigned blk = blockIdx.y;
   const unsigned ic = (blk / a.npol) % a.nchan_in;
-  const unsigned P = a.P, Q = a.Q, Nc = a.Nc;
-  const unsigned nslots = SPLIT ? 2 * G : G;
+  const unsigned P = a.P, Nc = a.Nc;
 
   auto slot_row = [&](unsigned s) -> unsigned {
     unsigned g = s % G;
@@ -128,7 +141,7 @@ __global__ void __launch_bounds__(1024, 1) k_rows(RowsArgs a) {
   };
   auto smap = [&](unsigned s, unsigned idx) -> unsigned {
     if (!EPT) return s;
-    return s * Q + ((idx ^ ((idx >> 4) & 15u)) ^ (((s % G) * 2u) & 15u));
+    return s * Q + ((idx ^ ((idx >> SH) & 15u)) ^ (((s % G) * 2u) & 15u));
   };
 
   const unsigned row = slot_row(slot);
@@ -136,11 +149,11 @@ __global__ void __launch_bounds__(1024, 1) k_rows(RowsArgs a) {
 
   // ---- phase 1: forward row FFT into shared memory (natural order) ----
   if (EPT) {
-    MapRows map{slot * Q, 4, ((slot % G) * 2u) & 15u};
+    MapRows map{slot * Q, SH, ((slot % G) * 2u) & 15u};
     const float2* src = Ablk + uint64_t(row) * Q;
     auto load = [&](unsigned idx) -> float2 { return src[idx]; };
     auto store = [&](unsigned idx, float2 v) { smem[map(idx)] = v; };
-    block_fft<(EPT ? EPT : 2), false>(Q, j, T, map, smem, a.twQ, Q, load, store);
+    fft_any<(EPT ? EPT : 2), false, QCT>(Q, j, T, map, smem, a.twQ, load, store);
   } else {
     smem[slot] = Ablk[row];
   }
@@ -208,12 +221,12 @@ __global__ void __launch_bounds__(1024, 1) k_rows(RowsArgs a) {
     __syncthreads();
     float2* dst = Ablk + uint64_t(row) * Q;
     if (EPT) {
-      MapRows map{slot * Q, 4, ((slot % G) * 2u) & 15u};
+      MapRows map{slot * Q, SH, ((slot % G) * 2u) & 15u};
       auto load = [&](unsigned idx) -> float2 { return smem[map(idx)]; };
       auto store = [&](unsigned m2, float2 v) {
         dst[m2] = cmul(v, big_twiddle<true>(a.blo, a.bhi, row * m2));
       };
-      block_fft<(EPT ? EPT : 2), true>(Q, j, T, map, smem, a.twQ, Q, load, store);
+      fft_any<(EPT ? EPT : 2), true, QCT>(Q, j, T, map, smem, a.twQ, load, store);
     } else {
       dst[0] = smem[slot];
     }
@@ -262,13 +275,12 @@ struct ChanArgs {
   unsigned nfilt_pos, nkeep;
   uint64_t part0;
   FbSink sink;
-  unsigned smem_bins;   // 1: phase bins accumulate in shared memory (CB*nbin*nprod floats)
 };
 
-template <int EPT, int EPI>
-__global__ void __launch_bounds__(1024, 1) k_chan_inv(ChanArgs a) {
+template <int EPT, int EPI, unsigned FCT>
+__global__ void __launch_bounds__(FCT ? 512 : 1024, 1) k_chan_inv(ChanArgs a) {
   extern __shared__ float2 smem[];
-  const unsigned F = a.F;
+  const unsigned F = FCT ? FCT : a.F;
   const unsigned T = EPT ? F / (EPT ? EPT : 1) : 1;
   const unsigned f = threadIdx.x / T;              // transform within the CTA
   const unsigned j = threadIdx.x % T;
@@ -281,19 +293,14 @@ __global__ void __launch_bounds__(1024, 1) k_chan_inv(ChanArgs a) {
   const unsigned partl = blockIdx.y;
   const uint64_t part = a.part0 + partl;
   const unsigned blk = (partl * a.nchan_in + ic) * a.npol + pol;
-  const unsigned sh = 4;
+  constexpr unsigned sh = SwzShift<EPT>::value;
   auto fmap = [&](unsigned ff, unsigned idx) -> unsigned {
     if (!EPT) return ff;
     if (F < 16) return ff * F + idx;
     return ff * F + (idx ^ ((idx >> sh) & 15u));
   };
 
-  float* bins = reinterpret_cast<float*>(smem + uint64_t(NF) * F);
   const unsigned nprod = (EPI == EPI_VOLT) ? 0 : state_nprod(a.sink.state, a.npol);
-  if (EPI == EPI_FOLD && a.smem_bins) {
-    const unsigned nb = a.CB * a.sink.nbin * nprod;
-    for (unsigned i = threadIdx.x; i < nb; i += blockDim.x) bins[i] = 0.f;
-  }
 
   const float2* src = a.Z + uint64_t(blk) * a.Nc + uint64_t(csub) * F;
   if (EPT) {
@@ -301,7 +308,7 @@ __global__ void __launch_bounds__(1024, 1) k_chan_inv(ChanArgs a) {
       MapRows map{f * F, sh, 0};
       auto load = [&](unsigned idx) -> float2 { return ld_nc_f2(src + idx); };
       auto store = [&](unsigned idx, float2 v) { smem[map(idx)] = v; };
-      block_fft<(EPT ? EPT : 2), true>(F, j, T, map, smem, a.twF, F, load, store);
+      fft_any<(EPT ? EPT : 2), true, FCT>(F, j, T, map, smem, a.twF, load, store);
     } else {
       // F = 2, 4, 8: one thread per transform, no shared-memory exchange needed
       MapRows map{f * F, 0, 0};
@@ -347,54 +354,72 @@ __global__ void __launch_bounds__(1024, 1) k_chan_inv(ChanArgs a) {
     return;
   }
 
-  // EPI_FOLD: every thread walks L consecutive samples, summing while the bin is unchanged
-  // (same order as the reference's per-bin sequential +=, Fold.C:844-852), then adds the run
-  // to the CTA's shared bins (or straight to the global profile when they do not fit).
+  // EPI_FOLD.  Every thread walks L consecutive samples of one channel, summing sequentially while
+  // the phase bin is unchanged (the order of the reference's per-bin +=, Fold.C:844-852).  A run
+  // that ends inside the chunk is added to the profile at once; the chunk's last run is first
+  // combined across the warp -- neighbouring lanes hold neighbouring chunks, so equal (channel,bin)
+  // keys are contiguous and a shuffle-based segmented sum leaves one add per key and warp.  All
+  // adds go to the global profile with RED.ADD.F32 (no shared-memory float atomics: those compile
+  // to CAS loops).
   {
-    const unsigned L = 8;
+    const unsigned nbin = a.sink.nbin;
+    const unsigned nthreads = blockDim.x;
+    unsigned L = (a.CB * nkeep + nthreads - 1) / nthreads;
+    L = (L + 3u) & ~3u;
+    if (L < 4) L = 4;
     const unsigned nchunk = (nkeep + L - 1) / L;
     const unsigned total = a.CB * nchunk;
-    const unsigned nbin = a.sink.nbin;
     const unsigned* plan = a.sink.bins + partl * uint64_t(nkeep);
-    for (unsigned it = threadIdx.x; it < total; it += blockDim.x) {
-      const unsigned c = it / nchunk, m0 = (it % nchunk) * L;
-      const unsigned m1 = min(nkeep, m0 + L);
+    float* prof0 = a.sink.profile + uint64_t(ch0) * nbin * nprod;
+    const unsigned lane = threadIdx.x & 31u;
+    auto red_add = [&](unsigned key, const float* acc) {
+      // key = c*nbin + bin; profile layout per channel [npol'][nbin][ndim']
+      const unsigned c = key / nbin, bin = key - c * nbin;
+      float* base = prof0 + uint64_t(c) * nbin * nprod;
+      for (unsigned pr = 0; pr < nprod; pr++)
+        atomicAdd(base + (uint64_t(pr / dndim) * nbin + bin) * dndim + pr % dndim, acc[pr]);
+    };
+    const unsigned niter = (total + nthreads - 1) / nthreads;
+    for (unsigned itr = 0; itr < niter; itr++) {
+      const unsigned it = itr * nthreads + threadIdx.x;
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      unsigned cur = 0xffffffffu;
-      float* dstbase = a.smem_bins ? bins + uint64_t(c) * nbin * nprod
-                                   : a.sink.profile + uint64_t(ch0 + c) * nbin * nprod;
-      auto flush = [&]() {
-        if (cur == 0xffffffffu) return;
-        for (unsigned pr = 0; pr < nprod; pr++) {
-          // profile layout [npol'][nbin][ndim']
-          float* d = dstbase + (uint64_t(pr / dndim) * nbin + cur) * dndim + pr % dndim;
-          atomicAdd(d, acc[pr]);
-        }
-      };
-      for (unsigned m = m0; m < m1; m++) {
-        const unsigned bin = __ldg(plan + m);
-        float2 p = smem[fmap(c * a.npol, np0 + m)];
-        float2 q = a.npol > 1 ? smem[fmap(c * a.npol + 1, np0 + m)] : make_float2(0.f, 0.f);
-        float r[4] = {0.f, 0.f, 0.f, 0.f};
-        detect_products(a.sink.state, p, q, r);
-        if (bin != cur) {
-          flush();
-          cur = bin;
-          for (int pr = 0; pr < 4; pr++) acc[pr] = r[pr];
-        } else {
-          for (int pr = 0; pr < 4; pr++) acc[pr] += r[pr];
+      unsigned key = 0xffffffffu;
+      if (it < total) {
+        const unsigned c = (a.CB == 1) ? 0 : it / nchunk;
+        const unsigned m0 = (it - c * nchunk) * L;
+        const unsigned m1 = min(nkeep, m0 + L);
+        const unsigned fp = c * a.npol;
+        for (unsigned m = m0; m < m1; m++) {
+          const unsigned k = c * nbin + __ldg(plan + m);
+          float2 p = smem[fmap(fp, np0 + m)];
+          float2 q = a.npol > 1 ? smem[fmap(fp + 1, np0 + m)] : make_float2(0.f, 0.f);
+          float r[4] = {0.f, 0.f, 0.f, 0.f};
+          detect_products(a.sink.state, p, q, r);
+          if (k != key) {
+            if (key != 0xffffffffu) red_add(key, acc);
+            key = k;
+#pragma unroll
+            for (int pr = 0; pr < 4; pr++) acc[pr] = r[pr];
+          } else {
+#pragma unroll
+            for (int pr = 0; pr < 4; pr++) acc[pr] += r[pr];
+          }
         }
       }
-      flush();
-    }
-    if (a.smem_bins) {
-      __syncthreads();
-      const unsigned nb = a.CB * nbin * nprod;
-      float* prof = a.sink.profile + uint64_t(ch0) * nbin * nprod;
-      for (unsigned i = threadIdx.x; i < nb; i += blockDim.x) {
-        float v = bins[i];
-        if (v != 0.f) atomicAdd(prof + i, v);
+      // segmented sum of the trailing runs across the warp
+#pragma unroll
+      for (unsigned off = 1; off < 32; off <<= 1) {
+        const unsigned okey = __shfl_down_sync(0xffffffffu, key, off);
+        float o[4];
+#pragma unroll
+        for (int pr = 0; pr < 4; pr++) o[pr] = __shfl_down_sync(0xffffffffu, acc[pr], off);
+        if (lane + off < 32 && okey == key) {
+#pragma unroll
+          for (int pr = 0; pr < 4; pr++) acc[pr] += o[pr];
+        }
       }
+      const unsigned pkey = __shfl_up_sync(0xffffffffu, key, 1);
+      if (key != 0xffffffffu && (lane == 0 || pkey != key)) red_add(key, acc);
     }
   }
 }
@@ -540,11 +565,17 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
       a.P = pl->P; a.Q = pl->Q; a.lb = pl->lbB; a.npol = npol; a.nchan_in = nchan_in; a.Nc = pl->Nc;
       a.part0 = part0;
       dim3 grid(pl->Q / B, nb * nblk1);
-      dim3 block((pl->P / 16) * B);
+      const bool ct = (pl->P == 2048);           // compile-time-sized fast path (EPT 32)
+      dim3 block((pl->P / (ct ? 32 : 16)) * B);
       size_t smem = size_t(pl->P) * B * sizeof(float2);
       LaunchScope ls(ctx, KC_COLS_FWD);
-      if (src.kind == SRC_F32) k_cols_fwd<SRC_F32><<<grid, block, smem, st>>>(a);
-      else k_cols_fwd<SRC_CASPSR8><<<grid, block, smem, st>>>(a);
+      if (ct) {
+        if (src.kind == SRC_F32) k_cols_fwd<SRC_F32, 32, 2048><<<grid, block, smem, st>>>(a);
+        else k_cols_fwd<SRC_CASPSR8, 32, 2048><<<grid, block, smem, st>>>(a);
+      } else {
+        if (src.kind == SRC_F32) k_cols_fwd<SRC_F32, 16, 0><<<grid, block, smem, st>>>(a);
+        else k_cols_fwd<SRC_CASPSR8, 16, 0><<<grid, block, smem, st>>>(a);
+      }
     }
     // ---- K2 ----
     {
@@ -554,22 +585,26 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
       a.P = pl->P; a.Q = pl->Q; a.G = pl->G; a.Nc = pl->Nc; a.npol = npol; a.nchan_in = nchan_in;
       const bool split = pl->desc.input_real;
       const unsigned nslots = split ? 2 * pl->G : pl->G;
-      const unsigned T = pl->Q >= 16 ? pl->Q / 16 : 1;
+      const bool ct = (pl->Q == 1024 && !pl->conv_path);   // compile-time-sized fast path (EPT 32)
+      const unsigned T = ct ? pl->Q / 32 : pl->Q >= 16 ? pl->Q / 16 : 1;
       dim3 grid(split ? (pl->P / 2) / pl->G : pl->P / pl->G, nb * nblk1);
       dim3 block(nslots * T);
       size_t smem = size_t(nslots) * pl->Q * sizeof(float2);
       LaunchScope ls(ctx, KC_ROWS);
-      if (pl->Q >= 16) {
+      if (ct) {
+        if (split) k_rows<true, false, 32, 1024><<<grid, block, smem, st>>>(a);
+        else k_rows<false, false, 32, 1024><<<grid, block, smem, st>>>(a);
+      } else if (pl->Q >= 16) {
         if (split) {
-          if (pl->conv_path) k_rows<true, true, 16><<<grid, block, smem, st>>>(a);
-          else k_rows<true, false, 16><<<grid, block, smem, st>>>(a);
+          if (pl->conv_path) k_rows<true, true, 16, 0><<<grid, block, smem, st>>>(a);
+          else k_rows<true, false, 16, 0><<<grid, block, smem, st>>>(a);
         } else {
-          if (pl->conv_path) k_rows<false, true, 16><<<grid, block, smem, st>>>(a);
-          else k_rows<false, false, 16><<<grid, block, smem, st>>>(a);
+          if (pl->conv_path) k_rows<false, true, 16, 0><<<grid, block, smem, st>>>(a);
+          else k_rows<false, false, 16, 0><<<grid, block, smem, st>>>(a);
         }
       } else {
-        if (split) k_rows<true, false, 0><<<grid, block, smem, st>>>(a);
-        else k_rows<false, false, 0><<<grid, block, smem, st>>>(a);
+        if (split) k_rows<true, false, 0, 0><<<grid, block, smem, st>>>(a);
+        else k_rows<false, false, 0, 0><<<grid, block, smem, st>>>(a);
       }
     }
     // ---- K3 ----
@@ -615,27 +650,22 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
         CB *= 2;
       a.CB = CB; a.npol_cta = npol_cta;
       size_t smem = size_t(CB) * npol_cta * F * sizeof(float2);
-      a.smem_bins = 0;
-      if (sk.kind == EPI_FOLD) {
-        size_t bins_bytes = size_t(CB) * sk.nbin * nprod * sizeof(float);
-        if (smem + bins_bytes <= size_t(ctx->max_smem_optin) - 1024 && bins_bytes <= 64 * 1024) {
-          a.smem_bins = 1;
-          smem += bins_bytes;
-        }
-      }
       dim3 grid(pl->nchan_out / CB, nb, npol / npol_cta);
-      dim3 block(CB * npol_cta * T);
+      const bool ct = (F == 8192 && npol_cta == npol && CB == 1);   // compile-time-sized fast path (EPT 32)
+      dim3 block(CB * npol_cta * (ct ? F / 32 : T));
       LaunchScope ls(ctx, KC_INV);
-#define B200_K3(E)                                                                          \
-  if (sk.kind == EPI_VOLT) k_chan_inv<E, EPI_VOLT><<<grid, block, smem, st>>>(a);            \
-  else if (sk.kind == EPI_DETECT) k_chan_inv<E, EPI_DETECT><<<grid, block, smem, st>>>(a);   \
-  else k_chan_inv<E, EPI_FOLD><<<grid, block, smem, st>>>(a);
-      switch (ept) {
-        case 16: B200_K3(16) break;
-        case 8: B200_K3(8) break;
-        case 4: B200_K3(4) break;
-        case 2: B200_K3(2) break;
-        default: B200_K3(0) break;
+#define B200_K3(E, FC)                                                                          \
+  if (sk.kind == EPI_VOLT) k_chan_inv<E, EPI_VOLT, FC><<<grid, block, smem, st>>>(a);            \
+  else if (sk.kind == EPI_DETECT) k_chan_inv<E, EPI_DETECT, FC><<<grid, block, smem, st>>>(a);   \
+  else k_chan_inv<E, EPI_FOLD, FC><<<grid, block, smem, st>>>(a);
+      if (ct) {
+        B200_K3(32, 8192)
+      } else switch (ept) {
+        case 16: B200_K3(16, 0) break;
+        case 8: B200_K3(8, 0) break;
+        case 4: B200_K3(4, 0) break;
+        case 2: B200_K3(2, 0) break;
+        default: B200_K3(0, 0) break;
       }
 #undef B200_K3
     }
@@ -647,15 +677,18 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
 static int plan_set_attributes(size_t maxs) {
   int rc;
 #define SET(k) if ((rc = set_smem(k, maxs)) != B200_OK) return rc;
-  SET(k_cols_fwd<SRC_F32>) SET(k_cols_fwd<SRC_CASPSR8>)
-  SET((k_rows<true, true, 16>)) SET((k_rows<true, false, 16>)) SET((k_rows<false, true, 16>))
-  SET((k_rows<false, false, 16>)) SET((k_rows<true, false, 0>)) SET((k_rows<false, false, 0>))
+  SET((k_cols_fwd<SRC_F32, 16, 0>)) SET((k_cols_fwd<SRC_CASPSR8, 16, 0>))
+  SET((k_cols_fwd<SRC_F32, 32, 2048>)) SET((k_cols_fwd<SRC_CASPSR8, 32, 2048>))
+  SET((k_rows<true, true, 16, 0>)) SET((k_rows<true, false, 16, 0>)) SET((k_rows<false, true, 16, 0>))
+  SET((k_rows<false, false, 16, 0>)) SET((k_rows<true, false, 0, 0>)) SET((k_rows<false, false, 0, 0>))
+  SET((k_rows<true, false, 32, 1024>)) SET((k_rows<false, false, 32, 1024>))
   SET(k_cols_inv<EPI_VOLT>) SET(k_cols_inv<EPI_DETECT>) SET(k_cols_inv<EPI_FOLD>)
-  SET((k_chan_inv<16, EPI_VOLT>)) SET((k_chan_inv<16, EPI_DETECT>)) SET((k_chan_inv<16, EPI_FOLD>))
-  SET((k_chan_inv<8, EPI_VOLT>)) SET((k_chan_inv<8, EPI_DETECT>)) SET((k_chan_inv<8, EPI_FOLD>))
-  SET((k_chan_inv<4, EPI_VOLT>)) SET((k_chan_inv<4, EPI_DETECT>)) SET((k_chan_inv<4, EPI_FOLD>))
-  SET((k_chan_inv<2, EPI_VOLT>)) SET((k_chan_inv<2, EPI_DETECT>)) SET((k_chan_inv<2, EPI_FOLD>))
-  SET((k_chan_inv<0, EPI_VOLT>)) SET((k_chan_inv<0, EPI_DETECT>)) SET((k_chan_inv<0, EPI_FOLD>))
+  SET((k_chan_inv<32, EPI_VOLT, 8192>)) SET((k_chan_inv<32, EPI_DETECT, 8192>)) SET((k_chan_inv<32, EPI_FOLD, 8192>))
+  SET((k_chan_inv<16, EPI_VOLT, 0>)) SET((k_chan_inv<16, EPI_DETECT, 0>)) SET((k_chan_inv<16, EPI_FOLD, 0>))
+  SET((k_chan_inv<8, EPI_VOLT, 0>)) SET((k_chan_inv<8, EPI_DETECT, 0>)) SET((k_chan_inv<8, EPI_FOLD, 0>))
+  SET((k_chan_inv<4, EPI_VOLT, 0>)) SET((k_chan_inv<4, EPI_DETECT, 0>)) SET((k_chan_inv<4, EPI_FOLD, 0>))
+  SET((k_chan_inv<2, EPI_VOLT, 0>)) SET((k_chan_inv<2, EPI_DETECT, 0>)) SET((k_chan_inv<2, EPI_FOLD, 0>))
+  SET((k_chan_inv<0, EPI_VOLT, 0>)) SET((k_chan_inv<0, EPI_DETECT, 0>)) SET((k_chan_inv<0, EPI_FOLD, 0>))
 #undef SET
   return B200_OK;
 }

@@ -134,8 +134,98 @@ static int sweep(unsigned nmin, unsigned nmax) {
   return bad;
 }
 
+
+// ---- compile-time-sized stages (stage_compute_ct / dft_tw) ------------------------------------
+template <int EPT, bool INV, unsigned N, unsigned NS>
+static void ct_stages(std::vector<float2>& regs, const float2* tw, std::vector<float2>& smem, const MapRows& map,
+                      std::vector<float2>& out) {
+  constexpr unsigned T = N / EPT;
+  constexpr unsigned REM = N / NS;
+  constexpr int R = REM >= (unsigned)EPT ? EPT : (int)REM;
+  constexpr int NB = EPT / R;
+  constexpr bool last = (REM == (unsigned)R);
+  for (unsigned j = 0; j < T; j++) stage_compute_ct<EPT, R, INV, N, NS>(&regs[size_t(j) * EPT], j, tw);
+  for (unsigned j = 0; j < T; j++)
+    for (int q = 0; q < NB; q++)
+      for (int r = 0; r < R; r++) {
+        unsigned b = j + q * T, k = b & (NS - 1);
+        unsigned d = (b - k) * R + k + r * NS;
+        if (last) out[d] = regs[size_t(j) * EPT + q + r * NB];
+        else smem[map(d)] = regs[size_t(j) * EPT + q + r * NB];
+      }
+  if constexpr (!last) {
+    for (unsigned j = 0; j < T; j++)
+      for (int e = 0; e < EPT; e++) regs[size_t(j) * EPT + e] = smem[map(j + e * T)];
+    ct_stages<EPT, INV, N, NS * R>(regs, tw, smem, map, out);
+  }
+}
+
+template <int EPT, bool INV, unsigned N>
+static double test_ct() {
+  const unsigned T = N / EPT;
+  std::vector<float2> tw(N);
+  for (unsigned m = 0; m < N; m++) {
+    double a = -2.0 * M_PI * m / N;
+    tw[m] = make_float2(float(cos(a)), float(sin(a)));
+  }
+  std::vector<std::complex<double>> x(N);
+  srand(N * 7 + EPT);
+  for (auto& z : x) z = {rand() / double(RAND_MAX) - 0.5, rand() / double(RAND_MAX) - 0.5};
+  std::vector<float2> regs(size_t(T) * EPT), smem(N + 64), out(N);
+  for (unsigned j = 0; j < T; j++)
+    for (int e = 0; e < EPT; e++)
+      regs[size_t(j) * EPT + e] = make_float2(float(x[j + e * T].real()), float(x[j + e * T].imag()));
+  unsigned sh = 0;
+  while ((1u << sh) < (unsigned)(N >= (unsigned)EPT ? EPT : N)) sh++;
+  MapRows map{8, sh, 3};
+  ct_stages<EPT, INV, N, 1>(regs, tw.data(), smem, map, out);
+  // reference: iterative radix-2 in double
+  std::vector<std::complex<double>> a(x);
+  unsigned lg = 0;
+  while ((1u << lg) < N) lg++;
+  for (unsigned i = 0; i < N; i++) {
+    unsigned r = 0;
+    for (unsigned bit = 0; bit < lg; bit++) if (i & (1u << bit)) r |= 1u << (lg - 1 - bit);
+    if (r > i) std::swap(a[i], a[r]);
+  }
+  for (unsigned len = 2; len <= N; len <<= 1) {
+    double ang = (INV ? 2.0 : -2.0) * M_PI / len;
+    for (unsigned i = 0; i < N; i += len)
+      for (unsigned k = 0; k < len / 2; k++) {
+        std::complex<double> w(cos(ang * k), sin(ang * k));
+        auto u = a[i + k], t = a[i + k + len / 2] * w;
+        a[i + k] = u + t;
+        a[i + k + len / 2] = u - t;
+      }
+  }
+  double rms = 0, err = 0;
+  for (unsigned k = 0; k < N; k++) rms += std::norm(a[k]);
+  rms = sqrt(rms / N);
+  for (unsigned k = 0; k < N; k++) {
+    double e = std::abs(std::complex<double>(out[k].x, out[k].y) - a[k]) / rms;
+    if (e > err) err = e;
+  }
+  return err;
+}
+
+#define CT_CASE(EPT, N)                                                     \
+  {                                                                         \
+    double e0 = test_ct<EPT, false, N>(), e1 = test_ct<EPT, true, N>();     \
+    printf("CT EPT=%d N=%d fwd %.3e inv %.3e\n", EPT, N, e0, e1);           \
+    if (!(e0 < 2e-6 && e1 < 2e-6)) bad++;                                   \
+  }
+
+static int sweep_ct() {
+  int bad = 0;
+  CT_CASE(16, 16) CT_CASE(16, 256) CT_CASE(16, 1024) CT_CASE(16, 2048) CT_CASE(16, 4096) CT_CASE(16, 8192)
+  CT_CASE(32, 32) CT_CASE(32, 64) CT_CASE(32, 512) CT_CASE(32, 1024) CT_CASE(32, 2048) CT_CASE(32, 4096)
+  CT_CASE(32, 8192) CT_CASE(32, 16384) CT_CASE(8, 64) CT_CASE(8, 512)
+  return bad;
+}
+
 int main() {
   int bad = 0;
+  bad += sweep_ct();
   bad += sweep<2>(2, 2);
   bad += sweep<4>(4, 64);
   bad += sweep<8>(8, 512);
