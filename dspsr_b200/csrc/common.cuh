@@ -76,7 +76,8 @@ static inline bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
 
 // Device twiddle tables owned by a plan
 struct TwiddleTable {
-  float2* tw = nullptr;   // exp(-2 pi i m / n), m < n
+  float2* tw = nullptr;     // exp(-2 pi i m / n), m < n
+  float2* stage = nullptr;  // compact per-stage tables for the EPT = 32 compile-time path (fft_core.cuh)
   unsigned n = 0;
 };
 // two-level table for big transforms: W_n^m = hi[m >> 11] * lo[m & 2047]
@@ -108,7 +109,8 @@ __device__ __forceinline__ float2 big_twiddle(const float2* __restrict__ lo, con
 //   j, T   this thread's index within its transform and threads per transform (N / EPT)
 //   map    shared-memory index map of this thread's transform
 //   load   load(idx)  -> float2      called EPT times for idx = j + e*T
-//   store  store(idx, value)         called EPT times with natural-order output indices
+//   store  store(idx, value, e)      called EPT times; idx = j + e*T is the natural-order output
+//                                     index of register e
 template <int EPT, bool INV, typename Map, typename LoadF, typename StoreF>
 __device__ __forceinline__ void block_fft(unsigned N, unsigned j, unsigned T, const Map& map, float2* smem,
                                           const float2* __restrict__ tw, unsigned NT, LoadF load,
@@ -128,7 +130,7 @@ __device__ __forceinline__ void block_fft(unsigned N, unsigned j, unsigned T, co
     if (last) {                                                                          \
       _Pragma("unroll") for (int q = 0; q < NB; q++)                                     \
         _Pragma("unroll") for (int r = 0; r < RR; r++)                                   \
-          store(stage_dest<EPT, RR>(j, T, Ns, q, r), v[q + r * NB]);                     \
+          store(stage_dest<EPT, RR>(j, T, Ns, q, r), v[q + r * NB], q + r * NB);         \
     } else {                                                                             \
       __syncthreads();                                                                   \
       _Pragma("unroll") for (int q = 0; q < NB; q++)                                     \
@@ -153,7 +155,7 @@ __device__ __forceinline__ void block_fft(unsigned N, unsigned j, unsigned T, co
 // stage loop is unrolled by template recursion.  Same contract as block_fft.
 template <int EPT, bool INV, unsigned N, unsigned NS, typename Map, typename StoreF>
 __device__ __forceinline__ void block_fft_ct_stages(float2* v, unsigned j, const Map& map, float2* smem,
-                                                    const float2* __restrict__ tw, StoreF store) {
+                                                    const float2* __restrict__ tw /* stage tables */, StoreF store) {
   constexpr unsigned T = N / EPT;
   constexpr unsigned REM = N / NS;
   constexpr int R = REM >= (unsigned)EPT ? EPT : (int)REM;
@@ -165,8 +167,8 @@ __device__ __forceinline__ void block_fft_ct_stages(float2* v, unsigned j, const
     for (int q = 0; q < NB; q++)
 #pragma unroll
       for (int r = 0; r < R; r++) {
-        const unsigned b = j + q * T, k = b & (NS - 1);
-        store((b - k) * R + k + r * NS, v[q + r * NB]);
+        // last stage: NS = N/R, so element (q, r) = register e = q + r*NB lands at j + e*T
+        store(j + (q + r * NB) * T, v[q + r * NB], q + r * NB);
       }
   } else {
     __syncthreads();

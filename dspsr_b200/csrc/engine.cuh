@@ -46,7 +46,7 @@ struct b200_fb_plan {
   unsigned P, Q, lbB, G;
   bool conv_path;           // large single-channel transforms: inverse also two-pass
   unsigned batch;           // parts per internal batch
-  b200::TwiddleTable twP, twQ, twF;
+  b200::TwiddleTable twP, twQ, twF, tw2Q;
   b200::BigTwiddle bigN, big2N;
   float2* d_response;       // nchan_in*Nc complex or null
   float2* scratchA;         // batch*nblk*Nc

@@ -21,11 +21,50 @@
 
 namespace b200 {
 
+// Complex arithmetic.  On the device it is written with Blackwell's packed FP32x2 instructions
+// (PTX add/mul/fma.rn.f32x2 -> SASS FADD2 / FMUL2 / FFMA2): a complex add is ONE issue slot and a
+// complex multiply TWO (ptxas folds the lane swap, broadcast and sign into operand modifiers),
+// half of what scalar FADD/FMUL/FFMA need.  The host versions are used by the CPU emulation test.
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 up2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return up2(add2(pk2(a.x, a.y), pk2(b.x, b.y))); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return up2(add2(pk2(a.x, a.y), pk2(-b.x, -b.y))); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  // (a.x b.x - a.y b.y, a.y b.x + a.x b.y)
+  unsigned long long t = mul2(pk2(a.x, a.y), pk2(b.x, b.x));
+  return up2(fma2(pk2(a.y, a.x), pk2(-b.y, b.y), t));
+}
+#else
 B200_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 B200_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 B200_HD float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+#endif
 B200_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 // multiply by -i (forward transforms) or +i (inverse transforms)
 template <bool INV> B200_HD float2 crot(float2 a) {
@@ -33,8 +72,13 @@ template <bool INV> B200_HD float2 crot(float2 a) {
 }
 // a * (c - i s) forward,  a * (c + i s) inverse  (c, s compile-time constants)
 template <bool INV> B200_HD float2 cmulc(float2 a, float c, float s) {
+#ifdef __CUDA_ARCH__
+  unsigned long long t = mul2(pk2(a.x, a.y), pk2(c, c));
+  return INV ? up2(fma2(pk2(a.y, a.x), pk2(-s, s), t)) : up2(fma2(pk2(a.y, a.x), pk2(s, -s), t));
+#else
   return INV ? make_float2(a.x * c - a.y * s, a.y * c + a.x * s)
              : make_float2(a.x * c + a.y * s, a.y * c - a.x * s);
+#endif
 }
 
 #define B200_SQRT1_2 0.70710678118654752440f
@@ -275,24 +319,76 @@ template <bool INV> B200_HD float2 mul_w32(float2 a, int m) {
   }
 }
 
-// Radix-R butterfly with the stage twiddles W^(r*k) folded into a (R/A) x A decomposition so
-// that only log-many runtime twiddles are live:  r = A*n1 + n2  (n1 < R/A... see below).
-//   R = 16: 4 x 4,  runtime twiddles w1,w2,w3 (on the second axis) and w4,w8,w12 (first axis)
+// ---- compact per-stage twiddle tables (compile-time-sized path) -----------------------------
+// For the stage with sub-transform length NS and radix R the butterflies of thread k need
+// W_{NS*R}^(m*k) for a handful of multipliers m; they are stored structure-of-arrays,
+//   stab[mi*NS + k] = exp(-2 pi i m_i k / (NS*R)),
+// so that consecutive lanes (consecutive k) read consecutive 8-byte words: one or two L1
+// wavefronts per load instead of the 8-32 of a strided gather from one big table.
+//   R = 32: m = {8, 16, 1, 2, 4}   R = 16: m = {4, 8, 1, 2}   R = 8: {1, 2, 4}   R = 4: {1, 2}   R = 2: {1}
+B200_HD constexpr int stage_radix(unsigned N, int EPT, unsigned NS) {
+  return (N / NS >= (unsigned)EPT) ? EPT : (int)(N / NS);
+}
+B200_HD constexpr int stage_nmult(int R) { return R == 32 ? 5 : R == 16 ? 4 : R == 8 ? 3 : R == 4 ? 2 : 1; }
+B200_HD constexpr int stage_mult(int R, int mi) {
+  return R >= 16 ? (mi == 0 ? R / 4 : mi == 1 ? R / 2 : (1 << (mi - 2))) : (1 << mi);
+}
+// offset (in float2) of the table of the stage whose sub-transform length is NS (NS > 1)
+B200_HD constexpr unsigned stage_offset(unsigned N, int EPT, unsigned NS) {
+  unsigned off = 0, ns = 1;
+  while (ns < NS) {
+    int R = stage_radix(N, EPT, ns);
+    if (ns > 1) off += (unsigned)stage_nmult(R) * ns;
+    ns *= (unsigned)R;
+  }
+  return off;
+}
+B200_HD constexpr unsigned stage_table_size(unsigned N, int EPT) {
+  unsigned off = 0, ns = 1;
+  while (ns < N) {
+    int R = stage_radix(N, EPT, ns);
+    if (ns > 1) off += (unsigned)stage_nmult(R) * ns;
+    ns *= (unsigned)R;
+  }
+  return off ? off : 1;
+}
+
+// Radix-R butterfly with the stage twiddles W^(r*k) folded into a 4 x (R/4) decomposition so
+// that only a handful of runtime twiddles are live:  r = A*n1 + n2, A = R/4
+//   R = 16: 4 x 4,  runtime twiddles w1,w2,w3 (second axis) and w4,w8,w12 (first axis)
 //   R = 32: 4 x 8,  runtime twiddles w1..w7 and w8,w16,w24
-// TW = false skips the runtime twiddles (first stage, Ns = 1).  tw[m] = exp(-2 pi i m / NT);
-// kk = k * NT/(Ns*R) is the table index of W^(1*k).
+// TW = false skips the runtime twiddles (first stage, NS = 1).  st points at this stage's compact
+// table, k is the butterfly's position inside its sub-transform.
 template <int R, bool INV, bool TW>
-B200_HD void dft_tw(float2* u, const float2* __restrict__ tw, unsigned kk) {
+B200_HD void dft_tw(float2* u, const float2* __restrict__ st, unsigned k, unsigned NS) {
   if constexpr (R <= 8) {
-    if (TW) apply_stage_twiddles<R, INV>(u, tw, kk);
+    if (TW) {
+      if (R == 2) {
+        u[1] = cmul(u[1], tw_get<INV>(st, k));
+      } else if (R == 4) {
+        float2 w1 = tw_get<INV>(st, k), w2 = tw_get<INV>(st, NS + k);
+        u[1] = cmul(u[1], w1);
+        u[2] = cmul(u[2], w2);
+        u[3] = cmul(u[3], cmul(w1, w2));
+      } else {
+        float2 w1 = tw_get<INV>(st, k), w2 = tw_get<INV>(st, NS + k), w4 = tw_get<INV>(st, 2 * NS + k);
+        float2 w3 = cmul(w1, w2);
+        u[1] = cmul(u[1], w1);
+        u[2] = cmul(u[2], w2);
+        u[3] = cmul(u[3], w3);
+        u[4] = cmul(u[4], w4);
+        u[5] = cmul(u[5], cmul(w1, w4));
+        u[6] = cmul(u[6], cmul(w2, w4));
+        u[7] = cmul(u[7], cmul(w3, w4));
+      }
+    }
     dftR<R, INV>(u);
   } else {
     constexpr int A = R / 4;        // second-axis length (4 or 8); first axis has 4 points
-    // first axis: r = A*n1 + n2, twiddle W^(A*n1*k)
     float2 wa1, wa2, wa3;
     if (TW) {
-      wa1 = tw_get<INV>(tw, A * kk);
-      wa2 = tw_get<INV>(tw, 2 * A * kk);
+      wa1 = tw_get<INV>(st, k);
+      wa2 = tw_get<INV>(st, NS + k);
       wa3 = cmul(wa1, wa2);
     }
 #pragma unroll
@@ -300,16 +396,15 @@ B200_HD void dft_tw(float2* u, const float2* __restrict__ tw, unsigned kk) {
       float2 a = u[n2], b = u[A + n2], c = u[2 * A + n2], d = u[3 * A + n2];
       if (TW) { b = cmul(b, wa1); c = cmul(c, wa2); d = cmul(d, wa3); }
       dft4<INV>(a, b, c, d);
-      u[n2] = a; u[A + n2] = b; u[2 * A + n2] = c; u[3 * A + n2] = d;   // now y[n2][k1] at u[k1*A + n2]
+      u[n2] = a; u[A + n2] = b; u[2 * A + n2] = c; u[3 * A + n2] = d;   // y[n2][k1] at u[k1*A + n2]
     }
-    // second axis twiddles: y[n2][k1] *= W^(n2*k) * W_R^(n2*k1)
     float2 w[A];
     if (TW) {
-      w[1] = tw_get<INV>(tw, kk);
-      w[2] = tw_get<INV>(tw, 2 * kk);
+      w[1] = tw_get<INV>(st, 2 * NS + k);
+      w[2] = tw_get<INV>(st, 3 * NS + k);
       w[3] = cmul(w[1], w[2]);
       if (A == 8) {
-        w[4] = tw_get<INV>(tw, 4 * kk);
+        w[4] = tw_get<INV>(st, 4 * NS + k);
         w[5] = cmul(w[1], w[4]);
         w[6] = cmul(w[2], w[4]);
         w[7] = cmul(w[3], w[4]);
@@ -325,7 +420,6 @@ B200_HD void dft_tw(float2* u, const float2* __restrict__ tw, unsigned kk) {
         u[k1 * A + n2] = y;
       }
     }
-    // second axis DFTs (length A) for every k1; output index k = k1 + 4*k2
     float2 o[R];
 #pragma unroll
     for (int k1 = 0; k1 < 4; k1++) {
@@ -342,12 +436,12 @@ B200_HD void dft_tw(float2* u, const float2* __restrict__ tw, unsigned kk) {
 }
 
 // One Stockham stage with every size a compile-time constant (N points, EPT per thread,
-// sub-transform length NS): same contract as stage_compute.
+// sub-transform length NS): same contract as stage_compute.  stw = compact stage tables of (N, EPT).
 template <int EPT, int R, bool INV, unsigned N, unsigned NS>
-B200_HD void stage_compute_ct(float2* v, unsigned j, const float2* __restrict__ tw) {
+B200_HD void stage_compute_ct(float2* v, unsigned j, const float2* __restrict__ stw) {
   constexpr int NB = EPT / R;
   constexpr unsigned T = N / EPT;
-  constexpr unsigned stride = N / (NS * R);
+  constexpr unsigned OFF = stage_offset(N, EPT, NS);
 #pragma unroll
   for (int q = 0; q < NB; q++) {
     float2 u[R];
@@ -355,9 +449,9 @@ B200_HD void stage_compute_ct(float2* v, unsigned j, const float2* __restrict__ 
     for (int r = 0; r < R; r++) u[r] = v[q + r * NB];
     if (NS > 1) {
       const unsigned k = (j + q * T) & (NS - 1);
-      dft_tw<R, INV, true>(u, tw, k * stride);
+      dft_tw<R, INV, true>(u, stw + OFF, k, NS);
     } else {
-      dft_tw<R, INV, false>(u, tw, 0);
+      dft_tw<R, INV, false>(u, stw, 0, 1);
     }
 #pragma unroll
     for (int r = 0; r < R; r++) v[q + r * NB] = u[r];

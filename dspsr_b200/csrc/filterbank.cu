@@ -17,6 +17,7 @@
 // No cuFFT.  FFTs are hand-written radix-16/8/4/2 Stockham stages on registers (fft_core.cuh)
 // exchanged through shared memory.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -34,8 +35,9 @@ __device__ __forceinline__ float2 ld_nc_f2(const float2* p) {
 // NCT == 0, of run-time size N (generic path).
 template <int EPT, bool INV, unsigned NCT, typename Map, typename LoadF, typename StoreF>
 __device__ __forceinline__ void fft_any(unsigned N, unsigned j, unsigned T, const Map& map, float2* smem,
-                                        const float2* __restrict__ tw, LoadF load, StoreF store) {
-  if constexpr (NCT != 0) block_fft_ct<EPT, INV, NCT>(j, map, smem, tw, load, store);
+                                        const float2* __restrict__ tw, const float2* __restrict__ stw,
+                                        LoadF load, StoreF store) {
+  if constexpr (NCT != 0) block_fft_ct<EPT, INV, NCT>(j, map, smem, stw, load, store);
   else block_fft<EPT, INV>(N, j, T, map, smem, tw, N, load, store);
 }
 // log2 of the first radix = swizzle shift of the shared-memory maps
@@ -50,6 +52,7 @@ struct ColsArgs {
   const float* lut;
   float2* dst;
   const float2* twP;
+  const float2* twPs;
   const float2* blo;
   const float2* bhi;
   unsigned P, Q, lb, npol, nchan_in, Nc;
@@ -60,6 +63,7 @@ template <int SRC, int EPT, unsigned PCT>
 __global__ void __launch_bounds__(PCT ? 512 : 1024, 1) k_cols_fwd(ColsArgs a) {
   extern __shared__ float2 smem[];
   __shared__ float s_lut[256];
+  __shared__ float2 s_h[32 * 16];   // W_N^(n2*T*e): output twiddle factors shared by the tile
   const unsigned P = PCT ? PCT : a.P;
   const unsigned B = 1u << a.lb;
   const unsigned b = threadIdx.x & (B - 1);
@@ -70,10 +74,18 @@ __global__ void __launch_bounds__(PCT ? 512 : 1024, 1) k_cols_fwd(ColsArgs a) {
   const unsigned pol = blk % a.npol;
   const unsigned ic = (blk / a.npol) % a.nchan_in;
   const uint64_t part = a.part0 + blk / (a.npol * a.nchan_in);
-  if (SRC == SRC_CASPSR8) {
+  if (SRC == SRC_CASPSR8)
     for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = a.lut[i];
-    __syncthreads();
-  }
+  // Output twiddle W_N^(n2*k1) with k1 = j + e*T factorises into W_N^(n2*j) (one per thread) times
+  // W_N^(n2*T*e) (EPT x B values per tile, staged here once): two table look-ups per thread
+  // instead of two scattered ones per element.
+  if (a.Q > 1)
+    for (unsigned i = threadIdx.x; i < EPT * B; i += blockDim.x) {
+      const unsigned e = i >> a.lb, bb = i & (B - 1);
+      const unsigned m = ((blockIdx.x * B + bb) * T * e) & (a.Nc - 1);
+      s_h[i] = big_twiddle<false>(a.blo, a.bhi, m);
+    }
+  __syncthreads();
   const float2* fsrc = nullptr;
   const unsigned char* raw = nullptr;
   uint64_t samp0 = 0;
@@ -97,11 +109,12 @@ __global__ void __launch_bounds__(PCT ? 512 : 1024, 1) k_cols_fwd(ColsArgs a) {
     }
   };
   float2* dst = a.dst + uint64_t(blk) * a.Nc + n2;
-  auto store = [&](unsigned k1, float2 v) {
-    if (a.Q > 1) v = cmul(v, big_twiddle<false>(a.blo, a.bhi, n2 * k1));
+  const float2 wbase = a.Q > 1 ? big_twiddle<false>(a.blo, a.bhi, n2 * j) : make_float2(1.f, 0.f);
+  auto store = [&](unsigned k1, float2 v, int e) {
+    if (a.Q > 1) v = cmul(cmul(v, wbase), s_h[(e << a.lb) + b]);
     dst[uint64_t(k1) * a.Q] = v;
   };
-  fft_any<EPT, false, PCT>(P, j, T, map, smem, a.twP, load, store);
+  fft_any<EPT, false, PCT>(P, j, T, map, smem, a.twP, a.twPs, load, store);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -112,6 +125,8 @@ struct RowsArgs {
   float2* Z;
   const float2* H;
   const float2* twQ;
+  const float2* twQs;
+  const float2* tw2Q;      // exp(-2 pi i m / (2Q)), m < 2Q: column factor of the real-split twiddle
   const float2* blo;
   const float2* bhi;
   const float2* b2lo;
@@ -122,6 +137,7 @@ struct RowsArgs {
 template <bool SPLIT, bool CONV, int EPT, unsigned QCT>
 __global__ void __launch_bounds__(QCT ? 512 : 1024, 1) k_rows(RowsArgs a) {
   extern __shared__ float2 smem[];
+  __shared__ float2 s_rowtw[32];   // W_2N^(row) of every slot: row factor of the real-split twiddle
   const unsigned Q = QCT ? QCT : a.Q;
   const unsigned T = EPT ? Q / (EPT ? EPT : 1) : 1;
   constexpr unsigned SH = SwzShift<EPT>::value;
@@ -146,14 +162,20 @@ __global__ void __launch_bounds__(QCT ? 512 : 1024, 1) k_rows(RowsArgs a) {
 
   const unsigned row = slot_row(slot);
   float2* Ablk = a.A + uint64_t(blk) * Nc;
+  if (SPLIT && threadIdx.x < 2 * G) {
+    // W_2N^k with k = row + P*k2 factorises into W_2N^row (here) times W_2Q^k2 (table tw2Q)
+    unsigned r = slot_row(threadIdx.x);
+    if (threadIdx.x == 0 && tile == 0) r = 0;
+    s_rowtw[threadIdx.x] = big_twiddle<false>(a.b2lo, a.b2hi, r);
+  }
 
   // ---- phase 1: forward row FFT into shared memory (natural order) ----
   if (EPT) {
     MapRows map{slot * Q, SH, ((slot % G) * 2u) & 15u};
     const float2* src = Ablk + uint64_t(row) * Q;
     auto load = [&](unsigned idx) -> float2 { return src[idx]; };
-    auto store = [&](unsigned idx, float2 v) { smem[map(idx)] = v; };
-    fft_any<(EPT ? EPT : 2), false, QCT>(Q, j, T, map, smem, a.twQ, load, store);
+    auto store = [&](unsigned idx, float2 v, int) { smem[map(idx)] = v; };
+    fft_any<(EPT ? EPT : 2), false, QCT>(Q, j, T, map, smem, a.twQ, a.twQs, load, store);
   } else {
     smem[slot] = Ablk[row];
   }
@@ -164,6 +186,7 @@ __global__ void __launch_bounds__(QCT ? 512 : 1024, 1) k_rows(RowsArgs a) {
   float2* Zblk = CONV ? nullptr : a.Z + uint64_t(blk) * Nc;
 
   if (SPLIT) {
+    // element (slot sA, column iA) is bin k = row(sA) + P*iA; its mirror N-k sits at (sB, iB)
     auto do_pair = [&](unsigned sA, unsigned iA, unsigned sB, unsigned iB, unsigned k) {
       const unsigned pa = smap(sA, iA), pb = smap(sB, iB);
       const bool same = (pa == pb);
@@ -171,7 +194,7 @@ __global__ void __launch_bounds__(QCT ? 512 : 1024, 1) k_rows(RowsArgs a) {
       float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y + zm.y));
       float2 d = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y - zm.y));
       float2 o = make_float2(d.y, -d.x);   // -i * d
-      float2 t = cmul(o, big_twiddle<false>(a.b2lo, a.b2hi, k));
+      float2 t = cmul(o, cmul(s_rowtw[sA], __ldg(a.tw2Q + iA)));
       float2 xk = cadd(e, t);
       float2 xm = cconj(csub(e, t));
       if (H) {
@@ -223,10 +246,10 @@ __global__ void __launch_bounds__(QCT ? 512 : 1024, 1) k_rows(RowsArgs a) {
     if (EPT) {
       MapRows map{slot * Q, SH, ((slot % G) * 2u) & 15u};
       auto load = [&](unsigned idx) -> float2 { return smem[map(idx)]; };
-      auto store = [&](unsigned m2, float2 v) {
+      auto store = [&](unsigned m2, float2 v, int) {
         dst[m2] = cmul(v, big_twiddle<true>(a.blo, a.bhi, row * m2));
       };
-      fft_any<(EPT ? EPT : 2), true, QCT>(Q, j, T, map, smem, a.twQ, load, store);
+      fft_any<(EPT ? EPT : 2), true, QCT>(Q, j, T, map, smem, a.twQ, a.twQs, load, store);
     } else {
       dst[0] = smem[slot];
     }
@@ -271,6 +294,7 @@ __host__ __device__ inline unsigned state_nprod(int state, unsigned npol) {
 struct ChanArgs {
   const float2* Z;
   const float2* twF;
+  const float2* twFs;
   unsigned F, C, Nc, npol, nchan_in, CB, npol_cta;
   unsigned nfilt_pos, nkeep;
   uint64_t part0;
@@ -307,13 +331,13 @@ __global__ void __launch_bounds__(FCT ? 512 : 1024, 1) k_chan_inv(ChanArgs a) {
     if (F >= 16) {
       MapRows map{f * F, sh, 0};
       auto load = [&](unsigned idx) -> float2 { return ld_nc_f2(src + idx); };
-      auto store = [&](unsigned idx, float2 v) { smem[map(idx)] = v; };
-      fft_any<(EPT ? EPT : 2), true, FCT>(F, j, T, map, smem, a.twF, load, store);
+      auto store = [&](unsigned idx, float2 v, int) { smem[map(idx)] = v; };
+      fft_any<(EPT ? EPT : 2), true, FCT>(F, j, T, map, smem, a.twF, a.twFs, load, store);
     } else {
       // F = 2, 4, 8: one thread per transform, no shared-memory exchange needed
       MapRows map{f * F, 0, 0};
       auto load = [&](unsigned idx) -> float2 { return ld_nc_f2(src + idx); };
-      auto store = [&](unsigned idx, float2 v) { smem[f * F + idx] = v; };
+      auto store = [&](unsigned idx, float2 v, int) { smem[f * F + idx] = v; };
       block_fft<(EPT ? EPT : 2), true>(F, j, T, map, smem, a.twF, F, load, store);
     }
   } else {
@@ -460,7 +484,7 @@ __global__ void __launch_bounds__(1024, 1) k_cols_inv(ColsInvArgs a) {
   if (EPI == EPI_VOLT) {
     float2* out = reinterpret_cast<float2*>(a.sink.volt + (uint64_t(ic) * a.npol + pol) * a.sink.volt_span +
                                             part * a.sink.volt_step);
-    auto store = [&](unsigned m1, float2 v) {
+    auto store = [&](unsigned m1, float2 v, int) {
       const unsigned m = m1 * a.Q + m2;
       if (m >= np0 && m < np0 + nkeep) out[m - np0] = v;
     };
@@ -476,7 +500,7 @@ __global__ void __launch_bounds__(1024, 1) k_cols_inv(ColsInvArgs a) {
     for (unsigned i = threadIdx.x; i < nbin * nprod; i += blockDim.x) bins[i] = 0.f;
 
   {
-    auto store = [&](unsigned m1, float2 v) { spol[map(m1)] = v; };
+    auto store = [&](unsigned m1, float2 v, int) { spol[map(m1)] = v; };
     block_fft<16, true>(a.P, j, T, map, spol, a.twP, a.P, load, store);
   }
   __syncthreads();
@@ -561,13 +585,19 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
     {
       ColsArgs a;
       a.src = src.ptr; a.span = src.span; a.step = src.step; a.lut = src.d_lut;
-      a.dst = pl->scratchA; a.twP = pl->twP.tw; a.blo = pl->bigN.lo; a.bhi = pl->bigN.hi;
+      a.dst = pl->scratchA; a.twP = pl->twP.tw; a.twPs = pl->twP.stage; a.blo = pl->bigN.lo; a.bhi = pl->bigN.hi;
       a.P = pl->P; a.Q = pl->Q; a.lb = pl->lbB; a.npol = npol; a.nchan_in = nchan_in; a.Nc = pl->Nc;
       a.part0 = part0;
       dim3 grid(pl->Q / B, nb * nblk1);
       const bool ct = (pl->P == 2048);           // compile-time-sized fast path (EPT 32)
       dim3 block((pl->P / (ct ? 32 : 16)) * B);
       size_t smem = size_t(pl->P) * B * sizeof(float2);
+      if (getenv("B200_DEBUG") && part0 == 0) {
+        int nb1 = 0, nb2 = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb1, k_cols_fwd<SRC_CASPSR8, 32, 2048>, block.x, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_cols_fwd<SRC_CASPSR8, 16, 0>, block.x, smem);
+        fprintf(stderr, "[b200] K1 grid (%u,%u) block %u smem %zu occupancy ct=%d generic=%d\n", grid.x, grid.y, block.x, smem, nb1, nb2);
+      }
       LaunchScope ls(ctx, KC_COLS_FWD);
       if (ct) {
         if (src.kind == SRC_F32) k_cols_fwd<SRC_F32, 32, 2048><<<grid, block, smem, st>>>(a);
@@ -580,7 +610,8 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
     // ---- K2 ----
     {
       RowsArgs a;
-      a.A = pl->scratchA; a.Z = pl->scratchZ; a.H = pl->d_response; a.twQ = pl->twQ.tw;
+      a.A = pl->scratchA; a.Z = pl->scratchZ; a.H = pl->d_response; a.twQ = pl->twQ.tw; a.twQs = pl->twQ.stage;
+      a.tw2Q = pl->tw2Q.tw;
       a.blo = pl->bigN.lo; a.bhi = pl->bigN.hi; a.b2lo = pl->big2N.lo; a.b2hi = pl->big2N.hi;
       a.P = pl->P; a.Q = pl->Q; a.G = pl->G; a.Nc = pl->Nc; a.npol = npol; a.nchan_in = nchan_in;
       const bool split = pl->desc.input_real;
@@ -630,7 +661,7 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
       else k_cols_inv<EPI_FOLD><<<grid, block, smem, st>>>(a);
     } else {
       ChanArgs a;
-      a.Z = pl->scratchZ; a.twF = pl->twF.tw;
+      a.Z = pl->scratchZ; a.twF = pl->twF.tw; a.twFs = pl->twF.stage;
       a.F = pl->F; a.C = pl->C; a.Nc = pl->Nc; a.npol = npol; a.nchan_in = nchan_in;
       a.nfilt_pos = pl->desc.nfilt_pos; a.nkeep = pl->nkeep; a.part0 = part0; a.sink = sk;
       const unsigned F = pl->F;
@@ -752,9 +783,13 @@ int b200_fb_plan_create(b200_context* cctx, const b200_fb_desc* d, b200_fb_plan*
     pl->Q = pl->Nc / pl->P;
   }
   // column tile: B columns, P*B elements <= 16384, (P/16)*B threads <= 1024
+  // (tuning overrides: B200_TILE_KB_COLS / B200_TILE_KB_ROWS = tile budget in KiB)
+  size_t tile_cols = SMEM_TILE, tile_rows = SMEM_TILE;
+  if (const char* e = getenv("B200_TILE_KB_COLS")) tile_cols = size_t(atoi(e)) * 1024;
+  if (const char* e = getenv("B200_TILE_KB_ROWS")) tile_rows = size_t(atoi(e)) * 1024;
   {
     unsigned lb = 0;
-    while ((2u << lb) <= pl->Q && size_t(pl->P) * (2u << lb) * sizeof(float2) <= SMEM_TILE &&
+    while ((2u << lb) <= pl->Q && size_t(pl->P) * (2u << lb) * sizeof(float2) <= tile_cols &&
            (pl->P / 16) * (2u << lb) <= 1024 && (2u << lb) <= 16)
       lb++;
     pl->lbB = lb;
@@ -765,7 +800,7 @@ int b200_fb_plan_create(b200_context* cctx, const b200_fb_desc* d, b200_fb_plan*
     const unsigned T = pl->Q >= 16 ? pl->Q / 16 : 1;
     const unsigned rows_avail = d->input_real ? pl->P / 2 : pl->P;
     unsigned G = 1;
-    while (G * 2 <= rows_avail && size_t(G) * 2 * mult * pl->Q * sizeof(float2) <= SMEM_TILE &&
+    while (G * 2 <= rows_avail && size_t(G) * 2 * mult * pl->Q * sizeof(float2) <= tile_rows &&
            G * 2 * mult * T <= 1024 && G * 2 <= 8)
       G *= 2;
     pl->G = G;
@@ -776,6 +811,7 @@ int b200_fb_plan_create(b200_context* cctx, const b200_fb_desc* d, b200_fb_plan*
   if (rc == B200_OK) rc = make_twiddle(pl->twP, pl->P, ctx->stream);
   if (rc == B200_OK) rc = make_twiddle(pl->twQ, pl->Q, ctx->stream);
   if (rc == B200_OK) rc = make_twiddle(pl->twF, pl->F, ctx->stream);
+  if (rc == B200_OK) rc = make_twiddle(pl->tw2Q, 2 * pl->Q, ctx->stream);
   if (rc == B200_OK) rc = make_big_twiddle(pl->bigN, pl->Nc, ctx->stream);
   if (rc == B200_OK) rc = make_big_twiddle(pl->big2N, 2ull * pl->Nc, ctx->stream);
   if (rc != B200_OK) { b200_fb_plan_destroy(pl); return rc; }
@@ -818,6 +854,7 @@ int b200_fb_plan_destroy(b200_fb_plan* pl) {
   free_twiddle(pl->twP);
   free_twiddle(pl->twQ);
   free_twiddle(pl->twF);
+  free_twiddle(pl->tw2Q);
   free_big_twiddle(pl->bigN);
   free_big_twiddle(pl->big2N);
   if (pl->d_response) cudaFree(pl->d_response);

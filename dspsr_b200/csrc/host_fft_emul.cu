@@ -163,10 +163,21 @@ static void ct_stages(std::vector<float2>& regs, const float2* tw, std::vector<f
 template <int EPT, bool INV, unsigned N>
 static double test_ct() {
   const unsigned T = N / EPT;
-  std::vector<float2> tw(N);
-  for (unsigned m = 0; m < N; m++) {
-    double a = -2.0 * M_PI * m / N;
-    tw[m] = make_float2(float(cos(a)), float(sin(a)));
+  std::vector<float2> tw(stage_table_size(N, EPT));
+  {
+    unsigned ns = 1, off = 0;
+    while (ns < N) {
+      int R = stage_radix(N, EPT, ns);
+      if (ns > 1) {
+        for (int mi = 0; mi < stage_nmult(R); mi++)
+          for (unsigned k = 0; k < ns; k++) {
+            double a = -2.0 * M_PI * double(stage_mult(R, mi)) * k / (double(ns) * R);
+            tw[off + mi * ns + k] = make_float2(float(cos(a)), float(sin(a)));
+          }
+        off += stage_nmult(R) * ns;
+      }
+      ns *= R;
+    }
   }
   std::vector<std::complex<double>> x(N);
   srand(N * 7 + EPT);
