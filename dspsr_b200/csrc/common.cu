@@ -31,26 +31,29 @@ int make_twiddle(TwiddleTable& t, unsigned n, cudaStream_t s) {
   }
   B200_CUDA(cudaMalloc(&t.tw, sizeof(float2) * h.size()));
   B200_CUDA(cudaMemcpyAsync(t.tw, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice, s));
-  // compact per-stage tables of the compile-time-sized EPT = 32 path
-  std::vector<float2> st(1, make_float2(1.f, 0.f));
-  if (n >= 32 && (n & (n - 1)) == 0) {
-    st.assign(stage_table_size(n, 32), make_float2(1.f, 0.f));
-    unsigned ns = 1, off = 0;
-    while (ns < n) {
-      const int R = stage_radix(n, 32, ns);
-      if (ns > 1) {
-        for (int mi = 0; mi < stage_nmult(R); mi++)
-          for (unsigned k = 0; k < ns; k++) {
-            double a = -2.0 * M_PI * double(stage_mult(R, mi)) * double(k) / (double(ns) * R);
-            st[off + mi * ns + k] = make_float2(float(std::cos(a)), float(std::sin(a)));
-          }
-        off += stage_nmult(R) * ns;
+  // compact per-stage tables of the compile-time-sized paths (EPT = 32 and 16)
+  for (int ept = 32; ept >= 16; ept -= 16) {
+    std::vector<float2> st(1, make_float2(1.f, 0.f));
+    if (n >= (unsigned)ept && (n & (n - 1)) == 0) {
+      st.assign(stage_table_size(n, ept), make_float2(1.f, 0.f));
+      unsigned ns = 1, off = 0;
+      while (ns < n) {
+        const int R = stage_radix(n, ept, ns);
+        if (ns > 1) {
+          for (int mi = 0; mi < stage_nmult(R); mi++)
+            for (unsigned k = 0; k < ns; k++) {
+              double a = -2.0 * M_PI * double(stage_mult(R, mi)) * double(k) / (double(ns) * R);
+              st[off + mi * ns + k] = make_float2(float(std::cos(a)), float(std::sin(a)));
+            }
+          off += stage_nmult(R) * ns;
+        }
+        ns *= R;
       }
-      ns *= R;
     }
+    float2** dst = ept == 32 ? &t.stage : &t.stage16;
+    B200_CUDA(cudaMalloc(dst, sizeof(float2) * st.size()));
+    B200_CUDA(cudaMemcpy(*dst, st.data(), sizeof(float2) * st.size(), cudaMemcpyHostToDevice));
   }
-  B200_CUDA(cudaMalloc(&t.stage, sizeof(float2) * st.size()));
-  B200_CUDA(cudaMemcpyAsync(t.stage, st.data(), sizeof(float2) * st.size(), cudaMemcpyHostToDevice, s));
   B200_CUDA(cudaStreamSynchronize(s));
   return B200_OK;
 }
@@ -79,7 +82,8 @@ int make_big_twiddle(BigTwiddle& t, uint64_t n, cudaStream_t s) {
 void free_twiddle(TwiddleTable& t) {
   if (t.tw) cudaFree(t.tw);
   if (t.stage) cudaFree(t.stage);
-  t.tw = t.stage = nullptr;
+  if (t.stage16) cudaFree(t.stage16);
+  t.tw = t.stage = t.stage16 = nullptr;
 }
 void free_big_twiddle(BigTwiddle& t) {
   if (t.lo) cudaFree(t.lo);

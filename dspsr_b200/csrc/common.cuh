@@ -78,6 +78,7 @@ static inline bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
 struct TwiddleTable {
   float2* tw = nullptr;     // exp(-2 pi i m / n), m < n
   float2* stage = nullptr;  // compact per-stage tables for the EPT = 32 compile-time path (fft_core.cuh)
+  float2* stage16 = nullptr;  // same for EPT = 16
   unsigned n = 0;
 };
 // two-level table for big transforms: W_n^m = hi[m >> 11] * lo[m & 2047]

@@ -31,6 +31,7 @@ struct FbSink {
   uint64_t det_span;
   // EPI_FOLD
   const unsigned* bins;     // bin of every output sample of the block (npart*nkeep)
+  double phase_per_sample;  // of the block's fold call (0 = unknown): enables the one-bin-per-chunk path
   unsigned nbin;
   float* profile;           // [chan][npol'][nbin][dndim]
 };

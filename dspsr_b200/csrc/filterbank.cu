@@ -60,7 +60,7 @@ struct ColsArgs {
 };
 
 template <int SRC, int EPT, unsigned PCT>
-__global__ void __launch_bounds__(PCT ? 512 : 1024, 1) k_cols_fwd(ColsArgs a) {
+__global__ void __launch_bounds__((PCT && EPT == 32) ? 512 : 1024, 1) k_cols_fwd(ColsArgs a) {
   extern __shared__ float2 smem[];
   __shared__ float s_lut[256];
   __shared__ float2 s_h[32 * 16];   // W_N^(n2*T*e): output twiddle factors shared by the tile
@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(PCT ? 512 : 1024, 1) k_cols_fwd(ColsArgs a) {
   const unsigned pol = blk % a.npol;
   const unsigned ic = (blk / a.npol) % a.nchan_in;
   const uint64_t part = a.part0 + blk / (a.npol * a.nchan_in);
+  // (a per-bank replicated table -- conflict-free gathers -- was measured slower: 0.71 vs 0.67 ms)
   if (SRC == SRC_CASPSR8)
     for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = a.lut[i];
   // Output twiddle W_N^(n2*k1) with k1 = j + e*T factorises into W_N^(n2*j) (one per thread) times
@@ -209,17 +210,58 @@ __global__ void __launch_bounds__(QCT ? 512 : 1024, 1) k_rows(RowsArgs a) {
         if (!same) Zblk[Nc - k] = xm;
       }
     };
+    // jobs are processed four at a time per thread so that the response / twiddle loads of all
+    // four are in flight together (they come from L2 / HBM and nothing else hides their latency)
     const unsigned njobs = G * Q;
-    for (unsigned it = threadIdx.x; it < njobs; it += blockDim.x) {
-      const unsigned g = it % G, k2 = it / G;
-      const unsigned low = tile * G + g;
-      if (low != 0) {
-        do_pair(g, k2, G + g, Q - 1 - k2, low + P * k2);
-      } else if (k2 <= Q / 2) {
-        do_pair(0, k2, 0, (Q - k2) % Q, P * k2);                       // row 0 pairs with itself
-      } else {
-        const unsigned kk = k2 - Q / 2 - 1;                            // row P/2 pairs with itself
-        do_pair(G, kk, G, Q - 1 - kk, P / 2 + P * kk);
+    constexpr int U = 4;
+    for (unsigned it0 = threadIdx.x; it0 < njobs; it0 += blockDim.x * U) {
+      unsigned sA[U], iA[U], sB[U], iB[U], kb[U];
+      float2 hk[U], hm[U], tq[U];
+      bool valid[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const unsigned it = it0 + u * blockDim.x;
+        valid[u] = it < njobs;
+        const unsigned itc = valid[u] ? it : threadIdx.x;
+        const unsigned g = itc % G, k2 = itc / G;
+        const unsigned low = tile * G + g;
+        if (low != 0) {
+          sA[u] = g; iA[u] = k2; sB[u] = G + g; iB[u] = Q - 1 - k2; kb[u] = low + P * k2;
+        } else if (k2 <= Q / 2) {                                      // row 0 pairs with itself
+          sA[u] = 0; iA[u] = k2; sB[u] = 0; iB[u] = (Q - k2) % Q; kb[u] = P * k2;
+        } else {                                                       // row P/2 pairs with itself
+          const unsigned kk = k2 - Q / 2 - 1;
+          sA[u] = G; iA[u] = kk; sB[u] = G; iB[u] = Q - 1 - kk; kb[u] = P / 2 + P * kk;
+        }
+        tq[u] = __ldg(a.tw2Q + iA[u]);
+        if (H) {
+          hk[u] = __ldg(H + kb[u]);
+          hm[u] = __ldg(H + ((Nc - kb[u]) & (Nc - 1)));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (!valid[u]) continue;
+        const unsigned pa = smap(sA[u], iA[u]), pb = smap(sB[u], iB[u]);
+        const bool same = (pa == pb);
+        float2 zk = smem[pa], zm = cconj(smem[pb]);
+        float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y + zm.y));
+        float2 d = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y - zm.y));
+        float2 o = make_float2(d.y, -d.x);   // -i * d
+        float2 t = cmul(o, cmul(s_rowtw[sA[u]], tq[u]));
+        float2 xk = cadd(e, t);
+        float2 xm = cconj(csub(e, t));
+        if (H) {
+          xk = cmul(xk, hk[u]);
+          xm = cmul(xm, hm[u]);
+        }
+        if (CONV) {
+          smem[pa] = xk;
+          if (!same) smem[pb] = xm;
+        } else {
+          Zblk[kb[u]] = xk;
+          if (!same) Zblk[Nc - kb[u]] = xm;
+        }
       }
     }
     if (tile == 0 && threadIdx.x == 0) {
@@ -302,7 +344,7 @@ struct ChanArgs {
 };
 
 template <int EPT, int EPI, unsigned FCT>
-__global__ void __launch_bounds__(FCT ? 512 : 1024, 1) k_chan_inv(ChanArgs a) {
+__global__ void __launch_bounds__((FCT && EPT == 32) ? 512 : 1024, 1) k_chan_inv(ChanArgs a) {
   extern __shared__ float2 smem[];
   const unsigned F = FCT ? FCT : a.F;
   const unsigned T = EPT ? F / (EPT ? EPT : 1) : 1;
@@ -403,6 +445,7 @@ __global__ void __launch_bounds__(FCT ? 512 : 1024, 1) k_chan_inv(ChanArgs a) {
       for (unsigned pr = 0; pr < nprod; pr++)
         atomicAdd(base + (uint64_t(pr / dndim) * nbin + bin) * dndim + pr % dndim, acc[pr]);
     };
+    const bool chunk_monotonic = a.sink.phase_per_sample > 0.0 && a.sink.phase_per_sample * double(L) < 0.25;
     const unsigned niter = (total + nthreads - 1) / nthreads;
     for (unsigned itr = 0; itr < niter; itr++) {
       const unsigned it = itr * nthreads + threadIdx.x;
@@ -413,20 +456,37 @@ __global__ void __launch_bounds__(FCT ? 512 : 1024, 1) k_chan_inv(ChanArgs a) {
         const unsigned m0 = (it - c * nchunk) * L;
         const unsigned m1 = min(nkeep, m0 + L);
         const unsigned fp = c * a.npol;
-        for (unsigned m = m0; m < m1; m++) {
-          const unsigned k = c * nbin + __ldg(plan + m);
-          float2 p = smem[fmap(fp, np0 + m)];
-          float2 q = a.npol > 1 ? smem[fmap(fp + 1, np0 + m)] : make_float2(0.f, 0.f);
-          float r[4] = {0.f, 0.f, 0.f, 0.f};
-          detect_products(a.sink.state, p, q, r);
-          if (k != key) {
-            if (key != 0xffffffffu) red_add(key, acc);
-            key = k;
-#pragma unroll
-            for (int pr = 0; pr < 4; pr++) acc[pr] = r[pr];
-          } else {
+        // When the phase advances by less than a quarter turn per chunk the bins of a chunk are
+        // monotonic, so first == last means the whole chunk falls into one bin (the common case:
+        // bins are usually many samples wide) and no per-sample bin look-up or compare is needed.
+        const unsigned bfirst = __ldg(plan + m0), blast = __ldg(plan + m1 - 1);
+        if (chunk_monotonic && bfirst == blast) {
+          key = c * nbin + bfirst;
+#pragma unroll 4
+          for (unsigned m = m0; m < m1; m++) {
+            float2 p = smem[fmap(fp, np0 + m)];
+            float2 q = a.npol > 1 ? smem[fmap(fp + 1, np0 + m)] : make_float2(0.f, 0.f);
+            float r[4] = {0.f, 0.f, 0.f, 0.f};
+            detect_products(a.sink.state, p, q, r);
 #pragma unroll
             for (int pr = 0; pr < 4; pr++) acc[pr] += r[pr];
+          }
+        } else {
+          for (unsigned m = m0; m < m1; m++) {
+            const unsigned k = c * nbin + __ldg(plan + m);
+            float2 p = smem[fmap(fp, np0 + m)];
+            float2 q = a.npol > 1 ? smem[fmap(fp + 1, np0 + m)] : make_float2(0.f, 0.f);
+            float r[4] = {0.f, 0.f, 0.f, 0.f};
+            detect_products(a.sink.state, p, q, r);
+            if (k != key) {
+              if (key != 0xffffffffu) red_add(key, acc);
+              key = k;
+#pragma unroll
+              for (int pr = 0; pr < 4; pr++) acc[pr] = r[pr];
+            } else {
+#pragma unroll
+              for (int pr = 0; pr < 4; pr++) acc[pr] += r[pr];
+            }
           }
         }
       }
@@ -589,8 +649,11 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
       a.P = pl->P; a.Q = pl->Q; a.lb = pl->lbB; a.npol = npol; a.nchan_in = nchan_in; a.Nc = pl->Nc;
       a.part0 = part0;
       dim3 grid(pl->Q / B, nb * nblk1);
-      const bool ct = (pl->P == 2048);           // compile-time-sized fast path (EPT 32)
-      dim3 block((pl->P / (ct ? 32 : 16)) * B);
+      const bool ct = (pl->P == 2048);           // compile-time-sized fast path
+      static const int k1_ept = getenv("B200_K1_EPT") ? atoi(getenv("B200_K1_EPT")) : 32;
+      const bool ct16 = ct && k1_ept == 16;
+      if (ct16) a.twPs = pl->twP.stage16;
+      dim3 block((pl->P / ((ct && !ct16) ? 32 : 16)) * B);
       size_t smem = size_t(pl->P) * B * sizeof(float2);
       if (getenv("B200_DEBUG") && part0 == 0) {
         int nb1 = 0, nb2 = 0;
@@ -599,7 +662,10 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
         fprintf(stderr, "[b200] K1 grid (%u,%u) block %u smem %zu occupancy ct=%d generic=%d\n", grid.x, grid.y, block.x, smem, nb1, nb2);
       }
       LaunchScope ls(ctx, KC_COLS_FWD);
-      if (ct) {
+      if (ct16) {
+        if (src.kind == SRC_F32) k_cols_fwd<SRC_F32, 16, 2048><<<grid, block, smem, st>>>(a);
+        else k_cols_fwd<SRC_CASPSR8, 16, 2048><<<grid, block, smem, st>>>(a);
+      } else if (ct) {
         if (src.kind == SRC_F32) k_cols_fwd<SRC_F32, 32, 2048><<<grid, block, smem, st>>>(a);
         else k_cols_fwd<SRC_CASPSR8, 32, 2048><<<grid, block, smem, st>>>(a);
       } else {
@@ -682,14 +748,19 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
       a.CB = CB; a.npol_cta = npol_cta;
       size_t smem = size_t(CB) * npol_cta * F * sizeof(float2);
       dim3 grid(pl->nchan_out / CB, nb, npol / npol_cta);
-      const bool ct = (F == 8192 && npol_cta == npol && CB == 1);   // compile-time-sized fast path (EPT 32)
-      dim3 block(CB * npol_cta * (ct ? F / 32 : T));
+      const bool ct = (F == 8192 && npol_cta == npol && CB == 1);   // compile-time-sized fast path
+      static const int k3_ept = getenv("B200_K3_EPT") ? atoi(getenv("B200_K3_EPT")) : 32;
+      const bool ct16 = ct && k3_ept == 16;
+      if (ct16) a.twFs = pl->twF.stage16;
+      dim3 block(CB * npol_cta * ((ct && !ct16) ? F / 32 : T));
       LaunchScope ls(ctx, KC_INV);
 #define B200_K3(E, FC)                                                                          \
   if (sk.kind == EPI_VOLT) k_chan_inv<E, EPI_VOLT, FC><<<grid, block, smem, st>>>(a);            \
   else if (sk.kind == EPI_DETECT) k_chan_inv<E, EPI_DETECT, FC><<<grid, block, smem, st>>>(a);   \
   else k_chan_inv<E, EPI_FOLD, FC><<<grid, block, smem, st>>>(a);
-      if (ct) {
+      if (ct16) {
+        B200_K3(16, 8192)
+      } else if (ct) {
         B200_K3(32, 8192)
       } else switch (ept) {
         case 16: B200_K3(16, 0) break;
@@ -710,6 +781,8 @@ static int plan_set_attributes(size_t maxs) {
 #define SET(k) if ((rc = set_smem(k, maxs)) != B200_OK) return rc;
   SET((k_cols_fwd<SRC_F32, 16, 0>)) SET((k_cols_fwd<SRC_CASPSR8, 16, 0>))
   SET((k_cols_fwd<SRC_F32, 32, 2048>)) SET((k_cols_fwd<SRC_CASPSR8, 32, 2048>))
+  SET((k_cols_fwd<SRC_F32, 16, 2048>)) SET((k_cols_fwd<SRC_CASPSR8, 16, 2048>))
+  SET((k_chan_inv<16, EPI_VOLT, 8192>)) SET((k_chan_inv<16, EPI_DETECT, 8192>)) SET((k_chan_inv<16, EPI_FOLD, 8192>))
   SET((k_rows<true, true, 16, 0>)) SET((k_rows<true, false, 16, 0>)) SET((k_rows<false, true, 16, 0>))
   SET((k_rows<false, false, 16, 0>)) SET((k_rows<true, false, 0, 0>)) SET((k_rows<false, false, 0, 0>))
   SET((k_rows<true, false, 32, 1024>)) SET((k_rows<false, false, 32, 1024>))

@@ -1,6 +1,7 @@
 // pipeline.cu -- fused path: raw bytes -> (K1, K2, K3 with detect+fold epilogue) -> PhaseSeries.
 // What dspsr computes with [IOManager(unpack), Filterbank|Convolution, Detection, Fold]
 // (Signal/Pulsar/LoadToFold1.C:117-599, SingleThread.C:405-431) when no operation sits between.
+#include <cstdlib>
 #include <cstring>
 
 #include "engine.cuh"
@@ -162,6 +163,10 @@ int b200_pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t input_
     sink.kind = EPI_FOLD;
     sink.bins = fold_bins(p->fold);
     sink.nbin = p->desc.nbin;
+    // one-bin-per-chunk shortcut of the fold epilogue: measured SLOWER than the per-sample walk on
+    // B200 (0.83 vs 0.76 ms per 32 parts of cfg1), so it is opt-in for experiments only
+    static const bool fold_fast = getenv("B200_FOLD_FAST") && atoi(getenv("B200_FOLD_FAST")) == 1;
+    sink.phase_per_sample = fold_fast ? pps : 0.0;
     sink.profile = b200_fold_device_profile(p->fold);
   } else {
     B200_REQUIRE(d_detected, "b200_pipeline_execute: nbin == 0 needs an output buffer for the detected series");
