@@ -1,0 +1,199 @@
+"""CPU tests of the product's host-side logic (no GPU, no compute kernels): the C-ABI library loads
+and exports what include/b200dsp.h declares, the exact fold bin plan, the host math against the
+oracle, the FFT core index algebra (host emulation), sharding helpers, and a world_size-2 gloo run
+of the sub-integration combine."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from dspsr_b200 import _lib as L
+    lib = L.load()
+    hdr = open(os.path.join(ROOT, "include", "b200dsp.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 45
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libb200dsp.so does not export %s" % name
+    assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
+    assert lib.b200_version() >= 100
+
+
+def test_no_gpu_is_a_loud_error_not_a_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from dspsr_b200 import _lib as L
+    h = C.c_void_p()
+    rc = L.load().b200_context_create(0, None, C.byref(h))
+    assert rc != 0 and b"no CUDA device" in L.load().b200_last_error()
+    from dspsr_b200 import engine as E
+    with pytest.raises(RuntimeError):
+        E.Context(0)
+
+
+def test_product_never_touches_the_oracle():
+    # the product (dspsr_b200/, include/) must not import, link or name anything under oracle/
+    for base, _, files in os.walk(os.path.join(ROOT, "dspsr_b200")):
+        if "_build" in base or "__pycache__" in base:
+            continue
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                txt = open(os.path.join(base, fn)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), fn
+                assert "liboracle" not in txt and "orc_" not in txt, fn
+
+
+def test_phase_segments_equal_sequential_recurrence(oracle):
+    from dspsr_b200 import engine as E
+    rng = np.random.default_rng(0)
+    cases = [(0.3, 7.2e-6, 300000), (0.999999, 0.013, 5000), (0.0, 0.5, 1000), (0.7, 1e-9, 100000),
+             (0.25, 0.25, 100), (0.1, 0.7, 1000), (-0.3, 3.3e-4, 50000), (5.75, 1e-3, 10000)]
+    for _ in range(30):
+        cases.append((rng.random(), 10 ** rng.uniform(-7, -1.3), int(rng.integers(1, 100000))))
+    for _ in range(20):   # few significant bits: round-half-even ties in the recurrence
+        cases.append((rng.integers(0, 1 << 20) / float(1 << 20),
+                      rng.integers(1, 1 << 12) / float(1 << (12 + rng.integers(1, 40))), 20000))
+    for phi, pps, n in cases:
+        for nbin in (1024, 1000):
+            ref, phi_end_ref = E.phase_bins_sequential(phi, pps, nbin, n)
+            orc, _, _, phi_end_orc = oracle.fold_plan(phi, pps, nbin, n)
+            segs, phi_end = E.phase_segments(phi, pps, n, 1 << 18)
+            got = E.expand_segments_numpy(segs, nbin, n)
+            assert np.array_equal(ref, orc) and np.array_equal(got, ref), (phi, pps, n, nbin)
+            assert phi_end == phi_end_ref == phi_end_orc
+            assert sum(s.count for s in segs) == n
+    segs, _ = E.phase_segments(0.3, 7.16e-6, 466000)     # a cfg1 block of 64 parts: a handful of segments
+    assert len(segs) < 100
+    assert E.phase_segments(0.3, 1e-3, 0)[0] == []        # empty input
+
+
+def test_hostmath_bitexact_with_oracle(oracle):
+    from dspsr_b200 import hostmath as HM
+    from dspsr_b200 import workloads as W
+    for twos in (True, False):
+        a, sa = HM.bittable8(twos)
+        b, sb = oracle.bittable8(twos)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and sa == sb
+    for args in [(1382, -400, 67.99, 1, 256, True), (1400, 128, 50, 1, 4096, True), (1284, 16, 0.5, 4, 4, False),
+                 (1400, 64, 1, 1, 8, False)]:
+        d, H = HM.dedispersion(*args)
+        do, Ho = oracle.dedispersion(*args)
+        assert (d.ndat, d.impulse_pos, d.impulse_neg) == (do.ndat, do.impulse_pos, do.impulse_neg)
+        assert np.array_equal(H.view(np.uint32), Ho.view(np.uint32))
+    with pytest.raises(Exception):
+        HM.dedispersion(1400, 400, 1500, 1, 1, False, build=False)
+    p = HM.Polyco(W.polyco_text())
+    po = oracle.polyco_parse(W.polyco_text())
+    start = HM.utc_to_mjd("2010-04-13-02:05:45")
+    assert start == (55299, 7545, 0.0)
+    for dt in (0.0, 1.2345678, 600.000001, 3599.5):
+        mjd = HM.mjd_add(start, dt)
+        assert p.phase(mjd) == oracle.polyco_phase(po, *mjd)[0]
+        assert p.frequency(mjd) == oracle.polyco_frequency(po, *mjd)
+    phi, pps = HM.fold_phase(p, start, 0, 1.5625e6)
+    assert 0 <= phi < 1 and pps == pytest.approx(7.16e-6, rel=1e-2)
+
+
+def test_fft_core_index_algebra_on_the_host():
+    """Builds csrc/host_fft_emul.cu with nvcc (host code only) and runs it: the very same
+    __host__ __device__ Stockham stage / twiddle / shared-memory map code the kernels use."""
+    exe = os.path.join(ROOT, "dspsr_b200", "_build", "host_fft_emul")
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "dspsr_b200", "csrc"), "../_build/host_fft_emul"],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout[-2000:]
+
+
+def test_sharding_helpers():
+    from dspsr_b200 import sharding as S
+    for total, world in [(64, 8), (10, 4), (3, 8), (1024, 3)]:
+        parts = [S.shard_parts(total, world, r) for r in range(world)]
+        assert sum(n for _, n in parts) == total
+        pos = 0
+        for first, n in parts:
+            assert first == pos
+            pos += n
+        assert max(n for _, n in parts) - min(n for _, n in parts) <= 1
+    lo, hi = S.part_byte_range(4, 2, 1000, 100, 2)
+    assert (lo, hi) == (8000, 12200)
+
+
+def _gloo_worker(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle as O
+    import synth
+    from dspsr_b200 import sharding as S
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    lut, _ = O.bittable8()
+    f = O.fb_sizes(1, 1, 2, 8, 64, 5, 6)
+    total_parts, nbin = 7, 32            # ragged: 4 + 3 parts
+    ndat = (total_parts * f.nsamp_step + f.nsamp_overlap + 3) // 4 * 4
+    raw = synth.caspsr_bytes(ndat, seed=21)
+    H = np.exp(1j * np.random.default_rng(21).uniform(-3, 3, (8, 64))).astype(np.complex64)
+    pipe = O.make_pipe(0, 1, 2, 1, lut, 0.0, f, None, H, "Coherence", 4, nbin)
+    first, n = S.shard_parts(total_parts, world, rank)
+    lo, hi = S.part_byte_range(first, n, f.nsamp_step, f.nsamp_overlap, 2)
+    assert hi <= raw.size
+    # every rank folds its own super-block with the phase of ITS first output sample; the CPU
+    # oracle stands in for the GPU here -- the test is about sharding + combine
+    pps = 1.0 / 61.7
+    phi = (0.15 + first * f.nkeep * pps) % 1.0
+    prof = np.zeros((8, 1, nbin * 4), np.float32)
+    hits = np.zeros(nbin, np.uint32)
+    O.lib().orc_pipe_block(C.byref(pipe), raw.ctypes.data_as(C.c_void_p), C.c_uint64(first), C.c_uint64(n),
+                           C.c_double(phi), C.c_double(pps), prof.ctypes.data_as(C.c_void_p),
+                           hits.ctypes.data_as(C.c_void_p), None)
+    tp = torch.from_numpy(prof)
+    th = torch.from_numpy(hits.astype(np.int32))
+    il, nt = S.combine_time_sharded(tp, th, n * f.nkeep / 1e6, n * f.nkeep)
+    # channel-sharded gather of ragged shards
+    c0, cn = S.shard_channels(5, world, rank)
+    local = torch.arange(c0, c0 + cn, dtype=torch.float32).reshape(cn, 1).repeat(1, 3)
+    gathered = S.gather_channel_sharded(local, 5)
+    if rank == 0:
+        np.savez(tmp, prof=tp.numpy(), hits=th.numpy(), nt=nt, il=il, gathered=gathered.numpy())
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_time_sharded_combine(oracle, tmp_path):
+    import socket
+    import torch.multiprocessing as mp
+    import synth
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    tmp = str(tmp_path / "out.npz")
+    mp.spawn(_gloo_worker, args=(2, port, tmp), nprocs=2, join=True)
+    g = np.load(tmp)
+    # single-process answer: the two super-blocks folded one after the other
+    lut, _ = oracle.bittable8()
+    f = oracle.fb_sizes(1, 1, 2, 8, 64, 5, 6)
+    total_parts, nbin = 7, 32
+    ndat = (total_parts * f.nsamp_step + f.nsamp_overlap + 3) // 4 * 4
+    raw = synth.caspsr_bytes(ndat, seed=21)
+    H = np.exp(1j * np.random.default_rng(21).uniform(-3, 3, (8, 64))).astype(np.complex64)
+    pipe = oracle.make_pipe(0, 1, 2, 1, lut, 0.0, f, None, H, "Coherence", 4, nbin)
+    pps = 1.0 / 61.7
+    prof = np.zeros((8, 1, nbin * 4), np.float32)
+    hits = np.zeros(nbin, np.uint32)
+    for first, n in ((0, 4), (4, 3)):
+        phi = (0.15 + first * f.nkeep * pps) % 1.0
+        oracle.lib().orc_pipe_block(C.byref(pipe), raw.ctypes.data_as(C.c_void_p), C.c_uint64(first), C.c_uint64(n),
+                                    C.c_double(phi), C.c_double(pps), prof.ctypes.data_as(C.c_void_p),
+                                    hits.ctypes.data_as(C.c_void_p), None)
+    assert np.array_equal(g["hits"].astype(np.uint32), hits) and int(g["nt"]) == total_parts * f.nkeep
+    assert synth.relerr(g["prof"], prof) < 1e-6
+    assert np.array_equal(g["gathered"][:, 0], np.arange(5, dtype=np.float32))
