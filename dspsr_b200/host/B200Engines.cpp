@@ -1,0 +1,161 @@
+// B200Engines.cpp -- see B200Engines.h.  No CUDA here: everything goes through the C ABI.
+#include "B200Engines.h"
+
+namespace B200 {
+
+void check(int status, const char* where) {
+  if (status != B200_OK) throw Error(FailedCall, where, "%s", b200_last_error());
+}
+
+void* DeviceMemory::do_allocate(size_t nbytes) {
+  void* p = 0;
+  check(b200_malloc(ctx, nbytes, &p), "B200::DeviceMemory::do_allocate");
+  return p;
+}
+void DeviceMemory::do_free(void* p) { b200_free(ctx, p); }
+
+// ---- Filterbank ---------------------------------------------------------------------------------
+FilterbankEngine::~FilterbankEngine() { b200_fb_plan_destroy(plan); }
+
+void FilterbankEngine::setup(dsp::Filterbank* filterbank) {
+  // what CUDA::FilterbankEngine::setup reads (FilterbankCUDA.cu:60-170)
+  b200_fb_desc d;
+  d.input_real = filterbank->get_input()->get_state() == Signal::Nyquist;
+  d.input_nchan = filterbank->get_input()->get_nchan();
+  d.npol = filterbank->get_input()->get_npol();
+  d.nchan_subband = filterbank->get_nchan_subband();
+  d.freq_res = filterbank->get_freq_res();
+  d.nfilt_pos = d.nfilt_neg = 0;
+  d.h_response = 0;
+  d.max_npart = 0;
+  if (filterbank->has_response()) {
+    const dsp::Response* r = filterbank->get_response();
+    if (r->get_ndim() != 2) throw Error(InvalidState, "B200::FilterbankEngine::setup", "matrix responses are not supported");
+    d.nfilt_pos = r->get_impulse_pos();
+    d.nfilt_neg = r->get_impulse_neg();
+    d.h_response = r->get_datptr(0, 0);
+  }
+  filterbank->set_passband(NULL);   // the engine does not integrate the bandpass (FilterbankCUDA.cu:73-77)
+  if (plan) b200_fb_plan_destroy(plan);
+  plan = 0;
+  check(b200_fb_plan_create(ctx, &d, &plan), "B200::FilterbankEngine::setup");
+}
+
+void FilterbankEngine::perform(const dsp::TimeSeries* in, dsp::TimeSeries* out, uint64_t npart,
+                               const uint64_t in_step, const uint64_t out_step) {
+  check(b200_fb_perform(plan, in->get_datptr(0, 0), in->get_nfloat_span(), out->get_datptr(0, 0),
+                        out->get_nfloat_span(), npart, in_step, out_step),
+        "B200::FilterbankEngine::perform");
+}
+
+void FilterbankEngine::finish() { check(b200_context_synchronize(ctx), "B200::FilterbankEngine::finish"); }
+
+// ---- Convolution --------------------------------------------------------------------------------
+ConvolutionEngine::~ConvolutionEngine() { b200_fb_plan_destroy(plan); }
+
+void ConvolutionEngine::prepare(dsp::Convolution* convolution) {
+  const dsp::Response* r = convolution->get_response();
+  b200_fb_desc d;
+  d.input_real = convolution->get_input()->get_state() == Signal::Nyquist;
+  d.input_nchan = convolution->get_input()->get_nchan();
+  d.npol = convolution->get_input()->get_npol();
+  d.nchan_subband = 1;
+  d.freq_res = r->get_ndat();
+  d.nfilt_pos = r->get_impulse_pos();
+  d.nfilt_neg = r->get_impulse_neg();
+  d.h_response = r->get_datptr(0, 0);
+  d.max_npart = 0;
+  if (plan) b200_fb_plan_destroy(plan);
+  plan = 0;
+  check(b200_fb_plan_create(ctx, &d, &plan), "B200::ConvolutionEngine::prepare");
+  b200_fb_info info;
+  check(b200_fb_plan_info(plan, &info), "B200::ConvolutionEngine::prepare");
+  nsamp_step = info.nsamp_step;
+  nkeep = info.nkeep;
+  ndim = d.input_real ? 1 : 2;
+  if (info.nsamp_fft != convolution->get_minimum_samples())
+    throw Error(InvalidState, "B200::ConvolutionEngine::prepare", "nsamp_fft mismatch %u != %u", info.nsamp_fft,
+                convolution->get_minimum_samples());
+}
+
+void ConvolutionEngine::perform(const dsp::TimeSeries* in, dsp::TimeSeries* out, unsigned npart) {
+  check(b200_fb_perform(plan, in->get_datptr(0, 0), in->get_nfloat_span(), out->get_datptr(0, 0),
+                        out->get_nfloat_span(), npart, uint64_t(nsamp_step) * ndim, uint64_t(nkeep) * 2),
+        "B200::ConvolutionEngine::perform");
+}
+
+// ---- Detection ----------------------------------------------------------------------------------
+void DetectionEngine::polarimetry(unsigned ndim, const dsp::TimeSeries* in, dsp::TimeSeries* out) {
+  // the caller fixes the output state before the call in the out-of-place case (Detection.C:109-110)
+  const int state = out->get_state() == Signal::Stokes ? B200_STOKES : B200_COHERENCE;
+  check(b200_detect(ctx, state, ndim, in->get_datptr(0, 0), in->get_nfloat_span(), in->get_nchan(), in->get_npol(),
+                    in->get_ndat(), out->get_datptr(0, 0), out->get_nfloat_span()),
+        "B200::DetectionEngine::polarimetry");
+}
+
+void DetectionEngine::square_law(const dsp::TimeSeries* in, dsp::TimeSeries* out) {
+  const int state = out->get_npol() == 1 ? B200_INTENSITY : B200_PPQQ;
+  check(b200_detect(ctx, state, 1, in->get_datptr(0, 0), in->get_nfloat_span(), in->get_nchan(), in->get_npol(),
+                    in->get_ndat(), out->get_datptr(0, 0), out->get_nfloat_span()),
+        "B200::DetectionEngine::square_law");
+}
+
+// ---- Fold ---------------------------------------------------------------------------------------
+FoldEngine::FoldEngine(b200_context* c) : ctx(c), handle(0), nbin(0), ndat_folded(0) {
+  use_set_bins = true;   // Fold::fold then calls set_bins once per block instead of set_bin per sample
+  device_profiles = new dsp::PhaseSeries;
+}
+FoldEngine::~FoldEngine() { b200_fold_destroy(handle); }
+
+void FoldEngine::set_nbin(unsigned n) { nbin = n; }
+
+void FoldEngine::ensure() {
+  if (handle) return;
+  setup();   // fills nchan, npol, ndim, input, input_span from the parent (Fold.C:973-1011)
+  check(b200_fold_create(ctx, nchan, npol, ndim, nbin, &handle), "B200::FoldEngine");
+}
+
+void FoldEngine::set_ndat(uint64_t, uint64_t) {}
+
+void FoldEngine::set_bin(uint64_t, double, double) {
+  throw Error(InvalidState, "B200::FoldEngine::set_bin", "this engine plans bins itself (use_set_bins)");
+}
+
+uint64_t FoldEngine::set_bins(double phi, double phase_per_sample, uint64_t ndat, uint64_t idat0) {
+  ensure();
+  setup();   // the input pointer may change from block to block
+  check(b200_fold_set_bins(handle, phi, phase_per_sample, ndat, idat0, &ndat_folded), "B200::FoldEngine::set_bins");
+  last_hits.resize(nbin);
+  check(b200_fold_get_bin_hits(handle, last_hits.data()), "B200::FoldEngine::set_bins");
+  synchronized = false;
+  return ndat_folded;
+}
+
+uint64_t FoldEngine::get_bin_hits(int ibin) { return last_hits[ibin]; }
+
+dsp::PhaseSeries* FoldEngine::get_profiles() { return parent ? parent->get_output() : device_profiles.get(); }
+
+void FoldEngine::fold() {
+  check(b200_fold_fold(handle, input, input_span), "B200::FoldEngine::fold");
+}
+
+void FoldEngine::synch(dsp::PhaseSeries* out) {
+  if (synchronized || !handle) return;   // idempotent, as FoldCUDA.cu:132-147
+  // the stand-in PhaseSeries keeps [chan][pol][bin][dim] planes with span nbin*ndim: copy plane by plane
+  std::vector<float> tmp(size_t(nchan) * npol * nbin * ndim);
+  check(b200_fold_synch(handle, tmp.data()), "B200::FoldEngine::synch");
+  for (unsigned c = 0; c < nchan; c++)
+    for (unsigned p = 0; p < npol; p++) {
+      float* dst = out->get_datptr(c, p);
+      const float* src = tmp.data() + (size_t(c) * npol + p) * nbin * ndim;
+      for (unsigned i = 0; i < nbin * ndim; i++) dst[i] = src[i];
+    }
+  synchronized = true;
+}
+
+void FoldEngine::zero() {
+  if (handle) check(b200_fold_zero(handle), "B200::FoldEngine::zero");
+  synchronized = false;
+}
+
+}  // namespace B200

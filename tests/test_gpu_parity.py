@@ -280,3 +280,39 @@ def test_pipeline_cfg1(ctx, oracle):
     # BASELINE configs[0] at full shape: 256 x 8192, 1024 bins, Coherence, 2 blocks x 2 parts
     err = _pipeline_case(ctx, oracle, 256, 8192, 457, 459, 2, "Coherence", 4, 1024, nblock=2, pps=7.18e-6)
     assert err <= TOL, err
+
+
+# ------------------------------------------------------------------------------------ C++ engine shims
+def test_cpp_engine_shims_demo(ctx, oracle, tmp_path):
+    """host/b200_demo drives B200::FilterbankEngine / DetectionEngine / FoldEngine through the
+    stand-in dsp::Filterbank / Detection / Fold operators (the reference's engine interfaces)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "dspsr_b200", "host", "b200_demo")
+    assert os.path.exists(exe), "run __graft_entry__.build() first"
+    lut, _ = oracle.bittable8()
+    C, nbin, npart = 16, 64, 4
+    d, H = oracle.dedispersion(1382.0, -400.0, 0.05, 1, C, True)
+    f = oracle.fb_sizes(1, 1, 2, C, d.ndat, d.impulse_pos, d.impulse_neg)
+    ndat = npart * f.nsamp_step + f.nsamp_overlap
+    ndat = (ndat + 3) // 4 * 4
+    raw = synth.caspsr_bytes(ndat, seed=31)
+    phi, pps = 0.31, 1.0 / (0.45 * npart * f.nkeep)
+    (tmp_path / "raw.bin").write_bytes(raw.tobytes())
+    (tmp_path / "resp.c64").write_bytes(H.tobytes())
+    out = tmp_path / "out.bin"
+    r = subprocess.run([exe, str(tmp_path / "raw.bin"), str(tmp_path / "resp.c64"), str(C), str(d.ndat),
+                        str(d.impulse_pos), str(d.impulse_neg), str(nbin), repr(phi), repr(pps), str(out)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr + r.stdout
+    buf = np.fromfile(out, dtype=np.uint8)
+    nprof = C * 4 * nbin
+    prof = buf[: nprof * 4].view(np.float32).reshape(C, 1, nbin * 4)
+    hits = buf[nprof * 4:].view(np.uint32)
+    # the demo hands the operators the whole stream at once: npart' = (ndat - overlap) / step parts
+    npart_all = (ndat - f.nsamp_overlap) // f.nsamp_step
+    p = oracle.make_pipe(0, 1, 2, 1, lut, 0.0, f, None, H, "Coherence", 4, nbin)
+    ref, ref_hits = oracle.pipe_run(p, raw, 1, npart_all, [phi], [pps], 1)
+    assert np.array_equal(hits, ref_hits)
+    assert synth.relerr(prof, ref) <= TOL
