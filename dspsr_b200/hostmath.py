@@ -78,3 +78,11 @@ def fold_phase(predictor, start_mjd, idat_start, rate, reference_phase=0.0):
     phi = predictor.phase(t0) - reference_phase
     pfold = 1.0 / predictor.frequency(t0)
     return phi, (1.0 / rate) / pfold
+
+
+def optimal_fft_length(nbadperfft, nfft_max=0):
+    """optimal_fft_length (Signal/General/optimize_fft.c:63-127)."""
+    f = L.load().b200_optimal_fft_length
+    f.restype = C.c_int64
+    f.argtypes = [C.c_uint64, C.c_uint64]
+    return f(nbadperfft, nfft_max)

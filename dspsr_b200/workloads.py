@@ -52,3 +52,34 @@ def cfg5_subband(k):
 def polyco_text():
     with open(VELA_POLYCO) as f:
         return f.read()
+
+
+_INSTRUMENT = {"CASPSR8": "CASPSR", "GENERIC8": "UNKNOWN", "MEERKAT8": "MKBF", "UWB16": "UWB", "CPSR2": "CPSR2"}
+
+
+def dada_header(cfg, obs_offset=0, hdr_size=4096):
+    """4096-byte ASCII DADA header of a configuration (keys per Kernel/Classes/ASCIIObservation.C:95-400,
+    SURVEY Appendix A.8), NUL-padded, so that a real dspsr could read the synthetic file."""
+    lines = [
+        ("HDR_VERSION", "1.0"), ("HDR_SIZE", str(hdr_size)), ("INSTRUMENT", _INSTRUMENT[cfg["format"]]),
+        ("TELESCOPE", "PKS"), ("SOURCE", "J0835-4510"), ("MODE", "PSR"), ("FREQ", repr(float(cfg["freq"]))),
+        ("BW", repr(float(cfg["bw"]))), ("NCHAN", str(cfg["input_nchan"])), ("NPOL", str(cfg["npol"])),
+        ("NDIM", "1" if cfg["input_real"] else "2"), ("NBIT", str(cfg["nbit"])), ("TSAMP", repr(float(cfg["tsamp_us"]))),
+        ("UTC_START", cfg["utc_start"]), ("OBS_OFFSET", str(obs_offset)), ("RESOLUTION", "4"),
+    ]
+    text = "".join("%-16s %s\n" % kv for kv in lines)
+    assert len(text) < hdr_size
+    return text + "\0" * (hdr_size - len(text))
+
+
+def parse_dada_header(raw):
+    """key -> value strings of an ASCII DADA header (first whitespace-separated token after the key, as
+    ascii_header_get's sscanf does; Kernel/Classes/ascii_header.c)."""
+    if isinstance(raw, bytes):
+        raw = raw.split(b"\0", 1)[0].decode()
+    out = {}
+    for line in raw.split("\n"):
+        line = line.split("#", 1)[0].split()
+        if len(line) >= 2:
+            out[line[0]] = line[1]
+    return out
