@@ -36,6 +36,41 @@ struct FbSink {
   float* profile;           // [chan][npol'][nbin][dndim]
 };
 
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------
+// detection products (cross_detect.ic:25-41, stokes_detect.ic:21-44, Detection.C:264-301);
+// explicit _rn intrinsics: no FMA contraction, bit-identical to the CPU loops.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int detect_products(int state, float2 p, float2 q, float* r) {
+  float pp = __fadd_rn(__fmul_rn(p.x, p.x), __fmul_rn(p.y, p.y));
+  float qq = __fadd_rn(__fmul_rn(q.x, q.x), __fmul_rn(q.y, q.y));
+  if (state == B200_INTENSITY) {
+    r[0] = __fadd_rn(pp, qq);
+    return 1;
+  }
+  if (state == B200_PPQQ) {
+    r[0] = pp;
+    r[1] = qq;
+    return 2;
+  }
+  float re = __fadd_rn(__fmul_rn(p.x, q.x), __fmul_rn(p.y, q.y));
+  float im = __fsub_rn(__fmul_rn(p.x, q.y), __fmul_rn(p.y, q.x));
+  if (state == B200_COHERENCE) {
+    r[0] = pp; r[1] = qq; r[2] = re; r[3] = im;
+  } else {
+    r[0] = __fadd_rn(pp, qq); r[1] = __fsub_rn(pp, qq); r[2] = __fmul_rn(2.f, re); r[3] = __fmul_rn(2.f, im);
+  }
+  return 4;
+}
+
+__host__ __device__ inline unsigned state_nprod(int state, unsigned npol) {
+  if (state == B200_INTENSITY) return 1;
+  if (state == B200_PPQQ) return npol;
+  return 4;
+}
+
+#endif
+
 }  // namespace b200
 
 struct b200_fb_plan {
@@ -53,9 +88,18 @@ struct b200_fb_plan {
   float2* scratchA;         // batch*nblk*Nc
   float2* scratchZ;         // batch*nblk*Nc (unused on the conv path)
   uint64_t scratch_bytes;
+  // second-generation kernels (fastpath.cu): which passes they cover for this plan + their stage tables
+  bool fast_k1, fast_k2, fast_k3;
+  float2 *c2P, *c2Q, *c2F;
 };
 
 namespace b200 {
 // Runs the engine over npart parts: source -> (K1, K2, K3) -> sink.
 int fb_run(b200_fb_plan* plan, const FbSource& src, const FbSink& sink, uint64_t npart);
+// fastpath.cu
+int fast_plan_init(b200_fb_plan* plan);
+void fast_plan_free(b200_fb_plan* plan);
+int fast_k1(b200_fb_plan* plan, const FbSource& src, uint64_t part0, unsigned nb);
+int fast_k2(b200_fb_plan* plan, unsigned nb);
+int fast_k3(b200_fb_plan* plan, const FbSink& sink, uint64_t part0, unsigned nb);
 }

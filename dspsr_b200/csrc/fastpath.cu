@@ -1,0 +1,663 @@
+// fastpath.cu -- second-generation K1 / K2 / K3 for the transform sizes of the headline workloads.
+//
+// Same three-kernel decomposition as filterbank.cu (forward column pass, row pass + real split +
+// response, per-channel inverse pass + epilogue) on the fft_c2.cuh core: 16 points of TWO sequences
+// per thread, 128-bit padded shared-memory exchanges with immediate addressing, stage twiddles
+// loaded once per pair.
+//   K1  k1_c2   pair = two adjacent columns: one 32-bit load carries the 4 raw bytes of both, one
+//               128-bit store writes both
+//   K2  k2_c2   pair = row k1 and its mirror row P-k1 (real input) or two adjacent rows (complex)
+//   K3  k3_c2   pair = the two polarisations of an output channel: detection straight from registers
+// All three are PERSISTENT: one 512-thread CTA per SM loops over tiles, and the global loads of the
+// next tile are issued into the (by then dead) data registers before the current tile's epilogue,
+// so load latency hides behind the store / split / fold phase instead of adding to it (one tile
+// fills the SM's registers and most of its shared memory: there is no second CTA to overlap with).
+// fb_run (filterbank.cu) dispatches here when the plan's sizes are instantiated below; every other
+// shape keeps the generic kernels.  B200_FAST=0 disables the dispatch (A/B measurements).
+#include <cstdlib>
+#include <vector>
+
+#include "engine.cuh"
+#include "fft_c2.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ float2 ldg_nc_f2(const float2* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+
+struct CtaSync {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+// ------------------------------------------------------------------------------------------
+// K1: unpack + forward column pass.  tile = (column block of 2*NP columns, block = part x chan x pol)
+// ------------------------------------------------------------------------------------------
+struct K1Args {
+  const void* src;
+  uint64_t span, step;
+  const float* lut;
+  float2* dst;
+  const float2* tw;      // c2 stage tables of P
+  const float2* blo;
+  const float2* bhi;
+  unsigned Q, npol, nchan_in, Nc, nblk;
+  uint64_t part0;
+  unsigned dbg;
+};
+
+template <int SRC, unsigned P, int NP>
+__global__ void __launch_bounds__(NP*(P / 16), 1) k1_c2(K1Args a) {
+  extern __shared__ float4 smem4[];
+  __shared__ float s_lut[256];
+  __shared__ float4 s_h[16 * NP];   // [e][pair] = (W_N^(n2a*T*e), W_N^(n2b*T*e))
+  constexpr unsigned T = P / 16;
+  static_assert(c2::pair_slots<P>() % 8 == 0, "region skew assumes an 8-aligned pair size");
+  constexpr unsigned RS = c2::pair_slots<P>() + 8 / NP;   // regions skewed so the NP pairs of a phase hit distinct banks
+  const unsigned pair = threadIdx.x % NP, j = threadIdx.x / NP;
+  const unsigned Q = a.Q;
+  const unsigned ncolblk = Q / (2 * NP);
+  const unsigned ntiles = ncolblk * a.nblk;
+
+  if (SRC == SRC_CASPSR8) {
+    for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = a.lut[i];
+    __syncthreads();
+  }
+
+  // CASPSR: byte 8*(i/4) + 4*pol + i%4 (CASPSRUnpacker.C:141-187); columns n2, n2+1 = samples
+  // 2*n2 .. 2*n2+3 = one 4-byte group of this polarisation
+  auto raw_ptr = [&](unsigned t) -> const unsigned char* {
+    const unsigned col0 = (t % ncolblk) * (2 * NP), blk = t / ncolblk;
+    const unsigned pol = blk % a.npol;
+    const uint64_t part = a.part0 + blk / (a.npol * a.nchan_in);
+    return static_cast<const unsigned char*>(a.src) + 2ull * (part * a.step) + 4u * pol +
+           4ull * (uint64_t(j) * Q + col0 + 2 * pair);
+  };
+
+  unsigned w[16];
+  unsigned t = blockIdx.x;
+  if (SRC == SRC_CASPSR8 && t < ntiles && !(a.dbg & 4)) {
+    const unsigned char* raw = raw_ptr(t);
+#pragma unroll
+    for (int e = 0; e < 16; e++) w[e] = __ldg(reinterpret_cast<const unsigned*>(raw + 4ull * Q * T * e));
+  }
+
+  for (; t < ntiles; t += gridDim.x) {
+    const unsigned col0 = (t % ncolblk) * (2 * NP), blk = t / ncolblk;
+    const unsigned n2 = col0 + 2 * pair;
+    const unsigned pol = blk % a.npol;
+    const unsigned ic = (blk / a.npol) % a.nchan_in;
+    const uint64_t part = a.part0 + blk / (a.npol * a.nchan_in);
+
+    // twiddles of this tile (loads in flight while the samples are converted)
+    float2 shv = make_float2(1.f, 0.f);
+    if (threadIdx.x < 16 * NP * 2) {
+      const unsigned e = threadIdx.x / (2 * NP), col = threadIdx.x % (2 * NP);
+      shv = big_twiddle<false>(a.blo, a.bhi, ((col0 + col) * T * e) & (a.Nc - 1));
+    }
+    // W_N^(n2*k1), k1 = j + e*T, factorised into W_N^(n2*j) (per thread) and W_N^(n2*T*e) (s_h)
+    const float2 wa = big_twiddle<false>(a.blo, a.bhi, (n2 * j) & (a.Nc - 1));
+    const float2 wb = big_twiddle<false>(a.blo, a.bhi, ((n2 + 1) * j) & (a.Nc - 1));
+
+    float2 va[16], vb[16];
+    if (a.dbg & 4) {
+#pragma unroll
+      for (int e = 0; e < 16; e++) { va[e] = make_float2(float(threadIdx.x + e), 1.f); vb[e] = make_float2(2.f, float(e)); }
+    } else if (SRC == SRC_CASPSR8) {
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        va[e] = make_float2(s_lut[w[e] & 255u], s_lut[(w[e] >> 8) & 255u]);
+        vb[e] = make_float2(s_lut[(w[e] >> 16) & 255u], s_lut[w[e] >> 24]);
+      }
+    } else {
+      const float2* f = reinterpret_cast<const float2*>(static_cast<const float*>(a.src) +
+                                                        (uint64_t(ic) * a.npol + pol) * a.span + part * a.step) +
+                        uint64_t(j) * Q + n2;
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        va[e] = ldg_nc_f2(f + uint64_t(Q) * T * e);
+        vb[e] = ldg_nc_f2(f + uint64_t(Q) * T * e + 1);
+      }
+    }
+    __syncthreads();     // the previous tile's readers of s_h and of the exchange buffer are done
+    if (threadIdx.x < 16 * NP * 2) reinterpret_cast<float2*>(s_h)[threadIdx.x] = shv;
+
+    if (!(a.dbg & 1)) c2::fft_pair<P, false>(va, vb, j, smem4 + pair * RS, a.tw, CtaSync());
+    else __syncthreads();
+
+    // prefetch the raw words of the next tile; they land while this tile is twiddled and stored
+    const unsigned tn = t + gridDim.x;
+    if (SRC == SRC_CASPSR8 && tn < ntiles && !(a.dbg & 4)) {
+      const unsigned char* raw = raw_ptr(tn);
+#pragma unroll
+      for (int e = 0; e < 16; e++) w[e] = __ldg(reinterpret_cast<const unsigned*>(raw + 4ull * Q * T * e));
+    }
+
+    float2* dst = a.dst + uint64_t(blk) * a.Nc + uint64_t(j) * Q + n2;
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+      const float4 h = s_h[e * NP + pair];
+      const float2 xa = cmul(cmul(va[e], wa), make_float2(h.x, h.y));
+      const float2 xb = cmul(cmul(vb[e], wb), make_float2(h.z, h.w));
+      if (!(a.dbg & 2) || xa.x == 12345.678f)
+        *reinterpret_cast<float4*>(dst + uint64_t(Q) * T * e) = make_float4(xa.x, xa.y, xb.x, xb.y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: forward row pass + real-input split + response.  tile = (G row pairs, block)
+// ------------------------------------------------------------------------------------------
+struct K2Args {
+  const float2* A;
+  float2* Z;
+  const float2* H;
+  const float2* tw;        // c2 stage tables of Q
+  const float2* tw2Q;      // exp(-2 pi i m / (2Q))
+  const float2* b2lo;
+  const float2* b2hi;
+  unsigned Nc, npol, nchan_in, nblk;
+  unsigned dbg;
+};
+
+template <unsigned P, unsigned Q, bool SPLIT>
+__global__ void __launch_bounds__(512, 1) k2_c2(K2Args a) {
+  extern __shared__ float4 smem4[];
+  constexpr unsigned T = Q / 16;
+  constexpr unsigned G = 512 / T;                          // sequence pairs per CTA
+  constexpr unsigned RS = c2::pair_slots<Q>() | 1u;        // odd: phase 2 walks the pairs lane by lane
+  constexpr unsigned TPB = SPLIT ? (P / 2) / G : P / (2 * G);   // tiles per block
+  __shared__ float2 s_rowtw[G + 1];
+  const unsigned g = threadIdx.x / T, j = threadIdx.x % T;
+  const unsigned Nc = a.Nc;
+  const unsigned ntiles = TPB * a.nblk;
+
+  float2 va[16], vb[16];
+  auto issue_loads = [&](unsigned tt) {
+    const unsigned tile = tt % TPB, blk = tt / TPB;
+    unsigned ra, rb;
+    if (SPLIT) {
+      const unsigned low = tile * G + g;
+      ra = low;
+      rb = low == 0 ? P / 2 : P - low;
+    } else {
+      ra = tile * 2 * G + 2 * g;
+      rb = ra + 1;
+    }
+    const float2* pa = a.A + uint64_t(blk) * Nc + uint64_t(ra) * Q + j;
+    const float2* pb = a.A + uint64_t(blk) * Nc + uint64_t(rb) * Q + j;
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+      if (a.dbg & 4) { va[e] = make_float2(float(threadIdx.x + e), 1.f); vb[e] = make_float2(2.f, float(e)); continue; }
+      va[e] = ldg_nc_f2(pa + e * T);
+      vb[e] = ldg_nc_f2(pb + e * T);
+    }
+  };
+
+  unsigned t = blockIdx.x;
+  if (t < ntiles) issue_loads(t);
+  for (; t < ntiles; t += gridDim.x) {
+    const unsigned tile = t % TPB, blk = t / TPB;
+    const unsigned ic = (blk / a.npol) % a.nchan_in;
+    if (SPLIT && threadIdx.x <= G) {
+      // W_2N^k, k = row + P*k2, factorises into W_2N^row (here) and W_2Q^k2 (tw2Q)
+      const unsigned r = threadIdx.x < G ? tile * G + threadIdx.x : P / 2;
+      s_rowtw[threadIdx.x] = big_twiddle<false>(a.b2lo, a.b2hi, r);
+    }
+    float4* sm = smem4 + g * RS;
+    if (!(a.dbg & 1)) c2::fft_pair<Q, false>(va, vb, j, sm, a.tw, CtaSync());
+    __syncthreads();
+    c2::store_natural<Q>(sm, va, vb, j);
+    __syncthreads();
+
+    // the rows of the next tile stream in while this tile is split, multiplied and stored
+    if (t + gridDim.x < ntiles) issue_loads(t + gridDim.x);
+
+    if (!((a.dbg & 2) && va[3].x != 12345.678f)) {
+      // ---- phase 2: lanes walk the G pairs first (G consecutive bins = one 64-byte segment of Z) ----
+      const float2* H = a.H ? a.H + uint64_t(ic) * Nc : nullptr;
+      float2* Zblk = a.Z + uint64_t(blk) * Nc;
+      const unsigned g2 = threadIdx.x % G, kk = threadIdx.x / G;   // kk < T
+      const float4* sg = smem4 + g2 * RS;
+      constexpr int SSTEP = T / 16 * 17;                           // pad16 advance of T elements
+      constexpr int KSTEP = T * P;                                 // bin advance of T elements
+
+      if (!SPLIT) {
+        const unsigned k0 = tile * 2 * G + 2 * g2 + P * kk;
+        const float4* sa = sg + c2::pad16(kk);
+#pragma unroll 4
+        for (int it = 0; it < 16; it++) {
+          const float4 x = sa[SSTEP * it];
+          const unsigned k = k0 + it * KSTEP;
+          float2 xa = make_float2(x.x, x.y), xb = make_float2(x.z, x.w);
+          if (H) {
+            const float4 h = __ldg(reinterpret_cast<const float4*>(H + k));
+            xa = cmul(xa, make_float2(h.x, h.y));
+            xb = cmul(xb, make_float2(h.z, h.w));
+          }
+          *reinterpret_cast<float4*>(Zblk + k) = make_float4(xa.x, xa.y, xb.x, xb.y);
+        }
+      } else {
+        // element k2 of row `low` is bin k = low + P*k2; its mirror N-k is element Q-1-k2 of row P-low:
+        //   e = (z_k + conj z_m)/2, d = (z_k - conj z_m)/2, t = -i d W_2N^k;  X_k = e + t, X_(N-k) = conj(e - t)
+        auto split = [&](float2 zk, float2 zmc, float2 w, float2& xk, float2& xm) {
+          const float2 e = make_float2(0.5f * (zk.x + zmc.x), 0.5f * (zk.y + zmc.y));
+          const float2 d = make_float2(0.5f * (zk.x - zmc.x), 0.5f * (zk.y - zmc.y));
+          const float2 tt = cmul(make_float2(d.y, -d.x), w);
+          xk = cadd(e, tt);
+          xm = cconj(csub(e, tt));
+        };
+        const unsigned low = tile * G + g2;
+        if (low != 0) {
+          const float2 rw = s_rowtw[g2];
+          const unsigned k0 = low + P * kk;
+          const float4* sa = sg + c2::pad16(kk);
+          const float4* sb = sg + c2::pad16(Q - 1 - kk);
+          const float2* t2 = a.tw2Q + kk;
+          const float2* Hk = H ? H + k0 : nullptr;
+          const float2* Hm = H ? H + (Nc - k0) : nullptr;
+          float2* Zk = Zblk + k0;
+          float2* Zm = Zblk + (Nc - k0);
+#pragma unroll 4
+          for (int it = 0; it < 16; it++) {
+            const float4 xa = sa[SSTEP * it];
+            const float4 xb = sb[-SSTEP * it];
+            const float2 w = cmul(rw, __ldg(t2 + it * int(T)));
+            float2 xk, xm;
+            split(make_float2(xa.x, xa.y), make_float2(xb.z, -xb.w), w, xk, xm);
+            if (H) {
+              xk = cmul(xk, __ldg(Hk + it * KSTEP));
+              xm = cmul(xm, __ldg(Hm - it * KSTEP));
+            }
+            Zk[it * KSTEP] = xk;
+            Zm[-it * KSTEP] = xm;
+          }
+        } else {
+          // rows 0 (sequence a) and P/2 (sequence b) mirror onto themselves
+          const float2 rwh = s_rowtw[G];
+          for (unsigned it = 0; it < 16; it++) {
+            const unsigned k2 = kk + it * T;
+            if (k2 <= Q / 2) {
+              const unsigned km2 = (Q - k2) % Q;
+              const float4 xa = sg[c2::pad16(k2)];
+              const float4 xm4 = sg[c2::pad16(km2)];
+              float2 xk, xm;
+              split(make_float2(xa.x, xa.y), make_float2(xm4.x, -xm4.y), __ldg(a.tw2Q + k2), xk, xm);
+              const unsigned k = P * k2, km = (Nc - k) & (Nc - 1);
+              if (H) { xk = cmul(xk, __ldg(H + k)); xm = cmul(xm, __ldg(H + km)); }
+              Zblk[k] = xk;
+              if (km2 != k2) Zblk[km] = xm;
+            }
+            if (k2 < Q / 2) {
+              const float4 xa = sg[c2::pad16(k2)];
+              const float4 xm4 = sg[c2::pad16(Q - 1 - k2)];
+              float2 xk, xm;
+              split(make_float2(xa.z, xa.w), make_float2(xm4.z, -xm4.w), cmul(rwh, __ldg(a.tw2Q + k2)), xk, xm);
+              const unsigned k = P / 2 + P * k2, km = Nc - k;
+              if (H) { xk = cmul(xk, __ldg(H + k)); xm = cmul(xm, __ldg(H + km)); }
+              Zblk[k] = xk;
+              Zblk[km] = xm;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();       // phase-2 readers are done before the next tile's first scatter
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: per-channel inverse pass (both polarisations per thread) + discard + epilogue.
+// tile = (CB output channels, part)
+// ------------------------------------------------------------------------------------------
+struct K3Args {
+  const float2* Z;
+  const float2* tw;        // c2 stage tables of F
+  unsigned C, Nc, nchan_in, nchan_out, npart;
+  unsigned nfilt_pos, nkeep;
+  uint64_t part0;
+  FbSink sink;
+  unsigned dbg;
+};
+
+// STATE >= 0: detection state fixed at compile time (no per-sample branches); -1: run-time state
+template <int STATE>
+__device__ __forceinline__ void detect4(int state, float2 p, float2 q, float* r) {
+  if (STATE == B200_COHERENCE) {
+    r[0] = __fadd_rn(__fmul_rn(p.x, p.x), __fmul_rn(p.y, p.y));
+    r[1] = __fadd_rn(__fmul_rn(q.x, q.x), __fmul_rn(q.y, q.y));
+    r[2] = __fadd_rn(__fmul_rn(p.x, q.x), __fmul_rn(p.y, q.y));
+    r[3] = __fsub_rn(__fmul_rn(p.x, q.y), __fmul_rn(p.y, q.x));
+  } else {
+    r[0] = r[1] = r[2] = r[3] = 0.f;
+    detect_products(state, p, q, r);
+  }
+}
+
+template <unsigned F, int EPI, int STATE>
+__global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
+  extern __shared__ float4 smem4[];
+  constexpr unsigned T = F / 16;
+  constexpr unsigned CB = 512 / T;                     // channels per CTA
+  constexpr unsigned RS = c2::pair_slots<F>();
+  const unsigned cb = threadIdx.x / T, j = threadIdx.x % T;
+  const unsigned tiles_per_part = a.nchan_out / CB;
+  const unsigned ntiles = tiles_per_part * a.npart;
+  const unsigned np0 = a.nfilt_pos, nkeep = a.nkeep;
+  const int state = STATE >= 0 ? STATE : a.sink.state;
+  const unsigned nprod = EPI == EPI_VOLT ? 1 : state_nprod(state, 2);
+  const unsigned dndim = EPI == EPI_VOLT ? 1 : a.sink.dndim, dnpol = nprod / dndim;
+  float4* sm = smem4 + cb * RS;
+
+  float2 vp[16], vq[16];
+  auto issue_loads = [&](unsigned tt) {
+    const unsigned ch = (tt % tiles_per_part) * CB + cb, partl = tt / tiles_per_part;
+    const unsigned ic = ch / a.C, csub = ch % a.C;
+    const uint64_t blk = (uint64_t(partl) * a.nchan_in + ic) * 2;
+    const float2* srcp = a.Z + blk * a.Nc + uint64_t(csub) * F + j;
+    const float2* srcq = srcp + a.Nc;
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+      if (a.dbg & 4) { vp[e] = make_float2(float(threadIdx.x + e), 1.f); vq[e] = make_float2(2.f, float(e)); continue; }
+      vp[e] = ldg_nc_f2(srcp + e * T);
+      vq[e] = ldg_nc_f2(srcq + e * T);
+    }
+  };
+
+  unsigned t = blockIdx.x;
+  if (t < ntiles) issue_loads(t);
+  for (; t < ntiles; t += gridDim.x) {
+    const unsigned ch0 = (t % tiles_per_part) * CB, ch = ch0 + cb, partl = t / tiles_per_part;
+    const uint64_t part = a.part0 + partl;
+    const unsigned tn = t + gridDim.x;
+
+    if (!(a.dbg & 1)) c2::fft_pair<F, true>(vp, vq, j, sm, a.tw, CtaSync());
+    if ((a.dbg & 2) && vp[3].x != 12345.678f) {
+      __syncthreads();
+      if (tn < ntiles) issue_loads(tn);
+      continue;
+    }
+
+    if (EPI == EPI_VOLT) {
+      float2* outp = reinterpret_cast<float2*>(a.sink.volt + (uint64_t(ch) * 2) * a.sink.volt_span + part * a.sink.volt_step);
+      float2* outq = reinterpret_cast<float2*>(a.sink.volt + (uint64_t(ch) * 2 + 1) * a.sink.volt_span + part * a.sink.volt_step);
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        const unsigned u = j + e * T - np0;             // unsigned: samples before nfilt_pos wrap to huge values
+        if (u < nkeep) {
+          outp[u] = vp[e];
+          outq[u] = vq[e];
+        }
+      }
+      __syncthreads();                                  // all gathers of the last stage are done
+      if (tn < ntiles) issue_loads(tn);
+      continue;
+    }
+
+    if (EPI == EPI_DETECT) {
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        const unsigned u = j + e * T - np0;
+        if (u < nkeep) {
+          float r[4];
+          detect4<STATE>(state, vp[e], vq[e], r);
+          const uint64_t osamp = part * nkeep + u;
+          for (unsigned pr = 0; pr < nprod; pr++) {
+            float* out = a.sink.det + (uint64_t(ch) * dnpol + pr / dndim) * a.sink.det_span;
+            out[osamp * dndim + pr % dndim] = r[pr];
+          }
+        }
+      }
+      __syncthreads();
+      if (tn < ntiles) issue_loads(tn);
+      continue;
+    }
+
+    // EPI_FOLD: detected products of the kept samples go back to shared memory in time order
+    // (slot pad16(t - nfilt_pos)); then every thread walks 16 consecutive samples of one channel,
+    // summing sequentially while the phase bin is unchanged (the order of Fold.C:844-852).  Runs that
+    // end inside the walk are added to the profile at once; the trailing run is first combined across
+    // the warp (neighbouring lanes hold neighbouring walks) so that one RED.ADD.F32 per (channel, bin)
+    // and warp reaches the global PhaseSeries.
+    constexpr unsigned L = 16;
+    const unsigned nchunk = (nkeep + L - 1) / L;
+    const unsigned total = CB * nchunk;
+    const unsigned* plan = a.sink.bins + partl * uint64_t(nkeep);
+    // bins of this thread's (first) walk: requested now, needed after the detection pass
+    unsigned b[16];
+    {
+      const unsigned it = threadIdx.x;
+      const unsigned c = (CB == 1) ? 0 : it / nchunk;
+      const unsigned m0 = (it - c * nchunk) * L;
+      if (it < total) {
+        const unsigned n = min(L, nkeep - m0);
+        const unsigned* pl = plan + m0;
+        if (n == L && (reinterpret_cast<uintptr_t>(pl) & 15) == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(pl) + i);
+            b[4 * i] = v.x; b[4 * i + 1] = v.y; b[4 * i + 2] = v.z; b[4 * i + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; i++) b[i] = (unsigned(i) < n) ? __ldg(pl + i) : 0xfffffffeu;
+        }
+      }
+    }
+    __syncthreads();                                      // all gathers of the last stage are done
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+      const unsigned u = j + e * T - np0;
+      if (u < nkeep) {
+        float r[4];
+        detect4<STATE>(state, vp[e], vq[e], r);
+        sm[c2::pad16(u)] = make_float4(r[0], r[1], r[2], r[3]);
+      }
+    }
+    __syncthreads();
+    // the spectra of the next tile stream in while this one is folded
+    if (tn < ntiles) issue_loads(tn);
+    {
+      const unsigned nbin = a.sink.nbin;
+      float* prof0 = a.sink.profile + uint64_t(ch0) * nbin * nprod;
+      const unsigned lane = threadIdx.x & 31u;
+      auto red_add = [&](unsigned key, const float* acc) {
+        // key = c*nbin + bin; profile layout per channel [npol'][nbin][ndim']
+        const unsigned c = key / nbin, bin = key - c * nbin;
+        float* base = prof0 + uint64_t(c) * nbin * nprod;
+        for (unsigned pr = 0; pr < nprod; pr++)
+          atomicAdd(base + (uint64_t(pr / dndim) * nbin + bin) * dndim + pr % dndim, acc[pr]);
+      };
+      const unsigned niter = (total + 511u) / 512u;
+      for (unsigned itr = 0; itr < niter; itr++) {
+        const unsigned it = itr * 512u + threadIdx.x;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        unsigned key = 0xffffffffu;
+        if (it < total) {
+          const unsigned c = (CB == 1) ? 0 : it / nchunk;
+          const unsigned chunk = it - c * nchunk;
+          const unsigned m0 = chunk * L;
+          const unsigned n = min(L, nkeep - m0);
+          const float4* det = smem4 + c * RS + 17u * chunk;      // pad16(16*chunk + i) = 17*chunk + i
+          if (itr > 0) {
+            const unsigned* pl = plan + m0;
+#pragma unroll
+            for (int i = 0; i < 16; i++) b[i] = (unsigned(i) < n) ? __ldg(pl + i) : 0xfffffffeu;
+          }
+          unsigned diff = 0;
+#pragma unroll
+          for (int i = 1; i < 16; i++) diff |= b[i] ^ b[0];
+          if (diff == 0) {
+            // the common case (bins are usually many samples wide): the whole walk is one run
+            key = c * nbin + b[0];
+            float4 r = det[0];
+            acc[0] = r.x; acc[1] = r.y; acc[2] = r.z; acc[3] = r.w;
+#pragma unroll
+            for (int i = 1; i < 16; i++) {
+              r = det[i];
+              acc[0] += r.x; acc[1] += r.y; acc[2] += r.z; acc[3] += r.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+              if (unsigned(i) < n) {
+                const unsigned k = c * nbin + b[i];
+                const float4 r = det[i];
+                if (k != key) {
+                  if (key != 0xffffffffu) red_add(key, acc);
+                  key = k;
+                  acc[0] = r.x; acc[1] = r.y; acc[2] = r.z; acc[3] = r.w;
+                } else {
+                  acc[0] += r.x; acc[1] += r.y; acc[2] += r.z; acc[3] += r.w;
+                }
+              }
+            }
+          }
+        }
+        // segmented sum of the trailing runs across the warp
+#pragma unroll
+        for (unsigned off = 1; off < 32; off <<= 1) {
+          const unsigned okey = __shfl_down_sync(0xffffffffu, key, off);
+          float o[4];
+#pragma unroll
+          for (int pr = 0; pr < 4; pr++) o[pr] = __shfl_down_sync(0xffffffffu, acc[pr], off);
+          if (lane + off < 32 && okey == key) {
+#pragma unroll
+            for (int pr = 0; pr < 4; pr++) acc[pr] += o[pr];
+          }
+        }
+        const unsigned pkey = __shfl_up_sync(0xffffffffu, key, 1);
+        if (key != 0xffffffffu && (lane == 0 || pkey != key)) red_add(key, acc);
+      }
+    }
+    __syncthreads();       // fold readers are done before the next tile's first scatter
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+template <unsigned L> static int make_c2_table(float2** d_tw) {
+  std::vector<float2> h(c2::twiddle_count<L>(), make_float2(1.f, 0.f));
+  c2::fill_twiddles<L>(h.data());
+  B200_CUDA(cudaMalloc(d_tw, sizeof(float2) * h.size()));
+  B200_CUDA(cudaMemcpy(*d_tw, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice));
+  return B200_OK;
+}
+
+template <typename K> static int opt_in_smem(K kernel, size_t dyn_bytes) {
+  B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes));
+  return B200_OK;
+}
+
+static unsigned dbg_flags(int k) {
+  const char* e = getenv(k == 1 ? "B200_DBG1" : k == 2 ? "B200_DBG2" : "B200_DBG3");
+  return e ? (unsigned)atoi(e) : 0u;
+}
+
+static bool fast_enabled() {
+  static const bool on = !(getenv("B200_FAST") && atoi(getenv("B200_FAST")) == 0);
+  return on;
+}
+
+static constexpr unsigned FP_P = 2048, FP_Q = 1024, FP_F = 8192;
+static constexpr int FP_NP = 4;
+static size_t k1_smem() { return size_t(FP_NP) * (c2::pair_slots<FP_P>() + 8 / FP_NP) * sizeof(float4); }
+static size_t k2_smem() { return size_t(512 / (FP_Q / 16)) * (c2::pair_slots<FP_Q>() | 1u) * sizeof(float4); }
+static size_t k3_smem() { return size_t(512 / (FP_F / 16)) * c2::pair_slots<FP_F>() * sizeof(float4); }
+
+int fast_plan_init(b200_fb_plan* pl) {
+  pl->fast_k1 = pl->fast_k2 = pl->fast_k3 = false;
+  pl->c2P = pl->c2Q = pl->c2F = nullptr;
+  if (!fast_enabled() || pl->conv_path) return B200_OK;
+  int rc = B200_OK;
+  if (pl->P == FP_P && pl->Q >= 2 * FP_NP && pl->Q % (2 * FP_NP) == 0) {
+    if ((rc = make_c2_table<FP_P>(&pl->c2P)) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k1_c2<SRC_F32, FP_P, FP_NP>, k1_smem())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k1_c2<SRC_CASPSR8, FP_P, FP_NP>, k1_smem())) != B200_OK) return rc;
+    pl->fast_k1 = true;
+  }
+  if (pl->Q == FP_Q && pl->P == FP_P) {
+    if ((rc = make_c2_table<FP_Q>(&pl->c2Q)) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k2_c2<FP_P, FP_Q, true>, k2_smem())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k2_c2<FP_P, FP_Q, false>, k2_smem())) != B200_OK) return rc;
+    pl->fast_k2 = true;
+  }
+  if (pl->F == FP_F && pl->desc.npol == 2) {
+    if ((rc = make_c2_table<FP_F>(&pl->c2F)) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k3_c2<FP_F, EPI_VOLT, -1>, k3_smem())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k3_c2<FP_F, EPI_DETECT, -1>, k3_smem())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k3_c2<FP_F, EPI_FOLD, -1>, k3_smem())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k3_c2<FP_F, EPI_FOLD, B200_COHERENCE>, k3_smem())) != B200_OK) return rc;
+    pl->fast_k3 = true;
+  }
+  return B200_OK;
+}
+
+void fast_plan_free(b200_fb_plan* pl) {
+  if (pl->c2P) cudaFree(pl->c2P);
+  if (pl->c2Q) cudaFree(pl->c2Q);
+  if (pl->c2F) cudaFree(pl->c2F);
+  pl->c2P = pl->c2Q = pl->c2F = nullptr;
+}
+
+static unsigned persistent_grid(Context* ctx, unsigned ntiles) {
+  return ntiles < (unsigned)ctx->sm_count ? ntiles : (unsigned)ctx->sm_count;
+}
+
+int fast_k1(b200_fb_plan* pl, const FbSource& src, uint64_t part0, unsigned nb) {
+  Context* ctx = pl->ctx;
+  K1Args a;
+  a.src = src.ptr; a.span = src.span; a.step = src.step; a.lut = src.d_lut;
+  a.dst = pl->scratchA; a.tw = pl->c2P; a.blo = pl->bigN.lo; a.bhi = pl->bigN.hi;
+  a.Q = pl->Q; a.npol = pl->desc.npol; a.nchan_in = pl->desc.input_nchan; a.Nc = pl->Nc; a.part0 = part0;
+  a.nblk = nb * pl->desc.input_nchan * pl->desc.npol;
+  a.dbg = dbg_flags(1);
+  const unsigned ntiles = pl->Q / (2 * FP_NP) * a.nblk;
+  dim3 grid(persistent_grid(ctx, ntiles));
+  dim3 block(FP_NP * (FP_P / 16));
+  LaunchScope ls(ctx, KC_COLS_FWD);
+  if (src.kind == SRC_F32) k1_c2<SRC_F32, FP_P, FP_NP><<<grid, block, k1_smem(), ctx->stream>>>(a);
+  else k1_c2<SRC_CASPSR8, FP_P, FP_NP><<<grid, block, k1_smem(), ctx->stream>>>(a);
+  return B200_OK;
+}
+
+int fast_k2(b200_fb_plan* pl, unsigned nb) {
+  Context* ctx = pl->ctx;
+  K2Args a;
+  a.A = pl->scratchA; a.Z = pl->scratchZ; a.H = pl->d_response; a.tw = pl->c2Q; a.tw2Q = pl->tw2Q.tw;
+  a.b2lo = pl->big2N.lo; a.b2hi = pl->big2N.hi;
+  a.Nc = pl->Nc; a.npol = pl->desc.npol; a.nchan_in = pl->desc.input_nchan;
+  a.nblk = nb * pl->desc.input_nchan * pl->desc.npol;
+  a.dbg = dbg_flags(2);
+  constexpr unsigned G = 512 / (FP_Q / 16);
+  const bool split = pl->desc.input_real;
+  const unsigned ntiles = (split ? (FP_P / 2) / G : FP_P / (2 * G)) * a.nblk;
+  dim3 grid(persistent_grid(ctx, ntiles));
+  LaunchScope ls(ctx, KC_ROWS);
+  if (split) k2_c2<FP_P, FP_Q, true><<<grid, 512, k2_smem(), ctx->stream>>>(a);
+  else k2_c2<FP_P, FP_Q, false><<<grid, 512, k2_smem(), ctx->stream>>>(a);
+  return B200_OK;
+}
+
+int fast_k3(b200_fb_plan* pl, const FbSink& sk, uint64_t part0, unsigned nb) {
+  Context* ctx = pl->ctx;
+  K3Args a;
+  a.Z = pl->scratchZ; a.tw = pl->c2F; a.C = pl->C; a.Nc = pl->Nc; a.nchan_in = pl->desc.input_nchan;
+  a.nchan_out = pl->nchan_out; a.npart = nb;
+  a.nfilt_pos = pl->desc.nfilt_pos; a.nkeep = pl->nkeep; a.part0 = part0; a.sink = sk;
+  a.dbg = dbg_flags(3);
+  constexpr unsigned CB = 512 / (FP_F / 16);
+  const unsigned ntiles = pl->nchan_out / CB * nb;
+  dim3 grid(persistent_grid(ctx, ntiles));
+  LaunchScope ls(ctx, KC_INV);
+  if (sk.kind == EPI_VOLT) k3_c2<FP_F, EPI_VOLT, -1><<<grid, 512, k3_smem(), ctx->stream>>>(a);
+  else if (sk.kind == EPI_DETECT) k3_c2<FP_F, EPI_DETECT, -1><<<grid, 512, k3_smem(), ctx->stream>>>(a);
+  else if (sk.state == B200_COHERENCE) k3_c2<FP_F, EPI_FOLD, B200_COHERENCE><<<grid, 512, k3_smem(), ctx->stream>>>(a);
+  else k3_c2<FP_F, EPI_FOLD, -1><<<grid, 512, k3_smem(), ctx->stream>>>(a);
+  return B200_OK;
+}
+
+}  // namespace b200

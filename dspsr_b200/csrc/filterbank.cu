@@ -299,38 +299,6 @@ __global__ void __launch_bounds__(QCT ? 512 : 1024, 1) k_rows(RowsArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// detection products (cross_detect.ic:25-41, stokes_detect.ic:21-44, Detection.C:264-301);
-// explicit _rn intrinsics: no FMA contraction, bit-identical to the CPU loops.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int detect_products(int state, float2 p, float2 q, float* r) {
-  float pp = __fadd_rn(__fmul_rn(p.x, p.x), __fmul_rn(p.y, p.y));
-  float qq = __fadd_rn(__fmul_rn(q.x, q.x), __fmul_rn(q.y, q.y));
-  if (state == B200_INTENSITY) {
-    r[0] = __fadd_rn(pp, qq);
-    return 1;
-  }
-  if (state == B200_PPQQ) {
-    r[0] = pp;
-    r[1] = qq;
-    return 2;
-  }
-  float re = __fadd_rn(__fmul_rn(p.x, q.x), __fmul_rn(p.y, q.y));
-  float im = __fsub_rn(__fmul_rn(p.x, q.y), __fmul_rn(p.y, q.x));
-  if (state == B200_COHERENCE) {
-    r[0] = pp; r[1] = qq; r[2] = re; r[3] = im;
-  } else {
-    r[0] = __fadd_rn(pp, qq); r[1] = __fsub_rn(pp, qq); r[2] = __fmul_rn(2.f, re); r[3] = __fmul_rn(2.f, im);
-  }
-  return 4;
-}
-
-__host__ __device__ inline unsigned state_nprod(int state, unsigned npol) {
-  if (state == B200_INTENSITY) return 1;
-  if (state == B200_PPQQ) return npol;
-  return 4;
-}
-
-// ------------------------------------------------------------------------------------------
 // K3: per-channel inverse FFT + discard + epilogue
 // ------------------------------------------------------------------------------------------
 struct ChanArgs {
@@ -642,7 +610,11 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
   for (uint64_t part0 = 0; part0 < npart; part0 += pl->batch) {
     const unsigned nb = (unsigned)std::min<uint64_t>(pl->batch, npart - part0);
     // ---- K1 ----
-    {
+    const bool k1_fast = pl->fast_k1 && (src.kind == SRC_F32 || (src.step % 4 == 0 && (reinterpret_cast<uintptr_t>(src.ptr) & 3) == 0));
+    if (k1_fast) {
+      int rc = fast_k1(pl, src, part0, nb);
+      if (rc != B200_OK) return rc;
+    } else {
       ColsArgs a;
       a.src = src.ptr; a.span = src.span; a.step = src.step; a.lut = src.d_lut;
       a.dst = pl->scratchA; a.twP = pl->twP.tw; a.twPs = pl->twP.stage; a.blo = pl->bigN.lo; a.bhi = pl->bigN.hi;
@@ -674,7 +646,10 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
       }
     }
     // ---- K2 ----
-    {
+    if (pl->fast_k2) {
+      int rc = fast_k2(pl, nb);
+      if (rc != B200_OK) return rc;
+    } else {
       RowsArgs a;
       a.A = pl->scratchA; a.Z = pl->scratchZ; a.H = pl->d_response; a.twQ = pl->twQ.tw; a.twQs = pl->twQ.stage;
       a.tw2Q = pl->tw2Q.tw;
@@ -707,7 +682,10 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
     // ---- K3 ----
     FbSink sk = sink;
     if (sk.kind == EPI_FOLD) sk.bins = sink.bins + part0 * pl->nkeep;
-    if (pl->conv_path) {
+    if (pl->fast_k3) {
+      int rc = fast_k3(pl, sk, part0, nb);
+      if (rc != B200_OK) return rc;
+    } else if (pl->conv_path) {
       ColsInvArgs a;
       a.A = pl->scratchA; a.twP = pl->twP.tw;
       a.P = pl->P; a.Q = pl->Q; a.npol = npol; a.nchan_in = nchan_in; a.Nc = pl->Nc;
@@ -878,7 +856,12 @@ int b200_fb_plan_create(b200_context* cctx, const b200_fb_desc* d, b200_fb_plan*
       G *= 2;
     pl->G = G;
   }
-  pl->batch = d->max_npart ? d->max_npart : 4;
+  // parts per internal batch: 16 (launch overhead < 2 %) unless one spectrum buffer would exceed 2 GiB
+  {
+    const uint64_t per_part = uint64_t(d->input_nchan) * d->npol * pl->Nc * sizeof(float2);
+    uint64_t b = (2ull << 30) / per_part;
+    pl->batch = d->max_npart ? d->max_npart : unsigned(b < 1 ? 1 : b > 16 ? 16 : b);
+  }
 
   int rc = plan_set_attributes(size_t(ctx->max_smem_optin));
   if (rc == B200_OK) rc = make_twiddle(pl->twP, pl->P, ctx->stream);
@@ -904,6 +887,8 @@ int b200_fb_plan_create(b200_context* cctx, const b200_fb_desc* d, b200_fb_plan*
     return cuda_fail(e, "plan allocation", __FILE__, __LINE__);
   }
   pl->scratch_bytes = sbytes * (pl->conv_path ? 1 : 2);
+  rc = fast_plan_init(pl);
+  if (rc != B200_OK) { b200_fb_plan_destroy(pl); return rc; }
   *out = pl;
   return B200_OK;
 }
@@ -930,6 +915,7 @@ int b200_fb_plan_destroy(b200_fb_plan* pl) {
   free_twiddle(pl->tw2Q);
   free_big_twiddle(pl->bigN);
   free_big_twiddle(pl->big2N);
+  fast_plan_free(pl);
   if (pl->d_response) cudaFree(pl->d_response);
   if (pl->scratchA) cudaFree(pl->scratchA);
   if (pl->scratchZ) cudaFree(pl->scratchZ);

@@ -2,6 +2,7 @@
 // test-suite: runs the very same __host__ __device__ stage code thread-by-thread with an
 // emulated shared memory, and compares against a double-precision DFT.
 // Build: nvcc -std=c++17 -O2 host_fft_emul.cu -o host_fft_emul   (no GPU needed to run)
+#include <algorithm>
 #include <cmath>
 #include <complex>
 #include <cstdio>
@@ -9,6 +10,7 @@
 #include <vector>
 
 #include "fft_core.cuh"
+#include "fft_c2.cuh"
 
 using namespace b200;
 
@@ -234,9 +236,91 @@ static int sweep_ct() {
   return bad;
 }
 
+// ---- fft_c2.cuh: two sequences per thread, padded affine exchange -----------------------------------
+template <unsigned L, bool INV, int S>
+static void c2_stages(std::vector<float2>& ra, std::vector<float2>& rb, std::vector<float4>& smem,
+                      const float2* tw, std::vector<int>& touched) {
+  constexpr unsigned T = L / 16;
+  for (unsigned j = 0; j < T; j++) c2::stage_compute<L, S, INV>(&ra[j * 16], &rb[j * 16], j, tw);
+  if constexpr (S + 1 < c2::Plan<L>::nstage) {
+    std::fill(smem.begin(), smem.end(), make_float4(NAN, NAN, NAN, NAN));
+    for (unsigned j = 0; j < T; j++) c2::scatter<L, S>(smem.data(), &ra[j * 16], &rb[j * 16], j);
+    for (unsigned j = 0; j < T; j++) c2::gather<L>(smem.data(), &ra[j * 16], &rb[j * 16], j);
+    c2_stages<L, INV, S + 1>(ra, rb, smem, tw, touched);
+  }
+}
+
+template <unsigned L, bool INV>
+static int c2_test() {
+  constexpr unsigned T = L / 16;
+  std::vector<float2> tw(c2::twiddle_count<L>());
+  c2::fill_twiddles<L>(tw.data());
+  std::vector<std::complex<double>> xa(L), xb(L);
+  srand(L * 3 + INV);
+  for (unsigned i = 0; i < L; i++) {
+    xa[i] = {rand() / double(RAND_MAX) - 0.5, rand() / double(RAND_MAX) - 0.5};
+    xb[i] = {rand() / double(RAND_MAX) - 0.5, rand() / double(RAND_MAX) - 0.5};
+  }
+  std::vector<float2> ra(L), rb(L);
+  for (unsigned j = 0; j < T; j++)
+    for (int e = 0; e < 16; e++) {
+      ra[j * 16 + e] = make_float2(float(xa[j + e * T].real()), float(xa[j + e * T].imag()));
+      rb[j * 16 + e] = make_float2(float(xb[j + e * T].real()), float(xb[j + e * T].imag()));
+    }
+  std::vector<float4> smem(c2::pair_slots<L>());
+  std::vector<int> touched;
+  c2_stages<L, INV, 0>(ra, rb, smem, tw.data(), touched);
+  // reference: double DFT via the O(L^2)-free route: recursive radix-2 in double
+  auto dft = [&](std::vector<std::complex<double>> x) {
+    const unsigned n = x.size();
+    for (unsigned i = 1, jj = 0; i < n; i++) {
+      unsigned bit = n >> 1;
+      for (; jj & bit; bit >>= 1) jj ^= bit;
+      jj ^= bit;
+      if (i < jj) std::swap(x[i], x[jj]);
+    }
+    for (unsigned len = 2; len <= n; len <<= 1) {
+      double ang = (INV ? 2.0 : -2.0) * M_PI / len;
+      for (unsigned i = 0; i < n; i += len)
+        for (unsigned k = 0; k < len / 2; k++) {
+          std::complex<double> w(cos(ang * k), sin(ang * k));
+          auto u = x[i + k], v = x[i + k + len / 2] * w;
+          x[i + k] = u + v;
+          x[i + k + len / 2] = u - v;
+        }
+    }
+    return x;
+  };
+  auto Xa = dft(xa), Xb = dft(xb);
+  double err = 0, rms = 0;
+  for (unsigned j = 0; j < T; j++)
+    for (int e = 0; e < 16; e++) {
+      const unsigned k = j + e * T;
+      err = std::max(err, std::abs(std::complex<double>(ra[j * 16 + e].x, ra[j * 16 + e].y) - Xa[k]));
+      err = std::max(err, std::abs(std::complex<double>(rb[j * 16 + e].x, rb[j * 16 + e].y) - Xb[k]));
+      rms += std::norm(Xa[k]);
+    }
+  rms = sqrt(rms / L);
+  const bool ok = err / rms < 2e-6;
+  if (!ok) printf("c2 L=%u inv=%d rel err %.3e FAIL\n", L, int(INV), err / rms);
+  return ok ? 0 : 1;
+}
+
+static int sweep_c2() {
+  int bad = 0;
+  bad += c2_test<256, false>() + c2_test<256, true>();
+  bad += c2_test<512, false>() + c2_test<512, true>();
+  bad += c2_test<1024, false>() + c2_test<1024, true>();
+  bad += c2_test<2048, false>() + c2_test<2048, true>();
+  bad += c2_test<4096, false>() + c2_test<4096, true>();
+  bad += c2_test<8192, false>() + c2_test<8192, true>();
+  return bad;
+}
+
 int main() {
   int bad = 0;
   bad += sweep_ct();
+  bad += sweep_c2();
   bad += sweep<2>(2, 2);
   bad += sweep<4>(4, 64);
   bad += sweep<8>(8, 512);

@@ -7,6 +7,18 @@ void check(int status, const char* where) {
   if (status != B200_OK) throw Error(FailedCall, where, "%s", b200_last_error());
 }
 
+b200_context* context_for(void* cuda_stream, int device) {
+  // one context per (device, stream) = per dspsr pipeline thread (SingleThread.C:237-244); cached so that
+  // the four engines of a thread share it
+  static std::vector<std::pair<std::pair<int, void*>, b200_context*> > cache;
+  for (size_t i = 0; i < cache.size(); i++)
+    if (cache[i].first.first == device && cache[i].first.second == cuda_stream) return cache[i].second;
+  b200_context* ctx = 0;
+  check(b200_context_create(device, cuda_stream, &ctx), "B200::context_for");
+  cache.push_back(std::make_pair(std::make_pair(device, cuda_stream), ctx));
+  return ctx;
+}
+
 void* DeviceMemory::do_allocate(size_t nbytes) {
   void* p = 0;
   check(b200_malloc(ctx, nbytes, &p), "B200::DeviceMemory::do_allocate");

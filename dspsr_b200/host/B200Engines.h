@@ -18,7 +18,9 @@
 
 namespace B200 {
 
-void check(int status, const char* where);   // status != 0 -> throw Error(FailedCall, where, b200_last_error())
+void check(int status, const char* where);
+//! The context of the pipeline thread that owns `cuda_stream` (CUDA::DeviceMemory::get_stream()); created on first use
+b200_context* context_for(void* cuda_stream, int device = 0);   // status != 0 -> throw Error(FailedCall, where, b200_last_error())
 
 //! dsp::Memory on the context's device (stand-in for CUDA::DeviceMemory, MemoryCUDA.C)
 class DeviceMemory : public dsp::Memory {
