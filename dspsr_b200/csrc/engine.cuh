@@ -15,6 +15,7 @@ struct FbSource {
   uint64_t span;            // SRC_F32: floats between (chan,pol) planes
   uint64_t step;            // SRC_F32: floats between parts; raw: SAMPLES between parts
   const float* d_lut;       // raw 8-bit formats: device copy of the 256-entry table
+  cudaEvent_t* batch_ready; // optional: event i must have fired before the i-th internal batch reads its input
 };
 
 // what the last kernel does with the dedispersed samples

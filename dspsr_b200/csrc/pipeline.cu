@@ -1,8 +1,10 @@
 // pipeline.cu -- fused path: raw bytes -> (K1, K2, K3 with detect+fold epilogue) -> PhaseSeries.
 // What dspsr computes with [IOManager(unpack), Filterbank|Convolution, Detection, Fold]
 // (Signal/Pulsar/LoadToFold1.C:117-599, SingleThread.C:405-431) when no operation sits between.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "engine.cuh"
 
@@ -17,9 +19,15 @@ struct b200_pipeline {
   b200_fb_plan* fb;
   b200_fold* fold;
   float* d_lut;
-  // staging for execute_host
-  void* d_stage;
-  uint64_t stage_bytes;
+  // staging for execute_host: two device buffers used alternately, filled chunk by chunk on a private
+  // copy stream so that the host->device transfer of batch i+1 (and of the next call) overlaps the
+  // kernels of batch i
+  void* d_stage[2];
+  uint64_t stage_bytes[2];
+  cudaStream_t copy_stream;
+  cudaEvent_t stage_free[2];         // fired when the kernels that read d_stage[i] are done
+  std::vector<cudaEvent_t>* chunk_ready;
+  unsigned stage_turn;
   // unpacked float series for formats whose unpack is not fused into K1
   float* d_unpacked;
   uint64_t unpacked_floats;
@@ -88,7 +96,15 @@ int b200_pipeline_destroy(b200_pipeline* p) {
   if (p->fb) b200_fb_plan_destroy(p->fb);
   if (p->fold) b200_fold_destroy(p->fold);
   if (p->d_lut) cudaFree(p->d_lut);
-  if (p->d_stage) cudaFree(p->d_stage);
+  for (int i = 0; i < 2; i++) {
+    if (p->d_stage[i]) cudaFree(p->d_stage[i]);
+    if (p->stage_free[i]) cudaEventDestroy(p->stage_free[i]);
+  }
+  if (p->chunk_ready) {
+    for (cudaEvent_t e : *p->chunk_ready) cudaEventDestroy(e);
+    delete p->chunk_ready;
+  }
+  if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
   if (p->d_unpacked) cudaFree(p->d_unpacked);
   delete p;
   return B200_OK;
@@ -101,8 +117,18 @@ int b200_pipeline_info(const b200_pipeline* p, b200_fb_info* info) {
 
 b200_fold* b200_pipeline_fold(b200_pipeline* p) { return p ? p->fold : nullptr; }
 
+static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t input_span, uint64_t first_sample,
+                            uint64_t npart, double phi, double pps, float* d_detected, uint64_t detected_span,
+                            cudaEvent_t* batch_ready);
+
 int b200_pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t input_span, uint64_t first_sample,
                           uint64_t npart, double phi, double pps, float* d_detected, uint64_t detected_span) {
+  return pipeline_execute(p, d_input, input_span, first_sample, npart, phi, pps, d_detected, detected_span, nullptr);
+}
+
+static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t input_span, uint64_t first_sample,
+                            uint64_t npart, double phi, double pps, float* d_detected, uint64_t detected_span,
+                            cudaEvent_t* batch_ready) {
   B200_REQUIRE(p && d_input, "b200_pipeline_execute: null argument");
   if (npart == 0) return B200_OK;
   Context* ctx = p->ctx;
@@ -113,6 +139,7 @@ int b200_pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t input_
 
   FbSource src;
   memset(&src, 0, sizeof(src));
+  src.batch_ready = batch_ready;
   if (fmt == B200_FMT_CASPSR8) {
     B200_REQUIRE(first_sample % 2 == 0, "CASPSR input must start on an even sample");
     src.kind = SRC_CASPSR8;
@@ -181,16 +208,62 @@ int b200_pipeline_execute_host(b200_pipeline* p, const void* h_input, uint64_t n
                                uint64_t npart, double phi, double pps) {
   B200_REQUIRE(p && h_input, "b200_pipeline_execute_host: null argument");
   B200_REQUIRE(p->desc.unpack.format != B200_FMT_FLOAT32, "execute_host takes raw bytes");
+  if (npart == 0) return B200_OK;
   Context* ctx = p->ctx;
-  if (nbytes > p->stage_bytes) {
-    B200_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (p->d_stage) cudaFree(p->d_stage);
-    p->d_stage = nullptr;
-    p->stage_bytes = nbytes;
-    B200_CUDA(cudaMalloc(&p->d_stage, p->stage_bytes));
+  b200_fb_plan* fb = p->fb;
+  if (!p->copy_stream) {
+    B200_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) B200_CUDA(cudaEventCreateWithFlags(&p->stage_free[i], cudaEventDisableTiming));
+    p->chunk_ready = new std::vector<cudaEvent_t>();
   }
-  B200_CUDA(cudaMemcpyAsync(p->d_stage, h_input, nbytes, cudaMemcpyHostToDevice, ctx->stream));
-  return b200_pipeline_execute(p, p->d_stage, 0, first_sample, npart, phi, pps, nullptr, 0);
+  const unsigned turn = p->stage_turn++ & 1u;
+  if (nbytes > p->stage_bytes[turn]) {
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(p->copy_stream));
+    if (p->d_stage[turn]) cudaFree(p->d_stage[turn]);
+    p->d_stage[turn] = nullptr;
+    p->stage_bytes[turn] = nbytes;
+    B200_CUDA(cudaMalloc(&p->d_stage[turn], nbytes));
+  }
+  // the copy stream may overwrite this buffer once the kernels of its previous use are done, and must
+  // not run ahead of work already queued on the pipeline's stream that produced h_input (none: host memory)
+  B200_CUDA(cudaStreamWaitEvent(p->copy_stream, p->stage_free[turn], 0));
+
+  // one chunk per internal batch of the fused formats; everything at once when a separate unpack
+  // pass reads the whole block first
+  const int fmt = p->desc.unpack.format;
+  const bool chunked = (fmt == B200_FMT_CASPSR8);
+  const uint64_t batch = fb->batch;
+  const uint64_t nchunk = chunked ? (npart + batch - 1) / batch : 1;
+  while (p->chunk_ready->size() < nchunk) {
+    cudaEvent_t e;
+    B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    p->chunk_ready->push_back(e);
+  }
+  const uint64_t bytes_per_sample =
+      uint64_t(p->desc.unpack.nchan) * p->desc.unpack.npol * p->desc.unpack.ndim * fmt_nbit(fmt) / 8;
+  uint64_t done = 0;
+  for (uint64_t c = 0; c < nchunk; c++) {
+    uint64_t end = nbytes;
+    if (c + 1 < nchunk) {
+      const uint64_t last_sample = first_sample + (c + 1) * batch * fb->nsamp_step + fb->nsamp_overlap;
+      end = std::min<uint64_t>(nbytes, (last_sample * bytes_per_sample + 4095) / 4096 * 4096);
+    }
+    if (end > done)
+      B200_CUDA(cudaMemcpyAsync(static_cast<char*>(p->d_stage[turn]) + done, static_cast<const char*>(h_input) + done,
+                                end - done, cudaMemcpyHostToDevice, p->copy_stream));
+    done = std::max(done, end);
+    B200_CUDA(cudaEventRecord((*p->chunk_ready)[c], p->copy_stream));
+  }
+  int rc;
+  if (chunked) {
+    rc = pipeline_execute(p, p->d_stage[turn], 0, first_sample, npart, phi, pps, nullptr, 0, p->chunk_ready->data());
+  } else {
+    B200_CUDA(cudaStreamWaitEvent(ctx->stream, (*p->chunk_ready)[0], 0));
+    rc = pipeline_execute(p, p->d_stage[turn], 0, first_sample, npart, phi, pps, nullptr, 0, nullptr);
+  }
+  B200_CUDA(cudaEventRecord(p->stage_free[turn], ctx->stream));
+  return rc;
 }
 
 int b200_pipeline_synch(b200_pipeline* p, float* h_profile, unsigned* h_hits, uint64_t* ndat_total) {
