@@ -184,7 +184,7 @@ def run_reference(args):
     }))
 
 
-def cpu_baseline_leg(S, budget_s=20.0):
+def cpu_baseline_leg(S, budget_s=12.0):
     import oracle as O
     ncores = os.cpu_count() or 1
     f = O.fb_sizes(1, 1, 2, S["C"], S["F"], S["npos"], S["nneg"])
@@ -201,7 +201,7 @@ def cpu_baseline_leg(S, budget_s=20.0):
     while True:
         O.pipe_run(pipe, raw, nblock, 1, phi, pps, nthread=ncores)
         reps += 1
-        if time.perf_counter() - t0 > budget_s / 2 or reps >= 3:
+        if time.perf_counter() - t0 > budget_s or reps >= 64:
             break
     dt = time.perf_counter() - t0
     v = reps * nblock * S["step"] / dt / 1e6
@@ -223,6 +223,8 @@ def run_ours(args):
         raise RuntimeError("bench.py (ours) needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL writes its version / INFO lines to stdout by default: keep stdout for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     parts = args.parts
     S = cfg1_setup(parts)
@@ -338,10 +340,20 @@ def run_ours(args):
             v["alg_bytes_per_launch"] = alg[k] * parts_per_launch
             v["gbs"] = v["alg_bytes_per_launch"] / (v["ms_per_launch"] * 1e-3) / 1e9
     dom = max((k for k in kinfo if k in alg), key=lambda k: kinfo[k]["ms_per_step"])
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture (profiles/)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            tj = json.load(f)
+        if dom in tj:
+            traffic = tj[dom]["dram_bytes_per_launch"] / tj[dom]["parts_per_launch"] * (parts / kinfo[dom]["launches_per_step"])
     roof = {"bound": "hbm", "kernel": {"cols_fwd": "k_cols_fwd (K1 unpack+column FFT)", "rows": "k_rows (K2 row FFT+split+chirp)",
                                         "inverse": "k_chan_inv (K3 inverse FFT+detect+fold)"}[dom],
             "achieved": kinfo[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kinfo[dom]["gbs"] / peak,
-            "traffic": None, "peak_source": peak_src, "share_of_step": kinfo[dom]["share"]}
+            "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu)",
+            "alg_bytes_per_launch": kinfo[dom]["alg_bytes_per_launch"],
+            "peak_source": peak_src, "share_of_step": kinfo[dom]["share"]}
     b_alg = (raw_b + 2 * spec_b) / npol / S["step"]          # 10.13 B per sample per pol
     path_gbs = b_alg * npol * samples_step / (ms / args.steps * 1e-3) / 1e9 * 1.0
     out = {
@@ -358,7 +370,11 @@ def run_ours(args):
         "clocks": clk,
         "roofline": roof,
         "roofline_path": {"bound": "hbm", "alg_bytes_per_sample_per_pol": b_alg, "achieved": path_gbs, "peak": peak,
-                          "unit": "GB/s", "frac": path_gbs / peak, "peak_source": peak_src},
+                          "unit": "GB/s", "frac": path_gbs / peak, "peak_source": peak_src,
+                          # FP32 side (5 N log2 N convention): 95.7 flop per sample per pol
+                          "fp32_alg_flop_per_sample_per_pol": 5.0 * Nc * (np.log2(Nc) + np.log2(S["F"])) / S["step"],
+                          "fp32_achieved_tflops": 5.0 * Nc * (np.log2(Nc) + np.log2(S["F"])) / S["step"] * value * 1e6 * npol / 1e12,
+                          "fp32_peak_tflops_nominal": 148 * 128 * 2 * 1.965e9 / 1e12},
         "kernels": kinfo,
     }
     if world == 1 and not args.no_cpu:
