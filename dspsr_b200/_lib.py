@@ -7,9 +7,21 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200dsp.so")
 
 OK = 0
-FMT_CASPSR8, FMT_GENERIC8, FMT_MEERKAT8, FMT_UWB16, FMT_FLOAT32 = range(5)
+FMT_CASPSR8, FMT_GENERIC8, FMT_MEERKAT8, FMT_UWB16, FMT_FLOAT32, FMT_TWOBIT = range(6)
 INTENSITY, PPQQ, COHERENCE, STOKES = range(4)
 STATE = {"Intensity": INTENSITY, "PPQQ": PPQQ, "Coherence": COHERENCE, "Stokes": STOKES}
+
+
+class TwoBitDesc(C.Structure):
+    _fields_ = [
+        ("table_type", C.c_int),
+        ("npol", C.c_uint),
+        ("ndat_per_weight", C.c_uint),
+        ("nlow_min", C.c_uint),
+        ("nlow_max", C.c_uint),
+        ("lo", C.c_float * 513),
+        ("hi", C.c_float * 513),
+    ]
 
 
 class UnpackDesc(C.Structure):
@@ -21,6 +33,7 @@ class UnpackDesc(C.Structure):
         ("lut", C.c_float * 256),
         ("scale", C.c_float),
         ("sample_swap", C.c_uint),
+        ("twobit", C.POINTER(TwoBitDesc)),
     ]
 
 
@@ -110,6 +123,8 @@ _pvp = C.POINTER(C.c_void_p)
 
 # name -> (restype, argtypes); every symbol include/b200dsp.h declares
 SIGNATURES = {
+    "b200_twobit_prepare": (_i, [C.c_double, C.c_float, _i, C.c_uint, C.c_uint, C.POINTER(TwoBitDesc)]),
+    "b200_unpack_twobit": (_i, [_vp, C.POINTER(TwoBitDesc), _vp, C.c_uint64, _vp, C.c_uint64, _vp]),
     "b200_version": (_i, []),
     "b200_last_error": (C.c_char_p, []),
     "b200_context_create": (_i, [_i, _vp, _pvp]),

@@ -95,6 +95,74 @@ __global__ void k_unpack_uwb(UnpackArgs a) {
   }
 }
 
+
+// Two-bit excision unpacker (TwoBitCorrection / ExcisionUnpacker / TwoBitFour, see b200dsp.h):
+// one warp per window of 512 samples.  Lane l owns bytes [4l, 4l+4) of every digitizer (bytes of the
+// npol digitizers are interleaved), i.e. samples [16l, 16l+16) of the window.  Pass 1 counts the
+// low-voltage states with a bit trick (a 2-bit code is "low" iff bit (lowsel >> code) & 1) and reduces
+// over the warp; pass 2 writes sign * (low ? lo : hi)[clamped nlow] or zeros.
+struct TwoBitArgs {
+  const unsigned char* raw;
+  float* out;
+  uint64_t span, nwindow;
+  unsigned npol, nlow_min, nlow_max;
+  unsigned lowsel;      // bit c set: code c is a low-voltage state
+  unsigned negsel;      // bit c set: code c is negative
+  const float* levels;  // lo[513] then hi[513]
+  unsigned* weights;
+};
+
+template <unsigned NPOL>
+__global__ void k_unpack_twobit(TwoBitArgs a) {
+  const unsigned lane = threadIdx.x & 31u;
+  const uint64_t warp0 = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5;
+  const uint64_t nwarp = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+  for (uint64_t w = warp0; w < a.nwindow; w += nwarp) {
+    // 4*NPOL consecutive bytes: byte b belongs to digitizer b % NPOL (ExcisionUnpacker.C:258-266)
+    unsigned words[NPOL];
+    const unsigned* src = reinterpret_cast<const unsigned*>(a.raw + (w * 128 + 4 * lane) * NPOL);
+#pragma unroll
+    for (unsigned i = 0; i < NPOL; i++) words[i] = __ldg(src + i);
+    unsigned bytes[NPOL][4];
+#pragma unroll
+    for (unsigned b = 0; b < 4 * NPOL; b++) bytes[b % NPOL][b / NPOL] = (words[b / 4] >> (8 * (b % 4))) & 255u;
+    bool zero_any = false;
+#pragma unroll
+    for (unsigned p = 0; p < NPOL; p++) {
+      unsigned nlow = 0, any = 0;
+#pragma unroll
+      for (unsigned k = 0; k < 4; k++) {
+        const unsigned byte = bytes[p][k];
+        any |= byte;
+#pragma unroll
+        for (unsigned s4 = 0; s4 < 4; s4++) nlow += (a.lowsel >> ((byte >> (6 - 2 * s4)) & 3u)) & 1u;
+      }
+      nlow = __reduce_add_sync(0xffffffffu, nlow);
+      any = __reduce_or_sync(0xffffffffu, any);
+      // excision_unpack.h:79-97: all-zero bytes, or nlow outside the limits
+      const bool bad = (any == 0) || nlow < a.nlow_min || nlow > a.nlow_max;
+      zero_any |= bad;
+      const unsigned row = min(max(nlow, a.nlow_min), a.nlow_max) - a.nlow_min;   // TwoBitFour.h:68-75
+      const float lo = bad ? 0.f : __ldg(a.levels + row);
+      const float hi = bad ? 0.f : __ldg(a.levels + 513 + row);
+      float4* dst = reinterpret_cast<float4*>(a.out + uint64_t(p) * a.span + w * 512 + 16 * lane);
+#pragma unroll
+      for (unsigned k = 0; k < 4; k++) {
+        const unsigned byte = bytes[p][k];
+        float v[4];
+#pragma unroll
+        for (unsigned s4 = 0; s4 < 4; s4++) {
+          const unsigned code = (byte >> (6 - 2 * s4)) & 3u;            // BitTable.C:154-163 MostToLeast
+          const float mag = ((a.lowsel >> code) & 1u) ? lo : hi;
+          v[s4] = ((a.negsel >> code) & 1u) ? -mag : mag;
+        }
+        dst[k] = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+    if (a.weights && lane == 0) a.weights[w] = zero_any ? 0u : 1u;     // WeightedTimeSeries::mask_weights
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // stand-alone detection (Detection.C:218-320,322-421)
 // ------------------------------------------------------------------------------------------
@@ -263,6 +331,12 @@ int b200_unpack(b200_context* cctx, const b200_unpack_desc* d, const void* d_raw
   a.out = d_out; a.span = out_span; a.ndat = ndat;
   a.nchan = d->nchan; a.npol = d->npol; a.ndim = d->ndim;
   a.scale = d->scale; a.sample_swap = d->sample_swap ? d->sample_swap : 1;
+  if (d->format == B200_FMT_TWOBIT) {
+    B200_REQUIRE(d->twobit, "b200_unpack: TWOBIT format needs desc->twobit");
+    B200_REQUIRE(d->nchan == 1 && d->ndim == 1 && d->npol == d->twobit->npol,
+                 "two-bit unpacker: nchan=1, ndim=1, npol matching the table");
+    return b200_unpack_twobit(cctx, d->twobit, d_raw, ndat, d_out, out_span, nullptr);
+  }
   const unsigned threads = 256;
   const unsigned maxgrid = ctx->sm_count * 16;
   float* d_lut = nullptr;
@@ -308,6 +382,47 @@ int b200_unpack(b200_context* cctx, const b200_unpack_desc* d, const void* d_raw
       return B200_ERR_INVALID;
   }
   if (d_lut) B200_CUDA(cudaFreeAsync(d_lut, ctx->stream));
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_unpack_twobit(b200_context* cctx, const b200_twobit_desc* d, const void* d_raw, uint64_t ndat, float* d_out,
+                       uint64_t out_span, unsigned* d_weights) {
+  B200_REQUIRE(cctx && d && d_raw && d_out, "b200_unpack_twobit: null argument");
+  Context* ctx = reinterpret_cast<Context*>(cctx);
+  B200_REQUIRE(d->npol == 1 || d->npol == 2, "two-bit unpacker: npol=%u (1 or 2 digitizers)", d->npol);
+  B200_REQUIRE(d->table_type >= 0 && d->table_type <= 2, "two-bit unpacker: unknown table type %d", d->table_type);
+  if (d->ndat_per_weight != 512) {
+    set_error("two-bit unpacker: ndat_per_weight=%u (only the reference default 512 is built)", d->ndat_per_weight);
+    return B200_ERR_UNSUPPORTED;
+  }
+  B200_REQUIRE(ndat % 512 == 0, "two-bit unpacker: ndat=%llu is not a multiple of ndat_per_weight=512 "
+               "(ExcisionUnpacker::get_resolution)", (unsigned long long)ndat);
+  B200_REQUIRE(out_span % 4 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(d_raw) & 3) == 0, "two-bit unpacker: unaligned buffers");
+  B200_REQUIRE(d->nlow_min <= d->nlow_max && d->nlow_max <= 512, "two-bit unpacker: invalid nlow limits");
+  if (ndat == 0) return B200_OK;
+  float* d_levels = nullptr;
+  B200_CUDA(cudaMallocAsync(&d_levels, 2 * 513 * sizeof(float), ctx->stream));
+  B200_CUDA(cudaMemcpyAsync(d_levels, d->lo, 513 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  B200_CUDA(cudaMemcpyAsync(d_levels + 513, d->hi, 513 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  TwoBitArgs a;
+  a.raw = static_cast<const unsigned char*>(d_raw);
+  a.out = d_out; a.span = out_span; a.nwindow = ndat / 512; a.npol = d->npol;
+  a.nlow_min = d->nlow_min; a.nlow_max = d->nlow_max; a.levels = d_levels; a.weights = d_weights;
+  // TwoBitTable::generate_unique_values (TwoBitTable.C:42-75): which codes are low / negative
+  static const unsigned lowsel[3] = {0x6u /* codes 1,2 */, 0x5u /* 0,2 */, 0x9u /* 0,3 */};
+  static const unsigned negsel[3] = {0x3u /* codes 0,1 */, 0xcu /* 2,3 */, 0xcu /* 2,3 */};
+  a.lowsel = lowsel[d->table_type];
+  a.negsel = negsel[d->table_type];
+  const unsigned threads = 256;
+  unsigned grid = (unsigned)std::min<uint64_t>((a.nwindow * 32 + threads - 1) / threads, uint64_t(ctx->sm_count) * 16);
+  {
+    LaunchScope ls(ctx, KC_OTHER);
+    if (d->npol == 1) k_unpack_twobit<1><<<grid, threads, 0, ctx->stream>>>(a);
+    else k_unpack_twobit<2><<<grid, threads, 0, ctx->stream>>>(a);
+  }
+  B200_CUDA(cudaFreeAsync(d_levels, ctx->stream));
   B200_CUDA(cudaGetLastError());
   return B200_OK;
 }

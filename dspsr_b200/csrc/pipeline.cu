@@ -32,6 +32,7 @@ struct b200_pipeline {
   float* d_unpacked;
   uint64_t unpacked_floats;
   unsigned nprod, dnpol, dndim;
+  b200_twobit_desc twobit;
 };
 
 static unsigned fmt_resolution(int fmt) {
@@ -39,10 +40,13 @@ static unsigned fmt_resolution(int fmt) {
     case B200_FMT_CASPSR8: return 4;
     case B200_FMT_MEERKAT8: return 256;
     case B200_FMT_UWB16: return 2048;
+    case B200_FMT_TWOBIT: return 512;      // ExcisionUnpacker::get_resolution = ndat_per_weight
     default: return 1;
   }
 }
-static unsigned fmt_nbit(int fmt) { return fmt == B200_FMT_UWB16 ? 16 : fmt == B200_FMT_FLOAT32 ? 32 : 8; }
+static unsigned fmt_nbit(int fmt) {
+  return fmt == B200_FMT_UWB16 ? 16 : fmt == B200_FMT_FLOAT32 ? 32 : fmt == B200_FMT_TWOBIT ? 2 : 8;
+}
 
 extern "C" {
 
@@ -50,7 +54,8 @@ int b200_pipeline_create(b200_context* cctx, const b200_pipeline_desc* d, b200_p
   B200_REQUIRE(cctx && d && out, "b200_pipeline_create: null argument");
   Context* ctx = reinterpret_cast<Context*>(cctx);
   const int fmt = d->unpack.format;
-  B200_REQUIRE(fmt >= B200_FMT_CASPSR8 && fmt <= B200_FMT_FLOAT32, "unknown input format %d", fmt);
+  B200_REQUIRE(fmt >= B200_FMT_CASPSR8 && fmt <= B200_FMT_TWOBIT, "unknown input format %d", fmt);
+  B200_REQUIRE(fmt != B200_FMT_TWOBIT || d->unpack.twobit, "TWOBIT input needs unpack.twobit");
   B200_REQUIRE(d->unpack.nchan == d->fb.input_nchan && d->unpack.npol == d->fb.npol,
                "unpacker nchan/npol (%u,%u) != filterbank input (%u,%u)", d->unpack.nchan, d->unpack.npol,
                d->fb.input_nchan, d->fb.npol);
@@ -62,6 +67,10 @@ int b200_pipeline_create(b200_context* cctx, const b200_pipeline_desc* d, b200_p
   p->ctx = ctx;
   p->desc = *d;
   p->desc.fb.h_response = nullptr;
+  if (fmt == B200_FMT_TWOBIT) {
+    p->twobit = *d->unpack.twobit;           // the caller's descriptor need not outlive the call
+    p->desc.unpack.twobit = &p->twobit;
+  }
   if (d->detect_state >= B200_COHERENCE) {
     p->nprod = 4;
     p->dndim = d->detect_ndim;
@@ -169,9 +178,9 @@ static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t inpu
       p->unpacked_floats = need + need / 8;
       B200_CUDA(cudaMalloc(&p->d_unpacked, p->unpacked_floats * sizeof(float)));
     }
-    const uint64_t bytes_per_sample = uint64_t(p->desc.unpack.nchan) * p->desc.unpack.npol * ndim * fmt_nbit(fmt) / 8;
+    const uint64_t bits_per_sample = uint64_t(p->desc.unpack.nchan) * p->desc.unpack.npol * ndim * fmt_nbit(fmt);
     int rc = b200_unpack(reinterpret_cast<b200_context*>(ctx), &p->desc.unpack,
-                         static_cast<const unsigned char*>(d_input) + a0 * bytes_per_sample, a1 - a0, p->d_unpacked, span);
+                         static_cast<const unsigned char*>(d_input) + a0 * bits_per_sample / 8, a1 - a0, p->d_unpacked, span);
     if (rc != B200_OK) return rc;
     src.kind = SRC_F32;
     src.ptr = p->d_unpacked + (first_sample - a0) * ndim;
@@ -240,14 +249,14 @@ int b200_pipeline_execute_host(b200_pipeline* p, const void* h_input, uint64_t n
     B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     p->chunk_ready->push_back(e);
   }
-  const uint64_t bytes_per_sample =
-      uint64_t(p->desc.unpack.nchan) * p->desc.unpack.npol * p->desc.unpack.ndim * fmt_nbit(fmt) / 8;
+  const uint64_t bits_per_sample =
+      uint64_t(p->desc.unpack.nchan) * p->desc.unpack.npol * p->desc.unpack.ndim * fmt_nbit(fmt);
   uint64_t done = 0;
   for (uint64_t c = 0; c < nchunk; c++) {
     uint64_t end = nbytes;
     if (c + 1 < nchunk) {
       const uint64_t last_sample = first_sample + (c + 1) * batch * fb->nsamp_step + fb->nsamp_overlap;
-      end = std::min<uint64_t>(nbytes, (last_sample * bytes_per_sample + 4095) / 4096 * 4096);
+      end = std::min<uint64_t>(nbytes, (last_sample * bits_per_sample / 8 + 4095) / 4096 * 4096);
     }
     if (end > done)
       B200_CUDA(cudaMemcpyAsync(static_cast<char*>(p->d_stage[turn]) + done, static_cast<const char*>(h_input) + done,

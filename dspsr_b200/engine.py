@@ -75,6 +75,30 @@ def make_unpack_desc(fmt, nchan, npol, ndim, lut=None, scale=0.0, sample_swap=1)
     return d
 
 
+def make_twobit_desc(npol=2, threshold=0.9674, cutoff_sigma=10.0, table_type=0, ndat_per_weight=512):
+    """Level table of the two-bit excision unpacker (TwoBitCorrection::build); table_type 0 = OffsetBinary."""
+    d = L.TwoBitDesc()
+    L.check(L.load().b200_twobit_prepare(threshold, cutoff_sigma, table_type, npol, ndat_per_weight, C.byref(d)))
+    return d
+
+
+def make_twobit_unpack_desc(twobit):
+    """b200_unpack_desc for FMT_TWOBIT; keeps the level table alive on the returned object."""
+    d = make_unpack_desc(L.FMT_TWOBIT, 1, twobit.npol, 1)
+    d.twobit = C.pointer(twobit)
+    d._keep = twobit
+    return d
+
+
+def unpack_twobit(ctx, twobit, raw, ndat):
+    """Two-bit excision unpacker: raw uint8 CUDA tensor -> (float32 [1, npol, ndat], weights uint32 [ndat/512])."""
+    _need_cuda(raw, "raw")
+    out = torch.empty((1, twobit.npol, ndat), dtype=torch.float32, device=raw.device)
+    w = torch.empty(ndat // twobit.ndat_per_weight, dtype=torch.int32, device=raw.device)
+    L.check(ctx.lib.b200_unpack_twobit(ctx.h, C.byref(twobit), _ptr(raw), ndat, _ptr(out), ndat, _ptr(w)))
+    return out, w
+
+
 def unpack(ctx, desc, raw, ndat):
     """Unpacker device hook: raw uint8 CUDA tensor -> float32 [nchan, npol, ndat*ndim]."""
     _need_cuda(raw, "raw")

@@ -227,6 +227,55 @@ int b200_dedispersion_build(const b200_dedispersion* d, float* h_response) {
   return B200_OK;
 }
 
+// ---- two-bit excision tables ---------------------------------------------------------------------
+// ExcisionUnpacker::set_limits (ExcisionUnpacker.C:95-158) + TwoBitLookup::lookup_build (TwoBitLookup.C:63-98)
+// with the Jenet & Anderson (1998) section 6 levels (PSRCHIVE's JenetAnderson98::set_Phi, restated):
+//   alpha = ierf(Phi); lo^2 = 1 - (2 alpha/sqrt pi) exp(-alpha^2)/Phi; hi^2 = 1 + (2 alpha/sqrt pi) exp(-alpha^2)/(1-Phi)
+static double inverse_erf(double y) {
+  const double a = 0.147;
+  const double ln1 = std::log(1.0 - y * y);
+  const double t = 2.0 / (M_PI * a) + 0.5 * ln1;
+  double x = std::copysign(std::sqrt(std::sqrt(t * t - ln1 / a) - t), y);
+  for (int i = 0; i < 4; i++) x -= (std::erf(x) - y) / (2.0 / std::sqrt(M_PI) * std::exp(-x * x));
+  return x;
+}
+
+int b200_twobit_prepare(double threshold, float cutoff_sigma, int table_type, unsigned npol,
+                        unsigned ndat_per_weight, b200_twobit_desc* d) {
+  if (!d || npol < 1 || npol > 2 || table_type < 0 || table_type > 2 || ndat_per_weight < 4 ||
+      ndat_per_weight > 512 || ndat_per_weight % 128 != 0)
+    return B200_ERR_INVALID;
+  d->table_type = table_type;
+  d->npol = npol;
+  d->ndat_per_weight = ndat_per_weight;
+  if (cutoff_sigma == 0.0) {
+    d->nlow_min = 0;
+    d->nlow_max = ndat_per_weight;
+  } else {
+    const double mean_Phi = std::erf(threshold / std::sqrt(2.0));
+    const double var_Phi = mean_Phi * (1.0 - mean_Phi);
+    float fsample = ndat_per_weight;
+    float nlo_mean = fsample * mean_Phi;
+    float nlo_variance = fsample * var_Phi;
+    float nlo_sigma = sqrt(nlo_variance);
+    d->nlow_max = unsigned(nlo_mean + (cutoff_sigma * nlo_sigma));
+    if (d->nlow_max >= ndat_per_weight) d->nlow_max = ndat_per_weight - 1;
+    if (cutoff_sigma * nlo_sigma >= nlo_mean + 1.0) d->nlow_min = 1;
+    else d->nlow_min = unsigned(nlo_mean - (cutoff_sigma * nlo_sigma));
+  }
+  const double root_pi = std::sqrt(M_PI);
+  for (unsigned nlo = d->nlow_min; nlo <= d->nlow_max; nlo++) {
+    unsigned use_nlow = nlo == 0 ? 1 : nlo;
+    float p_in = (float)use_nlow / (float)ndat_per_weight;
+    const double Phi = p_in;
+    const double alpha = inverse_erf(Phi);
+    const double expon = std::exp(-alpha * alpha);
+    d->lo[nlo - d->nlow_min] = float(std::sqrt(1.0 - (2.0 * alpha / root_pi) * (expon / Phi)));
+    d->hi[nlo - d->nlow_min] = float(std::sqrt(1.0 + (2.0 * alpha / root_pi) * (expon / (1.0 - Phi))));
+  }
+  return B200_OK;
+}
+
 int64_t b200_optimal_fft_length(uint64_t nbadperfft, uint64_t nfft_max) {
   return Dedispersion::optimal_fft_length(nbadperfft, nfft_max);
 }

@@ -82,8 +82,34 @@ typedef enum {
   B200_FMT_GENERIC8 = 1,
   B200_FMT_MEERKAT8 = 2,
   B200_FMT_UWB16 = 3,
-  B200_FMT_FLOAT32 = 4 /* already a float TimeSeries (pipeline input only) */
+  B200_FMT_FLOAT32 = 4, /* already a float TimeSeries (pipeline input only) */
+  B200_FMT_TWOBIT = 5   /* 2-bit real-sampled, one digitizer per polarisation, bytes interleaved (CPSR2) */
 } b200_format;
+
+/* Two-bit excision unpacker.  Replaces: TwoBitCorrection::build/dig_unpack (Kernel/Classes/
+ * TwoBitCorrection.C:89-151), ExcisionUnpacker::set_limits/unpack (ExcisionUnpacker.C:95-158,174-256),
+ * excision_unpack (dsp/excision_unpack.h:21-106), TwoBitFour (dsp/TwoBitFour.h:42-89), TwoBitLookup::
+ * lookup_build (TwoBitLookup.C:63-98).  Per digitizer and window of ndat_per_weight samples: nlow =
+ * number of low-voltage states; the output levels (lo, hi) are those of Jenet & Anderson (1998) for
+ * Phi = nlow/ndat_per_weight (clamped to [nlow_min, nlow_max]); windows that are all-zero bytes or whose
+ * nlow falls outside the limits are zeroed and their weight set to 0.  The level table is built on the
+ * HOST (b200_twobit_prepare) so that device output is bit-identical to the CPU path. */
+typedef struct {
+  int table_type;            /* 0 OffsetBinary (CPSR2TwoBitCorrection.C:21), 1 SignMagnitude, 2 TwosComplement */
+  unsigned npol;             /* digitizers = polarisations (1 or 2) */
+  unsigned ndat_per_weight;  /* TwoBitCorrection.C:31: 512 */
+  unsigned nlow_min, nlow_max;
+  float lo[513], hi[513];    /* levels of row nlow at index nlow - nlow_min */
+} b200_twobit_desc;
+
+/* threshold: sampling threshold in sigma (JenetAnderson98 optimal 4-level value 0.9674);
+ * cutoff_sigma: ExcisionUnpacker default 10.0, 0 disables the limits */
+int b200_twobit_prepare(double threshold, float cutoff_sigma, int table_type, unsigned npol,
+                        unsigned ndat_per_weight, b200_twobit_desc* desc);
+/* d_weights (nullable): ndat/ndat_per_weight entries, 1 = good, 0 = flagged in any polarisation
+ * (WeightedTimeSeries::mask_weights).  ndat must be a multiple of ndat_per_weight. */
+int b200_unpack_twobit(b200_context* ctx, const b200_twobit_desc* desc, const void* d_raw, uint64_t ndat,
+                       float* d_out, uint64_t out_span, unsigned* d_weights);
 
 typedef struct {
   int format;            /* b200_format */
@@ -91,6 +117,7 @@ typedef struct {
   float lut[256];        /* CASPSR8 / GENERIC8: BitTable::get_values() */
   float scale;           /* MEERKAT8: float(BitTable::get_scale()) */
   unsigned sample_swap;  /* MEERKAT8: 1 (MKBF) or 2 (MKBFRo) */
+  const b200_twobit_desc* twobit; /* TWOBIT only (copied by b200_pipeline_create) */
 } b200_unpack_desc;
 
 int b200_unpack(b200_context* ctx, const b200_unpack_desc* desc, const void* d_raw, uint64_t ndat,

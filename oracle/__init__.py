@@ -184,6 +184,55 @@ def unpack_uwb(raw, ndat, npol):
     return out
 
 
+# ----------------------------------------------------------------------------- a6
+class TwoBit:
+    """TwoBitCorrection (CPSR2 convention): level lookup + excision limits, and the unpack loop."""
+
+    def __init__(self, table_type=0, threshold=0.9674, cutoff_sigma=10.0, ndat_per_weight=512):
+        L = lib()
+        L.orc_twobit_create.restype = C.c_void_p
+        L.orc_twobit_create.argtypes = [C.c_int, C.c_double, C.c_float, C.c_uint]
+        self.h = C.c_void_p(L.orc_twobit_create(table_type, threshold, cutoff_sigma, ndat_per_weight))
+        self.ndat_per_weight = ndat_per_weight
+        a, b = C.c_uint(0), C.c_uint(0)
+        L.orc_twobit_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+        L.orc_twobit_info(self.h, C.byref(a), C.byref(b))
+        self.nlow_min, self.nlow_max = a.value, b.value
+
+    def levels(self, nlow):
+        lo, hi = C.c_float(0), C.c_float(0)
+        f = lib().orc_twobit_levels
+        f.argtypes = [C.c_void_p, C.c_uint, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        f(self.h, nlow, C.byref(lo), C.byref(hi))
+        return lo.value, hi.value
+
+    def unpack(self, raw, ndat, npol):
+        """raw uint8 -> (float32 [1, npol, ndat], weights uint32 [npol, ndat/ndat_per_weight] after mask_weights)."""
+        raw = np.ascontiguousarray(raw, np.uint8)
+        out = np.zeros((1, npol, ndat), np.float32)
+        nw = ndat // self.ndat_per_weight
+        w = np.zeros((npol, nw), np.uint32)
+        f = lib().orc_unpack_twobit
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        f(self.h, _p(raw), ndat, npol, _p(out), ndat, _p(w), nw)
+        return out, w
+
+    def __del__(self):
+        try:
+            lib().orc_twobit_destroy.argtypes = [C.c_void_p]
+            lib().orc_twobit_destroy(self.h)
+        except Exception:
+            pass
+
+
+def ja98_levels(phi):
+    lo, hi = C.c_double(0), C.c_double(0)
+    f = lib().orc_ja98_levels
+    f.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    f(phi, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
 # ----------------------------------------------------------------------------- a7-a9
 def optimal_fft_length(nbad, nfft_max=0):
     return lib().orc_optimal_fft_length(nbad, nfft_max)

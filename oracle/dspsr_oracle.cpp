@@ -188,6 +188,184 @@ void orc_unpack_uwb(const int16_t* raw, uint64_t ndat, unsigned npol, float* out
 }
 
 // ---------------------------------------------------------------------------------------
+// a6  two-bit excision unpacker: TwoBitCorrection::build / dig_unpack (Kernel/Classes/
+//     TwoBitCorrection.C:89-151), ExcisionUnpacker::set_limits / unpack (ExcisionUnpacker.C:95-158,
+//     174-256), excision_unpack (dsp/excision_unpack.h:21-106), TwoBitFour::prepare / unpack /
+//     nlow_build (dsp/TwoBitFour.h:42-89, TwoBitFour.C:25-40), TwoBitLookup::lookup_build
+//     (TwoBitLookup.C:63-98), TwoBitTable::generate_unique_values (TwoBitTable.C:42-75), BitTable::
+//     generate MostToLeast (BitTable.C:121-163).  CPSR2 convention: OffsetBinary, polarisations
+//     interleaved byte by byte (cpsr2/CPSR2TwoBitCorrection.C:11-23, ExcisionUnpacker.C:258-277).
+//
+//     JenetAnderson98 lives in PSRCHIVE (not in the reference tree); restated from Jenet & Anderson
+//     (1998, PASP 110, 1467) section 6 with sigma = 1:
+//       alpha = ierf(Phi)                                          (Eq. 45)
+//       lo^2  = 1 - (2 alpha / sqrt(pi)) exp(-alpha^2) / Phi        (Eq. 41: <x^2 | |x| < threshold>)
+//       hi^2  = 1 + (2 alpha / sqrt(pi)) exp(-alpha^2) / (1 - Phi)  (Eq. 40: <x^2 | |x| > threshold>)
+//     i.e. the power-preserving levels of the dynamic level-setting scheme (NOT the Lloyd-Max
+//     conditional means 0.4528 / 1.510); PARITY UNPINNED against PSRCHIVE's own JenetAnderson98.C.
+//       mean_Phi = erf(threshold / sqrt 2), var_Phi = mean_Phi (1 - mean_Phi); optimal threshold 0.9674
+// ---------------------------------------------------------------------------------------
+static double orc_ierf(double y) {
+  // inverse error function: Newton iterations on erf from a rational starting point
+  if (y <= -1.0) return -INFINITY;
+  if (y >= 1.0) return INFINITY;
+  const double a = 0.147;
+  const double ln1 = std::log(1.0 - y * y);
+  const double t = 2.0 / (M_PI * a) + 0.5 * ln1;
+  double x = std::copysign(std::sqrt(std::sqrt(t * t - ln1 / a) - t), y);
+  for (int i = 0; i < 4; i++) x -= (std::erf(x) - y) / (2.0 / std::sqrt(M_PI) * std::exp(-x * x));
+  return x;
+}
+
+void orc_ja98_levels(double Phi, double* lo, double* hi) {
+  const double root_pi = std::sqrt(M_PI);
+  const double alpha = orc_ierf(Phi);
+  const double expon = std::exp(-alpha * alpha);
+  *lo = std::sqrt(1.0 - (2.0 * alpha / root_pi) * (expon / Phi));
+  *hi = std::sqrt(1.0 + (2.0 * alpha / root_pi) * (expon / (1.0 - Phi)));
+}
+
+// ExcisionUnpacker::set_limits (ExcisionUnpacker.C:95-158)
+void orc_twobit_limits(double threshold, float cutoff_sigma, unsigned ndat_per_weight, unsigned* nlow_min,
+                       unsigned* nlow_max) {
+  if (cutoff_sigma == 0.0) {
+    *nlow_min = 0;
+    *nlow_max = ndat_per_weight;
+    return;
+  }
+  const double mean_Phi = std::erf(threshold / std::sqrt(2.0));
+  const double var_Phi = mean_Phi * (1.0 - mean_Phi);
+  float fsample = ndat_per_weight;
+  float nlo_mean = fsample * mean_Phi;
+  float nlo_variance = fsample * var_Phi;
+  float nlo_sigma = sqrt(nlo_variance);
+  *nlow_max = unsigned(nlo_mean + (cutoff_sigma * nlo_sigma));
+  if (*nlow_max >= ndat_per_weight) *nlow_max = ndat_per_weight - 1;
+  if (cutoff_sigma * nlo_sigma >= nlo_mean + 1.0) *nlow_min = 1;
+  else *nlow_min = unsigned(nlo_mean - (cutoff_sigma * nlo_sigma));
+}
+
+// TwoBitTable::generate_unique_values (TwoBitTable.C:42-75); type 0 OffsetBinary, 1 SignMagnitude,
+// 2 TwosComplement
+static void twobit_unique_values(int type, float lo_val, float hi_val, float* vals) {
+  switch (type) {
+    case 0: vals[0] = -hi_val; vals[1] = -lo_val; vals[2] = lo_val; vals[3] = hi_val; break;
+    case 1: vals[0] = lo_val; vals[1] = hi_val; vals[2] = -lo_val; vals[3] = -hi_val; break;
+    default: vals[0] = lo_val; vals[1] = hi_val; vals[2] = -hi_val; vals[3] = -lo_val; break;
+  }
+}
+
+// BitTable::generate for nbit = 2, MostToLeast (BitTable.C:121-163): 4 floats per unique byte
+static void twobit_generate(int type, float lo_val, float hi_val, float* table /* 256*4 */) {
+  float vals[4];
+  twobit_unique_values(type, lo_val, hi_val, vals);
+  for (unsigned byte = 0; byte < 256; byte++)
+    for (unsigned samp = 0; samp < 4; samp++) table[byte * 4 + samp] = vals[(byte >> (6 - 2 * samp)) & 3];
+}
+
+struct orc_twobit {
+  int table_type;
+  unsigned ndat_per_weight, nlow_min, nlow_max;
+  std::vector<float>* lookup;     // (nlow_max-nlow_min+1) blocks of 256*4 floats (TwoBitLookup::lookup_build)
+  char nlow_lookup[256];          // TwoBitFour::nlow_build
+};
+
+orc_twobit* orc_twobit_create(int table_type, double threshold, float cutoff_sigma, unsigned ndat_per_weight) {
+  orc_twobit* t = new orc_twobit();
+  t->table_type = table_type;
+  t->ndat_per_weight = ndat_per_weight;
+  orc_twobit_limits(threshold, cutoff_sigma, ndat_per_weight, &t->nlow_min, &t->nlow_max);
+  t->lookup = new std::vector<float>(size_t(t->nlow_max - t->nlow_min + 1) * 1024);
+  float* lookup = t->lookup->data();
+  for (unsigned nlo = t->nlow_min; nlo <= t->nlow_max; nlo++) {   // TwoBitLookup.C:75-97
+    unsigned use_nlow = nlo;
+    if (nlo == 0) use_nlow = 1;
+    float p_in = (float)use_nlow / (float)ndat_per_weight;
+    double lo, hi;
+    orc_ja98_levels(p_in, &lo, &hi);
+    twobit_generate(table_type, float(lo), float(hi), lookup);
+    lookup += 1024;
+  }
+  // TwoBitFour::nlow_build (TwoBitFour.C:25-40): count the low-voltage states of every byte
+  float fv[1024];
+  twobit_generate(table_type, 1.0f, 0.75f, fv);
+  for (unsigned byte = 0; byte < 256; byte++) {
+    t->nlow_lookup[byte] = 0;
+    for (unsigned i = 0; i < 4; i++)
+      if (fv[byte * 4 + i] * fv[byte * 4 + i] == 1.0f) t->nlow_lookup[byte]++;
+  }
+  return t;
+}
+void orc_twobit_destroy(orc_twobit* t) {
+  if (t) {
+    delete t->lookup;
+    delete t;
+  }
+}
+void orc_twobit_info(const orc_twobit* t, unsigned* nlow_min, unsigned* nlow_max) {
+  *nlow_min = t->nlow_min;
+  *nlow_max = t->nlow_max;
+}
+// lo / hi of table row nlow (for the product's compact table)
+void orc_twobit_levels(const orc_twobit* t, unsigned nlow, float* lo, float* hi) {
+  const float* blk = t->lookup->data() + size_t(nlow - t->nlow_min) * 1024;
+  float a = std::fabs(blk[0]), b = a;   // byte 0 and the other magnitude
+  for (unsigned i = 0; i < 1024; i++) {
+    a = std::min(a, std::fabs(blk[i]));
+    b = std::max(b, std::fabs(blk[i]));
+  }
+  *lo = a;
+  *hi = b;
+}
+
+// ExcisionUnpacker::unpack for real-sampled (ndim 1) data, one digitizer per polarisation:
+// out plane p = out + p*span, weights[p*nweights + w] start at 1 and are masked (AND over
+// polarisations, WeightedTimeSeries::mask_weights) at the end.
+void orc_unpack_twobit(const orc_twobit* t, const uint8_t* raw, uint64_t ndat, unsigned npol, float* out,
+                       uint64_t span, unsigned* weights, uint64_t nweights) {
+  const unsigned ndat_per_weight = t->ndat_per_weight;
+  const uint64_t n_weights = ndat / ndat_per_weight;
+  for (uint64_t i = 0; i < nweights * npol; i++) weights[i] = 1;
+  for (unsigned idig = 0; idig < npol; idig++) {
+    const uint8_t* input = raw + idig;            // get_input_offset = idig, get_input_incr = npol
+    float* output = out + uint64_t(idig) * span;
+    unsigned* w = weights + uint64_t(idig) * nweights;
+    for (uint64_t wt = 0; wt < n_weights; wt++) {
+      // TwoBitFour::prepare
+      const unsigned nbyte = ndat_per_weight / 4;
+      unsigned total = 0, nlow = 0;
+      for (unsigned bt = 0; bt < nbyte; bt++) {
+        nlow += t->nlow_lookup[input[bt * npol]];
+        total += input[bt * npol];
+      }
+      const bool bad = (total == 0);
+      // TwoBitFour::unpack
+      const unsigned n_low = nlow;
+      if (nlow < t->nlow_min) nlow = t->nlow_min;
+      else if (nlow > t->nlow_max) nlow = t->nlow_max;
+      const float* lookup = t->lookup->data() + size_t(nlow - t->nlow_min) * 1024;
+      for (unsigned bt = 0; bt < nbyte; bt++) {
+        const float* fourval = lookup + input[bt * npol] * 4;
+        for (unsigned pt = 0; pt < 4; pt++) output[bt * 4 + pt] = fourval[pt];
+      }
+      input += uint64_t(nbyte) * npol;
+      // excision_unpack.h:79-97
+      if (bad || n_low < t->nlow_min || n_low > t->nlow_max || w[wt] == 0) {
+        w[wt] = 0;
+        for (unsigned i = 0; i < ndat_per_weight; i++) output[i] = 0.0;
+      }
+      output += ndat_per_weight;
+    }
+  }
+  // WeightedTimeSeries::mask_weights: a window flagged in any polarisation is flagged in all
+  for (uint64_t wt = 0; wt < n_weights; wt++) {
+    unsigned all = 1;
+    for (unsigned p = 0; p < npol; p++) all &= weights[p * nweights + wt] != 0;
+    for (unsigned p = 0; p < npol; p++) weights[p * nweights + wt] = all;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // a9  optimal_fft_length (Signal/General/optimize_fft.c:63-127)
 // ---------------------------------------------------------------------------------------
 int64_t orc_optimal_fft_length(uint64_t nbadperfft, uint64_t nfft_max) {

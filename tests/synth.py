@@ -38,3 +38,15 @@ def relerr(a, b):
     b = np.asarray(b, np.float64).ravel()
     rms = np.sqrt(np.mean(b * b))
     return float(np.max(np.abs(a - b)) / rms) if rms > 0 else float(np.max(np.abs(a - b)))
+
+
+def twobit_bytes(ndat, npol=2, seed=0, sigma=1.0, threshold=0.9674):
+    """CPSR2-style 2-bit OffsetBinary stream: Gaussian noise digitised at +-threshold*sigma_nominal
+    (codes 0..3 = -hi, -lo, +lo, +hi), four samples per byte most-significant first, polarisations
+    interleaved byte by byte.  `sigma` scales the input power (1 = nominal)."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((npol, ndat)) * sigma
+    code = np.where(x < -threshold, 0, np.where(x < 0, 1, np.where(x < threshold, 2, 3))).astype(np.uint8)
+    c = code.reshape(npol, ndat // 4, 4)
+    byte = (c[:, :, 0] << 6) | (c[:, :, 1] << 4) | (c[:, :, 2] << 2) | c[:, :, 3]
+    return np.ascontiguousarray(byte.T).reshape(-1).astype(np.uint8)     # [ndat/4][npol]

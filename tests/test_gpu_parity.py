@@ -316,3 +316,58 @@ def test_cpp_engine_shims_demo(ctx, oracle, tmp_path):
     ref, ref_hits = oracle.pipe_run(p, raw, 1, npart_all, [phi], [pps], 1)
     assert np.array_equal(hits, ref_hits)
     assert synth.relerr(prof, ref) <= TOL
+
+
+# ------------------------------------------------------------------------------------ two-bit excision (a6)
+@pytest.mark.parametrize("npol", [1, 2])
+def test_unpack_twobit_bitexact(ctx, oracle, npol):
+    """TwoBitCorrection (CPSR2 convention) on the device: floats and weights identical to the CPU loops,
+    including all-zero windows, windows outside the nlow limits and windows at other input powers."""
+    torch, E = _torch(), _E()
+    ndat = 512 * 40
+    raw = synth.twobit_bytes(ndat, npol, seed=5).reshape(-1, npol).copy()
+    loud = synth.twobit_bytes(ndat, npol, seed=6, sigma=1.6).reshape(-1, npol)
+    quiet = synth.twobit_bytes(ndat, npol, seed=7, sigma=0.7).reshape(-1, npol)
+    raw[128 * 10:128 * 14] = loud[128 * 10:128 * 14]        # nlow well below the mean: other table rows
+    raw[128 * 20:128 * 24] = quiet[128 * 20:128 * 24]
+    raw[128 * 3:128 * 4, 0] = 0x00                         # all-zero bytes
+    raw[128 * 5:128 * 6, npol - 1] = 0xFF                  # nlow = 0
+    raw[128 * 7:128 * 8, 0] = 0x99                         # nlow = 512
+    raw = raw.reshape(-1)
+    t = oracle.TwoBit()
+    ref, wref = t.unpack(raw, ndat, npol)
+    tb = E.make_twobit_desc(npol=npol)
+    assert (tb.nlow_min, tb.nlow_max) == (t.nlow_min, t.nlow_max)
+    out, w = E.unpack_twobit(ctx, tb, torch.from_numpy(raw).cuda(), ndat)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    assert np.array_equal(w.cpu().numpy().astype(np.uint32), wref[0])
+    assert wref[0].sum() < len(wref[0])                     # some windows really were excised
+    # through the generic Unpacker hook as well
+    ud = E.make_twobit_unpack_desc(tb)
+    out2 = E.unpack(ctx, ud, torch.from_numpy(raw).cuda(), ndat)
+    assert np.array_equal(out2.cpu().numpy(), ref)
+
+
+def test_pipeline_cfg2_twobit_filterbank_intensity(ctx, oracle):
+    """BASELINE configs[1] (digifil-style): 2-bit dual-pol real input, -F 4096:D coherent filterbank
+    (freq_res 8, nfilt 1+1), Intensity detection, no fold -- detected float series vs the oracle chain."""
+    torch, E, L = _torch(), _E(), _L()
+    C, F, npos, nneg, npart = 4096, 8, 1, 1, 5
+    d, H = oracle.dedispersion(1400.0, 128.0, 50.0, 1, C, True)
+    assert (d.ndat, d.impulse_pos, d.impulse_neg) == (F, npos, nneg)
+    f = oracle.fb_sizes(1, 1, 2, C, F, npos, nneg)
+    ndat = npart * f.nsamp_step + f.nsamp_overlap
+    ndat = (ndat + 511) // 512 * 512
+    raw = synth.twobit_bytes(ndat, 2, seed=21)
+    t = oracle.TwoBit()
+    x, _ = t.unpack(raw, ndat, 2)
+    volt = oracle.filterbank(f, x[:, :, : npart * f.nsamp_step + f.nsamp_overlap], H)
+    ref = oracle.detect("Intensity", 1, volt)
+    tb = E.make_twobit_desc(npol=2)
+    ud = E.make_twobit_unpack_desc(tb)
+    fd, keep = E.make_fb_desc(1, 1, 2, C, F, npos, nneg, H)
+    pipe = E.Pipeline(ctx, ud, fd, keep, "Intensity", 1, 0)
+    det = pipe.execute(torch.from_numpy(raw).cuda(), npart, 0.0, 0.0, first_sample=0)
+    det = det.cpu().numpy()
+    assert det.shape == ref.shape
+    assert synth.relerr(det, ref) <= TOL

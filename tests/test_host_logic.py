@@ -197,3 +197,16 @@ def test_gloo_world2_time_sharded_combine(oracle, tmp_path):
     assert np.array_equal(g["hits"].astype(np.uint32), hits) and int(g["nt"]) == total_parts * f.nkeep
     assert synth.relerr(g["prof"], prof) < 1e-6
     assert np.array_equal(g["gathered"][:, 0], np.arange(5, dtype=np.float32))
+
+
+def test_twobit_tables_bitexact_with_oracle(oracle):
+    """b200_twobit_prepare (product) and the oracle's TwoBitCorrection::build restatement produce the same
+    limits and bit-identical float levels for every table row."""
+    from dspsr_b200 import engine as E
+    for cutoff in (10.0, 3.0, 0.0):
+        t = oracle.TwoBit(cutoff_sigma=cutoff)
+        d = E.make_twobit_desc(npol=2, cutoff_sigma=cutoff)
+        assert (d.nlow_min, d.nlow_max) == (t.nlow_min, t.nlow_max)
+        for nlow in range(max(t.nlow_min, 1), min(t.nlow_max, 511) + 1):
+            lo, hi = t.levels(nlow)
+            assert (d.lo[nlow - d.nlow_min], d.hi[nlow - d.nlow_min]) == (lo, hi), nlow

@@ -269,3 +269,55 @@ def test_pipeline_threads_equal_serial(oracle):
     b, hb = oracle.pipe_run(p, raw, nblock, npart, phi, pps, nthread=3)
     assert np.array_equal(ha, hb) and ha.sum() == nblock * npart * f.nkeep
     assert synth.relerr(b, a) < 1e-6
+
+
+# ----------------------------------------------------------------------------- a6 two-bit excision
+def test_twobit_levels_and_limits(oracle):
+    """JA98 section 6 levels are the conditional rms of a unit Gaussian below / above the threshold, so the
+    digitised power equals the undigitised power (Phi lo^2 + (1-Phi) hi^2 = 1); checked against numerical
+    integration.  ExcisionUnpacker::set_limits for the defaults (512 samples, threshold 0.9674, cutoff
+    10 sigma) gives [234, 447]."""
+    for phi in (0.2, 0.5, 0.6667, 0.9):
+        lo, hi = oracle.ja98_levels(phi)
+        assert phi * lo * lo + (1 - phi) * hi * hi == pytest.approx(1.0, abs=1e-12)
+        assert 0 < lo < 1 < hi
+    import math
+    from scipy import integrate, stats
+    u = 0.9674
+    lo, hi = oracle.ja98_levels(math.erf(u / math.sqrt(2)))
+    p_lo = integrate.quad(lambda x: x * x * stats.norm.pdf(x), -u, u)[0] / (stats.norm.cdf(u) - stats.norm.cdf(-u))
+    p_hi = 2 * integrate.quad(lambda x: x * x * stats.norm.pdf(x), u, 12)[0] / (2 * stats.norm.cdf(-u))
+    assert lo == pytest.approx(math.sqrt(p_lo), rel=1e-9) and hi == pytest.approx(math.sqrt(p_hi), rel=1e-9)
+    t = oracle.TwoBit()
+    assert (t.nlow_min, t.nlow_max) == (234, 447)
+    t0 = oracle.TwoBit(cutoff_sigma=0.0)
+    assert (t0.nlow_min, t0.nlow_max) == (0, 512)
+    # rows are ordered: more low states = more input power below threshold = smaller sigma estimate
+    lo_a, hi_a = t.levels(300)
+    lo_b, hi_b = t.levels(400)
+    assert lo_a < lo_b and hi_a < hi_b
+
+
+def test_twobit_unpack_semantics(oracle):
+    """Window statistics select the level row; all-zero windows and windows whose nlow is outside the
+    limits are zeroed and flagged (excision_unpack.h:79-97), per digitizer; weights are masked over pols."""
+    ndat, npol = 512 * 6, 2
+    raw = synth.twobit_bytes(ndat, npol, seed=3).reshape(-1, npol).copy()
+    raw[128 * 1:128 * 2, 0] = 0x00          # pol 0, window 1: all-zero bytes -> bad
+    raw[128 * 3:128 * 4, 1] = 0xFF          # pol 1, window 3: every sample +hi -> nlow = 0 < nlow_min
+    raw[128 * 4:128 * 5, 0] = 0x66          # pol 0, window 4: every sample low -> nlow = 512 > nlow_max
+    t = oracle.TwoBit()
+    out, w = t.unpack(raw.reshape(-1), ndat, npol)
+    assert np.array_equal(w[0], [1, 0, 1, 0, 0, 1]) and np.array_equal(w[0], w[1])
+    assert not out[0, 0, 512:1024].any() and out[0, 1, 512:1024].any()       # only the bad digitizer is zeroed
+    assert not out[0, 1, 1536:2048].any() and out[0, 0, 1536:2048].any()
+    assert not out[0, 0, 2048:2560].any()
+    # a good window: four distinct values -hi, -lo, lo, hi of the row selected by its own nlow
+    win = out[0, 0, :512]
+    codes = np.array([(b >> s) & 3 for b in raw[:128, 0] for s in (6, 4, 2, 0)])
+    nlow = int(np.sum((codes == 1) | (codes == 2)))
+    lo, hi = t.levels(nlow)
+    want = np.array([-hi, -lo, lo, hi], np.float32)[codes]
+    assert np.array_equal(win, want)
+    # unit variance on average at nominal power
+    assert np.var(out[0, 0, 2560:]) == pytest.approx(1.0, rel=0.15)
