@@ -33,6 +33,11 @@ struct b200_pipeline {
   uint64_t unpacked_floats;
   unsigned nprod, dnpol, dndim;
   b200_twobit_desc twobit;
+  // unfused tail (per-channel transforms too long for the fused epilogues): voltages, then detected series
+  float* d_volt;
+  uint64_t volt_floats;
+  float* d_det;
+  uint64_t det_floats;
 };
 
 static unsigned fmt_resolution(int fmt) {
@@ -115,6 +120,8 @@ int b200_pipeline_destroy(b200_pipeline* p) {
   }
   if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
   if (p->d_unpacked) cudaFree(p->d_unpacked);
+  if (p->d_volt) cudaFree(p->d_volt);
+  if (p->d_det) cudaFree(p->d_det);
   delete p;
   return B200_OK;
 }
@@ -193,6 +200,50 @@ static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t inpu
   memset(&sink, 0, sizeof(sink));
   sink.state = p->desc.detect_state;
   sink.dndim = p->dndim;
+
+  // Per-channel inverse transforms above 8192 points do not fit one SM with both polarisations, so the
+  // detection / fold epilogues cannot be fused: run the engine for voltages, then the stand-alone
+  // detection and fold engines (what dspsr itself does: three separate operations).
+  if (fb->F > 8192 && !fb->conv_path) {
+    const unsigned npol = fb->desc.npol;
+    const uint64_t vneed = uint64_t(fb->nchan_out) * npol * ndat_out * 2;
+    if (vneed > p->volt_floats) {
+      B200_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (p->d_volt) cudaFree(p->d_volt);
+      p->d_volt = nullptr;
+      p->volt_floats = vneed;
+      B200_CUDA(cudaMalloc(&p->d_volt, vneed * sizeof(float)));
+    }
+    sink.kind = EPI_VOLT;
+    sink.volt = p->d_volt;
+    sink.volt_span = ndat_out * 2;
+    sink.volt_step = uint64_t(fb->nkeep) * 2;
+    int rc = fb_run(fb, src, sink, npart);
+    if (rc != B200_OK) return rc;
+    float* det = d_detected;
+    uint64_t det_span = detected_span;
+    if (p->desc.nbin) {
+      const uint64_t dneed = uint64_t(fb->nchan_out) * p->dnpol * ndat_out * p->dndim;
+      if (dneed > p->det_floats) {
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (p->d_det) cudaFree(p->d_det);
+        p->d_det = nullptr;
+        p->det_floats = dneed;
+        B200_CUDA(cudaMalloc(&p->d_det, dneed * sizeof(float)));
+      }
+      det = p->d_det;
+      det_span = ndat_out * p->dndim;
+    } else {
+      B200_REQUIRE(d_detected, "b200_pipeline_execute: nbin == 0 needs an output buffer for the detected series");
+    }
+    rc = b200_detect(reinterpret_cast<b200_context*>(ctx), p->desc.detect_state, p->dndim, p->d_volt, ndat_out * 2,
+                     fb->nchan_out, npol, ndat_out, det, det_span);
+    if (rc != B200_OK || !p->desc.nbin) return rc;
+    rc = b200_fold_set_bins(p->fold, phi, pps, ndat_out, 0, nullptr);
+    if (rc != B200_OK) return rc;
+    return b200_fold_fold(p->fold, det, det_span);
+  }
+
   if (p->desc.nbin) {
     int rc = b200_fold_set_bins(p->fold, phi, pps, ndat_out, 0, nullptr);
     if (rc != B200_OK) return rc;

@@ -371,3 +371,76 @@ def test_pipeline_cfg2_twobit_filterbank_intensity(ctx, oracle):
     det = det.cpu().numpy()
     assert det.shape == ref.shape
     assert synth.relerr(det, ref) <= TOL
+
+
+# ------------------------------------------------------------------------------------ other BASELINE configs, end to end
+def _pipe_generic(ctx, oracle, fmt, input_nchan, npol, ndim, raw, ndat_unpacked, fbs, convs, H, C, F, npos, nneg,
+                  npart, state, dndim, nbin, lut=None, scale=0.0, swap=1, nblock=1, max_npart=0):
+    """raw bytes of `fmt` -> pipeline (fold) on the GPU vs the oracle pipeline."""
+    torch, E = _torch(), _E()
+    nkeep = F - npos - nneg
+    pps = 1.0 / (0.41 * nkeep * npart)
+    phis = [0.2 + 0.17 * b for b in range(nblock)]
+    ppss = [pps] * nblock
+    op = oracle.make_pipe(fmt, input_nchan, npol, ndim, lut, scale, fbs, convs, H, state, dndim, nbin)
+    ref, ref_hits = oracle.pipe_run(op, raw, nblock, npart, phis, ppss, nthread=1)
+    ud = E.make_unpack_desc(fmt, input_nchan, npol, ndim, lut, scale, swap)
+    fd, keep = E.make_fb_desc(ndim == 1, input_nchan, npol, C, F, npos, nneg, H, max_npart)
+    pipe = E.Pipeline(ctx, ud, fd, keep, state, dndim, nbin)
+    d_raw = torch.from_numpy(raw).cuda()
+    step = pipe.info.nsamp_step
+    for b in range(nblock):
+        pipe.execute(d_raw, npart, phis[b], ppss[b], first_sample=b * npart * step)
+    prof, hits, ntot = pipe.synch()
+    assert np.array_equal(hits, ref_hits) and ntot == nblock * npart * nkeep
+    return synth.relerr(prof, ref)
+
+
+def test_pipeline_cfg3_meerkat_convolution_fold(ctx, oracle):
+    """BASELINE configs[2] on a channel shard: MeerKAT 8-bit complex, 8 of the 1024 input channels,
+    Convolution with the 65536-point response (M = 2536 + 2543), Coherence, fold 1024 bins."""
+    L = _L()
+    nchan, F, npos, nneg, npart = 8, 65536, 2536, 2543, 2
+    c = oracle.conv_sizes(0, nchan, 2, F, npos, nneg)
+    ndat = (npart * c.nsamp_step + c.nsamp_overlap + 255) // 256 * 256
+    rng = np.random.default_rng(31)
+    raw = rng.integers(-60, 60, size=ndat * nchan * 2 * 2, dtype=np.int8).view(np.uint8)
+    _, scale = oracle.bittable8()
+    H = np.exp(1j * rng.uniform(-np.pi, np.pi, (nchan, F))).astype(np.complex64)
+    err = _pipe_generic(ctx, oracle, L.FMT_MEERKAT8, nchan, 2, 2, raw, ndat, None, c, H, 1, F, npos, nneg, npart,
+                        "Coherence", 4, 1024, scale=np.float32(scale))
+    assert err <= TOL, err
+
+
+def test_pipeline_cfg4_single_channel_4m_convolution(ctx, oracle):
+    """BASELINE configs[3]: one 400 MHz channel at 12.5 GHz, DM 1500, 2^22-point overlap-save
+    (M = 534848 + 588748), generic 8-bit complex input, Coherence, fold."""
+    L = _L()
+    F, npos, nneg, npart = 1 << 22, 534848, 588748, 2
+    c = oracle.conv_sizes(0, 1, 2, F, npos, nneg)
+    ndat = npart * c.nsamp_step + c.nsamp_overlap
+    rng = np.random.default_rng(41)
+    raw = rng.integers(0, 256, size=ndat * 2 * 2, dtype=np.uint8)
+    lut, _ = oracle.bittable8()
+    d, H = oracle.dedispersion(12500.0, 400.0, 1500.0, 1, 1, False, frequency_resolution=F)
+    assert (d.impulse_pos, d.impulse_neg) == (npos, nneg)
+    err = _pipe_generic(ctx, oracle, L.FMT_GENERIC8, 1, 2, 2, raw, ndat, None, c, H, 1, F, npos, nneg, npart,
+                        "Coherence", 4, 1024, lut=lut)
+    assert err <= TOL, err
+
+
+@pytest.mark.parametrize("sb,F,npos,nneg", [(0, 16384, 886, 890), (6, 2048, 98, 98), (25, 64, 6, 6)])
+def test_pipeline_cfg5_uwl_subband(ctx, oracle, sb, F, npos, nneg):
+    """BASELINE configs[4]: UWL-like 128 MHz sub-bands, 16-bit complex dual-pol, -F 128:D, fold.
+    Sub-band 0 (freq_res 16384) takes the unfused tail (voltages -> detect -> fold)."""
+    L = _L()
+    C, npart = 128, 2
+    d, H = oracle.dedispersion(768.0 + 128.0 * sb, 128.0, 67.99, 1, C, False)
+    assert (d.ndat, d.impulse_pos, d.impulse_neg) == (F, npos, nneg)
+    f = oracle.fb_sizes(0, 1, 2, C, F, npos, nneg)
+    ndat = (npart * f.nsamp_step + f.nsamp_overlap + 2047) // 2048 * 2048
+    rng = np.random.default_rng(50 + sb)
+    raw = (rng.normal(0, 2000, size=ndat * 2 * 2).astype(np.int16) ^ np.int16(-32768)).view(np.uint8)
+    err = _pipe_generic(ctx, oracle, L.FMT_UWB16, 1, 2, 2, raw, ndat, f, None, H, C, F, npos, nneg, npart,
+                        "Coherence", 4, 1024)
+    assert err <= TOL, err
