@@ -24,6 +24,16 @@ class TwoBitDesc(C.Structure):
     ]
 
 
+class TimeDivide(C.Structure):
+    _fields_ = [("division_seconds", C.c_double), ("lower", C.c_double), ("upper", C.c_double),
+                ("current_end", C.c_double), ("is_valid", C.c_int), ("division", C.c_uint64)]
+
+
+class TimeBounds(C.Structure):
+    _fields_ = [("is_valid", C.c_int), ("new_division", C.c_int), ("end_reached", C.c_int), ("in_next", C.c_int),
+                ("idat_start", C.c_uint64), ("ndat", C.c_uint64), ("division", C.c_uint64)]
+
+
 class UnpackDesc(C.Structure):
     _fields_ = [
         ("format", C.c_int),
@@ -123,6 +133,9 @@ _pvp = C.POINTER(C.c_void_p)
 
 # name -> (restype, argtypes); every symbol include/b200dsp.h declares
 SIGNATURES = {
+    "b200_time_divide_init": (_i, [C.POINTER(TimeDivide), C.c_double]),
+    "b200_time_divide_set_bounds": (_i, [C.POINTER(TimeDivide), C.c_double, C.c_double, C.c_uint64,
+                                         C.POINTER(TimeBounds)]),
     "b200_twobit_prepare": (_i, [C.c_double, C.c_float, _i, C.c_uint, C.c_uint, C.POINTER(TwoBitDesc)]),
     "b200_unpack_twobit": (_i, [_vp, C.POINTER(TwoBitDesc), _vp, C.c_uint64, _vp, C.c_uint64, _vp]),
     "b200_version": (_i, []),

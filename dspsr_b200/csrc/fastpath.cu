@@ -69,9 +69,11 @@ __global__ void __launch_bounds__(NP*(P / 16), 1) k1_c2(K1Args a) {
   // CASPSR: byte 8*(i/4) + 4*pol + i%4 (CASPSRUnpacker.C:141-187); columns n2, n2+1 = samples
   // 2*n2 .. 2*n2+3 = one 4-byte group of this polarisation
   auto raw_ptr = [&](unsigned t) -> const unsigned char* {
-    const unsigned col0 = (t % ncolblk) * (2 * NP), blk = t / ncolblk;
-    const unsigned pol = blk % a.npol;
-    const uint64_t part = a.part0 + blk / (a.npol * a.nchan_in);
+    // tile order: polarisation fastest, then column block -- the two polarisations of a column block
+    // share every 32-byte sector of the raw stream, so they run side by side and the second reader hits L2
+    const unsigned pol = t % a.npol, col0 = ((t / a.npol) % ncolblk) * (2 * NP);
+    const unsigned rest = t / (a.npol * ncolblk);
+    const uint64_t part = a.part0 + rest / a.nchan_in;
     return static_cast<const unsigned char*>(a.src) + 2ull * (part * a.step) + 4u * pol +
            4ull * (uint64_t(j) * Q + col0 + 2 * pair);
   };
@@ -85,11 +87,12 @@ __global__ void __launch_bounds__(NP*(P / 16), 1) k1_c2(K1Args a) {
   }
 
   for (; t < ntiles; t += gridDim.x) {
-    const unsigned col0 = (t % ncolblk) * (2 * NP), blk = t / ncolblk;
+    const unsigned pol = t % a.npol, col0 = ((t / a.npol) % ncolblk) * (2 * NP);
+    const unsigned rest = t / (a.npol * ncolblk);            // (part, input channel)
     const unsigned n2 = col0 + 2 * pair;
-    const unsigned pol = blk % a.npol;
-    const unsigned ic = (blk / a.npol) % a.nchan_in;
-    const uint64_t part = a.part0 + blk / (a.npol * a.nchan_in);
+    const unsigned ic = rest % a.nchan_in;
+    const uint64_t part = a.part0 + rest / a.nchan_in;
+    const unsigned blk = rest * a.npol + pol;
 
     // twiddles of this tile (loads in flight while the samples are converted)
     float2 shv = make_float2(1.f, 0.f);

@@ -276,6 +276,68 @@ int b200_twobit_prepare(double threshold, float cutoff_sigma, int table_type, un
   return B200_OK;
 }
 
+// ---- TimeDivide (seconds mode) ------------------------------------------------------------------
+int b200_time_divide_init(b200_time_divide* td, double division_seconds) {
+  if (!td || !(division_seconds > 0)) return B200_ERR_INVALID;
+  td->division_seconds = division_seconds;
+  td->lower = td->upper = td->current_end = 0.0;
+  td->is_valid = 0;
+  td->division = 0;
+  return B200_OK;
+}
+
+int b200_time_divide_set_bounds(b200_time_divide* td, double input_start, double rate, uint64_t input_ndat,
+                                b200_time_bounds* o) {
+  if (!td || !o || !(rate > 0)) return B200_ERR_INVALID;
+  const double input_end = input_start + double(input_ndat) / rate;
+  // TimeDivide.C:147-160: where to start
+  double divide_start = input_start;
+  if (td->is_valid) divide_start = std::max(td->current_end, input_start);
+  o->new_division = o->end_reached = o->in_next = 0;
+  if (input_end < td->lower || divide_start + 0.5 / rate > td->upper) {       // :166-196
+    o->new_division = 1;
+    const double t = divide_start + 0.55 / rate;                              // set_boundaries(:349-425)
+    const double ds = std::max(0.0, t);
+    td->division = uint64_t(ds / td->division_seconds);
+    td->lower = double(td->division) * td->division_seconds;
+    td->upper = double(td->division + 1) * td->division_seconds;
+  }
+  divide_start = std::max(td->lower, divide_start);
+  o->division = td->division;
+  // :210-231: how far into the block to start
+  double start_sample = std::rint((divide_start - input_start) * rate);
+  if (start_sample < 0) start_sample = 0;
+  o->idat_start = uint64_t(start_sample);
+  o->ndat = 0;
+  if (o->idat_start >= input_ndat) {
+    td->is_valid = o->is_valid = 0;
+    return B200_OK;
+  }
+  // :233-300: how far into the block to end
+  double divide_end = std::min(input_end, td->upper);
+  uint64_t idat_end = uint64_t(std::rint((divide_end - input_start) * rate));
+  if (idat_end <= o->idat_start) {
+    // A boundary exactly half-way between two samples leaves the old division with nothing to fold; the
+    // reference throws InvalidState here (TimeDivide.C:258-287).  Start the next division instead.
+    o->new_division = 1;
+    td->division += 1;
+    td->lower = double(td->division) * td->division_seconds;
+    td->upper = double(td->division + 1) * td->division_seconds;
+    divide_end = std::min(input_end, td->upper);
+    idat_end = uint64_t(std::rint((divide_end - input_start) * rate));
+    o->division = td->division;
+    if (idat_end <= o->idat_start) return B200_ERR_INVALID;
+  }
+  if (idat_end > input_ndat) idat_end = input_ndat;
+  else if (idat_end < input_ndat) o->in_next = 1;
+  o->ndat = idat_end - o->idat_start;
+  // :302-317: has the end of the division been reached?
+  if ((td->upper - divide_end) * rate < 0.5) o->end_reached = 1;
+  td->is_valid = o->is_valid = 1;
+  td->current_end = input_start + double(idat_end) / rate;
+  return B200_OK;
+}
+
 int64_t b200_optimal_fft_length(uint64_t nbadperfft, uint64_t nfft_max) {
   return Dedispersion::optimal_fft_length(nbadperfft, nfft_max);
 }

@@ -310,6 +310,33 @@ int b200_polyco_parse(const char* text, b200_polyco* pc);
 double b200_polyco_phase(const b200_polyco* pc, int day, int sec, double frac, double* turns);
 double b200_polyco_frequency(const b200_polyco* pc, int day, int sec, double frac);
 
+/* Sub-integration boundaries.  Replaces the arithmetic of dsp::TimeDivide::set_bounds / set_boundaries
+ * (Signal/Pulsar/TimeDivide.C:132-330,349-425) for divisions given in seconds (dspsr -L), as driven by
+ * dsp::Subint<Fold>::transformation (Signal/Pulsar/dsp/Subint.h:235-305): each input block is cut at the
+ * division boundaries k*L measured from the observation start; the caller folds [idat_start, idat_start+ndat)
+ * (Fold::Engine::set_ndat) and, when end_reached, unloads and zeroes the PhaseSeries.  Times are seconds
+ * since the observation start. */
+typedef struct {
+  double division_seconds;
+  double lower, upper;       /* boundaries of the current division */
+  double current_end;        /* end of the data folded so far */
+  int is_valid;
+  uint64_t division;         /* index of the current division */
+} b200_time_divide;
+
+typedef struct {
+  int is_valid;              /* 0: the block ends before the current division starts */
+  int new_division;          /* a new division was started by this call */
+  int end_reached;           /* the block reaches the end of the division: unload + zero */
+  int in_next;               /* the block extends beyond the division: call set_bounds again */
+  uint64_t idat_start, ndat; /* slice of the block that belongs to the division */
+  uint64_t division;
+} b200_time_bounds;
+
+int b200_time_divide_init(b200_time_divide* td, double division_seconds);
+int b200_time_divide_set_bounds(b200_time_divide* td, double input_start, double rate, uint64_t input_ndat,
+                                b200_time_bounds* out);
+
 #ifdef __cplusplus
 }
 #endif

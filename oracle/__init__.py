@@ -427,3 +427,47 @@ def pipe_run(p, raw, nblock, parts_per_block, phi, pps, nthread=1):
     lib().orc_pipe_run(C.byref(p), _p(raw), C.c_uint64(nblock), C.c_uint64(parts_per_block), _p(phi), _p(pps),
                        C.c_uint(nthread), _p(profile), _p(hits))
     return profile, hits
+
+
+# ----------------------------------------------------------------------------- a15
+class TimeDivide:
+    """dsp::TimeDivide for divisions in seconds, restated line by line from Signal/Pulsar/TimeDivide.C
+    (set_bounds :132-330, set_boundaries :349-425) with times in seconds since the observation start."""
+
+    def __init__(self, division_seconds):
+        self.division_seconds = division_seconds
+        self.lower = self.upper = self.current_end = 0.0
+        self.is_valid = False
+        self.division = 0
+
+    def set_bounds(self, input_start, rate, input_ndat):
+        input_end = input_start + input_ndat / rate
+        divide_start = input_start
+        if self.is_valid:
+            divide_start = max(self.current_end, input_start)
+        new_division = end_reached = in_next = False
+        if input_end < self.lower or divide_start + 0.5 / rate > self.upper:
+            new_division = True
+            seconds = max(0.0, divide_start + 0.55 / rate)
+            self.division = int(seconds / self.division_seconds)
+            self.lower = float(self.division) * self.division_seconds
+            self.upper = float(self.division + 1) * self.division_seconds
+        divide_start = max(self.lower, divide_start)
+        idat_start = int(max(0.0, np.rint((divide_start - input_start) * rate)))
+        if idat_start >= input_ndat:
+            self.is_valid = False
+            return dict(is_valid=False, new_division=new_division, end_reached=False, in_next=False,
+                        idat_start=idat_start, ndat=0, division=self.division)
+        divide_end = min(input_end, self.upper)
+        idat_end = int(np.rint((divide_end - input_start) * rate))
+        assert idat_end > idat_start
+        if idat_end > input_ndat:
+            idat_end = input_ndat
+        elif idat_end < input_ndat:
+            in_next = True
+        if (self.upper - divide_end) * rate < 0.5:
+            end_reached = True
+        self.is_valid = True
+        self.current_end = input_start + idat_end / rate
+        return dict(is_valid=True, new_division=new_division, end_reached=end_reached, in_next=in_next,
+                    idat_start=idat_start, ndat=idat_end - idat_start, division=self.division)

@@ -444,3 +444,64 @@ def test_pipeline_cfg5_uwl_subband(ctx, oracle, sb, F, npos, nneg):
     err = _pipe_generic(ctx, oracle, L.FMT_UWB16, 1, 2, 2, raw, ndat, f, None, H, C, F, npos, nneg, npart,
                         "Coherence", 4, 1024)
     assert err <= TOL, err
+
+
+# ------------------------------------------------------------------------------------ sub-integrations (a15)
+def test_subint_folder_cuts_at_division_boundaries(ctx, oracle):
+    """dsp::Subint<Fold>: a detected stream folded block by block with -L seconds; every unloaded
+    sub-integration equals the oracle fold of exactly the samples of that division, sliced per block with
+    Fold::fold's phase set-up, and the hit totals add up to the stream length."""
+    torch, E = _torch(), _E()
+    from dspsr_b200 import hostmath as HM, workloads as W
+    from dspsr_b200.subint import SubintFolder
+    nchan, npol, ndim, nbin = 3, 1, 4, 256
+    rate = 1.5625e6 / 8
+    Ldiv = 0.05                                   # 9765.625 samples per division
+    start = HM.utc_to_mjd("2010-04-13-02:05:45")
+    pred = HM.Polyco(W.polyco_text())
+    opc = oracle.polyco_parse(W.polyco_text())
+    rng = np.random.default_rng(77)
+    blocks = [int(n) for n in rng.integers(3000, 9000, 9)]
+    total = sum(blocks)
+    x = (rng.standard_normal((nchan, npol, total * ndim)) + 2.0).astype(np.float32)
+    got = {}
+
+    def unload(division, prof, hits, ntot, partial):
+        assert division not in got
+        got[division] = (prof.copy(), hits.copy(), ntot, partial)
+
+    fe = E.FoldEngine(ctx, nchan, npol, ndim, nbin)
+    sf = SubintFolder(fe, pred, start, Ldiv, unload)
+    # oracle: same cutting rule (restated TimeDivide), CPU fold per slice
+    ot = oracle.TimeDivide(Ldiv)
+    want = {}
+    t0 = 0
+    for n in blocks:
+        blk = x[:, :, t0 * ndim:(t0 + n) * ndim]
+        sf.fold_block(torch.from_numpy(np.ascontiguousarray(blk)).cuda(), t0 / rate, rate)
+        more = True
+        while more:
+            o = ot.set_bounds(t0 / rate, rate, n)
+            more = o["in_next"]
+            if not o["is_valid"]:
+                continue
+            tb = HM.mjd_add(start, t0 / rate)
+            ts = HM.mjd_add(tb, (o["idat_start"] + 0.5) / rate)
+            phi = oracle.polyco_phase(opc, *ts)[0]
+            pps = (1.0 / rate) / (1.0 / oracle.polyco_frequency(opc, *ts))      # Fold.C:718-720
+            bp, hh, _, _ = oracle.fold_plan(phi, pps, nbin, o["ndat"])
+            prof, hits = want.get(o["division"], (None, np.zeros(nbin, np.uint32)))
+            prof = oracle.fold(np.ascontiguousarray(blk), ndim, bp, nbin, profile=prof, idat_start=o["idat_start"])
+            want[o["division"]] = (prof, hits + hh)
+        t0 += n
+    sf.finish()
+    assert sorted(got) == sorted(want) and len(got) >= 5
+    ntot = 0
+    for div in want:
+        prof, hits, n, partial = got[div]
+        assert np.array_equal(hits, want[div][1]) and n == hits.sum()
+        assert synth.relerr(prof, want[div][0]) <= TOL
+        ntot += n
+    assert ntot == total
+    assert got[min(got)][3] and got[max(got)][3]          # first and last divisions are flagged partial
+    assert not any(got[d][3] for d in sorted(got)[1:-1])

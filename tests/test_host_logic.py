@@ -210,3 +210,71 @@ def test_twobit_tables_bitexact_with_oracle(oracle):
         for nlow in range(max(t.nlow_min, 1), min(t.nlow_max, 511) + 1):
             lo, hi = t.levels(nlow)
             assert (d.lo[nlow - d.nlow_min], d.hi[nlow - d.nlow_min]) == (lo, hi), nlow
+
+
+def test_time_divide_matches_oracle_and_partitions_the_stream(oracle):
+    """b200_time_divide_set_bounds (product) vs the oracle's TimeDivide restatement on block sequences whose
+    boundaries do not line up with the divisions: identical decisions; every sample lands in exactly one
+    slice; slices of one division cover [k L, (k+1) L) of the stream."""
+    import ctypes as C
+    from dspsr_b200 import _lib as L
+    lib = L.load()
+    rng = np.random.default_rng(9)
+    for rate, Ldiv in ((1.5625e6, 0.01), (1e4, 0.37), (128e6 / 128, 10.0 / 4099)):
+        td = L.TimeDivide()
+        L.check(lib.b200_time_divide_init(C.byref(td), Ldiv))
+        ot = oracle.TimeDivide(Ldiv)
+        t0 = 0
+        covered = []
+        for blk in range(40):
+            ndat = int(rng.integers(1000, 30000))
+            start = t0 / rate
+            more = True
+            guard = 0
+            while more:
+                b = L.TimeBounds()
+                L.check(lib.b200_time_divide_set_bounds(C.byref(td), start, rate, ndat, C.byref(b)))
+                o = ot.set_bounds(start, rate, ndat)
+                got = dict(is_valid=bool(b.is_valid), new_division=bool(b.new_division), end_reached=bool(b.end_reached),
+                           in_next=bool(b.in_next), idat_start=b.idat_start, ndat=b.ndat, division=b.division)
+                assert got == o, (blk, got, o)
+                more = o["in_next"]
+                if o["is_valid"]:
+                    covered.append((t0 + o["idat_start"], t0 + o["idat_start"] + o["ndat"], o["division"], o["end_reached"]))
+                guard += 1
+                assert guard < 100
+            t0 += ndat
+        # contiguous, non-overlapping cover of [0, t0)
+        assert covered[0][0] == 0 and covered[-1][1] == t0
+        for a, b2 in zip(covered, covered[1:]):
+            assert a[1] == b2[0]
+        # a division's slices end within half a sample of its boundary
+        for s0, s1, div, end in covered:
+            assert s0 >= int(np.floor(div * Ldiv * rate - 0.51)) and s1 <= int(np.ceil((div + 1) * Ldiv * rate + 0.51))
+            if end:
+                assert abs(s1 - (div + 1) * Ldiv * rate) <= 0.5 + 1e-6
+
+
+def test_time_divide_half_sample_boundary_does_not_throw():
+    """A division boundary exactly half-way between samples makes the reference throw (TimeDivide.C:258-287);
+    the product starts the next division instead and still partitions the stream."""
+    import ctypes as C
+    from dspsr_b200 import _lib as L
+    lib = L.load()
+    rate, Ldiv = 1e6, 10.0 / 4096          # 2441.40625 samples per division: boundaries at x.5 occur
+    td = L.TimeDivide()
+    L.check(lib.b200_time_divide_init(C.byref(td), Ldiv))
+    rng = np.random.default_rng(9)
+    t0, prev_end = 0, 0
+    for blk in range(200):
+        ndat = int(rng.integers(1000, 30000))
+        more = True
+        while more:
+            b = L.TimeBounds()
+            L.check(lib.b200_time_divide_set_bounds(C.byref(td), t0 / rate, rate, ndat, C.byref(b)))
+            more = bool(b.in_next)
+            if b.is_valid:
+                assert t0 + b.idat_start == prev_end and b.ndat > 0
+                prev_end = t0 + b.idat_start + b.ndat
+        t0 += ndat
+    assert prev_end == t0
