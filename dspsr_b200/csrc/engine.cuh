@@ -16,7 +16,15 @@ struct FbSource {
   uint64_t step;            // SRC_F32: floats between parts; raw: SAMPLES between parts
   const float* d_lut;       // raw 8-bit formats: device copy of the 256-entry table
   cudaEvent_t* batch_ready; // optional: event i must have fired before the i-th internal batch reads its input
+  // two's-complement 8-bit tables that are exactly  lut[b] = RN(x * c), x = int8(b) + 0.5, c = conv_hi + conv_lo
+  // (checked entry by entry on the host): the fast path converts arithmetically instead of gathering
+  int conv_ok;
+  float conv_hi, conv_lo;
 };
+
+// Tries to express a 256-entry 8-bit table as the float evaluation fmaf(x, hi, x*lo); returns 1 and the
+// constants iff every entry is reproduced bit for bit.
+int lut_as_arithmetic(const float* lut256, float* hi, float* lo);
 
 // what the last kernel does with the dedispersed samples
 struct FbSink {

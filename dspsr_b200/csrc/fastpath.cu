@@ -14,11 +14,16 @@
 // fills the SM's registers and most of its shared memory: there is no second CTA to overlap with).
 // fb_run (filterbank.cu) dispatches here when the plan's sizes are instantiated below; every other
 // shape keeps the generic kernels.  B200_FAST=0 disables the dispatch (A/B measurements).
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
 #include "engine.cuh"
 #include "fft_c2.cuh"
+
+#ifndef B200_K1_NP
+#define B200_K1_NP 4
+#endif
 
 namespace b200 {
 
@@ -46,10 +51,13 @@ struct K1Args {
   unsigned Q, npol, nchan_in, Nc, nblk;
   uint64_t part0;
   unsigned dbg;
+  unsigned skew_ns, nsm;
+  int conv_ok;               // 8-bit table is RN(x*(conv_hi+conv_lo)): convert arithmetically, no gathers
+  float conv_hi, conv_lo;
 };
 
 template <int SRC, unsigned P, int NP>
-__global__ void __launch_bounds__(NP*(P / 16), 1) k1_c2(K1Args a) {
+__global__ void __launch_bounds__(NP*(P / 16), 512 / (NP * (P / 16))) k1_c2(K1Args a) {
   extern __shared__ float4 smem4[];
   __shared__ float s_lut[256];
   __shared__ float4 s_h[16 * NP];   // [e][pair] = (W_N^(n2a*T*e), W_N^(n2b*T*e))
@@ -65,6 +73,8 @@ __global__ void __launch_bounds__(NP*(P / 16), 1) k1_c2(K1Args a) {
     for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = a.lut[i];
     __syncthreads();
   }
+  // co-resident CTAs would otherwise run their phases in lock step: stagger every other one
+  if (a.skew_ns && (blockIdx.x / a.nsm) & 1) __nanosleep(a.skew_ns);
 
   // CASPSR: byte 8*(i/4) + 4*pol + i%4 (CASPSRUnpacker.C:141-187); columns n2, n2+1 = samples
   // 2*n2 .. 2*n2+3 = one 4-byte group of this polarisation
@@ -109,10 +119,27 @@ __global__ void __launch_bounds__(NP*(P / 16), 1) k1_c2(K1Args a) {
 #pragma unroll
       for (int e = 0; e < 16; e++) { va[e] = make_float2(float(threadIdx.x + e), 1.f); vb[e] = make_float2(2.f, float(e)); }
     } else if (SRC == SRC_CASPSR8) {
+      if (a.conv_ok) {
+        // byte -> float without the table: (b ^ 0x80) dropped into bits 8..15 of the float 32768 reads
+        // 32768 + 128 + int8(b); subtracting 32895.5 leaves x = int8(b) + 0.5 exactly, and fma(x, hi, x*lo)
+        // is the table entry bit for bit (verified for all 256 entries on the host, lut_as_arithmetic)
+        const float hi = a.conv_hi, lo = a.conv_lo;
+        auto cv = [&](unsigned word, unsigned sel) -> float {
+          const float x = __uint_as_float(__byte_perm(word, 0x47000000u, sel)) - 32895.5f;
+          return __fmaf_rn(x, hi, __fmul_rn(x, lo));
+        };
 #pragma unroll
-      for (int e = 0; e < 16; e++) {
-        va[e] = make_float2(s_lut[w[e] & 255u], s_lut[(w[e] >> 8) & 255u]);
-        vb[e] = make_float2(s_lut[(w[e] >> 16) & 255u], s_lut[w[e] >> 24]);
+        for (int e = 0; e < 16; e++) {
+          const unsigned x = w[e] ^ 0x80808080u;
+          va[e] = make_float2(cv(x, 0x7604), cv(x, 0x7614));
+          vb[e] = make_float2(cv(x, 0x7624), cv(x, 0x7634));
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+          va[e] = make_float2(s_lut[w[e] & 255u], s_lut[(w[e] >> 8) & 255u]);
+          vb[e] = make_float2(s_lut[(w[e] >> 16) & 255u], s_lut[w[e] >> 24]);
+        }
       }
     } else {
       const float2* f = reinterpret_cast<const float2*>(static_cast<const float*>(a.src) +
@@ -566,7 +593,7 @@ static bool fast_enabled() {
 }
 
 static constexpr unsigned FP_P = 2048, FP_Q = 1024, FP_F = 8192;
-static constexpr int FP_NP = 4;
+static constexpr int FP_NP = B200_K1_NP;
 static size_t k1_smem() { return size_t(FP_NP) * (c2::pair_slots<FP_P>() + 8 / FP_NP) * sizeof(float4); }
 static size_t k2_smem() { return size_t(512 / (FP_Q / 16)) * (c2::pair_slots<FP_Q>() | 1u) * sizeof(float4); }
 static size_t k3_smem() { return size_t(512 / (FP_F / 16)) * c2::pair_slots<FP_F>() * sizeof(float4); }
@@ -618,8 +645,12 @@ int fast_k1(b200_fb_plan* pl, const FbSource& src, uint64_t part0, unsigned nb) 
   a.Q = pl->Q; a.npol = pl->desc.npol; a.nchan_in = pl->desc.input_nchan; a.Nc = pl->Nc; a.part0 = part0;
   a.nblk = nb * pl->desc.input_nchan * pl->desc.npol;
   a.dbg = dbg_flags(1);
+  a.conv_ok = src.kind == SRC_CASPSR8 ? src.conv_ok : 0; a.conv_hi = src.conv_hi; a.conv_lo = src.conv_lo;
   const unsigned ntiles = pl->Q / (2 * FP_NP) * a.nblk;
-  dim3 grid(persistent_grid(ctx, ntiles));
+  const unsigned cta_per_sm = 512 / (FP_NP * (FP_P / 16));
+  a.nsm = (unsigned)ctx->sm_count;
+  a.skew_ns = cta_per_sm > 1 ? (getenv("B200_K1_SKEW") ? (unsigned)atoi(getenv("B200_K1_SKEW")) : 3000u) : 0u;
+  dim3 grid(std::min(ntiles, cta_per_sm * (unsigned)ctx->sm_count));
   dim3 block(FP_NP * (FP_P / 16));
   LaunchScope ls(ctx, KC_COLS_FWD);
   if (src.kind == SRC_F32) k1_c2<SRC_F32, FP_P, FP_NP><<<grid, block, k1_smem(), ctx->stream>>>(a);

@@ -938,7 +938,7 @@ int b200_fb_perform(b200_fb_plan* pl, const float* d_in, uint64_t in_span, float
                "time series planes must be 8-byte aligned with even spans");
   B200_REQUIRE(in_step % 2 == 0, "nsamp_step must be even for real input");
   FbSource src;
-  src.kind = SRC_F32; src.ptr = d_in; src.span = in_span; src.step = in_step; src.d_lut = nullptr; src.batch_ready = nullptr;
+  src.kind = SRC_F32; src.ptr = d_in; src.span = in_span; src.step = in_step; src.d_lut = nullptr; src.batch_ready = nullptr; src.conv_ok = 0;
   FbSink sink;
   memset(&sink, 0, sizeof(sink));
   sink.kind = EPI_VOLT; sink.volt = d_out; sink.volt_span = out_span; sink.volt_step = out_step;

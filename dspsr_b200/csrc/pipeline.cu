@@ -3,6 +3,8 @@
 // (Signal/Pulsar/LoadToFold1.C:117-599, SingleThread.C:405-431) when no operation sits between.
 #include <algorithm>
 #include <cstdlib>
+#include <cmath>
+#include <cstdint>
 #include <cstring>
 #include <vector>
 
@@ -32,6 +34,8 @@ struct b200_pipeline {
   float* d_unpacked;
   uint64_t unpacked_floats;
   unsigned nprod, dnpol, dndim;
+  int conv_ok;
+  float conv_hi, conv_lo;
   b200_twobit_desc twobit;
   // unfused tail (per-channel transforms too long for the fused epilogues): voltages, then detected series
   float* d_volt;
@@ -39,6 +43,34 @@ struct b200_pipeline {
   float* d_det;
   uint64_t det_floats;
 };
+
+namespace b200 {
+int lut_as_arithmetic(const float* lut, float* hi_out, float* lo_out) {
+  // every entry constrains the double constant c to an interval: RN_float(x*c) == lut[b]
+  double lo_c = -1e300, hi_c = 1e300;
+  for (int b = 0; b < 256; b++) {
+    const double x = double(int(int8_t(uint8_t(b)))) + 0.5;
+    const float v = lut[b];
+    const float up = std::nextafterf(v, INFINITY), dn = std::nextafterf(v, -INFINITY);
+    double a = (double(v) + double(dn)) * 0.5 / x, c = (double(v) + double(up)) * 0.5 / x;
+    if (a > c) std::swap(a, c);
+    lo_c = std::max(lo_c, a);
+    hi_c = std::min(hi_c, c);
+  }
+  if (!(lo_c < hi_c)) return 0;
+  const double c = 0.5 * (lo_c + hi_c);
+  const float hi = float(c), lo = float(c - double(hi));
+  for (int b = 0; b < 256; b++) {
+    const float x = float(int(int8_t(uint8_t(b)))) + 0.5f;
+    volatile float t = x * lo;                 // rounded to float, as FMUL does
+    const float r = std::fmaf(x, hi, t);
+    if (std::memcmp(&r, &lut[b], sizeof(float)) != 0) return 0;
+  }
+  *hi_out = hi;
+  *lo_out = lo;
+  return 1;
+}
+}  // namespace b200
 
 static unsigned fmt_resolution(int fmt) {
   switch (fmt) {
@@ -96,6 +128,8 @@ int b200_pipeline_create(b200_context* cctx, const b200_pipeline_desc* d, b200_p
     if (rc != B200_OK) { b200_pipeline_destroy(p); return rc; }
   }
   if (fmt == B200_FMT_CASPSR8 || fmt == B200_FMT_GENERIC8) {
+    static const bool arith = !(getenv("B200_LUT_ARITH") && atoi(getenv("B200_LUT_ARITH")) == 0);
+    p->conv_ok = arith ? lut_as_arithmetic(d->unpack.lut, &p->conv_hi, &p->conv_lo) : 0;
     cudaError_t e = cudaMalloc(&p->d_lut, 256 * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_lut, d->unpack.lut, 256 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -164,6 +198,7 @@ static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t inpu
     B200_REQUIRE(first_sample % 4 == 0, "CASPSR block must start on a 4-sample boundary");
     src.step = fb->nsamp_step;
     src.d_lut = p->d_lut;
+    src.conv_ok = p->conv_ok; src.conv_hi = p->conv_hi; src.conv_lo = p->conv_lo;
   } else if (fmt == B200_FMT_FLOAT32) {
     src.kind = SRC_F32;
     src.ptr = static_cast<const float*>(d_input) + first_sample * ndim;
