@@ -133,6 +133,12 @@ _pvp = C.POINTER(C.c_void_p)
 
 # name -> (restype, argtypes); every symbol include/b200dsp.h declares
 SIGNATURES = {
+    "b200_rescale_create": (_i, [_vp, C.c_uint, C.c_uint, C.c_uint64, _i, C.POINTER(C.c_void_p)]),
+    "b200_rescale_destroy": (_i, [_vp]),
+    "b200_rescale_transform": (_i, [_vp, _vp, C.c_uint64, C.c_uint64, _vp, C.c_uint64]),
+    "b200_rescale_get": (_i, [_vp, _vp, _vp]),
+    "b200_sigproc_digitize8": (_i, [_vp, _vp, C.c_uint64, C.c_uint, C.c_uint, C.c_uint64, C.c_float, C.c_float,
+                                    C.c_float, _i, _i, _vp]),
     "b200_time_divide_init": (_i, [C.POINTER(TimeDivide), C.c_double]),
     "b200_time_divide_set_bounds": (_i, [C.POINTER(TimeDivide), C.c_double, C.c_double, C.c_uint64,
                                          C.POINTER(TimeBounds)]),

@@ -344,3 +344,45 @@ def expand_segments_numpy(segs, nbin, ndat):
         phi = np.ldexp(a.astype(np.float64), s.scale_exp)
         bins[s.start:s.start + s.count] = (phi * float(nbin)).astype(np.uint32)
     return bins
+
+
+class Rescale:
+    """dsp::Rescale on the device (b200_rescale_*): per-channel offset/scale of a detected FPT series."""
+
+    def __init__(self, ctx, nchan, npol, interval_samples=0, constant=False):
+        self.ctx, self.nchan, self.npol = ctx, nchan, npol
+        h = C.c_void_p()
+        L.check(ctx.lib.b200_rescale_create(ctx.h, nchan, npol, interval_samples, int(constant), C.byref(h)))
+        self.h = h
+
+    def transform(self, x, out=None):
+        _need_cuda(x, "x")
+        out = torch.empty_like(x) if out is None else out
+        L.check(self.ctx.lib.b200_rescale_transform(self.h, _ptr(x), x.shape[2], x.shape[2], _ptr(out), out.shape[2]))
+        return out
+
+    def offset_scale(self):
+        o = np.zeros((self.nchan, self.npol), np.float32)
+        s = np.zeros((self.nchan, self.npol), np.float32)
+        L.check(self.ctx.lib.b200_rescale_get(self.h, o.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p)))
+        return o, s
+
+    def __del__(self):
+        try:
+            self.ctx.lib.b200_rescale_destroy(self.h)
+        except Exception:
+            pass
+
+
+def sigproc_digitize8(ctx, x, input_scale=1.0, scale_fac=1.0, rescale=True, bandwidth=-1.0, swap=False):
+    """dsp::SigProcDigitizer::pack (8 bit): detected FPT CUDA tensor [nchan, npol, ndat] -> uint8 [ndat, npol, nchan]."""
+    _need_cuda(x, "x")
+    nchan, npol, ndat = x.shape
+    digi_mean, digi_scale, xpol = np.float32(127.5), np.float32(np.float32(127.5) / np.float32(6)), np.float32(0)
+    if not rescale:
+        xpol, digi_mean, digi_scale = digi_mean, np.float32(0), np.float32(1)
+    digi_scale = np.float32(np.float64(digi_scale) / (np.float64(input_scale) * np.float64(scale_fac)))
+    out = torch.empty((ndat, npol, nchan), dtype=torch.uint8, device=x.device)
+    L.check(ctx.lib.b200_sigproc_digitize8(ctx.h, _ptr(x), ndat, nchan, npol, ndat, float(digi_scale), float(digi_mean),
+                                          float(xpol), int(bandwidth > 0), int(swap), _ptr(out)))
+    return out

@@ -310,6 +310,26 @@ int b200_polyco_parse(const char* text, b200_polyco* pc);
 double b200_polyco_phase(const b200_polyco* pc, int day, int sec, double frac, double* turns);
 double b200_polyco_frequency(const b200_polyco* pc, int day, int sec, double frac);
 
+/* digifil tail.  Replaces dsp::Rescale::transformation / compute_various
+ * (Signal/General/Rescale.C:165-412; FPT order, default mode: statistics over `interval_samples`, 0 = the
+ * length of the first block; offset = -mean, scale = 1/sqrt(variance) on the first call and at every interval
+ * end) and dsp::SigProcDigitizer::pack for 8 bits (Kernel/Formats/sigproc/SigProcDigitizer.C:80-160,244-300:
+ * TPF bytes clip(int(x*digi_scale + 127.5 + 0.5), 0, 255), digi_scale = (127.5/6)/(input_scale*scale_fac),
+ * channels re-ordered by ChannelSort :38-70). */
+typedef struct b200_rescale b200_rescale;
+int b200_rescale_create(b200_context* ctx, unsigned nchan, unsigned npol, uint64_t interval_samples, int constant,
+                        b200_rescale** out);
+int b200_rescale_destroy(b200_rescale* r);
+/* d_in / d_out: planes (ichan*npol+ipol)*span of ndat floats; in place allowed */
+int b200_rescale_transform(b200_rescale* r, const float* d_in, uint64_t in_span, uint64_t ndat, float* d_out,
+                           uint64_t out_span);
+/* current offset / scale, [nchan][npol] each (synchronises) */
+int b200_rescale_get(b200_rescale* r, float* h_offset, float* h_scale);
+/* d_out: ndat*npol*nchan bytes in TPF order; flip_band: input bandwidth > 0; swap_band: Observation::get_swap */
+int b200_sigproc_digitize8(b200_context* ctx, const float* d_in, uint64_t in_span, unsigned nchan, unsigned npol,
+                           uint64_t ndat, float digi_scale, float digi_mean, float xpol_offset, int flip_band,
+                           int swap_band, unsigned char* d_out);
+
 /* Sub-integration boundaries.  Replaces the arithmetic of dsp::TimeDivide::set_bounds / set_boundaries
  * (Signal/Pulsar/TimeDivide.C:132-330,349-425) for divisions given in seconds (dspsr -L), as driven by
  * dsp::Subint<Fold>::transformation (Signal/Pulsar/dsp/Subint.h:235-305): each input block is cut at the

@@ -471,3 +471,91 @@ class TimeDivide:
         self.current_end = input_start + idat_end / rate
         return dict(is_valid=True, new_division=new_division, end_reached=end_reached, in_next=in_next,
                     idat_start=idat_start, ndat=idat_end - idat_start, division=self.division)
+
+
+# ----------------------------------------------------------------------------- f1 (digifil tail)
+class Rescale:
+    """dsp::Rescale (Signal/General/Rescale.C:165-385, compute_various :387-412), FPT order, default mode
+    (not exact, no decay): statistics accumulate over `interval_samples` (0: the first block's length);
+    on the first call and at every interval end offset = -mean, scale = 1/sqrt(variance)."""
+
+    def __init__(self, interval_samples=0, constant=False):
+        self.interval_samples = interval_samples
+        self.constant = constant
+        self.nsample = 0
+        self.isample = 0
+        self.offset = self.scale = None
+
+    def transform(self, x):
+        """x: [nchan, npol, ndat] float32 -> same shape."""
+        x = np.ascontiguousarray(x, np.float32)
+        nchan, npol, ndat = x.shape
+        first_call = self.nsample == 0
+        if first_call:
+            self.nsample = self.interval_samples if self.interval_samples else ndat
+            self.tot = np.zeros((nchan, npol), np.float64)
+            self.totsq = np.zeros((nchan, npol), np.float64)
+            self.offset = np.zeros((nchan, npol), np.float32)
+            self.scale = np.ones((nchan, npol), np.float32)
+        out = np.empty_like(x)
+        start = 0
+        while True:
+            end = min(ndat, start + self.nsample - self.isample)
+            seg = x[:, :, start:end]
+            # sequential double accumulation of float samples and float squares (Rescale.C:258-262)
+            self.tot += np.cumsum(seg.astype(np.float64), axis=2)[:, :, -1] if end > start else 0.0
+            self.totsq += np.cumsum((seg * seg).astype(np.float64), axis=2)[:, :, -1] if end > start else 0.0
+            self.isample += end - start
+            if self.isample == self.nsample or first_call:
+                mean = self.tot / self.isample
+                var = self.totsq / self.isample - mean * mean
+                if not self.constant or first_call:
+                    self.offset = (-mean).astype(np.float32)
+                    with np.errstate(divide="ignore", invalid="ignore"):
+                        self.scale = np.where(var == 0.0, 1.0, 1.0 / np.sqrt(var)).astype(np.float32)
+                self.isample = 0
+                first_call = False
+                self.tot[:] = 0
+                self.totsq[:] = 0
+            out[:, :, start:end] = (seg + self.offset[:, :, None]) * self.scale[:, :, None]
+            start = end
+            if end >= ndat:
+                break
+        return out
+
+
+def sigproc_channel_sort(nchan, bandwidth, swap=False, nsub_swap=0):
+    """ChannelSort (Kernel/Formats/sigproc/SigProcDigitizer.C:38-70): output channel -> input channel."""
+    m = np.arange(nchan)
+    if nsub_swap > 1:
+        if swap:
+            m = (m + nchan // 2) % nchan
+        sub = nchan // nsub_swap
+        m = (m // sub) * sub + ((m % sub) + sub // 2) % sub
+    elif swap:
+        m = (m + nchan // 2) % nchan
+    if bandwidth > 0:
+        m = nchan - m - 1
+    return m
+
+
+def sigproc_digitize(x, nbit=8, input_scale=1.0, scale_fac=1.0, rescale=True, bandwidth=-1.0, swap=False):
+    """SigProcDigitizer::pack, FPT input, nbit 8 (SigProcDigitizer.C:80-160,244-300): TPF bytes
+    [ndat][npol][nchan] = clip(int(x*digi_scale + mean + 0.5), 0, 255)."""
+    assert nbit == 8
+    x = np.ascontiguousarray(x, np.float32)
+    nchan, npol, ndat = x.shape
+    digi_mean, digi_sigma = np.float32(127.5), np.float32(6)
+    digi_scale = np.float32(digi_mean / digi_sigma)
+    xpol_offset = np.float32(0)
+    if not rescale:
+        xpol_offset, digi_mean, digi_scale = digi_mean, np.float32(0), np.float32(1)
+    digi_scale = np.float32(np.float64(digi_scale) / (np.float64(input_scale) * np.float64(scale_fac)))
+    chan = sigproc_channel_sort(nchan, bandwidth, swap)
+    out = np.zeros((ndat, npol, nchan), np.uint8)
+    for ipol in range(npol):
+        mean = np.float32(digi_mean + (xpol_offset if ipol > 1 else 0))
+        v = (x[chan, ipol, :] * digi_scale + mean).astype(np.float64) + 0.5  # float product and sum, + 0.5 in double
+        r = np.clip(np.trunc(v), 0, 255).astype(np.uint8)
+        out[:, ipol, :] = r.T
+    return out

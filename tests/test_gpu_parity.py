@@ -505,3 +505,32 @@ def test_subint_folder_cuts_at_division_boundaries(ctx, oracle):
     assert ntot == total
     assert got[min(got)][3] and got[max(got)][3]          # first and last divisions are flagged partial
     assert not any(got[d][3] for d in sorted(got)[1:-1])
+
+
+# ------------------------------------------------------------------------------------ digifil tail (f1)
+def test_rescale_and_sigproc_digitizer(ctx, oracle):
+    """dsp::Rescale over several blocks (interval not a multiple of the block length) and the 8-bit SIGPROC
+    digitiser: floats within 2e-6 of the CPU restatement (the device sums in parallel), bytes identical except
+    where the value sits within 1e-3 of a rounding boundary; channel order flipped for positive bandwidth."""
+    torch, E = _torch(), _E()
+    rng = np.random.default_rng(91)
+    nchan, npol = 96, 1
+    blocks = [5000, 7000, 3000, 9000]
+    interval = 8192
+    gain = rng.uniform(0.5, 20.0, (nchan, npol, 1)).astype(np.float32)
+    base = rng.uniform(1.0, 50.0, (nchan, npol, 1)).astype(np.float32)
+    ro = oracle.Rescale(interval_samples=interval)
+    rg = E.Rescale(ctx, nchan, npol, interval_samples=interval)
+    for i, n in enumerate(blocks):
+        x = (rng.standard_normal((nchan, npol, n)).astype(np.float32) ** 2 * gain + base * (1 + 0.1 * i)).astype(np.float32)
+        want = ro.transform(x)
+        got = rg.transform(torch.from_numpy(x).cuda())
+        assert np.max(np.abs(got.cpu().numpy() - want)) <= 2e-5 * max(1.0, np.max(np.abs(want)))
+        o, s = rg.offset_scale()
+        assert np.allclose(o, ro.offset, rtol=1e-6) and np.allclose(s, ro.scale, rtol=1e-6)
+        for bw in (-64.0, 64.0):
+            bo = oracle.sigproc_digitize(want, bandwidth=bw)
+            bg = E.sigproc_digitize8(ctx, torch.from_numpy(want).cuda(), bandwidth=bw).cpu().numpy()
+            assert bg.shape == bo.shape == (n, npol, nchan)
+            assert np.array_equal(bg, bo)
+    assert 100 < bo.mean() < 155      # rescaled noise sits around 127.5

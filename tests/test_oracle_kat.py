@@ -321,3 +321,30 @@ def test_twobit_unpack_semantics(oracle):
     assert np.array_equal(win, want)
     # unit variance on average at nominal power
     assert np.var(out[0, 0, 2560:]) == pytest.approx(1.0, rel=0.15)
+
+
+# ----------------------------------------------------------------------------- f1 digifil tail
+def test_rescale_and_digitizer_known_answers(oracle):
+    """dsp::Rescale: the first block is normalised with its own statistics (zero mean, unit variance per
+    channel), later blocks with the statistics of the last completed interval; SigProcDigitizer 8 bit:
+    0 -> 127.5 + 0.5 truncated = 128, +-6 sigma span the byte range, positive bandwidth flips the channel order."""
+    rng = np.random.default_rng(4)
+    x = (rng.standard_normal((5, 1, 4000)) * np.arange(1, 6)[:, None, None] + 10).astype(np.float32)
+    r = oracle.Rescale()
+    y = r.transform(x)
+    assert np.allclose(y.mean(axis=2), 0, atol=1e-5) and np.allclose(y.var(axis=2), 1, rtol=1e-4)
+    y2 = r.transform(x + 1.0)                       # interval = first block: statistics of THIS block apply at its end
+    assert np.allclose(y2.mean(axis=2), 0, atol=1e-5)
+    r3 = oracle.Rescale(interval_samples=6000)
+    a = r3.transform(x)                             # first call: own statistics
+    b = r3.transform(x + 1.0)                       # samples 4000..5999 complete the interval inside this block
+    assert np.allclose(a.mean(axis=2), 0, atol=1e-5)
+    assert np.allclose(b[:, :, :2000].mean(axis=2), 1.0 / np.arange(1, 6)[:, None], rtol=0.1)   # old offsets still in force
+    z = np.zeros((4, 1, 3), np.float32)
+    z[:, 0, 1] = [6, -6, 3, -3]
+    z[:, 0, 2] = [100, -100, 0, 0]
+    d = oracle.sigproc_digitize(z, bandwidth=-1.0)
+    assert d.shape == (3, 1, 4) and np.array_equal(d[0, 0], [128, 128, 128, 128])
+    assert np.array_equal(d[1, 0], [255, 0, 191, 64]) and np.array_equal(d[2, 0], [255, 0, 128, 128])
+    assert np.array_equal(oracle.sigproc_digitize(z, bandwidth=1.0)[1, 0], [64, 191, 0, 255])
+    assert np.array_equal(oracle.sigproc_channel_sort(8, -1.0, swap=True), [4, 5, 6, 7, 0, 1, 2, 3])
