@@ -281,28 +281,43 @@ __global__ void __launch_bounds__(512, 1) k2_c2(K2Args a) {
         };
         const unsigned low = tile * G + g2;
         if (low != 0) {
+          // Each thread takes bins k2 = kk + T*it of the lower half (k2 < Q/2) TOGETHER with their partners
+          // Q-1-k2: the two float4 it reads hold (a[k2], b[k2]) and (a[Q-1-k2], b[Q-1-k2]), i.e. both
+          // members of two mirror pairs -- no half of a shared-memory read is wasted.
           const float2 rw = s_rowtw[g2];
-          const unsigned k0 = low + P * kk;
+          const unsigned k0 = low + P * kk;                 // bin of a[k2]
+          const unsigned k1b = low + P * (Q - 1 - kk);      // bin of a[Q-1-k2]
           const float4* sa = sg + c2::pad16(kk);
           const float4* sb = sg + c2::pad16(Q - 1 - kk);
-          const float2* t2 = a.tw2Q + kk;
-          const float2* Hk = H ? H + k0 : nullptr;
-          const float2* Hm = H ? H + (Nc - k0) : nullptr;
-          float2* Zk = Zblk + k0;
-          float2* Zm = Zblk + (Nc - k0);
-#pragma unroll 4
-          for (int it = 0; it < 16; it++) {
-            const float4 xa = sa[SSTEP * it];
-            const float4 xb = sb[-SSTEP * it];
-            const float2 w = cmul(rw, __ldg(t2 + it * int(T)));
-            float2 xk, xm;
-            split(make_float2(xa.x, xa.y), make_float2(xb.z, -xb.w), w, xk, xm);
+          const float2* t2a = a.tw2Q + kk;
+          const float2* t2b = a.tw2Q + (Q - 1 - kk);
+          const float2* HA = H ? H + k0 : nullptr;          // item A: X[k0 + ..], mirror X[Nc - k0 - ..]
+          const float2* HAm = H ? H + (Nc - k0) : nullptr;
+          const float2* HB = H ? H + k1b : nullptr;         // item B: X[k1b - ..], mirror X[Nc - k1b + ..]
+          const float2* HBm = H ? H + (Nc - k1b) : nullptr;
+          float2* ZA = Zblk + k0;
+          float2* ZAm = Zblk + (Nc - k0);
+          float2* ZB = Zblk + k1b;
+          float2* ZBm = Zblk + (Nc - k1b);
+#pragma unroll 2
+          for (int it = 0; it < 8; it++) {
+            const float4 u = sa[SSTEP * it];                // (a[k2], b[k2])
+            const float4 v = sb[-SSTEP * it];               // (a[Q-1-k2], b[Q-1-k2])
+            const float2 wA = cmul(rw, __ldg(t2a + it * int(T)));
+            const float2 wB = cmul(rw, __ldg(t2b - it * int(T)));
+            float2 xk, xm, yk, ym;
+            split(make_float2(u.x, u.y), make_float2(v.z, -v.w), wA, xk, xm);
+            split(make_float2(v.x, v.y), make_float2(u.z, -u.w), wB, yk, ym);
             if (H) {
-              xk = cmul(xk, __ldg(Hk + it * KSTEP));
-              xm = cmul(xm, __ldg(Hm - it * KSTEP));
+              xk = cmul(xk, __ldg(HA + it * KSTEP));
+              xm = cmul(xm, __ldg(HAm - it * KSTEP));
+              yk = cmul(yk, __ldg(HB - it * KSTEP));
+              ym = cmul(ym, __ldg(HBm + it * KSTEP));
             }
-            Zk[it * KSTEP] = xk;
-            Zm[-it * KSTEP] = xm;
+            ZA[it * KSTEP] = xk;
+            ZAm[-it * KSTEP] = xm;
+            ZB[-it * KSTEP] = yk;
+            ZBm[it * KSTEP] = ym;
           }
         } else {
           // rows 0 (sequence a) and P/2 (sequence b) mirror onto themselves
