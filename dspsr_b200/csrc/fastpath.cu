@@ -14,8 +14,11 @@
 // fills the SM's registers and most of its shared memory: there is no second CTA to overlap with).
 // fb_run (filterbank.cu) dispatches here when the plan's sizes are instantiated below; every other
 // shape keeps the generic kernels.  B200_FAST=0 disables the dispatch (A/B measurements).
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "engine.cuh"
@@ -54,11 +57,13 @@ struct K1Args {
   unsigned skew_ns, nsm;
   int conv_ok;               // 8-bit table is RN(x*(conv_hi+conv_lo)): convert arithmetically, no gathers
   float conv_hi, conv_lo;
+  int use_tma;               // store the tile with cp.async.bulk.tensor (tensor map over the A buffer)
 };
 
-template <int SRC, unsigned P, int NP>
-__global__ void __launch_bounds__(NP*(P / 16), 512 / (NP * (P / 16))) k1_c2(K1Args a) {
-  extern __shared__ float4 smem4[];
+template <int SRC, unsigned P, int NP, bool TMA>
+__global__ void __launch_bounds__(NP*(P / 16), 512 / (NP * (P / 16)))
+k1_c2(K1Args a, const __grid_constant__ CUtensorMap tmapA) {
+  extern __shared__ __align__(128) float4 smem4[];
   __shared__ float s_lut[256];
   __shared__ float4 s_h[16 * NP];   // [e][pair] = (W_N^(n2a*T*e), W_N^(n2b*T*e))
   constexpr unsigned T = P / 16;
@@ -151,6 +156,8 @@ __global__ void __launch_bounds__(NP*(P / 16), 512 / (NP * (P / 16))) k1_c2(K1Ar
         vb[e] = ldg_nc_f2(f + uint64_t(Q) * T * e + 1);
       }
     }
+    // the exchange buffer is scattered into again after this barrier: TMA must have finished reading it
+    if (TMA && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();     // the previous tile's readers of s_h and of the exchange buffer are done
     if (threadIdx.x < 16 * NP * 2) reinterpret_cast<float2*>(s_h)[threadIdx.x] = shv;
 
@@ -165,16 +172,46 @@ __global__ void __launch_bounds__(NP*(P / 16), 512 / (NP * (P / 16))) k1_c2(K1Ar
       for (int e = 0; e < 16; e++) w[e] = __ldg(reinterpret_cast<const unsigned*>(raw + 4ull * Q * T * e));
     }
 
-    float2* dst = a.dst + uint64_t(blk) * a.Nc + uint64_t(j) * Q + n2;
+    if (TMA) {
+      // TMA store: the exchange buffer is free once every thread has gathered its last-stage inputs, so the
+      // twiddled tile is laid out there as [k1][2*NP columns] (dense 16*NP-byte rows) and handed to the TMA
+      // unit as P/256 boxes of 256 rows -- 128-bit shared-memory stores (128 B per cycle) instead of global
+      // stores through the LSU data pipe (32 B per cycle), and no store instructions left to drain.
+      __syncthreads();
+      float4* stage = smem4 + j * NP + pair;                          // row k1 = j + e*T, NP float4 per row
 #pragma unroll
-    for (int e = 0; e < 16; e++) {
-      const float4 h = s_h[e * NP + pair];
-      const float2 xa = cmul(cmul(va[e], wa), make_float2(h.x, h.y));
-      const float2 xb = cmul(cmul(vb[e], wb), make_float2(h.z, h.w));
-      if (!(a.dbg & 2) || xa.x == 12345.678f)
-        *reinterpret_cast<float4*>(dst + uint64_t(Q) * T * e) = make_float4(xa.x, xa.y, xb.x, xb.y);
+      for (int e = 0; e < 16; e++) {
+        const float4 h = s_h[e * NP + pair];
+        const float2 xa = cmul(cmul(va[e], wa), make_float2(h.x, h.y));
+        const float2 xb = cmul(cmul(vb[e], wb), make_float2(h.z, h.w));
+        stage[e * int(T * NP)] = make_float4(xa.x, xa.y, xb.x, xb.y);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem4);
+#pragma unroll
+        for (unsigned box = 0; box < P / 256; box++) {
+          const int c0 = int(col0 * 2);                               // inner coordinate in floats
+          const int c1 = int(blk * P + box * 256);                    // row of the [nblk*P][2Q] float tensor
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                       :: "l"(&tmapA), "r"(c0), "r"(c1), "r"(smem_base + box * 256u * 16u * NP) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else {
+      float2* dst = a.dst + uint64_t(blk) * a.Nc + uint64_t(j) * Q + n2;
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        const float4 h = s_h[e * NP + pair];
+        const float2 xa = cmul(cmul(va[e], wa), make_float2(h.x, h.y));
+        const float2 xb = cmul(cmul(vb[e], wb), make_float2(h.z, h.w));
+        if (!(a.dbg & 2) || xa.x == 12345.678f)
+          *reinterpret_cast<float4*>(dst + uint64_t(Q) * T * e) = make_float4(xa.x, xa.y, xb.x, xb.y);
+      }
     }
   }
+  if (TMA && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -613,16 +650,34 @@ static size_t k1_smem() { return size_t(FP_NP) * (c2::pair_slots<FP_P>() + 8 / F
 static size_t k2_smem() { return size_t(512 / (FP_Q / 16)) * (c2::pair_slots<FP_Q>() | 1u) * sizeof(float4); }
 static size_t k3_smem() { return size_t(512 / (FP_F / 16)) * c2::pair_slots<FP_F>() * sizeof(float4); }
 
+static bool rows_fit_tma(const b200_fb_plan* pl);
+static int make_a_tensor_map(b200_fb_plan* pl, CUtensorMap* tm);
+
 int fast_plan_init(b200_fb_plan* pl) {
   pl->fast_k1 = pl->fast_k2 = pl->fast_k3 = false;
   pl->c2P = pl->c2Q = pl->c2F = nullptr;
+  pl->tmapA = nullptr;
+  pl->k1_tma = false;
   if (!fast_enabled() || pl->conv_path) return B200_OK;
   int rc = B200_OK;
   if (pl->P == FP_P && pl->Q >= 2 * FP_NP && pl->Q % (2 * FP_NP) == 0) {
     if ((rc = make_c2_table<FP_P>(&pl->c2P)) != B200_OK) return rc;
-    if ((rc = opt_in_smem(k1_c2<SRC_F32, FP_P, FP_NP>, k1_smem())) != B200_OK) return rc;
-    if ((rc = opt_in_smem(k1_c2<SRC_CASPSR8, FP_P, FP_NP>, k1_smem())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k1_c2<SRC_F32, FP_P, FP_NP, false>, k1_smem())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k1_c2<SRC_CASPSR8, FP_P, FP_NP, false>, k1_smem())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k1_c2<SRC_F32, FP_P, FP_NP, true>, k1_smem())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k1_c2<SRC_CASPSR8, FP_P, FP_NP, true>, k1_smem())) != B200_OK) return rc;
     pl->fast_k1 = true;
+    // TMA tensor store of the K1 tile: correct (parity-tested) but measured 3.6 % SLOWER than plain 128-bit
+    // global stores on B200 (0.278 vs 0.269 ms per 16 parts: two more CTA barriers, one issuing thread), so
+    // it is opt-in (B200_K1_TMA=1) until tiles shrink enough to double-buffer the staging area.
+    static const bool want_tma = getenv("B200_K1_TMA") && atoi(getenv("B200_K1_TMA")) == 1;
+    pl->k1_tma = false;
+    if (want_tma && rows_fit_tma(pl)) {
+      pl->tmapA = new CUtensorMap();
+      const int trc = make_a_tensor_map(pl, static_cast<CUtensorMap*>(pl->tmapA));
+      if (trc == B200_OK) pl->k1_tma = true;
+      if (getenv("B200_DEBUG")) fprintf(stderr, "[b200] K1 TMA store: tensor map rc=%d enabled=%d\n", trc, int(pl->k1_tma));
+    }
   }
   if (pl->Q == FP_Q && pl->P == FP_P) {
     if ((rc = make_c2_table<FP_Q>(&pl->c2Q)) != B200_OK) return rc;
@@ -642,10 +697,41 @@ int fast_plan_init(b200_fb_plan* pl) {
 }
 
 void fast_plan_free(b200_fb_plan* pl) {
+  if (pl->tmapA) delete static_cast<CUtensorMap*>(pl->tmapA);
+  pl->tmapA = nullptr;
   if (pl->c2P) cudaFree(pl->c2P);
   if (pl->c2Q) cudaFree(pl->c2Q);
   if (pl->c2F) cudaFree(pl->c2F);
   pl->c2P = pl->c2Q = pl->c2F = nullptr;
+}
+
+static bool rows_fit_tma(const b200_fb_plan* pl) {
+  return uint64_t(pl->batch) * pl->desc.input_nchan * pl->desc.npol * pl->P < (1ull << 31) && pl->P % 256 == 0;
+}
+
+// Tensor map of the A buffer seen as a 2-D float array [batch*nblk*P rows][2*Q floats], box = 256 rows x
+// 2*NP columns (16*NP bytes).  cuTensorMapEncodeTiled is fetched through the runtime so that the library
+// does not link against libcuda.
+static int make_a_tensor_map(b200_fb_plan* pl, CUtensorMap* tm) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return B200_ERR_UNSUPPORTED;
+  }
+  const uint64_t rows = uint64_t(pl->batch) * pl->desc.input_nchan * pl->desc.npol * pl->P;
+  const cuuint64_t gdim[2] = {cuuint64_t(pl->Q) * 2, rows};
+  const cuuint64_t gstride[1] = {cuuint64_t(pl->Q) * 2 * sizeof(float)};
+  const cuuint32_t box[2] = {4u * FP_NP, 256u};
+  const cuuint32_t estride[2] = {1u, 1u};
+  CUresult r = reinterpret_cast<encode_fn>(fn)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, pl->scratchA, gdim, gstride, box, estride,
+                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? B200_OK : B200_ERR_UNSUPPORTED;
 }
 
 static unsigned persistent_grid(Context* ctx, unsigned ntiles) {
@@ -667,9 +753,18 @@ int fast_k1(b200_fb_plan* pl, const FbSource& src, uint64_t part0, unsigned nb) 
   a.skew_ns = cta_per_sm > 1 ? (getenv("B200_K1_SKEW") ? (unsigned)atoi(getenv("B200_K1_SKEW")) : 3000u) : 0u;
   dim3 grid(std::min(ntiles, cta_per_sm * (unsigned)ctx->sm_count));
   dim3 block(FP_NP * (FP_P / 16));
+  a.use_tma = pl->k1_tma ? 1 : 0;
+  CUtensorMap tm;
+  if (pl->k1_tma) tm = *static_cast<CUtensorMap*>(pl->tmapA);
+  else memset(&tm, 0, sizeof(tm));
   LaunchScope ls(ctx, KC_COLS_FWD);
-  if (src.kind == SRC_F32) k1_c2<SRC_F32, FP_P, FP_NP><<<grid, block, k1_smem(), ctx->stream>>>(a);
-  else k1_c2<SRC_CASPSR8, FP_P, FP_NP><<<grid, block, k1_smem(), ctx->stream>>>(a);
+  if (pl->k1_tma) {
+    if (src.kind == SRC_F32) k1_c2<SRC_F32, FP_P, FP_NP, true><<<grid, block, k1_smem(), ctx->stream>>>(a, tm);
+    else k1_c2<SRC_CASPSR8, FP_P, FP_NP, true><<<grid, block, k1_smem(), ctx->stream>>>(a, tm);
+  } else {
+    if (src.kind == SRC_F32) k1_c2<SRC_F32, FP_P, FP_NP, false><<<grid, block, k1_smem(), ctx->stream>>>(a, tm);
+    else k1_c2<SRC_CASPSR8, FP_P, FP_NP, false><<<grid, block, k1_smem(), ctx->stream>>>(a, tm);
+  }
   return B200_OK;
 }
 
