@@ -105,7 +105,7 @@ class ClockSampler:
                     seen.add(name)
         return {"sm_mhz": float(np.median([x[0] for x in self.samples])), "sm_max_mhz": float(mx) if mx else None,
                 "reasons": sorted(seen), "power_w_max": max(x[2] for x in self.samples), "samples": len(self.samples),
-                "source": "NVML polled every 3 ms during the timed region"}
+                "source": "NVML polled every 3 ms during the two timed regions (device-resident and end-to-end)"}
 
     def _smi_once(self):
         try:
@@ -306,12 +306,12 @@ def run_ours(args):
         l0 = ctx.launches
         ms = timed(step_resident, args.steps)
         launches = ctx.launches - l0
-        clk = clocks.stop() if rank == 0 else None
 
-        # end to end: host bytes in, profile out
+        # end to end: host bytes in, profile out (the clock sampler keeps running: both timed regions count)
         for _ in range(2):
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
+        clk = clocks.stop() if rank == 0 else None
 
         # per-kernel device times (events around every launch, same stream), one extra pass
         pipe.zero()
