@@ -190,7 +190,7 @@ def run_reference(args):
     samples = args.steps * nblock * parts_per_block * S["step"]
     v = samples / dt / 1e6
     sample = "%d blocks x %d part(s) of cfg1 per step on %d threads" % (nblock, parts_per_block, ncores)
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -396,12 +396,27 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline_leg(S)
-    print(json.dumps(out))
+    emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's original stdout; everything else libraries print (NCCL's
+    version banner, torchrun chatter) was redirected to stderr in main()."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
