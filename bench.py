@@ -105,7 +105,7 @@ class ClockSampler:
                     seen.add(name)
         return {"sm_mhz": float(np.median([x[0] for x in self.samples])), "sm_max_mhz": float(mx) if mx else None,
                 "reasons": sorted(seen), "power_w_max": max(x[2] for x in self.samples), "samples": len(self.samples),
-                "source": "NVML polled every 3 ms during the two timed regions (device-resident and end-to-end)"}
+                "source": "NVML polled every 3 ms from the start of the device-resident timed region to the end of the per-kernel timing pass (same load throughout)"}
 
     def _smi_once(self):
         try:
@@ -311,7 +311,6 @@ def run_ours(args):
         for _ in range(2):
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
-        clk = clocks.stop() if rank == 0 else None
 
         # per-kernel device times (events around every launch, same stream), one extra pass
         pipe.zero()
@@ -322,6 +321,7 @@ def run_ours(args):
             pipe.execute(d_raw, parts, phi, pps, first_sample=0)
         kms, kn = ctx.read_timing()
         ctx.set_timing(False)
+        clk = clocks.stop() if rank == 0 else None
 
         # sanity: the folded result is real (hits add up)
         pipe.zero()

@@ -37,6 +37,7 @@ struct b200_pipeline {
   int conv_ok;
   float conv_hi, conv_lo;
   b200_twobit_desc twobit;
+  bool bins_preset;        // execute_host already issued set_bins for the coming block
   // unfused tail (per-channel transforms too long for the fused epilogues): voltages, then detected series
   float* d_volt;
   uint64_t volt_floats;
@@ -280,8 +281,11 @@ static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t inpu
   }
 
   if (p->desc.nbin) {
-    int rc = b200_fold_set_bins(p->fold, phi, pps, ndat_out, 0, nullptr);
-    if (rc != B200_OK) return rc;
+    if (!p->bins_preset) {
+      int rc = b200_fold_set_bins(p->fold, phi, pps, ndat_out, 0, nullptr);
+      if (rc != B200_OK) return rc;
+    }
+    p->bins_preset = false;
     sink.kind = EPI_FOLD;
     sink.bins = fold_bins(p->fold);
     sink.nbin = p->desc.nbin;
@@ -328,6 +332,15 @@ int b200_pipeline_execute_host(b200_pipeline* p, const void* h_input, uint64_t n
   // pass reads the whole block first
   const int fmt = p->desc.unpack.format;
   const bool chunked = (fmt == B200_FMT_CASPSR8);
+  // The bin plan uploads a few KiB of phase segments on the pipeline's stream.  Host-to-device copies of all
+  // streams share one copy engine and run in submission order, so that small copy must be SUBMITTED BEFORE
+  // the bulk chunks -- queued behind them it would hold the first kernels back until the whole block had
+  // arrived, serialising transfer and compute.
+  if (p->desc.nbin && chunked && !(fb->F > 8192 && !fb->conv_path)) {
+    int rc0 = b200_fold_set_bins(p->fold, phi, pps, npart * fb->nkeep, 0, nullptr);
+    if (rc0 != B200_OK) return rc0;
+    p->bins_preset = true;
+  }
   const uint64_t batch = fb->batch;
   const uint64_t nchunk = chunked ? (npart + batch - 1) / batch : 1;
   while (p->chunk_ready->size() < nchunk) {
