@@ -16,6 +16,7 @@ struct FbSource {
   uint64_t step;            // SRC_F32: floats between parts; raw: SAMPLES between parts
   const float* d_lut;       // raw 8-bit formats: device copy of the 256-entry table
   cudaEvent_t* batch_ready; // optional: event i must have fired before the i-th internal batch reads its input
+  unsigned batch_override;  // parts per internal batch for this call (0 = the plan's), <= the plan's batch
   // two's-complement 8-bit tables that are exactly  lut[b] = RN(x * c), x = int8(b) + 0.5, c = conv_hi + conv_lo
   // (checked entry by entry on the host): the fast path converts arithmetically instead of gathering
   int conv_ok;

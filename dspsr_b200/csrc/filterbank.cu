@@ -607,9 +607,10 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
     }
   }
 
-  for (uint64_t part0 = 0; part0 < npart; part0 += pl->batch) {
-    const unsigned nb = (unsigned)std::min<uint64_t>(pl->batch, npart - part0);
-    if (src.batch_ready) B200_CUDA(cudaStreamWaitEvent(st, src.batch_ready[part0 / pl->batch], 0));
+  const unsigned batch = (src.batch_override && src.batch_override < pl->batch) ? src.batch_override : pl->batch;
+  for (uint64_t part0 = 0; part0 < npart; part0 += batch) {
+    const unsigned nb = (unsigned)std::min<uint64_t>(batch, npart - part0);
+    if (src.batch_ready) B200_CUDA(cudaStreamWaitEvent(st, src.batch_ready[part0 / batch], 0));
     // ---- K1 ----
     const bool k1_fast = pl->fast_k1 && (src.kind == SRC_F32 || (src.step % 4 == 0 && (reinterpret_cast<uintptr_t>(src.ptr) & 3) == 0));
     if (k1_fast) {
@@ -938,7 +939,7 @@ int b200_fb_perform(b200_fb_plan* pl, const float* d_in, uint64_t in_span, float
                "time series planes must be 8-byte aligned with even spans");
   B200_REQUIRE(in_step % 2 == 0, "nsamp_step must be even for real input");
   FbSource src;
-  src.kind = SRC_F32; src.ptr = d_in; src.span = in_span; src.step = in_step; src.d_lut = nullptr; src.batch_ready = nullptr; src.conv_ok = 0;
+  src.kind = SRC_F32; src.ptr = d_in; src.span = in_span; src.step = in_step; src.d_lut = nullptr; src.batch_ready = nullptr; src.conv_ok = 0; src.batch_override = 0;
   FbSink sink;
   memset(&sink, 0, sizeof(sink));
   sink.kind = EPI_VOLT; sink.volt = d_out; sink.volt_span = out_span; sink.volt_step = out_step;

@@ -170,7 +170,7 @@ b200_fold* b200_pipeline_fold(b200_pipeline* p) { return p ? p->fold : nullptr; 
 
 static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t input_span, uint64_t first_sample,
                             uint64_t npart, double phi, double pps, float* d_detected, uint64_t detected_span,
-                            cudaEvent_t* batch_ready);
+                            cudaEvent_t* batch_ready, unsigned batch_override = 0);
 
 int b200_pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t input_span, uint64_t first_sample,
                           uint64_t npart, double phi, double pps, float* d_detected, uint64_t detected_span) {
@@ -179,7 +179,7 @@ int b200_pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t input_
 
 static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t input_span, uint64_t first_sample,
                             uint64_t npart, double phi, double pps, float* d_detected, uint64_t detected_span,
-                            cudaEvent_t* batch_ready) {
+                            cudaEvent_t* batch_ready, unsigned batch_override) {
   B200_REQUIRE(p && d_input, "b200_pipeline_execute: null argument");
   if (npart == 0) return B200_OK;
   Context* ctx = p->ctx;
@@ -191,6 +191,7 @@ static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t inpu
   FbSource src;
   memset(&src, 0, sizeof(src));
   src.batch_ready = batch_ready;
+  src.batch_override = batch_override;
   if (fmt == B200_FMT_CASPSR8) {
     B200_REQUIRE(first_sample % 2 == 0, "CASPSR input must start on an even sample");
     src.kind = SRC_CASPSR8;
@@ -341,7 +342,10 @@ int b200_pipeline_execute_host(b200_pipeline* p, const void* h_input, uint64_t n
     if (rc0 != B200_OK) return rc0;
     p->bins_preset = true;
   }
-  const uint64_t batch = fb->batch;
+  // host-fed blocks are PCIe-bound: chunks (= kernel batches) of 8 parts keep the pipeline fine-grained
+  // (first kernels start after 1/4 of a 32-part block instead of 1/2) at a small cost in kernel efficiency
+  static const unsigned host_batch = getenv("B200_HOST_BATCH") ? (unsigned)atoi(getenv("B200_HOST_BATCH")) : 8u;
+  const uint64_t batch = chunked ? std::max<uint64_t>(1, std::min<uint64_t>(fb->batch, host_batch)) : fb->batch;
   const uint64_t nchunk = chunked ? (npart + batch - 1) / batch : 1;
   while (p->chunk_ready->size() < nchunk) {
     cudaEvent_t e;
@@ -365,7 +369,8 @@ int b200_pipeline_execute_host(b200_pipeline* p, const void* h_input, uint64_t n
   }
   int rc;
   if (chunked) {
-    rc = pipeline_execute(p, p->d_stage[turn], 0, first_sample, npart, phi, pps, nullptr, 0, p->chunk_ready->data());
+    rc = pipeline_execute(p, p->d_stage[turn], 0, first_sample, npart, phi, pps, nullptr, 0, p->chunk_ready->data(),
+                          (unsigned)batch);
   } else {
     B200_CUDA(cudaStreamWaitEvent(ctx->stream, (*p->chunk_ready)[0], 0));
     rc = pipeline_execute(p, p->d_stage[turn], 0, first_sample, npart, phi, pps, nullptr, 0, nullptr);
