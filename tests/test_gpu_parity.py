@@ -534,3 +534,31 @@ def test_rescale_and_sigproc_digitizer(ctx, oracle):
             assert bg.shape == bo.shape == (n, npol, nchan)
             assert np.array_equal(bg, bo)
     assert 100 < bo.mean() < 155      # rescaled noise sits around 127.5
+
+
+# ------------------------------------------------------------------------------------ fast-path K3 epilogues
+@pytest.mark.parametrize("state,dndim,nbin", [("Stokes", 2, 128), ("Intensity", 1, 64), ("PPQQ", 1, 256),
+                                               ("Coherence", 1, 0), ("Stokes", 4, 0), ("Intensity", 1, 0)])
+def test_fast_k3_all_epilogues(ctx, oracle, state, dndim, nbin):
+    """freq_res 8192 with two polarisations takes the second-generation K3 (fastpath.cu) whatever the
+    forward factorisation: every detection state / layout, folded (run-time state variant) and unfolded."""
+    torch, E, L = _torch(), _E(), _L()
+    C, F, npos, nneg, npart = 4, 8192, 457, 459, 3
+    if nbin:
+        err = _pipeline_case(ctx, oracle, C, F, npos, nneg, npart, state, dndim, nbin, nblock=1)
+        assert err <= TOL, err
+        return
+    lut, _ = oracle.bittable8()
+    f = oracle.fb_sizes(1, 1, 2, C, F, npos, nneg)
+    ndat = (npart * f.nsamp_step + f.nsamp_overlap + 3) // 4 * 4
+    raw = synth.caspsr_bytes(ndat, seed=61)
+    H = np.exp(1j * np.random.default_rng(62).uniform(-np.pi, np.pi, (C, F))).astype(np.complex64)
+    x = oracle.unpack_caspsr(raw, ndat, lut)
+    volt = oracle.filterbank(f, x[:, :, : npart * f.nsamp_step + f.nsamp_overlap], H)
+    ref = oracle.detect(state, dndim, volt)
+    ud = E.make_unpack_desc(L.FMT_CASPSR8, 1, 2, 1, lut)
+    fd, keep = E.make_fb_desc(1, 1, 2, C, F, npos, nneg, H)
+    pipe = E.Pipeline(ctx, ud, fd, keep, state, dndim, 0)
+    det = pipe.execute(torch.from_numpy(raw).cuda(), npart, 0.0, 0.0, first_sample=0).cpu().numpy()
+    assert det.shape == ref.shape
+    assert np.array_equal(det, ref) or synth.relerr(det, ref) <= TOL
