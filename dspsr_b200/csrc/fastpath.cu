@@ -82,6 +82,8 @@ struct K1Args {
   int conv_ok;               // 8-bit table is RN(x*(conv_hi+conv_lo)): convert arithmetically, no gathers
   float conv_hi, conv_lo;
   int use_tma;               // store the tile with cp.async.bulk.tensor (tensor map over the A buffer)
+  int l2_prefetch;           // prefetch the next part's raw bytes into L2 as contiguous slices
+  unsigned overlap;          // nsamp_overlap (samples)
 };
 
 template <int SRC, unsigned P, int NP, bool TMA>
@@ -132,6 +134,28 @@ k1_c2(K1Args a, const __grid_constant__ CUtensorMap tmapA) {
     const unsigned ic = rest % a.nchan_in;
     const uint64_t part = a.part0 + rest / a.nchan_in;
     const unsigned blk = rest * a.npol + pol;
+
+    // L2 prefetch of the NEXT part's raw bytes.  This kernel reads the raw stream as 32-byte granules 4 KiB
+    // apart (one per FFT row), which DRAM serves at a quarter of its streaming rate; the same bytes requested
+    // ahead of time as one contiguous slice per tile stream into L2 at full speed, and the scattered reads
+    // of the next part then hit L2.  (tiles are ordered part-slowest: the 2*ncolblk tiles of a part each
+    // prefetch 1/(2*ncolblk) of the following part.)
+    if (SRC == SRC_CASPSR8 && a.l2_prefetch && threadIdx.x == 0 && a.nchan_in == 1) {
+      const unsigned slices = a.npol * ncolblk;
+      const unsigned slice = t % slices;
+      const uint64_t next_part = a.part0 + rest + 1;
+      if (rest + 1 < a.nblk / a.npol) {
+        // new bytes of the next part: [ (next_part*step + overlap) , ((next_part+1)*step + overlap) ) samples x npol bytes
+        const uint64_t lo = a.npol * (next_part * a.step + a.overlap), len = a.npol * a.step;
+        const uint64_t per = ((len / slices) + 15) & ~15ull;
+        const uint64_t off = slice * per;
+        if (off < len) {
+          const uint64_t n = min(per, len - off) & ~15ull;
+          const unsigned char* ptr = static_cast<const unsigned char*>(a.src) + ((lo + off) & ~15ull);
+          if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(ptr), "r"((unsigned)n) : "memory");
+        }
+      }
+    }
 
     // twiddles of this tile (loads in flight while the samples are converted)
     float2 shv = make_float2(1.f, 0.f);
@@ -784,6 +808,9 @@ int fast_k1(b200_fb_plan* pl, const FbSource& src, uint64_t part0, unsigned nb) 
   dim3 grid(std::min(ntiles, cta_per_sm * (unsigned)ctx->sm_count));
   dim3 block(FP_NP * (FP_P / 16));
   a.use_tma = pl->k1_tma ? 1 : 0;
+  static const bool l2pf = !(getenv("B200_K1_L2PF") && atoi(getenv("B200_K1_L2PF")) == 0);
+  a.l2_prefetch = l2pf ? 1 : 0;
+  a.overlap = pl->nsamp_overlap;
   CUtensorMap tm;
   if (pl->k1_tma) tm = *static_cast<CUtensorMap*>(pl->tmapA);
   else memset(&tm, 0, sizeof(tm));
