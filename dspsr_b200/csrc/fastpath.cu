@@ -698,11 +698,35 @@ static bool fast_enabled() {
   return on;
 }
 
-static constexpr unsigned FP_P = 2048, FP_Q = 1024, FP_F = 8192;
+static constexpr unsigned FP_P = 2048, FP_Q = 1024;
 static constexpr int FP_NP = B200_K1_NP;
 static size_t k1_smem() { return size_t(FP_NP) * (c2::pair_slots<FP_P>() + 8 / FP_NP) * sizeof(float4); }
 static size_t k2_smem() { return size_t(512 / (FP_Q / 16)) * (c2::pair_slots<FP_Q>() | 1u) * sizeof(float4); }
-static size_t k3_smem() { return size_t(512 / (FP_F / 16)) * c2::pair_slots<FP_F>() * sizeof(float4); }
+template <unsigned F> static size_t k3_smem() { return size_t(512 / (F / 16)) * c2::pair_slots<F>() * sizeof(float4); }
+
+template <unsigned F> static int k3_init(b200_fb_plan* pl) {
+  constexpr unsigned CB = 512 / (F / 16);
+  if (pl->nchan_out % CB != 0) return B200_OK;          // ragged channel count: generic kernels
+  int rc;
+  if ((rc = make_c2_table<F>(&pl->c2F)) != B200_OK) return rc;
+  if ((rc = opt_in_smem(k3_c2<F, EPI_VOLT, -1>, k3_smem<F>())) != B200_OK) return rc;
+  if ((rc = opt_in_smem(k3_c2<F, EPI_DETECT, -1>, k3_smem<F>())) != B200_OK) return rc;
+  if ((rc = opt_in_smem(k3_c2<F, EPI_FOLD, -1>, k3_smem<F>())) != B200_OK) return rc;
+  if ((rc = opt_in_smem(k3_c2<F, EPI_FOLD, B200_COHERENCE>, k3_smem<F>())) != B200_OK) return rc;
+  pl->fast_k3 = true;
+  return B200_OK;
+}
+
+template <unsigned F> static void k3_launch(b200_fb_plan* pl, const K3Args& a, const FbSink& sk, unsigned nb) {
+  Context* ctx = pl->ctx;
+  constexpr unsigned CB = 512 / (F / 16);
+  const unsigned ntiles = pl->nchan_out / CB * nb;
+  dim3 grid(ntiles < (unsigned)ctx->sm_count ? ntiles : (unsigned)ctx->sm_count);
+  if (sk.kind == EPI_VOLT) k3_c2<F, EPI_VOLT, -1><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a);
+  else if (sk.kind == EPI_DETECT) k3_c2<F, EPI_DETECT, -1><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a);
+  else if (sk.state == B200_COHERENCE) k3_c2<F, EPI_FOLD, B200_COHERENCE><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a);
+  else k3_c2<F, EPI_FOLD, -1><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a);
+}
 
 static bool rows_fit_tma(const b200_fb_plan* pl);
 static int make_a_tensor_map(b200_fb_plan* pl, CUtensorMap* tm);
@@ -739,13 +763,18 @@ int fast_plan_init(b200_fb_plan* pl) {
     if ((rc = opt_in_smem(k2_c2<FP_P, FP_Q, false>, k2_smem())) != B200_OK) return rc;
     pl->fast_k2 = true;
   }
-  if (pl->F == FP_F && pl->desc.npol == 2) {
-    if ((rc = make_c2_table<FP_F>(&pl->c2F)) != B200_OK) return rc;
-    if ((rc = opt_in_smem(k3_c2<FP_F, EPI_VOLT, -1>, k3_smem())) != B200_OK) return rc;
-    if ((rc = opt_in_smem(k3_c2<FP_F, EPI_DETECT, -1>, k3_smem())) != B200_OK) return rc;
-    if ((rc = opt_in_smem(k3_c2<FP_F, EPI_FOLD, -1>, k3_smem())) != B200_OK) return rc;
-    if ((rc = opt_in_smem(k3_c2<FP_F, EPI_FOLD, B200_COHERENCE>, k3_smem())) != B200_OK) return rc;
-    pl->fast_k3 = true;
+  // K3: any per-channel transform length the c2 core is planned for (CB = 8192/F channels per CTA)
+  if (pl->desc.npol == 2) {
+    switch (pl->F) {
+      case 8192: rc = k3_init<8192>(pl); break;
+      case 4096: rc = k3_init<4096>(pl); break;
+      case 2048: rc = k3_init<2048>(pl); break;
+      case 1024: rc = k3_init<1024>(pl); break;
+      case 512: rc = k3_init<512>(pl); break;
+      case 256: rc = k3_init<256>(pl); break;
+      default: break;
+    }
+    if (rc != B200_OK) return rc;
   }
   return B200_OK;
 }
@@ -850,14 +879,15 @@ int fast_k3(b200_fb_plan* pl, const FbSink& sk, uint64_t part0, unsigned nb) {
   a.nchan_out = pl->nchan_out; a.npart = nb;
   a.nfilt_pos = pl->desc.nfilt_pos; a.nkeep = pl->nkeep; a.part0 = part0; a.sink = sk;
   a.dbg = dbg_flags(3);
-  constexpr unsigned CB = 512 / (FP_F / 16);
-  const unsigned ntiles = pl->nchan_out / CB * nb;
-  dim3 grid(persistent_grid(ctx, ntiles));
   LaunchScope ls(ctx, KC_INV);
-  if (sk.kind == EPI_VOLT) k3_c2<FP_F, EPI_VOLT, -1><<<grid, 512, k3_smem(), ctx->stream>>>(a);
-  else if (sk.kind == EPI_DETECT) k3_c2<FP_F, EPI_DETECT, -1><<<grid, 512, k3_smem(), ctx->stream>>>(a);
-  else if (sk.state == B200_COHERENCE) k3_c2<FP_F, EPI_FOLD, B200_COHERENCE><<<grid, 512, k3_smem(), ctx->stream>>>(a);
-  else k3_c2<FP_F, EPI_FOLD, -1><<<grid, 512, k3_smem(), ctx->stream>>>(a);
+  switch (pl->F) {
+    case 8192: k3_launch<8192>(pl, a, sk, nb); break;
+    case 4096: k3_launch<4096>(pl, a, sk, nb); break;
+    case 2048: k3_launch<2048>(pl, a, sk, nb); break;
+    case 1024: k3_launch<1024>(pl, a, sk, nb); break;
+    case 512: k3_launch<512>(pl, a, sk, nb); break;
+    default: k3_launch<256>(pl, a, sk, nb); break;
+  }
   return B200_OK;
 }
 
