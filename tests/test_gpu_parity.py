@@ -562,3 +562,14 @@ def test_fast_k3_all_epilogues(ctx, oracle, state, dndim, nbin):
     det = pipe.execute(torch.from_numpy(raw).cuda(), npart, 0.0, 0.0, first_sample=0).cpu().numpy()
     assert det.shape == ref.shape
     assert np.array_equal(det, ref) or synth.relerr(det, ref) <= TOL
+
+
+@pytest.mark.parametrize("C,F,npos,nneg", [(32, 256, 20, 21), (16, 512, 30, 31), (8, 1024, 60, 61), (4, 2048, 98, 98),
+                                           (2, 4096, 200, 201)])
+def test_fast_k3_every_planned_length(ctx, oracle, C, F, npos, nneg):
+    """The second-generation K3 is instantiated for every per-channel length the c2 core plans (256 ... 8192),
+    with 8192/F channels sharing a CTA: fused fold (Coherence) and fused detection (Stokes, ndim 2) per length."""
+    err = _pipeline_case(ctx, oracle, C, F, npos, nneg, 3, "Coherence", 4, 128, nblock=2)
+    assert err <= TOL, err
+    err = _pipeline_case(ctx, oracle, C, F, npos, nneg, 2, "Stokes", 2, 64, nblock=1)
+    assert err <= TOL, err
