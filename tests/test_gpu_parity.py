@@ -573,3 +573,43 @@ def test_fast_k3_every_planned_length(ctx, oracle, C, F, npos, nneg):
     assert err <= TOL, err
     err = _pipeline_case(ctx, oracle, C, F, npos, nneg, 2, "Stokes", 2, 64, nblock=1)
     assert err <= TOL, err
+
+
+def test_pipeline_cfg1_bench_scale(ctx, oracle):
+    """BASELINE configs[0] at the size bench.py times (32 overlap-save parts = 119 M samples per polarisation,
+    239 MB of raw bytes, 4 blocks of 8 parts with their own fold phase): whole folded profile against the
+    oracle, exact hits, and the device-resident and host-fed paths agree bit for bit in hits and to 1e-6
+    in the profile (they differ only in internal batch size)."""
+    torch, E, L = _torch(), _E(), _L()
+    from dspsr_b200 import hostmath as HM
+    C, F, npos, nneg, nbin = 256, 8192, 457, 459, 1024
+    nblock, npart = 4, 8
+    lut, _ = oracle.bittable8()
+    f = oracle.fb_sizes(1, 1, 2, C, F, npos, nneg)
+    ndat = (nblock * npart * f.nsamp_step + f.nsamp_overlap + 3) // 4 * 4
+    raw = synth.caspsr_bytes(ndat, seed=99)
+    d, H = HM.dedispersion(1382.0, -400.0, 67.99, 1, C, True)
+    assert (d.ndat, d.impulse_pos, d.impulse_neg) == (F, npos, nneg)
+    pps = 7.18e-6
+    phis = [(0.1 + b * npart * f.nkeep * pps) % 1.0 for b in range(nblock)]
+    op = oracle.make_pipe(0, 1, 2, 1, lut, 0.0, f, None, H, "Coherence", 4, nbin)
+    ref, ref_hits = oracle.pipe_run(op, raw, nblock, npart, phis, [pps] * nblock, nthread=4)
+    ud = E.make_unpack_desc(L.FMT_CASPSR8, 1, 2, 1, lut)
+    fd, keep = E.make_fb_desc(1, 1, 2, C, F, npos, nneg, H)
+    pipe = E.Pipeline(ctx, ud, fd, keep, "Coherence", 4, nbin)
+    d_raw = torch.from_numpy(raw).cuda()
+    for b in range(nblock):
+        pipe.execute(d_raw, npart, phis[b], pps, first_sample=b * npart * f.nsamp_step)
+    prof, hits, ntot = pipe.synch()
+    assert np.array_equal(hits, ref_hits) and ntot == nblock * npart * f.nkeep == hits.sum()
+    err = synth.relerr(prof, ref)
+    assert err <= TOL, err
+    # host-fed path (chunked copies, smaller internal batches)
+    pipe.zero()
+    for b in range(nblock):
+        lo = b * npart * f.nsamp_step * 2
+        nbytes = (npart * f.nsamp_step + f.nsamp_overlap) * 2
+        pipe.execute_host(raw[lo: lo + nbytes], npart, phis[b], pps, 0)
+    prof2, hits2, ntot2 = pipe.synch()
+    assert np.array_equal(hits2, hits) and ntot2 == ntot
+    assert synth.relerr(prof2, prof) <= 1e-6
