@@ -17,6 +17,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -445,6 +446,7 @@ __global__ void __launch_bounds__(512, 1) k2_c2(K2Args a) {
 struct K3Args {
   const float2* Z;
   const float2* tw;        // c2 stage tables of F
+  const float2* tw32;      // stage tables of the 32.16.16 plan (F = 8192): [15][32] then [15][512]
   unsigned C, Nc, nchan_in, nchan_out, npart;
   unsigned nfilt_pos, nkeep;
   uint64_t part0;
@@ -466,8 +468,13 @@ __device__ __forceinline__ void detect4(int state, float2 p, float2 q, float* r)
   }
 }
 
-template <unsigned F, int EPI, int STATE>
+// R32 (F = 8192 only): the transform is planned 32.16.16 instead of 16.16.16.2 -- the first, twiddle-free
+// stage runs as ONE 32-point butterfly per thread (threads 0-255 polarisation p, 256-511 polarisation q),
+// which removes one of the three shared-memory exchanges and two of the six barriers.  The exchanges are
+// 64-bit (one float2 array per polarisation, one pad slot after every 32: stride 33 is conflict free).
+template <unsigned F, int EPI, int STATE, bool R32 = false>
 __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
+  static_assert(!R32 || F == 8192, "the 32.16.16 plan is built for 8192 points");
   extern __shared__ float4 smem4[];
   constexpr unsigned T = F / 16;
   constexpr unsigned CB = 512 / T;                     // channels per CTA
@@ -486,6 +493,17 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
     const unsigned ch = (tt % tiles_per_part) * CB + cb, partl = tt / tiles_per_part;
     const unsigned ic = ch / a.C, csub = ch % a.C;
     const uint64_t blk = (uint64_t(partl) * a.nchan_in + ic) * 2;
+    if (R32) {
+      // stage-0 ownership: thread (pol, j0) holds x_pol[j0 + 256 e], e < 32, in vp[0..15], vq[0..15]
+      const unsigned pol = threadIdx.x >> 8, j0 = threadIdx.x & 255u;
+      const float2* src = a.Z + (blk + pol) * a.Nc + uint64_t(csub) * F + j0;
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        vp[e] = B200_LDS1(src + e * 256);
+        vq[e] = B200_LDS1(src + (16 + e) * 256);
+      }
+      return;
+    }
     const float2* srcp = a.Z + blk * a.Nc + uint64_t(csub) * F + j;
     const float2* srcq = srcp + a.Nc;
 #pragma unroll
@@ -503,7 +521,50 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
     const uint64_t part = a.part0 + partl;
     const unsigned tn = t + gridDim.x;
 
-    if (!(a.dbg & 1)) c2::fft_pair<F, true>(vp, vq, j, sm, a.tw, CtaSync());
+    if (R32) {
+      float2* arrP = reinterpret_cast<float2*>(smem4);
+      float2* arrQ = arrP + (F + F / 32);
+      {
+        // stage 0: 32-point inverse butterfly of one polarisation, outputs r of butterfly j0 at 32 j0 + r
+        const unsigned pol = threadIdx.x >> 8, j0 = threadIdx.x & 255u;
+        float2 u[32];
+#pragma unroll
+        for (int e = 0; e < 16; e++) { u[e] = vp[e]; u[16 + e] = vq[e]; }
+        dft32<true>(u);
+        float2* dst = (pol ? arrQ : arrP) + 33u * j0;           // pad33(32 j0 + r) = 33 j0 + r
+#pragma unroll
+        for (int r = 0; r < 32; r++) dst[r] = u[r];
+      }
+      const unsigned k1 = j & 31u;
+      float2 w[15];
+#pragma unroll
+      for (int r = 1; r < 16; r++) w[r - 1] = tw_get<true>(a.tw32, (unsigned)(r - 1) * 32u + k1);
+      __syncthreads();
+      const unsigned pj = j + (j >> 5);                           // pad33(j + 512 e) = pj + 528 e
+#pragma unroll
+      for (int e = 0; e < 16; e++) { vp[e] = arrP[pj + 528u * e]; vq[e] = arrQ[pj + 528u * e]; }
+      // stage 1: radix 16, sub-transform length 32
+#pragma unroll
+      for (int r = 1; r < 16; r++) { vp[r] = cmul(vp[r], w[r - 1]); vq[r] = cmul(vq[r], w[r - 1]); }
+      dft16<true>(vp);
+      dft16<true>(vq);
+      __syncthreads();
+      {
+        const unsigned base1 = (j - k1) / 2u * 33u + k1;          // pad33((j-k)*16 + k + 32 r) = base1 + 33 r
+#pragma unroll
+        for (int r = 0; r < 16; r++) { arrP[base1 + 33u * r] = vp[r]; arrQ[base1 + 33u * r] = vq[r]; }
+      }
+#pragma unroll
+      for (int r = 1; r < 16; r++) w[r - 1] = tw_get<true>(a.tw32 + 15 * 32, (unsigned)(r - 1) * 512u + j);
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < 16; e++) { vp[e] = arrP[pj + 528u * e]; vq[e] = arrQ[pj + 528u * e]; }
+      // stage 2: radix 16, sub-transform length 512: register e ends up holding element j + 512 e
+#pragma unroll
+      for (int r = 1; r < 16; r++) { vp[r] = cmul(vp[r], w[r - 1]); vq[r] = cmul(vq[r], w[r - 1]); }
+      dft16<true>(vp);
+      dft16<true>(vq);
+    } else if (!(a.dbg & 1)) c2::fft_pair<F, true>(vp, vq, j, sm, a.tw, CtaSync());
     if ((a.dbg & 2) && vp[3].x != 12345.678f) {
       __syncthreads();
       if (tn < ntiles) issue_loads(tn);
@@ -704,11 +765,36 @@ static size_t k1_smem() { return size_t(FP_NP) * (c2::pair_slots<FP_P>() + 8 / F
 static size_t k2_smem() { return size_t(512 / (FP_Q / 16)) * (c2::pair_slots<FP_Q>() | 1u) * sizeof(float4); }
 template <unsigned F> static size_t k3_smem() { return size_t(512 / (F / 16)) * c2::pair_slots<F>() * sizeof(float4); }
 
+static bool k3_r32_enabled() {
+  static const bool on = !(getenv("B200_K3_R32") && atoi(getenv("B200_K3_R32")) == 0);
+  return on;
+}
+
 template <unsigned F> static int k3_init(b200_fb_plan* pl) {
   constexpr unsigned CB = 512 / (F / 16);
   if (pl->nchan_out % CB != 0) return B200_OK;          // ragged channel count: generic kernels
   int rc;
   if ((rc = make_c2_table<F>(&pl->c2F)) != B200_OK) return rc;
+  if (F == 8192) {
+    // stage tables of the 32.16.16 plan: W_512^(r k), k < 32, then W_8192^(r k), k < 512 (forward sign)
+    std::vector<float2> h(15 * 32 + 15 * 512);
+    for (int r = 1; r < 16; r++) {
+      for (unsigned k = 0; k < 32; k++) {
+        const double ang = -2.0 * 3.14159265358979323846 * r * k / 512.0;
+        h[(r - 1) * 32 + k] = make_float2(float(cos(ang)), float(sin(ang)));
+      }
+      for (unsigned k = 0; k < 512; k++) {
+        const double ang = -2.0 * 3.14159265358979323846 * r * k / 8192.0;
+        h[15 * 32 + (r - 1) * 512 + k] = make_float2(float(cos(ang)), float(sin(ang)));
+      }
+    }
+    B200_CUDA(cudaMalloc(&pl->c2F32, sizeof(float2) * h.size()));
+    B200_CUDA(cudaMemcpy(pl->c2F32, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice));
+    if ((rc = opt_in_smem(k3_c2<8192, EPI_VOLT, -1, true>, k3_smem<8192>())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k3_c2<8192, EPI_DETECT, -1, true>, k3_smem<8192>())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k3_c2<8192, EPI_FOLD, -1, true>, k3_smem<8192>())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k3_c2<8192, EPI_FOLD, B200_COHERENCE, true>, k3_smem<8192>())) != B200_OK) return rc;
+  }
   if ((rc = opt_in_smem(k3_c2<F, EPI_VOLT, -1>, k3_smem<F>())) != B200_OK) return rc;
   if ((rc = opt_in_smem(k3_c2<F, EPI_DETECT, -1>, k3_smem<F>())) != B200_OK) return rc;
   if ((rc = opt_in_smem(k3_c2<F, EPI_FOLD, -1>, k3_smem<F>())) != B200_OK) return rc;
@@ -722,6 +808,15 @@ template <unsigned F> static void k3_launch(b200_fb_plan* pl, const K3Args& a, c
   constexpr unsigned CB = 512 / (F / 16);
   const unsigned ntiles = pl->nchan_out / CB * nb;
   dim3 grid(ntiles < (unsigned)ctx->sm_count ? ntiles : (unsigned)ctx->sm_count);
+  if constexpr (F == 8192) {
+    if (k3_r32_enabled() && pl->c2F32) {
+      if (sk.kind == EPI_VOLT) k3_c2<8192, EPI_VOLT, -1, true><<<grid, 512, k3_smem<8192>(), ctx->stream>>>(a);
+      else if (sk.kind == EPI_DETECT) k3_c2<8192, EPI_DETECT, -1, true><<<grid, 512, k3_smem<8192>(), ctx->stream>>>(a);
+      else if (sk.state == B200_COHERENCE) k3_c2<8192, EPI_FOLD, B200_COHERENCE, true><<<grid, 512, k3_smem<8192>(), ctx->stream>>>(a);
+      else k3_c2<8192, EPI_FOLD, -1, true><<<grid, 512, k3_smem<8192>(), ctx->stream>>>(a);
+      return;
+    }
+  }
   if (sk.kind == EPI_VOLT) k3_c2<F, EPI_VOLT, -1><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a);
   else if (sk.kind == EPI_DETECT) k3_c2<F, EPI_DETECT, -1><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a);
   else if (sk.state == B200_COHERENCE) k3_c2<F, EPI_FOLD, B200_COHERENCE><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a);
@@ -734,6 +829,7 @@ static int make_a_tensor_map(b200_fb_plan* pl, CUtensorMap* tm);
 int fast_plan_init(b200_fb_plan* pl) {
   pl->fast_k1 = pl->fast_k2 = pl->fast_k3 = false;
   pl->c2P = pl->c2Q = pl->c2F = nullptr;
+  pl->c2F32 = nullptr;
   pl->tmapA = nullptr;
   pl->k1_tma = false;
   if (!fast_enabled() || pl->conv_path) return B200_OK;
@@ -785,7 +881,9 @@ void fast_plan_free(b200_fb_plan* pl) {
   if (pl->c2P) cudaFree(pl->c2P);
   if (pl->c2Q) cudaFree(pl->c2Q);
   if (pl->c2F) cudaFree(pl->c2F);
+  if (pl->c2F32) cudaFree(pl->c2F32);
   pl->c2P = pl->c2Q = pl->c2F = nullptr;
+  pl->c2F32 = nullptr;
 }
 
 static bool rows_fit_tma(const b200_fb_plan* pl) {
@@ -875,7 +973,7 @@ int fast_k2(b200_fb_plan* pl, unsigned nb) {
 int fast_k3(b200_fb_plan* pl, const FbSink& sk, uint64_t part0, unsigned nb) {
   Context* ctx = pl->ctx;
   K3Args a;
-  a.Z = pl->scratchZ; a.tw = pl->c2F; a.C = pl->C; a.Nc = pl->Nc; a.nchan_in = pl->desc.input_nchan;
+  a.Z = pl->scratchZ; a.tw = pl->c2F; a.tw32 = pl->c2F32; a.C = pl->C; a.Nc = pl->Nc; a.nchan_in = pl->desc.input_nchan;
   a.nchan_out = pl->nchan_out; a.npart = nb;
   a.nfilt_pos = pl->desc.nfilt_pos; a.nkeep = pl->nkeep; a.part0 = part0; a.sink = sk;
   a.dbg = dbg_flags(3);
