@@ -272,6 +272,7 @@ struct K2Args {
   const float2* H;
   const float2* tw;        // c2 stage tables of Q
   const float2* tw2Q;      // exp(-2 pi i m / (2Q))
+  const float2* tw32;      // 32.32 plan: W_1024^(s j), s = 1..7, then W_1024^(8 m j), m = 1..3  ([10][32])
   const float2* b2lo;
   const float2* b2hi;
   unsigned Nc, npol, nchan_in, nblk;
@@ -436,6 +437,178 @@ __global__ void __launch_bounds__(512, 1) k2_c2(K2Args a) {
       }
     }
     __syncthreads();       // phase-2 readers are done before the next tile's first scatter
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2, 32.32 plan (Q = 1024): every row is transformed by ONE WARP -- 32 threads x 32 points, two
+// radix-32 stages -- so the single exchange of the transform is warp-local (__syncwarp, stride-33 padded
+// 64-bit accesses) and the whole tile needs just two CTA barriers (before and after the split phase)
+// instead of six.  Rows a / b of a mirror pair sit in separate float2 arrays (a at sequence 2g, b at 2g+1);
+// the array stride 1057 = 1 mod 8 makes the lane-by-pair walk of the split phase conflict free.
+// ------------------------------------------------------------------------------------------
+template <unsigned P, bool SPLIT>
+__global__ void __launch_bounds__(512, 1) k2_r32(K2Args a) {
+  extern __shared__ float4 smem4[];
+  float2* sm2 = reinterpret_cast<float2*>(smem4);
+  constexpr unsigned Q = 1024, G = 8, RSQ = 1057;
+  constexpr unsigned TPB = SPLIT ? (P / 2) / G : P / (2 * G);
+  __shared__ float2 s_rowtw[G + 1];
+  const unsigned seq = threadIdx.x >> 5, j = threadIdx.x & 31u;
+  const unsigned g = seq >> 1, which = seq & 1u;
+  const unsigned Nc = a.Nc;
+  const unsigned ntiles = TPB * a.nblk;
+
+  float2 v[32];
+  auto issue_loads = [&](unsigned tt) {
+    const unsigned tile = tt % TPB, blk = tt / TPB;
+    unsigned row;
+    if (SPLIT) {
+      const unsigned low = tile * G + g;
+      row = which ? (low == 0 ? P / 2 : P - low) : low;
+    } else {
+      row = tile * 2 * G + 2 * g + which;
+    }
+    const float2* src = a.A + uint64_t(blk) * Nc + uint64_t(row) * Q + j;
+#pragma unroll
+    for (int e = 0; e < 32; e++) v[e] = B200_LDS1(src + 32 * e);
+  };
+
+  unsigned t = blockIdx.x;
+  if (t < ntiles) issue_loads(t);
+  for (; t < ntiles; t += gridDim.x) {
+    const unsigned tile = t % TPB, blk = t / TPB;
+    const unsigned ic = (blk / a.npol) % a.nchan_in;
+    if (SPLIT && threadIdx.x <= G) {
+      const unsigned r = threadIdx.x < G ? tile * G + threadIdx.x : P / 2;
+      s_rowtw[threadIdx.x] = big_twiddle<false>(a.b2lo, a.b2hi, r);
+    }
+    float2* sq = sm2 + seq * RSQ;
+    // stage 0: thread j holds x[j + 32 e]; outputs r of butterfly j go to 32 j + r -> slot 33 j + r
+    dft32<false>(v);
+#pragma unroll
+    for (int r = 0; r < 32; r++) sq[33u * j + r] = v[r];
+    // stage-1 twiddles W_1024^(r j), r = 8 m + s, from W^(s j) (s = 1..7) and W^(8 m j) (m = 1..3)
+    float2 ws[8], wm[4];
+#pragma unroll
+    for (int s1 = 1; s1 < 8; s1++) ws[s1] = __ldg(a.tw32 + (s1 - 1) * 32 + j);
+#pragma unroll
+    for (int m = 1; m < 4; m++) wm[m] = __ldg(a.tw32 + (6 + m) * 32 + j);
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 32; e++) v[e] = sq[j + 33u * e];          // x1[j + 32 e] at slot j + 33 e
+#pragma unroll
+    for (int r = 1; r < 32; r++) {
+      const int s1 = r & 7, m = r >> 3;
+      const float2 w = m == 0 ? ws[s1] : (s1 == 0 ? wm[m] : cmul(wm[m], ws[s1]));
+      v[r] = cmul(v[r], w);
+    }
+    dft32<false>(v);                                               // register e = X[j + 32 e]
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 32; e++) sq[j + 33u * e] = v[e];           // natural order, slot k2 + (k2 >> 5)
+    __syncthreads();
+
+    // the rows of the next tile stream in while this tile is split, multiplied and stored
+    if (t + gridDim.x < ntiles) issue_loads(t + gridDim.x);
+
+    {
+      const float2* H = a.H ? a.H + uint64_t(ic) * Nc : nullptr;
+      float2* Zblk = a.Z + uint64_t(blk) * Nc;
+      const unsigned g2 = threadIdx.x % G, kk = threadIdx.x / G;   // kk < 64
+      const float2* SA = sm2 + (2 * g2) * RSQ;                     // row a of pair g2
+      const float2* SB = SA + RSQ;                                 // row b
+      auto p33 = [](unsigned i) { return i + (i >> 5); };
+      constexpr int SSTEP = 66;                                    // slot advance of 64 elements
+      constexpr int KSTEP = 64 * P;                                // bin advance of 64 elements
+
+      if (!SPLIT) {
+        const unsigned k0 = tile * 2 * G + 2 * g2 + P * kk;
+        const unsigned s0 = p33(kk);
+#pragma unroll 4
+        for (int it = 0; it < 16; it++) {
+          float2 xa = SA[s0 + SSTEP * it], xb = SB[s0 + SSTEP * it];
+          const unsigned k = k0 + it * KSTEP;
+          if (H) {
+            const float4 h = __ldg(reinterpret_cast<const float4*>(H + k));
+            xa = cmul(xa, make_float2(h.x, h.y));
+            xb = cmul(xb, make_float2(h.z, h.w));
+          }
+          B200_ZST(reinterpret_cast<float4*>(Zblk + k), make_float4(xa.x, xa.y, xb.x, xb.y));
+        }
+      } else {
+        auto split = [&](float2 zk, float2 zmc, float2 w, float2& xk, float2& xm) {
+          const float2 e = make_float2(0.5f * (zk.x + zmc.x), 0.5f * (zk.y + zmc.y));
+          const float2 d = make_float2(0.5f * (zk.x - zmc.x), 0.5f * (zk.y - zmc.y));
+          const float2 tt = cmul(make_float2(d.y, -d.x), w);
+          xk = cadd(e, tt);
+          xm = cconj(csub(e, tt));
+        };
+        const unsigned low = tile * G + g2;
+        if (low != 0) {
+          const float2 rw = s_rowtw[g2];
+          const unsigned k0 = low + P * kk;                 // bin of a[k2]
+          const unsigned k1b = low + P * (Q - 1 - kk);      // bin of a[Q-1-k2]
+          const unsigned sa = p33(kk), sb = p33(Q - 1 - kk);
+          const float2* t2a = a.tw2Q + kk;
+          const float2* t2b = a.tw2Q + (Q - 1 - kk);
+          const float2* HA = H ? H + k0 : nullptr;
+          const float2* HAm = H ? H + (Nc - k0) : nullptr;
+          const float2* HB = H ? H + k1b : nullptr;
+          const float2* HBm = H ? H + (Nc - k1b) : nullptr;
+          float2* ZA = Zblk + k0;
+          float2* ZAm = Zblk + (Nc - k0);
+          float2* ZB = Zblk + k1b;
+          float2* ZBm = Zblk + (Nc - k1b);
+#pragma unroll 2
+          for (int it = 0; it < 8; it++) {
+            const float2 ua = SA[sa + SSTEP * it], ub = SB[sa + SSTEP * it];      // a[k2], b[k2]
+            const float2 va2 = SA[sb - SSTEP * it], vb2 = SB[sb - SSTEP * it];    // a[Q-1-k2], b[Q-1-k2]
+            const float2 wA = cmul(rw, __ldg(t2a + it * 64));
+            const float2 wB = cmul(rw, __ldg(t2b - it * 64));
+            float2 xk, xm, yk, ym;
+            split(ua, make_float2(vb2.x, -vb2.y), wA, xk, xm);
+            split(va2, make_float2(ub.x, -ub.y), wB, yk, ym);
+            if (H) {
+              xk = cmul(xk, __ldg(HA + it * KSTEP));
+              xm = cmul(xm, __ldg(HAm - it * KSTEP));
+              yk = cmul(yk, __ldg(HB - it * KSTEP));
+              ym = cmul(ym, __ldg(HBm + it * KSTEP));
+            }
+            B200_ZST(ZA + it * KSTEP, xk);
+            B200_ZST(ZAm - it * KSTEP, xm);
+            B200_ZST(ZB - it * KSTEP, yk);
+            B200_ZST(ZBm + it * KSTEP, ym);
+          }
+        } else {
+          // rows 0 (array a) and P/2 (array b) mirror onto themselves
+          const float2 rwh = s_rowtw[G];
+          for (unsigned it = 0; it < 16; it++) {
+            const unsigned k2 = kk + it * 64;
+            if (k2 <= Q / 2) {
+              const unsigned km2 = (Q - k2) % Q;
+              const float2 xa = SA[p33(k2)], xm2 = SA[p33(km2)];
+              float2 xk, xm;
+              split(xa, make_float2(xm2.x, -xm2.y), __ldg(a.tw2Q + k2), xk, xm);
+              const unsigned k = P * k2, km = (Nc - k) & (Nc - 1);
+              if (H) { xk = cmul(xk, __ldg(H + k)); xm = cmul(xm, __ldg(H + km)); }
+              Zblk[k] = xk;
+              if (km2 != k2) Zblk[km] = xm;
+            }
+            if (k2 < Q / 2) {
+              const float2 xb = SB[p33(k2)], xm2 = SB[p33(Q - 1 - k2)];
+              float2 xk, xm;
+              split(xb, make_float2(xm2.x, -xm2.y), cmul(rwh, __ldg(a.tw2Q + k2)), xk, xm);
+              const unsigned k = P / 2 + P * k2, km = Nc - k;
+              if (H) { xk = cmul(xk, __ldg(H + k)); xm = cmul(xm, __ldg(H + km)); }
+              Zblk[k] = xk;
+              Zblk[km] = xm;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();       // split-phase readers are done before the next tile's first scatter
   }
 }
 
@@ -763,6 +936,7 @@ static constexpr unsigned FP_P = 2048, FP_Q = 1024;
 static constexpr int FP_NP = B200_K1_NP;
 static size_t k1_smem() { return size_t(FP_NP) * (c2::pair_slots<FP_P>() + 8 / FP_NP) * sizeof(float4); }
 static size_t k2_smem() { return size_t(512 / (FP_Q / 16)) * (c2::pair_slots<FP_Q>() | 1u) * sizeof(float4); }
+static size_t k2r32_smem() { return size_t(16) * 1057 * sizeof(float2); }
 template <unsigned F> static size_t k3_smem() { return size_t(512 / (F / 16)) * c2::pair_slots<F>() * sizeof(float4); }
 
 static bool k3_r32_enabled() {
@@ -830,6 +1004,7 @@ int fast_plan_init(b200_fb_plan* pl) {
   pl->fast_k1 = pl->fast_k2 = pl->fast_k3 = false;
   pl->c2P = pl->c2Q = pl->c2F = nullptr;
   pl->c2F32 = nullptr;
+  pl->c2Q32 = nullptr;
   pl->tmapA = nullptr;
   pl->k1_tma = false;
   if (!fast_enabled() || pl->conv_path) return B200_OK;
@@ -857,6 +1032,23 @@ int fast_plan_init(b200_fb_plan* pl) {
     if ((rc = make_c2_table<FP_Q>(&pl->c2Q)) != B200_OK) return rc;
     if ((rc = opt_in_smem(k2_c2<FP_P, FP_Q, true>, k2_smem())) != B200_OK) return rc;
     if ((rc = opt_in_smem(k2_c2<FP_P, FP_Q, false>, k2_smem())) != B200_OK) return rc;
+    {
+      std::vector<float2> h(10 * 32);
+      for (unsigned jj = 0; jj < 32; jj++) {
+        for (int s1 = 1; s1 < 8; s1++) {
+          const double ang = -2.0 * 3.14159265358979323846 * s1 * jj / 1024.0;
+          h[(s1 - 1) * 32 + jj] = make_float2(float(cos(ang)), float(sin(ang)));
+        }
+        for (int m = 1; m < 4; m++) {
+          const double ang = -2.0 * 3.14159265358979323846 * 8 * m * jj / 1024.0;
+          h[(6 + m) * 32 + jj] = make_float2(float(cos(ang)), float(sin(ang)));
+        }
+      }
+      B200_CUDA(cudaMalloc(&pl->c2Q32, sizeof(float2) * h.size()));
+      B200_CUDA(cudaMemcpy(pl->c2Q32, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice));
+      if ((rc = opt_in_smem(k2_r32<FP_P, true>, k2r32_smem())) != B200_OK) return rc;
+      if ((rc = opt_in_smem(k2_r32<FP_P, false>, k2r32_smem())) != B200_OK) return rc;
+    }
     pl->fast_k2 = true;
   }
   // K3: any per-channel transform length the c2 core is planned for (CB = 8192/F channels per CTA)
@@ -882,6 +1074,8 @@ void fast_plan_free(b200_fb_plan* pl) {
   if (pl->c2Q) cudaFree(pl->c2Q);
   if (pl->c2F) cudaFree(pl->c2F);
   if (pl->c2F32) cudaFree(pl->c2F32);
+  if (pl->c2Q32) cudaFree(pl->c2Q32);
+  pl->c2Q32 = nullptr;
   pl->c2P = pl->c2Q = pl->c2F = nullptr;
   pl->c2F32 = nullptr;
 }
@@ -965,6 +1159,13 @@ int fast_k2(b200_fb_plan* pl, unsigned nb) {
   const unsigned ntiles = (split ? (FP_P / 2) / G : FP_P / (2 * G)) * a.nblk;
   dim3 grid(persistent_grid(ctx, ntiles));
   LaunchScope ls(ctx, KC_ROWS);
+  static const bool r32 = !(getenv("B200_K2_R32") && atoi(getenv("B200_K2_R32")) == 0);
+  a.tw32 = pl->c2Q32;
+  if (r32 && pl->c2Q32) {
+    if (split) k2_r32<FP_P, true><<<grid, 512, k2r32_smem(), ctx->stream>>>(a);
+    else k2_r32<FP_P, false><<<grid, 512, k2r32_smem(), ctx->stream>>>(a);
+    return B200_OK;
+  }
   if (split) k2_c2<FP_P, FP_Q, true><<<grid, 512, k2_smem(), ctx->stream>>>(a);
   else k2_c2<FP_P, FP_Q, false><<<grid, 512, k2_smem(), ctx->stream>>>(a);
   return B200_OK;
