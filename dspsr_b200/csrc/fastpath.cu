@@ -825,7 +825,6 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
     {
       const unsigned nbin = a.sink.nbin;
       float* prof0 = a.sink.profile + uint64_t(ch0) * nbin * nprod;
-      const unsigned lane = threadIdx.x & 31u;
       auto red_add = [&](unsigned key, const float* acc) {
         // key = c*nbin + bin; profile layout per channel [npol'][nbin][ndim']
         const unsigned c = key / nbin, bin = key - c * nbin;
@@ -879,27 +878,11 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
             }
           }
         }
-#ifndef B200_FOLD_WARP_REDUCE
         // every walk adds its trailing run straight to the profile: about nine walks share a (channel, bin)
-        // address, which RED.ADD.F32 absorbs easily -- measured 6 % faster for K3 than first combining equal
-        // keys across the warp with 25 shuffles per thread (B200_FOLD_WARP_REDUCE keeps that variant)
+        // address, which RED.ADD.F32 absorbs easily -- 6 % faster for K3 than first combining equal keys
+        // across the warp with shuffles, and valid for any pulse period (a shuffle scan over "equal
+        // neighbouring keys" double counts once the period is shorter than a warp's span of samples)
         if (key != 0xffffffffu) red_add(key, acc);
-#else
-        // segmented sum of the trailing runs across the warp
-#pragma unroll
-        for (unsigned off = 1; off < 32; off <<= 1) {
-          const unsigned okey = __shfl_down_sync(0xffffffffu, key, off);
-          float o[4];
-#pragma unroll
-          for (int pr = 0; pr < 4; pr++) o[pr] = __shfl_down_sync(0xffffffffu, acc[pr], off);
-          if (lane + off < 32 && okey == key) {
-#pragma unroll
-            for (int pr = 0; pr < 4; pr++) acc[pr] += o[pr];
-          }
-        }
-        const unsigned pkey = __shfl_up_sync(0xffffffffu, key, 1);
-        if (key != 0xffffffffu && (lane == 0 || pkey != key)) red_add(key, acc);
-#endif
       }
     }
     __syncthreads();       // fold readers are done before the next tile's first scatter

@@ -390,11 +390,8 @@ __global__ void __launch_bounds__((FCT && EPT == 32) ? 512 : 1024, 1) k_chan_inv
 
   // EPI_FOLD.  Every thread walks L consecutive samples of one channel, summing sequentially while
   // the phase bin is unchanged (the order of the reference's per-bin +=, Fold.C:844-852).  A run
-  // that ends inside the chunk is added to the profile at once; the chunk's last run is first
-  // combined across the warp -- neighbouring lanes hold neighbouring chunks, so equal (channel,bin)
-  // keys are contiguous and a shuffle-based segmented sum leaves one add per key and warp.  All
-  // adds go to the global profile with RED.ADD.F32 (no shared-memory float atomics: those compile
-  // to CAS loops).
+  // is added to the global profile with RED.ADD.F32 as soon as it ends (no shared-memory float
+  // atomics: those compile to CAS loops).
   {
     const unsigned nbin = a.sink.nbin;
     const unsigned nthreads = blockDim.x;
@@ -405,7 +402,6 @@ __global__ void __launch_bounds__((FCT && EPT == 32) ? 512 : 1024, 1) k_chan_inv
     const unsigned total = a.CB * nchunk;
     const unsigned* plan = a.sink.bins + partl * uint64_t(nkeep);
     float* prof0 = a.sink.profile + uint64_t(ch0) * nbin * nprod;
-    const unsigned lane = threadIdx.x & 31u;
     auto red_add = [&](unsigned key, const float* acc) {
       // key = c*nbin + bin; profile layout per channel [npol'][nbin][ndim']
       const unsigned c = key / nbin, bin = key - c * nbin;
@@ -458,20 +454,11 @@ __global__ void __launch_bounds__((FCT && EPT == 32) ? 512 : 1024, 1) k_chan_inv
           }
         }
       }
-      // segmented sum of the trailing runs across the warp
-#pragma unroll
-      for (unsigned off = 1; off < 32; off <<= 1) {
-        const unsigned okey = __shfl_down_sync(0xffffffffu, key, off);
-        float o[4];
-#pragma unroll
-        for (int pr = 0; pr < 4; pr++) o[pr] = __shfl_down_sync(0xffffffffu, acc[pr], off);
-        if (lane + off < 32 && okey == key) {
-#pragma unroll
-          for (int pr = 0; pr < 4; pr++) acc[pr] += o[pr];
-        }
-      }
-      const unsigned pkey = __shfl_up_sync(0xffffffffu, key, 1);
-      if (key != 0xffffffffu && (lane == 0 || pkey != key)) red_add(key, acc);
+      // every walk adds its trailing run straight to the profile.  (An earlier version first combined equal
+      // keys of neighbouring lanes with a shuffle scan; that is only valid while the keys of a warp are
+      // contiguous, i.e. while the pulse period is longer than the samples a warp walks -- a randomised
+      // sweep with 8-bin, few-sample periods caught it double counting.  Direct RED is also faster.)
+      if (key != 0xffffffffu) red_add(key, acc);
     }
   }
 }

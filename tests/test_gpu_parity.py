@@ -613,3 +613,13 @@ def test_pipeline_cfg1_bench_scale(ctx, oracle):
     prof2, hits2, ntot2 = pipe.synch()
     assert np.array_equal(hits2, hits) and ntot2 == ntot
     assert synth.relerr(prof2, prof) <= 1e-6
+
+
+@pytest.mark.parametrize("C,F,npos,nneg,nbin,period", [(128, 128, 19, 9, 8, 23.0), (16, 256, 20, 21, 8, 11.0),
+                                                       (4, 8192, 457, 459, 16, 37.0), (64, 32, 0, 4, 4, 5.5)])
+def test_pipeline_fold_short_period(ctx, oracle, C, F, npos, nneg, nbin, period):
+    """Pulse periods of a few samples with few bins: the phase wraps many times inside the samples one warp
+    walks, so equal (channel, bin) keys are NOT contiguous across lanes (regression test for a shuffle-scan
+    reduction that double counted in this regime; found by scratch/fuzz_gpu.py)."""
+    err = _pipeline_case(ctx, oracle, C, F, npos, nneg, 2, "Stokes", 2, nbin, nblock=2, pps=1.0 / period)
+    assert err <= TOL, err
