@@ -283,6 +283,7 @@ struct K2Args {
   const float2* b2hi;
   unsigned Nc, npol, nchan_in, nblk;
   unsigned dbg;
+  int z_tiled;             // write Z in the tile-major order (k2_r32 + the 32.16.16 K3 only)
 };
 
 template <unsigned P, unsigned Q, bool SPLIT>
@@ -562,10 +563,28 @@ __global__ void __launch_bounds__(512, 1) k2_r32(K2Args a) {
           const float2* HAm = H ? H + (Nc - k0) : nullptr;
           const float2* HB = H ? H + k1b : nullptr;
           const float2* HBm = H ? H + (Nc - k1b) : nullptr;
-          float2* ZA = Zblk + k0;
-          float2* ZAm = Zblk + (Nc - k0);
-          float2* ZB = Zblk + k1b;
-          float2* ZBm = Zblk + (Nc - k1b);
+          // natural order: bin k at Z[k].  Tiled order (a.z_tiled): element k2 of row r sits at
+          // Z'[tile][side][k2][g] (r < P/2: tile = r/8, side 0, g = r%8; r > P/2: m = P-r, tile = m/8, side 1,
+          // g = m%8), so a K2 tile writes two contiguous 64 KiB regions -- sequential stores -- and a warp's
+          // store covers 256 contiguous bytes.  K3 (32.16.16 plan) reads the same layout.
+          float2 *ZA, *ZAm, *ZB, *ZBm;
+          int zstep, zstepm;
+          if (a.z_tiled) {
+            float2* zt = Zblk + uint64_t(tile) * (2 * Q * G) + g2;
+            ZA = zt + kk * G;                        // (side 0, k2)
+            ZBm = zt + Q * G + kk * G;               // (side 1, k2)
+            ZB = zt + (Q - 1 - kk) * G;              // (side 0, Q-1-k2)
+            ZAm = zt + Q * G + (Q - 1 - kk) * G;     // (side 1, Q-1-k2)
+            zstep = 64 * G;
+            zstepm = 64 * G;
+          } else {
+            ZA = Zblk + k0;
+            ZAm = Zblk + (Nc - k0);
+            ZB = Zblk + k1b;
+            ZBm = Zblk + (Nc - k1b);
+            zstep = KSTEP;
+            zstepm = KSTEP;
+          }
 #pragma unroll 2
           for (int it = 0; it < 8; it++) {
             const float2 ua = SA[sa + SSTEP * it], ub = SB[sa + SSTEP * it];      // a[k2], b[k2]
@@ -581,10 +600,10 @@ __global__ void __launch_bounds__(512, 1) k2_r32(K2Args a) {
               yk = cmul(yk, __ldg(HB - it * KSTEP));
               ym = cmul(ym, __ldg(HBm + it * KSTEP));
             }
-            B200_ZST(ZA + it * KSTEP, xk);
-            B200_ZST(ZAm - it * KSTEP, xm);
-            B200_ZST(ZB - it * KSTEP, yk);
-            B200_ZST(ZBm + it * KSTEP, ym);
+            B200_ZST(ZA + it * zstep, xk);
+            B200_ZST(ZAm - it * zstepm, xm);
+            B200_ZST(ZB - it * zstep, yk);
+            B200_ZST(ZBm + it * zstepm, ym);
           }
         } else {
           // rows 0 (array a) and P/2 (array b) mirror onto themselves
@@ -598,8 +617,13 @@ __global__ void __launch_bounds__(512, 1) k2_r32(K2Args a) {
               split(xa, make_float2(xm2.x, -xm2.y), __ldg(a.tw2Q + k2), xk, xm);
               const unsigned k = P * k2, km = (Nc - k) & (Nc - 1);
               if (H) { xk = cmul(xk, __ldg(H + k)); xm = cmul(xm, __ldg(H + km)); }
-              Zblk[k] = xk;
-              if (km2 != k2) Zblk[km] = xm;
+              if (a.z_tiled) {                       // row 0: tile 0, side 0, g 0
+                Zblk[k2 * G] = xk;
+                if (km2 != k2) Zblk[km2 * G] = xm;
+              } else {
+                Zblk[k] = xk;
+                if (km2 != k2) Zblk[km] = xm;
+              }
             }
             if (k2 < Q / 2) {
               const float2 xb = SB[p33(k2)], xm2 = SB[p33(Q - 1 - k2)];
@@ -607,8 +631,13 @@ __global__ void __launch_bounds__(512, 1) k2_r32(K2Args a) {
               split(xb, make_float2(xm2.x, -xm2.y), cmul(rwh, __ldg(a.tw2Q + k2)), xk, xm);
               const unsigned k = P / 2 + P * k2, km = Nc - k;
               if (H) { xk = cmul(xk, __ldg(H + k)); xm = cmul(xm, __ldg(H + km)); }
-              Zblk[k] = xk;
-              Zblk[km] = xm;
+              if (a.z_tiled) {                       // row P/2: tile 0, side 1, g 0
+                Zblk[Q * G + k2 * G] = xk;
+                Zblk[Q * G + (Q - 1 - k2) * G] = xm;
+              } else {
+                Zblk[k] = xk;
+                Zblk[km] = xm;
+              }
             }
           }
         }
@@ -631,6 +660,7 @@ struct K3Args {
   uint64_t part0;
   FbSink sink;
   unsigned dbg;
+  int z_tiled;             // Z is in K2's tile-major order (see k2_r32)
 };
 
 // STATE >= 0: detection state fixed at compile time (no per-sample branches); -1: run-time state
@@ -675,6 +705,26 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
     if (R32) {
       // stage-0 ownership: thread (pol, j0) holds x_pol[j0 + 256 e], e < 32, in vp[0..15], vq[0..15]
       const unsigned pol = threadIdx.x >> 8, j0 = threadIdx.x & 255u;
+      if (a.z_tiled) {
+        // bin f = j0 + 256 e of channel csub is element k2 = 4 csub + (e >> 3) of row r = j0 + 256 (e & 7)
+        const float2* zb = a.Z + (blk + pol) * a.Nc + 32u * csub;     // + k2 * 8 with k2 = 4 csub + q
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const unsigned r = j0 + 256u * i;
+          unsigned tile, side, g8;
+          if (r < 1024u) { tile = r >> 3; side = 0; g8 = r & 7u; }
+          else if (r == 1024u) { tile = 0; side = 1; g8 = 0; }
+          else { const unsigned m = 2048u - r; tile = m >> 3; side = 1; g8 = m & 7u; }
+          const float2* p = zb + (uint64_t(tile) * 2 + side) * 8192u + g8;
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const int e = i + 8 * q;
+            const float2 x = B200_LDS1(p + 8 * q);
+            if (e < 16) vp[e] = x; else vq[e - 16] = x;
+          }
+        }
+        return;
+      }
       const float2* src = a.Z + (blk + pol) * a.Nc + uint64_t(csub) * F + j0;
 #pragma unroll
       for (int e = 0; e < 16; e++) {
@@ -986,6 +1036,15 @@ template <unsigned F> static void k3_launch(b200_fb_plan* pl, const K3Args& a, c
   else k3_c2<F, EPI_FOLD, -1><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a);
 }
 
+// Z travels from K2 to K3 in K2's tile-major order when both ends are the kernels that implement it:
+// k2_r32 with the real-input split and the 32.16.16 K3, i.e. P = 2048, Q = 1024, freq_res = 8192 (cfg1).
+static bool z_tiled(const b200_fb_plan* pl) {
+  static const bool want = !(getenv("B200_Z_TILED") && atoi(getenv("B200_Z_TILED")) == 0);
+  static const bool k2r32 = !(getenv("B200_K2_R32") && atoi(getenv("B200_K2_R32")) == 0);
+  return want && k2r32 && k3_r32_enabled() && pl->fast_k2 && pl->fast_k3 && pl->c2Q32 && pl->c2F32 &&
+         pl->desc.input_real && pl->P == 2048 && pl->Q == 1024 && pl->F == 8192;
+}
+
 static bool rows_fit_tma(const b200_fb_plan* pl);
 static int make_a_tensor_map(b200_fb_plan* pl, CUtensorMap* tm);
 
@@ -1150,6 +1209,7 @@ int fast_k2(b200_fb_plan* pl, unsigned nb) {
   LaunchScope ls(ctx, KC_ROWS);
   static const bool r32 = !(getenv("B200_K2_R32") && atoi(getenv("B200_K2_R32")) == 0);
   a.tw32 = pl->c2Q32;
+  a.z_tiled = z_tiled(pl) ? 1 : 0;
   if (r32 && pl->c2Q32) {
     if (split) k2_r32<FP_P, true><<<grid, 512, k2r32_smem(), ctx->stream>>>(a);
     else k2_r32<FP_P, false><<<grid, 512, k2r32_smem(), ctx->stream>>>(a);
@@ -1167,6 +1227,7 @@ int fast_k3(b200_fb_plan* pl, const FbSink& sk, uint64_t part0, unsigned nb) {
   a.nchan_out = pl->nchan_out; a.npart = nb;
   a.nfilt_pos = pl->desc.nfilt_pos; a.nkeep = pl->nkeep; a.part0 = part0; a.sink = sk;
   a.dbg = dbg_flags(3);
+  a.z_tiled = z_tiled(pl) ? 1 : 0;
   LaunchScope ls(ctx, KC_INV);
   switch (pl->F) {
     case 8192: k3_launch<8192>(pl, a, sk, nb); break;
