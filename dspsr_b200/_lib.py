@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200dsp.so")
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(_HERE, "libb200dsp.so")   # B200_LIB: developer override (A/B builds)
 
 OK = 0
 FMT_CASPSR8, FMT_GENERIC8, FMT_MEERKAT8, FMT_UWB16, FMT_FLOAT32, FMT_TWOBIT = range(6)

@@ -101,6 +101,7 @@ struct b200_fb_plan {
   // second-generation kernels (fastpath.cu): which passes they cover for this plan + their stage tables
   bool fast_k1, fast_k2, fast_k3;
   float2 *c2P, *c2Q, *c2F, *c2F32, *c2Q32;
+  float2* d_response_tiled;   // the response in K2's tile-major Z order (fastpath.cu, z_tiled), or null
   void* tmapA;              // CUtensorMap of scratchA for K1's TMA store (heap copy), or null
   bool k1_tma;
 };

@@ -31,11 +31,29 @@
 
 namespace b200 {
 
+// Ablation switches (B200_DBG1/2/3 bit flags: 1 skip the FFT, 2 skip the epilogue, 4 skip the loads) exist only in
+// builds made with -DB200_ABLATION: in the product build the tests compile away.
+#ifdef B200_ABLATION
+#define B200_DBGF(a, bit) ((a).dbg & (bit))
+#else
+#define B200_DBGF(a, bit) 0
+#endif
+
 __device__ __forceinline__ float2 ldg_nc_f2(const float2* p) {
   float2 r;
   asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
   return r;
 }
+
+// 256-bit load of four consecutive float2 (sm_100: LDG.E.256); p must be 32-byte aligned
+__device__ __forceinline__ void ldg_nc_f2x4(const float2* p, float2& a, float2& b, float2& c, float2& d) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(b.x), "=f"(b.y), "=f"(c.x), "=f"(c.y), "=f"(d.x), "=f"(d.y) : "l"(p));
+}
+// Tile-major Z (see k2_r32): float2 offset of element k2 of tile row g inside one (tile, side) region of Q*8
+// elements.  Four consecutive k2 of a row are contiguous (32 bytes: one sector, one 256-bit load in K3), the
+// eight rows of the tile follow each other, then the next group of four k2.
+__device__ __forceinline__ unsigned zt_pos(unsigned k2, unsigned g) { return ((k2 >> 2) << 5) + (g << 2) + (k2 & 3u); }
 
 // Cache policy of the once-written / once-read streams (spectrum scratch A and Z).  st.global.cs (evict
 // first) for the Z stores of K2 measured -7.7 % on that kernel; B200_NO_STREAMING restores default policies.
@@ -87,7 +105,8 @@ struct K1Args {
   unsigned overlap;          // nsamp_overlap (samples)
 };
 
-template <int SRC, unsigned P, int NP, bool TMA>
+// QC: row length Q fixed at compile time (0 = run-time a.Q): all row strides become immediates
+template <int SRC, unsigned P, int NP, bool TMA, unsigned QC = 0>
 __global__ void __launch_bounds__(NP*(P / 16), 512 / (NP * (P / 16)))
 k1_c2(K1Args a, const __grid_constant__ CUtensorMap tmapA) {
   extern __shared__ __align__(128) float4 smem4[];
@@ -97,7 +116,7 @@ k1_c2(K1Args a, const __grid_constant__ CUtensorMap tmapA) {
   static_assert(c2::pair_slots<P>() % 8 == 0, "region skew assumes an 8-aligned pair size");
   constexpr unsigned RS = c2::pair_slots<P>() + 8 / NP;   // regions skewed so the NP pairs of a phase hit distinct banks
   const unsigned pair = threadIdx.x % NP, j = threadIdx.x / NP;
-  const unsigned Q = a.Q;
+  const unsigned Q = QC ? QC : a.Q;
   const unsigned ncolblk = Q / (2 * NP);
   const unsigned ntiles = ncolblk * a.nblk;
 
@@ -122,7 +141,7 @@ k1_c2(K1Args a, const __grid_constant__ CUtensorMap tmapA) {
 
   unsigned w[16];
   unsigned t = blockIdx.x;
-  if (SRC == SRC_CASPSR8 && t < ntiles && !(a.dbg & 4)) {
+  if (SRC == SRC_CASPSR8 && t < ntiles && !(B200_DBGF(a, 4))) {
     const unsigned char* raw = raw_ptr(t);
 #pragma unroll
     for (int e = 0; e < 16; e++) w[e] = __ldg(reinterpret_cast<const unsigned*>(raw + 4ull * Q * T * e));
@@ -169,7 +188,7 @@ k1_c2(K1Args a, const __grid_constant__ CUtensorMap tmapA) {
     const float2 wb = big_twiddle<false>(a.blo, a.bhi, ((n2 + 1) * j) & (a.Nc - 1));
 
     float2 va[16], vb[16];
-    if (a.dbg & 4) {
+    if (B200_DBGF(a, 4)) {
 #pragma unroll
       for (int e = 0; e < 16; e++) { va[e] = make_float2(float(threadIdx.x + e), 1.f); vb[e] = make_float2(2.f, float(e)); }
     } else if (SRC == SRC_CASPSR8) {
@@ -216,12 +235,12 @@ k1_c2(K1Args a, const __grid_constant__ CUtensorMap tmapA) {
     __syncthreads();     // the previous tile's readers of s_h and of the exchange buffer are done
     if (threadIdx.x < 16 * NP * 2) reinterpret_cast<float2*>(s_h)[threadIdx.x] = shv;
 
-    if (!(a.dbg & 1)) c2::fft_pair<P, false>(va, vb, j, smem4 + pair * RS, a.tw, CtaSync());
+    if (!(B200_DBGF(a, 1))) c2::fft_pair<P, false>(va, vb, j, smem4 + pair * RS, a.tw, CtaSync());
     else __syncthreads();
 
     // prefetch the raw words of the next tile; they land while this tile is twiddled and stored
     const unsigned tn = t + gridDim.x;
-    if (SRC == SRC_CASPSR8 && tn < ntiles && !(a.dbg & 4)) {
+    if (SRC == SRC_CASPSR8 && tn < ntiles && !(B200_DBGF(a, 4))) {
       const unsigned char* raw = raw_ptr(tn);
 #pragma unroll
       for (int e = 0; e < 16; e++) w[e] = __ldg(reinterpret_cast<const unsigned*>(raw + 4ull * Q * T * e));
@@ -261,7 +280,7 @@ k1_c2(K1Args a, const __grid_constant__ CUtensorMap tmapA) {
         const float4 h = s_h[e * NP + pair];
         const float2 xa = cmul(cmul(va[e], wa), make_float2(h.x, h.y));
         const float2 xb = cmul(cmul(vb[e], wb), make_float2(h.z, h.w));
-        if (!(a.dbg & 2) || xa.x == 12345.678f)
+        if (!(B200_DBGF(a, 2)) || xa.x == 12345.678f)
           B200_AST(reinterpret_cast<float4*>(dst + uint64_t(Q) * T * e), make_float4(xa.x, xa.y, xb.x, xb.y));
       }
     }
@@ -276,6 +295,7 @@ struct K2Args {
   const float2* A;
   float2* Z;
   const float2* H;
+  const float2* Ht;        // H in the tile-major order of Z (same offsets as the Z stores), used when z_tiled
   const float2* tw;        // c2 stage tables of Q
   const float2* tw2Q;      // exp(-2 pi i m / (2Q))
   const float2* tw32;      // 32.32 plan: W_1024^(s j), s = 1..7, then W_1024^(8 m j), m = 1..3  ([10][32])
@@ -314,7 +334,7 @@ __global__ void __launch_bounds__(512, 1) k2_c2(K2Args a) {
     const float2* pb = a.A + uint64_t(blk) * Nc + uint64_t(rb) * Q + j;
 #pragma unroll
     for (int e = 0; e < 16; e++) {
-      if (a.dbg & 4) { va[e] = make_float2(float(threadIdx.x + e), 1.f); vb[e] = make_float2(2.f, float(e)); continue; }
+      if (B200_DBGF(a, 4)) { va[e] = make_float2(float(threadIdx.x + e), 1.f); vb[e] = make_float2(2.f, float(e)); continue; }
       va[e] = B200_LDS1(pa + e * T);
       vb[e] = B200_LDS1(pb + e * T);
     }
@@ -331,7 +351,7 @@ __global__ void __launch_bounds__(512, 1) k2_c2(K2Args a) {
       s_rowtw[threadIdx.x] = big_twiddle<false>(a.b2lo, a.b2hi, r);
     }
     float4* sm = smem4 + g * RS;
-    if (!(a.dbg & 1)) c2::fft_pair<Q, false>(va, vb, j, sm, a.tw, CtaSync());
+    if (!(B200_DBGF(a, 1))) c2::fft_pair<Q, false>(va, vb, j, sm, a.tw, CtaSync());
     __syncthreads();
     c2::store_natural<Q>(sm, va, vb, j);
     __syncthreads();
@@ -339,7 +359,7 @@ __global__ void __launch_bounds__(512, 1) k2_c2(K2Args a) {
     // the rows of the next tile stream in while this tile is split, multiplied and stored
     if (t + gridDim.x < ntiles) issue_loads(t + gridDim.x);
 
-    if (!((a.dbg & 2) && va[3].x != 12345.678f)) {
+    if (!((B200_DBGF(a, 2)) && va[3].x != 12345.678f)) {
       // ---- phase 2: lanes walk the G pairs first (G consecutive bins = one 64-byte segment of Z) ----
       const float2* H = a.H ? a.H + uint64_t(ic) * Nc : nullptr;
       float2* Zblk = a.Z + uint64_t(blk) * Nc;
@@ -452,13 +472,18 @@ __global__ void __launch_bounds__(512, 1) k2_c2(K2Args a) {
 // radix-32 stages -- so the single exchange of the transform is warp-local (__syncwarp, stride-33 padded
 // 64-bit accesses) and the whole tile needs just two CTA barriers (before and after the split phase)
 // instead of six.  Rows a / b of a mirror pair sit in separate float2 arrays (a at sequence 2g, b at 2g+1);
-// the array stride 1057 = 1 mod 8 makes the lane-by-pair walk of the split phase conflict free.
+// the array stride (1057 or 1058, see RSQ) makes the lane-by-pair walk of the split phase conflict free.
 // ------------------------------------------------------------------------------------------
 template <unsigned P, bool SPLIT>
 __global__ void __launch_bounds__(512, 1) k2_r32(K2Args a) {
   extern __shared__ float4 smem4[];
   float2* sm2 = reinterpret_cast<float2*>(smem4);
-  constexpr unsigned Q = 1024, G = 8, RSQ = 1057;
+  constexpr unsigned Q = 1024, G = 8;
+  // row stride of the shared arrays (float2): the split phase reads element kk of 8 pair rows per warp.  Natural Z
+  // order walks the rows fastest (half-warp = 8 rows x 2 kk: 2 RSQ = 2 mod 16 is conflict free); the tiled order
+  // walks kk fastest so that lanes are in address order (half-warp = 4 kk x 4 rows: 2 RSQ = 4 mod 16).
+  const bool kfast = a.z_tiled != 0;
+  const unsigned RSQ = kfast ? 1058u : 1057u;
   constexpr unsigned TPB = SPLIT ? (P / 2) / G : P / (2 * G);
   __shared__ float2 s_rowtw[G + 1];
   const unsigned seq = threadIdx.x >> 5, j = threadIdx.x & 31u;
@@ -522,7 +547,9 @@ __global__ void __launch_bounds__(512, 1) k2_r32(K2Args a) {
     {
       const float2* H = a.H ? a.H + uint64_t(ic) * Nc : nullptr;
       float2* Zblk = a.Z + uint64_t(blk) * Nc;
-      const unsigned g2 = threadIdx.x % G, kk = threadIdx.x / G;   // kk < 64
+      // kk < 64.  Tiled: lane = (kk & 3) + 4 g2 is the address order inside the warp's 256-byte block (zt_pos)
+      const unsigned g2 = kfast ? (threadIdx.x >> 2) & 7u : threadIdx.x % G;
+      const unsigned kk = kfast ? (threadIdx.x & 3u) + 4u * (threadIdx.x >> 5) : threadIdx.x / G;
       const float2* SA = sm2 + (2 * g2) * RSQ;                     // row a of pair g2
       const float2* SB = SA + RSQ;                                 // row b
       auto p33 = [](unsigned i) { return i + (i >> 5); };
@@ -563,20 +590,26 @@ __global__ void __launch_bounds__(512, 1) k2_r32(K2Args a) {
           const float2* HAm = H ? H + (Nc - k0) : nullptr;
           const float2* HB = H ? H + k1b : nullptr;
           const float2* HBm = H ? H + (Nc - k1b) : nullptr;
+          int hstep = KSTEP;
           // natural order: bin k at Z[k].  Tiled order (a.z_tiled): element k2 of row r sits at
-          // Z'[tile][side][k2][g] (r < P/2: tile = r/8, side 0, g = r%8; r > P/2: m = P-r, tile = m/8, side 1,
+          // Z'[tile][side][k2/4][g][k2%4] (zt_pos; r < P/2: tile = r/8, side 0, g = r%8; r > P/2: m = P-r, tile = m/8, side 1,
           // g = m%8), so a K2 tile writes two contiguous 64 KiB regions -- sequential stores -- and a warp's
           // store covers 256 contiguous bytes.  K3 (32.16.16 plan) reads the same layout.
           float2 *ZA, *ZAm, *ZB, *ZBm;
           int zstep, zstepm;
           if (a.z_tiled) {
-            float2* zt = Zblk + uint64_t(tile) * (2 * Q * G) + g2;
-            ZA = zt + kk * G;                        // (side 0, k2)
-            ZBm = zt + Q * G + kk * G;               // (side 1, k2)
-            ZB = zt + (Q - 1 - kk) * G;              // (side 0, Q-1-k2)
-            ZAm = zt + Q * G + (Q - 1 - kk) * G;     // (side 1, Q-1-k2)
-            zstep = 64 * G;
+            float2* zt = Zblk + uint64_t(tile) * (2 * Q * G);
+            ZA = zt + zt_pos(kk, g2);                        // (side 0, k2)
+            ZBm = zt + Q * G + zt_pos(kk, g2);               // (side 1, k2)
+            ZB = zt + zt_pos(Q - 1 - kk, g2);                // (side 0, Q-1-k2)
+            ZAm = zt + Q * G + zt_pos(Q - 1 - kk, g2);       // (side 1, Q-1-k2)
+            zstep = 64 * G;                                  // k2 += 64 keeps k2 & 3: the group index moves by 16
             zstepm = 64 * G;
+            if (H) {                                         // the response sits in the same order (Ht)
+              const float2* Htc = a.Ht + uint64_t(ic) * Nc;
+              HA = Htc + (ZA - Zblk); HAm = Htc + (ZAm - Zblk); HB = Htc + (ZB - Zblk); HBm = Htc + (ZBm - Zblk);
+              hstep = 64 * G;
+            }
           } else {
             ZA = Zblk + k0;
             ZAm = Zblk + (Nc - k0);
@@ -595,10 +628,10 @@ __global__ void __launch_bounds__(512, 1) k2_r32(K2Args a) {
             split(ua, make_float2(vb2.x, -vb2.y), wA, xk, xm);
             split(va2, make_float2(ub.x, -ub.y), wB, yk, ym);
             if (H) {
-              xk = cmul(xk, __ldg(HA + it * KSTEP));
-              xm = cmul(xm, __ldg(HAm - it * KSTEP));
-              yk = cmul(yk, __ldg(HB - it * KSTEP));
-              ym = cmul(ym, __ldg(HBm + it * KSTEP));
+              xk = cmul(xk, __ldg(HA + it * hstep));
+              xm = cmul(xm, __ldg(HAm - it * hstep));
+              yk = cmul(yk, __ldg(HB - it * hstep));
+              ym = cmul(ym, __ldg(HBm + it * hstep));
             }
             B200_ZST(ZA + it * zstep, xk);
             B200_ZST(ZAm - it * zstepm, xm);
@@ -618,8 +651,8 @@ __global__ void __launch_bounds__(512, 1) k2_r32(K2Args a) {
               const unsigned k = P * k2, km = (Nc - k) & (Nc - 1);
               if (H) { xk = cmul(xk, __ldg(H + k)); xm = cmul(xm, __ldg(H + km)); }
               if (a.z_tiled) {                       // row 0: tile 0, side 0, g 0
-                Zblk[k2 * G] = xk;
-                if (km2 != k2) Zblk[km2 * G] = xm;
+                Zblk[zt_pos(k2, 0)] = xk;
+                if (km2 != k2) Zblk[zt_pos(km2, 0)] = xm;
               } else {
                 Zblk[k] = xk;
                 if (km2 != k2) Zblk[km] = xm;
@@ -632,8 +665,8 @@ __global__ void __launch_bounds__(512, 1) k2_r32(K2Args a) {
               const unsigned k = P / 2 + P * k2, km = Nc - k;
               if (H) { xk = cmul(xk, __ldg(H + k)); xm = cmul(xm, __ldg(H + km)); }
               if (a.z_tiled) {                       // row P/2: tile 0, side 1, g 0
-                Zblk[Q * G + k2 * G] = xk;
-                Zblk[Q * G + (Q - 1 - k2) * G] = xm;
+                Zblk[Q * G + zt_pos(k2, 0)] = xk;
+                Zblk[Q * G + zt_pos(Q - 1 - k2, 0)] = xm;
               } else {
                 Zblk[k] = xk;
                 Zblk[km] = xm;
@@ -706,8 +739,9 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
       // stage-0 ownership: thread (pol, j0) holds x_pol[j0 + 256 e], e < 32, in vp[0..15], vq[0..15]
       const unsigned pol = threadIdx.x >> 8, j0 = threadIdx.x & 255u;
       if (a.z_tiled) {
-        // bin f = j0 + 256 e of channel csub is element k2 = 4 csub + (e >> 3) of row r = j0 + 256 (e & 7)
-        const float2* zb = a.Z + (blk + pol) * a.Nc + 32u * csub;     // + k2 * 8 with k2 = 4 csub + q
+        // bin f = j0 + 256 e of channel csub is element k2 = 4 csub + (e >> 3) of row r = j0 + 256 (e & 7):
+        // the four k2 of a row are one 32-byte group of the tiled layout -> one 256-bit load
+        const float2* zb = a.Z + (blk + pol) * a.Nc + 32u * csub;     // zt_pos(4 csub, 0)
 #pragma unroll
         for (int i = 0; i < 8; i++) {
           const unsigned r = j0 + 256u * i;
@@ -715,12 +749,13 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
           if (r < 1024u) { tile = r >> 3; side = 0; g8 = r & 7u; }
           else if (r == 1024u) { tile = 0; side = 1; g8 = 0; }
           else { const unsigned m = 2048u - r; tile = m >> 3; side = 1; g8 = m & 7u; }
-          const float2* p = zb + (uint64_t(tile) * 2 + side) * 8192u + g8;
+          const float2* p = zb + (uint64_t(tile) * 2 + side) * 8192u + 4u * g8;
+          float2 x[4];
+          ldg_nc_f2x4(p, x[0], x[1], x[2], x[3]);
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             const int e = i + 8 * q;
-            const float2 x = B200_LDS1(p + 8 * q);
-            if (e < 16) vp[e] = x; else vq[e - 16] = x;
+            if (e < 16) vp[e] = x[q]; else vq[e - 16] = x[q];
           }
         }
         return;
@@ -737,7 +772,7 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
     const float2* srcq = srcp + a.Nc;
 #pragma unroll
     for (int e = 0; e < 16; e++) {
-      if (a.dbg & 4) { vp[e] = make_float2(float(threadIdx.x + e), 1.f); vq[e] = make_float2(2.f, float(e)); continue; }
+      if (B200_DBGF(a, 4)) { vp[e] = make_float2(float(threadIdx.x + e), 1.f); vq[e] = make_float2(2.f, float(e)); continue; }
       vp[e] = B200_LDS1(srcp + e * T);
       vq[e] = B200_LDS1(srcq + e * T);
     }
@@ -793,8 +828,8 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
       for (int r = 1; r < 16; r++) { vp[r] = cmul(vp[r], w[r - 1]); vq[r] = cmul(vq[r], w[r - 1]); }
       dft16<true>(vp);
       dft16<true>(vq);
-    } else if (!(a.dbg & 1)) c2::fft_pair<F, true>(vp, vq, j, sm, a.tw, CtaSync());
-    if ((a.dbg & 2) && vp[3].x != 12345.678f) {
+    } else if (!(B200_DBGF(a, 1))) c2::fft_pair<F, true>(vp, vq, j, sm, a.tw, CtaSync());
+    if ((B200_DBGF(a, 2)) && vp[3].x != 12345.678f) {
       __syncthreads();
       if (tn < ntiles) issue_loads(tn);
       continue;
@@ -876,60 +911,69 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
       }
     }
     __syncthreads();
+    // the bins of the first walk have long arrived: looking at them BEFORE the next tile's loads are queued keeps
+    // the walk from waiting behind those loads (the compiler tracks both on the same scoreboard)
+    unsigned diff = 0;
+    if (threadIdx.x < total) {
+#pragma unroll
+      for (int i = 1; i < 16; i++) diff |= b[i] ^ b[0];
+    }
     // the spectra of the next tile stream in while this one is folded
     if (tn < ntiles) issue_loads(tn);
     {
       const unsigned nbin = a.sink.nbin;
       float* prof0 = a.sink.profile + uint64_t(ch0) * nbin * nprod;
-      auto red_add = [&](unsigned key, const float* acc) {
-        // key = c*nbin + bin; profile layout per channel [npol'][nbin][ndim']
-        const unsigned c = key / nbin, bin = key - c * nbin;
-        float* base = prof0 + uint64_t(c) * nbin * nprod;
+      // profile layout per channel [npol'][nbin][ndim']
+      auto red_add = [&](float* base, unsigned bin, const float* acc) {
         for (unsigned pr = 0; pr < nprod; pr++)
           atomicAdd(base + (uint64_t(pr / dndim) * nbin + bin) * dndim + pr % dndim, acc[pr]);
       };
       const unsigned niter = (total + 511u) / 512u;
       for (unsigned itr = 0; itr < niter; itr++) {
         const unsigned it = itr * 512u + threadIdx.x;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        unsigned key = 0xffffffffu;
-        if (it < total) {
-          const unsigned c = (CB == 1) ? 0 : it / nchunk;
-          const unsigned chunk = it - c * nchunk;
-          const unsigned m0 = chunk * L;
-          const unsigned n = min(L, nkeep - m0);
-          const float4* det = smem4 + c * RS + 17u * chunk;      // pad16(16*chunk + i) = 17*chunk + i
-          if (itr > 0) {
-            const unsigned* pl = plan + m0;
+        if (it >= total) break;
+        const unsigned c = (CB == 1) ? 0 : it / nchunk;
+        const unsigned chunk = it - c * nchunk;
+        const unsigned m0 = chunk * L;
+        const unsigned n = min(L, nkeep - m0);
+        const float4* det = smem4 + c * RS + 17u * chunk;      // pad16(16*chunk + i) = 17*chunk + i
+        float* base = prof0 + uint64_t(c) * nbin * nprod;
+        if (itr > 0) {
+          const unsigned* pl = plan + m0;
 #pragma unroll
-            for (int i = 0; i < 16; i++) b[i] = (unsigned(i) < n) ? __ldg(pl + i) : 0xfffffffeu;
-          }
-          unsigned diff = 0;
+          for (int i = 0; i < 16; i++) b[i] = (unsigned(i) < n) ? __ldg(pl + i) : 0xfffffffeu;
+          diff = 0;
 #pragma unroll
           for (int i = 1; i < 16; i++) diff |= b[i] ^ b[0];
-          if (diff == 0) {
-            // the common case (bins are usually many samples wide): the whole walk is one run
-            key = c * nbin + b[0];
-            float4 r = det[0];
+        }
+        float acc[4];
+        unsigned key;
+        if (diff == 0) {
+          // bins are usually several samples wide: the whole walk is one run
+          key = b[0];
+          float4 r = det[0];
+          acc[0] = r.x; acc[1] = r.y; acc[2] = r.z; acc[3] = r.w;
+#pragma unroll
+          for (int i = 1; i < 16; i++) {
+            r = det[i];
+            acc[0] += r.x; acc[1] += r.y; acc[2] += r.z; acc[3] += r.w;
+          }
+        } else {
+          key = b[0];
+          {
+            const float4 r = det[0];
             acc[0] = r.x; acc[1] = r.y; acc[2] = r.z; acc[3] = r.w;
+          }
 #pragma unroll
-            for (int i = 1; i < 16; i++) {
-              r = det[i];
-              acc[0] += r.x; acc[1] += r.y; acc[2] += r.z; acc[3] += r.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-              if (unsigned(i) < n) {
-                const unsigned k = c * nbin + b[i];
-                const float4 r = det[i];
-                if (k != key) {
-                  if (key != 0xffffffffu) red_add(key, acc);
-                  key = k;
-                  acc[0] = r.x; acc[1] = r.y; acc[2] = r.z; acc[3] = r.w;
-                } else {
-                  acc[0] += r.x; acc[1] += r.y; acc[2] += r.z; acc[3] += r.w;
-                }
+          for (int i = 1; i < 16; i++) {
+            if (unsigned(i) < n) {
+              const float4 r = det[i];
+              if (b[i] != key) {
+                red_add(base, key, acc);
+                key = b[i];
+                acc[0] = r.x; acc[1] = r.y; acc[2] = r.z; acc[3] = r.w;
+              } else {
+                acc[0] += r.x; acc[1] += r.y; acc[2] += r.z; acc[3] += r.w;
               }
             }
           }
@@ -938,10 +982,24 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
         // address, which RED.ADD.F32 absorbs easily -- 6 % faster for K3 than first combining equal keys
         // across the warp with shuffles, and valid for any pulse period (a shuffle scan over "equal
         // neighbouring keys" double counts once the period is shorter than a warp's span of samples)
-        if (key != 0xffffffffu) red_add(key, acc);
+        red_add(base, key, acc);
       }
     }
     __syncthreads();       // fold readers are done before the next tile's first scatter
+  }
+}
+
+// Response in the tile-major order of Z: bin k = r + P k2 (row r, element k2) goes where k2_r32 stores that bin.
+__global__ void k_tile_response(const float2* __restrict__ H, float2* __restrict__ Ht, unsigned nchan_in) {
+  constexpr unsigned P = 2048, Q = 1024, Nc = P * Q;
+  const uint64_t n = uint64_t(nchan_in) * Nc;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+    const unsigned k = unsigned(i % Nc), r = k % P, k2 = k / P;
+    unsigned tile, side, g;
+    if (r < P / 2) { tile = r >> 3; side = 0; g = r & 7u; }
+    else if (r == P / 2) { tile = 0; side = 1; g = 0; }
+    else { const unsigned m = P - r; tile = m >> 3; side = 1; g = m & 7u; }
+    Ht[(i - k) + (uint64_t(tile) * 2 + side) * (Q * 8) + zt_pos(k2, g)] = H[i];
   }
 }
 
@@ -975,7 +1033,7 @@ static constexpr unsigned FP_P = 2048, FP_Q = 1024;
 static constexpr int FP_NP = B200_K1_NP;
 static size_t k1_smem() { return size_t(FP_NP) * (c2::pair_slots<FP_P>() + 8 / FP_NP) * sizeof(float4); }
 static size_t k2_smem() { return size_t(512 / (FP_Q / 16)) * (c2::pair_slots<FP_Q>() | 1u) * sizeof(float4); }
-static size_t k2r32_smem() { return size_t(16) * 1057 * sizeof(float2); }
+static size_t k2r32_smem() { return size_t(16) * 1058 * sizeof(float2); }
 template <unsigned F> static size_t k3_smem() { return size_t(512 / (F / 16)) * c2::pair_slots<F>() * sizeof(float4); }
 
 static bool k3_r32_enabled() {
@@ -1053,6 +1111,7 @@ int fast_plan_init(b200_fb_plan* pl) {
   pl->c2P = pl->c2Q = pl->c2F = nullptr;
   pl->c2F32 = nullptr;
   pl->c2Q32 = nullptr;
+  pl->d_response_tiled = nullptr;
   pl->tmapA = nullptr;
   pl->k1_tma = false;
   if (!fast_enabled() || pl->conv_path) return B200_OK;
@@ -1061,6 +1120,8 @@ int fast_plan_init(b200_fb_plan* pl) {
     if ((rc = make_c2_table<FP_P>(&pl->c2P)) != B200_OK) return rc;
     if ((rc = opt_in_smem(k1_c2<SRC_F32, FP_P, FP_NP, false>, k1_smem())) != B200_OK) return rc;
     if ((rc = opt_in_smem(k1_c2<SRC_CASPSR8, FP_P, FP_NP, false>, k1_smem())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k1_c2<SRC_F32, FP_P, FP_NP, false, FP_Q>, k1_smem())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k1_c2<SRC_CASPSR8, FP_P, FP_NP, false, FP_Q>, k1_smem())) != B200_OK) return rc;
     if ((rc = opt_in_smem(k1_c2<SRC_F32, FP_P, FP_NP, true>, k1_smem())) != B200_OK) return rc;
     if ((rc = opt_in_smem(k1_c2<SRC_CASPSR8, FP_P, FP_NP, true>, k1_smem())) != B200_OK) return rc;
     pl->fast_k1 = true;
@@ -1112,10 +1173,19 @@ int fast_plan_init(b200_fb_plan* pl) {
     }
     if (rc != B200_OK) return rc;
   }
+  if (z_tiled(pl) && pl->d_response) {
+    const uint64_t n = uint64_t(pl->desc.input_nchan) * pl->Nc;
+    B200_CUDA(cudaMalloc(&pl->d_response_tiled, n * sizeof(float2)));
+    k_tile_response<<<1024, 256, 0, pl->ctx->stream>>>(pl->d_response, pl->d_response_tiled, pl->desc.input_nchan);
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaStreamSynchronize(pl->ctx->stream));
+  }
   return B200_OK;
 }
 
 void fast_plan_free(b200_fb_plan* pl) {
+  if (pl->d_response_tiled) cudaFree(pl->d_response_tiled);
+  pl->d_response_tiled = nullptr;
   if (pl->tmapA) delete static_cast<CUtensorMap*>(pl->tmapA);
   pl->tmapA = nullptr;
   if (pl->c2P) cudaFree(pl->c2P);
@@ -1188,7 +1258,10 @@ int fast_k1(b200_fb_plan* pl, const FbSource& src, uint64_t part0, unsigned nb) 
     if (src.kind == SRC_F32) k1_c2<SRC_F32, FP_P, FP_NP, true><<<grid, block, k1_smem(), ctx->stream>>>(a, tm);
     else k1_c2<SRC_CASPSR8, FP_P, FP_NP, true><<<grid, block, k1_smem(), ctx->stream>>>(a, tm);
   } else {
-    if (src.kind == SRC_F32) k1_c2<SRC_F32, FP_P, FP_NP, false><<<grid, block, k1_smem(), ctx->stream>>>(a, tm);
+    if (pl->Q == FP_Q) {
+      if (src.kind == SRC_F32) k1_c2<SRC_F32, FP_P, FP_NP, false, FP_Q><<<grid, block, k1_smem(), ctx->stream>>>(a, tm);
+      else k1_c2<SRC_CASPSR8, FP_P, FP_NP, false, FP_Q><<<grid, block, k1_smem(), ctx->stream>>>(a, tm);
+    } else if (src.kind == SRC_F32) k1_c2<SRC_F32, FP_P, FP_NP, false><<<grid, block, k1_smem(), ctx->stream>>>(a, tm);
     else k1_c2<SRC_CASPSR8, FP_P, FP_NP, false><<<grid, block, k1_smem(), ctx->stream>>>(a, tm);
   }
   return B200_OK;
@@ -1197,7 +1270,7 @@ int fast_k1(b200_fb_plan* pl, const FbSource& src, uint64_t part0, unsigned nb) 
 int fast_k2(b200_fb_plan* pl, unsigned nb) {
   Context* ctx = pl->ctx;
   K2Args a;
-  a.A = pl->scratchA; a.Z = pl->scratchZ; a.H = pl->d_response; a.tw = pl->c2Q; a.tw2Q = pl->tw2Q.tw;
+  a.A = pl->scratchA; a.Z = pl->scratchZ; a.H = pl->d_response; a.Ht = pl->d_response_tiled; a.tw = pl->c2Q; a.tw2Q = pl->tw2Q.tw;
   a.b2lo = pl->big2N.lo; a.b2hi = pl->big2N.hi;
   a.Nc = pl->Nc; a.npol = pl->desc.npol; a.nchan_in = pl->desc.input_nchan;
   a.nblk = nb * pl->desc.input_nchan * pl->desc.npol;
