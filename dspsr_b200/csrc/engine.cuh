@@ -41,6 +41,8 @@ struct FbSink {
   uint64_t det_span;
   // EPI_FOLD
   const unsigned* bins;     // bin of every output sample of the block (npart*nkeep)
+  const uint2* runs;        // run table of the bin plan, [npart][nkeep+1] of (start, bin) (fold.cu k_bin_runs), or null
+  const unsigned* nruns;    // [npart]
   double phase_per_sample;  // of the block's fold call (0 = unknown): enables the one-bin-per-chunk path
   unsigned nbin;
   float* profile;           // [chan][npol'][nbin][dndim]

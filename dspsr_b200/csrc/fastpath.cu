@@ -870,36 +870,25 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
       continue;
     }
 
-    // EPI_FOLD: detected products of the kept samples go back to shared memory in time order
-    // (slot pad16(t - nfilt_pos)); then every thread walks 16 consecutive samples of one channel,
-    // summing sequentially while the phase bin is unchanged (the order of Fold.C:844-852).  Every run is
-    // added to the global PhaseSeries with RED.ADD.F32 (no shared-memory float atomics: those compile
-    // to CAS loops).
-    constexpr unsigned L = 16;
-    const unsigned nchunk = (nkeep + L - 1) / L;
-    const unsigned total = CB * nchunk;
-    const unsigned* plan = a.sink.bins + partl * uint64_t(nkeep);
-    // bins of this thread's (first) walk: requested now, needed after the detection pass
-    unsigned b[16];
-    {
-      const unsigned it = threadIdx.x;
-      const unsigned c = (CB == 1) ? 0 : it / nchunk;
-      const unsigned m0 = (it - c * nchunk) * L;
-      if (it < total) {
-        const unsigned n = min(L, nkeep - m0);
-        const unsigned* pl = plan + m0;
-        if (n == L && (reinterpret_cast<uintptr_t>(pl) & 15) == 0) {
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(pl) + i);
-            b[4 * i] = v.x; b[4 * i + 1] = v.y; b[4 * i + 2] = v.z; b[4 * i + 3] = v.w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; i++) b[i] = (unsigned(i) < n) ? __ldg(pl + i) : 0xfffffffeu;
-        }
-      }
-    }
+    // EPI_FOLD: detected products of the kept samples go back to shared memory in time order (slot
+    // pad16(t - nfilt_pos)); then every thread takes whole RUNS of the bin plan -- maximal stretches of
+    // consecutive samples in one phase bin, tabulated per part by k_bin_runs (fold.cu) -- sums each run
+    // sequentially (the order of Fold.C:844-852) and adds it to the global PhaseSeries with one RED.ADD.F32 per
+    // product.  No per-sample bin comparisons, no divergent flushes; valid for any pulse period (a run is one
+    // sample long in the worst case).  (Shared-memory float atomics would compile to CAS loops.)
+    const uint2* runs = a.sink.runs + partl * (uint64_t(nkeep) + 1);
+    const unsigned nrun = __ldg(a.sink.nruns + partl);
+    const unsigned total = CB * nrun;
+    // (start, bin) and end of this thread's first two runs: requested now, needed after the detection pass
+    auto run_of = [&](unsigned it, unsigned& t0, unsigned& t1, unsigned& bin) {
+      const unsigned r = (CB == 1) ? it : it % nrun;
+      const uint2 h = __ldg(runs + r);
+      t0 = h.x; bin = h.y;
+      t1 = __ldg(runs + r + 1).x;
+    };
+    unsigned rt0 = 0, rt1 = 0, rbin = 0, st0 = 0, st1 = 0, sbin = 0;
+    if (threadIdx.x < total) run_of(threadIdx.x, rt0, rt1, rbin);
+    if (threadIdx.x + 512u < total) run_of(threadIdx.x + 512u, st0, st1, sbin);
     __syncthreads();                                      // all gathers of the last stage are done
 #pragma unroll
     for (int e = 0; e < 16; e++) {
@@ -911,78 +900,36 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
       }
     }
     __syncthreads();
-    // the bins of the first walk have long arrived: looking at them BEFORE the next tile's loads are queued keeps
-    // the walk from waiting behind those loads (the compiler tracks both on the same scoreboard)
-    unsigned diff = 0;
-    if (threadIdx.x < total) {
-#pragma unroll
-      for (int i = 1; i < 16; i++) diff |= b[i] ^ b[0];
-    }
     // the spectra of the next tile stream in while this one is folded
     if (tn < ntiles) issue_loads(tn);
     {
       const unsigned nbin = a.sink.nbin;
-      float* prof0 = a.sink.profile + uint64_t(ch0) * nbin * nprod;
-      // profile layout per channel [npol'][nbin][ndim']
-      auto red_add = [&](float* base, unsigned bin, const float* acc) {
-        for (unsigned pr = 0; pr < nprod; pr++)
-          atomicAdd(base + (uint64_t(pr / dndim) * nbin + bin) * dndim + pr % dndim, acc[pr]);
-      };
-      const unsigned niter = (total + 511u) / 512u;
-      for (unsigned itr = 0; itr < niter; itr++) {
-        const unsigned it = itr * 512u + threadIdx.x;
-        if (it >= total) break;
-        const unsigned c = (CB == 1) ? 0 : it / nchunk;
-        const unsigned chunk = it - c * nchunk;
-        const unsigned m0 = chunk * L;
-        const unsigned n = min(L, nkeep - m0);
-        const float4* det = smem4 + c * RS + 17u * chunk;      // pad16(16*chunk + i) = 17*chunk + i
+      float* prof0 = a.sink.profile + uint64_t(ch0) * nbin * nprod;     // per channel [npol'][nbin][ndim']
+      for (unsigned it = threadIdx.x; it < total; it += 512u) {
+        const unsigned c = (CB == 1) ? 0 : it / nrun;
+        if (it >= 1024u) run_of(it, rt0, rt1, rbin);
+        else if (it >= 512u) { rt0 = st0; rt1 = st1; rbin = sbin; }
+        const float4* det = smem4 + c * RS;
+        // the first eight samples of the run are requested together (runs are short: a phase bin is a few
+        // samples wide); longer runs continue one by one
+        float4 x[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const unsigned tt = rt0 + i;
+          x[i] = tt < rt1 ? det[c2::pad16(tt)] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float acc[4] = {x[0].x, x[0].y, x[0].z, x[0].w};
+#pragma unroll
+        for (int i = 1; i < 8; i++) {
+          if (rt0 + i < rt1) { acc[0] += x[i].x; acc[1] += x[i].y; acc[2] += x[i].z; acc[3] += x[i].w; }
+        }
+        for (unsigned tt = rt0 + 8; tt < rt1; tt++) {
+          const float4 y = det[c2::pad16(tt)];
+          acc[0] += y.x; acc[1] += y.y; acc[2] += y.z; acc[3] += y.w;
+        }
         float* base = prof0 + uint64_t(c) * nbin * nprod;
-        if (itr > 0) {
-          const unsigned* pl = plan + m0;
-#pragma unroll
-          for (int i = 0; i < 16; i++) b[i] = (unsigned(i) < n) ? __ldg(pl + i) : 0xfffffffeu;
-          diff = 0;
-#pragma unroll
-          for (int i = 1; i < 16; i++) diff |= b[i] ^ b[0];
-        }
-        float acc[4];
-        unsigned key;
-        if (diff == 0) {
-          // bins are usually several samples wide: the whole walk is one run
-          key = b[0];
-          float4 r = det[0];
-          acc[0] = r.x; acc[1] = r.y; acc[2] = r.z; acc[3] = r.w;
-#pragma unroll
-          for (int i = 1; i < 16; i++) {
-            r = det[i];
-            acc[0] += r.x; acc[1] += r.y; acc[2] += r.z; acc[3] += r.w;
-          }
-        } else {
-          key = b[0];
-          {
-            const float4 r = det[0];
-            acc[0] = r.x; acc[1] = r.y; acc[2] = r.z; acc[3] = r.w;
-          }
-#pragma unroll
-          for (int i = 1; i < 16; i++) {
-            if (unsigned(i) < n) {
-              const float4 r = det[i];
-              if (b[i] != key) {
-                red_add(base, key, acc);
-                key = b[i];
-                acc[0] = r.x; acc[1] = r.y; acc[2] = r.z; acc[3] = r.w;
-              } else {
-                acc[0] += r.x; acc[1] += r.y; acc[2] += r.z; acc[3] += r.w;
-              }
-            }
-          }
-        }
-        // every walk adds its trailing run straight to the profile: about nine walks share a (channel, bin)
-        // address, which RED.ADD.F32 absorbs easily -- 6 % faster for K3 than first combining equal keys
-        // across the warp with shuffles, and valid for any pulse period (a shuffle scan over "equal
-        // neighbouring keys" double counts once the period is shorter than a warp's span of samples)
-        red_add(base, key, acc);
+        for (unsigned pr = 0; pr < nprod; pr++)
+          atomicAdd(base + (uint64_t(pr / dndim) * nbin + rbin) * dndim + pr % dndim, acc[pr]);
       }
     }
     __syncthreads();       // fold readers are done before the next tile's first scatter
@@ -1283,6 +1230,7 @@ int fast_k2(b200_fb_plan* pl, unsigned nb) {
   static const bool r32 = !(getenv("B200_K2_R32") && atoi(getenv("B200_K2_R32")) == 0);
   a.tw32 = pl->c2Q32;
   a.z_tiled = z_tiled(pl) ? 1 : 0;
+  if (getenv("B200_K2_NOH")) a.H = nullptr;   // timing experiment only: results are wrong
   if (r32 && pl->c2Q32) {
     if (split) k2_r32<FP_P, true><<<grid, 512, k2r32_smem(), ctx->stream>>>(a);
     else k2_r32<FP_P, false><<<grid, 512, k2r32_smem(), ctx->stream>>>(a);
@@ -1301,6 +1249,7 @@ int fast_k3(b200_fb_plan* pl, const FbSink& sk, uint64_t part0, unsigned nb) {
   a.nfilt_pos = pl->desc.nfilt_pos; a.nkeep = pl->nkeep; a.part0 = part0; a.sink = sk;
   a.dbg = dbg_flags(3);
   a.z_tiled = z_tiled(pl) ? 1 : 0;
+  B200_REQUIRE(sk.kind != EPI_FOLD || (sk.runs && sk.nruns), "fast_k3: the fold epilogue needs the run table (fold_build_runs)");
   LaunchScope ls(ctx, KC_INV);
   switch (pl->F) {
     case 8192: k3_launch<8192>(pl, a, sk, nb); break;

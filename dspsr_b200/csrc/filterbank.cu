@@ -670,7 +670,13 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
     }
     // ---- K3 ----
     FbSink sk = sink;
-    if (sk.kind == EPI_FOLD) sk.bins = sink.bins + part0 * pl->nkeep;
+    if (sk.kind == EPI_FOLD) {
+      sk.bins = sink.bins + part0 * pl->nkeep;
+      if (sink.runs) {
+        sk.runs = sink.runs + part0 * (uint64_t(pl->nkeep) + 1);
+        sk.nruns = sink.nruns + part0;
+      }
+    }
     if (pl->fast_k3) {
       int rc = fast_k3(pl, sk, part0, nb);
       if (rc != B200_OK) return rc;

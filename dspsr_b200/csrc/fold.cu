@@ -235,6 +235,50 @@ __global__ void k_expand_bins(const b200_phase_segment* __restrict__ seg, unsign
 }
 
 // ------------------------------------------------------------------------------------------
+// run table of the bin plan, per part of nkeep samples: runs[part][r] = (first sample relative to the part, bin) of
+// the r-th maximal stretch of consecutive samples with the same bin, runs[part][nruns] = (nkeep, 0).  The fused fold
+// epilogue (fastpath.cu) gives every run to one thread: one sequential sum and one RED per product, no per-sample
+// branching.  One CTA per part.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_bin_runs(const unsigned* __restrict__ bins, unsigned nkeep,
+                                                   uint2* __restrict__ runs, unsigned* __restrict__ nruns) {
+  __shared__ unsigned wsum[32];
+  __shared__ unsigned s_total;
+  const unsigned part = blockIdx.x, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  const unsigned* b = bins + uint64_t(part) * nkeep;
+  uint2* r = runs + uint64_t(part) * (nkeep + 1);
+  const unsigned per = (nkeep + 1023u) / 1024u;
+  const unsigned t0 = min(nkeep, threadIdx.x * per), t1 = min(nkeep, t0 + per);
+  unsigned cnt = 0;
+  for (unsigned t = t0; t < t1; t++) cnt += (t == 0 || b[t] != b[t - 1]) ? 1u : 0u;
+  unsigned incl = cnt;
+  for (unsigned o = 1; o < 32; o <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    const unsigned v = wsum[lane];
+    unsigned iv = v;
+    for (unsigned o = 1; o < 32; o <<= 1) {
+      const unsigned x = __shfl_up_sync(0xffffffffu, iv, o);
+      if (lane >= o) iv += x;
+    }
+    wsum[lane] = iv - v;
+    if (lane == 31) s_total = iv;
+  }
+  __syncthreads();
+  unsigned pos = wsum[w] + incl - cnt;
+  for (unsigned t = t0; t < t1; t++)
+    if (t == 0 || b[t] != b[t - 1]) r[pos++] = make_uint2(t, b[t]);
+  if (threadIdx.x == 0) {
+    nruns[part] = s_total;
+    r[s_total] = make_uint2(nkeep, 0u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // stand-alone fold (Fold.C:835-873): one CTA per (chan, pol, time slab); per-thread runs of
 // consecutive samples summed sequentially, then added to shared bins, then to the profile.
 // ------------------------------------------------------------------------------------------
@@ -310,6 +354,9 @@ struct b200_fold {
   unsigned* d_hits_last;
   unsigned* d_bins;
   uint64_t bins_capacity;
+  uint2* d_runs;                 // run table of the last set_bins (fold_build_runs), [npart][nkeep+1] (start, bin)
+  unsigned* d_nruns;             // [npart]
+  uint64_t runs_capacity, nruns_capacity;
   b200_phase_segment* d_seg;
   b200_phase_segment* h_seg;     // pinned
   uint64_t seg_capacity;
@@ -489,6 +536,8 @@ int b200_fold_destroy(b200_fold* f) {
   if (f->d_hits_total) cudaFree(f->d_hits_total);
   if (f->d_hits_last) cudaFree(f->d_hits_last);
   if (f->d_bins) cudaFree(f->d_bins);
+  if (f->d_runs) cudaFree(f->d_runs);
+  if (f->d_nruns) cudaFree(f->d_nruns);
   if (f->d_seg) cudaFree(f->d_seg);
   if (f->h_seg) cudaFreeHost(f->h_seg);
   if (f->seg_free) cudaEventDestroy(f->seg_free);
@@ -617,4 +666,31 @@ unsigned* b200_fold_device_hits(b200_fold* f) { return f ? f->d_hits_total : nul
 // internal accessors for pipeline.cu
 namespace b200 {
 const unsigned* fold_bins(b200_fold* f) { return f->d_bins; }
+const uint2* fold_runs(b200_fold* f) { return f->d_runs; }
+const unsigned* fold_nruns(b200_fold* f) { return f->d_nruns; }
+
+// Builds the per-part run table of the bin plan set by the last b200_fold_set_bins (ndat = npart * nkeep).
+int fold_build_runs(b200_fold* f, unsigned nkeep) {
+  B200_REQUIRE(f && f->d_bins && nkeep && f->ndat % nkeep == 0, "fold_build_runs: the bin plan is not a whole number of parts");
+  Context* ctx = f->ctx;
+  const uint64_t npart = f->ndat / nkeep, need = npart * (uint64_t(nkeep) + 1);
+  if (need > f->runs_capacity || npart > f->nruns_capacity) {
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (f->d_runs) cudaFree(f->d_runs);
+    if (f->d_nruns) cudaFree(f->d_nruns);
+    f->d_runs = nullptr;
+    f->d_nruns = nullptr;
+    f->runs_capacity = need + need / 4;
+    f->nruns_capacity = npart + npart / 4 + 16;
+    B200_CUDA(cudaMalloc(&f->d_runs, f->runs_capacity * sizeof(uint2)));
+    B200_CUDA(cudaMalloc(&f->d_nruns, f->nruns_capacity * sizeof(unsigned)));
+  }
+  if (npart == 0) return B200_OK;
+  {
+    LaunchScope ls(ctx, KC_BINS);
+    k_bin_runs<<<(unsigned)npart, 1024, 0, ctx->stream>>>(f->d_bins, nkeep, f->d_runs, f->d_nruns);
+  }
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
 }
