@@ -714,10 +714,18 @@ __device__ __forceinline__ void detect4(int state, float2 p, float2 q, float* r)
 // stage runs as ONE 32-point butterfly per thread (threads 0-255 polarisation p, 256-511 polarisation q),
 // which removes one of the three shared-memory exchanges and two of the six barriers.  The exchanges are
 // 64-bit (one float2 array per polarisation, one pad slot after every 32: stride 33 is conflict free).
-template <unsigned F, int EPI, int STATE, bool R32 = false>
-__global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
+//
+// ZTMA (R32 with the tile-major Z only): the side-0 half of the next tile (rows < P/2: 64 KiB) is fetched by the
+// TMA unit into a landing zone behind the exchange buffer WHILE the current tile is transformed -- a 3-D box of
+// the tensor [tile][side][8192 float2] -- and only the side-1 half still travels through registers during the fold
+// phase.  With one 128 KiB tile filling the register file, the register prefetch alone confines all HBM reads of
+// the kernel to the short fold phase of 148 SMs running in lock step.
+template <unsigned F, int EPI, int STATE, bool R32 = false, bool ZTMA = false>
+__global__ void __launch_bounds__(512, 1) k3_c2(K3Args a, const __grid_constant__ CUtensorMap tmapZ) {
   static_assert(!R32 || F == 8192, "the 32.16.16 plan is built for 8192 points");
-  extern __shared__ float4 smem4[];
+  static_assert(!ZTMA || R32, "the TMA landing zone belongs to the 32.16.16 plan");
+  extern __shared__ __align__(128) float4 smem4[];
+  __shared__ __align__(8) unsigned long long s_mbar;
   constexpr unsigned T = F / 16;
   constexpr unsigned CB = 512 / T;                     // channels per CTA
   constexpr unsigned RS = c2::pair_slots<F>();
@@ -743,7 +751,7 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
         // the four k2 of a row are one 32-byte group of the tiled layout -> one 256-bit load
         const float2* zb = a.Z + (blk + pol) * a.Nc + 32u * csub;     // zt_pos(4 csub, 0)
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = ZTMA ? 4 : 0; i < 8; i++) {
           const unsigned r = j0 + 256u * i;
           unsigned tile, side, g8;
           if (r < 1024u) { tile = r >> 3; side = 0; g8 = r & 7u; }
@@ -778,6 +786,33 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
     }
   };
 
+  // landing zone of the TMA half: [pol][tile 0..127][8 rows][4 k2] float2 = 2 x 32 KiB behind the exchange buffer
+  constexpr unsigned LAND_OFF = RS * CB * sizeof(float4);
+  static_assert(!ZTMA || LAND_OFF % 128 == 0, "TMA destination alignment");
+  unsigned char* land = reinterpret_cast<unsigned char*>(smem4) + LAND_OFF;
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(&s_mbar);
+  unsigned mbar_parity = 0;
+  auto issue_tma = [&](unsigned tt) {       // one thread: both polarisations of tile tt, side 0
+    const unsigned ch = tt % tiles_per_part, partl = tt / tiles_per_part;
+    const unsigned ic = ch / a.C, csub = ch % a.C;
+    const unsigned blk = (partl * a.nchan_in + ic) * 2;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(land);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(65536u) : "memory");
+#pragma unroll
+    for (unsigned pol = 0; pol < 2; pol++)
+      asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                   :: "r"(dst + pol * 32768u), "l"(&tmapZ), "r"(int(csub * 64u)), "r"(0), "r"(int((blk + pol) * 128u)), "r"(mbar)
+                   : "memory");
+  };
+  if (ZTMA) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x < ntiles) issue_tma(blockIdx.x);
+  }
+
   unsigned t = blockIdx.x;
   if (t < ntiles) issue_loads(t);
   for (; t < ntiles; t += gridDim.x) {
@@ -794,6 +829,27 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
         float2 u[32];
 #pragma unroll
         for (int e = 0; e < 16; e++) { u[e] = vp[e]; u[16 + e] = vq[e]; }
+        if (ZTMA) {
+          // wait for the TMA half of this tile, then rows j0 + 256 i, i < 4 (tile = (j0 >> 3) + 32 i, g = j0 & 7):
+          // 32 bytes per row, read as two 16-byte halves in a lane-dependent order so that a quarter warp covers
+          // all banks (lanes are 32 bytes apart)
+          asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                       "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" :: "r"(mbar), "r"(mbar_parity) : "memory");
+          mbar_parity ^= 1u;
+          const unsigned g8 = j0 & 7u, hsel = (g8 >> 2) & 1u;
+          const unsigned char* lp = land + pol * 32768u + (j0 >> 3) * 256u + g8 * 32u;
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const float4 fa = *reinterpret_cast<const float4*>(lp + i * 8192 + hsel * 16u);
+            const float4 fb = *reinterpret_cast<const float4*>(lp + i * 8192 + (hsel ^ 1u) * 16u);
+            const float4 lo = hsel ? fb : fa, hi = hsel ? fa : fb;
+            u[i] = make_float2(lo.x, lo.y);
+            u[i + 8] = make_float2(lo.z, lo.w);
+            u[i + 16] = make_float2(hi.x, hi.y);
+            u[i + 24] = make_float2(hi.z, hi.w);
+          }
+        }
         dft32<true>(u);
         float2* dst = (pol ? arrQ : arrP) + 33u * j0;           // pad33(32 j0 + r) = 33 j0 + r
 #pragma unroll
@@ -804,6 +860,8 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
 #pragma unroll
       for (int r = 1; r < 16; r++) w[r - 1] = tw_get<true>(a.tw32, (unsigned)(r - 1) * 32u + k1);
       __syncthreads();
+      // every thread has read the landing zone: the TMA unit may refill it with the next tile's half
+      if (ZTMA && threadIdx.x == 0 && tn < ntiles) issue_tma(tn);
       const unsigned pj = j + (j >> 5);                           // pad33(j + 512 e) = pj + 528 e
 #pragma unroll
       for (int e = 0; e < 16; e++) { vp[e] = arrP[pj + 528u * e]; vq[e] = arrQ[pj + 528u * e]; }
@@ -871,10 +929,10 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
     }
 
     // EPI_FOLD: detected products of the kept samples go back to shared memory in time order (slot
-    // pad16(t - nfilt_pos)); then every thread takes whole RUNS of the bin plan -- maximal stretches of
-    // consecutive samples in one phase bin, tabulated per part by k_bin_runs (fold.cu) -- sums each run
+    // pad16(t - nfilt_pos)); then every thread takes whole ITEMS of the bin plan -- at most 16 consecutive samples
+    // of one phase bin inside a 16-aligned block, tabulated per part by k_bin_runs (fold.cu) -- sums each item
     // sequentially (the order of Fold.C:844-852) and adds it to the global PhaseSeries with one RED.ADD.F32 per
-    // product.  No per-sample bin comparisons, no divergent flushes; valid for any pulse period (a run is one
+    // product.  No per-sample bin comparisons, no divergent flushes; valid for any pulse period (an item is one
     // sample long in the worst case).  (Shared-memory float atomics would compile to CAS loops.)
     const uint2* runs = a.sink.runs + partl * (uint64_t(nkeep) + 1);
     const unsigned nrun = __ldg(a.sink.nruns + partl);
@@ -909,23 +967,24 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
         const unsigned c = (CB == 1) ? 0 : it / nrun;
         if (it >= 1024u) run_of(it, rt0, rt1, rbin);
         else if (it >= 512u) { rt0 = st0; rt1 = st1; rbin = sbin; }
-        const float4* det = smem4 + c * RS;
-        // the first eight samples of the run are requested together (runs are short: a phase bin is a few
-        // samples wide); longer runs continue one by one
+        // an item never crosses a 16-aligned block: its samples are consecutive slots of the padded layout
+        const float4* det = smem4 + c * RS + c2::pad16(rt0);
+        const unsigned n = rt1 - rt0;                       // 1..16
         float4 x[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const unsigned tt = rt0 + i;
-          x[i] = tt < rt1 ? det[c2::pad16(tt)] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int i = 0; i < 8; i++) x[i] = unsigned(i) < n ? det[i] : make_float4(0.f, 0.f, 0.f, 0.f);
         float acc[4] = {x[0].x, x[0].y, x[0].z, x[0].w};
 #pragma unroll
         for (int i = 1; i < 8; i++) {
-          if (rt0 + i < rt1) { acc[0] += x[i].x; acc[1] += x[i].y; acc[2] += x[i].z; acc[3] += x[i].w; }
+          if (unsigned(i) < n) { acc[0] += x[i].x; acc[1] += x[i].y; acc[2] += x[i].z; acc[3] += x[i].w; }
         }
-        for (unsigned tt = rt0 + 8; tt < rt1; tt++) {
-          const float4 y = det[c2::pad16(tt)];
-          acc[0] += y.x; acc[1] += y.y; acc[2] += y.z; acc[3] += y.w;
+        if (n > 8) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) x[i] = unsigned(8 + i) < n ? det[8 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            if (unsigned(8 + i) < n) { acc[0] += x[i].x; acc[1] += x[i].y; acc[2] += x[i].z; acc[3] += x[i].w; }
+          }
         }
         float* base = prof0 + uint64_t(c) * nbin * nprod;
         for (unsigned pr = 0; pr < nprod; pr++)
@@ -982,6 +1041,7 @@ static size_t k1_smem() { return size_t(FP_NP) * (c2::pair_slots<FP_P>() + 8 / F
 static size_t k2_smem() { return size_t(512 / (FP_Q / 16)) * (c2::pair_slots<FP_Q>() | 1u) * sizeof(float4); }
 static size_t k2r32_smem() { return size_t(16) * 1058 * sizeof(float2); }
 template <unsigned F> static size_t k3_smem() { return size_t(512 / (F / 16)) * c2::pair_slots<F>() * sizeof(float4); }
+static size_t k3_tma_smem() { return k3_smem<8192>() + 65536; }   // + landing zone of the TMA half tile
 
 static bool k3_r32_enabled() {
   static const bool on = !(getenv("B200_K3_R32") && atoi(getenv("B200_K3_R32")) == 0);
@@ -1012,6 +1072,10 @@ template <unsigned F> static int k3_init(b200_fb_plan* pl) {
     if ((rc = opt_in_smem(k3_c2<8192, EPI_DETECT, -1, true>, k3_smem<8192>())) != B200_OK) return rc;
     if ((rc = opt_in_smem(k3_c2<8192, EPI_FOLD, -1, true>, k3_smem<8192>())) != B200_OK) return rc;
     if ((rc = opt_in_smem(k3_c2<8192, EPI_FOLD, B200_COHERENCE, true>, k3_smem<8192>())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k3_c2<8192, EPI_VOLT, -1, true, true>, k3_tma_smem())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k3_c2<8192, EPI_DETECT, -1, true, true>, k3_tma_smem())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k3_c2<8192, EPI_FOLD, -1, true, true>, k3_tma_smem())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k3_c2<8192, EPI_FOLD, B200_COHERENCE, true, true>, k3_tma_smem())) != B200_OK) return rc;
   }
   if ((rc = opt_in_smem(k3_c2<F, EPI_VOLT, -1>, k3_smem<F>())) != B200_OK) return rc;
   if ((rc = opt_in_smem(k3_c2<F, EPI_DETECT, -1>, k3_smem<F>())) != B200_OK) return rc;
@@ -1026,19 +1090,30 @@ template <unsigned F> static void k3_launch(b200_fb_plan* pl, const K3Args& a, c
   constexpr unsigned CB = 512 / (F / 16);
   const unsigned ntiles = pl->nchan_out / CB * nb;
   dim3 grid(ntiles < (unsigned)ctx->sm_count ? ntiles : (unsigned)ctx->sm_count);
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
   if constexpr (F == 8192) {
+    if (a.z_tiled && pl->tmapZ) {
+      tm = *static_cast<CUtensorMap*>(pl->tmapZ);
+      const size_t sm = k3_tma_smem();
+      if (sk.kind == EPI_VOLT) k3_c2<8192, EPI_VOLT, -1, true, true><<<grid, 512, sm, ctx->stream>>>(a, tm);
+      else if (sk.kind == EPI_DETECT) k3_c2<8192, EPI_DETECT, -1, true, true><<<grid, 512, sm, ctx->stream>>>(a, tm);
+      else if (sk.state == B200_COHERENCE) k3_c2<8192, EPI_FOLD, B200_COHERENCE, true, true><<<grid, 512, sm, ctx->stream>>>(a, tm);
+      else k3_c2<8192, EPI_FOLD, -1, true, true><<<grid, 512, sm, ctx->stream>>>(a, tm);
+      return;
+    }
     if (k3_r32_enabled() && pl->c2F32) {
-      if (sk.kind == EPI_VOLT) k3_c2<8192, EPI_VOLT, -1, true><<<grid, 512, k3_smem<8192>(), ctx->stream>>>(a);
-      else if (sk.kind == EPI_DETECT) k3_c2<8192, EPI_DETECT, -1, true><<<grid, 512, k3_smem<8192>(), ctx->stream>>>(a);
-      else if (sk.state == B200_COHERENCE) k3_c2<8192, EPI_FOLD, B200_COHERENCE, true><<<grid, 512, k3_smem<8192>(), ctx->stream>>>(a);
-      else k3_c2<8192, EPI_FOLD, -1, true><<<grid, 512, k3_smem<8192>(), ctx->stream>>>(a);
+      if (sk.kind == EPI_VOLT) k3_c2<8192, EPI_VOLT, -1, true><<<grid, 512, k3_smem<8192>(), ctx->stream>>>(a, tm);
+      else if (sk.kind == EPI_DETECT) k3_c2<8192, EPI_DETECT, -1, true><<<grid, 512, k3_smem<8192>(), ctx->stream>>>(a, tm);
+      else if (sk.state == B200_COHERENCE) k3_c2<8192, EPI_FOLD, B200_COHERENCE, true><<<grid, 512, k3_smem<8192>(), ctx->stream>>>(a, tm);
+      else k3_c2<8192, EPI_FOLD, -1, true><<<grid, 512, k3_smem<8192>(), ctx->stream>>>(a, tm);
       return;
     }
   }
-  if (sk.kind == EPI_VOLT) k3_c2<F, EPI_VOLT, -1><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a);
-  else if (sk.kind == EPI_DETECT) k3_c2<F, EPI_DETECT, -1><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a);
-  else if (sk.state == B200_COHERENCE) k3_c2<F, EPI_FOLD, B200_COHERENCE><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a);
-  else k3_c2<F, EPI_FOLD, -1><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a);
+  if (sk.kind == EPI_VOLT) k3_c2<F, EPI_VOLT, -1><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a, tm);
+  else if (sk.kind == EPI_DETECT) k3_c2<F, EPI_DETECT, -1><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a, tm);
+  else if (sk.state == B200_COHERENCE) k3_c2<F, EPI_FOLD, B200_COHERENCE><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a, tm);
+  else k3_c2<F, EPI_FOLD, -1><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a, tm);
 }
 
 // Z travels from K2 to K3 in K2's tile-major order when both ends are the kernels that implement it:
@@ -1052,6 +1127,7 @@ static bool z_tiled(const b200_fb_plan* pl) {
 
 static bool rows_fit_tma(const b200_fb_plan* pl);
 static int make_a_tensor_map(b200_fb_plan* pl, CUtensorMap* tm);
+static int make_z_tensor_map(b200_fb_plan* pl, CUtensorMap* tm);
 
 int fast_plan_init(b200_fb_plan* pl) {
   pl->fast_k1 = pl->fast_k2 = pl->fast_k3 = false;
@@ -1060,6 +1136,7 @@ int fast_plan_init(b200_fb_plan* pl) {
   pl->c2Q32 = nullptr;
   pl->d_response_tiled = nullptr;
   pl->tmapA = nullptr;
+  pl->tmapZ = nullptr;
   pl->k1_tma = false;
   if (!fast_enabled() || pl->conv_path) return B200_OK;
   int rc = B200_OK;
@@ -1120,6 +1197,16 @@ int fast_plan_init(b200_fb_plan* pl) {
     }
     if (rc != B200_OK) return rc;
   }
+  // K3's TMA half-tile loads from the tile-major Z: correct (parity-tested) but measured no faster than the
+  // all-register prefetch on B200 (0.248 vs 0.246 ms per 16 parts), so it is opt-in (B200_K3_TMA=1)
+  static const bool want_ztma = getenv("B200_K3_TMA") && atoi(getenv("B200_K3_TMA")) == 1;
+  if (z_tiled(pl) && want_ztma) {
+    pl->tmapZ = new CUtensorMap();
+    if (make_z_tensor_map(pl, static_cast<CUtensorMap*>(pl->tmapZ)) != B200_OK) {
+      delete static_cast<CUtensorMap*>(pl->tmapZ);
+      pl->tmapZ = nullptr;
+    }
+  }
   if (z_tiled(pl) && pl->d_response) {
     const uint64_t n = uint64_t(pl->desc.input_nchan) * pl->Nc;
     B200_CUDA(cudaMalloc(&pl->d_response_tiled, n * sizeof(float2)));
@@ -1135,6 +1222,8 @@ void fast_plan_free(b200_fb_plan* pl) {
   pl->d_response_tiled = nullptr;
   if (pl->tmapA) delete static_cast<CUtensorMap*>(pl->tmapA);
   pl->tmapA = nullptr;
+  if (pl->tmapZ) delete static_cast<CUtensorMap*>(pl->tmapZ);
+  pl->tmapZ = nullptr;
   if (pl->c2P) cudaFree(pl->c2P);
   if (pl->c2Q) cudaFree(pl->c2Q);
   if (pl->c2F) cudaFree(pl->c2F);
@@ -1169,6 +1258,31 @@ static int make_a_tensor_map(b200_fb_plan* pl, CUtensorMap* tm) {
   const cuuint32_t box[2] = {4u * FP_NP, 256u};
   const cuuint32_t estride[2] = {1u, 1u};
   CUresult r = reinterpret_cast<encode_fn>(fn)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, pl->scratchA, gdim, gstride, box, estride,
+                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? B200_OK : B200_ERR_UNSUPPORTED;
+}
+
+// Tensor map of the tile-major Z scratch: [blocks * 128 tiles][2 sides][8192 float2] seen as floats; box = one
+// 256-byte k2 group of 128 tiles of one side (32 KiB): the side-0 half of one polarisation of a K3 tile.
+static int make_z_tensor_map(b200_fb_plan* pl, CUtensorMap* tm) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return B200_ERR_UNSUPPORTED;
+  }
+  const uint64_t nblk = uint64_t(pl->batch) * pl->desc.input_nchan * pl->desc.npol;
+  if (nblk * 128 >= (1ull << 31)) return B200_ERR_UNSUPPORTED;
+  const cuuint64_t gdim[3] = {16384, 2, nblk * 128};
+  const cuuint64_t gstride[2] = {16384 * sizeof(float), 2 * 16384 * sizeof(float)};
+  const cuuint32_t box[3] = {64u, 1u, 128u};
+  const cuuint32_t estride[3] = {1u, 1u, 1u};
+  CUresult r = reinterpret_cast<encode_fn>(fn)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, pl->scratchZ, gdim, gstride, box, estride,
                                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? B200_OK : B200_ERR_UNSUPPORTED;

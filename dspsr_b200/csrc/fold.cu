@@ -235,10 +235,11 @@ __global__ void k_expand_bins(const b200_phase_segment* __restrict__ seg, unsign
 }
 
 // ------------------------------------------------------------------------------------------
-// run table of the bin plan, per part of nkeep samples: runs[part][r] = (first sample relative to the part, bin) of
-// the r-th maximal stretch of consecutive samples with the same bin, runs[part][nruns] = (nkeep, 0).  The fused fold
-// epilogue (fastpath.cu) gives every run to one thread: one sequential sum and one RED per product, no per-sample
-// branching.  One CTA per part.
+// fold work items of the bin plan, per part of nkeep samples: a new item starts wherever the phase bin changes and
+// at every multiple of 16 samples, so an item is at most 16 consecutive samples of ONE bin inside one 16-aligned
+// block.  runs[part][r] = (first sample relative to the part, bin), runs[part][nruns] = (nkeep, 0).  The fused fold
+// epilogue (fastpath.cu) gives every item to one thread: one sequential sum and one RED per product, no per-sample
+// bin comparisons, balanced for wide bins (items of 16) and narrow ones alike.  One CTA per part.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_bin_runs(const unsigned* __restrict__ bins, unsigned nkeep,
                                                    uint2* __restrict__ runs, unsigned* __restrict__ nruns) {
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(1024) k_bin_runs(const unsigned* __restrict__ 
   const unsigned per = (nkeep + 1023u) / 1024u;
   const unsigned t0 = min(nkeep, threadIdx.x * per), t1 = min(nkeep, t0 + per);
   unsigned cnt = 0;
-  for (unsigned t = t0; t < t1; t++) cnt += (t == 0 || b[t] != b[t - 1]) ? 1u : 0u;
+  for (unsigned t = t0; t < t1; t++) cnt += ((t & 15u) == 0 || b[t] != b[t - 1]) ? 1u : 0u;
   unsigned incl = cnt;
   for (unsigned o = 1; o < 32; o <<= 1) {
     const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(1024) k_bin_runs(const unsigned* __restrict__ 
   __syncthreads();
   unsigned pos = wsum[w] + incl - cnt;
   for (unsigned t = t0; t < t1; t++)
-    if (t == 0 || b[t] != b[t - 1]) r[pos++] = make_uint2(t, b[t]);
+    if ((t & 15u) == 0 || b[t] != b[t - 1]) r[pos++] = make_uint2(t, b[t]);
   if (threadIdx.x == 0) {
     nruns[part] = s_total;
     r[s_total] = make_uint2(nkeep, 0u);
