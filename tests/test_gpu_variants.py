@@ -1,0 +1,31 @@
+"""The opt-in / fallback kernel variants behind the developer switches of fastpath.cu must stay
+bit-for-bit as correct as the default path: each variant re-runs the cfg1-shaped fused parity test (through the C ABI,
+against the oracle) in a fresh process, because the switches are read once per process."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+VARIANTS = {
+    "k3_tma_half_tile": {"B200_K3_TMA": "1"},
+    "k1_tma_store": {"B200_K1_TMA": "1"},
+    "z_natural_order": {"B200_Z_TILED": "0"},
+    "first_generation_plans": {"B200_K2_R32": "0", "B200_K3_R32": "0"},
+    "generic_kernels": {"B200_FAST": "0"},
+}
+
+
+@pytest.mark.parametrize("name", sorted(VARIANTS))
+def test_variant_matches_oracle(name):
+    env = dict(os.environ)
+    env.update(VARIANTS[name])
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-x",
+                        "-m", "gpu", "-k", "test_pipeline_cfg1 and not bench_scale or test_filterbank_cfg1_shape",
+                        "-p", "no:cacheprovider"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (name, r.stdout[-2000:], r.stderr[-2000:])
+    assert "2 passed" in r.stdout, r.stdout[-500:]
