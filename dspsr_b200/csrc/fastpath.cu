@@ -958,6 +958,10 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a, const __grid_constant_
       }
     }
     __syncthreads();
+    // the item descriptors have long arrived.  They are looked at BEFORE the next tile's loads are queued -- a
+    // sanity check of the table (an item is 1..16 samples) that also keeps the first item from waiting behind
+    // those loads: the compiler tracks descriptor and spectrum loads on the same scoreboard
+    if (rt1 - rt0 > 16u || st1 - st0 > 16u) asm volatile("trap;");
     // the spectra of the next tile stream in while this one is folded
     if (tn < ntiles) issue_loads(tn);
     {
