@@ -928,9 +928,9 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a, const __grid_constant_
       continue;
     }
 
-    // EPI_FOLD: detected products of the kept samples go back to shared memory in time order (slot
-    // pad16(t - nfilt_pos)); then every thread takes whole ITEMS of the bin plan -- at most 16 consecutive samples
-    // of one phase bin inside a 16-aligned block, tabulated per part by k_bin_runs (fold.cu) -- sums each item
+    // EPI_FOLD: detected products of the kept samples go back to shared memory in time order (slot pad16(t), t the
+    // transform index); then every thread takes whole ITEMS of the bin plan -- at most 16 consecutive samples
+    // of one phase bin inside a 16-aligned block of t, tabulated per part by k_bin_runs (fold.cu) -- sums each item
     // sequentially (the order of Fold.C:844-852) and adds it to the global PhaseSeries with one RED.ADD.F32 per
     // product.  No per-sample bin comparisons, no divergent flushes; valid for any pulse period (an item is one
     // sample long in the worst case).  (Shared-memory float atomics would compile to CAS loops.)
@@ -954,7 +954,7 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a, const __grid_constant_
       if (u < nkeep) {
         float r[4];
         detect4<STATE>(state, vp[e], vq[e], r);
-        sm[c2::pad16(u)] = make_float4(r[0], r[1], r[2], r[3]);
+        sm[c2::pad16(j + e * T)] = make_float4(r[0], r[1], r[2], r[3]);   // staged by transform index: aligned lanes
       }
     }
     __syncthreads();
@@ -972,7 +972,7 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a, const __grid_constant_
         if (it >= 1024u) run_of(it, rt0, rt1, rbin);
         else if (it >= 512u) { rt0 = st0; rt1 = st1; rbin = sbin; }
         // an item never crosses a 16-aligned block: its samples are consecutive slots of the padded layout
-        const float4* det = smem4 + c * RS + c2::pad16(rt0);
+        const float4* det = smem4 + c * RS + c2::pad16(rt0 + np0);
         const unsigned n = rt1 - rt0;                       // 1..16
         float4 x[8];
 #pragma unroll

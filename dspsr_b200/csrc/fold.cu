@@ -236,12 +236,12 @@ __global__ void k_expand_bins(const b200_phase_segment* __restrict__ seg, unsign
 
 // ------------------------------------------------------------------------------------------
 // fold work items of the bin plan, per part of nkeep samples: a new item starts wherever the phase bin changes and
-// at every multiple of 16 samples, so an item is at most 16 consecutive samples of ONE bin inside one 16-aligned
-// block.  runs[part][r] = (first sample relative to the part, bin), runs[part][nruns] = (nkeep, 0).  The fused fold
+// wherever (sample + align) is a multiple of 16, so an item is at most 16 consecutive samples of ONE bin inside one
+// 16-aligned block of the consumer's staging buffer (align = nfilt_pos mod 16: K3 stages by transform index).  runs[part][r] = (first sample relative to the part, bin), runs[part][nruns] = (nkeep, 0).  The fused fold
 // epilogue (fastpath.cu) gives every item to one thread: one sequential sum and one RED per product, no per-sample
 // bin comparisons, balanced for wide bins (items of 16) and narrow ones alike.  One CTA per part.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_bin_runs(const unsigned* __restrict__ bins, unsigned nkeep,
+__global__ void __launch_bounds__(1024) k_bin_runs(const unsigned* __restrict__ bins, unsigned nkeep, unsigned align,
                                                    uint2* __restrict__ runs, unsigned* __restrict__ nruns) {
   __shared__ unsigned wsum[32];
   __shared__ unsigned s_total;
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(1024) k_bin_runs(const unsigned* __restrict__ 
   const unsigned per = (nkeep + 1023u) / 1024u;
   const unsigned t0 = min(nkeep, threadIdx.x * per), t1 = min(nkeep, t0 + per);
   unsigned cnt = 0;
-  for (unsigned t = t0; t < t1; t++) cnt += ((t & 15u) == 0 || b[t] != b[t - 1]) ? 1u : 0u;
+  for (unsigned t = t0; t < t1; t++) cnt += (t == 0 || ((t + align) & 15u) == 0 || b[t] != b[t - 1]) ? 1u : 0u;
   unsigned incl = cnt;
   for (unsigned o = 1; o < 32; o <<= 1) {
     const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(1024) k_bin_runs(const unsigned* __restrict__ 
   __syncthreads();
   unsigned pos = wsum[w] + incl - cnt;
   for (unsigned t = t0; t < t1; t++)
-    if ((t & 15u) == 0 || b[t] != b[t - 1]) r[pos++] = make_uint2(t, b[t]);
+    if (t == 0 || ((t + align) & 15u) == 0 || b[t] != b[t - 1]) r[pos++] = make_uint2(t, b[t]);
   if (threadIdx.x == 0) {
     nruns[part] = s_total;
     r[s_total] = make_uint2(nkeep, 0u);
@@ -671,7 +671,7 @@ const uint2* fold_runs(b200_fold* f) { return f->d_runs; }
 const unsigned* fold_nruns(b200_fold* f) { return f->d_nruns; }
 
 // Builds the per-part run table of the bin plan set by the last b200_fold_set_bins (ndat = npart * nkeep).
-int fold_build_runs(b200_fold* f, unsigned nkeep) {
+int fold_build_runs(b200_fold* f, unsigned nkeep, unsigned align) {
   B200_REQUIRE(f && f->d_bins && nkeep && f->ndat % nkeep == 0, "fold_build_runs: the bin plan is not a whole number of parts");
   Context* ctx = f->ctx;
   const uint64_t npart = f->ndat / nkeep, need = npart * (uint64_t(nkeep) + 1);
@@ -689,7 +689,7 @@ int fold_build_runs(b200_fold* f, unsigned nkeep) {
   if (npart == 0) return B200_OK;
   {
     LaunchScope ls(ctx, KC_BINS);
-    k_bin_runs<<<(unsigned)npart, 1024, 0, ctx->stream>>>(f->d_bins, nkeep, f->d_runs, f->d_nruns);
+    k_bin_runs<<<(unsigned)npart, 1024, 0, ctx->stream>>>(f->d_bins, nkeep, align & 15u, f->d_runs, f->d_nruns);
   }
   B200_CUDA(cudaGetLastError());
   return B200_OK;

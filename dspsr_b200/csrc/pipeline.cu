@@ -14,7 +14,7 @@ namespace b200 {
 const unsigned* fold_bins(b200_fold* f);
 const uint2* fold_runs(b200_fold* f);
 const unsigned* fold_nruns(b200_fold* f);
-int fold_build_runs(b200_fold* f, unsigned nkeep);
+int fold_build_runs(b200_fold* f, unsigned nkeep, unsigned align);
 }
 using namespace b200;
 
@@ -287,7 +287,7 @@ static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t inpu
   if (p->desc.nbin) {
     if (!p->bins_preset) {
       int rc = b200_fold_set_bins(p->fold, phi, pps, ndat_out, 0, nullptr);
-      if (rc == B200_OK) rc = fold_build_runs(p->fold, fb->nkeep);
+      if (rc == B200_OK) rc = fold_build_runs(p->fold, fb->nkeep, fb->desc.nfilt_pos);
       if (rc != B200_OK) return rc;
     }
     p->bins_preset = false;
@@ -345,7 +345,7 @@ int b200_pipeline_execute_host(b200_pipeline* p, const void* h_input, uint64_t n
   // arrived, serialising transfer and compute.
   if (p->desc.nbin && chunked && !(fb->F > 8192 && !fb->conv_path)) {
     int rc0 = b200_fold_set_bins(p->fold, phi, pps, npart * fb->nkeep, 0, nullptr);
-    if (rc0 == B200_OK) rc0 = fold_build_runs(p->fold, fb->nkeep);
+    if (rc0 == B200_OK) rc0 = fold_build_runs(p->fold, fb->nkeep, fb->desc.nfilt_pos);
     if (rc0 != B200_OK) return rc0;
     p->bins_preset = true;
   }
