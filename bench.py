@@ -239,6 +239,12 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (ours) needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local)
+    numa_cores = 0
+    if world > 1:
+        # one process per GPU: stay on the GPU's NUMA node before any pinned buffer is allocated (N = 1 keeps all
+        # cores: the cpu_baseline leg runs there)
+        from dspsr_b200 import sharding
+        numa_cores = sharding.bind_cpu_affinity(local)
     if world > 1:
         # NCCL writes its version / INFO lines to stdout by default: keep stdout for the one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -378,7 +384,7 @@ def run_ours(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": S["cfg"]["name"], "parts_per_step": parts, "samples_per_pol_per_step": samples_step,
-                   "batch_parts": pipe.info.batch_npart, "sharding": "time blocks with overlap re-read (nchan=1)",
+                   "batch_parts": pipe.info.batch_npart, "sharding": "time blocks with overlap re-read (nchan=1)", "numa_bound_cores": numa_cores,
                    "l2": "inputs larger than L2: %d MB raw per step" % (raw.nbytes // 1000000)},
         "real_time_factor": value / 800.0,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(raw.nbytes),

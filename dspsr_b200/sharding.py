@@ -66,3 +66,28 @@ def gather_channel_sharded(profile_local, nchan_total, dst=0, group=None):
         _, n = shard_channels(nchan_total, world, r)
         out.append(bufs[r][:n])
     return torch.cat(out, dim=0)
+
+
+def bind_cpu_affinity(device_index):
+    """Pin the calling process to the CPU cores NVML reports as local to GPU `device_index` (the role of dspsr's
+    `-cpu` option next to `-cuda`, dspsr.C / SingleThread.C set_affinity), so that the pinned staging buffers
+    allocated afterwards are first touched on the GPU's NUMA node.  With one process per GPU on a multi-socket
+    host this keeps every host-to-device stream off the inter-socket link.  Returns the number of cores bound
+    (0: NVML unavailable or no usable mask -- the affinity is then left alone)."""
+    import os
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        h = nv.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (dom, bus, dev)).encode())
+        ncpu = os.cpu_count() or 1
+        mask = nv.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1} & os.sched_getaffinity(0)
+        if not cpus:
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0

@@ -278,3 +278,14 @@ def test_time_divide_half_sample_boundary_does_not_throw():
                 prev_end = t0 + b.idat_start + b.ndat
         t0 += ndat
     assert prev_end == t0
+
+
+def test_bind_cpu_affinity_is_harmless_without_gpu():
+    """sharding.bind_cpu_affinity: no GPU / no NVML here -> returns 0 and leaves the affinity mask alone."""
+    import os
+    from dspsr_b200 import sharding
+    before = os.sched_getaffinity(0)
+    n = sharding.bind_cpu_affinity(0)
+    assert n == 0 or n == len(os.sched_getaffinity(0))
+    if n == 0:
+        assert os.sched_getaffinity(0) == before
