@@ -229,8 +229,13 @@ __global__ void k_expand_bins(const b200_phase_segment* __restrict__ seg, unsign
     const double double_ibin = __dmul_rn(phi, double_nbin);      // Fold.C:766
     const unsigned ibin = unsigned(double_ibin);                 // Fold.C:767 (truncation)
     bins[i] = ibin;
-    atomicAdd(hits_last + ibin, 1u);
-    atomicAdd(hits_total + ibin, 1u);
+    // neighbouring samples mostly share a bin: one atomic per distinct bin of the warp instead of one per lane
+    const unsigned peers = __match_any_sync(__activemask(), ibin);
+    if ((threadIdx.x & 31u) == unsigned(__ffs(peers) - 1)) {
+      const unsigned n = __popc(peers);
+      atomicAdd(hits_last + ibin, n);
+      atomicAdd(hits_total + ibin, n);
+    }
   }
 }
 
