@@ -428,7 +428,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--parts", type=int, default=32, help="overlap-save parts per step (per GPU)")
+    ap.add_argument("--parts", type=int, default=74,
+                    help="overlap-save parts per step (per GPU); 74 = two internal batches of 37 parts (full waves on 148 SMs)")
     ap.add_argument("--batch", type=int, default=0, help="parts per internal kernel batch (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

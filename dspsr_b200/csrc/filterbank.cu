@@ -851,11 +851,27 @@ int b200_fb_plan_create(b200_context* cctx, const b200_fb_desc* d, b200_fb_plan*
       G *= 2;
     pl->G = G;
   }
-  // parts per internal batch: 16 (launch overhead < 2 %) unless one spectrum buffer would exceed 2 GiB
+  // parts per internal batch: 16 (launch overhead < 2 %) unless one spectrum buffer would exceed 2 GiB -- or, when
+  // it fits, the smallest count that makes the tiles of all three persistent kernels a multiple of the SM count
+  // (cfg1: 256 tiles per part, 148 SMs -> 37 parts = 64 full waves; measured +4.8 % over batches of 16)
   {
     const uint64_t per_part = uint64_t(d->input_nchan) * d->npol * pl->Nc * sizeof(float2);
-    uint64_t b = (2ull << 30) / per_part;
-    pl->batch = d->max_npart ? d->max_npart : unsigned(b < 1 ? 1 : b > 16 ? 16 : b);
+    const uint64_t cap = std::max<uint64_t>(1, (2ull << 30) / per_part);
+    uint64_t b = std::min<uint64_t>(cap, 16);
+    if (!pl->conv_path && pl->Q >= 8 && pl->P >= 16) {
+      auto gcd = [](uint64_t x, uint64_t y) { while (y) { const uint64_t t = x % y; x = y; y = t; } return x; };
+      const uint64_t sm = uint64_t(std::max(1, ctx->sm_count)), blk = uint64_t(d->input_nchan) * d->npol;
+      const uint64_t tiles[3] = {pl->Q / 8 * blk, pl->P / 16 * blk,
+                                 pl->F >= 8192 ? uint64_t(pl->nchan_out) : std::max<uint64_t>(1, uint64_t(pl->nchan_out) * pl->F / 8192)};
+      uint64_t need = 1;
+      for (uint64_t t : tiles) {
+        const uint64_t g = sm / gcd(sm, t);
+        need = need / gcd(need, g) * g;
+        if (need > 64) break;
+      }
+      if (need > 1 && need <= 64 && need <= cap) b = need;
+    }
+    pl->batch = d->max_npart ? d->max_npart : unsigned(b);
   }
 
   int rc = plan_set_attributes(size_t(ctx->max_smem_optin));
