@@ -287,14 +287,16 @@ static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t inpu
   if (p->desc.nbin) {
     if (!p->bins_preset) {
       int rc = b200_fold_set_bins(p->fold, phi, pps, ndat_out, 0, nullptr);
-      if (rc == B200_OK) rc = fold_build_runs(p->fold, fb->nkeep, fb->desc.nfilt_pos);
+      if (rc == B200_OK && fb->fast_k3) rc = fold_build_runs(p->fold, fb->nkeep, fb->desc.nfilt_pos);
       if (rc != B200_OK) return rc;
     }
     p->bins_preset = false;
     sink.kind = EPI_FOLD;
     sink.bins = fold_bins(p->fold);
-    sink.runs = fold_runs(p->fold);
-    sink.nruns = fold_nruns(p->fold);
+    if (fb->fast_k3) {                     // item table of the fused fold epilogue (fastpath.cu); the generic K3 walks the bins
+      sink.runs = fold_runs(p->fold);
+      sink.nruns = fold_nruns(p->fold);
+    }
     sink.nbin = p->desc.nbin;
     // one-bin-per-chunk shortcut of the fold epilogue: measured SLOWER than the per-sample walk on
     // B200 (0.83 vs 0.76 ms per 32 parts of cfg1), so it is opt-in for experiments only
@@ -345,7 +347,7 @@ int b200_pipeline_execute_host(b200_pipeline* p, const void* h_input, uint64_t n
   // arrived, serialising transfer and compute.
   if (p->desc.nbin && chunked && !(fb->F > 8192 && !fb->conv_path)) {
     int rc0 = b200_fold_set_bins(p->fold, phi, pps, npart * fb->nkeep, 0, nullptr);
-    if (rc0 == B200_OK) rc0 = fold_build_runs(p->fold, fb->nkeep, fb->desc.nfilt_pos);
+    if (rc0 == B200_OK && fb->fast_k3) rc0 = fold_build_runs(p->fold, fb->nkeep, fb->desc.nfilt_pos);
     if (rc0 != B200_OK) return rc0;
     p->bins_preset = true;
   }
