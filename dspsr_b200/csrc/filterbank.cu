@@ -869,7 +869,8 @@ int b200_fb_plan_create(b200_context* cctx, const b200_fb_desc* d, b200_fb_plan*
         need = need / gcd(need, g) * g;
         if (need > 64) break;
       }
-      if (need > 1 && need <= 64 && need <= cap) b = need;
+      // ... as long as one spectrum buffer stays below 1.25 GiB (cfg1: 37 x 32 MiB = 1.16 GiB)
+      if (need > 1 && need <= 64 && need <= cap && need * per_part <= (5ull << 28)) b = need;
     }
     pl->batch = d->max_npart ? d->max_npart : unsigned(b);
   }
