@@ -1,5 +1,7 @@
 #!/bin/bash
-# per-kernel ablations: B200_DBGn bit0 = no FFT, bit1 = no epilogue/stores, bit2 = no global loads
+# per-kernel ablations: B200_DBGn bit0 = no FFT, bit1 = no epilogue/stores, bit2 = no global loads.
+# Needs a library built with the switches compiled in:  make -C dspsr_b200/csrc EXTRA=-DB200_ABLATION  (the product build
+# compiles them out; the 32.16.16 plan of K3 has no switches)
 run() { python bench.py --steps 5 --warmup 3 --no-cpu 2>/dev/null | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print('$1', ' '.join('%s %.4f' % (k, v['ms_per_launch']) for k,v in d['kernels'].items()))"; }
 run base
