@@ -7,7 +7,10 @@
 //   K1  k1_c2   pair = two adjacent columns: one 32-bit load carries the 4 raw bytes of both, one
 //               128-bit store writes both
 //   K2  k2_c2   pair = row k1 and its mirror row P-k1 (real input) or two adjacent rows (complex)
-//   K3  k3_c2   pair = the two polarisations of an output channel: detection straight from registers
+//       k2_r32  Q = 1024 planned 32.32, one warp per row (the default for cfg1); writes Z in the tile-major order
+//               zt_pos() that K3 reads with 256-bit loads, with the response pre-permuted into the same order
+//   K3  k3_c2   pair = the two polarisations of an output channel: detection straight from registers; 8192 points
+//               planned 32.16.16; fold epilogue by items of the bin plan (fold.cu k_bin_runs)
 // All three are PERSISTENT: one 512-thread CTA per SM loops over tiles, and the global loads of the
 // next tile are issued into the (by then dead) data registers before the current tile's epilogue,
 // so load latency hides behind the store / split / fold phase instead of adding to it (one tile
