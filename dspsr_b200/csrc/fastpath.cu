@@ -1351,7 +1351,9 @@ int fast_k2(b200_fb_plan* pl, unsigned nb) {
   static const bool r32 = !(getenv("B200_K2_R32") && atoi(getenv("B200_K2_R32")) == 0);
   a.tw32 = pl->c2Q32;
   a.z_tiled = z_tiled(pl) ? 1 : 0;
-  if (getenv("B200_K2_NOH")) a.H = nullptr;   // timing experiment only: results are wrong
+#ifdef B200_ABLATION
+  if (getenv("B200_K2_NOH")) a.H = nullptr;   // timing experiment only (cost of the response stream): results are wrong
+#endif
   if (r32 && pl->c2Q32) {
     if (split) k2_r32<FP_P, true><<<grid, 512, k2r32_smem(), ctx->stream>>>(a);
     else k2_r32<FP_P, false><<<grid, 512, k2r32_smem(), ctx->stream>>>(a);
