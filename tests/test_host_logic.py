@@ -289,3 +289,31 @@ def test_bind_cpu_affinity_is_harmless_without_gpu():
     assert n == 0 or n == len(os.sched_getaffinity(0))
     if n == 0:
         assert os.sched_getaffinity(0) == before
+
+
+def test_tile_major_spectrum_layout_spec():
+    """Executable statement of the tile-major order of Z between K2 and K3 (fastpath.cu zt_pos /
+    k_tile_response): bin k = r + P*k2 -> Z'[tile][side][k2/4][row%8][k2%4].  The map is a bijection onto [0, Nc); a K2
+    tile owns two contiguous 64 KiB regions; the four k2 of one K3 channel and row are one 32-byte group and the 32
+    points of a K3 thread are eight such groups."""
+    P, Q = 2048, 1024
+    r = np.arange(P, dtype=np.int64)[:, None]
+    k2 = np.arange(Q, dtype=np.int64)[None, :]
+    m = np.where(r > P // 2, P - r, r)
+    tile = np.where(r == P // 2, 0, m >> 3)
+    side = np.where(r >= P // 2, 1, 0)
+    g = np.where(r == P // 2, 0, m & 7)
+    pos = (tile * 2 + side) * (Q * 8) + ((k2 >> 2) << 5) + (g << 2) + (k2 & 3)
+    flat = pos.ravel()
+    assert flat.min() == 0 and flat.max() == P * Q - 1 and np.unique(flat).size == P * Q
+    # a K2 tile (rows 8t..8t+7 and their mirrors) = regions [2t, 2t+2) of Q*8 elements = 2 x 64 KiB of float2
+    t = 5
+    rows = np.concatenate([np.arange(8 * t, 8 * t + 8), P - np.arange(8 * t, 8 * t + 8)])
+    got = np.sort(pos[rows].ravel())
+    assert np.array_equal(got, np.arange(2 * t * Q * 8, (2 * t + 2) * Q * 8))
+    # K3: thread (pol, j0) of channel csub holds bins f = j0 + 256 e, e < 32: rows j0 + 256 i (i < 8), k2 = 4 csub + q
+    csub, j0 = 77, 201
+    for i in range(8):
+        row = j0 + 256 * i
+        offs = pos[row, 4 * csub: 4 * csub + 4]
+        assert np.array_equal(offs, offs[0] + np.arange(4)) and offs[0] % 4 == 0      # one aligned 32-byte group
