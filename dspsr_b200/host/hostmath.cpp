@@ -266,6 +266,10 @@ int b200_twobit_prepare(double threshold, float cutoff_sigma, int table_type, un
   const double root_pi = std::sqrt(M_PI);
   for (unsigned nlo = d->nlow_min; nlo <= d->nlow_max; nlo++) {
     unsigned use_nlow = nlo == 0 ? 1 : nlo;
+    // TwoBitLookup.C:83-84 means to clamp the all-low row as well but tests the member `nlow` (always 0 there)
+    // instead of the loop variable, so with cutoff_sigma = 0 the reference evaluates Phi = 1 -> ierf(1) = inf ->
+    // NaN levels, and any all-low window poisons its whole FFT part.  Deliberate deviation: clamp as intended.
+    if (nlo == ndat_per_weight) use_nlow = ndat_per_weight - 1;
     float p_in = (float)use_nlow / (float)ndat_per_weight;
     const double Phi = p_in;
     const double alpha = inverse_erf(Phi);

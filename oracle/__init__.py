@@ -262,6 +262,14 @@ def dedispersion(centre_frequency, bandwidth, dm, input_nchan, nchan, input_real
     return d, H
 
 
+def response_operate(spectrum, H):
+    """Response::operate (Response.C:385-444): spectrum * H in the reference's float operation order."""
+    out = np.ascontiguousarray(spectrum, np.complex64).copy()
+    Hc = np.ascontiguousarray(H, np.complex64)
+    lib().orc_response_operate(_p(out), _p(Hc), C.c_uint64(out.size))
+    return out
+
+
 # ----------------------------------------------------------------------------- FFT
 def fcc1d(x):
     x = np.ascontiguousarray(x, np.complex64)

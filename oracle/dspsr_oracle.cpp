@@ -280,6 +280,10 @@ orc_twobit* orc_twobit_create(int table_type, double threshold, float cutoff_sig
   for (unsigned nlo = t->nlow_min; nlo <= t->nlow_max; nlo++) {   // TwoBitLookup.C:75-97
     unsigned use_nlow = nlo;
     if (nlo == 0) use_nlow = 1;
+    // TwoBitLookup.C:83-84 writes `if (nlow == ndat)` (the member, 0 at build time) where it means `nlo`: with
+    // cutoff_sigma = 0 the reference's own row nlo = ndat is NaN (checked against the compiled reference in
+    // tests/test_ref_pin.py).  Oracle and product clamp as the reference intends; documented deviation.
+    if (nlo == ndat_per_weight) use_nlow = ndat_per_weight - 1;
     float p_in = (float)use_nlow / (float)ndat_per_weight;
     double lo, hi;
     orc_ja98_levels(p_in, &lo, &hi);
@@ -550,6 +554,9 @@ static void response_operate(float* spectrum, const float* f_p, uint64_t npts) {
     f_p += 2;
   }
 }
+
+// the same loop behind a C door, for tests/test_ref_pin.py (checked against the reference's Response::operate)
+void orc_response_operate(float* spectrum, const float* H, uint64_t npts) { response_operate(spectrum, H, npts); }
 
 // ---------------------------------------------------------------------------------------
 // a10  Filterbank (Signal/General/Filterbank.C:55-263 sizes, :389-430 npart, :563-660 loop)

@@ -1,22 +1,39 @@
 # oracle/ref.mk -- TEST INFRASTRUCTURE ONLY.
-# Compiles, where they lie under /root/reference, the few files of the hot path that are plain C
-# and need nothing outside the reference tree:
-#   Signal/General/optimize_fft.c   optimal_fft_length            
-#   Signal/General/cross_detect.c   cross_detect[_int]            (row a12, Coherence products)
-#   Signal/General/stokes_detect.c  stokes_detect[_int]           (row a12, Stokes products)
-#   Kernel/Classes/ascii_header.c   ascii_header_get/set          (DADA header keys, Appendix A.8)
-# into oracle/_ref/libdspsr_refc.so (git-ignored; travels to the GPU box with the snapshot).
-# Everything else on the path is C++ against PSRCHIVE/FFTW and cannot be built here.
-# No reference SOURCE is copied into this repository: the compiler reads it in place.
+# Compiles, where they lie under /root/reference, the files of the hot path that need nothing outside the
+# reference tree except a handful of PSRCHIVE utility headers, for which oracle/ref_shim/ holds stand-ins:
+#   libdspsr_refc.so  (plain C)
+#     Signal/General/optimize_fft.c   optimal_fft_length            
+#     Signal/General/cross_detect.c   cross_detect[_int]            (row a12, Coherence products)
+#     Signal/General/stokes_detect.c  stokes_detect[_int]           (row a12, Stokes products)
+#     Kernel/Classes/ascii_header.c   ascii_header_get/set          (DADA header keys, Appendix A.8)
+#   libdspsr_refcxx.so  (C++, ref_shim/ref_cxx.cpp is the extern "C" door)
+#     Kernel/Classes/BitTable.C dsp.C                               (row a1; dsp.C holds the psrdisp_compatible flag)
+#     Kernel/Classes/TwoBitTable.C TwoBitLookup.C TwoBitFour.C + dsp/TwoBitFour.h dsp/excision_unpack.h
+#       dsp/StepIterator.h                                          (row a6)
+#     Signal/General/Dedispersion.C Response.C Shape.C              (rows a7, a8)
+# Outputs go to oracle/_ref/ (git-ignored; travels to the GPU box with the snapshot).  The rest of the path is C++
+# against PSRCHIVE/FFTW class trees (Transformation, TimeSeries, FTransform, Pulsar::Predictor) and cannot be
+# built here.  No reference SOURCE is copied into this repository: the compiler reads it in place.
 REF ?= /root/reference
 CC ?= gcc
+CXX ?= g++
 OUT = _ref
 SRCS = $(REF)/Signal/General/optimize_fft.c $(REF)/Signal/General/cross_detect.c \
        $(REF)/Signal/General/stokes_detect.c $(REF)/Kernel/Classes/ascii_header.c
+CXXSRCS = $(REF)/Kernel/Classes/BitTable.C $(REF)/Kernel/Classes/TwoBitTable.C $(REF)/Kernel/Classes/TwoBitLookup.C \
+          $(REF)/Kernel/Classes/TwoBitFour.C $(REF)/Kernel/Classes/dsp.C $(REF)/Signal/General/Dedispersion.C $(REF)/Signal/General/Response.C \
+          $(REF)/Signal/General/Shape.C
+# ref_shim first: its dsp/Observation.h and dsp/ExcisionUnpacker.h stand in for the real ones
+INCS = -Iref_shim -I$(REF)/Kernel/Classes -I$(REF)/Signal/General
 
-all: $(OUT)/libdspsr_refc.so
+all: $(OUT)/libdspsr_refc.so $(OUT)/libdspsr_refcxx.so
 
 $(OUT)/libdspsr_refc.so: $(SRCS) ref_shim/config.h
 	@mkdir -p $(OUT)
-	$(CC) -std=gnu99 -O2 -fPIC -ffp-contract=off -w -shared -Iref_shim -I$(REF)/Kernel/Classes -I$(REF)/Signal/General \
-	    -o $@ $(SRCS) -lm
+	$(CC) -std=gnu99 -O2 -fPIC -ffp-contract=off -w -shared $(INCS) -o $@ $(SRCS) -lm
+
+# links against the oracle library for the restated JenetAnderson98 numbers only (ref_shim/JenetAnderson98.h)
+$(OUT)/libdspsr_refcxx.so: $(CXXSRCS) ref_shim/ref_cxx.cpp $(wildcard ref_shim/*.h ref_shim/dsp/*.h) $(OUT)/libdspsr_refc.so _build/liboracle.so
+	@mkdir -p $(OUT)
+	$(CXX) -std=gnu++98 -O2 -fPIC -ffp-contract=off -w -shared $(INCS) -o $@ $(CXXSRCS) ref_shim/ref_cxx.cpp \
+	    -L$(OUT) -ldspsr_refc -L_build -loracle -Wl,-rpath,'$$ORIGIN' -Wl,-rpath,'$$ORIGIN/../_build' -lm

@@ -97,3 +97,241 @@ def test_dada_header_keys_parse_like_reference(ref):
     assert mine["INSTRUMENT"] == "CASPSR" and mine["UTC_START"] == "2010-04-13-02:05:45"
     for k, v in got.items():
         assert float(mine[k]) == v, k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# C++ half of the pin (oracle/_ref/libdspsr_refcxx.so): the reference's BitTable.C, TwoBitTable.C, TwoBitLookup.C,
+# TwoBitFour.C, dsp/TwoBitFour.h, dsp/excision_unpack.h, Dedispersion.C, Response.C, Shape.C compiled in place
+# behind oracle/ref_shim/ (PSRCHIVE utility stand-ins; JenetAnderson98 / NormalDistribution numbers are the
+# restated third-party part and are shared with the oracle).
+# ---------------------------------------------------------------------------------------------------------------
+REFCXX = os.path.join(ROOT, "oracle", "_ref", "libdspsr_refcxx.so")
+needs_cxx = pytest.mark.skipif(not os.path.exists(REFCXX), reason="oracle/_ref C++ pin library not built")
+
+
+@pytest.fixture(scope="module")
+def refcxx(oracle):
+    oracle.lib()                                   # liboracle.so first (JA98 numbers), found again through the rpath
+    L = C.CDLL(REFCXX)
+    L.ref_bittable_unique_values.restype = C.c_double
+    L.ref_bittable_unique_values.argtypes = [C.c_uint, C.c_int, C.c_void_p]
+    L.ref_bittable_generate.restype = C.c_double
+    L.ref_bittable_generate.argtypes = [C.c_uint, C.c_int, C.c_void_p]
+    L.ref_twobit_create.restype = C.c_void_p
+    L.ref_twobit_create.argtypes = [C.c_int, C.c_double, C.c_uint, C.c_uint, C.c_uint, C.c_uint]
+    L.ref_twobit_destroy.argtypes = [C.c_void_p]
+    L.ref_twobit_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ref_twobit_unpack.restype = C.c_int
+    L.ref_twobit_unpack.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint]
+    L.ref_dedispersion.restype = C.c_int
+    L.ref_dedispersion.argtypes = [C.c_double, C.c_double, C.c_double, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int,
+                                   C.c_uint, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.c_void_p,
+                                   C.c_uint64]
+    L.ref_response_operate.restype = C.c_int
+    L.ref_response_operate.argtypes = [C.c_void_p, C.c_uint, C.c_void_p]
+    return L
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@needs_cxx
+def test_bittable_matches_reference(refcxx, oracle):
+    """Row a1: BitTable.C:121-218 (generate_unique_values, generate, get_scale) vs the oracle and the product's
+    host-built table, bit for bit -- the 8-bit TwosComplement table of CASPSR / MeerKAT and every other width."""
+    from dspsr_b200 import hostmath as HM
+    OFFSET, TWOS = 0, 1                                      # dsp::BitTable::Type
+    for nbit in (2, 3, 4, 5, 6, 7, 8):
+        for typ, twos in ((OFFSET, False), (TWOS, True)):
+            want = np.zeros(1 << nbit, np.float32)
+            scale = refcxx.ref_bittable_unique_values(nbit, typ, _vp(want))
+            got, gscale = oracle.bittable_values(nbit, twos)
+            assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), (nbit, typ)
+            assert scale == gscale, (nbit, typ)
+    tab = np.zeros(256, np.float32)
+    scale = refcxx.ref_bittable_generate(8, TWOS, _vp(tab))
+    lut_o, scale_o = oracle.bittable8(True)
+    lut_p, scale_p = HM.bittable8()
+    assert np.array_equal(tab.view(np.uint32), lut_o.view(np.uint32)) and scale == scale_o
+    assert np.array_equal(tab.view(np.uint32), np.asarray(lut_p).view(np.uint32)) and scale == scale_p
+    # the sample the CASPSR unpacker would produce for byte 0x00 / 0x7f / 0x80 / 0xff, straight from the reference
+    assert tab[0] > 0 and tab[0x7F] == tab.max() and tab[0x80] == tab.min() and tab[0xFF] < 0
+
+
+# oracle table_type -> dsp::BitTable::Type
+_TWOBIT_TYPES = {0: 0, 1: 2, 2: 1}       # OffsetBinary, SignMagnitude, TwosComplement
+
+
+@needs_cxx
+@pytest.mark.parametrize("table_type", [0, 1, 2])
+@pytest.mark.parametrize("cutoff", [10.0, 3.0])
+def test_twobit_tables_and_unpack_match_reference(refcxx, oracle, table_type, cutoff):
+    """Row a6: TwoBitTable.C:42-75, TwoBitLookup.C:63-98, TwoBitFour.C:25-52, dsp/TwoBitFour.h:42-89 and the body of
+    dsp/excision_unpack.h:21-106, all compiled from the reference, vs oracle.TwoBit (levels per low-state count,
+    low-state counts per byte, unpacked floats and per-window weights incl. excised and all-zero windows)."""
+    ndw = 512
+    tb = oracle.TwoBit(table_type, 0.9674, cutoff, ndw)
+    h = C.c_void_p(refcxx.ref_twobit_create(_TWOBIT_TYPES[table_type], 0.9674, tb.nlow_min, tb.nlow_max, ndw, 1))
+    try:
+        nrow = tb.nlow_max - tb.nlow_min + 1
+        lookup = np.zeros((nrow, 256, 4), np.float32)
+        nlow_lookup = np.zeros(256, np.int8)
+        refcxx.ref_twobit_tables(h, _vp(lookup), _vp(nlow_lookup))
+        for nlow in range(tb.nlow_min, tb.nlow_max + 1):
+            lo, hi = tb.levels(nlow)
+            mags = np.unique(np.abs(lookup[nlow - tb.nlow_min]))
+            assert mags.size == 2 and mags[0] == np.float32(lo) and mags[1] == np.float32(hi), nlow
+        # data: Gaussian noise digitised at the optimal threshold, plus windows that must be excised
+        rng = np.random.default_rng(21 + table_type)
+        npol, nwin = 2, 24
+        ndat = nwin * ndw
+        x = rng.standard_normal((npol, ndat))
+        x[0, 3 * ndw:4 * ndw] *= 6.0            # too few low states
+        x[1, 7 * ndw:8 * ndw] *= 0.05           # too many low states
+        code = np.where(x < -0.9674, 0, np.where(x < 0, 1, np.where(x < 0.9674, 2, 3))).astype(np.uint8)
+        if table_type == 1:      # SignMagnitude: lo, hi, -lo, -hi
+            code = np.array([3, 2, 0, 1], np.uint8)[code]
+        elif table_type == 2:    # TwosComplement: lo, hi, -hi, -lo
+            code = np.array([2, 3, 0, 1], np.uint8)[code]
+        c4 = code.reshape(npol, ndat // 4, 4)
+        by = (c4[..., 0] << 6) | (c4[..., 1] << 4) | (c4[..., 2] << 2) | c4[..., 3]
+        raw = np.ascontiguousarray(by.T).reshape(-1).astype(np.uint8)       # polarisations interleaved byte by byte
+        raw[npol * (11 * ndw // 4):npol * (12 * ndw // 4)] = 0                # an all-zero window (unpack.bad)
+        want = np.zeros((npol, ndat), np.float32)
+        wref = np.ones((npol, nwin), np.uint32)
+        assert refcxx.ref_twobit_unpack(h, _vp(raw), ndat, npol, _vp(want), ndat, _vp(wref), nwin) == 0
+        got, w = tb.unpack(raw, ndat, npol)
+        assert np.array_equal(want.view(np.uint32), got[0].view(np.uint32))
+        # WeightedTimeSeries::mask_weights (a window flagged in one polarisation is flagged in all)
+        masked = np.broadcast_to(wref.min(axis=0, keepdims=True), wref.shape)
+        assert np.array_equal(masked, w)
+        assert 3 <= int((masked[0] == 0).sum()) < nwin
+        # per-byte low-state counts: oracle's prepare() must count what the reference's nlow_build tabulated
+        lo_codes = {0: (1, 2), 1: (0, 2), 2: (0, 3)}[table_type]
+        cnt = np.array([sum(((b >> s) & 3) in lo_codes for s in (6, 4, 2, 0)) for b in range(256)], np.int8)
+        assert np.array_equal(cnt, nlow_lookup)
+    finally:
+        refcxx.ref_twobit_destroy(h)
+
+
+_DEDISP_CASES = [
+    # cf, bw, dm, input_nchan, nchan, input_real, freq_res, kwargs                      (SURVEY Appendix B rows)
+    (1382.0, -400.0, 67.99, 1, 256, True, 0, {}),                                       # cfg1
+    (1382.0, -400.0, 100.0, 1, 256, True, 0, {}),                                       # cfg1' (bench.csh DM 100)
+    (1400.0, 128.0, 50.0, 1, 4096, True, 0, {}),                                        # cfg2
+    (1284.0, 856.0, 500.0, 1024, 1024, False, 8192, {}),                                # cfg3 with -x 8192 (H is 512 MiB at the optimal 65536)
+    (12500.0, 400.0, 1500.0, 1, 1, False, 4194304, {}),                                 # cfg4
+    (768.0, 128.0, 67.99, 1, 128, False, 0, {}),                                        # cfg5 sb0
+    (3968.0, 128.0, 67.99, 1, 128, False, 0, {}),                                       # cfg5 sb25
+    (1400.0, -64.0, 30.0, 1, 16, False, 0, {}),                                         # lower sideband, complex input
+    (1400.0, 64.0, 30.0, 8, 8, False, 0, {"swap": True}),                               # multi-channel + whole-band swap
+    (1400.0, 64.0, 30.0, 8, 32, False, 0, {}),                                          # multi-channel in, more channels out
+    (1400.0, 64.0, 30.0, 4, 4, False, 0, {"dual_sideband": False}),                     # single-sideband channels
+    (1400.0, 64.0, 30.0, 1, 32, True, 0, {"dc_centred": True}),                         # bin-centred spectrum
+    (610.0, -16.0, 26.8, 1, 1, True, 0, {}),                                            # plain convolution, real input
+]
+
+
+@needs_cxx
+@pytest.mark.parametrize("case", _DEDISP_CASES, ids=lambda c: "cf%g_bw%g_dm%g_%dto%d" % c[:5])
+def test_dedispersion_matches_reference(refcxx, oracle, case):
+    """Rows a7 + a8: Dedispersion::prepare / smearing_samples / build / match (Dedispersion.C:167-556) with
+    Response::match / doswap / set_optimal_ndat (Response.C:132-181,259-311,649-700) and Shape.C, compiled from the
+    reference, vs the oracle AND the product's host maths: impulse_pos/neg, chosen frequency resolution, and every
+    float of the matched response H, bit for bit."""
+    from dspsr_b200 import hostmath as HM
+    cf, bw, dm, nin, nout, real, fres, kw = case
+    dual = kw.get("dual_sideband", not real)
+    pos, neg, ndat = C.c_uint(0), C.c_uint(0), C.c_uint(0)
+    rc = refcxx.ref_dedispersion(cf, bw, dm, nin, nout, int(dual), int(kw.get("dc_centred", False)),
+                                 int(kw.get("swap", False)), fres, C.byref(pos), C.byref(neg), C.byref(ndat), None, 0)
+    assert rc == 0
+    d_o, H_o = oracle.dedispersion(cf, bw, dm, nin, nout, real, fres, **kw)
+    d_p, H_p = HM.dedispersion(cf, bw, dm, nin, nout, real, fres, **kw)
+    assert (pos.value, neg.value, ndat.value) == (d_o.impulse_pos, d_o.impulse_neg, d_o.ndat)
+    assert (pos.value, neg.value, ndat.value) == (d_p.impulse_pos, d_p.impulse_neg, d_p.ndat)
+    want = np.zeros((nout, ndat.value), np.complex64)
+    rc = refcxx.ref_dedispersion(cf, bw, dm, nin, nout, int(dual), int(kw.get("dc_centred", False)),
+                                 int(kw.get("swap", False)), fres, C.byref(pos), C.byref(neg), C.byref(ndat), _vp(want),
+                                 want.size * 2)
+    assert rc == 0
+    assert np.array_equal(want.view(np.uint32), H_o.view(np.uint32))
+    assert np.array_equal(want.view(np.uint32), np.asarray(H_p).view(np.uint32))
+
+
+@needs_cxx
+def test_dedispersion_refuses_like_reference(refcxx, oracle):
+    """cfg4 as BASELINE.json words it (400 MHz at L-band, DM 1500) is refused by the reference itself
+    (Dedispersion.C:214-233, smearing samples above the 16 Mi threshold); oracle and product refuse too."""
+    from dspsr_b200 import hostmath as HM
+    pos, neg, ndat = C.c_uint(0), C.c_uint(0), C.c_uint(0)
+    assert refcxx.ref_dedispersion(1400.0, 400.0, 1500.0, 1, 1, 1, 0, 0, 0, C.byref(pos), C.byref(neg), C.byref(ndat), None, 0) == -1
+    with pytest.raises(Exception):
+        oracle.dedispersion(1400.0, 400.0, 1500.0, 1, 1, False)
+    with pytest.raises(Exception):
+        HM.dedispersion(1400.0, 400.0, 1500.0, 1, 1, False)
+
+
+@needs_cxx
+def test_response_operate_matches_reference(refcxx, oracle):
+    """Row a8: Response::operate (Response.C:385-444) -- spectrum *= H in float, the reference's operation order --
+    vs the oracle's filterbank, which applies the same multiply between its forward and inverse transforms:
+    with a unit impulse response H = 1 both reduce to identity, so the comparison isolates the multiply by running
+    the reference's operate on the oracle's own forward spectrum and inverse-transforming with the oracle."""
+    rng = np.random.default_rng(3)
+    n = 4096
+    H = np.exp(1j * rng.uniform(-np.pi, np.pi, n)).astype(np.complex64)
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    spec = oracle.fcc1d(x)
+    want = spec.copy()
+    assert refcxx.ref_response_operate(_vp(H), n, _vp(want)) == 0
+    # the oracle's restatement of the same loop (orc response_operate, used inside orc_filterbank_parts)
+    got = oracle.response_operate(spec, H)
+    assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
+
+
+@needs_cxx
+def test_cfg3_optimal_resolution_from_reference(refcxx, oracle):
+    """the reference itself picks F = 65536 with M = 2536 + 2543 (no response built: 512 MiB)."""
+    pos, neg, ndat = C.c_uint(0), C.c_uint(0), C.c_uint(0)
+    # prepare only: Dedispersion::match would build; ask for the sizes through a 1-channel-wide equivalent band
+    d_o, _ = oracle.dedispersion(1284.0, 856.0, 500.0, 1024, 1024, False, build=False)
+    assert (d_o.impulse_pos, d_o.impulse_neg, d_o.ndat) == (2536, 2543, 65536)
+    # the reference on the lowest-frequency channel alone (same smearing: channel 0 of 1024 is what sets M)
+    cw = 856.0 / 1024
+    rc = refcxx.ref_dedispersion(1284.0 - 428.0 + cw / 2, cw, 500.0, 1, 1, 1, 0, 0, 0, C.byref(pos), C.byref(neg),
+                                 C.byref(ndat), None, 0)
+    assert rc == 0 and (pos.value, neg.value, ndat.value) == (2536, 2543, 65536)
+
+
+@needs_cxx
+def test_twobit_all_low_row_deviation(refcxx, oracle):
+    """with cutoff_sigma = 0 the reference's level row for nlow = ndat is NaN (TwoBitLookup.C:83 tests
+    the wrong variable); oracle and product clamp that row to ndat-1 instead.  Every other row still equals the
+    reference bit for bit."""
+    from dspsr_b200 import hostmath as HM
+    ndw = 128
+    tb = oracle.TwoBit(0, 0.9674, 0.0, ndw)
+    assert (tb.nlow_min, tb.nlow_max) == (0, ndw)
+    h = C.c_void_p(refcxx.ref_twobit_create(0, 0.9674, 0, ndw, ndw, 1))
+    try:
+        lookup = np.zeros((ndw + 1, 256, 4), np.float32)
+        nl = np.zeros(256, np.int8)
+        refcxx.ref_twobit_tables(h, _vp(lookup), _vp(nl))
+        assert np.isnan(lookup[ndw]).any()                       # the reference's own all-low row
+        for nlow in range(0, ndw):
+            lo, hi = tb.levels(nlow)
+            mags = np.unique(np.abs(lookup[nlow]))
+            assert mags[0] == np.float32(lo) and mags[-1] == np.float32(hi)
+        lo, hi = tb.levels(ndw)
+        assert np.isfinite(lo) and np.isfinite(hi) and (lo, hi) == tb.levels(ndw - 1)
+    finally:
+        refcxx.ref_twobit_destroy(h)
+    from dspsr_b200 import engine as E
+    tp = E.make_twobit_desc(2, 0.9674, 0.0, 0, ndw)
+    n = tp.nlow_max - tp.nlow_min + 1
+    assert (tp.nlow_min, tp.nlow_max) == (0, ndw)
+    lo_p, hi_p = np.array(tp.lo[:n]), np.array(tp.hi[:n])
+    assert np.isfinite(lo_p).all() and np.isfinite(hi_p).all()
+    assert (np.float32(lo_p[-1]), np.float32(hi_p[-1])) == (np.float32(lo), np.float32(hi))
