@@ -37,3 +37,14 @@ $(OUT)/libdspsr_refcxx.so: $(CXXSRCS) ref_shim/ref_cxx.cpp $(wildcard ref_shim/*
 	@mkdir -p $(OUT)
 	$(CXX) -std=gnu++98 -O2 -fPIC -ffp-contract=off -w -shared $(INCS) -o $@ $(CXXSRCS) ref_shim/ref_cxx.cpp \
 	    -L$(OUT) -ldspsr_refc -L_build -loracle -Wl,-rpath,'$$ORIGIN' -Wl,-rpath,'$$ORIGIN/../_build' -lm
+
+# libdspsr_reffmt.so: the format unpackers (rows a2, a4, a5).  Their own first-level headers are the reference's;
+# dsp/EightBitUnpacker.h / dsp/HistUnpacker.h resolve to the ref_shim stand-ins.
+FMT = $(REF)/Kernel/Formats
+FMTSRCS = $(FMT)/caspsr/CASPSRUnpacker.C $(FMT)/kat/MeerKATUnpacker.C $(FMT)/uwb/UWBUnpacker.C $(REF)/Kernel/Classes/BitTable.C
+all: $(OUT)/libdspsr_reffmt.so
+$(OUT)/libdspsr_reffmt.so: $(FMTSRCS) ref_shim/ref_formats.cpp $(wildcard ref_shim/*.h ref_shim/dsp/*.h) _build/liboracle.so
+	@mkdir -p $(OUT)
+	$(CXX) -std=gnu++98 -O2 -fPIC -ffp-contract=off -w -shared -Iref_shim -I$(FMT)/caspsr -I$(FMT)/kat -I$(FMT)/uwb \
+	    -I$(REF)/Kernel/Classes -o $@ $(FMTSRCS) ref_shim/ref_formats.cpp \
+	    -L_build -loracle -Wl,-rpath,'$$ORIGIN/../_build' -lm -lpthread

@@ -335,3 +335,71 @@ def test_twobit_all_low_row_deviation(refcxx, oracle):
     lo_p, hi_p = np.array(tp.lo[:n]), np.array(tp.hi[:n])
     assert np.isfinite(lo_p).all() and np.isfinite(hi_p).all()
     assert (np.float32(lo_p[-1]), np.float32(hi_p[-1])) == (np.float32(lo), np.float32(hi))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Format unpackers (oracle/_ref/libdspsr_reffmt.so): the reference's CASPSRUnpacker.C, MeerKATUnpacker.C and
+# UWBUnpacker.C compiled in place; their unpack() bodies run on the same seeded bytes as the oracle.
+# ---------------------------------------------------------------------------------------------------------------
+REFFMT = os.path.join(ROOT, "oracle", "_ref", "libdspsr_reffmt.so")
+needs_fmt = pytest.mark.skipif(not os.path.exists(REFFMT), reason="oracle/_ref format pin library not built")
+
+
+@pytest.fixture(scope="module")
+def reffmt(oracle):
+    oracle.lib()
+    L = C.CDLL(REFFMT)
+    L.ref_unpack_caspsr.restype = C.c_int
+    L.ref_unpack_caspsr.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    L.ref_unpack_meerkat.restype = C.c_int
+    L.ref_unpack_meerkat.argtypes = [C.c_void_p, C.c_uint64, C.c_uint, C.c_uint, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_float)]
+    L.ref_unpack_uwb.restype = C.c_int
+    L.ref_unpack_uwb.argtypes = [C.c_void_p, C.c_uint64, C.c_uint, C.c_void_p, C.c_uint64]
+    return L
+
+
+@needs_fmt
+def test_caspsr_unpack_matches_reference(reffmt, oracle):
+    """Row a2: CASPSRUnpacker.C:132-187 (4 samples pol0, 4 samples pol1 per 8 bytes, BitTable look-up), every byte value."""
+    rng = np.random.default_rng(31)
+    ndat = 1024 * 5
+    raw = rng.integers(0, 256, 2 * ndat, dtype=np.uint8)
+    raw[:256] = np.arange(256, dtype=np.uint8)
+    want = np.zeros((1, 2, ndat), np.float32)
+    assert reffmt.ref_unpack_caspsr(_vp(raw), ndat, _vp(want), ndat) == 0
+    lut, _ = oracle.bittable8(True)
+    got = oracle.unpack_caspsr(raw, ndat, lut)
+    assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
+
+
+@needs_fmt
+@pytest.mark.parametrize("npol,swap", [(2, 1), (2, 2), (1, 1)])
+def test_meerkat_unpack_matches_reference(reffmt, oracle, npol, swap):
+    """Row a4: MeerKATUnpacker.C:196-229 (heaps of 256 samples, [heap][pol][chan][256 x (re, im)], (float(x) + 0.5) * scale,
+    MKBFRo sample swap) and the scale the reference derives from its BitTable."""
+    rng = np.random.default_rng(32)
+    nchan, nheap = 12, 3
+    ndat = 256 * nheap
+    raw = rng.integers(0, 256, ndat * nchan * npol * 2, dtype=np.uint8)
+    raw[:256] = np.arange(256, dtype=np.uint8)
+    want = np.zeros((nchan, npol, ndat * 2), np.float32)
+    scale = C.c_float(0)
+    assert reffmt.ref_unpack_meerkat(_vp(raw), ndat, nchan, npol, swap, _vp(want), ndat * 2, C.byref(scale)) == 0
+    _, tscale = oracle.bittable8(True)
+    assert np.float32(tscale) == np.float32(scale.value)
+    got = oracle.unpack_meerkat(raw.view(np.int8), ndat, nchan, npol, np.float32(tscale), swap)
+    assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
+
+
+@needs_fmt
+@pytest.mark.parametrize("npol", [2, 1])
+def test_uwb_unpack_matches_reference(reffmt, oracle, npol):
+    """Row a5: UWBUnpacker.C:177-218 (blocks of 2048 samples per polarisation, offset-binary 16 bit, no scaling)."""
+    rng = np.random.default_rng(33)
+    ndat = 2048 * 3
+    raw = rng.integers(0, 65536, ndat * npol * 2, dtype=np.uint16)
+    raw[:8] = [0, 1, 0x7FFF, 0x8000, 0x8001, 0xFFFF, 0x1234, 0xFEDC]
+    want = np.zeros((1, npol, ndat * 2), np.float32)
+    assert reffmt.ref_unpack_uwb(_vp(raw), ndat, npol, _vp(want), ndat * 2) == 0
+    got = oracle.unpack_uwb(raw.view(np.int16), ndat, npol)
+    assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
