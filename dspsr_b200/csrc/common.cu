@@ -198,6 +198,11 @@ int b200_memset(b200_context* c, void* d_ptr, int value, uint64_t nbytes) {
   B200_CUDA(cudaMemsetAsync(d_ptr, value, nbytes, c->stream));
   return B200_OK;
 }
+int b200_memcpy_d2d(b200_context* c, void* d_dst, const void* d_src, uint64_t nbytes) {
+  B200_REQUIRE(c, "null context");
+  B200_CUDA(cudaMemcpyAsync(d_dst, d_src, nbytes, cudaMemcpyDeviceToDevice, c->stream));
+  return B200_OK;
+}
 int b200_memcpy_h2d(b200_context* c, void* d_dst, const void* h_src, uint64_t nbytes) {
   B200_REQUIRE(c, "null context");
   B200_CUDA(cudaMemcpyAsync(d_dst, h_src, nbytes, cudaMemcpyHostToDevice, c->stream));

@@ -873,6 +873,15 @@ int b200_fb_plan_create(b200_context* cctx, const b200_fb_desc* d, b200_fb_plan*
       if (need > 1 && need <= 64 && need <= cap && need * per_part <= (5ull << 28)) b = need;
     }
     pl->batch = d->max_npart ? d->max_npart : unsigned(b);
+    // the generic kernels index (part, input channel, polarisation) blocks through grid.y (limit 65535): a
+    // 4096-channel dual-pol input allows 7 parts per launch, not 16
+    const uint64_t blocks_per_part = uint64_t(d->input_nchan) * d->npol;
+    if (blocks_per_part > 65535) {
+      b200_fb_plan_destroy(pl);
+      set_error("input_nchan*npol = %llu exceeds the 65535 blocks one launch can index", (unsigned long long)blocks_per_part);
+      return B200_ERR_UNSUPPORTED;
+    }
+    pl->batch = unsigned(std::min<uint64_t>(pl->batch, 65535 / blocks_per_part));
   }
 
   int rc = plan_set_attributes(size_t(ctx->max_smem_optin));

@@ -293,6 +293,7 @@ struct FoldArgs {
   uint64_t in_span, idat_start, ndat;
   const unsigned* bins;
   float* profile;
+  uint64_t prof_span;            // floats between the planes of the profile (nbin*ndim when the handle owns it)
   unsigned nchan, npol, ndim, nbin, slab;
   unsigned smem_bins;
 };
@@ -304,7 +305,7 @@ __global__ void k_fold(FoldArgs a) {
   const uint64_t s0 = uint64_t(blockIdx.x) * a.slab;
   const uint64_t s1 = min(a.ndat, s0 + a.slab);
   const float* tp = a.in + uint64_t(plane) * a.in_span + a.idat_start * NDIM;
-  float* prof = a.profile + uint64_t(plane) * a.nbin * NDIM;
+  float* prof = a.profile + uint64_t(plane) * a.prof_span;
   if (a.smem_bins) {
     for (unsigned i = threadIdx.x; i < a.nbin * NDIM; i += blockDim.x) sbins[i] = 0.f;
     __syncthreads();
@@ -609,14 +610,14 @@ int b200_fold_get_bin_hits(b200_fold* f, unsigned* h_hits) {
   return B200_OK;
 }
 
-int b200_fold_fold(b200_fold* f, const float* d_in, uint64_t in_span) {
-  B200_REQUIRE(f && d_in, "b200_fold_fold: null argument");
+static int fold_into(b200_fold* f, const float* d_in, uint64_t in_span, float* d_out, uint64_t out_span) {
   Context* ctx = f->ctx;
   if (f->ndat == 0) return B200_OK;
   B200_REQUIRE(f->d_bins, "b200_fold_fold: set_bins has not been called");
   FoldArgs a;
   a.in = d_in; a.in_span = in_span; a.idat_start = f->idat_start; a.ndat = f->ndat; a.bins = f->d_bins;
-  a.profile = f->d_profile; a.nchan = f->nchan; a.npol = f->npol; a.ndim = f->ndim; a.nbin = f->nbin;
+  a.profile = d_out; a.prof_span = out_span;
+  a.nchan = f->nchan; a.npol = f->npol; a.ndim = f->ndim; a.nbin = f->nbin;
   const unsigned threads = 256;
   const unsigned nplane = f->nchan * f->npol;
   // slabs so that the grid fills the machine a few times over
@@ -627,13 +628,31 @@ int b200_fold_fold(b200_fold* f, const float* d_in, uint64_t in_span) {
   size_t smem = size_t(f->nbin) * f->ndim * sizeof(float);
   a.smem_bins = smem <= 48 * 1024 ? 1 : 0;
   if (!a.smem_bins) smem = 0;
-  dim3 grid(gx, nplane);
   LaunchScope ls(ctx, KC_OTHER);
-  if (f->ndim == 4) k_fold<4><<<grid, threads, smem, ctx->stream>>>(a);
-  else if (f->ndim == 2) k_fold<2><<<grid, threads, smem, ctx->stream>>>(a);
-  else k_fold<1><<<grid, threads, smem, ctx->stream>>>(a);
+  // planes beyond the 65535 limit of grid.y go in further launches
+  for (unsigned p0 = 0; p0 < nplane; p0 += 65535u) {
+    const unsigned np = std::min(65535u, nplane - p0);
+    FoldArgs b = a;
+    b.in = a.in + uint64_t(p0) * in_span;
+    b.profile = a.profile + uint64_t(p0) * out_span;
+    dim3 grid(gx, np);
+    if (f->ndim == 4) k_fold<4><<<grid, threads, smem, ctx->stream>>>(b);
+    else if (f->ndim == 2) k_fold<2><<<grid, threads, smem, ctx->stream>>>(b);
+    else k_fold<1><<<grid, threads, smem, ctx->stream>>>(b);
+  }
   B200_CUDA(cudaGetLastError());
   return B200_OK;
+}
+
+int b200_fold_fold(b200_fold* f, const float* d_in, uint64_t in_span) {
+  B200_REQUIRE(f && d_in, "b200_fold_fold: null argument");
+  return fold_into(f, d_in, in_span, f->d_profile, uint64_t(f->nbin) * f->ndim);
+}
+
+int b200_fold_fold_into(b200_fold* f, const float* d_in, uint64_t in_span, float* d_out, uint64_t out_span) {
+  B200_REQUIRE(f && d_in && d_out, "b200_fold_fold_into: null argument");
+  B200_REQUIRE(out_span >= uint64_t(f->nbin) * f->ndim, "b200_fold_fold_into: out_span smaller than nbin*ndim");
+  return fold_into(f, d_in, in_span, d_out, out_span);
 }
 
 int b200_fold_synch(b200_fold* f, float* h_profile) {

@@ -25,6 +25,51 @@ void* DeviceMemory::do_allocate(size_t nbytes) {
   return p;
 }
 void DeviceMemory::do_free(void* p) { b200_free(ctx, p); }
+void DeviceMemory::do_zero(void* p, size_t nbytes) { check(b200_memset(ctx, p, 0, nbytes), "B200::DeviceMemory::do_zero"); }
+void DeviceMemory::do_copy(void* to, const void* from, size_t nbytes) {
+  check(b200_memcpy_d2d(ctx, to, from, nbytes), "B200::DeviceMemory::do_copy");
+}
+
+// ---- Unpacker device hooks ----------------------------------------------------------------------
+// Both engines receive device pointers: the BitSeries was loaded with File::load_bytes_device and the unpacked
+// TimeSeries lives in DeviceMemory (SingleThread.C:249-275).
+void MeerKATUnpackerEngine::unpack(float scale, const dsp::BitSeries* input, dsp::TimeSeries* output, unsigned sample_swap) {
+  b200_unpack_desc d;
+  d.format = B200_FMT_MEERKAT8;
+  d.nchan = input->get_nchan();
+  d.npol = input->get_npol();
+  d.ndim = 2;
+  d.scale = scale;
+  d.sample_swap = sample_swap;
+  d.twobit = 0;
+  check(b200_unpack(ctx, &d, input->get_rawptr(), input->get_ndat(), output->get_datptr(0, 0), output->get_nfloat_span()),
+        "B200::MeerKATUnpackerEngine::unpack");
+}
+bool MeerKATUnpackerEngine::get_device_supported(dsp::Memory* memory) const { return dynamic_cast<DeviceMemory*>(memory) != 0; }
+void MeerKATUnpackerEngine::set_device(dsp::Memory* memory) {
+  DeviceMemory* m = dynamic_cast<DeviceMemory*>(memory);
+  if (!m) throw Error(InvalidState, "B200::MeerKATUnpackerEngine::set_device", "not a B200::DeviceMemory");
+  ctx = m->get_context();
+}
+
+void UWBUnpackerEngine::unpack(const dsp::BitSeries* input, dsp::TimeSeries* output) {
+  b200_unpack_desc d;
+  d.format = B200_FMT_UWB16;
+  d.nchan = 1;
+  d.npol = input->get_npol();
+  d.ndim = 2;
+  d.scale = 0;
+  d.sample_swap = 1;
+  d.twobit = 0;
+  check(b200_unpack(ctx, &d, input->get_rawptr(), input->get_ndat(), output->get_datptr(0, 0), output->get_nfloat_span()),
+        "B200::UWBUnpackerEngine::unpack");
+}
+bool UWBUnpackerEngine::get_device_supported(dsp::Memory* memory) const { return dynamic_cast<DeviceMemory*>(memory) != 0; }
+void UWBUnpackerEngine::set_device(dsp::Memory* memory) {
+  DeviceMemory* m = dynamic_cast<DeviceMemory*>(memory);
+  if (!m) throw Error(InvalidState, "B200::UWBUnpackerEngine::set_device", "not a B200::DeviceMemory");
+  ctx = m->get_context();
+}
 
 // ---- Filterbank ---------------------------------------------------------------------------------
 FilterbankEngine::~FilterbankEngine() { b200_fb_plan_destroy(plan); }
@@ -115,15 +160,19 @@ void DetectionEngine::square_law(const dsp::TimeSeries* in, dsp::TimeSeries* out
 // ---- Fold ---------------------------------------------------------------------------------------
 FoldEngine::FoldEngine(b200_context* c) : ctx(c), handle(0), nbin(0), ndat_folded(0) {
   use_set_bins = true;   // Fold::fold then calls set_bins once per block instead of set_bin per sample
+  // as CUDA::FoldEngine (FoldCUDA.cu:43-44): the accumulating PhaseSeries belongs to the engine and lives on the device
   device_profiles = new dsp::PhaseSeries;
+  device_profiles->set_memory(new DeviceMemory(ctx));
+  synchronized = true;   // no data on either side yet (FoldCUDA.cu:53-54)
 }
 FoldEngine::~FoldEngine() { b200_fold_destroy(handle); }
 
 void FoldEngine::set_nbin(unsigned n) { nbin = n; }
 
 void FoldEngine::ensure() {
+  setup();   // fills nchan, npol, ndim, input, input_span, output, output_span from the parent (Fold.C:973-1011);
+             // the input pointer may change from block to block
   if (handle) return;
-  setup();   // fills nchan, npol, ndim, input, input_span from the parent (Fold.C:973-1011)
   check(b200_fold_create(ctx, nchan, npol, ndim, nbin, &handle), "B200::FoldEngine");
 }
 
@@ -135,7 +184,6 @@ void FoldEngine::set_bin(uint64_t, double, double) {
 
 uint64_t FoldEngine::set_bins(double phi, double phase_per_sample, uint64_t ndat, uint64_t idat0) {
   ensure();
-  setup();   // the input pointer may change from block to block
   check(b200_fold_set_bins(handle, phi, phase_per_sample, ndat, idat0, &ndat_folded), "B200::FoldEngine::set_bins");
   last_hits.resize(nbin);
   check(b200_fold_get_bin_hits(handle, last_hits.data()), "B200::FoldEngine::set_bins");
@@ -145,27 +193,29 @@ uint64_t FoldEngine::set_bins(double phi, double phase_per_sample, uint64_t ndat
 
 uint64_t FoldEngine::get_bin_hits(int ibin) { return last_hits[ibin]; }
 
-dsp::PhaseSeries* FoldEngine::get_profiles() { return parent ? parent->get_output() : device_profiles.get(); }
+// Never parent->get_output(): the reference's Fold::get_output() IS engine->get_profiles() (Fold.C:88-94)
+dsp::PhaseSeries* FoldEngine::get_profiles() { return device_profiles; }
 
 void FoldEngine::fold() {
-  check(b200_fold_fold(handle, input, input_span), "B200::FoldEngine::fold");
+  // `output` / `output_span` are the engine-owned PhaseSeries' device buffer and plane span (Fold::Engine::setup)
+  check(b200_fold_fold_into(handle, input, input_span, output, output_span), "B200::FoldEngine::fold");
 }
 
 void FoldEngine::synch(dsp::PhaseSeries* out) {
-  if (synchronized || !handle) return;   // idempotent, as FoldCUDA.cu:132-147
-  // the stand-in PhaseSeries keeps [chan][pol][bin][dim] planes with span nbin*ndim: copy plane by plane
-  std::vector<float> tmp(size_t(nchan) * npol * nbin * ndim);
-  check(b200_fold_synch(handle, tmp.data()), "B200::FoldEngine::synch");
-  for (unsigned c = 0; c < nchan; c++)
-    for (unsigned p = 0; p < npol; p++) {
-      float* dst = out->get_datptr(c, p);
-      const float* src = tmp.data() + (size_t(c) * npol + p) * nbin * ndim;
-      for (unsigned i = 0; i < nbin * ndim; i++) dst[i] = src[i];
-    }
+  if (synchronized) return;   // idempotent, as FoldCUDA.cu:132-147
+  // TransferPhaseSeriesCUDA (TransferPhaseSeriesCUDA.C:25-83): match shape, copy attributes (incl. the host-side hits),
+  // then one device-to-host copy of the whole buffer
+  out->internal_match(device_profiles);
+  out->copy_configuration(device_profiles);
+  check(b200_memcpy_d2h(ctx, out->internal_get_buffer(), device_profiles->internal_get_buffer(),
+                        device_profiles->internal_get_size()),
+        "B200::FoldEngine::synch");
   synchronized = true;
 }
 
 void FoldEngine::zero() {
+  // CUDA::FoldEngine::zero (FoldCUDA.cu): the profiles are zeroed through their Memory (DeviceMemory::do_zero)
+  device_profiles->zero();
   if (handle) check(b200_fold_zero(handle), "B200::FoldEngine::zero");
   synchronized = false;
 }

@@ -14,6 +14,8 @@
 #include "dsp/Detection.h"
 #include "dsp/Fold.h"
 #include "dsp/MemoryCUDA.h"
+#include "dsp/MeerKATUnpacker.h"
+#include "dsp/UWBUnpacker.h"
 #endif
 
 namespace B200 {
@@ -28,7 +30,34 @@ class DeviceMemory : public dsp::Memory {
   explicit DeviceMemory(b200_context* c) : ctx(c) {}
   void* do_allocate(size_t nbytes);
   void do_free(void*);
+  void do_zero(void* ptr, size_t nbytes);                     // MemoryCUDA.C:70-82 (stream ordered)
+  void do_copy(void* to, const void* from, size_t nbytes);    // MemoryCUDA.C:90-106 (device to device)
   bool on_host() const { return false; }
+  b200_context* get_context() const { return ctx; }
+ protected:
+  b200_context* ctx;
+};
+
+//! Device hook of dsp::MeerKATUnpacker (kat/dsp/MeerKATUnpacker.h:72-85); replaces CUDA::MeerKATUnpackerEngine
+class MeerKATUnpackerEngine : public dsp::MeerKATUnpacker::Engine {
+ public:
+  explicit MeerKATUnpackerEngine(b200_context* c) : ctx(c) {}
+  void setup() {}
+  void unpack(float scale, const dsp::BitSeries* input, dsp::TimeSeries* output, unsigned sample_swap);
+  bool get_device_supported(dsp::Memory* memory) const;
+  void set_device(dsp::Memory* memory);
+ protected:
+  b200_context* ctx;
+};
+
+//! Device hook of dsp::UWBUnpacker (uwb/dsp/UWBUnpacker.h nested Engine); replaces CUDA::UWBUnpackerEngine
+class UWBUnpackerEngine : public dsp::UWBUnpacker::Engine {
+ public:
+  explicit UWBUnpackerEngine(b200_context* c) : ctx(c) {}
+  void setup() {}
+  void unpack(const dsp::BitSeries* input, dsp::TimeSeries* output);
+  bool get_device_supported(dsp::Memory* memory) const;
+  void set_device(dsp::Memory* memory);
  protected:
   b200_context* ctx;
 };
@@ -95,7 +124,9 @@ class FoldEngine : public dsp::Fold::Engine {
   unsigned nbin;
   uint64_t ndat_folded;
   std::vector<unsigned> last_hits;
-  Reference::To<dsp::PhaseSeries> device_profiles;   // attributes only; the data live in `handle`
+  //! The engine-owned accumulating PhaseSeries on the device (what CUDA::FoldEngine calls d_profiles, FoldCUDA.cu:43-44):
+  //! Fold::get_output() returns it, Fold::transformation sizes and zeroes it, fold() accumulates into its buffer.
+  Reference::To<dsp::PhaseSeries> device_profiles;
 };
 
 }  // namespace B200

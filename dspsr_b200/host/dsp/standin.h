@@ -14,9 +14,13 @@
 //   dsp::Convolution(+Engine)       Signal/General/dsp/Convolution.h:158-167, Convolution.C
 //   dsp::Detection(+Engine)         Signal/General/dsp/Detection.h:98-106, Detection.C
 //   dsp::Fold(+Engine), PhaseSeries Signal/Pulsar/dsp/Fold.h:249-312, Fold.C, PhaseSeries.C
+//   dsp::BitSeries, MeerKATUnpacker / UWBUnpacker (+Engine)  Kernel/Formats/kat/dsp/MeerKATUnpacker.h:72-85,
+//                                   Kernel/Formats/uwb/dsp/UWBUnpacker.h (nested Engine), MeerKATUnpacker.C:196-206
+//   MJD                             PSRCHIVE Util/genutil/MJD.h (day / second / fraction split)
 #ifndef B200_DSP_STANDIN_H
 #define B200_DSP_STANDIN_H
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -75,6 +79,36 @@ namespace Signal {
 enum State { Nyquist, Analytic, Intensity, PPQQ, Coherence, Stokes };
 }
 
+// split epoch as PSRCHIVE's MJD keeps it: integer day, integer second of day, fractional second
+class MJD {
+ public:
+  MJD(int d = 0, int s = 0, double f = 0.0) : days(d), secs(s), fracsec(f) { settle(); }
+  MJD operator+(double seconds) const {
+    const double whole = std::floor(seconds);
+    MJD r(days, secs, fracsec + (seconds - whole));
+    long long s = (long long)r.secs + (long long)whole;
+    long long dd = s >= 0 ? s / 86400 : -((-s + 86399) / 86400);
+    r.days += int(dd);
+    r.secs = int(s - dd * 86400);
+    return r;
+  }
+  double operator-(const MJD& o) const { return double(days - o.days) * 86400.0 + double(secs - o.secs) + (fracsec - o.fracsec); }
+  bool operator<(const MJD& o) const { return (*this - o) < 0; }
+  bool operator==(const MJD& o) const { return days == o.days && secs == o.secs && fracsec == o.fracsec; }
+  int intday() const { return days; }
+  int get_secs() const { return secs; }
+  double get_fracsec() const { return fracsec; }
+ private:
+  void settle() {
+    while (fracsec >= 1.0) { fracsec -= 1.0; secs++; }
+    while (fracsec < 0.0) { fracsec += 1.0; secs--; }
+    while (secs >= 86400) { secs -= 86400; days++; }
+    while (secs < 0) { secs += 86400; days--; }
+  }
+  int days, secs;
+  double fracsec;
+};
+
 namespace dsp {
 
 class Observation : public Reference::Able {
@@ -93,7 +127,14 @@ class Observation : public Reference::Able {
   void set_rate(double r) { rate = r; }
   void rescale(double f) { scale *= f; }
   double get_scale() const { return scale; }
+  MJD get_start_time() const { return start_time; }
+  void set_start_time(const MJD& t) { start_time = t; }
+  MJD get_end_time() const { return start_time + double(ndat) / rate; }      // Observation.C get_end_time
+  const std::string& get_machine() const { return machine; }
+  void set_machine(const std::string& m) { machine = m; }
  protected:
+  MJD start_time;
+  std::string machine;
   Signal::State state;
   unsigned nchan, npol, ndim;
   uint64_t ndat;
@@ -105,7 +146,22 @@ class Memory : public Reference::Able {
  public:
   virtual void* do_allocate(size_t nbytes) = 0;
   virtual void do_free(void*) = 0;
+  virtual void do_zero(void* ptr, size_t nbytes) = 0;                       // Memory.h / MemoryCUDA.C:70-82
+  virtual void do_copy(void* to, const void* from, size_t nbytes) = 0;      // MemoryCUDA.C:90-106
   virtual bool on_host() const = 0;
+};
+
+// Raw (packed) data of one block, on the device when the unpacker runs there (Kernel/Classes/dsp/BitSeries.h)
+class BitSeries : public Observation {
+ public:
+  BitSeries() : raw(0), nbit(8) {}
+  const unsigned char* get_rawptr() const { return raw; }
+  void set_rawptr(const unsigned char* p, uint64_t n) { raw = p; ndat = n; }
+  unsigned get_nbit() const { return nbit; }
+  void set_nbit(unsigned n) { nbit = n; }
+ protected:
+  const unsigned char* raw;
+  unsigned nbit;
 };
 
 // FPT-ordered time series: plane(ichan,ipol) = base + (ichan*npol+ipol)*span floats
@@ -127,10 +183,20 @@ class TimeSeries : public Observation {
   float* get_datptr(unsigned ichan, unsigned ipol) { return buffer + (uint64_t(ichan) * npol + ipol) * span; }
   const float* get_datptr(unsigned ichan, unsigned ipol) const { return buffer + (uint64_t(ichan) * npol + ipol) * span; }
   uint64_t get_nfloat_span() const { return span; }
-  void copy_configuration(const Observation* o) {
+  virtual void copy_configuration(const Observation* o) {
     state = o->get_state(); nchan = o->get_nchan(); npol = o->get_npol(); ndim = o->get_ndim();
-    rate = o->get_rate(); scale = o->get_scale();
+    rate = o->get_rate(); scale = o->get_scale(); start_time = o->get_start_time(); machine = o->get_machine();
   }
+  void zero() { if (buffer) memory->do_zero(buffer, size_t(span) * nchan * npol * sizeof(float)); }   // DataSeries::zero
+  unsigned char* internal_get_buffer() { return reinterpret_cast<unsigned char*>(buffer); }            // DataSeries.h:103-107
+  const unsigned char* internal_get_buffer() const { return reinterpret_cast<const unsigned char*>(buffer); }
+  uint64_t internal_get_size() const { return uint64_t(span) * nchan * npol * sizeof(float); }
+  void internal_match(const TimeSeries* o) {                                 // TimeSeries.h:88: same shape and span
+    nchan = o->nchan; npol = o->npol; ndim = o->ndim;
+    resize(o->ndat);
+  }
+  bool get_zeroed_data() const { return false; }
+  Memory* get_memory() const { return memory; }
  protected:
   Reference::To<Memory> memory;
   float* buffer;
@@ -261,16 +327,36 @@ class Detection::Engine : public Reference::Able {    // Detection.h:98-106
 };
 
 // ---------------------------------------------------------------------------------------------
-class PhaseSeries : public TimeSeries {
+class PhaseSeries : public TimeSeries {                       // Signal/Pulsar/dsp/PhaseSeries.h, PhaseSeries.C
  public:
   PhaseSeries() : integration_length(0), ndat_total(0) {}
-  void resize_bins(unsigned nbin) { resize(nbin); hits.assign(nbin, 0u); }
   unsigned get_nbin() const { return unsigned(ndat); }
   unsigned* get_hits() { return hits.data(); }
+  const unsigned* get_hits() const { return hits.data(); }
   unsigned get_hits_nchan() const { return 1; }
+  MJD get_end_time() const { return end_time; }
+  //! PhaseSeries::mixable (PhaseSeries.C:336-418): adopt the observation when empty, else widen the time span
+  bool mixable(const Observation& obs, unsigned nbin, int64_t istart = 0, int64_t fold_ndat = 0);
+  //! PhaseSeries::combine (PhaseSeries.C:442-480); host memory only
+  void combine(const PhaseSeries* prof);
+  //! PhaseSeries::zero (PhaseSeries.C:239-256)
+  void zero() { integration_length = 0; ndat_total = 0; hits.assign(hits.size(), 0u); TimeSeries::zero(); }
+  //! PhaseSeries::copy_configuration + copy_attributes (PhaseSeries.C:258-316): host hits travel with the attributes
+  void copy_configuration(const Observation* o) {
+    TimeSeries::copy_configuration(o);
+    const PhaseSeries* like = dynamic_cast<const PhaseSeries*>(o);
+    if (like) {
+      integration_length = like->integration_length;
+      ndat_total = like->ndat_total;
+      end_time = like->end_time;
+      hits = like->hits;
+    }
+  }
   double integration_length;
   uint64_t ndat_total;
+  void resize_bins(unsigned nbin) { resize(nbin); hits.assign(nbin, 0u); }
  protected:
+  MJD end_time;
   std::vector<unsigned> hits;
 };
 
@@ -288,7 +374,8 @@ class Fold : public Reference::Able {
   void set_engine(Engine* e);
   void operate();          // Fold::transformation + fold() engine branch (Fold.C:510-604,724-829)
   PhaseSeries* get_result();  // Fold::get_result -> engine->synch (Fold.C:123-135)
-  PhaseSeries* get_output() { return output; }
+  PhaseSeries* get_output() const;   // Fold.C:88-94: the ENGINE's PhaseSeries whenever an engine is set
+  void reset();                      // Fold.C:137-148
  protected:
   Reference::To<TimeSeries> input;
   Reference::To<PhaseSeries> output;
@@ -330,6 +417,64 @@ class Fold::Engine : public Reference::Able {         // Fold.h:249-312
   Fold* parent;
   bool synchronized;
   friend class Fold;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Unpacker device hook (Kernel/Classes/dsp/Unpacker.h:57-61,100).  The two formats of the BASELINE configurations that
+// have a nested Engine interface in the reference: MeerKATUnpacker::Engine (kat/dsp/MeerKATUnpacker.h:72-85) and
+// UWBUnpacker::Engine (uwb/dsp/UWBUnpacker.h).  operate() is the engine branch of their unpack() (MeerKATUnpacker.C:
+// 196-206, UWBUnpacker.C:163-168).
+class Unpacker : public Reference::Able {
+ public:
+  void set_input(const BitSeries* i) { input = const_cast<BitSeries*>(i); }
+  void set_output(TimeSeries* o) { output = o; }
+ protected:
+  void prepare_output(unsigned ndim_out) {                   // Unpacker::resize_output (Unpacker.C): FPT floats
+    output->copy_configuration(input);
+    output->set_ndim(ndim_out);
+    output->resize(input->get_ndat());
+  }
+  Reference::To<BitSeries> input;
+  Reference::To<TimeSeries> output;
+};
+
+class MeerKATUnpacker : public Unpacker {
+ public:
+  class Engine;
+  MeerKATUnpacker() : table_scale(0) {}
+  void set_table_scale(double s) { table_scale = s; }        // BitTable(8, TwosComplement).get_scale() (MeerKATUnpacker.C:36)
+  void set_engine(Engine* e);
+  bool get_device_supported(Memory* m) const;
+  void set_device(Memory* m);
+  void operate();
+ protected:
+  Reference::To<Engine> engine;
+  double table_scale;
+};
+class MeerKATUnpacker::Engine : public Reference::Able {
+ public:
+  virtual void setup() = 0;
+  virtual void unpack(float scale, const BitSeries* input, TimeSeries* output, unsigned sample_swap) = 0;
+  virtual bool get_device_supported(Memory* memory) const = 0;
+  virtual void set_device(Memory* memory) = 0;
+};
+
+class UWBUnpacker : public Unpacker {
+ public:
+  class Engine;
+  void set_engine(Engine* e);
+  bool get_device_supported(Memory* m) const;
+  void set_device(Memory* m);
+  void operate();
+ protected:
+  Reference::To<Engine> engine;
+};
+class UWBUnpacker::Engine : public Reference::Able {
+ public:
+  virtual void unpack(const BitSeries* input, TimeSeries* output) = 0;
+  virtual bool get_device_supported(Memory* memory) const = 0;
+  virtual void set_device(Memory* memory) = 0;
+  virtual void setup() = 0;
 };
 
 }  // namespace dsp

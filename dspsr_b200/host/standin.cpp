@@ -134,10 +134,65 @@ void Detection::operate() {                                   // :74-147
   output->set_state(state);
 }
 
+// ---- PhaseSeries (Signal/Pulsar/PhaseSeries.C) -------------------------------------------------
+bool PhaseSeries::mixable(const Observation& obs, unsigned nbin, int64_t istart, int64_t fold_ndat) {   // :336-418
+  MJD obsStart = obs.get_start_time() + double(istart) / obs.get_rate();
+  MJD obsEnd = fold_ndat == 0 ? obs.get_end_time() : obsStart + double(fold_ndat) / obs.get_rate();
+  if (integration_length == 0.0) {
+    // the integration is currently empty: adopt the observation, size and zero the bins (:355-395)
+    const uint64_t backup_ndat_total = ndat_total;
+    const PhaseSeries* like = dynamic_cast<const PhaseSeries*>(&obs);
+    TimeSeries::copy_configuration(&obs);
+    if (like) end_time = like->end_time;
+    resize_bins(nbin);
+    zero();
+    end_time = obsEnd;
+    start_time = obsStart;
+    ndat_total = backup_ndat_total;
+    return true;
+  }
+  if (obs.get_nchan() != nchan || obs.get_npol() != npol || obs.get_ndim() != ndim || obs.get_state() != state)
+    return false;                                             // Observation::combinable
+  if (get_nbin() != nbin) return false;
+  if (end_time < obsEnd) end_time = obsEnd;                   // :408-409
+  if (obsStart < start_time) start_time = obsStart;
+  return true;
+}
+
+void PhaseSeries::combine(const PhaseSeries* prof) {          // :442-480
+  if (!prof || prof->get_nbin() == 0) return;
+  if (!integration_length) {                                  // *this = *prof
+    internal_match(prof);
+    copy_configuration(prof);
+    memory->do_copy(buffer, prof->buffer, size_t(internal_get_size()));
+    return;
+  }
+  // mixable(*prof, nbin) with fold_ndat = 0 uses the observation's end time: a PhaseSeries ends at end_time
+  if (prof->get_nchan() != nchan || prof->get_npol() != npol || prof->get_ndim() != ndim || prof->get_nbin() != get_nbin())
+    throw Error(InvalidParam, "PhaseSeries::combine", "PhaseSeries !mixable");
+  if (end_time < prof->end_time) end_time = prof->end_time;
+  if (prof->start_time < start_time) start_time = prof->start_time;
+  const size_t n = size_t(span) * nchan * npol;               // TimeSeries::operator +=
+  for (size_t i = 0; i < n; i++) buffer[i] += prof->buffer[i];
+  for (size_t i = 0; i < hits.size(); i++) hits[i] += prof->hits[i];
+  integration_length += prof->integration_length;
+  ndat_total += prof->ndat_total;
+}
+
 // ---- Fold (Signal/Pulsar/Fold.C) --------------------------------------------------------------
 void Fold::set_engine(Engine* e) {
   engine = e;
   if (engine) engine->set_parent(this);
+}
+
+PhaseSeries* Fold::get_output() const {                       // :88-94
+  if (engine) return engine->get_profiles();
+  return output;
+}
+
+void Fold::reset() {                                          // :137-148
+  if (engine) engine->zero();
+  if (output) output->zero();
 }
 
 void Fold::Engine::setup() {                                  // Fold.C:973-1011
@@ -153,17 +208,20 @@ void Fold::Engine::setup() {                                  // Fold.C:973-1011
   output_span = unsigned(out->get_nfloat_span());
   hits = out->get_hits();
   hits_nchan = out->get_hits_nchan();
-  zeroed_samples = false;
+  zeroed_samples = in->get_zeroed_data();
 }
 
 void Fold::operate() {                                        // transformation :510-604 + fold :626-829
   if (!engine) throw Error(InvalidState, "dsp::Fold::fold", "stand-in has no CPU path: set an engine");
   if (input->get_ndat() == 0) return;
   if (!folding_nbin) throw Error(InvalidState, "dsp::Fold::fold", "nbin not set");
+  PhaseSeries* use = get_output();                            // :536 -- the engine's PhaseSeries
   idat_start = 0;                                             // set_limits :961-965
   ndat_fold = input->get_ndat();
+  if (!use->mixable(*input, folding_nbin, int64_t(idat_start), int64_t(ndat_fold)))   // prepare_output :495-504
+    throw Error(InvalidParam, "dsp::Fold::prepare_output", "input and output are not mixable");
   const uint64_t idat_end = idat_start + ndat_fold;
-  unsigned* hits = output->get_hits();
+  unsigned* hits = get_output()->get_hits();                  // :721
   engine->set_nbin(folding_nbin);                             // :728
   engine->set_ndat(idat_end - idat_start, idat_start);        // :729
   uint64_t ndat_folded = 0;
@@ -182,14 +240,42 @@ void Fold::operate() {                                        // transformation 
       ndat_folded++;
     }
   }
-  output->integration_length += double(ndat_folded) / input->get_rate();   // :792-803
-  output->ndat_total += ndat_fold;
+  PhaseSeries* result = get_output();                         // :800
+  result->integration_length += double(ndat_folded) / input->get_rate();   // :792-803
+  result->ndat_total += ndat_fold;
+  if (result->get_nbin() != folding_nbin)
+    throw Error(InvalidParam, "dsp::Fold::fold", "folding_nbin != output->nbin (%d != %d)", folding_nbin, result->get_nbin());
   engine->fold();                                             // :817-829
 }
 
 PhaseSeries* Fold::get_result() {                             // :123-135
   if (engine) engine->synch(output);
   return output;
+}
+
+// ---- Unpacker device hooks ----------------------------------------------------------------------
+void MeerKATUnpacker::set_engine(Engine* e) { engine = e; }
+bool MeerKATUnpacker::get_device_supported(Memory* m) const { return engine && engine->get_device_supported(m); }
+void MeerKATUnpacker::set_device(Memory* m) {                 // MeerKATUnpacker.C:120-143
+  if (engine) { engine->set_device(m); engine->setup(); }
+}
+void MeerKATUnpacker::operate() {                             // unpack(), engine branch :186-206
+  if (!engine) throw Error(InvalidState, "dsp::MeerKATUnpacker::unpack", "stand-in has no CPU path: set an engine");
+  prepare_output(2);
+  if (input->get_ndat() == 0) return;
+  const unsigned sample_swap = input->get_machine() == "MKBFRo" ? 2 : 1;
+  engine->unpack(float(table_scale), input, output, sample_swap);
+}
+
+void UWBUnpacker::set_engine(Engine* e) { engine = e; }
+bool UWBUnpacker::get_device_supported(Memory* m) const { return engine && engine->get_device_supported(m); }
+void UWBUnpacker::set_device(Memory* m) {                     // UWBUnpacker.C:113-139
+  if (engine) { engine->set_device(m); engine->setup(); }
+}
+void UWBUnpacker::operate() {                                 // unpack(), engine branch :150-168
+  if (!engine) throw Error(InvalidState, "dsp::UWBUnpacker::unpack", "stand-in has no CPU path: set an engine");
+  prepare_output(2);
+  engine->unpack(input, output);
 }
 
 }  // namespace dsp

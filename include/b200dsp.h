@@ -63,6 +63,8 @@ int b200_free(b200_context* ctx, void* d_ptr);
 int b200_malloc_host(b200_context* ctx, uint64_t nbytes, void** h_ptr); /* pinned */
 int b200_free_host(b200_context* ctx, void* h_ptr);
 int b200_memset(b200_context* ctx, void* d_ptr, int value, uint64_t nbytes);
+/* dsp::Memory::do_copy on the device (CUDA::DeviceMemory::do_copy, Kernel/Classes/MemoryCUDA.C:90-106); stream ordered */
+int b200_memcpy_d2d(b200_context* ctx, void* d_dst, const void* d_src, uint64_t nbytes);
 int b200_memcpy_h2d(b200_context* ctx, void* d_dst, const void* h_src, uint64_t nbytes);
 int b200_memcpy_d2h(b200_context* ctx, void* h_dst, const void* d_src, uint64_t nbytes);
 
@@ -194,6 +196,11 @@ int b200_fold_set_bins(b200_fold* fold, double phi, double phase_per_sample, uin
 int b200_fold_get_bin_hits(b200_fold* fold, unsigned* h_hits);
 /* Fold::Engine::fold(): d_in = input->get_datptr(0,0), in_span = get_nfloat_span (Fold.C:989-990). */
 int b200_fold_fold(b200_fold* fold, const float* d_in, uint64_t in_span);
+/* Same, accumulating into a caller-owned device PhaseSeries instead of the handle's own: d_out = the engine-owned
+ * PhaseSeries' get_datptr(0,0) and out_span = its get_nfloat_span(), exactly the `output` / `output_span` that
+ * Fold::Engine::setup hands every engine (Fold.C:992-996; CUDA::FoldEngine folds into d_profiles the same way,
+ * FoldCUDA.cu:122,586-697).  Plane (ichan, ipol) starts at d_out + (ichan*npol + ipol)*out_span. */
+int b200_fold_fold_into(b200_fold* fold, const float* d_in, uint64_t in_span, float* d_out, uint64_t out_span);
 /* Fold::Engine::synch(PhaseSeries*): copies the device profiles to the host (idempotent). */
 int b200_fold_synch(b200_fold* fold, float* h_profile);
 /* accumulated hits of every set_bins since the last zero (PhaseSeries::get_hits) */

@@ -309,13 +309,59 @@ def test_cpp_engine_shims_demo(ctx, oracle, tmp_path):
     buf = np.fromfile(out, dtype=np.uint8)
     nprof = C * 4 * nbin
     prof = buf[: nprof * 4].view(np.float32).reshape(C, 1, nbin * 4)
-    hits = buf[nprof * 4:].view(np.uint32)
+    hits = buf[nprof * 4:nprof * 4 + nbin * 4].view(np.uint32)
+    tail = buf[nprof * 4 + nbin * 4:]
+    integration_length, ndat_total = tail[:8].view(np.float64)[0], int(tail[8:16].view(np.uint64)[0])
     # the demo hands the operators the whole stream at once: npart' = (ndat - overlap) / step parts
     npart_all = (ndat - f.nsamp_overlap) // f.nsamp_step
     p = oracle.make_pipe(0, 1, 2, 1, lut, 0.0, f, None, H, "Coherence", 4, nbin)
     ref, ref_hits = oracle.pipe_run(p, raw, 1, npart_all, [phi], [pps], 1)
     assert np.array_equal(hits, ref_hits)
     assert synth.relerr(prof, ref) <= TOL
+    # Fold.C:792-803 bookkeeping kept on the engine-owned PhaseSeries and carried over by synch()
+    assert ndat_total == npart_all * f.nkeep == int(hits.sum())
+    rate_out = 800e6 * d.ndat / f.nsamp_fft
+    assert abs(integration_length - ndat_total / rate_out) <= 1e-12 * integration_length
+
+
+def test_cpp_engine_shims_demo_meerkat_convolution(ctx, oracle, tmp_path):
+    """BASELINE configs[2] wiring in C++: B200::MeerKATUnpackerEngine (Unpacker device hook) -> ConvolutionEngine ->
+    DetectionEngine -> FoldEngine through the stand-in operators, whose Fold::get_output() is the ENGINE's PhaseSeries
+    as in the reference (Fold.C:88-94).  The demo folds the block, resets (engine->zero()), then folds it twice: the
+    result must be exactly two accumulations of the oracle's single fold."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "dspsr_b200", "host", "b200_demo")
+    assert os.path.exists(exe), "run __graft_entry__.build() first"
+    nchan, F, npos, nneg, npart, nbin = 6, 4096, 150, 170, 3, 128
+    c = oracle.conv_sizes(0, nchan, 2, F, npos, nneg)
+    ndat = (npart * c.nsamp_step + c.nsamp_overlap + 255) // 256 * 256
+    raw = synth.meerkat_bytes(ndat, nchan, 2, seed=77)
+    rng = np.random.default_rng(78)
+    H = np.exp(1j * rng.uniform(-np.pi, np.pi, (nchan, F))).astype(np.complex64)
+    H[:, 0] = 0
+    phi, pps = 0.12, 1.0 / 977.3
+    (tmp_path / "raw.bin").write_bytes(raw.tobytes())
+    (tmp_path / "resp.c64").write_bytes(H.tobytes())
+    out = tmp_path / "out.bin"
+    r = subprocess.run([exe, "--meerkat", str(tmp_path / "raw.bin"), str(tmp_path / "resp.c64"), str(nchan), str(F),
+                        str(npos), str(nneg), str(nbin), repr(phi), repr(pps), str(out)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr + r.stdout
+    buf = np.fromfile(out, dtype=np.uint8)
+    nprof = nchan * 4 * nbin
+    prof = buf[: nprof * 4].view(np.float32).reshape(nchan, 1, nbin * 4)
+    hits = buf[nprof * 4:nprof * 4 + nbin * 4].view(np.uint32)
+    tail = buf[nprof * 4 + nbin * 4:]
+    ndat_total = int(tail[8:16].view(np.uint64)[0])
+    _, scale = oracle.bittable8()
+    npart_all = (ndat - c.nsamp_overlap) // c.nsamp_step
+    p = oracle.make_pipe(2, nchan, 2, 2, None, np.float32(scale), None, c, H, "Coherence", 4, nbin)
+    ref, ref_hits = oracle.pipe_run(p, raw, 1, npart_all, [phi], [pps], 1)
+    assert np.array_equal(hits, 2 * ref_hits)
+    assert ndat_total == 2 * npart_all * (c.n_fft - c.nfilt_pos - c.nfilt_neg)
+    assert synth.relerr(prof, 2.0 * ref) <= TOL
 
 
 # ------------------------------------------------------------------------------------ two-bit excision (a6)
@@ -409,6 +455,23 @@ def test_pipeline_cfg3_meerkat_convolution_fold(ctx, oracle):
     H = np.exp(1j * rng.uniform(-np.pi, np.pi, (nchan, F))).astype(np.complex64)
     err = _pipe_generic(ctx, oracle, L.FMT_MEERKAT8, nchan, 2, 2, raw, ndat, None, c, H, 1, F, npos, nneg, npart,
                         "Coherence", 4, 1024, scale=np.float32(scale))
+    assert err <= TOL, err
+
+
+def test_pipeline_4096_input_channels_grid_limit(ctx, oracle):
+    """4096 input channels x 2 polarisations = 8192 (channel, pol) blocks per part; with the default
+    16 parts per launch the generic kernels' grid.y would be 131072 (> 65535).  The plan caps the batch; 20 parts
+    force several launches.  MeerKAT heaps, 64-point convolution."""
+    L = _L()
+    nchan, F, npos, nneg, npart = 4096, 64, 5, 6, 20
+    c = oracle.conv_sizes(0, nchan, 2, F, npos, nneg)
+    ndat = (npart * c.nsamp_step + c.nsamp_overlap + 255) // 256 * 256
+    raw = synth.meerkat_bytes(ndat, nchan, 2, seed=91)
+    _, scale = oracle.bittable8()
+    rng = np.random.default_rng(92)
+    H = np.exp(1j * rng.uniform(-np.pi, np.pi, (nchan, F))).astype(np.complex64)
+    err = _pipe_generic(ctx, oracle, L.FMT_MEERKAT8, nchan, 2, 2, raw, ndat, None, c, H, 1, F, npos, nneg, npart,
+                        "Coherence", 4, 64, scale=np.float32(scale))
     assert err <= TOL, err
 
 
