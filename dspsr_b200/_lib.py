@@ -159,6 +159,7 @@ SIGNATURES = {
     "b200_free_host": (_i, [_vp, _vp]),
     "b200_memset": (_i, [_vp, _vp, _i, _u64]),
     "b200_memcpy_h2d": (_i, [_vp, _vp, _vp, _u64]),
+    "b200_memcpy_d2d": (_i, [_vp, _vp, _vp, _u64]),
     "b200_memcpy_d2h": (_i, [_vp, _vp, _vp, _u64]),
     "b200_unpack": (_i, [_vp, C.POINTER(UnpackDesc), _vp, _u64, _vp, _u64]),
     "b200_fb_plan_create": (_i, [_vp, C.POINTER(FbDesc), _pvp]),
@@ -171,6 +172,7 @@ SIGNATURES = {
     "b200_fold_set_bins": (_i, [_vp, _d, _d, _u64, _u64, C.POINTER(_u64)]),
     "b200_fold_get_bin_hits": (_i, [_vp, _vp]),
     "b200_fold_fold": (_i, [_vp, _vp, _u64]),
+    "b200_fold_fold_into": (_i, [_vp, _vp, _u64, _vp, _u64]),
     "b200_fold_synch": (_i, [_vp, _vp]),
     "b200_fold_get_hits": (_i, [_vp, _vp, C.POINTER(_u64)]),
     "b200_fold_zero": (_i, [_vp]),
