@@ -684,6 +684,160 @@ __global__ void __launch_bounds__(512, 1) k2_r32(K2Args a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// K2, two half-CTA groups (real input, tile-major Z).  Same arithmetic and the same Z' / H' layout as k2_r32, but
+// the 512 threads work as TWO independent 256-thread groups, each on four of the tile's eight mirror-row pairs,
+// synchronised by their own named barriers (bar.sync 1 + grp, 256) instead of CTA-wide barriers.  A tile has two
+// phases of about equal length that stress different units -- the row transforms (FP32 pipe + warp-local exchanges)
+// and the split / response / store phase (L1TEX + global stores).  One lock-stepped group of 16 warps runs them one
+// after the other; two groups drift apart and one's split phase runs under the other's transforms: K2 -5 %
+// (0.576 -> 0.548 ms per 37 parts, profiles/r2_*).  Measured and rejected: a token (bar.arrive / bar.sync pair) that
+// lets only one group transform at a time, +2.5 % -- eight warps alone do not fill the FP32 pipe.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_sync(unsigned id, unsigned n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+
+template <unsigned P>
+__global__ void __launch_bounds__(512, 1) k2_g2(K2Args a) {
+  extern __shared__ float4 smem4[];
+  float2* sm2 = reinterpret_cast<float2*>(smem4);
+  constexpr unsigned Q = 1024, G = 8, RSQ = 1058u;
+  constexpr unsigned TPB = (P / 2) / G;
+  __shared__ float2 s_rowtw[G + 1];
+  const unsigned grp = threadIdx.x >> 8, tl = threadIdx.x & 255u;
+  const unsigned seq = threadIdx.x >> 5, j = threadIdx.x & 31u;
+  const unsigned g = seq >> 1, which = seq & 1u;            // pair g (0..7; group grp owns 4 grp .. 4 grp + 3)
+  const unsigned Nc = a.Nc;
+  const unsigned ntiles = TPB * a.nblk;
+
+  float2 v[32];
+  auto issue_loads = [&](unsigned tt) {
+    const unsigned tile = tt % TPB, blk = tt / TPB;
+    const unsigned low = tile * G + g;
+    const unsigned row = which ? (low == 0 ? P / 2 : P - low) : low;
+    const float2* src = a.A + uint64_t(blk) * Nc + uint64_t(row) * Q + j;
+#pragma unroll
+    for (int e = 0; e < 32; e++) v[e] = B200_LDS1(src + 32 * e);
+  };
+
+  unsigned t = blockIdx.x;
+  if (t < ntiles) issue_loads(t);
+  for (; t < ntiles; t += gridDim.x) {
+    const unsigned tile = t % TPB, blk = t / TPB;
+    const unsigned ic = (blk / a.npol) % a.nchan_in;
+    // W_2N^row of this group's four pairs (+ row P/2, needed by pair 0 of tile 0 only: group 0)
+    if (tl < 4) s_rowtw[4 * grp + tl] = big_twiddle<false>(a.b2lo, a.b2hi, tile * G + 4 * grp + tl);
+    if (threadIdx.x == 4) s_rowtw[G] = big_twiddle<false>(a.b2lo, a.b2hi, P / 2);
+    float2* sq = sm2 + seq * RSQ;
+    dft32<false>(v);
+#pragma unroll
+    for (int r = 0; r < 32; r++) sq[33u * j + r] = v[r];
+    float2 ws[8], wm[4];
+#pragma unroll
+    for (int s1 = 1; s1 < 8; s1++) ws[s1] = __ldg(a.tw32 + (s1 - 1) * 32 + j);
+#pragma unroll
+    for (int m = 1; m < 4; m++) wm[m] = __ldg(a.tw32 + (6 + m) * 32 + j);
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 32; e++) v[e] = sq[j + 33u * e];
+#pragma unroll
+    for (int r = 1; r < 32; r++) {
+      const int s1 = r & 7, m = r >> 3;
+      const float2 w = m == 0 ? ws[s1] : (s1 == 0 ? wm[m] : cmul(wm[m], ws[s1]));
+      v[r] = cmul(v[r], w);
+    }
+    dft32<false>(v);
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 32; e++) sq[j + 33u * e] = v[e];
+    named_sync(1 + grp, 256);
+
+    if (t + gridDim.x < ntiles) issue_loads(t + gridDim.x);
+
+    {
+      const float2* H = a.H ? a.H + uint64_t(ic) * Nc : nullptr;
+      float2* Zblk = a.Z + uint64_t(blk) * Nc;
+      // 64 kk x 4 pairs per group; lane = (kk & 3) + 4 g2l: 16 lanes cover 128 contiguous bytes of Z'
+      const unsigned g2 = 4u * grp + ((tl >> 2) & 3u);
+      const unsigned kk = (tl & 3u) + 4u * (tl >> 4);
+      const float2* SA = sm2 + (2 * g2) * RSQ;
+      const float2* SB = SA + RSQ;
+      auto p33 = [](unsigned i) { return i + (i >> 5); };
+      constexpr int SSTEP = 66;
+      auto split = [&](float2 zk, float2 zmc, float2 w, float2& xk, float2& xm) {
+        const float2 e = make_float2(0.5f * (zk.x + zmc.x), 0.5f * (zk.y + zmc.y));
+        const float2 d = make_float2(0.5f * (zk.x - zmc.x), 0.5f * (zk.y - zmc.y));
+        const float2 tt = cmul(make_float2(d.y, -d.x), w);
+        xk = cadd(e, tt);
+        xm = cconj(csub(e, tt));
+      };
+      const unsigned low = tile * G + g2;
+      if (low != 0) {
+        const float2 rw = s_rowtw[g2];
+        const unsigned sa = p33(kk), sb = p33(Q - 1 - kk);
+        const float2* t2a = a.tw2Q + kk;
+        const float2* t2b = a.tw2Q + (Q - 1 - kk);
+        float2* zt = Zblk + uint64_t(tile) * (2 * Q * G);
+        float2* ZA = zt + zt_pos(kk, g2);
+        float2* ZBm = zt + Q * G + zt_pos(kk, g2);
+        float2* ZB = zt + zt_pos(Q - 1 - kk, g2);
+        float2* ZAm = zt + Q * G + zt_pos(Q - 1 - kk, g2);
+        constexpr int zstep = 64 * G;
+        const float2 *HA = nullptr, *HAm = nullptr, *HB = nullptr, *HBm = nullptr;
+        if (H) {
+          const float2* Htc = a.Ht + uint64_t(ic) * Nc;
+          HA = Htc + (ZA - Zblk); HAm = Htc + (ZAm - Zblk); HB = Htc + (ZB - Zblk); HBm = Htc + (ZBm - Zblk);
+        }
+#pragma unroll 2
+        for (int it = 0; it < 8; it++) {
+          const float2 ua = SA[sa + SSTEP * it], ub = SB[sa + SSTEP * it];
+          const float2 va2 = SA[sb - SSTEP * it], vb2 = SB[sb - SSTEP * it];
+          const float2 wA = cmul(rw, __ldg(t2a + it * 64));
+          const float2 wB = cmul(rw, __ldg(t2b - it * 64));
+          float2 xk, xm, yk, ym;
+          split(ua, make_float2(vb2.x, -vb2.y), wA, xk, xm);
+          split(va2, make_float2(ub.x, -ub.y), wB, yk, ym);
+          if (H) {
+            xk = cmul(xk, __ldg(HA + it * zstep));
+            xm = cmul(xm, __ldg(HAm - it * zstep));
+            yk = cmul(yk, __ldg(HB - it * zstep));
+            ym = cmul(ym, __ldg(HBm + it * zstep));
+          }
+          B200_ZST(ZA + it * zstep, xk);
+          B200_ZST(ZAm - it * zstep, xm);
+          B200_ZST(ZB - it * zstep, yk);
+          B200_ZST(ZBm + it * zstep, ym);
+        }
+      } else {
+        // rows 0 (array a) and P/2 (array b) mirror onto themselves
+        const float2 rwh = s_rowtw[G];
+        for (unsigned it = 0; it < 16; it++) {
+          const unsigned k2 = kk + it * 64;
+          if (k2 <= Q / 2) {
+            const unsigned km2 = (Q - k2) % Q;
+            const float2 xa = SA[p33(k2)], xm2 = SA[p33(km2)];
+            float2 xk, xm;
+            split(xa, make_float2(xm2.x, -xm2.y), __ldg(a.tw2Q + k2), xk, xm);
+            const unsigned k = P * k2, km = (Nc - k) & (Nc - 1);
+            if (H) { xk = cmul(xk, __ldg(H + k)); xm = cmul(xm, __ldg(H + km)); }
+            Zblk[zt_pos(k2, 0)] = xk;
+            if (km2 != k2) Zblk[zt_pos(km2, 0)] = xm;
+          }
+          if (k2 < Q / 2) {
+            const float2 xb = SB[p33(k2)], xm2 = SB[p33(Q - 1 - k2)];
+            float2 xk, xm;
+            split(xb, make_float2(xm2.x, -xm2.y), cmul(rwh, __ldg(a.tw2Q + k2)), xk, xm);
+            const unsigned k = P / 2 + P * k2, km = Nc - k;
+            if (H) { xk = cmul(xk, __ldg(H + k)); xm = cmul(xm, __ldg(H + km)); }
+            Zblk[Q * G + zt_pos(k2, 0)] = xk;
+            Zblk[Q * G + zt_pos(Q - 1 - k2, 0)] = xm;
+          }
+        }
+      }
+    }
+    named_sync(1 + grp, 256);     // this group's split readers are done before its next scatter
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K3: per-channel inverse pass (both polarisations per thread) + discard + epilogue.
 // tile = (CB output channels, part)
 // ------------------------------------------------------------------------------------------
@@ -1188,6 +1342,7 @@ int fast_plan_init(b200_fb_plan* pl) {
       B200_CUDA(cudaMemcpy(pl->c2Q32, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice));
       if ((rc = opt_in_smem(k2_r32<FP_P, true>, k2r32_smem())) != B200_OK) return rc;
       if ((rc = opt_in_smem(k2_r32<FP_P, false>, k2r32_smem())) != B200_OK) return rc;
+      if ((rc = opt_in_smem(k2_g2<FP_P>, k2r32_smem())) != B200_OK) return rc;
     }
     pl->fast_k2 = true;
   }
@@ -1354,6 +1509,11 @@ int fast_k2(b200_fb_plan* pl, unsigned nb) {
 #ifdef B200_ABLATION
   if (getenv("B200_K2_NOH")) a.H = nullptr;   // timing experiment only (cost of the response stream): results are wrong
 #endif
+  static const bool g2 = !(getenv("B200_K2_G2") && atoi(getenv("B200_K2_G2")) == 0);
+  if (r32 && pl->c2Q32 && split && a.z_tiled && g2) {
+    k2_g2<FP_P><<<grid, 512, k2r32_smem(), ctx->stream>>>(a);
+    return B200_OK;
+  }
   if (r32 && pl->c2Q32) {
     if (split) k2_r32<FP_P, true><<<grid, 512, k2r32_smem(), ctx->stream>>>(a);
     else k2_r32<FP_P, false><<<grid, 512, k2r32_smem(), ctx->stream>>>(a);
