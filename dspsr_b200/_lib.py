@@ -182,13 +182,15 @@ SIGNATURES = {
     "b200_pipeline_destroy": (_i, [_vp]),
     "b200_pipeline_info": (_i, [_vp, C.POINTER(FbInfo)]),
     "b200_pipeline_execute": (_i, [_vp, _vp, _u64, _u64, _u64, _d, _d, _vp, _u64]),
-    "b200_pipeline_execute_host": (_i, [_vp, _vp, _u64, _u64, _u64, _d, _d]),
+    "b200_pipeline_execute_host": (_i, [_vp, _vp, _u64, _u64, _u64, _d, _d, _vp, _u64]),
+    "b200_pipeline_input_consumed": (_i, [_vp]),
     "b200_pipeline_synch": (_i, [_vp, _vp, _vp, C.POINTER(_u64)]),
     "b200_pipeline_zero": (_i, [_vp]),
     "b200_pipeline_fold": (_vp, [_vp]),
     "b200_bittable8": (_i, [_i, _vp, C.POINTER(_d)]),
     "b200_dedispersion_prepare": (_i, [C.POINTER(Dedispersion)]),
     "b200_dedispersion_build": (_i, [C.POINTER(Dedispersion), _vp]),
+    "b200_dedispersion_build_channels": (_i, [C.POINTER(Dedispersion), C.c_uint, C.c_uint, _vp]),
     "b200_optimal_fft_length": (C.c_int64, [_u64, _u64]),
     "b200_polyco_parse": (_i, [C.c_char_p, C.POINTER(Polyco)]),
     "b200_polyco_phase": (_d, [C.POINTER(Polyco), _i, _i, _d, C.POINTER(_d)]),

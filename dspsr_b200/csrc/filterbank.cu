@@ -858,6 +858,10 @@ int b200_fb_plan_create(b200_context* cctx, const b200_fb_desc* d, b200_fb_plan*
     const uint64_t per_part = uint64_t(d->input_nchan) * d->npol * pl->Nc * sizeof(float2);
     const uint64_t cap = std::max<uint64_t>(1, (2ull << 30) / per_part);
     uint64_t b = std::min<uint64_t>(cap, 16);
+    // short transforms (cfg2: 512 KiB per part; the upper UWL sub-bands): 16 parts would be a few hundred CTAs of a few
+    // microseconds each.  Take as many parts as keep one spectrum buffer near 32 MiB -- A and Z then stay in the
+    // 126 MB L2 between the kernels of a batch
+    if (per_part * 16 < (32ull << 20)) b = std::min<uint64_t>(std::min<uint64_t>(cap, 4096), (32ull << 20) / per_part);
     if (!pl->conv_path && pl->Q >= 8 && pl->P >= 16) {
       auto gcd = [](uint64_t x, uint64_t y) { while (y) { const uint64_t t = x % y; x = y; y = t; } return x; };
       const uint64_t sm = uint64_t(std::max(1, ctx->sm_count)), blk = uint64_t(d->input_nchan) * d->npol;

@@ -312,13 +312,29 @@ static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t inpu
   return fb_run(fb, src, sink, npart);
 }
 
+int b200_pipeline_input_consumed(b200_pipeline* p) {
+  B200_REQUIRE(p, "b200_pipeline_input_consumed: null pipeline");
+  if (p->copy_stream) B200_CUDA(cudaStreamSynchronize(p->copy_stream));
+  return B200_OK;
+}
+
 int b200_pipeline_execute_host(b200_pipeline* p, const void* h_input, uint64_t nbytes, uint64_t first_sample,
-                               uint64_t npart, double phi, double pps) {
+                               uint64_t npart, double phi, double pps, float* d_detected, uint64_t detected_span) {
   B200_REQUIRE(p && h_input, "b200_pipeline_execute_host: null argument");
   B200_REQUIRE(p->desc.unpack.format != B200_FMT_FLOAT32, "execute_host takes raw bytes");
   if (npart == 0) return B200_OK;
   Context* ctx = p->ctx;
   b200_fb_plan* fb = p->fb;
+  // everything pipeline_execute would reject is rejected here, BEFORE the bin plan of the block is committed
+  B200_REQUIRE(p->desc.nbin || d_detected, "b200_pipeline_execute_host: nbin == 0 needs an output buffer for the detected series");
+  if (p->desc.unpack.format == B200_FMT_CASPSR8)
+    B200_REQUIRE(first_sample % 4 == 0, "CASPSR block must start on a 4-sample boundary");
+  {
+    const uint64_t bits = uint64_t(p->desc.unpack.nchan) * p->desc.unpack.npol * p->desc.unpack.ndim * fmt_nbit(p->desc.unpack.format);
+    const uint64_t last = first_sample + npart * fb->nsamp_step + fb->nsamp_overlap;
+    B200_REQUIRE(nbytes >= (last * bits + 7) / 8, "b200_pipeline_execute_host: %llu bytes do not hold %llu samples",
+                 (unsigned long long)nbytes, (unsigned long long)last);
+  }
   if (!p->copy_stream) {
     B200_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) B200_CUDA(cudaEventCreateWithFlags(&p->stage_free[i], cudaEventDisableTiming));
@@ -378,12 +394,13 @@ int b200_pipeline_execute_host(b200_pipeline* p, const void* h_input, uint64_t n
   }
   int rc;
   if (chunked) {
-    rc = pipeline_execute(p, p->d_stage[turn], 0, first_sample, npart, phi, pps, nullptr, 0, p->chunk_ready->data(),
-                          (unsigned)batch);
+    rc = pipeline_execute(p, p->d_stage[turn], 0, first_sample, npart, phi, pps, d_detected, detected_span,
+                          p->chunk_ready->data(), (unsigned)batch);
   } else {
     B200_CUDA(cudaStreamWaitEvent(ctx->stream, (*p->chunk_ready)[0], 0));
-    rc = pipeline_execute(p, p->d_stage[turn], 0, first_sample, npart, phi, pps, nullptr, 0, nullptr);
+    rc = pipeline_execute(p, p->d_stage[turn], 0, first_sample, npart, phi, pps, d_detected, detected_span, nullptr);
   }
+  if (rc != B200_OK) p->bins_preset = false;
   B200_CUDA(cudaEventRecord(p->stage_free[turn], ctx->stream));
   return rc;
 }

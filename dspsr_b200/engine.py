@@ -278,25 +278,40 @@ class Pipeline:
             fh = C.c_void_p(ctx.lib.b200_pipeline_fold(h))
             self.fold = FoldEngine(ctx, self.nchan, self.dnpol, self.dndim, nbin, handle=fh)
 
-    def execute(self, d_input, npart, phi=0.0, pps=0.0, first_sample=0, input_span=0):
+    def _detected(self, npart, out):
+        """(tensor, pointer, span) of the detected series when the pipeline has no fold stage."""
+        if self.nbin:
+            return None, None, 0
+        dspan = npart * self.info.nkeep * self.dndim
+        if out is None:
+            out = torch.empty((self.nchan, self.dnpol, dspan), dtype=torch.float32, device="cuda:%d" % self.ctx.device)
+        else:
+            _need_cuda(out, "out")
+            assert out.shape[0] == self.nchan and out.shape[1] == self.dnpol and out.shape[2] >= dspan
+            dspan = out.shape[2]
+        return out, _ptr(out), dspan
+
+    def execute(self, d_input, npart, phi=0.0, pps=0.0, first_sample=0, input_span=0, out=None):
         _need_cuda(d_input, "d_input")
-        det = None
-        dptr, dspan = None, 0
-        if not self.nbin:
-            dspan = npart * self.info.nkeep * self.dndim
-            det = torch.empty((self.nchan, self.dnpol, dspan), dtype=torch.float32, device=d_input.device)
-            dptr = _ptr(det)
+        det, dptr, dspan = self._detected(npart, out)
         L.check(self.ctx.lib.b200_pipeline_execute(self.h, _ptr(d_input), input_span, first_sample, npart, phi, pps,
                                                    dptr, dspan))
         return det
 
-    def execute_host(self, h_input, npart, phi=0.0, pps=0.0, first_sample=0):
-        """h_input: numpy uint8 array or pinned torch CPU tensor of raw bytes."""
+    def execute_host(self, h_input, npart, phi=0.0, pps=0.0, first_sample=0, out=None):
+        """h_input: numpy uint8 array or pinned torch CPU tensor of raw bytes; it must stay untouched until
+        input_consumed() (the copies are asynchronous)."""
         if isinstance(h_input, torch.Tensor):
             ptr, nbytes = h_input.data_ptr(), h_input.numel() * h_input.element_size()
         else:
             ptr, nbytes = h_input.ctypes.data, h_input.nbytes
-        L.check(self.ctx.lib.b200_pipeline_execute_host(self.h, C.c_void_p(ptr), nbytes, first_sample, npart, phi, pps))
+        det, dptr, dspan = self._detected(npart, out)
+        L.check(self.ctx.lib.b200_pipeline_execute_host(self.h, C.c_void_p(ptr), nbytes, first_sample, npart, phi, pps,
+                                                        dptr, dspan))
+        return det
+
+    def input_consumed(self):
+        L.check(self.ctx.lib.b200_pipeline_input_consumed(self.h))
 
     def synch(self):
         p = np.zeros((self.nchan, self.dnpol, self.nbin * self.dndim), np.float32)
@@ -374,7 +389,7 @@ class Rescale:
             pass
 
 
-def sigproc_digitize8(ctx, x, input_scale=1.0, scale_fac=1.0, rescale=True, bandwidth=-1.0, swap=False):
+def sigproc_digitize8(ctx, x, input_scale=1.0, scale_fac=1.0, rescale=True, bandwidth=-1.0, swap=False, out=None):
     """dsp::SigProcDigitizer::pack (8 bit): detected FPT CUDA tensor [nchan, npol, ndat] -> uint8 [ndat, npol, nchan]."""
     _need_cuda(x, "x")
     nchan, npol, ndat = x.shape
@@ -382,7 +397,8 @@ def sigproc_digitize8(ctx, x, input_scale=1.0, scale_fac=1.0, rescale=True, band
     if not rescale:
         xpol, digi_mean, digi_scale = digi_mean, np.float32(0), np.float32(1)
     digi_scale = np.float32(np.float64(digi_scale) / (np.float64(input_scale) * np.float64(scale_fac)))
-    out = torch.empty((ndat, npol, nchan), dtype=torch.uint8, device=x.device)
+    if out is None:
+        out = torch.empty((ndat, npol, nchan), dtype=torch.uint8, device=x.device)
     L.check(ctx.lib.b200_sigproc_digitize8(ctx.h, _ptr(x), ndat, nchan, npol, ndat, float(digi_scale), float(digi_mean),
                                           float(xpol), int(bandwidth > 0), int(swap), _ptr(out)))
     return out

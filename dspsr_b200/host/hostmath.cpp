@@ -156,6 +156,37 @@ class Dedispersion {
     }
   }
 
+  // The same response restricted to channels [chan0, chan0+nloc): what one rank of a channel-sharded
+  // run uploads (SURVEY 8e i; channels are independent, Convolution.C:389-391).  Only where the band
+  // re-ordering of Response::match stays inside a channel: nchan == input_nchan (Convolution), no input swap.
+  int build_channels(unsigned chan0, unsigned nloc, float* H) const {
+    if (p_.nchan != p_.input_nchan || p_.input_swap || chan0 + nloc > p_.nchan) return B200_ERR_UNSUPPORTED;
+    const unsigned ndat = p_.ndat, nchan = p_.nchan;
+    const double bw = p_.bandwidth, cf = p_.centre_frequency;
+    const double sign = bw / std::fabs(bw);
+    const double chanwidth = bw / double(nchan);
+    const double binwidth = chanwidth / double(ndat);
+    double lower_cfreq = cf - 0.5 * bw;
+    if (!p_.input_dc_centred) lower_cfreq += 0.5 * chanwidth;
+    const double dispersion_per_MHz = 1e6 * p_.dispersion_measure / dm_dispersion;
+    std::complex<float>* phasors = reinterpret_cast<std::complex<float>*>(H);
+    for (unsigned ichan = chan0; ichan < chan0 + nloc; ichan++) {
+      const double chan_cfreq = lower_cfreq + double(ichan) * chanwidth;
+      const double coeff = -sign * 2 * M_PI * dispersion_per_MHz / sqr(chan_cfreq);
+      std::complex<float>* row = phasors + uint64_t(ichan - chan0) * ndat;
+      for (unsigned ipt = 0; ipt < ndat; ipt++) {
+        const double freq = double(ipt) * binwidth - 0.5 * chanwidth;
+        const float phase = coeff * sqr(freq) / (chan_cfreq + freq);
+        row[ipt] = std::polar(float(1.0), phase);
+      }
+    }
+    if (chan0 == 0) phasors[0] = 0;
+    if (p_.input_dual_sideband)               // per input channel = per response row here (Response.C:165-171)
+      swap_halves(H, uint64_t(ndat) * nloc * 2, nloc);
+    if (chan0 == 0) H[0] = H[1] = 0.0f;
+    return B200_OK;
+  }
+
   // Dedispersion::build (:291-331,478-556) + Response::match (:132-181) + DC zap (:278,323)
   void build(float* H) const {
     const unsigned ndat = p_.ndat, nchan = p_.nchan;
@@ -225,6 +256,12 @@ int b200_dedispersion_build(const b200_dedispersion* d, float* h_response) {
   if (!d || !h_response || d->ndat == 0) return B200_ERR_INVALID;
   Dedispersion(*d).build(h_response);
   return B200_OK;
+}
+
+int b200_dedispersion_build_channels(const b200_dedispersion* d, unsigned first_chan, unsigned nchan_local,
+                                     float* h_response) {
+  if (!d || !h_response || d->ndat == 0 || nchan_local == 0) return B200_ERR_INVALID;
+  return Dedispersion(*d).build_channels(first_chan, nchan_local, h_response);
 }
 
 // ---- two-bit excision tables ---------------------------------------------------------------------

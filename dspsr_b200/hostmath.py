@@ -33,6 +33,13 @@ def dedispersion(centre_frequency, bandwidth, dm, input_nchan, nchan, input_real
     return d, H
 
 
+def dedispersion_channels(d, first_chan, nchan_local):
+    """Rows [first_chan, first_chan+nchan_local) of the matched response of a prepared `d` (channel shard)."""
+    H = np.zeros((nchan_local, d.ndat), np.complex64)
+    L.check(L.load().b200_dedispersion_build_channels(C.byref(d), first_chan, nchan_local, H.ctypes.data_as(C.c_void_p)))
+    return H
+
+
 class Polyco:
     """TEMPO polyco predictor (Pulsar::Predictor::phase / frequency as used by Fold.C:943-958)."""
 

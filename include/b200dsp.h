@@ -238,10 +238,16 @@ int b200_pipeline_info(const b200_pipeline* pipe, b200_fb_info* info);
 int b200_pipeline_execute(b200_pipeline* pipe, const void* d_input, uint64_t input_span, uint64_t first_sample,
                           uint64_t npart, double phi, double phase_per_sample, float* d_detected,
                           uint64_t detected_span);
-/* Same, from HOST memory (pinned or pageable): copies nbytes to the device on the pipeline's
- * stream first (File::load_bytes_device, Kernel/Classes/File.C:213-272). */
+/* Same, from HOST memory (pinned or pageable; File::load_bytes_device, Kernel/Classes/File.C:213-272): the bytes
+ * are copied chunk by chunk on a private copy stream into one of two staging buffers while the kernels of the
+ * previous chunk run.  The call RETURNS BEFORE THE COPIES HAVE FINISHED: h_input must stay untouched until
+ * b200_pipeline_input_consumed (or any later synchronisation of the pipeline's stream) has returned. */
 int b200_pipeline_execute_host(b200_pipeline* pipe, const void* h_input, uint64_t nbytes, uint64_t first_sample,
-                               uint64_t npart, double phi, double phase_per_sample);
+                               uint64_t npart, double phi, double phase_per_sample, float* d_detected,
+                               uint64_t detected_span);
+/* Blocks the calling thread until every host buffer handed to b200_pipeline_execute_host so far has been read
+ * (the copy stream is idle); kernels may still be running. */
+int b200_pipeline_input_consumed(b200_pipeline* pipe);
 int b200_pipeline_synch(b200_pipeline* pipe, float* h_profile, unsigned* h_hits, uint64_t* ndat_total);
 int b200_pipeline_zero(b200_pipeline* pipe);
 b200_fold* b200_pipeline_fold(b200_pipeline* pipe);
@@ -300,6 +306,11 @@ int b200_dedispersion_prepare(b200_dedispersion* d);
 /* Dedispersion::build (:310-331,478-556) then Response::match and the DC zap (:278):
  * h_response receives nchan*ndat complex floats in the order the FFT produces them. */
 int b200_dedispersion_build(const b200_dedispersion* d, float* h_response);
+/* The rows [first_chan, first_chan + nchan_local) of the same matched response: the slice one rank of a
+ * channel-sharded run needs (channels are independent, Convolution.C:389-391).  Requires
+ * nchan == input_nchan and no input swap (B200_ERR_UNSUPPORTED otherwise). */
+int b200_dedispersion_build_channels(const b200_dedispersion* d, unsigned first_chan, unsigned nchan_local,
+                                     float* h_response);
 int64_t b200_optimal_fft_length(uint64_t nbadperfft, uint64_t nfft_max);
 
 /* TEMPO polyco block (what Pulsar::Predictor::phase/frequency evaluate for Fold.C:943-958). */

@@ -102,6 +102,7 @@ class Pipe(C.Structure):
         ("detect_state", C.c_int),
         ("detect_ndim", C.c_uint),
         ("nbin", C.c_uint),
+        ("twobit", C.c_void_p),
     ]
 
 
@@ -401,11 +402,14 @@ def polyco_frequency(pc, day, sec, frac):
 
 
 # ----------------------------------------------------------------------------- whole path
-def make_pipe(unpack_fmt, input_nchan, npol, ndim, lut, scale, fb, conv, H, detect_state, detect_ndim, nbin):
+def make_pipe(unpack_fmt, input_nchan, npol, ndim, lut, scale, fb, conv, H, detect_state, detect_ndim, nbin,
+              twobit=None):
+    """unpack_fmt: 0 CASPSR, 1 generic 8-bit, 2 MeerKAT, 3 UWB, 5 two-bit (pass `twobit`, a TwoBit)."""
     p = Pipe()
     p.unpack_fmt = unpack_fmt
     p.input_nchan, p.npol, p.ndim = input_nchan, npol, ndim
-    p._keep = (lut, H)
+    p._keep = (lut, H, twobit)
+    p.twobit = twobit.h if twobit is not None else None
     p.lut = lut.ctypes.data if lut is not None else None
     p.scale = scale
     p.use_filterbank = int(fb is not None)
@@ -426,15 +430,65 @@ def pipe_profile_shape(p):
     return out_nchan, onpol, p.nbin * ondim
 
 
-def pipe_run(p, raw, nblock, parts_per_block, phi, pps, nthread=1):
+def pipe_run(p, raw, nblock, parts_per_block, phi, pps, nthread=1, with_total=False):
+    """-> (profile, hits[, ndat_total]): nblock Fold calls of parts_per_block parts each, `dspsr -t nthread` style."""
     shape = pipe_profile_shape(p)
     profile = np.zeros(shape, np.float32)
     hits = np.zeros(p.nbin, np.uint32)
     phi = np.ascontiguousarray(phi, np.float64)
     pps = np.ascontiguousarray(pps, np.float64)
+    ntot = C.c_uint64(0)
     lib().orc_pipe_run(C.byref(p), _p(raw), C.c_uint64(nblock), C.c_uint64(parts_per_block), _p(phi), _p(pps),
-                       C.c_uint(nthread), _p(profile), _p(hits))
+                       C.c_uint(nthread), _p(profile), _p(hits), C.byref(ntot))
+    if ntot.value == 2 ** 64 - 1:
+        raise RuntimeError("oracle: the reference would throw here (weights exhausted, Fold.C:699 / WeightedTimeSeries.C:626)")
+    if with_total:
+        return profile, hits, ntot.value
     return profile, hits
+
+
+def pipe_block_detected(p, raw, ipart0, npart):
+    """One block of the path without fold: the detected series [out_nchan, out_npol, npart*nkeep*out_ndim]."""
+    out_nchan = p.fb.nchan if p.use_filterbank else p.conv.nchan
+    nkeep = p.fb.nkeep if p.use_filterbank else p.conv.n_fft - p.conv.nfilt_pos - p.conv.nfilt_neg
+    onpol, ondim = detect_shape(p.detect_state, p.detect_ndim)
+    det = np.zeros((out_nchan, onpol, npart * nkeep * ondim), np.float32)
+    f = lib().orc_pipe_block
+    f.restype = C.c_uint64
+    f(C.byref(p), _p(raw), C.c_uint64(ipart0), C.c_uint64(npart), C.c_double(0), C.c_double(0), None, None, _p(det))
+    return det
+
+
+def convolve_weights(weights, ndat_per_weight, weight_idat, ndat, nfft, nkeep):
+    """WeightedTimeSeries::convolve_weights (WeightedTimeSeries.C:582-690) on a copy of `weights`."""
+    w = np.ascontiguousarray(weights, np.uint32).copy()
+    rc = lib().orc_convolve_weights(_p(w), C.c_uint64(w.size), C.c_uint(ndat_per_weight), C.c_uint64(weight_idat),
+                                    C.c_uint64(ndat), C.c_uint(nfft), C.c_uint(nkeep))
+    if rc != 0:
+        raise RuntimeError("convolve_weights: end_weight > nweights")
+    return w
+
+
+def scrunch_weights(weights, ndat_per_weight, weight_idat, nscrunch):
+    """WeightedTimeSeries::scrunch_weights (:692-780): -> (weights, ndat_per_weight, weight_idat)."""
+    w = np.ascontiguousarray(weights, np.uint32).copy()
+    n, npw, wi = C.c_uint64(w.size), C.c_uint(ndat_per_weight), C.c_uint64(weight_idat)
+    lib().orc_scrunch_weights(_p(w), C.byref(n), C.byref(npw), C.byref(wi), C.c_uint(nscrunch))
+    return w[: n.value], npw.value, wi.value
+
+
+def fold_plan_weighted(phi, pps, nbin, idat_start, ndat, weights, ndat_per_weight, weight_idat):
+    """Fold.C:687-788 with a weighted input: -> (binplan with nbin for skipped samples, hits, ndat_folded)."""
+    binplan = np.zeros(ndat, np.uint32)
+    hits = np.zeros(nbin, np.uint32)
+    w = np.ascontiguousarray(weights, np.uint32)
+    f = lib().orc_fold_plan_weighted
+    f.restype = C.c_uint64
+    n = f(C.c_double(phi), C.c_double(pps), C.c_uint(nbin), C.c_uint64(idat_start), C.c_uint64(ndat), _p(w),
+          C.c_uint64(w.size), C.c_uint(ndat_per_weight), C.c_uint64(weight_idat), _p(binplan), _p(hits), None)
+    if n == 2 ** 64 - 1:
+        raise RuntimeError("fold: iweight >= nweights (Fold.C:699)")
+    return binplan, hits, n
 
 
 # ----------------------------------------------------------------------------- a15

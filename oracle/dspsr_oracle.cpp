@@ -778,6 +778,111 @@ uint64_t orc_fold_plan(double phi, double phase_per_sample, unsigned nbin, uint6
   return ndat_folded;
 }
 
+// The same loop with a WeightedTimeSeries input (Fold.C:687-716 set-up, :746-763 per sample): samples of a
+// window whose weight is zero get binplan = nbin (not folded, no hit).  Returns ndat_folded, or
+// UINT64_MAX where the reference throws ("iweight >= nweights").
+uint64_t orc_fold_plan_weighted(double phi, double phase_per_sample, unsigned nbin, uint64_t idat_start, uint64_t ndat,
+                                const unsigned* weights, uint64_t nweights, unsigned ndatperweight,
+                                uint64_t weight_idat, unsigned* binplan, unsigned* hits, double* phi_out) {
+  if (!ndatperweight || !weights) return orc_fold_plan(phi, phase_per_sample, nbin, ndat, binplan, hits, phi_out);
+  const double double_nbin = double(nbin);
+  uint64_t ndat_folded = 0;
+  uint64_t iweight = (idat_start + weight_idat) / ndatperweight;
+  uint64_t idat_nextweight = (iweight + 1) * ndatperweight - weight_idat;
+  if (iweight >= nweights) return UINT64_MAX;
+  bool bad_data = weights[iweight] == 0;
+  for (uint64_t idat = idat_start; idat < idat_start + ndat; idat++) {
+    if (idat >= idat_nextweight) {
+      iweight++;
+      if (iweight >= nweights) return UINT64_MAX;       // assert (iweight < nweights), Fold.C:751
+      bad_data = weights[iweight] == 0;
+      idat_nextweight += ndatperweight;
+    }
+    phi -= std::floor(phi);
+    double double_ibin = phi * double_nbin;
+    unsigned ibin = unsigned(double_ibin);
+    phi += phase_per_sample;
+    binplan[idat - idat_start] = ibin;
+    if (bad_data)
+      binplan[idat - idat_start] = nbin;
+    else {
+      if (hits) hits[ibin]++;
+      ndat_folded++;
+    }
+  }
+  if (phi_out) *phi_out = phi;
+  return ndat_folded;
+}
+
+// WeightedTimeSeries::convolve_weights (Kernel/Classes/WeightedTimeSeries.C:582-690): a transform that
+// contains a bad window is flagged as a whole; the flagging of transform i is applied while looking at
+// transform i+1 ("flag only the previous data set"), so that it does not influence the next test.
+// Returns 0, or -1 where the reference throws (end_weight > nweights).
+int orc_convolve_weights(unsigned* weights, uint64_t nweights_tot, unsigned ndat_per_weight, uint64_t weight_idat,
+                         uint64_t ndat, unsigned nfft, unsigned nkeep) {
+  if (ndat_per_weight >= nfft) return 0;
+  if (ndat + nkeep < nfft) return 0;
+  if (ndat_per_weight == 0) return 0;
+  const double weights_per_dat = 1.0 / ndat_per_weight;
+  const uint64_t blocks = (ndat + nkeep - nfft) / nkeep;
+  const uint64_t end_idat = blocks * nkeep;
+  uint64_t zero_start = 0, zero_end = 0;
+  for (uint64_t start_idat = 0; start_idat < end_idat; start_idat += nkeep) {
+    const uint64_t wt_idat = start_idat + weight_idat;
+    const uint64_t start_weight = uint64_t(wt_idat * weights_per_dat);
+    const uint64_t end_weight = uint64_t(std::ceil((wt_idat + nfft) * weights_per_dat));
+    if (end_weight > nweights_tot) return -1;
+    uint64_t zero_weights = 0;
+    for (uint64_t iweight = start_weight; iweight < end_weight; iweight++)
+      if (weights[iweight] == 0) zero_weights++;
+    for (uint64_t iweight = zero_start; iweight < zero_end; iweight++) weights[iweight] = 0;
+    if (zero_weights == 0)
+      zero_start = zero_end = 0;
+    else {
+      zero_start = start_weight;
+      zero_end = uint64_t(std::ceil((start_idat + nkeep) * weights_per_dat));
+    }
+  }
+  for (uint64_t iweight = zero_start; iweight < zero_end; iweight++) weights[iweight] = 0;
+  return 0;
+}
+
+// WeightedTimeSeries::scrunch_weights (WeightedTimeSeries.C:692-780), in place; the three attributes are
+// updated like the members of the reference.
+void orc_scrunch_weights(unsigned* weights, uint64_t* nweights, unsigned* ndat_per_weight, uint64_t* weight_idat,
+                         unsigned nscrunch) {
+  const uint64_t nweights_tot = *nweights;
+  if (!*ndat_per_weight) return;
+  const double points_per_weight = double(*ndat_per_weight) / double(nscrunch);
+  if (points_per_weight >= 1.0) {
+    *ndat_per_weight = unsigned(points_per_weight);
+    const bool leftover = (*weight_idat % *ndat_per_weight != 0);
+    *weight_idat /= *ndat_per_weight;
+    if (leftover) (*weight_idat)++;
+    return;
+  }
+  uint64_t new_nweights = nweights_tot / nscrunch;
+  const uint64_t extra = nweights_tot % nscrunch;
+  if (extra) new_nweights++;
+  for (uint64_t iwt = 0; iwt < new_nweights; iwt++) {
+    unsigned* indi_weight = weights + iwt * nscrunch;
+    if ((iwt + 1) * nscrunch > nweights_tot) nscrunch = unsigned(extra);
+    for (unsigned ivt = 0; ivt < nscrunch; ivt++) {
+      if (*indi_weight == 0) {
+        weights[iwt] = 0;
+        break;
+      } else if (ivt == 0)
+        weights[iwt] = *indi_weight;
+      else
+        weights[iwt] += *indi_weight;
+      indi_weight++;
+    }
+    weights[iwt] /= nscrunch;
+  }
+  *nweights = new_nweights;
+  *ndat_per_weight = 1;
+}
+
 // Fold::fold accumulate, OrderFPT (Fold.C:835-873).  profile planes:
 // (ichan*npol+ipol)*nbin*ndim, element [ibin*ndim + idim]; float +=, sequential.
 void orc_fold(const float* in, uint64_t in_span, unsigned nchan, unsigned npol, unsigned ndim,
@@ -917,7 +1022,7 @@ void orc_phaseseries_combine(float* data, unsigned* hits, double* integration_le
 extern "C" {
 
 struct orc_pipe {
-  int unpack_fmt;            // 0 CASPSR 8-bit, 1 generic 8-bit TFP, 2 MeerKAT, 3 UWB 16-bit
+  int unpack_fmt;            // 0 CASPSR 8-bit, 1 generic 8-bit TFP, 2 MeerKAT, 3 UWB 16-bit, 5 two-bit (CPSR2 convention)
   unsigned input_nchan, npol, ndim;
   const float* lut;          // 256-entry table (fmt 0,1)
   float scale;               // fmt 2
@@ -928,19 +1033,22 @@ struct orc_pipe {
   int detect_state;          // 0 Intensity 1 PPQQ 2 Coherence 3 Stokes
   unsigned detect_ndim;      // 1,2,4 (Coherence/Stokes)
   unsigned nbin;             // 0 = no fold
+  const orc_twobit* twobit;  // fmt 5: two-bit excision unpacker (WeightedTimeSeries: weights travel to Fold)
 };
 
-static uint64_t raw_bytes_per_sample(const orc_pipe* p) {
-  unsigned nbit = (p->unpack_fmt == 3) ? 16 : 8;
-  return uint64_t(p->input_nchan) * p->npol * p->ndim * nbit / 8;
+static uint64_t raw_bits_per_sample(const orc_pipe* p) {
+  unsigned nbit = (p->unpack_fmt == 3) ? 16 : (p->unpack_fmt == 5) ? 2 : 8;
+  return uint64_t(p->input_nchan) * p->npol * p->ndim * nbit;
 }
 
-static void pipe_unpack(const orc_pipe* p, const uint8_t* raw, uint64_t ndat, float* out, uint64_t span) {
+static void pipe_unpack(const orc_pipe* p, const uint8_t* raw, uint64_t ndat, float* out, uint64_t span,
+                        unsigned* weights, uint64_t nweights) {
   switch (p->unpack_fmt) {
     case 0: orc_unpack_caspsr(raw, ndat, p->lut, out, span); break;
     case 1: orc_unpack_generic8(raw, ndat, p->input_nchan, p->npol, p->ndim, p->lut, out, span, nullptr); break;
     case 2: orc_unpack_meerkat(reinterpret_cast<const int8_t*>(raw), ndat, p->input_nchan, p->npol, p->scale, 1, out, span); break;
     case 3: orc_unpack_uwb(reinterpret_cast<const int16_t*>(raw), ndat, p->npol, out, span); break;
+    case 5: orc_unpack_twobit(p->twobit, raw, ndat, p->npol, out, span, weights, nweights); break;
   }
 }
 
@@ -949,27 +1057,52 @@ static void pipe_unpack(const orc_pipe* p, const uint8_t* raw, uint64_t ndat, fl
 // block's first output sample and phase advance per output sample (Fold.C:650-657,718-720).
 // profile: [out_nchan][out_npol][nbin][out_ndim] (+=), hits: [nbin] (+=).
 // detected (nullable): receives the detected block, planes of nkeep*npart*out_ndim floats.
-void orc_pipe_block(const orc_pipe* p, const uint8_t* raw, uint64_t ipart0, uint64_t npart,
-                    double phi, double pps, float* profile, unsigned* hits, float* detected) {
+// Two-bit input is a WeightedTimeSeries: the per-window weights go through
+// convolve_weights/scrunch_weights (Filterbank.C:279-307, Convolution.C:312-319) and Fold
+// skips the samples of flagged windows (Fold.C:687-716,746-763).  Returns the number of samples
+// folded (ndat_folded), or UINT64_MAX where the reference would throw.
+uint64_t orc_pipe_block(const orc_pipe* p, const uint8_t* raw, uint64_t ipart0, uint64_t npart,
+                        double phi, double pps, float* profile, unsigned* hits, float* detected) {
   const unsigned step = p->use_filterbank ? p->fb.nsamp_step : p->conv.nsamp_step;
   const unsigned overlap = p->use_filterbank ? p->fb.nsamp_overlap : p->conv.nsamp_overlap;
   const uint64_t ndat_in = npart * step + overlap;
   // The raw layouts are periodic in `res` samples (Unpacker resolution: CASPSR 4, MeerKAT
-  // 256-sample heaps, UWB 2048-sample blocks).  As IOManager/Unpacker::transformation do
-  // (Unpacker.C:82-111), unpack the enclosing aligned range and seek to the requested sample.
-  const unsigned res = p->unpack_fmt == 0 ? 4 : p->unpack_fmt == 2 ? 256 : p->unpack_fmt == 3 ? 2048 : 1;
+  // 256-sample heaps, UWB 2048-sample blocks, two-bit ndat_per_weight).  As IOManager/Unpacker::transformation
+  // do (Unpacker.C:82-111), unpack the enclosing aligned range and seek to the requested sample.
+  const unsigned res = p->unpack_fmt == 0 ? 4 : p->unpack_fmt == 2 ? 256 : p->unpack_fmt == 3 ? 2048
+                       : p->unpack_fmt == 5 ? p->twobit->ndat_per_weight : 1;
   const uint64_t s0 = ipart0 * step;
   const uint64_t a0 = (s0 / res) * res;
   const uint64_t a1 = ((s0 + ndat_in + res - 1) / res) * res;
   const uint64_t seek = s0 - a0;
   const uint64_t in_span = (a1 - a0) * p->ndim;
   std::vector<float> unpacked_v(uint64_t(p->input_nchan) * p->npol * in_span);
-  pipe_unpack(p, raw + a0 * raw_bytes_per_sample(p), a1 - a0, unpacked_v.data(), in_span);
+  std::vector<unsigned> weights;
+  uint64_t nweights = 0, weight_idat = 0;
+  unsigned ndat_per_weight = 0;
+  if (p->unpack_fmt == 5) {
+    ndat_per_weight = p->twobit->ndat_per_weight;
+    nweights = (a1 - a0) / ndat_per_weight;
+    weights.resize(nweights * p->npol);
+    weight_idat = seek;                       // TimeSeries::seek -> WeightedTimeSeries::seek moves weight_idat
+  }
+  pipe_unpack(p, raw + a0 * raw_bits_per_sample(p) / 8, a1 - a0, unpacked_v.data(), in_span, weights.data(), nweights);
   struct { float* p; float* data() { return p; } } unpacked{unpacked_v.data() + seek * p->ndim};
 
-  unsigned out_nchan, nkeep;
-  if (p->use_filterbank) { out_nchan = p->fb.nchan; nkeep = p->fb.nkeep; }
-  else { out_nchan = p->conv.nchan; nkeep = p->conv.n_fft - p->conv.nfilt_pos - p->conv.nfilt_neg; }
+  unsigned out_nchan, nkeep, nsamp_fft, tres_ratio;
+  if (p->use_filterbank) {
+    out_nchan = p->fb.nchan; nkeep = p->fb.nkeep; nsamp_fft = p->fb.nsamp_fft;
+    tres_ratio = p->fb.nsamp_fft / p->fb.freq_res;         // Filterbank.C:289
+  } else {
+    out_nchan = p->conv.nchan; nkeep = p->conv.n_fft - p->conv.nfilt_pos - p->conv.nfilt_neg; nsamp_fft = p->conv.nsamp_fft;
+    tres_ratio = p->conv.input_real ? 2 : 1;                 // Convolution.C:317-318 (Nyquist input -> scrunch 2)
+  }
+  if (ndat_per_weight) {
+    // polarisation 0's weights (identical in all polarisations after mask_weights; npol_weight = 1)
+    if (orc_convolve_weights(weights.data(), nweights, ndat_per_weight, weight_idat, ndat_in, nsamp_fft, step) != 0)
+      return UINT64_MAX;
+    if (tres_ratio > 1 || p->use_filterbank) orc_scrunch_weights(weights.data(), &nweights, &ndat_per_weight, &weight_idat, tres_ratio);
+  }
   const uint64_t ndat_out = npart * nkeep;
   const uint64_t v_span = ndat_out * 2;
   std::vector<float> volt(uint64_t(out_nchan) * p->npol * v_span);
@@ -990,34 +1123,47 @@ void orc_pipe_block(const orc_pipe* p, const uint8_t* raw, uint64_t ipart0, uint
   orc_detect(p->detect_state, d_ndim, volt.data(), v_span, out_nchan, p->npol, ndat_out, det, d_span);
   std::vector<float>().swap(volt);
 
+  uint64_t ndat_folded = 0;
   if (p->nbin) {
     std::vector<unsigned> binplan(ndat_out);
-    orc_fold_plan(phi, pps, p->nbin, ndat_out, binplan.data(), hits, nullptr);
+    ndat_folded = orc_fold_plan_weighted(phi, pps, p->nbin, 0, ndat_out, ndat_per_weight ? weights.data() : nullptr,
+                                         nweights, ndat_per_weight, weight_idat, binplan.data(), hits, nullptr);
+    if (ndat_folded == UINT64_MAX) return ndat_folded;
     orc_fold(det, d_span, out_nchan, d_npol, d_ndim, 0, ndat_out, binplan.data(), p->nbin, profile);
   }
+  return ndat_folded;
 }
 
 // P threads, thread t takes blocks t, t+P, ... ; each block = parts_per_block parts.
 // phi[b], pps[b] per block.  profile/hits must be zeroed by the caller.
 void orc_pipe_run(const orc_pipe* p, const uint8_t* raw, uint64_t nblock, uint64_t parts_per_block,
-                  const double* phi, const double* pps, unsigned nthread, float* profile, unsigned* hits) {
+                  const double* phi, const double* pps, unsigned nthread, float* profile, unsigned* hits,
+                  uint64_t* ndat_total) {
   unsigned out_nchan = p->use_filterbank ? p->fb.nchan : p->conv.nchan;
   unsigned per = (p->detect_state >= 2) ? 4 : (p->detect_state == 1 ? 2 : 1);
   const uint64_t nfloat = uint64_t(out_nchan) * per * p->nbin;
   if (nthread < 1) nthread = 1;
   std::vector<std::vector<float>> profs(nthread, std::vector<float>(nfloat, 0.f));
   std::vector<std::vector<unsigned>> hts(nthread, std::vector<unsigned>(p->nbin, 0u));
+  std::vector<uint64_t> folded(nthread, 0);
   std::vector<std::thread> th;
   for (unsigned t = 0; t < nthread; t++)
     th.emplace_back([&, t]() {
-      for (uint64_t b = t; b < nblock; b += nthread)
-        orc_pipe_block(p, raw, b * parts_per_block, parts_per_block, phi ? phi[b] : 0.0, pps ? pps[b] : 0.0,
-                       profs[t].data(), hts[t].data(), nullptr);
+      for (uint64_t b = t; b < nblock; b += nthread) {
+        const uint64_t n = orc_pipe_block(p, raw, b * parts_per_block, parts_per_block, phi ? phi[b] : 0.0,
+                                          pps ? pps[b] : 0.0, profs[t].data(), hts[t].data(), nullptr);
+        folded[t] = (n == UINT64_MAX || folded[t] == UINT64_MAX) ? UINT64_MAX : folded[t] + n;
+      }
     });
   for (auto& t : th) t.join();
   double il = 0; uint64_t nt = 0;
   for (unsigned t = 0; t < nthread; t++)
-    orc_phaseseries_combine(profile, hits, &il, &nt, profs[t].data(), hts[t].data(), 0, 0, nfloat, p->nbin);
+    orc_phaseseries_combine(profile, hits, &il, &nt, profs[t].data(), hts[t].data(), 0,
+                            folded[t], nfloat, p->nbin);
+  if (ndat_total) {
+    *ndat_total = nt;
+    for (unsigned t = 0; t < nthread; t++) if (folded[t] == UINT64_MAX) *ndat_total = UINT64_MAX;
+  }
 }
 
 }  // extern "C"

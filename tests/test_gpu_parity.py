@@ -515,7 +515,8 @@ def test_subint_folder_cuts_at_division_boundaries(ctx, oracle):
     sub-integration equals the oracle fold of exactly the samples of that division, sliced per block with
     Fold::fold's phase set-up, and the hit totals add up to the stream length."""
     torch, E = _torch(), _E()
-    from dspsr_b200 import hostmath as HM, workloads as W
+    from dspsr_b200 import hostmath as HM
+    import workloads as W
     from dspsr_b200.subint import SubintFolder
     nchan, npol, ndim, nbin = 3, 1, 4, 256
     rate = 1.5625e6 / 8

@@ -78,7 +78,7 @@ def test_phase_segments_equal_sequential_recurrence(oracle):
 
 def test_hostmath_bitexact_with_oracle(oracle):
     from dspsr_b200 import hostmath as HM
-    from dspsr_b200 import workloads as W
+    import workloads as W
     for twos in (True, False):
         a, sa = HM.bittable8(twos)
         b, sb = oracle.bittable8(twos)

@@ -238,7 +238,7 @@ def test_fold_boxcar_and_hits(oracle):
 
 
 def test_polyco_fixture(oracle):
-    from dspsr_b200 import workloads as W
+    import workloads as W
     pc = oracle.polyco_parse(W.polyco_text())
     assert pc.tmid_day == 55299 and pc.ncoef == 15 and pc.f0 == pytest.approx(11.1946499395)
     assert pc.tmid_sec == pytest.approx(0.1041666666 * 86400, abs=1e-3)

@@ -75,7 +75,7 @@ def test_detect_products_match_reference(ref, oracle, state, fn):
 
 def test_dada_header_keys_parse_like_reference(ref):
     """ascii_header.c ascii_header_get on the cfg1 header the bench writes."""
-    from dspsr_b200 import workloads as W
+    import workloads as W
     hdr = W.dada_header(W.CFG1).encode()
     assert len(hdr) == 4096
     buf = C.create_string_buffer(hdr, 4096)
