@@ -174,7 +174,7 @@ class OracleApi:
 
         class P:
             def phase(self, mjd):
-                return O.polyco_phase(pc, *mjd)
+                return O.polyco_phase(pc, *mjd)[0]
 
             def frequency(self, mjd):
                 return O.polyco_frequency(pc, *mjd)

@@ -155,7 +155,7 @@ def main():
                 opc = O.polyco_parse(W.polyco_text())
 
                 class OP:
-                    phase = staticmethod(lambda m: O.polyco_phase(opc, *m))
+                    phase = staticmethod(lambda m: O.polyco_phase(opc, *m)[0])
                     frequency = staticmethod(lambda m: O.polyco_frequency(opc, *m))
                 import ctypes as C
                 O.lib().orc_pipe_block.restype = C.c_uint64
