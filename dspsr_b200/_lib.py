@@ -117,6 +117,37 @@ class Polyco(C.Structure):
     ]
 
 
+class Mjd(C.Structure):
+    _fields_ = [("day", C.c_int), ("sec", C.c_int), ("frac", C.c_double)]
+
+
+class Observation(C.Structure):
+    _fields_ = [
+        ("telescope", C.c_char * 32), ("receiver", C.c_char * 32), ("source", C.c_char * 32),
+        ("mode", C.c_char * 32), ("machine", C.c_char * 32), ("format", C.c_char * 32),
+        ("centre_frequency", C.c_double), ("bandwidth", C.c_double), ("rate", C.c_double), ("scale", C.c_double),
+        ("dispersion_measure", C.c_double), ("rotation_measure", C.c_double),
+        ("nchan", C.c_uint), ("npol", C.c_uint), ("ndim", C.c_uint), ("nbit", C.c_uint),
+        ("state", C.c_int), ("type", C.c_int), ("basis", C.c_int), ("swap", C.c_int), ("nsub_swap", C.c_int),
+        ("dc_centred", C.c_int),
+        ("start_time", Mjd),
+        ("ndat", C.c_uint64),
+    ]
+
+
+class PhaseSeries(C.Structure):
+    _fields_ = [
+        ("obs", Observation),
+        ("nbin", C.c_uint), ("hits_nchan", C.c_uint),
+        ("integration_length", C.c_double),
+        ("ndat_total", C.c_uint64), ("ndat_expected", C.c_uint64),
+        ("end_time", Mjd),
+        ("folding_period", C.c_double), ("reference_phase", C.c_double),
+        ("data", C.c_void_p),
+        ("hits", C.c_void_p),
+    ]
+
+
 class PhaseSegment(C.Structure):
     _fields_ = [
         ("start", C.c_uint64),
@@ -187,6 +218,13 @@ SIGNATURES = {
     "b200_pipeline_synch": (_i, [_vp, _vp, _vp, C.POINTER(_u64)]),
     "b200_pipeline_zero": (_i, [_vp]),
     "b200_pipeline_fold": (_vp, [_vp]),
+    "b200_pipeline_set_observation": (_i, [_vp, C.POINTER(Observation)]),
+    "b200_pipeline_set_predictor": (_i, [_vp, C.POINTER(Polyco), _d]),
+    "b200_pipeline_set_folding_period": (_i, [_vp, _d, _d]),
+    "b200_pipeline_execute_obs": (_i, [_vp, _vp, _u64, _u64, _u64, _u64]),
+    "b200_pipeline_execute_host_obs": (_i, [_vp, _vp, _u64, _u64, _u64, _u64]),
+    "b200_pipeline_get_phase_series": (_i, [_vp, C.POINTER(PhaseSeries)]),
+    "b200_pipeline_reset": (_i, [_vp]),
     "b200_bittable8": (_i, [_i, _vp, C.POINTER(_d)]),
     "b200_dedispersion_prepare": (_i, [C.POINTER(Dedispersion)]),
     "b200_dedispersion_build": (_i, [C.POINTER(Dedispersion), _vp]),
@@ -195,6 +233,15 @@ SIGNATURES = {
     "b200_polyco_parse": (_i, [C.c_char_p, C.POINTER(Polyco)]),
     "b200_polyco_phase": (_d, [C.POINTER(Polyco), _i, _i, _d, C.POINTER(_d)]),
     "b200_polyco_frequency": (_d, [C.POINTER(Polyco), _i, _i, _d]),
+    "b200_observation_combinable": (_i, [C.POINTER(Observation), C.POINTER(Observation), C.c_char_p, C.c_uint]),
+    "b200_mjd_diff": (_d, [C.POINTER(Mjd), C.POINTER(Mjd)]),
+    "b200_mjd_add": (Mjd, [C.POINTER(Mjd), _d]),
+    "b200_phase_series_mixable": (_i, [C.POINTER(PhaseSeries), C.POINTER(Observation), C.c_uint, C.c_int64, C.c_int64]),
+    "b200_phase_series_folded": (_i, [C.POINTER(PhaseSeries), _u64, _u64]),
+    "b200_phase_series_combine": (_i, [C.POINTER(PhaseSeries), C.POINTER(PhaseSeries)]),
+    "b200_phase_series_normalise": (_i, [C.POINTER(PhaseSeries), _vp, _vp, C.POINTER(C.c_uint)]),
+    "b200_phase_series_unload": (_i, [C.POINTER(PhaseSeries), C.c_char_p]),
+    "b200_phase_series_load": (_i, [C.c_char_p, C.POINTER(PhaseSeries), _vp, _vp, _vp, _vp]),
     "b200_phase_segments": (C.c_int64, [_d, _d, _u64, C.POINTER(PhaseSegment), _u64, C.POINTER(_d)]),
     "b200_phase_bins_sequential": (None, [_d, _d, _u, _u64, _vp, C.POINTER(_d)]),
 }

@@ -46,6 +46,13 @@ struct b200_pipeline {
   uint64_t volt_floats;
   float* d_det;
   uint64_t det_floats;
+  // observation-driven folding (b200_pipeline_execute_obs): attributes of the raw input, of the series that
+  // reaches Fold, the predictor, and the PhaseSeries attributes that Fold::transformation / Fold::fold maintain
+  bool have_obs, have_poly;
+  b200_observation raw_obs, fold_obs;
+  b200_polyco poly;
+  double folding_period, reference_phase;
+  b200_phase_series ps;
 };
 
 namespace b200 {
@@ -403,6 +410,148 @@ int b200_pipeline_execute_host(b200_pipeline* p, const void* h_input, uint64_t n
   if (rc != B200_OK) p->bins_preset = false;
   B200_CUDA(cudaEventRecord(p->stage_free[turn], ctx->stream));
   return rc;
+}
+
+// ---- observation-driven blocks ---------------------------------------------------------------------
+int b200_pipeline_set_observation(b200_pipeline* p, const b200_observation* raw) {
+  B200_REQUIRE(p && raw, "b200_pipeline_set_observation: null argument");
+  B200_REQUIRE(raw->rate > 0, "b200_pipeline_set_observation: rate must be positive");
+  B200_REQUIRE(raw->nchan == p->desc.fb.input_nchan && raw->npol == p->desc.fb.npol,
+               "observation nchan/npol (%u,%u) != pipeline input (%u,%u)", raw->nchan, raw->npol,
+               p->desc.fb.input_nchan, p->desc.fb.npol);
+  b200_fb_plan* fb = p->fb;
+  p->raw_obs = *raw;
+  b200_observation o = *raw;
+  o.nchan = fb->nchan_out;
+  if (fb->conv_path || fb->C == 1) {
+    // Convolution::prepare_output (Convolution.C:286-305): same rate (halved for Nyquist input, which the engine
+    // turns into an analytic signal), scale *= nsamp_fft * n_fft
+    o.rate = raw->rate * double(fb->F) / double(fb->nsamp_fft);
+    o.scale = raw->scale * (double(fb->nsamp_fft) * double(fb->Nc));
+  } else {
+    // Filterbank::prepare_output (Filterbank.C:325-371)
+    o.rate = raw->rate * (double(fb->F) / double(fb->nsamp_fft));
+    o.scale = raw->scale * (double(fb->Nc) * double(fb->F));
+    o.dc_centred = int(fb->F % 2);
+    const bool dual = !p->desc.fb.input_real;
+    if (dual) {
+      if (raw->nchan > 1) o.nsub_swap = int(raw->nchan);
+      else o.swap = 1;
+    }
+  }
+  // Detection::transformation: state and shape of the detected series
+  o.state = p->desc.detect_state;
+  o.npol = p->dnpol;
+  o.ndim = p->dndim;
+  o.nbit = 32;
+  p->fold_obs = o;
+  p->have_obs = true;
+  return B200_OK;
+}
+
+int b200_pipeline_set_predictor(b200_pipeline* p, const b200_polyco* pc, double reference_phase) {
+  B200_REQUIRE(p && pc, "b200_pipeline_set_predictor: null argument");
+  p->poly = *pc;
+  p->have_poly = true;
+  p->folding_period = 0.0;
+  p->reference_phase = reference_phase;
+  return B200_OK;
+}
+
+int b200_pipeline_set_folding_period(b200_pipeline* p, double period, double reference_phase) {
+  B200_REQUIRE(p && period > 0, "b200_pipeline_set_folding_period: period must be positive");
+  p->folding_period = period;
+  p->have_poly = false;
+  p->reference_phase = reference_phase;
+  return B200_OK;
+}
+
+// attributes of the block that reaches Fold + its phase: Fold.C:650-657,718-720,943-958
+static int obs_block(b200_pipeline* p, uint64_t npart, uint64_t obs_sample, b200_observation* blk, double* phi, double* pps) {
+  B200_REQUIRE(p->have_obs, "b200_pipeline_execute_obs: call b200_pipeline_set_observation first");
+  B200_REQUIRE(p->desc.nbin, "b200_pipeline_execute_obs: the pipeline has no fold stage");
+  B200_REQUIRE(p->have_poly || p->folding_period > 0, "no polynomial and no period specified (Fold.C:638-640)");
+  b200_fb_plan* fb = p->fb;
+  *blk = p->fold_obs;
+  // the block's first input sample, then change_start_time(nfilt_pos) in output samples (Filterbank.C:370)
+  b200_mjd t = b200_mjd_add(&p->raw_obs.start_time, double(obs_sample) / p->raw_obs.rate);
+  t = b200_mjd_add(&t, double(fb->desc.nfilt_pos) / blk->rate);
+  blk->start_time = t;
+  blk->ndat = npart * fb->nkeep;
+  const b200_mjd mid = b200_mjd_add(&t, 0.5 / blk->rate);                    // midpoint of the first sample
+  double pfold;
+  if (p->folding_period > 0.0) {
+    const double since = b200_mjd_diff(&mid, &p->raw_obs.start_time);
+    *phi = std::fmod(since, p->folding_period) / p->folding_period - p->reference_phase;
+    pfold = p->folding_period;
+  } else {
+    *phi = b200_polyco_phase(&p->poly, mid.day, mid.sec, mid.frac, nullptr) - p->reference_phase;
+    pfold = 1.0 / b200_polyco_frequency(&p->poly, mid.day, mid.sec, mid.frac);
+  }
+  *pps = (1.0 / blk->rate) / pfold;
+  return B200_OK;
+}
+
+static int obs_commit(b200_pipeline* p, const b200_observation* blk) {
+  // Fold::transformation: get_output()->mixable(*input, nbin, idat_start, ndat_fold) ...
+  if (!b200_phase_series_mixable(&p->ps, blk, p->desc.nbin, 0, (int64_t)blk->ndat)) {
+    set_error("PhaseSeries !mixable: the block differs from what has been folded so far");
+    return B200_ERR_INVALID;
+  }
+  p->ps.folding_period = p->folding_period;
+  p->ps.reference_phase = p->reference_phase;
+  // ... Fold::fold: integration_length += ndat_folded / rate, ndat_total += ndat_fold (Fold.C:789-802)
+  return b200_phase_series_folded(&p->ps, blk->ndat, blk->ndat);
+}
+
+int b200_pipeline_execute_obs(b200_pipeline* p, const void* d_input, uint64_t input_span, uint64_t first_sample,
+                              uint64_t npart, uint64_t obs_sample) {
+  B200_REQUIRE(p && d_input, "b200_pipeline_execute_obs: null argument");
+  if (npart == 0) return B200_OK;
+  b200_observation blk;
+  double phi, pps;
+  int rc = obs_block(p, npart, obs_sample, &blk, &phi, &pps);
+  if (rc == B200_OK) rc = pipeline_execute(p, d_input, input_span, first_sample, npart, phi, pps, nullptr, 0, nullptr);
+  if (rc == B200_OK) rc = obs_commit(p, &blk);
+  return rc;
+}
+
+int b200_pipeline_execute_host_obs(b200_pipeline* p, const void* h_input, uint64_t nbytes, uint64_t first_sample,
+                                   uint64_t npart, uint64_t obs_sample) {
+  B200_REQUIRE(p && h_input, "b200_pipeline_execute_host_obs: null argument");
+  if (npart == 0) return B200_OK;
+  b200_observation blk;
+  double phi, pps;
+  int rc = obs_block(p, npart, obs_sample, &blk, &phi, &pps);
+  if (rc == B200_OK) rc = b200_pipeline_execute_host(p, h_input, nbytes, first_sample, npart, phi, pps, nullptr, 0);
+  if (rc == B200_OK) rc = obs_commit(p, &blk);
+  return rc;
+}
+
+int b200_pipeline_get_phase_series(b200_pipeline* p, b200_phase_series* out) {
+  B200_REQUIRE(p && out && p->fold, "b200_pipeline_get_phase_series: null argument or no fold stage");
+  float* data = out->data;
+  unsigned* hits = out->hits;
+  *out = p->ps;
+  out->data = data;
+  out->hits = hits;
+  if (!p->have_obs || p->ps.integration_length == 0.0) {
+    // nothing folded through execute_obs: shape only
+    out->obs.nchan = p->fb->nchan_out; out->obs.npol = p->dnpol; out->obs.ndim = p->dndim;
+    out->nbin = p->desc.nbin; out->hits_nchan = 1;
+  }
+  int rc = B200_OK;
+  if (data) rc = b200_fold_synch(p->fold, data);
+  uint64_t ntot = 0;
+  if (rc == B200_OK && hits) rc = b200_fold_get_hits(p->fold, hits, &ntot);
+  return rc;
+}
+
+int b200_pipeline_reset(b200_pipeline* p) {
+  B200_REQUIRE(p && p->fold, "b200_pipeline_reset: pipeline has no fold stage");
+  p->ps.integration_length = 0.0;
+  p->ps.ndat_total = 0;
+  return b200_fold_zero(p->fold);
 }
 
 int b200_pipeline_synch(b200_pipeline* p, float* h_profile, unsigned* h_hits, uint64_t* ndat_total) {

@@ -310,6 +310,39 @@ class Pipeline:
                                                         dptr, dspan))
         return det
 
+    # ---- observation-driven blocks: the library evaluates the predictor and keeps the PhaseSeries attributes ----
+    def set_observation(self, raw_obs):
+        L.check(self.ctx.lib.b200_pipeline_set_observation(self.h, C.byref(raw_obs)))
+
+    def set_predictor(self, predictor, reference_phase=0.0):
+        """predictor: hostmath.Polyco"""
+        L.check(self.ctx.lib.b200_pipeline_set_predictor(self.h, C.byref(predictor.pc), reference_phase))
+
+    def set_folding_period(self, period, reference_phase=0.0):
+        L.check(self.ctx.lib.b200_pipeline_set_folding_period(self.h, period, reference_phase))
+
+    def execute_obs(self, d_input, npart, obs_sample, first_sample=0, input_span=0):
+        _need_cuda(d_input, "d_input")
+        L.check(self.ctx.lib.b200_pipeline_execute_obs(self.h, _ptr(d_input), input_span, first_sample, npart, obs_sample))
+
+    def execute_host_obs(self, h_input, npart, obs_sample, first_sample=0):
+        if isinstance(h_input, torch.Tensor):
+            ptr, nbytes = h_input.data_ptr(), h_input.numel() * h_input.element_size()
+        else:
+            ptr, nbytes = h_input.ctypes.data, h_input.nbytes
+        L.check(self.ctx.lib.b200_pipeline_execute_host_obs(self.h, C.c_void_p(ptr), nbytes, first_sample, npart, obs_sample))
+
+    def phase_series(self):
+        """-> phaseseries.PhaseSeries holding the accumulated sums, hits and attributes (synchronises)."""
+        from . import phaseseries as P
+        out = P.PhaseSeries(self.nchan, self.dnpol, self.dndim, self.nbin)
+        L.check(self.ctx.lib.b200_pipeline_get_phase_series(self.h, C.byref(out.ps)))
+        out._bind()
+        return out
+
+    def reset(self):
+        L.check(self.ctx.lib.b200_pipeline_reset(self.h))
+
     def input_consumed(self):
         L.check(self.ctx.lib.b200_pipeline_input_consumed(self.h))
 

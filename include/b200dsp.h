@@ -348,6 +348,93 @@ int b200_sigproc_digitize8(b200_context* ctx, const float* d_in, uint64_t in_spa
                            uint64_t ndat, float digi_scale, float digi_mean, float xpol_offset, int flip_band,
                            int swap_band, unsigned char* d_out);
 
+/* ---------------------------------------------------------------------------------------
+ * PhaseSeries on the host: the accumulator's attributes and its merge / unload rules.
+ * Replaces: dsp::PhaseSeries::mixable / combine (Signal/Pulsar/PhaseSeries.C:336-418,442-480) with the
+ * attribute comparison of dsp::Observation::combinable (Kernel/Classes/Observation.C:139-310), the
+ * bookkeeping of Fold::fold (Fold.C:796-812: integration_length += ndat_folded / rate, ndat_total += ndat_fold)
+ * and the normalisation applied when a PhaseSeries is archived (dsp::Archiver::set, Signal/Pulsar/Archiver.C:
+ * 773-895: amplitude / (scale * hits), bins without hits set to the mean of the others, non-finite profiles
+ * zeroed with weight 0).  Times are split MJDs (integer day, integer second, fraction) like PSRCHIVE's MJD.
+ * ------------------------------------------------------------------------------------- */
+typedef struct { int day; int sec; double frac; } b200_mjd;
+
+/* the dsp::Observation attributes that travel with a block of data and decide whether two can be combined */
+typedef struct {
+  char telescope[32], receiver[32], source[32], mode[32], machine[32], format[32];
+  double centre_frequency, bandwidth;      /* MHz */
+  double rate;                             /* samples per second of this series */
+  double scale;                            /* product of the un-normalised FFT lengths so far (Observation::scale) */
+  double dispersion_measure, rotation_measure;
+  unsigned nchan, npol, ndim, nbit;
+  int state;                               /* Signal::State as b200_state, or 16 + ndim_in for undetected data */
+  int type, basis, swap, nsub_swap, dc_centred;
+  b200_mjd start_time;                     /* time of sample 0 */
+  uint64_t ndat;
+} b200_observation;
+
+typedef struct {
+  b200_observation obs;                    /* attributes of the folded series (copied from the first block mixed in) */
+  unsigned nbin, hits_nchan;               /* hits_nchan = 1: hits are common to all channels (no zeroed data) */
+  double integration_length;               /* seconds */
+  uint64_t ndat_total, ndat_expected;
+  b200_mjd end_time;                       /* obs.start_time .. end_time bound the folded data */
+  double folding_period, reference_phase;
+  float* data;                             /* [nchan][npol][nbin][ndim], caller-owned host memory */
+  unsigned* hits;                          /* [hits_nchan][nbin] */
+} b200_phase_series;
+
+/* Observation::combinable: 1 / 0; `reason` (nullable, reason_len bytes) receives the reference's explanation */
+int b200_observation_combinable(const b200_observation* a, const b200_observation* b, char* reason, unsigned reason_len);
+/* seconds from a to b */
+double b200_mjd_diff(const b200_mjd* b, const b200_mjd* a);
+b200_mjd b200_mjd_add(const b200_mjd* t, double seconds);
+/* PhaseSeries::mixable(obs, nbin, istart, fold_ndat): prepares an empty PhaseSeries (attributes copied, data and
+ * hits zeroed, ndat_total kept) or checks combinable + nbin and widens [start_time, end_time].  Returns 1 / 0. */
+int b200_phase_series_mixable(b200_phase_series* ps, const b200_observation* obs, unsigned nbin, int64_t istart,
+                              int64_t fold_ndat);
+/* The bookkeeping of one Fold::fold call after mixable (Fold.C:796-812). */
+int b200_phase_series_folded(b200_phase_series* ps, uint64_t ndat_folded, uint64_t ndat_fold);
+/* PhaseSeries::combine: B200_OK, or B200_ERR_INVALID ("PhaseSeries !mixable"). */
+int b200_phase_series_combine(b200_phase_series* ps, const b200_phase_series* other);
+/* Archiver::set for every (ichan, ipol, idim): h_profiles [nchan][npol][ndim][nbin] floats, h_weights
+ * [nchan][npol][ndim] (1, or 0 for a corrupted profile); *corrupted (nullable) counts the latter. */
+int b200_phase_series_normalise(const b200_phase_series* ps, float* h_profiles, float* h_weights, unsigned* corrupted);
+/* Self-describing dump of a sub-integration (the reference writes PSRFITS through PSRCHIVE, which
+ * cannot be built here): a 4096-byte ASCII header of `KEY value` lines (DADA style), then the normalised profiles
+ * (float32 [nchan][npol][ndim][nbin]), the weights (float32 [nchan][npol][ndim]), the hits (uint32 [hits_nchan][nbin])
+ * and the raw accumulated sums (float32 [nchan][npol][nbin][ndim]). */
+int b200_phase_series_unload(const b200_phase_series* ps, const char* path);
+/* Reads the header of such a file into *ps (data / hits pointers untouched) and, when the buffers are given, the
+ * arrays (any may be NULL). */
+int b200_phase_series_load(const char* path, b200_phase_series* ps, float* h_profiles, float* h_weights,
+                           unsigned* h_hits, float* h_raw);
+
+/* ---------------------------------------------------------------------------------------
+ * The fused path driven like dsp::Fold::transformation drives it: the library itself evaluates the predictor for
+ * every block (Fold.C:650-657 get_phi / get_pfold at the midpoint of the block's first output sample, :718-720
+ * phase_per_sample), derives the attributes of the series that reaches Fold from those of the raw input
+ * (Filterbank.C:325-371 / Convolution.C:286-305: rate *= freq_res / nsamp_fft, scale *= n_fft * freq_res or
+ * nsamp_fft * n_fft, start_time += nfilt_pos samples; Detection: state, npol, ndim) and keeps the PhaseSeries
+ * attributes (mixable, integration_length, ndat_total, start / end) next to the device accumulator.
+ * ------------------------------------------------------------------------------------- */
+/* attributes of the RAW input (rate = samples per second of one input channel, start_time = time of sample 0) */
+int b200_pipeline_set_observation(b200_pipeline* pipe, const b200_observation* raw_obs);
+int b200_pipeline_set_predictor(b200_pipeline* pipe, const b200_polyco* polyco, double reference_phase);
+/* constant-period folding instead (Fold::set_folding_period; reference epoch = the observation start) */
+int b200_pipeline_set_folding_period(b200_pipeline* pipe, double period_seconds, double reference_phase);
+/* One block whose first sample (sample `first_sample` of the buffer) is sample `obs_sample` of the observation.
+ * B200_ERR_INVALID ("PhaseSeries !mixable") when the block cannot be added to what has been folded so far. */
+int b200_pipeline_execute_obs(b200_pipeline* pipe, const void* d_input, uint64_t input_span, uint64_t first_sample,
+                              uint64_t npart, uint64_t obs_sample);
+int b200_pipeline_execute_host_obs(b200_pipeline* pipe, const void* h_input, uint64_t nbytes, uint64_t first_sample,
+                                   uint64_t npart, uint64_t obs_sample);
+/* Fold::Engine::synch + the attributes: fills *ps; when ps->data / ps->hits are non-NULL they receive the
+ * accumulated sums [nchan][npol][nbin][ndim] and hits [nbin] (synchronises the stream). */
+int b200_pipeline_get_phase_series(b200_pipeline* pipe, b200_phase_series* ps);
+/* Fold::reset -> Engine::zero + PhaseSeries::zero: clears the sums, the hits and integration_length / ndat_total */
+int b200_pipeline_reset(b200_pipeline* pipe);
+
 /* Sub-integration boundaries.  Replaces the arithmetic of dsp::TimeDivide::set_bounds / set_boundaries
  * (Signal/Pulsar/TimeDivide.C:132-330,349-425) for divisions given in seconds (dspsr -L), as driven by
  * dsp::Subint<Fold>::transformation (Signal/Pulsar/dsp/Subint.h:235-305): each input block is cut at the

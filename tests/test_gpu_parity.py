@@ -687,3 +687,70 @@ def test_pipeline_fold_short_period(ctx, oracle, C, F, npos, nneg, nbin, period)
     reduction that double counted in this regime; found by scratch/fuzz_gpu.py)."""
     err = _pipeline_case(ctx, oracle, C, F, npos, nneg, 2, "Stokes", 2, nbin, nblock=2, pps=1.0 / period)
     assert err <= TOL, err
+
+
+# ------------------------------------------------------------------------------------ library-side PhaseSeries (a14, f3)
+def test_pipeline_execute_obs_keeps_phase_series_attributes(ctx, oracle, tmp_path):
+    """b200_pipeline_execute_obs: the library evaluates the polyco at the midpoint of each block's first output sample
+    (Fold.C:650-657) and maintains the PhaseSeries attributes like Fold::transformation / Fold::fold (mixable,
+    integration_length, ndat_total, start/end, scale of Filterbank.C:124-125); the result is dumped normalised
+    (Archiver::set) and read back.  Oracle: the same blocks with the oracle's own predictor."""
+    torch, E, L = _torch(), _E(), _L()
+    from dspsr_b200 import hostmath as HM
+    from dspsr_b200 import phaseseries as P
+    import workloads as W
+    C_, F, npos, nneg, npart, nblock, nbin = 16, 256, 20, 21, 3, 3, 128
+    cfg = dict(W.CFG1, nchan=C_)
+    S = W.sizes(cfg, F, npos, nneg)
+    lut, _ = oracle.bittable8()
+    f = oracle.fb_sizes(1, 1, 2, C_, F, npos, nneg)
+    ndat = (nblock * npart * f.nsamp_step + f.nsamp_overlap + 3) // 4 * 4
+    raw = synth.caspsr_bytes(ndat, seed=61)
+    rng = np.random.default_rng(62)
+    H = np.exp(1j * rng.uniform(-np.pi, np.pi, (C_, F))).astype(np.complex64)
+    start = W.utc_to_mjd(cfg["utc_start"])
+    opc = oracle.polyco_parse(W.polyco_text())
+    ph = [W.block_phase(S, start, b * npart * S["step"], lambda m: oracle.polyco_phase(opc, *m)[0],
+                        lambda m: oracle.polyco_frequency(opc, *m)) for b in range(nblock)]
+    op = oracle.make_pipe(0, 1, 2, 1, lut, 0.0, f, None, H, "Coherence", 4, nbin)
+    ref, ref_hits = oracle.pipe_run(op, raw, nblock, npart, [p[0] for p in ph], [p[1] for p in ph], nthread=1)
+
+    ud = E.make_unpack_desc(L.FMT_CASPSR8, 1, 2, 1, lut)
+    fd, keep = E.make_fb_desc(1, 1, 2, C_, F, npos, nneg, H)
+    pipe = E.Pipeline(ctx, ud, fd, keep, "Coherence", 4, nbin)
+    robs = P.observation(1, 2, 1, S["rate_in"], start, ndat=ndat, centre_frequency=cfg["freq"], bandwidth=cfg["bw"],
+                         dm=cfg["dm"], state=17, nbit=8)
+    pipe.set_observation(robs)
+    pipe.set_predictor(HM.Polyco(W.polyco_text()))
+    d_raw = torch.from_numpy(raw).cuda()
+    order = [1, 0, 2]                                          # blocks need not arrive in time order
+    for b in order:
+        first = b * npart * S["step"]
+        pipe.execute_obs(d_raw, npart, obs_sample=first, first_sample=first)
+    ps = pipe.phase_series()
+    assert np.array_equal(ps.hits, ref_hits)
+    assert synth.relerr(ps.data, ref) <= TOL
+    n_out = nblock * npart * S["nkeep"]
+    assert ps.ndat_total == n_out
+    assert ps.integration_length == pytest.approx(n_out / S["rate_out"], rel=1e-12)
+    o = ps.ps.obs
+    assert (o.nchan, o.npol, o.ndim, o.state) == (C_, 1, 4, L.COHERENCE)
+    assert o.rate == pytest.approx(S["rate_out"], rel=1e-15) and o.scale == float(C_ * F) * F
+    t0 = W.mjd_add(start, npos / S["rate_out"])
+    t1 = W.mjd_add(t0, (nblock * npart * S["step"]) / S["rate_in"] - (npart * S["step"]) / S["rate_in"] + npart * S["nkeep"] / S["rate_out"])
+    assert ps.start_time[:2] == t0[:2] and ps.start_time[2] == pytest.approx(t0[2], abs=1e-9)
+    assert ps.end_time[:2] == t1[:2] and ps.end_time[2] == pytest.approx(t1[2], abs=1e-9)
+    # unload: normalised by scale * hits
+    path = tmp_path / "cfg1mini.b200ps"
+    ps.unload(path)
+    hdr, prof, w, hits, rawsum = P.load(path)
+    assert np.array_equal(hits[0], ref_hits) and np.all(w == 1)
+    want = ref.reshape(C_, 1, nbin, 4).transpose(0, 1, 3, 2) / (o.scale * ref_hits.astype(np.float64))
+    assert synth.relerr(prof, want) <= TOL
+    # a block of another observation is refused, and reset clears the integration
+    pipe.set_observation(P.observation(1, 2, 1, S["rate_in"], start, ndat=ndat, centre_frequency=1400.0,
+                                       bandwidth=cfg["bw"], dm=cfg["dm"], state=17, nbit=8))
+    with pytest.raises(L.B200Error):
+        pipe.execute_obs(d_raw, npart, obs_sample=0, first_sample=0)
+    pipe.reset()
+    assert pipe.phase_series().integration_length == 0.0
