@@ -492,15 +492,28 @@ static int obs_block(b200_pipeline* p, uint64_t npart, uint64_t obs_sample, b200
   return B200_OK;
 }
 
-static int obs_commit(b200_pipeline* p, const b200_observation* blk) {
-  // Fold::transformation: get_output()->mixable(*input, nbin, idat_start, ndat_fold) ...
-  if (!b200_phase_series_mixable(&p->ps, blk, p->desc.nbin, 0, (int64_t)blk->ndat)) {
+// Fold::transformation: get_output()->mixable(*input, nbin, idat_start, ndat_fold), tried on a copy of the attributes
+// BEFORE any kernel runs, so that a refused block leaves the accumulator untouched
+static int obs_mixable(b200_pipeline* p, const b200_observation* blk, b200_phase_series* trial) {
+  *trial = p->ps;
+  trial->data = nullptr;
+  trial->hits = nullptr;
+  if (trial->integration_length != 0.0 && trial->reference_phase != p->reference_phase) {
+    set_error("reference phase changed within an integration (Fold.C:538-543)");
+    return B200_ERR_INVALID;
+  }
+  if (!b200_phase_series_mixable(trial, blk, p->desc.nbin, 0, (int64_t)blk->ndat)) {
     set_error("PhaseSeries !mixable: the block differs from what has been folded so far");
     return B200_ERR_INVALID;
   }
+  return B200_OK;
+}
+
+static int obs_commit(b200_pipeline* p, const b200_observation* blk, const b200_phase_series* trial) {
+  p->ps = *trial;
   p->ps.folding_period = p->folding_period;
   p->ps.reference_phase = p->reference_phase;
-  // ... Fold::fold: integration_length += ndat_folded / rate, ndat_total += ndat_fold (Fold.C:789-802)
+  // Fold::fold: integration_length += ndat_folded / rate, ndat_total += ndat_fold (Fold.C:789-802)
   return b200_phase_series_folded(&p->ps, blk->ndat, blk->ndat);
 }
 
@@ -510,9 +523,11 @@ int b200_pipeline_execute_obs(b200_pipeline* p, const void* d_input, uint64_t in
   if (npart == 0) return B200_OK;
   b200_observation blk;
   double phi, pps;
+  b200_phase_series trial;
   int rc = obs_block(p, npart, obs_sample, &blk, &phi, &pps);
+  if (rc == B200_OK) rc = obs_mixable(p, &blk, &trial);
   if (rc == B200_OK) rc = pipeline_execute(p, d_input, input_span, first_sample, npart, phi, pps, nullptr, 0, nullptr);
-  if (rc == B200_OK) rc = obs_commit(p, &blk);
+  if (rc == B200_OK) rc = obs_commit(p, &blk, &trial);
   return rc;
 }
 
@@ -522,9 +537,11 @@ int b200_pipeline_execute_host_obs(b200_pipeline* p, const void* h_input, uint64
   if (npart == 0) return B200_OK;
   b200_observation blk;
   double phi, pps;
+  b200_phase_series trial;
   int rc = obs_block(p, npart, obs_sample, &blk, &phi, &pps);
+  if (rc == B200_OK) rc = obs_mixable(p, &blk, &trial);
   if (rc == B200_OK) rc = b200_pipeline_execute_host(p, h_input, nbytes, first_sample, npart, phi, pps, nullptr, 0);
-  if (rc == B200_OK) rc = obs_commit(p, &blk);
+  if (rc == B200_OK) rc = obs_commit(p, &blk, &trial);
   return rc;
 }
 
