@@ -27,6 +27,19 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.b200_version() >= 100
 
 
+def test_multi_library_loads_and_exports_every_declared_symbol():
+    from dspsr_b200 import multi as M
+    lib = M.load()
+    hdr = open(os.path.join(ROOT, "include", "b200multi.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(b200_multi_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 11
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libb200multi.so does not export %s" % name
+    assert declared == set(M.SIGNATURES), declared ^ set(M.SIGNATURES)
+    assert lib.b200_multi_nccl_version() >= 22000
+
+
 def test_no_gpu_is_a_loud_error_not_a_fallback():
     import torch
     if torch.cuda.is_available():
