@@ -220,7 +220,7 @@ SIGNATURES = {
     "b200_pipeline_fold": (_vp, [_vp]),
     "b200_pipeline_set_observation": (_i, [_vp, C.POINTER(Observation)]),
     "b200_pipeline_set_predictor": (_i, [_vp, C.POINTER(Polyco), _d]),
-    "b200_pipeline_set_folding_period": (_i, [_vp, _d, _d]),
+    "b200_pipeline_set_folding_period": (_i, [_vp, _d, _d, C.POINTER(Mjd)]),
     "b200_pipeline_execute_obs": (_i, [_vp, _vp, _u64, _u64, _u64, _u64]),
     "b200_pipeline_execute_host_obs": (_i, [_vp, _vp, _u64, _u64, _u64, _u64]),
     "b200_pipeline_get_phase_series": (_i, [_vp, C.POINTER(PhaseSeries)]),

@@ -52,6 +52,7 @@ struct b200_pipeline {
   b200_observation raw_obs, fold_obs;
   b200_polyco poly;
   double folding_period, reference_phase;
+  b200_mjd reference_epoch;
   b200_phase_series ps;
 };
 
@@ -458,9 +459,10 @@ int b200_pipeline_set_predictor(b200_pipeline* p, const b200_polyco* pc, double 
   return B200_OK;
 }
 
-int b200_pipeline_set_folding_period(b200_pipeline* p, double period, double reference_phase) {
+int b200_pipeline_set_folding_period(b200_pipeline* p, double period, double reference_phase, const b200_mjd* epoch) {
   B200_REQUIRE(p && period > 0, "b200_pipeline_set_folding_period: period must be positive");
   p->folding_period = period;
+  p->reference_epoch = epoch ? *epoch : b200_mjd{0, 0, 0.0};
   p->have_poly = false;
   p->reference_phase = reference_phase;
   return B200_OK;
@@ -481,7 +483,7 @@ static int obs_block(b200_pipeline* p, uint64_t npart, uint64_t obs_sample, b200
   const b200_mjd mid = b200_mjd_add(&t, 0.5 / blk->rate);                    // midpoint of the first sample
   double pfold;
   if (p->folding_period > 0.0) {
-    const double since = b200_mjd_diff(&mid, &p->raw_obs.start_time);
+    const double since = b200_mjd_diff(&mid, &p->reference_epoch);        // (start_time - reference_epoch).in_seconds()
     *phi = std::fmod(since, p->folding_period) / p->folding_period - p->reference_phase;
     pfold = p->folding_period;
   } else {

@@ -318,8 +318,10 @@ class Pipeline:
         """predictor: hostmath.Polyco"""
         L.check(self.ctx.lib.b200_pipeline_set_predictor(self.h, C.byref(predictor.pc), reference_phase))
 
-    def set_folding_period(self, period, reference_phase=0.0):
-        L.check(self.ctx.lib.b200_pipeline_set_folding_period(self.h, period, reference_phase))
+    def set_folding_period(self, period, reference_phase=0.0, reference_epoch=None):
+        """reference_epoch: (day, sec, frac) or None (= MJD 0, the reference's default)"""
+        ep = C.byref(L.Mjd(*reference_epoch)) if reference_epoch is not None else None
+        L.check(self.ctx.lib.b200_pipeline_set_folding_period(self.h, period, reference_phase, ep))
 
     def execute_obs(self, d_input, npart, obs_sample, first_sample=0, input_span=0):
         _need_cuda(d_input, "d_input")

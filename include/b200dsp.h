@@ -421,8 +421,10 @@ int b200_phase_series_load(const char* path, b200_phase_series* ps, float* h_pro
 /* attributes of the RAW input (rate = samples per second of one input channel, start_time = time of sample 0) */
 int b200_pipeline_set_observation(b200_pipeline* pipe, const b200_observation* raw_obs);
 int b200_pipeline_set_predictor(b200_pipeline* pipe, const b200_polyco* polyco, double reference_phase);
-/* constant-period folding instead (Fold::set_folding_period; reference epoch = the observation start) */
-int b200_pipeline_set_folding_period(b200_pipeline* pipe, double period_seconds, double reference_phase);
+/* constant-period folding instead (Fold::set_folding_period, Fold::set_reference_epoch; reference_epoch NULL = MJD 0,
+ * the reference's default): phi = fmod((t - epoch) seconds, period) / period - reference_phase (Fold.C:943-950) */
+int b200_pipeline_set_folding_period(b200_pipeline* pipe, double period_seconds, double reference_phase,
+                                     const b200_mjd* reference_epoch);
 /* One block whose first sample (sample `first_sample` of the buffer) is sample `obs_sample` of the observation.
  * B200_ERR_INVALID ("PhaseSeries !mixable") when the block cannot be added to what has been folded so far. */
 int b200_pipeline_execute_obs(b200_pipeline* pipe, const void* d_input, uint64_t input_span, uint64_t first_sample,

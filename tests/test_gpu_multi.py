@@ -1,6 +1,7 @@
 """Multi-GPU parity on real devices: the three sharding modes under torchrun + NCCL against the
 single-process oracle.  Skipped below two devices (the driver's one-GPU box); run with `gpurun --gpus 2`."""
 import json
+import math
 import os
 import subprocess
 import sys
@@ -8,6 +9,10 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def W_seconds(mjd, start):
+    return (mjd[0] - start[0]) * 86400.0 + (mjd[1] - start[1]) + (mjd[2] - start[2])
 
 
 def _ngpu():
@@ -74,13 +79,18 @@ def test_native_multi_host_combines_like_phase_series(mode):
         lut, _ = HM.bittable8()
         robs = P.observation(1, 2, 1, S["rate_in"], start, ndat=ndat, centre_frequency=cfg["freq"], bandwidth=cfg["bw"],
                              dm=cfg["dm"], state=17)
+        # constant-period folding (Fold::get_phi, Fold.C:943-950) with a period of the order of one block, so that
+        # every bin is hit: phi = fmod(t - start, P) / P
+        period = 0.37 * K * S["nkeep"] / S["rate_out"]
+        ophase = lambda m: math.fmod(W_seconds(m, start), period) / period
+        ofreq = lambda m: 1.0 / period
         for i in range(ndev):
             ctx = host.context(i)
             ud = E.make_unpack_desc(L.FMT_CASPSR8, 1, 2, 1, lut)
             fd, keep = E.make_fb_desc(1, 1, 2, C_, F, npos, nneg, H)
             pipe = E.Pipeline(ctx, ud, fd, keep, "Coherence", 4, nbin)
             pipe.set_observation(robs)
-            pipe.set_predictor(pred)
+            pipe.set_folding_period(period, reference_epoch=start)
             host.set_pipeline(i, pipe)
         nbytes = (K * S["step"] + S["overlap"]) * 2
         inputs = [raw[i * K * S["step"] * 2: i * K * S["step"] * 2 + nbytes] for i in range(ndev)]
@@ -109,6 +119,9 @@ def test_native_multi_host_combines_like_phase_series(mode):
         H = np.exp(1j * rng.uniform(-np.pi, np.pi, (nchan, F))).astype(np.complex64)
         _, scale = HM.bittable8()
         bw, cf = 856.0 * nchan / 1024, 1284.0
+        period = 0.41 * npart * step / (856e6 / 1024)
+        ophase = lambda m: math.fmod(W_seconds(m, start), period) / period
+        ofreq = lambda m: 1.0 / period
         inputs = []
         for i in range(ndev):
             ctx = host.context(i)
@@ -122,7 +135,7 @@ def test_native_multi_host_combines_like_phase_series(mode):
             pipe.set_observation(P.observation(nloc, 2, 2, 856e6 / 1024, start, ndat=ndat,
                                                centre_frequency=cf - 0.5 * bw + (i + 0.5) * sub_bw, bandwidth=sub_bw,
                                                dm=500.0, state=18, machine="MKBF"))
-            pipe.set_predictor(pred)
+            pipe.set_folding_period(period, reference_epoch=start)
             host.set_pipeline(i, pipe)
         host.execute_host_obs(inputs, [npart] * ndev, [0] * ndev)
         out = host.combine(M.SHARD_CHANNEL, nchan, 1, 4, nbin)

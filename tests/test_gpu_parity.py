@@ -729,7 +729,10 @@ def test_pipeline_execute_obs_keeps_phase_series_attributes(ctx, oracle, tmp_pat
         pipe.execute_obs(d_raw, npart, obs_sample=first, first_sample=first)
     ps = pipe.phase_series()
     assert np.array_equal(ps.hits, ref_hits)
-    assert synth.relerr(ps.data, ref) <= TOL
+    # the Vela period (89 ms) is much longer than these few blocks: compare on the bins that were hit
+    hit = ref_hits > 0
+    assert synth.relerr(ps.data.reshape(C_, 1, nbin, 4)[:, :, hit], ref.reshape(C_, 1, nbin, 4)[:, :, hit]) <= TOL
+    assert np.all(ps.data.reshape(C_, 1, nbin, 4)[:, :, ~hit] == 0)
     n_out = nblock * npart * S["nkeep"]
     assert ps.ndat_total == n_out
     assert ps.integration_length == pytest.approx(n_out / S["rate_out"], rel=1e-12)
@@ -745,8 +748,10 @@ def test_pipeline_execute_obs_keeps_phase_series_attributes(ctx, oracle, tmp_pat
     ps.unload(path)
     hdr, prof, w, hits, rawsum = P.load(path)
     assert np.array_equal(hits[0], ref_hits) and np.all(w == 1)
-    want = ref.reshape(C_, 1, nbin, 4).transpose(0, 1, 3, 2) / (o.scale * ref_hits.astype(np.float64))
-    assert synth.relerr(prof, want) <= TOL
+    want = ref.reshape(C_, 1, nbin, 4).transpose(0, 1, 3, 2)[..., hit] / (o.scale * ref_hits[hit].astype(np.float64))
+    assert synth.relerr(prof[..., hit], want) <= TOL
+    # bins without hits take the mean of the others (Archiver.C:869-889)
+    assert np.allclose(prof[..., ~hit], prof[..., hit].astype(np.float64).mean(axis=-1, keepdims=True), rtol=1e-5)
     # a block of another observation is refused, and reset clears the integration
     pipe.set_observation(P.observation(1, 2, 1, S["rate_in"], start, ndat=ndat, centre_frequency=1400.0,
                                        bandwidth=cfg["bw"], dm=cfg["dm"], state=17, nbit=8))
