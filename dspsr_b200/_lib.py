@@ -201,6 +201,8 @@ SIGNATURES = {
     "b200_fold_create": (_i, [_vp, _u, _u, _u, _u, _pvp]),
     "b200_fold_destroy": (_i, [_vp]),
     "b200_fold_set_bins": (_i, [_vp, _d, _d, _u64, _u64, C.POINTER(_u64)]),
+    "b200_fold_set_bins_weighted": (_i, [_vp, _d, _d, _u64, _u64, _vp, _u64, _u, _u64]),
+    "b200_fold_weighted": (_i, [_vp]),
     "b200_fold_get_bin_hits": (_i, [_vp, _vp]),
     "b200_fold_fold": (_i, [_vp, _vp, _u64]),
     "b200_fold_fold_into": (_i, [_vp, _vp, _u64, _vp, _u64]),
@@ -211,6 +213,9 @@ SIGNATURES = {
     "b200_fold_device_hits": (_vp, [_vp]),
     "b200_pipeline_create": (_i, [_vp, C.POINTER(PipelineDesc), _pvp]),
     "b200_pipeline_destroy": (_i, [_vp]),
+    "b200_pipeline_reserve": (_i, [_vp, _u64]),
+    "b200_weights_convolve": (_i, [_vp, _vp, _u64, _u, _u64, _u64, _u, _u, _vp, _vp]),
+    "b200_weights_scrunch": (_i, [_vp, _vp, C.POINTER(_u64), C.POINTER(_u), C.POINTER(_u64), _u, _vp]),
     "b200_pipeline_info": (_i, [_vp, C.POINTER(FbInfo)]),
     "b200_pipeline_execute": (_i, [_vp, _vp, _u64, _u64, _u64, _d, _d, _vp, _u64]),
     "b200_pipeline_execute_host": (_i, [_vp, _vp, _u64, _u64, _u64, _d, _d, _vp, _u64]),

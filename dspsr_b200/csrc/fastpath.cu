@@ -1148,8 +1148,9 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a, const __grid_constant_
           }
         }
         float* base = prof0 + uint64_t(c) * nbin * nprod;
-        for (unsigned pr = 0; pr < nprod; pr++)
-          atomicAdd(base + (uint64_t(pr / dndim) * nbin + rbin) * dndim + pr % dndim, acc[pr]);
+        if (rbin < nbin)                                    // bin == nbin: samples of a flagged window (weights.cu)
+          for (unsigned pr = 0; pr < nprod; pr++)
+            atomicAdd(base + (uint64_t(pr / dndim) * nbin + rbin) * dndim + pr % dndim, acc[pr]);
       }
     }
     __syncthreads();       // fold readers are done before the next tile's first scatter

@@ -403,8 +403,10 @@ __global__ void __launch_bounds__((FCT && EPT == 32) ? 512 : 1024, 1) k_chan_inv
     const unsigned* plan = a.sink.bins + partl * uint64_t(nkeep);
     float* prof0 = a.sink.profile + uint64_t(ch0) * nbin * nprod;
     auto red_add = [&](unsigned key, const float* acc) {
-      // key = c*nbin + bin; profile layout per channel [npol'][nbin][ndim']
-      const unsigned c = key / nbin, bin = key - c * nbin;
+      // key = c*(nbin+1) + bin; profile layout per channel [npol'][nbin][ndim'];  bin == nbin marks the samples of
+      // a flagged window (weights.cu): dropped
+      const unsigned c = key / (nbin + 1u), bin = key - c * (nbin + 1u);
+      if (bin == nbin) return;
       float* base = prof0 + uint64_t(c) * nbin * nprod;
       for (unsigned pr = 0; pr < nprod; pr++)
         atomicAdd(base + (uint64_t(pr / dndim) * nbin + bin) * dndim + pr % dndim, acc[pr]);
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__((FCT && EPT == 32) ? 512 : 1024, 1) k_chan_inv
         // bins are usually many samples wide) and no per-sample bin look-up or compare is needed.
         const unsigned bfirst = __ldg(plan + m0), blast = __ldg(plan + m1 - 1);
         if (chunk_monotonic && bfirst == blast) {
-          key = c * nbin + bfirst;
+          key = c * (nbin + 1u) + bfirst;
 #pragma unroll 4
           for (unsigned m = m0; m < m1; m++) {
             float2 p = smem[fmap(fp, np0 + m)];
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__((FCT && EPT == 32) ? 512 : 1024, 1) k_chan_inv
           }
         } else {
           for (unsigned m = m0; m < m1; m++) {
-            const unsigned k = c * nbin + __ldg(plan + m);
+            const unsigned k = c * (nbin + 1u) + __ldg(plan + m);
             float2 p = smem[fmap(fp, np0 + m)];
             float2 q = a.npol > 1 ? smem[fmap(fp + 1, np0 + m)] : make_float2(0.f, 0.f);
             float r[4] = {0.f, 0.f, 0.f, 0.f};
@@ -547,8 +549,9 @@ __global__ void __launch_bounds__(1024, 1) k_cols_inv(ColsInvArgs a) {
     } else {
       if (valid) {
         const unsigned bin = __ldg(plan + (m - np0));
-        for (unsigned pr = 0; pr < nprod; pr++)
-          atomicAdd(bins + (uint64_t(pr / dndim) * nbin + bin) * dndim + pr % dndim, r[pr]);
+        if (bin < nbin)                                      // nbin: flagged window
+          for (unsigned pr = 0; pr < nprod; pr++)
+            atomicAdd(bins + (uint64_t(pr / dndim) * nbin + bin) * dndim + pr % dndim, r[pr]);
       }
     }
   }

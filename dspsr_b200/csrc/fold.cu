@@ -211,9 +211,17 @@ __global__ void k_detect(DetectArgs a) {
 // ------------------------------------------------------------------------------------------
 // bin-plan expansion: segments -> bin of every sample (+ hits).  Exact integer arithmetic.
 // ------------------------------------------------------------------------------------------
+// Weighted input (Fold.C:687-716,746-763): sample idat belongs to window (idat + weight_idat) / ndatperweight; samples of
+// a window whose flag is 0 get bin = nbin (every fold consumer skips that value) and give no hit.
+struct BinWeights {
+  const unsigned* w;         // null: unweighted input
+  uint64_t nweights, weight_idat, idat_start;
+  unsigned ndatperweight;
+};
+
 __global__ void k_expand_bins(const b200_phase_segment* __restrict__ seg, unsigned nseg, uint64_t ndat, unsigned nbin,
                               unsigned* __restrict__ bins, unsigned* __restrict__ hits_last,
-                              unsigned* __restrict__ hits_total) {
+                              unsigned* __restrict__ hits_total, BinWeights bw) {
   const double double_nbin = double(nbin);
   for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < ndat; i += uint64_t(gridDim.x) * blockDim.x) {
     // binary search for the segment containing sample i
@@ -227,11 +235,15 @@ __global__ void k_expand_bins(const b200_phase_segment* __restrict__ seg, unsign
     const uint64_t a = s.a0 + (i - s.start) * s.step;            // < 2^53: exact in double
     const double phi = ldexp(double(a), s.scale_exp);            // exact scaling
     const double double_ibin = __dmul_rn(phi, double_nbin);      // Fold.C:766
-    const unsigned ibin = unsigned(double_ibin);                 // Fold.C:767 (truncation)
+    unsigned ibin = unsigned(double_ibin);                       // Fold.C:767 (truncation)
+    if (bw.w) {
+      const uint64_t iw = (bw.idat_start + i + bw.weight_idat) / bw.ndatperweight;
+      if (iw >= bw.nweights || bw.w[iw] == 0u) ibin = nbin;      // bad_data: binplan = folding_nbin (Fold.C:773-774)
+    }
     bins[i] = ibin;
     // neighbouring samples mostly share a bin: one atomic per distinct bin of the warp instead of one per lane
     const unsigned peers = __match_any_sync(__activemask(), ibin);
-    if ((threadIdx.x & 31u) == unsigned(__ffs(peers) - 1)) {
+    if (ibin < nbin && (threadIdx.x & 31u) == unsigned(__ffs(peers) - 1)) {
       const unsigned n = __popc(peers);
       atomicAdd(hits_last + ibin, n);
       atomicAdd(hits_total + ibin, n);
@@ -329,7 +341,7 @@ __global__ void k_fold(FoldArgs a) {
         v[0] = tp[i];
       }
       if (bin != cur) {
-        if (cur != 0xffffffffu)
+        if (cur < a.nbin)                                    // cur == nbin: samples of a flagged window, dropped
           for (int d = 0; d < NDIM; d++) atomicAdd(dst + uint64_t(cur) * NDIM + d, acc[d]);
         cur = bin;
         for (int d = 0; d < NDIM; d++) acc[d] = v[d];
@@ -337,7 +349,7 @@ __global__ void k_fold(FoldArgs a) {
         for (int d = 0; d < NDIM; d++) acc[d] += v[d];
       }
     }
-    if (cur != 0xffffffffu)
+    if (cur < a.nbin)
       for (int d = 0; d < NDIM; d++) atomicAdd(dst + uint64_t(cur) * NDIM + d, acc[d]);
   }
   if (a.smem_bins) {
@@ -371,6 +383,7 @@ struct b200_fold {
   uint64_t ndat_total;
   cudaEvent_t seg_free;          // the pinned segment buffer may be rewritten after this event
   bool seg_pending;
+  bool weighted;                 // some set_bins since the last zero skipped flagged samples: ndat_folded = sum of hits
 };
 
 extern "C" {
@@ -552,9 +565,36 @@ int b200_fold_destroy(b200_fold* f) {
   return B200_OK;
 }
 
+static int fold_set_bins(b200_fold* f, double phi, double pps, uint64_t ndat, uint64_t idat_start, uint64_t* ndat_folded,
+                         const BinWeights& bw);
+
 int b200_fold_set_bins(b200_fold* f, double phi, double pps, uint64_t ndat, uint64_t idat_start, uint64_t* ndat_folded) {
+  BinWeights bw;
+  memset(&bw, 0, sizeof bw);
+  return fold_set_bins(f, phi, pps, ndat, idat_start, ndat_folded, bw);
+}
+
+int b200_fold_set_bins_weighted(b200_fold* f, double phi, double pps, uint64_t ndat, uint64_t idat_start,
+                                const unsigned* d_weights, uint64_t nweights, unsigned ndatperweight, uint64_t weight_idat) {
+  B200_REQUIRE(f, "b200_fold_set_bins_weighted: null fold");
+  BinWeights bw;
+  memset(&bw, 0, sizeof bw);
+  if (d_weights && ndatperweight) {
+    // Fold.C:693-706: the first and the last window of the block must exist
+    const uint64_t last = ndat ? (idat_start + ndat - 1 + weight_idat) / ndatperweight : 0;
+    B200_REQUIRE(last < nweights, "Fold: iweight=%llu >= nweights=%llu (Fold.C:699)", (unsigned long long)last,
+                 (unsigned long long)nweights);
+    bw.w = d_weights; bw.nweights = nweights; bw.weight_idat = weight_idat; bw.idat_start = idat_start;
+    bw.ndatperweight = ndatperweight;
+  }
+  return fold_set_bins(f, phi, pps, ndat, idat_start, nullptr, bw);
+}
+
+static int fold_set_bins(b200_fold* f, double phi, double pps, uint64_t ndat, uint64_t idat_start, uint64_t* ndat_folded,
+                         const BinWeights& bw) {
   B200_REQUIRE(f, "b200_fold_set_bins: null fold");
   Context* ctx = f->ctx;
+  if (bw.w) f->weighted = true;
   f->ndat = ndat;
   f->idat_start = idat_start;
   if (ndat_folded) *ndat_folded = ndat;
@@ -576,7 +616,15 @@ int b200_fold_set_bins(b200_fold* f, double phi, double pps, uint64_t ndat, uint
     // the staging buffer holds.  Run the reference recurrence on the host and upload the bins.
     std::vector<unsigned> hb(ndat), hh(f->nbin, 0u), ht(f->nbin);
     b200_phase_bins_sequential(phi, pps, f->nbin, ndat, hb.data(), nullptr);
-    for (uint64_t i = 0; i < ndat; i++) hh[hb[i]]++;
+    if (bw.w) {
+      std::vector<unsigned> hw(bw.nweights);
+      B200_CUDA(cudaMemcpyAsync(hw.data(), bw.w, bw.nweights * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+      B200_CUDA(cudaStreamSynchronize(ctx->stream));
+      for (uint64_t i = 0; i < ndat; i++)
+        if (hw[(idat_start + i + bw.weight_idat) / bw.ndatperweight] == 0u) hb[i] = f->nbin;
+    }
+    for (uint64_t i = 0; i < ndat; i++)
+      if (hb[i] < f->nbin) hh[hb[i]]++;
     B200_CUDA(cudaMemcpyAsync(ht.data(), f->d_hits_total, f->nbin * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
     for (unsigned b = 0; b < f->nbin; b++) ht[b] += hh[b];
@@ -596,7 +644,7 @@ int b200_fold_set_bins(b200_fold* f, double phi, double pps, uint64_t ndat, uint
   {
     LaunchScope ls(ctx, KC_BINS);
     k_expand_bins<<<grid, threads, 0, ctx->stream>>>(f->d_seg, (unsigned)nseg, ndat, f->nbin, f->d_bins, f->d_hits_last,
-                                                    f->d_hits_total);
+                                                    f->d_hits_total, bw);
   }
   f->ndat_total += ndat;
   B200_CUDA(cudaGetLastError());
@@ -680,8 +728,11 @@ int b200_fold_zero(b200_fold* f) {
   B200_CUDA(cudaMemsetAsync(f->d_hits_total, 0, f->nbin * sizeof(unsigned), f->ctx->stream));
   B200_CUDA(cudaMemsetAsync(f->d_hits_last, 0, f->nbin * sizeof(unsigned), f->ctx->stream));
   f->ndat_total = 0;
+  f->weighted = false;
   return B200_OK;
 }
+
+int b200_fold_weighted(const b200_fold* f) { return f && f->weighted ? 1 : 0; }
 
 float* b200_fold_device_profile(b200_fold* f) { return f ? f->d_profile : nullptr; }
 unsigned* b200_fold_device_hits(b200_fold* f) { return f ? f->d_hits_total : nullptr; }
@@ -693,6 +744,34 @@ namespace b200 {
 const unsigned* fold_bins(b200_fold* f) { return f->d_bins; }
 const uint2* fold_runs(b200_fold* f) { return f->d_runs; }
 const unsigned* fold_nruns(b200_fold* f) { return f->d_nruns; }
+
+// Sizes the bin plan (and, when nkeep != 0, the item table) for blocks of up to ndat output samples, so that no
+// later set_bins / fold_build_runs has to allocate.
+int fold_reserve(b200_fold* f, uint64_t ndat, unsigned nkeep) {
+  Context* ctx = f->ctx;
+  if (ndat > f->bins_capacity) {
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (f->d_bins) cudaFree(f->d_bins);
+    f->d_bins = nullptr;
+    f->bins_capacity = ndat + 1024;
+    B200_CUDA(cudaMalloc(&f->d_bins, f->bins_capacity * sizeof(unsigned)));
+  }
+  if (nkeep) {
+    const uint64_t npart = (ndat + nkeep - 1) / nkeep, need = npart * (uint64_t(nkeep) + 1);
+    if (need > f->runs_capacity || npart > f->nruns_capacity) {
+      B200_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (f->d_runs) cudaFree(f->d_runs);
+      if (f->d_nruns) cudaFree(f->d_nruns);
+      f->d_runs = nullptr;
+      f->d_nruns = nullptr;
+      f->runs_capacity = need;
+      f->nruns_capacity = npart + 16;
+      B200_CUDA(cudaMalloc(&f->d_runs, f->runs_capacity * sizeof(uint2)));
+      B200_CUDA(cudaMalloc(&f->d_nruns, f->nruns_capacity * sizeof(unsigned)));
+    }
+  }
+  return B200_OK;
+}
 
 // Builds the per-part run table of the bin plan set by the last b200_fold_set_bins (ndat = npart * nkeep).
 int fold_build_runs(b200_fold* f, unsigned nkeep, unsigned align) {

@@ -10,11 +10,13 @@
 
 #include "engine.cuh"
 
+extern "C" int b200_fold_weighted(const b200_fold* f);
 namespace b200 {
 const unsigned* fold_bins(b200_fold* f);
 const uint2* fold_runs(b200_fold* f);
 const unsigned* fold_nruns(b200_fold* f);
 int fold_build_runs(b200_fold* f, unsigned nkeep, unsigned align);
+int fold_reserve(b200_fold* f, uint64_t ndat, unsigned nkeep);
 }
 using namespace b200;
 
@@ -46,6 +48,12 @@ struct b200_pipeline {
   uint64_t volt_floats;
   float* d_det;
   uint64_t det_floats;
+  // WeightedTimeSeries flags of two-bit input: as unpacked / after convolve_weights + scrunch_weights, and the
+  // scratch of the convolution (one word per transform + 1)
+  unsigned* d_weights;
+  unsigned* d_weights2;
+  unsigned* d_wscratch;
+  uint64_t weights_capacity, wscratch_capacity;
   // observation-driven folding (b200_pipeline_execute_obs): attributes of the raw input, of the series that
   // reaches Fold, the predictor, and the PhaseSeries attributes that Fold::transformation / Fold::fold maintain
   bool have_obs, have_poly;
@@ -168,6 +176,9 @@ int b200_pipeline_destroy(b200_pipeline* p) {
   if (p->d_unpacked) cudaFree(p->d_unpacked);
   if (p->d_volt) cudaFree(p->d_volt);
   if (p->d_det) cudaFree(p->d_det);
+  if (p->d_weights) cudaFree(p->d_weights);
+  if (p->d_weights2) cudaFree(p->d_weights2);
+  if (p->d_wscratch) cudaFree(p->d_wscratch);
   delete p;
   return B200_OK;
 }
@@ -182,6 +193,62 @@ b200_fold* b200_pipeline_fold(b200_pipeline* p) { return p ? p->fold : nullptr; 
 static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t input_span, uint64_t first_sample,
                             uint64_t npart, double phi, double pps, float* d_detected, uint64_t detected_span,
                             cudaEvent_t* batch_ready, unsigned batch_override = 0);
+
+}  // extern "C"
+
+// (re)allocation of a scratch array that must hold `need` elements; synchronises only when it has to grow
+template <typename T>
+static int grow(Context* ctx, T** ptr, uint64_t* capacity, uint64_t need) {
+  if (need <= *capacity) return B200_OK;
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr;
+  *capacity = 0;
+  B200_CUDA(cudaMalloc(ptr, need * sizeof(T)));
+  *capacity = need;
+  return B200_OK;
+}
+
+// scratch of a block of npart parts for everything execute needs besides the plan's own buffers
+static int pipeline_scratch(b200_pipeline* p, uint64_t npart) {
+  Context* ctx = p->ctx;
+  b200_fb_plan* fb = p->fb;
+  const int fmt = p->desc.unpack.format;
+  const unsigned ndim = p->desc.unpack.ndim;
+  const uint64_t ndat_out = npart * fb->nkeep;
+  int rc = B200_OK;
+  if (fmt != B200_FMT_CASPSR8 && fmt != B200_FMT_FLOAT32) {
+    const unsigned res = fmt_resolution(fmt);
+    const uint64_t ndat_in = npart * fb->nsamp_step + fb->nsamp_overlap + 2 * res;
+    rc = grow(ctx, &p->d_unpacked, &p->unpacked_floats, ndat_in * ndim * p->desc.unpack.nchan * p->desc.unpack.npol);
+    if (rc == B200_OK && fmt == B200_FMT_TWOBIT) {
+      const uint64_t nw = ndat_in / p->twobit.ndat_per_weight + 2;
+      uint64_t cap2 = p->weights_capacity;
+      rc = grow(ctx, &p->d_weights, &p->weights_capacity, nw);
+      if (rc == B200_OK) rc = grow(ctx, &p->d_weights2, &cap2, nw);
+      if (rc == B200_OK) rc = grow(ctx, &p->d_wscratch, &p->wscratch_capacity, npart + 2);
+    }
+  }
+  if (rc == B200_OK && fb->F > 8192 && !fb->conv_path) {
+    rc = grow(ctx, &p->d_volt, &p->volt_floats, uint64_t(fb->nchan_out) * fb->desc.npol * ndat_out * 2);
+    if (rc == B200_OK && p->desc.nbin)
+      rc = grow(ctx, &p->d_det, &p->det_floats, uint64_t(fb->nchan_out) * p->dnpol * ndat_out * p->dndim);
+  }
+  return rc;
+}
+
+extern "C" {
+
+int b200_pipeline_reserve(b200_pipeline* p, uint64_t max_npart) {
+  B200_REQUIRE(p && max_npart, "b200_pipeline_reserve: null pipeline or zero parts");
+  int rc = pipeline_scratch(p, max_npart);
+  if (rc == B200_OK && p->fold) {
+    // the bin plan (and the item table of the fused fold) of a block of max_npart parts
+    rc = b200_fold_set_bins(p->fold, 0.0, 0.0, 0, 0, nullptr);
+    if (rc == B200_OK) rc = fold_reserve(p->fold, max_npart * p->fb->nkeep, p->fb->fast_k3 ? p->fb->nkeep : 0);
+  }
+  return rc;
+}
 
 int b200_pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t input_span, uint64_t first_sample,
                           uint64_t npart, double phi, double pps, float* d_detected, uint64_t detected_span) {
@@ -199,6 +266,7 @@ static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t inpu
   const unsigned ndim = p->desc.unpack.ndim;
   const uint64_t ndat_out = npart * fb->nkeep;
 
+  struct { const unsigned* d; uint64_t nweights, weight_idat; unsigned ndat_per_weight; } wt = {nullptr, 0, 0, 0};
   FbSource src;
   memset(&src, 0, sizeof(src));
   src.batch_ready = batch_ready;
@@ -225,18 +293,40 @@ static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t inpu
     const uint64_t a0 = (first_sample / res) * res;
     const uint64_t a1 = ((first_sample + ndat_in + res - 1) / res) * res;
     const uint64_t span = (a1 - a0) * ndim;
-    const uint64_t need = span * p->desc.unpack.nchan * p->desc.unpack.npol;
-    if (need > p->unpacked_floats) {
-      B200_CUDA(cudaStreamSynchronize(ctx->stream));
-      if (p->d_unpacked) cudaFree(p->d_unpacked);
-      p->d_unpacked = nullptr;
-      p->unpacked_floats = need + need / 8;
-      B200_CUDA(cudaMalloc(&p->d_unpacked, p->unpacked_floats * sizeof(float)));
-    }
-    const uint64_t bits_per_sample = uint64_t(p->desc.unpack.nchan) * p->desc.unpack.npol * ndim * fmt_nbit(fmt);
-    int rc = b200_unpack(reinterpret_cast<b200_context*>(ctx), &p->desc.unpack,
-                         static_cast<const unsigned char*>(d_input) + a0 * bits_per_sample / 8, a1 - a0, p->d_unpacked, span);
+    int rc = pipeline_scratch(p, npart);              // no-op when b200_pipeline_reserve covered this block size
     if (rc != B200_OK) return rc;
+    const uint64_t bits_per_sample = uint64_t(p->desc.unpack.nchan) * p->desc.unpack.npol * ndim * fmt_nbit(fmt);
+    const unsigned char* raw0 = static_cast<const unsigned char*>(d_input) + a0 * bits_per_sample / 8;
+    if (fmt == B200_FMT_TWOBIT) {
+      // a WeightedTimeSeries: the flags of the windows travel with the data (weights.cu)
+      rc = b200_unpack_twobit(reinterpret_cast<b200_context*>(ctx), &p->twobit, raw0, a1 - a0, p->d_unpacked, span, p->d_weights);
+      if (rc != B200_OK) return rc;
+      wt.nweights = (a1 - a0) / p->twobit.ndat_per_weight;
+      wt.ndat_per_weight = p->twobit.ndat_per_weight;
+      wt.weight_idat = first_sample - a0;               // TimeSeries::seek moves weight_idat
+      if (p->desc.nbin) {
+        rc = b200_weights_convolve(reinterpret_cast<b200_context*>(ctx), p->d_weights, wt.nweights, wt.ndat_per_weight,
+                                   wt.weight_idat, ndat_in, fb->nsamp_fft, fb->nsamp_step, p->d_weights2, p->d_wscratch);
+        if (rc != B200_OK) return rc;
+        // Filterbank.C:289,306: scrunch by nsamp_fft / freq_res; Convolution.C:317-318: by 2 for Nyquist input
+        const unsigned tres = (fb->conv_path || fb->C == 1) ? (p->desc.fb.input_real ? 2u : 1u) : fb->nsamp_fft / fb->F;
+        wt.d = p->d_weights2;
+        if (tres > 1) {
+          if (double(wt.ndat_per_weight) / double(tres) < 1.0) {
+            // the reference scrunches `tres` FLAGS (not samples) into one and Fold then runs off the end of the array
+            set_error("two-bit weights: time resolution ratio %u exceeds ndat_per_weight %u -- the reference's Fold throws "
+                      "here (iweight >= nweights, Fold.C:699)", tres, wt.ndat_per_weight);
+            return B200_ERR_INVALID;
+          }
+          rc = b200_weights_scrunch(reinterpret_cast<b200_context*>(ctx), wt.d, &wt.nweights, &wt.ndat_per_weight,
+                                    &wt.weight_idat, tres, nullptr);
+          if (rc != B200_OK) return rc;
+        }
+      }
+    } else {
+      rc = b200_unpack(reinterpret_cast<b200_context*>(ctx), &p->desc.unpack, raw0, a1 - a0, p->d_unpacked, span);
+      if (rc != B200_OK) return rc;
+    }
     src.kind = SRC_F32;
     src.ptr = p->d_unpacked + (first_sample - a0) * ndim;
     src.span = span;
@@ -254,14 +344,8 @@ static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t inpu
   // detection and fold engines (what dspsr itself does: three separate operations).
   if (fb->F > 8192 && !fb->conv_path) {
     const unsigned npol = fb->desc.npol;
-    const uint64_t vneed = uint64_t(fb->nchan_out) * npol * ndat_out * 2;
-    if (vneed > p->volt_floats) {
-      B200_CUDA(cudaStreamSynchronize(ctx->stream));
-      if (p->d_volt) cudaFree(p->d_volt);
-      p->d_volt = nullptr;
-      p->volt_floats = vneed;
-      B200_CUDA(cudaMalloc(&p->d_volt, vneed * sizeof(float)));
-    }
+    int rcs = pipeline_scratch(p, npart);
+    if (rcs != B200_OK) return rcs;
     sink.kind = EPI_VOLT;
     sink.volt = p->d_volt;
     sink.volt_span = ndat_out * 2;
@@ -271,14 +355,6 @@ static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t inpu
     float* det = d_detected;
     uint64_t det_span = detected_span;
     if (p->desc.nbin) {
-      const uint64_t dneed = uint64_t(fb->nchan_out) * p->dnpol * ndat_out * p->dndim;
-      if (dneed > p->det_floats) {
-        B200_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (p->d_det) cudaFree(p->d_det);
-        p->d_det = nullptr;
-        p->det_floats = dneed;
-        B200_CUDA(cudaMalloc(&p->d_det, dneed * sizeof(float)));
-      }
       det = p->d_det;
       det_span = ndat_out * p->dndim;
     } else {
@@ -287,14 +363,14 @@ static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t inpu
     rc = b200_detect(reinterpret_cast<b200_context*>(ctx), p->desc.detect_state, p->dndim, p->d_volt, ndat_out * 2,
                      fb->nchan_out, npol, ndat_out, det, det_span);
     if (rc != B200_OK || !p->desc.nbin) return rc;
-    rc = b200_fold_set_bins(p->fold, phi, pps, ndat_out, 0, nullptr);
+    rc = b200_fold_set_bins_weighted(p->fold, phi, pps, ndat_out, 0, wt.d, wt.nweights, wt.ndat_per_weight, wt.weight_idat);
     if (rc != B200_OK) return rc;
     return b200_fold_fold(p->fold, det, det_span);
   }
 
   if (p->desc.nbin) {
     if (!p->bins_preset) {
-      int rc = b200_fold_set_bins(p->fold, phi, pps, ndat_out, 0, nullptr);
+      int rc = b200_fold_set_bins_weighted(p->fold, phi, pps, ndat_out, 0, wt.d, wt.nweights, wt.ndat_per_weight, wt.weight_idat);
       if (rc == B200_OK && fb->fast_k3) rc = fold_build_runs(p->fold, fb->nkeep, fb->desc.nfilt_pos);
       if (rc != B200_OK) return rc;
     }
@@ -309,7 +385,7 @@ static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t inpu
     // one-bin-per-chunk shortcut of the fold epilogue: measured SLOWER than the per-sample walk on
     // B200 (0.83 vs 0.76 ms per 32 parts of cfg1), so it is opt-in for experiments only
     static const bool fold_fast = getenv("B200_FOLD_FAST") && atoi(getenv("B200_FOLD_FAST")) == 1;
-    sink.phase_per_sample = fold_fast ? pps : 0.0;
+    sink.phase_per_sample = (fold_fast && !wt.d) ? pps : 0.0;      // flagged samples break the one-bin-per-chunk shortcut
     sink.profile = b200_fold_device_profile(p->fold);
   } else {
     B200_REQUIRE(d_detected, "b200_pipeline_execute: nbin == 0 needs an output buffer for the detected series");
@@ -563,6 +639,19 @@ int b200_pipeline_get_phase_series(b200_pipeline* p, b200_phase_series* out) {
   if (data) rc = b200_fold_synch(p->fold, data);
   uint64_t ntot = 0;
   if (rc == B200_OK && hits) rc = b200_fold_get_hits(p->fold, hits, &ntot);
+  if (rc == B200_OK && b200_fold_weighted(p->fold) && out->obs.rate > 0) {
+    // flagged windows were skipped: time_folded = ndat_folded / rate with ndat_folded = the hits (Fold.C:783-789)
+    std::vector<unsigned> tmp;
+    const unsigned* h = hits;
+    if (!h) {
+      tmp.resize(p->desc.nbin);
+      rc = b200_fold_get_hits(p->fold, tmp.data(), &ntot);
+      h = tmp.data();
+    }
+    uint64_t folded = 0;
+    for (unsigned b = 0; b < p->desc.nbin; b++) folded += h[b];
+    if (rc == B200_OK) out->integration_length = double(folded) / out->obs.rate;
+  }
   return rc;
 }
 

@@ -196,6 +196,12 @@ class FoldEngine:
         L.check(self.ctx.lib.b200_fold_set_bins(self.h, phi, phase_per_sample, ndat, idat_start, C.byref(n)))
         return n.value
 
+    def set_bins_weighted(self, phi, phase_per_sample, ndat, idat_start, weights, ndatperweight, weight_idat=0):
+        """weights: int32 CUDA tensor of per-window flags (Fold.C:687-716)."""
+        _need_cuda(weights, "weights")
+        L.check(self.ctx.lib.b200_fold_set_bins_weighted(self.h, phi, phase_per_sample, ndat, idat_start, _ptr(weights),
+                                                         weights.numel(), ndatperweight, weight_idat))
+
     def get_bin_hits(self):
         h = np.zeros(self.nbin, np.uint32)
         L.check(self.ctx.lib.b200_fold_get_bin_hits(self.h, h.ctypes.data_as(C.c_void_p)))
@@ -345,6 +351,9 @@ class Pipeline:
     def reset(self):
         L.check(self.ctx.lib.b200_pipeline_reset(self.h))
 
+    def reserve(self, max_npart):
+        L.check(self.ctx.lib.b200_pipeline_reserve(self.h, max_npart))
+
     def input_consumed(self):
         L.check(self.ctx.lib.b200_pipeline_input_consumed(self.h))
 
@@ -364,6 +373,25 @@ class Pipeline:
             self.ctx.lib.b200_pipeline_destroy(self.h)
         except Exception:
             pass
+
+
+def weights_convolve(ctx, w, ndat_per_weight, weight_idat, ndat, nfft, nkeep):
+    """WeightedTimeSeries::convolve_weights on device flags (int32 CUDA tensor) -> new tensor."""
+    _need_cuda(w, "w")
+    out = torch.empty_like(w)
+    scratch = torch.empty(ndat // nkeep + 2, dtype=torch.int32, device=w.device)
+    L.check(ctx.lib.b200_weights_convolve(ctx.h, _ptr(w), w.numel(), ndat_per_weight, weight_idat, ndat, nfft, nkeep,
+                                          _ptr(out), _ptr(scratch)))
+    return out
+
+
+def weights_scrunch(ctx, w, ndat_per_weight, weight_idat, nscrunch):
+    """WeightedTimeSeries::scrunch_weights -> (flags tensor, ndat_per_weight, weight_idat)."""
+    _need_cuda(w, "w")
+    n, npw, wi = C.c_uint64(w.numel()), C.c_uint(ndat_per_weight), C.c_uint64(weight_idat)
+    out = torch.empty_like(w)
+    L.check(ctx.lib.b200_weights_scrunch(ctx.h, _ptr(w), C.byref(n), C.byref(npw), C.byref(wi), nscrunch, _ptr(out)))
+    return out[: n.value], npw.value, wi.value
 
 
 # ---- host-only helpers (exact fold bin plan) -------------------------------------------------

@@ -192,6 +192,15 @@ int b200_fold_destroy(b200_fold* fold);
 /* Fold::Engine::set_bins(phi, phase_per_sample, ndat, idat_start) (Fold.h:261). */
 int b200_fold_set_bins(b200_fold* fold, double phi, double phase_per_sample, uint64_t ndat,
                        uint64_t idat_start, uint64_t* ndat_folded);
+/* The same for a WeightedTimeSeries input whose per-window flags live on the device (Fold.C:687-716,746-763): sample
+ * idat belongs to window (idat + weight_idat) / ndatperweight; samples of windows flagged 0 are not folded and give no
+ * hit.  d_weights NULL or ndatperweight 0: identical to b200_fold_set_bins.  The number of samples folded is the sum
+ * of the hits (b200_fold_get_hits). */
+int b200_fold_set_bins_weighted(b200_fold* fold, double phi, double phase_per_sample, uint64_t ndat, uint64_t idat_start,
+                                const unsigned* d_weights, uint64_t nweights, unsigned ndatperweight,
+                                uint64_t weight_idat);
+/* 1 when some set_bins since the last zero skipped flagged samples */
+int b200_fold_weighted(const b200_fold* fold);
 /* Fold::Engine::get_bin_hits for every bin of the last set_bins (Fold.C:731-735). */
 int b200_fold_get_bin_hits(b200_fold* fold, unsigned* h_hits);
 /* Fold::Engine::fold(): d_in = input->get_datptr(0,0), in_span = get_nfloat_span (Fold.C:989-990). */
@@ -238,6 +247,10 @@ int b200_pipeline_info(const b200_pipeline* pipe, b200_fb_info* info);
 int b200_pipeline_execute(b200_pipeline* pipe, const void* d_input, uint64_t input_span, uint64_t first_sample,
                           uint64_t npart, double phi, double phase_per_sample, float* d_detected,
                           uint64_t detected_span);
+/* Sizes every scratch array for blocks of up to max_npart parts (what Convolution::reserve / Filterbank::reserve do
+ * for the reference's scratch space): afterwards execute-type calls with npart <= max_npart do not allocate.
+ * Without it the arrays grow on first use (one synchronisation each time a larger block arrives). */
+int b200_pipeline_reserve(b200_pipeline* pipe, uint64_t max_npart);
 /* Same, from HOST memory (pinned or pageable; File::load_bytes_device, Kernel/Classes/File.C:213-272): the bytes
  * are copied chunk by chunk on a private copy stream into one of two staging buffers while the kernels of the
  * previous chunk run.  The call RETURNS BEFORE THE COPIES HAVE FINISHED: h_input must stay untouched until
@@ -347,6 +360,23 @@ int b200_rescale_get(b200_rescale* r, float* h_offset, float* h_scale);
 int b200_sigproc_digitize8(b200_context* ctx, const float* d_in, uint64_t in_span, unsigned nchan, unsigned npol,
                            uint64_t ndat, float digi_scale, float digi_mean, float xpol_offset, int flip_band,
                            int swap_band, unsigned char* d_out);
+
+/* ---------------------------------------------------------------------------------------
+ * WeightedTimeSeries flags on the device.  Replaces: WeightedTimeSeries::convolve_weights and
+ * scrunch_weights (Kernel/Classes/WeightedTimeSeries.C:582-690,692-780) as called by Filterbank::prepare_output
+ * (Filterbank.C:302-307) and Convolution::prepare_output (Convolution.C:312-319).  Flags: one uint32 per window of
+ * ndat_per_weight samples, 0 = bad.  The fused pipeline applies them itself to two-bit input.
+ * ------------------------------------------------------------------------------------- */
+/* d_out (distinct from d_weights) receives the flags after the convolution of a block of ndat samples processed as
+ * overlap-save transforms of nfft samples every nkeep samples; d_scratch: (ndat / nkeep + 2) words.  Requires
+ * nkeep >= ndat_per_weight. */
+int b200_weights_convolve(b200_context* ctx, const unsigned* d_weights, uint64_t nweights, unsigned ndat_per_weight,
+                          uint64_t weight_idat, uint64_t ndat, unsigned nfft, unsigned nkeep, unsigned* d_out,
+                          unsigned* d_scratch);
+/* nweights / ndat_per_weight / weight_idat are updated like the members of the reference.  When ndat_per_weight >=
+ * nscrunch only they change (d_out may be NULL); otherwise d_out (distinct) receives the scrunched flags. */
+int b200_weights_scrunch(b200_context* ctx, const unsigned* d_weights, uint64_t* nweights, unsigned* ndat_per_weight,
+                         uint64_t* weight_idat, unsigned nscrunch, unsigned* d_out);
 
 /* ---------------------------------------------------------------------------------------
  * PhaseSeries on the host: the accumulator's attributes and its merge / unload rules.

@@ -759,3 +759,85 @@ def test_pipeline_execute_obs_keeps_phase_series_attributes(ctx, oracle, tmp_pat
         pipe.execute_obs(d_raw, npart, obs_sample=0, first_sample=0)
     pipe.reset()
     assert pipe.phase_series().integration_length == 0.0
+
+
+# ------------------------------------------------------------------------------------ WeightedTimeSeries flags (f4)
+@pytest.mark.parametrize("nfft,nkeep,npw,widat,nscr", [(2048, 1408, 512, 0, 128), (4096, 3000, 512, 100, 512),
+                                                         (65536, 49152, 512, 0, 8192), (1024, 512, 512, 7, 2)])
+def test_weights_convolve_and_scrunch_match_reference_loops(ctx, oracle, nfft, nkeep, npw, widat, nscr):
+    """b200_weights_convolve / b200_weights_scrunch against the literal sequential loops of
+    WeightedTimeSeries.C:582-690,692-780 (oracle), random flags at several densities incl. none and all."""
+    torch, E = _torch(), _E()
+    rng = np.random.default_rng(nfft + nkeep)
+    nblocks = 37
+    ndat = nblocks * nkeep + (nfft - nkeep)
+    nw = (ndat + widat + npw - 1) // npw + 1
+    for density in (0.0, 0.002, 0.05, 0.5, 1.0):
+        w = (rng.random(nw) >= density).astype(np.uint32) * rng.integers(1, 4, nw).astype(np.uint32)
+        want = oracle.convolve_weights(w, npw, widat, ndat, nfft, nkeep)
+        got = E.weights_convolve(ctx, torch.from_numpy(w.astype(np.int32)).cuda(), npw, widat, ndat, nfft, nkeep)
+        assert np.array_equal(got.cpu().numpy().astype(np.uint32), want), density
+        w2, npw2, wi2 = oracle.scrunch_weights(want, npw, widat, nscr)
+        g2, gnpw, gwi = E.weights_scrunch(ctx, got, npw, widat, nscr)
+        assert (gnpw, gwi) == (npw2, wi2)
+        assert np.array_equal(g2.cpu().numpy().astype(np.uint32)[: w2.size], w2)
+
+
+def test_fold_engine_skips_flagged_windows(ctx, oracle):
+    """b200_fold_set_bins_weighted: bins, hits and ndat_folded of Fold.C:687-788 with a weighted input."""
+    torch, E = _torch(), _E()
+    rng = np.random.default_rng(71)
+    nchan, npol, ndim, nbin, ndat, npw, widat, start = 3, 2, 2, 64, 20000, 128, 37, 11
+    w = (rng.random((start + ndat + widat) // npw + 1) > 0.2).astype(np.uint32)
+    x = rng.standard_normal((nchan, npol, (start + ndat) * ndim)).astype(np.float32)
+    phi, pps = 0.37, 1.0 / 713.3
+    bp, hits, nfold = oracle.fold_plan_weighted(phi, pps, nbin, start, ndat, w, npw, widat)
+    ref = oracle.fold(x, ndim, bp, nbin, idat_start=start)
+    fe = E.FoldEngine(ctx, nchan, npol, ndim, nbin)
+    fe.set_bins_weighted(phi, pps, ndat, start, torch.from_numpy(w.astype(np.int32)).cuda(), npw, widat)
+    fe.fold(torch.from_numpy(x).cuda())
+    h, ntot = fe.hits()
+    assert np.array_equal(h, hits) and int(h.sum()) == nfold < ndat and ntot == ndat
+    assert synth.relerr(fe.synch(), ref) <= TOL
+
+
+@pytest.mark.parametrize("C_,F,npos,nneg", [(64, 16, 2, 2), (128, 256, 20, 20)])
+def test_pipeline_twobit_fold_with_excised_windows(ctx, oracle, C_, F, npos, nneg):
+    """Two-bit input with windows that the excision unpacker flags (all-zero bytes in one polarisation, a run of
+    saturated samples in the other): the flags are convolved with the overlap-save transforms, scrunched to the
+    filterbank's time resolution and the fold skips the flagged samples -- profile, hits, ndat_total and
+    integration_length as the reference's CPU path (oracle pipeline with a WeightedTimeSeries)."""
+    torch, E, L = _torch(), _E(), _L()
+    npart, nbin, nblock = 9, 32, 2
+    f = oracle.fb_sizes(1, 1, 2, C_, F, npos, nneg)
+    assert f.nsamp_step % 512 == 0                  # blocks start on a window boundary
+    ndat = (nblock * npart * f.nsamp_step + f.nsamp_overlap + 511) // 512 * 512
+    raw = synth.twobit_bytes(ndat, 2, seed=81).copy()
+    nwin = ndat // 512
+    rng = np.random.default_rng(82)
+    for wbad in rng.choice(nwin, max(2, nwin // 12), replace=False):
+        if wbad % 2:
+            raw[wbad * 256: wbad * 256 + 256: 2] = 0            # polarisation 0: all-zero bytes
+        else:
+            raw[wbad * 256 + 1: wbad * 256 + 256: 2] = 0xFF     # polarisation 1: every sample in the top state
+    t = oracle.TwoBit()
+    _, w = t.unpack(raw, ndat, 2)
+    assert 0 < (w[0] == 0).sum() < nwin
+    H = np.exp(1j * rng.uniform(-np.pi, np.pi, (C_, F))).astype(np.complex64)
+    pps = 1.0 / (0.41 * f.nkeep * npart)
+    phis = [0.2 + 0.17 * b for b in range(nblock)]
+    op = oracle.make_pipe(5, 1, 2, 1, None, 0.0, f, None, H, "Coherence", 4, nbin, twobit=t)
+    ref, ref_hits, ref_nfold = oracle.pipe_run(op, raw, nblock, npart, phis, [pps] * nblock, nthread=1, with_total=True)
+    assert 0 < ref_nfold < nblock * npart * f.nkeep
+    tb = E.make_twobit_desc(npol=2)
+    ud = E.make_twobit_unpack_desc(tb)
+    fd, keep = E.make_fb_desc(1, 1, 2, C_, F, npos, nneg, H)
+    pipe = E.Pipeline(ctx, ud, fd, keep, "Coherence", 4, nbin)
+    pipe.reserve(npart)
+    d_raw = torch.from_numpy(raw).cuda()
+    for b in range(nblock):
+        pipe.execute(d_raw, npart, phis[b], pps, first_sample=b * npart * f.nsamp_step)
+    prof, hits, ntot = pipe.synch()
+    assert np.array_equal(hits, ref_hits) and int(hits.sum()) == ref_nfold
+    assert ntot == nblock * npart * f.nkeep
+    assert synth.relerr(prof, ref) <= TOL
