@@ -148,6 +148,16 @@ class PhaseSeries(C.Structure):
     ]
 
 
+class SigprocHeader(C.Structure):
+    _fields_ = [
+        ("rawdatafile", C.c_char * 80), ("source_name", C.c_char * 80),
+        ("machine_id", C.c_int), ("telescope_id", C.c_int), ("nchans", C.c_int), ("nbits", C.c_int), ("nifs", C.c_int),
+        ("nbeams", C.c_int), ("ibeam", C.c_int),
+        ("src_raj", C.c_double), ("src_dej", C.c_double), ("az_start", C.c_double), ("za_start", C.c_double),
+        ("fch1", C.c_double), ("foff", C.c_double), ("tstart", C.c_double), ("tsamp", C.c_double),
+    ]
+
+
 class PhaseSegment(C.Structure):
     _fields_ = [
         ("start", C.c_uint64),
@@ -228,6 +238,9 @@ SIGNATURES = {
     "b200_pipeline_set_folding_period": (_i, [_vp, _d, _d, C.POINTER(Mjd)]),
     "b200_pipeline_execute_obs": (_i, [_vp, _vp, _u64, _u64, _u64, _u64]),
     "b200_pipeline_execute_host_obs": (_i, [_vp, _vp, _u64, _u64, _u64, _u64]),
+    "b200_pipeline_stream_begin": (_i, [_vp, _u64, _u64]),
+    "b200_pipeline_feed_host": (_i, [_vp, _vp, _u64, _vp, _u64, C.POINTER(_u64)]),
+    "b200_pipeline_feed": (_i, [_vp, _vp, _u64, _vp, _u64, C.POINTER(_u64)]),
     "b200_pipeline_get_phase_series": (_i, [_vp, C.POINTER(PhaseSeries)]),
     "b200_pipeline_reset": (_i, [_vp]),
     "b200_bittable8": (_i, [_i, _vp, C.POINTER(_d)]),
@@ -247,6 +260,9 @@ SIGNATURES = {
     "b200_phase_series_normalise": (_i, [C.POINTER(PhaseSeries), _vp, _vp, C.POINTER(C.c_uint)]),
     "b200_phase_series_unload": (_i, [C.POINTER(PhaseSeries), C.c_char_p]),
     "b200_phase_series_load": (_i, [C.c_char_p, C.POINTER(PhaseSeries), _vp, _vp, _vp, _vp]),
+    "b200_sigproc_header_from_observation": (_i, [C.POINTER(Observation), _u, C.POINTER(SigprocHeader)]),
+    "b200_sigproc_header_write": (C.c_int64, [C.POINTER(SigprocHeader), _vp, _u64]),
+    "b200_sigproc_file_write": (_i, [C.c_char_p, C.POINTER(SigprocHeader), _vp, _u64, _i]),
     "b200_phase_segments": (C.c_int64, [_d, _d, _u64, C.POINTER(PhaseSegment), _u64, C.POINTER(_d)]),
     "b200_phase_bins_sequential": (None, [_d, _d, _u, _u64, _vp, C.POINTER(_d)]),
 }

@@ -54,6 +54,18 @@ struct b200_pipeline {
   unsigned* d_weights2;
   unsigned* d_wscratch;
   uint64_t weights_capacity, wscratch_capacity;
+  // streaming input with block-edge carry (b200_pipeline_stream_begin / feed): two device buffers [carry | block]
+  // used alternately; see the comment at b200_pipeline_feed_host
+  unsigned char* d_stream[2];
+  uint64_t stream_bytes;           // capacity of each
+  cudaEvent_t stream_free[2];      // kernels that read d_stream[i] are done
+  cudaEvent_t stream_loaded;       // the H2D of the current block has landed
+  unsigned stream_turn;
+  uint64_t stream_block;           // largest block (samples) a feed may bring
+  uint64_t carry_samples;          // samples at the start of the current buffer that were kept from earlier feeds
+  uint64_t carry_skip;             // of those, samples before the next part's first sample
+  uint64_t stream_pos;             // observation sample index of the first sample of the current buffer
+  bool streaming;
   // observation-driven folding (b200_pipeline_execute_obs): attributes of the raw input, of the series that
   // reaches Fold, the predictor, and the PhaseSeries attributes that Fold::transformation / Fold::fold maintain
   bool have_obs, have_poly;
@@ -176,6 +188,11 @@ int b200_pipeline_destroy(b200_pipeline* p) {
   if (p->d_unpacked) cudaFree(p->d_unpacked);
   if (p->d_volt) cudaFree(p->d_volt);
   if (p->d_det) cudaFree(p->d_det);
+  for (int i = 0; i < 2; i++) {
+    if (p->d_stream[i]) cudaFree(p->d_stream[i]);
+    if (p->stream_free[i]) cudaEventDestroy(p->stream_free[i]);
+  }
+  if (p->stream_loaded) cudaEventDestroy(p->stream_loaded);
   if (p->d_weights) cudaFree(p->d_weights);
   if (p->d_weights2) cudaFree(p->d_weights2);
   if (p->d_wscratch) cudaFree(p->d_wscratch);
@@ -660,6 +677,132 @@ int b200_pipeline_reset(b200_pipeline* p) {
   p->ps.integration_length = 0.0;
   p->ps.ndat_total = 0;
   return b200_fold_zero(p->fold);
+}
+
+// ---- streaming input with block-edge carry --------------------------------------------------
+// The reference: IOManager loads blocks of the file; Filterbank/Convolution consume npart = (ndat - overlap) / step
+// whole parts and tell their InputBuffering policy where the next block must start (set_next_start(step * npart),
+// Filterbank.C:420-427); InputBuffering::set_next_start / pre_transformation (Kernel/Classes/InputBuffering.C:35-126)
+// then copy the unconsumed tail (the overlap plus the samples of an incomplete part) in front of the next block.
+// Here the tail stays on the device: a feed copies the new block straight behind the carried tail of the buffer the
+// previous feed prepared, runs every whole part, and moves the new tail (from the last resolution boundary of the
+// format at or before the next part) to the head of the other buffer with one device-to-device copy.  The
+// host-to-device copy of feed k+1 runs on the copy stream while the kernels of feed k are still busy.
+static uint64_t sample_bytes(const b200_pipeline* p, uint64_t nsamples) {
+  const uint64_t bits = uint64_t(p->desc.unpack.nchan) * p->desc.unpack.npol * p->desc.unpack.ndim * fmt_nbit(p->desc.unpack.format);
+  return nsamples * bits / 8;
+}
+
+int b200_pipeline_stream_begin(b200_pipeline* p, uint64_t max_block_samples, uint64_t obs_sample0) {
+  B200_REQUIRE(p && max_block_samples, "b200_pipeline_stream_begin: null pipeline or empty block");
+  B200_REQUIRE(p->desc.unpack.format != B200_FMT_FLOAT32, "streaming input takes raw bytes");
+  Context* ctx = p->ctx;
+  b200_fb_plan* fb = p->fb;
+  const unsigned res = fmt_resolution(p->desc.unpack.format);
+  B200_REQUIRE(max_block_samples % res == 0, "block length %llu is not a multiple of the format resolution %u",
+               (unsigned long long)max_block_samples, res);
+  // the carry never exceeds one step + the overlap + one resolution unit
+  const uint64_t carry_max = uint64_t(fb->nsamp_step) + fb->nsamp_overlap + 2 * res;
+  const uint64_t need = sample_bytes(p, carry_max + max_block_samples) + 256;
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (!p->copy_stream) {
+    B200_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) B200_CUDA(cudaEventCreateWithFlags(&p->stage_free[i], cudaEventDisableTiming));
+    p->chunk_ready = new std::vector<cudaEvent_t>();
+  }
+  for (int i = 0; i < 2; i++) {
+    if (need > p->stream_bytes) {
+      if (p->d_stream[i]) cudaFree(p->d_stream[i]);
+      p->d_stream[i] = nullptr;
+      B200_CUDA(cudaMalloc(&p->d_stream[i], need));
+    }
+    if (!p->stream_free[i]) B200_CUDA(cudaEventCreateWithFlags(&p->stream_free[i], cudaEventDisableTiming));
+  }
+  if (!p->stream_loaded) B200_CUDA(cudaEventCreateWithFlags(&p->stream_loaded, cudaEventDisableTiming));
+  p->stream_bytes = std::max(p->stream_bytes, need);
+  p->stream_block = max_block_samples;
+  p->carry_samples = p->carry_skip = 0;
+  p->stream_pos = obs_sample0;
+  p->stream_turn = 0;
+  p->streaming = true;
+  // scratch for the largest number of parts one feed can complete
+  const uint64_t maxparts = (carry_max + max_block_samples) / fb->nsamp_step + 1;
+  return b200_pipeline_reserve(p, maxparts);
+}
+
+static int pipeline_feed(b200_pipeline* p, const void* bytes, bool from_host, uint64_t nsamples, float* d_detected,
+                         uint64_t detected_span, uint64_t* nparts_out) {
+  B200_REQUIRE(p && (bytes || !nsamples), "b200_pipeline_feed: null argument");
+  B200_REQUIRE(p->streaming, "b200_pipeline_feed: call b200_pipeline_stream_begin first");
+  B200_REQUIRE(nsamples <= p->stream_block, "b200_pipeline_feed: block of %llu samples exceeds the %llu announced",
+               (unsigned long long)nsamples, (unsigned long long)p->stream_block);
+  Context* ctx = p->ctx;
+  b200_fb_plan* fb = p->fb;
+  const unsigned res = fmt_resolution(p->desc.unpack.format);
+  B200_REQUIRE(nsamples % res == 0, "block length %llu is not a multiple of the format resolution %u",
+               (unsigned long long)nsamples, res);
+  if (nparts_out) *nparts_out = 0;
+  const unsigned turn = p->stream_turn & 1u;
+  unsigned char* buf = p->d_stream[turn];
+  const uint64_t total = p->carry_samples + nsamples;
+  const uint64_t avail = total - p->carry_skip;
+  const uint64_t npart = avail > fb->nsamp_overlap ? (avail - fb->nsamp_overlap) / fb->nsamp_step : 0;
+  B200_REQUIRE(p->desc.nbin || !npart || d_detected, "b200_pipeline_feed: nbin == 0 needs an output buffer");
+  // 1. the new block lands behind the carried tail
+  if (nsamples) {
+    unsigned char* dst = buf + sample_bytes(p, p->carry_samples);
+    if (from_host) {
+      // the carried tail was written by the compute stream (step 3 of the previous feed); only the region behind it
+      // is written here, and nothing reads that region before the wait below
+      B200_CUDA(cudaMemcpyAsync(dst, bytes, sample_bytes(p, nsamples), cudaMemcpyHostToDevice, p->copy_stream));
+      B200_CUDA(cudaEventRecord(p->stream_loaded, p->copy_stream));
+      B200_CUDA(cudaStreamWaitEvent(ctx->stream, p->stream_loaded, 0));
+    } else {
+      B200_CUDA(cudaMemcpyAsync(dst, bytes, sample_bytes(p, nsamples), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  }
+  // 2. every whole part of [carry | block]
+  int rc = B200_OK;
+  if (npart) {
+    const uint64_t obs_sample = p->stream_pos + p->carry_skip;
+    if (p->desc.nbin && p->have_obs) {
+      rc = b200_pipeline_execute_obs(p, buf, 0, p->carry_skip, npart, obs_sample);
+    } else {
+      B200_REQUIRE(!p->desc.nbin, "b200_pipeline_feed: a folding pipeline needs b200_pipeline_set_observation and a predictor");
+      rc = pipeline_execute(p, buf, 0, p->carry_skip, npart, 0.0, 0.0, d_detected, detected_span, nullptr);
+    }
+    if (rc != B200_OK) return rc;
+  }
+  // 3. InputBuffering::set_next_start(step * npart): keep everything from the last resolution boundary at or before
+  //    the next part's first sample
+  const uint64_t next = p->carry_skip + npart * fb->nsamp_step;
+  const uint64_t aligned = (next / res) * res;
+  const uint64_t tail = total - aligned;
+  const unsigned other = turn ^ 1u;
+  // the other buffer may still be read by the kernels of the previous feed: they are earlier on this stream -- in order
+  if (tail)
+    B200_CUDA(cudaMemcpyAsync(p->d_stream[other], buf + sample_bytes(p, aligned), sample_bytes(p, tail),
+                              cudaMemcpyDeviceToDevice, ctx->stream));
+  B200_CUDA(cudaEventRecord(p->stream_free[turn], ctx->stream));
+  // the NEXT feed's host-to-device copy writes into `other` behind the tail: it must wait for the tail copy and for
+  // every kernel queued so far
+  B200_CUDA(cudaStreamWaitEvent(p->copy_stream, p->stream_free[turn], 0));
+  p->carry_samples = tail;
+  p->carry_skip = next - aligned;
+  p->stream_pos += aligned;
+  p->stream_turn++;
+  if (nparts_out) *nparts_out = npart;
+  return B200_OK;
+}
+
+int b200_pipeline_feed_host(b200_pipeline* p, const void* h_bytes, uint64_t nsamples, float* d_detected,
+                            uint64_t detected_span, uint64_t* nparts) {
+  return pipeline_feed(p, h_bytes, true, nsamples, d_detected, detected_span, nparts);
+}
+
+int b200_pipeline_feed(b200_pipeline* p, const void* d_bytes, uint64_t nsamples, float* d_detected,
+                       uint64_t detected_span, uint64_t* nparts) {
+  return pipeline_feed(p, d_bytes, false, nsamples, d_detected, detected_span, nparts);
 }
 
 int b200_pipeline_synch(b200_pipeline* p, float* h_profile, unsigned* h_hits, uint64_t* ndat_total) {

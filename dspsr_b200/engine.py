@@ -351,6 +351,22 @@ class Pipeline:
     def reset(self):
         L.check(self.ctx.lib.b200_pipeline_reset(self.h))
 
+    # ---- streaming input with block-edge carry (InputBuffering) ----
+    def stream_begin(self, max_block_samples, obs_sample0=0):
+        L.check(self.ctx.lib.b200_pipeline_stream_begin(self.h, max_block_samples, obs_sample0))
+
+    def feed(self, block, nsamples, out=None):
+        """block: raw bytes of `nsamples` new samples -- a CUDA uint8 tensor, a pinned CPU tensor or a numpy array.
+        Returns the number of overlap-save parts this feed completed (and `out` holds their detected samples)."""
+        n = C.c_uint64(0)
+        dptr, dspan = (None, 0) if out is None else (_ptr(out), out.shape[2])
+        if isinstance(block, torch.Tensor) and block.is_cuda:
+            L.check(self.ctx.lib.b200_pipeline_feed(self.h, _ptr(block), nsamples, dptr, dspan, C.byref(n)))
+        else:
+            ptr = block.data_ptr() if isinstance(block, torch.Tensor) else block.ctypes.data
+            L.check(self.ctx.lib.b200_pipeline_feed_host(self.h, C.c_void_p(ptr), nsamples, dptr, dspan, C.byref(n)))
+        return n.value
+
     def reserve(self, max_npart):
         L.check(self.ctx.lib.b200_pipeline_reserve(self.h, max_npart))
 

@@ -461,11 +461,40 @@ int b200_pipeline_execute_obs(b200_pipeline* pipe, const void* d_input, uint64_t
                               uint64_t npart, uint64_t obs_sample);
 int b200_pipeline_execute_host_obs(b200_pipeline* pipe, const void* h_input, uint64_t nbytes, uint64_t first_sample,
                                    uint64_t npart, uint64_t obs_sample);
+/* Streaming input with block-edge carry.  Replaces the block loop of IOManager (Kernel/Classes/
+ * IOManager.C:322-470) with InputBuffering::set_next_start / pre_transformation (InputBuffering.C:35-126) as driven
+ * by Filterbank::transformation (Filterbank.C:420-427): blocks of ANY length (a multiple of the format's resolution)
+ * are appended to the samples left over from earlier blocks; every whole overlap-save part is processed, the rest
+ * (overlap + incomplete part) is carried on the device.  Folding pipelines must have an observation and a predictor
+ * (each feed is one Fold call whose phase the library evaluates); for nbin == 0 the detected samples of the *nparts
+ * completed parts go to d_detected.  stream_begin sizes every buffer for blocks of up to max_block_samples. */
+int b200_pipeline_stream_begin(b200_pipeline* pipe, uint64_t max_block_samples, uint64_t obs_sample0);
+int b200_pipeline_feed_host(b200_pipeline* pipe, const void* h_bytes, uint64_t nsamples, float* d_detected,
+                            uint64_t detected_span, uint64_t* nparts);
+int b200_pipeline_feed(b200_pipeline* pipe, const void* d_bytes, uint64_t nsamples, float* d_detected,
+                       uint64_t detected_span, uint64_t* nparts);
 /* Fold::Engine::synch + the attributes: fills *ps; when ps->data / ps->hits are non-NULL they receive the
  * accumulated sums [nchan][npol][nbin][ndim] and hits [nbin] (synchronises the stream). */
 int b200_pipeline_get_phase_series(b200_pipeline* pipe, b200_phase_series* ps);
 /* Fold::reset -> Engine::zero + PhaseSeries::zero: clears the sums, the hits and integration_length / ndat_total */
 int b200_pipeline_reset(b200_pipeline* pipe);
+
+/* SIGPROC filterbank (.fil) header / file: the end of digifil.  Replaces SigProcOutputFile::write_header
+ * (Kernel/Formats/sigproc/SigProcOutputFile.C:35-60) -> SigProcObservation::unload_global (SigProcObservation.C:
+ * 228-275) -> filterbank_header (filterbank_header.c:44-100, send_stuff.c). */
+typedef struct {
+  char rawdatafile[80], source_name[80];
+  int machine_id, telescope_id, nchans, nbits, nifs, nbeams, ibeam;
+  double src_raj, src_dej, az_start, za_start, fch1, foff, tstart, tsamp;
+} b200_sigproc_header;
+/* header fields of the BitSeries SigProcDigitizer::pack makes of the detected series `detected`
+ * (SigProcDigitizer.C:84-86: bandwidth = -|bandwidth|, channels in descending frequency order) */
+int b200_sigproc_header_from_observation(const b200_observation* detected, unsigned nbit, b200_sigproc_header* h);
+/* returns the number of bytes written to buf, or -1 (buffer too small) */
+int64_t b200_sigproc_header_write(const b200_sigproc_header* h, unsigned char* buf, uint64_t buflen);
+/* header + TPF bytes (append != 0: bytes only, added to an existing file) */
+int b200_sigproc_file_write(const char* path, const b200_sigproc_header* h, const unsigned char* h_bytes,
+                            uint64_t nbytes, int append);
 
 /* Sub-integration boundaries.  Replaces the arithmetic of dsp::TimeDivide::set_bounds / set_boundaries
  * (Signal/Pulsar/TimeDivide.C:132-330,349-425) for divisions given in seconds (dspsr -L), as driven by

@@ -447,6 +447,23 @@ def pipe_run(p, raw, nblock, parts_per_block, phi, pps, nthread=1, with_total=Fa
     return profile, hits
 
 
+def pipe_blocks(p, raw, blocks):
+    """Fold calls of arbitrary extent: blocks = [(ipart0, npart, phi, pps), ...] -> (profile, hits, ndat_folded)."""
+    shape = pipe_profile_shape(p)
+    profile = np.zeros(shape, np.float32)
+    hits = np.zeros(p.nbin, np.uint32)
+    f = lib().orc_pipe_block
+    f.restype = C.c_uint64
+    nfold = 0
+    for ipart0, npart, phi, pps in blocks:
+        n = f(C.byref(p), _p(raw), C.c_uint64(ipart0), C.c_uint64(npart), C.c_double(phi), C.c_double(pps),
+              _p(profile), _p(hits), None)
+        if n == 2 ** 64 - 1:
+            raise RuntimeError("oracle: the reference would throw here")
+        nfold += n
+    return profile, hits, nfold
+
+
 def pipe_block_detected(p, raw, ipart0, npart):
     """One block of the path without fold: the detected series [out_nchan, out_npol, npart*nkeep*out_ndim]."""
     out_nchan = p.fb.nchan if p.use_filterbank else p.conv.nchan

@@ -48,3 +48,13 @@ $(OUT)/libdspsr_reffmt.so: $(FMTSRCS) ref_shim/ref_formats.cpp $(wildcard ref_sh
 	$(CXX) -std=gnu++98 -O2 -fPIC -ffp-contract=off -w -shared -Iref_shim -I$(FMT)/caspsr -I$(FMT)/kat -I$(FMT)/uwb \
 	    -I$(REF)/Kernel/Classes -o $@ $(FMTSRCS) ref_shim/ref_formats.cpp \
 	    -L_build -loracle -Wl,-rpath,'$$ORIGIN/../_build' -lm -lpthread
+
+# libdspsr_refsigproc.so: the SIGPROC header writer of digifil's last stage, plain C with its state
+# in globals (filterbank.h / header.h)
+SIGPROC = $(REF)/Kernel/Formats/sigproc
+SIGSRCS = $(SIGPROC)/filterbank_header.c $(SIGPROC)/send_stuff.c $(SIGPROC)/strings_equal.c $(SIGPROC)/swap_bytes.c \
+          $(SIGPROC)/error_message.c
+all: $(OUT)/libdspsr_refsigproc.so
+$(OUT)/libdspsr_refsigproc.so: $(SIGSRCS) ref_shim/ref_sigproc.c
+	@mkdir -p $(OUT)
+	$(CC) -std=gnu99 -O2 -fPIC -w -shared -I$(SIGPROC) -o $@ $(SIGSRCS) ref_shim/ref_sigproc.c -lm

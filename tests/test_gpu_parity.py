@@ -1,6 +1,8 @@
 """GPU parity tests: every C-ABI engine against the CPU oracle on the same seeded inputs.
 Tolerances follow BASELINE.json north_star: unpack bit-exact; voltages and folded profiles
 <= 1e-5 relative (normalised to RMS); hits / ndat_total exact."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -815,7 +817,8 @@ def test_pipeline_twobit_fold_with_excised_windows(ctx, oracle, C_, F, npos, nne
     raw = synth.twobit_bytes(ndat, 2, seed=81).copy()
     nwin = ndat // 512
     rng = np.random.default_rng(82)
-    for wbad in rng.choice(nwin, max(2, nwin // 12), replace=False):
+    # few enough that some transforms stay clean (a transform holds nsamp_fft / 512 windows)
+    for wbad in rng.choice(nwin, max(2, nwin * 512 // (12 * f.nsamp_fft)), replace=False):
         if wbad % 2:
             raw[wbad * 256: wbad * 256 + 256: 2] = 0            # polarisation 0: all-zero bytes
         else:
@@ -841,3 +844,117 @@ def test_pipeline_twobit_fold_with_excised_windows(ctx, oracle, C_, F, npos, nne
     assert np.array_equal(hits, ref_hits) and int(hits.sum()) == ref_nfold
     assert ntot == nblock * npart * f.nkeep
     assert synth.relerr(prof, ref) <= TOL
+
+
+# ------------------------------------------------------------------------------------ streaming input with carry (f2)
+@pytest.mark.parametrize("from_host", [False, True])
+def test_stream_feed_carries_block_edges(ctx, oracle, from_host):
+    """b200_pipeline_stream_begin / feed: blocks of ragged length; each feed processes the whole parts of
+    [carried tail | new block] as ONE Fold call (phase evaluated by the library for the first output sample of that
+    call) and carries the rest (InputBuffering::set_next_start).  Oracle: the same partition of the stream."""
+    import math
+    torch, E, L = _torch(), _E(), _L()
+    from dspsr_b200 import phaseseries as P
+    import workloads as W
+    C_, F, npos, nneg, nbin = 16, 256, 20, 21, 64
+    cfg = dict(W.CFG1, nchan=C_)
+    S = W.sizes(cfg, F, npos, nneg)
+    step, overlap = S["step"], S["overlap"]
+    rng = np.random.default_rng(91)
+    feeds = [int(x) // 4 * 4 for x in rng.integers(step // 3, 4 * step, 9)] + [4, 0, 5 * step]
+    ndat = sum(feeds)
+    raw = synth.caspsr_bytes(ndat, seed=92)
+    H = np.exp(1j * rng.uniform(-np.pi, np.pi, (C_, F))).astype(np.complex64)
+    lut, _ = oracle.bittable8()
+    start = W.utc_to_mjd(cfg["utc_start"])
+    period = 0.37 * 3 * S["nkeep"] / S["rate_out"]
+
+    def phase(m):
+        return math.fmod((m[0] - start[0]) * 86400.0 + (m[1] - start[1]) + (m[2] - start[2]), period) / period
+    # the partition the feeds imply
+    blocks, have, done = [], 0, 0
+    for n in feeds:
+        have += n
+        npart = (have - done * step - overlap) // step if have - done * step > overlap else 0
+        if npart:
+            phi, pps = W.block_phase(S, start, done * step, phase, lambda m: 1.0 / period)
+            blocks.append((done, npart, phi, pps))
+            done += npart
+    assert len(blocks) >= 8 and done == (ndat - overlap) // step
+    f = oracle.fb_sizes(1, 1, 2, C_, F, npos, nneg)
+    op = oracle.make_pipe(0, 1, 2, 1, lut, 0.0, f, None, H, "Coherence", 4, nbin)
+    ref, ref_hits, _ = oracle.pipe_blocks(op, raw, blocks)
+
+    ud = E.make_unpack_desc(L.FMT_CASPSR8, 1, 2, 1, lut)
+    fd, keep = E.make_fb_desc(1, 1, 2, C_, F, npos, nneg, H)
+    pipe = E.Pipeline(ctx, ud, fd, keep, "Coherence", 4, nbin)
+    pipe.set_observation(P.observation(1, 2, 1, S["rate_in"], start, ndat=ndat, centre_frequency=cfg["freq"],
+                                       bandwidth=cfg["bw"], dm=cfg["dm"], state=17))
+    pipe.set_folding_period(period, reference_epoch=start)
+    pipe.stream_begin(max(feeds))
+    pos, got_parts = 0, []
+    h_raw = torch.from_numpy(raw).pin_memory()
+    d_raw = torch.from_numpy(raw).cuda()
+    for n in feeds:
+        src = h_raw[2 * pos: 2 * (pos + n)] if from_host else d_raw[2 * pos: 2 * (pos + n)]
+        if n == 0:
+            src = h_raw[:4] if from_host else d_raw[:4]
+        got_parts.append(pipe.feed(src, n))
+        pos += n
+    assert [g for g in got_parts if g] == [b[1] for b in blocks]
+    ps = pipe.phase_series()
+    assert np.array_equal(ps.hits, ref_hits)
+    assert synth.relerr(ps.data, ref) <= TOL
+    assert ps.ndat_total == done * S["nkeep"]
+
+
+def test_stream_feed_twobit_filterbank_detected_and_fil(ctx, oracle, tmp_path):
+    """cfg2's chain as a stream: 2-bit blocks -> coherent filterbank -> Intensity, carried across block edges; the
+    concatenated detected series equals the oracle's over the whole stream; then Rescale + 8-bit digitiser and a
+    SIGPROC file whose payload is the oracle's digitised bytes."""
+    torch, E, L = _torch(), _E(), _L()
+    from dspsr_b200 import phaseseries as P
+    C_, F, npos, nneg = 64, 8, 1, 1
+    f = oracle.fb_sizes(1, 1, 2, C_, F, npos, nneg)
+    rng = np.random.default_rng(95)
+    H = np.exp(1j * rng.uniform(-np.pi, np.pi, (C_, F))).astype(np.complex64)
+    feeds = [int(x) // 512 * 512 for x in rng.integers(600, 6 * f.nsamp_step, 8)]
+    ndat = sum(feeds)
+    raw = synth.twobit_bytes(ndat, 2, seed=96)
+    t = oracle.TwoBit()
+    op = oracle.make_pipe(5, 1, 2, 1, None, 0.0, f, None, H, "Intensity", 1, 0, twobit=t)
+    nparts = (ndat - f.nsamp_overlap) // f.nsamp_step
+    ref = oracle.pipe_block_detected(op, raw, 0, nparts)
+    tb = E.make_twobit_desc(npol=2)
+    ud = E.make_twobit_unpack_desc(tb)
+    fd, keep = E.make_fb_desc(1, 1, 2, C_, F, npos, nneg, H)
+    pipe = E.Pipeline(ctx, ud, fd, keep, "Intensity", 1, 0)
+    pipe.stream_begin(max(feeds))
+    d_raw = torch.from_numpy(raw).cuda()
+    pos, chunks = 0, []
+    maxparts = max(feeds) // f.nsamp_step + 2
+    out = torch.empty((C_, 1, maxparts * f.nkeep), dtype=torch.float32, device="cuda")
+    for n in feeds:
+        k = pipe.feed(d_raw[pos // 2: (pos + n) // 2], n, out=out)
+        if k:
+            chunks.append(out[:, :, : k * f.nkeep].clone())
+        pos += n
+    det = torch.cat(chunks, dim=2)
+    assert det.shape[2] == nparts * f.nkeep
+    assert synth.relerr(det.cpu().numpy(), ref) <= TOL
+    # digifil tail: Rescale over the whole series, 8-bit digitiser, .fil
+    r = E.Rescale(ctx, C_, 1, interval_samples=0)
+    scaled = r.transform(det.contiguous())
+    fil = E.sigproc_digitize8(ctx, scaled, bandwidth=128.0)
+    orr = oracle.Rescale(interval_samples=0)
+    want = oracle.sigproc_digitize(orr.transform(ref), nbit=8, bandwidth=128.0)
+    got = fil.cpu().numpy()
+    assert got.shape == want.shape and np.mean(got != want) < 2e-3         # float sums differ in the last bits
+    obs = P.observation(C_, 1, 1, 128e6 * 2 * F / f.nsamp_fft, (55299, 7545, 0.0), centre_frequency=1400.0,
+                        bandwidth=128.0, state=L.INTENSITY, telescope="PKS", machine="CPSR2")
+    h = L.SigprocHeader()
+    L.check(ctx.lib.b200_sigproc_header_from_observation(C.byref(obs), 8, C.byref(h)))
+    path = tmp_path / "cfg2mini.fil"
+    L.check(ctx.lib.b200_sigproc_file_write(str(path).encode(), C.byref(h), got.ctypes.data, got.size, 0))
+    blob = open(path, "rb").read()
+    assert blob.endswith(got.tobytes()) and b"HEADER_END" in blob and h.nchans == C_ and h.foff == -2.0

@@ -403,3 +403,76 @@ def test_uwb_unpack_matches_reference(reffmt, oracle, npol):
     assert reffmt.ref_unpack_uwb(_vp(raw), ndat, npol, _vp(want), ndat * 2) == 0
     got = oracle.unpack_uwb(raw.view(np.int16), ndat, npol)
     assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# SIGPROC filterbank header (f1): the reference's own filterbank_header.c + send_stuff.c, compiled in place
+# ------------------------------------------------------------------------------------------------------------
+REFSIG = os.path.join(ROOT, "oracle", "_ref", "libdspsr_refsigproc.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REFSIG), reason="oracle/_ref/libdspsr_refsigproc.so not built")
+@pytest.mark.parametrize("bw,nchan,npol,telescope,machine", [(128.0, 4096, 1, "PKS", "CPSR2"), (-400.0, 256, 4, "Parkes", "BPSR"),
+                                                              (64.0, 16, 2, "GBT", "COBALT"), (856.0, 1024, 1, "MeerKAT", "MKBF")])
+def test_sigproc_header_bytes_equal_reference_writer(tmp_path, bw, nchan, npol, telescope, machine):
+    """b200_sigproc_header_write against filterbank_header() (filterbank_header.c:44-100) fed with the globals that
+    SigProcObservation::unload_global (SigProcObservation.C:228-275) sets for the same observation."""
+    from dspsr_b200 import _lib as L
+    from dspsr_b200 import phaseseries as P
+    lib = L.load()
+    start = (55299, 7545, 0.25)
+    rate = 128e6 * 8 / 65536
+    det = P.observation(nchan, npol, 1, rate, start, centre_frequency=1400.0, bandwidth=bw, state=L.INTENSITY,
+                        source="J0835-4510", telescope=telescope, machine=machine)
+    h = L.SigprocHeader()
+    L.check(lib.b200_sigproc_header_from_observation(C.byref(det), 8, C.byref(h)))
+    buf = C.create_string_buffer(1024)
+    n = lib.b200_sigproc_header_write(C.byref(h), buf, 1024)
+    assert n > 0
+    mine = buf.raw[:n]
+    # unload_global, by hand, into the reference's globals
+    R = C.CDLL(REFSIG)
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+
+    def setstr(name, val, size=80):
+        a = (C.c_char * size).in_dll(R, name)
+        a.value = val
+
+    def setv(ctype, name, val):
+        ctype.in_dll(R, name).value = val
+    tel = {"PKS": 4, "Parkes": 4, "GBT": 6, "MeerKAT": 0}[telescope]
+    mach = {"BPSR": 10, "SCAMP": 6, "COBALT": 11}.get(machine, 0)
+    setstr("inpfile", b"unknown")
+    setstr("source_name", b"J0835-4510")
+    setv(C.c_int, "machine_id", mach)
+    setv(C.c_int, "telescope_id", tel)
+    obw = -abs(bw)                                                    # SigProcDigitizer.C:84
+    setv(C.c_double, "fch1", 1400.0 - 0.5 * obw + 0.5 * obw / nchan)  # Observation.C:438-451, channel 0, not dc-centred
+    setv(C.c_double, "foff", obw / nchan)
+    setv(C.c_int, "nchans", nchan)
+    setv(C.c_int, "nifs", npol)
+    setv(C.c_int, "obits", 8)
+    setv(C.c_double, "tsamp", 1.0 / rate)
+    setv(C.c_double, "tstart", start[0] + (start[1] + start[2]) / 86400.0)
+    for k in ("src_raj", "src_dej", "az_start", "za_start"):
+        setv(C.c_double, k, 0.0)
+    ifs = (C.c_char * 8).in_dll(R, "ifstream")
+    ifs.value = b"Y" * npol
+    path = tmp_path / "ref.hdr"
+    fp = libc.fopen(str(path).encode(), b"wb")
+    R.filterbank_header.argtypes = [C.c_void_p]
+    R.filterbank_header(fp)
+    libc.fclose(fp)
+    ref = open(path, "rb").read()
+    assert mine == ref
+    assert mine.startswith(b"\x0c\x00\x00\x00HEADER_START") and mine.endswith(b"HEADER_END")
+    # the file writer: header + bytes, then appended bytes
+    data = np.arange(3 * nchan * npol, dtype=np.uint8)
+    fil = tmp_path / "out.fil"
+    L.check(lib.b200_sigproc_file_write(str(fil).encode(), C.byref(h), data.ctypes.data, data.size, 0))
+    L.check(lib.b200_sigproc_file_write(str(fil).encode(), None, data.ctypes.data, data.size, 1))
+    blob = open(fil, "rb").read()
+    assert blob[:n] == ref and blob[n:] == data.tobytes() * 2
