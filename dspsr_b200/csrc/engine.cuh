@@ -5,7 +5,7 @@
 
 namespace b200 {
 
-enum SrcKind { SRC_F32 = 0, SRC_CASPSR8 = 1 };
+enum SrcKind { SRC_F32 = 0, SRC_CASPSR8 = 1, SRC_MEERKAT8 = 2, SRC_UWB16 = 3, SRC_GENERIC8 = 4 };
 enum Epilogue { EPI_VOLT = 0, EPI_DETECT = 1, EPI_FOLD = 2 };
 
 // where the forward transform reads its samples
@@ -21,6 +21,12 @@ struct FbSource {
   // (checked entry by entry on the host): the fast path converts arithmetically instead of gathering
   int conv_ok;
   float conv_hi, conv_lo;
+  // raw formats unpacked inside the generic K1 (MeerKAT heaps, UWB blocks, generic TFP bytes): ptr is the start of a
+  // stream that begins on a boundary of the format's resolution, `first` the first sample of part 0 in it
+  uint64_t first;
+  float scale;              // MeerKAT: (float(x) + 0.5) * scale
+  unsigned sample_swap;     // MeerKAT: 2 = odd/even samples exchanged (MKBFRo)
+  unsigned ndim;            // generic 8-bit: 1 real, 2 complex
 };
 
 // Tries to express a 256-entry 8-bit table as the float evaluation fmaf(x, hi, x*lo); returns 1 and the

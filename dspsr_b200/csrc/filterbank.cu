@@ -57,6 +57,9 @@ struct ColsArgs {
   const float2* bhi;
   unsigned P, Q, lb, npol, nchan_in, Nc;
   uint64_t part0;
+  uint64_t first;           // raw formats: first sample of part 0 within the stream at src
+  float scale;
+  unsigned sample_swap, ndim;
 };
 
 template <int SRC, int EPT, unsigned PCT>
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__((PCT && EPT == 32) ? 512 : 1024, 1) k_cols_fwd
   const unsigned ic = (blk / a.npol) % a.nchan_in;
   const uint64_t part = a.part0 + blk / (a.npol * a.nchan_in);
   // (a per-bank replicated table -- conflict-free gathers -- was measured slower: 0.71 vs 0.67 ms)
-  if (SRC == SRC_CASPSR8)
+  if (SRC == SRC_CASPSR8 || SRC == SRC_GENERIC8)
     for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = a.lut[i];
   // Output twiddle W_N^(n2*k1) with k1 = j + e*T factorises into W_N^(n2*j) (one per thread) times
   // W_N^(n2*T*e) (EPT x B values per tile, staged here once): two table look-ups per thread
@@ -95,12 +98,41 @@ __global__ void __launch_bounds__((PCT && EPT == 32) ? 512 : 1024, 1) k_cols_fwd
                                            part * a.step) + n2;
   else {
     raw = static_cast<const unsigned char*>(a.src);
-    samp0 = part * a.step + 2ull * n2;
+    // element n = Q*n1 + n2 of the part is the sample pair (2n, 2n+1) of a real stream, sample n of a complex one
+    const bool real_in = (SRC == SRC_CASPSR8) || (SRC == SRC_GENERIC8 && a.ndim == 1);
+    samp0 = a.first + part * a.step + (real_in ? 2ull * n2 : uint64_t(n2));
   }
   MapCols map{b, a.lb, SwzShift<EPT>::value};
   auto load = [&](unsigned n1) -> float2 {
     if (SRC == SRC_F32) {
       return ld_nc_f2(fsrc + uint64_t(n1) * a.Q);
+    } else if (SRC == SRC_MEERKAT8) {
+      // heaps of 256 samples, [heap][pol][chan][256 x (re, im) int8] (MeerKATUnpacker.C:196-229); MKBFRo exchanges
+      // odd and even samples: output sample i comes from input sample i ^ 1
+      uint64_t i = samp0 + uint64_t(n1) * a.Q;
+      if (a.sample_swap == 2) i ^= 1ull;
+      const uint64_t word = (((i >> 8) * a.npol + pol) * a.nchan_in + ic) * 256ull + (i & 255ull);
+      const unsigned short w = __ldg(reinterpret_cast<const unsigned short*>(raw) + word);
+      return make_float2(__fmul_rn(float(int(int8_t(w & 255u))) + 0.5f, a.scale),
+                         __fmul_rn(float(int(int8_t(w >> 8))) + 0.5f, a.scale));
+    } else if (SRC == SRC_UWB16) {
+      // blocks of 2048 complex int16 samples per polarisation, offset binary (UWBUnpacker.C:177-218)
+      const uint64_t i = samp0 + uint64_t(n1) * a.Q;
+      const uint64_t word = ((i >> 11) * a.npol + pol) * 2048ull + (i & 2047ull);
+      const unsigned w = __ldg(reinterpret_cast<const unsigned*>(raw) + word);
+      return make_float2(float(short((w & 0xffffu) ^ 0x8000u)), float(short((w >> 16) ^ 0x8000u)));
+    } else if (SRC == SRC_GENERIC8) {
+      // TFP bytes: i*(nchan*npol*ndim) + ndim*(npol*c + p) + d (BitUnpacker.C:56-75)
+      if (a.ndim == 2) {
+        const uint64_t i = samp0 + uint64_t(n1) * a.Q;
+        const uint64_t off = i * (uint64_t(a.nchan_in) * a.npol * 2u) + 2u * (a.npol * ic + pol);
+        const unsigned short w = __ldg(reinterpret_cast<const unsigned short*>(raw + off));
+        return make_float2(s_lut[w & 255u], s_lut[w >> 8]);
+      }
+      const uint64_t i0 = samp0 + 2ull * uint64_t(n1) * a.Q;
+      const uint64_t stride = uint64_t(a.nchan_in) * a.npol;
+      const uint64_t off = i0 * stride + (a.npol * ic + pol);
+      return make_float2(s_lut[__ldg(raw + off)], s_lut[__ldg(raw + off + stride)]);
     } else {
       // CASPSR: byte 8*(i/4) + 4*pol + i%4 (CASPSRUnpacker.C:141-187); samples 2n, 2n+1 are adjacent
       uint64_t i0 = samp0 + 2ull * uint64_t(n1) * a.Q;
@@ -565,6 +597,102 @@ __global__ void __launch_bounds__(1024, 1) k_cols_inv(ColsInvArgs a) {
   }
 }
 
+// K3' with the fold epilogue.  A CTA's kept samples are P groups of B consecutive time samples (one group per
+// m1, Q samples apart).  The detected products go back to shared memory in (m1, b) order (padded by one sample per
+// group: conflict-free for the readers); then one thread per group walks its B consecutive samples, sums runs of
+// equal phase bin sequentially (the order of Fold.C:844-852) and adds every finished run to the PhaseSeries with one
+// RED.ADD.F32 per product.  (The first version accumulated per-sample into shared-memory bins with float atomics --
+// CAS loops, 16 lanes on one address -- and then flushed ~one RED per sample anyway: 4.3 ms per 16 parts of cfg3
+// against 0.5 ms for the transform itself.)
+template <unsigned NPOL, unsigned NPROD>
+__global__ void __launch_bounds__(1024, 1) k_cols_inv_fold(ColsInvArgs a) {
+  extern __shared__ float2 smem[];
+  const unsigned B = 1u << a.lb;
+  const unsigned T = a.P >> 4;
+  const unsigned per_pol = T * B;
+  const unsigned pol = threadIdx.x / per_pol;
+  const unsigned t = threadIdx.x % per_pol;
+  const unsigned b = t & (B - 1);
+  const unsigned j = t >> a.lb;
+  const unsigned m2 = blockIdx.x * B + b;
+  const unsigned partl = blockIdx.y / a.nchan_in;
+  const unsigned ic = blockIdx.y % a.nchan_in;
+  const unsigned blk = (partl * a.nchan_in + ic) * NPOL + pol;
+  float2* spol = smem + uint64_t(pol) * a.P * B;
+  MapCols map{b, a.lb, 4};
+  const float2* src = a.A + uint64_t(blk) * a.Nc + m2;
+  auto load = [&](unsigned k1) -> float2 { return ld_nc_f2(src + uint64_t(k1) * a.Q); };
+  const unsigned np0 = a.nfilt_pos, nkeep = a.nkeep;
+  {
+    auto store = [&](unsigned m1, float2 v, int) { spol[map(m1)] = v; };
+    block_fft<16, true>(a.P, j, T, map, spol, a.twP, a.P, load, store);
+  }
+  __syncthreads();
+  // detect: NIT samples per thread, kept in registers while the transforms are overwritten
+  constexpr unsigned NIT = 16 / NPOL;                       // P*B samples / (NPOL * P/16 * B) threads
+  float r[NIT][NPROD];
+#pragma unroll
+  for (unsigned i = 0; i < NIT; i++) {
+    const unsigned it = i * blockDim.x + threadIdx.x;
+    const unsigned m1 = it >> a.lb, bb = it & (B - 1);
+    MapCols mp{bb, a.lb, 4};
+    const float2 p = smem[mp(m1)];
+    const float2 q = NPOL > 1 ? smem[uint64_t(a.P) * B + mp(m1)] : make_float2(0.f, 0.f);
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    detect_products(a.sink.state, p, q, d);
+#pragma unroll
+    for (unsigned pr = 0; pr < NPROD; pr++) r[i][pr] = d[pr];
+  }
+  __syncthreads();
+  float* stage = reinterpret_cast<float*>(smem);
+#pragma unroll
+  for (unsigned i = 0; i < NIT; i++) {
+    const unsigned it = i * blockDim.x + threadIdx.x;
+    float* s = stage + uint64_t(it + (it >> a.lb)) * NPROD;
+    if (NPROD == 4) *reinterpret_cast<float4*>(s) = make_float4(r[i][0], r[i][1 % NPROD], r[i][2 % NPROD], r[i][3 % NPROD]);
+    else if (NPROD == 2) *reinterpret_cast<float2*>(s) = make_float2(r[i][0], r[i][1 % NPROD]);
+    else s[0] = r[i][0];
+  }
+  __syncthreads();
+  const unsigned nbin = a.sink.nbin, dndim = a.sink.dndim;
+  const unsigned* plan = a.sink.bins + partl * uint64_t(nkeep);
+  float* prof = a.sink.profile + uint64_t(ic) * nbin * NPROD;      // per channel [npol'][nbin][ndim']
+  for (unsigned g = threadIdx.x; g < a.P; g += blockDim.x) {
+    const unsigned mbase = g * a.Q + blockIdx.x * B;
+    const float* s = stage + uint64_t(g * B + g) * NPROD;
+    float acc[NPROD];
+    unsigned cur = 0xffffffffu;
+    for (unsigned bb = 0; bb < B; bb++) {
+      const unsigned m = mbase + bb;
+      const unsigned bin = (m >= np0 && m < np0 + nkeep) ? __ldg(plan + (m - np0)) : 0xffffffffu;
+      float v[NPROD];
+      if (NPROD == 4) {
+        const float4 x = *reinterpret_cast<const float4*>(s + bb * NPROD);
+        v[0] = x.x; v[1 % NPROD] = x.y; v[2 % NPROD] = x.z; v[3 % NPROD] = x.w;
+      } else if (NPROD == 2) {
+        const float2 x = *reinterpret_cast<const float2*>(s + bb * NPROD);
+        v[0] = x.x; v[1 % NPROD] = x.y;
+      } else v[0] = s[bb];
+      if (bin != cur) {
+        if (cur < nbin)                                      // nbin: flagged window; 0xffffffff: discarded sample
+#pragma unroll
+          for (unsigned pr = 0; pr < NPROD; pr++)
+            atomicAdd(prof + (uint64_t(pr / dndim) * nbin + cur) * dndim + pr % dndim, acc[pr]);
+        cur = bin;
+#pragma unroll
+        for (unsigned pr = 0; pr < NPROD; pr++) acc[pr] = v[pr];
+      } else {
+#pragma unroll
+        for (unsigned pr = 0; pr < NPROD; pr++) acc[pr] += v[pr];
+      }
+    }
+    if (cur < nbin)
+#pragma unroll
+      for (unsigned pr = 0; pr < NPROD; pr++)
+        atomicAdd(prof + (uint64_t(pr / dndim) * nbin + cur) * dndim + pr % dndim, acc[pr]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -602,7 +730,7 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
     const unsigned nb = (unsigned)std::min<uint64_t>(batch, npart - part0);
     if (src.batch_ready) B200_CUDA(cudaStreamWaitEvent(st, src.batch_ready[part0 / batch], 0));
     // ---- K1 ----
-    const bool k1_fast = pl->fast_k1 && (src.kind == SRC_F32 || (src.step % 4 == 0 && (reinterpret_cast<uintptr_t>(src.ptr) & 3) == 0));
+    const bool k1_fast = pl->fast_k1 && src.kind <= SRC_CASPSR8 && (src.kind == SRC_F32 || (src.step % 4 == 0 && (reinterpret_cast<uintptr_t>(src.ptr) & 3) == 0));
     if (k1_fast) {
       int rc = fast_k1(pl, src, part0, nb);
       if (rc != B200_OK) return rc;
@@ -612,8 +740,9 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
       a.dst = pl->scratchA; a.twP = pl->twP.tw; a.twPs = pl->twP.stage; a.blo = pl->bigN.lo; a.bhi = pl->bigN.hi;
       a.P = pl->P; a.Q = pl->Q; a.lb = pl->lbB; a.npol = npol; a.nchan_in = nchan_in; a.Nc = pl->Nc;
       a.part0 = part0;
+      a.first = src.first; a.scale = src.scale; a.sample_swap = src.sample_swap; a.ndim = src.ndim;
       dim3 grid(pl->Q / B, nb * nblk1);
-      const bool ct = (pl->P == 2048);           // compile-time-sized fast path
+      const bool ct = (pl->P == 2048) && src.kind <= SRC_CASPSR8;   // compile-time-sized fast path (float / CASPSR sources)
       static const int k1_ept = getenv("B200_K1_EPT") ? atoi(getenv("B200_K1_EPT")) : 32;
       const bool ct16 = ct && k1_ept == 16;
       if (ct16) a.twPs = pl->twP.stage16;
@@ -634,6 +763,9 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
         else k_cols_fwd<SRC_CASPSR8, 32, 2048><<<grid, block, smem, st>>>(a);
       } else {
         if (src.kind == SRC_F32) k_cols_fwd<SRC_F32, 16, 0><<<grid, block, smem, st>>>(a);
+        else if (src.kind == SRC_MEERKAT8) k_cols_fwd<SRC_MEERKAT8, 16, 0><<<grid, block, smem, st>>>(a);
+        else if (src.kind == SRC_UWB16) k_cols_fwd<SRC_UWB16, 16, 0><<<grid, block, smem, st>>>(a);
+        else if (src.kind == SRC_GENERIC8) k_cols_fwd<SRC_GENERIC8, 16, 0><<<grid, block, smem, st>>>(a);
         else k_cols_fwd<SRC_CASPSR8, 16, 0><<<grid, block, smem, st>>>(a);
       }
     }
@@ -696,11 +828,16 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
       const unsigned Bi = 1u << lb;
       dim3 grid(pl->Q / Bi, nb * nchan_in);
       dim3 block(npol * (pl->P / 16) * Bi);
-      size_t smem = size_t(npol) * pl->P * Bi * sizeof(float2) + (sk.kind == EPI_FOLD ? size_t(sk.nbin) * nprod * 4 : 0);
+      size_t smem = size_t(npol) * pl->P * Bi * sizeof(float2);
+      if (sk.kind == EPI_FOLD)   // the detected products are staged over the transforms, one padding sample per group
+        smem = std::max(smem, (size_t(pl->P) * Bi + pl->P) * nprod * sizeof(float));
       LaunchScope ls(ctx, KC_INV);
       if (sk.kind == EPI_VOLT) k_cols_inv<EPI_VOLT><<<grid, block, smem, st>>>(a);
       else if (sk.kind == EPI_DETECT) k_cols_inv<EPI_DETECT><<<grid, block, smem, st>>>(a);
-      else k_cols_inv<EPI_FOLD><<<grid, block, smem, st>>>(a);
+      else if (npol == 2 && nprod == 4) k_cols_inv_fold<2, 4><<<grid, block, smem, st>>>(a);
+      else if (npol == 2 && nprod == 2) k_cols_inv_fold<2, 2><<<grid, block, smem, st>>>(a);
+      else if (npol == 2) k_cols_inv_fold<2, 1><<<grid, block, smem, st>>>(a);
+      else k_cols_inv_fold<1, 1><<<grid, block, smem, st>>>(a);
     } else {
       ChanArgs a;
       a.Z = pl->scratchZ; a.twF = pl->twF.tw; a.twFs = pl->twF.stage;
@@ -756,13 +893,15 @@ static int plan_set_attributes(size_t maxs) {
   int rc;
 #define SET(k) if ((rc = set_smem(k, maxs)) != B200_OK) return rc;
   SET((k_cols_fwd<SRC_F32, 16, 0>)) SET((k_cols_fwd<SRC_CASPSR8, 16, 0>))
+  SET((k_cols_fwd<SRC_MEERKAT8, 16, 0>)) SET((k_cols_fwd<SRC_UWB16, 16, 0>)) SET((k_cols_fwd<SRC_GENERIC8, 16, 0>))
   SET((k_cols_fwd<SRC_F32, 32, 2048>)) SET((k_cols_fwd<SRC_CASPSR8, 32, 2048>))
   SET((k_cols_fwd<SRC_F32, 16, 2048>)) SET((k_cols_fwd<SRC_CASPSR8, 16, 2048>))
   SET((k_chan_inv<16, EPI_VOLT, 8192>)) SET((k_chan_inv<16, EPI_DETECT, 8192>)) SET((k_chan_inv<16, EPI_FOLD, 8192>))
   SET((k_rows<true, true, 16, 0>)) SET((k_rows<true, false, 16, 0>)) SET((k_rows<false, true, 16, 0>))
   SET((k_rows<false, false, 16, 0>)) SET((k_rows<true, false, 0, 0>)) SET((k_rows<false, false, 0, 0>))
   SET((k_rows<true, false, 32, 1024>)) SET((k_rows<false, false, 32, 1024>))
-  SET(k_cols_inv<EPI_VOLT>) SET(k_cols_inv<EPI_DETECT>) SET(k_cols_inv<EPI_FOLD>)
+  SET(k_cols_inv<EPI_VOLT>) SET(k_cols_inv<EPI_DETECT>)
+  SET((k_cols_inv_fold<2, 4>)) SET((k_cols_inv_fold<2, 2>)) SET((k_cols_inv_fold<2, 1>)) SET((k_cols_inv_fold<1, 1>))
   SET((k_chan_inv<32, EPI_VOLT, 8192>)) SET((k_chan_inv<32, EPI_DETECT, 8192>)) SET((k_chan_inv<32, EPI_FOLD, 8192>))
   SET((k_chan_inv<16, EPI_VOLT, 0>)) SET((k_chan_inv<16, EPI_DETECT, 0>)) SET((k_chan_inv<16, EPI_FOLD, 0>))
   SET((k_chan_inv<8, EPI_VOLT, 0>)) SET((k_chan_inv<8, EPI_DETECT, 0>)) SET((k_chan_inv<8, EPI_FOLD, 0>))
@@ -965,6 +1104,7 @@ int b200_fb_perform(b200_fb_plan* pl, const float* d_in, uint64_t in_span, float
                "time series planes must be 8-byte aligned with even spans");
   B200_REQUIRE(in_step % 2 == 0, "nsamp_step must be even for real input");
   FbSource src;
+  memset(&src, 0, sizeof(src));
   src.kind = SRC_F32; src.ptr = d_in; src.span = in_span; src.step = in_step; src.d_lut = nullptr; src.batch_ready = nullptr; src.conv_ok = 0; src.batch_override = 0;
   FbSink sink;
   memset(&sink, 0, sizeof(sink));

@@ -234,7 +234,9 @@ static int pipeline_scratch(b200_pipeline* p, uint64_t npart) {
   const unsigned ndim = p->desc.unpack.ndim;
   const uint64_t ndat_out = npart * fb->nkeep;
   int rc = B200_OK;
-  if (fmt != B200_FMT_CASPSR8 && fmt != B200_FMT_FLOAT32) {
+  const bool fused_unpack = fmt == B200_FMT_CASPSR8 ||
+                            (!fb->fast_k1 && (fmt == B200_FMT_MEERKAT8 || fmt == B200_FMT_UWB16 || fmt == B200_FMT_GENERIC8));
+  if (!fused_unpack && fmt != B200_FMT_FLOAT32) {
     const unsigned res = fmt_resolution(fmt);
     const uint64_t ndat_in = npart * fb->nsamp_step + fb->nsamp_overlap + 2 * res;
     rc = grow(ctx, &p->d_unpacked, &p->unpacked_floats, ndat_in * ndim * p->desc.unpack.nchan * p->desc.unpack.npol);
@@ -303,6 +305,19 @@ static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t inpu
     src.span = input_span;
     src.step = uint64_t(fb->nsamp_step) * ndim;
     B200_REQUIRE(input_span % 2 == 0 && (first_sample * ndim) % 2 == 0, "float input planes must be 8-byte aligned");
+  } else if (!fb->fast_k1 && (fmt == B200_FMT_MEERKAT8 || fmt == B200_FMT_UWB16 || fmt == B200_FMT_GENERIC8)) {
+    // unpacked inside K1 (filterbank.cu k_cols_fwd): no float time series is ever written.  d_input starts on a
+    // boundary of the format's resolution; the kernel seeks to first_sample itself
+    src.kind = fmt == B200_FMT_MEERKAT8 ? SRC_MEERKAT8 : fmt == B200_FMT_UWB16 ? SRC_UWB16 : SRC_GENERIC8;
+    src.ptr = d_input;
+    src.first = first_sample;
+    src.step = fb->nsamp_step;
+    src.d_lut = p->d_lut;
+    src.scale = p->desc.unpack.scale;
+    src.sample_swap = p->desc.unpack.sample_swap ? p->desc.unpack.sample_swap : 1;
+    src.ndim = ndim;
+    if (fmt == B200_FMT_GENERIC8 && ndim == 1)
+      B200_REQUIRE(first_sample % 2 == 0, "real 8-bit input must start on an even sample");
   } else {
     // unpack the enclosing resolution-aligned range, then seek (Unpacker.C:82-111)
     const unsigned res = fmt_resolution(fmt);
@@ -457,7 +472,9 @@ int b200_pipeline_execute_host(b200_pipeline* p, const void* h_input, uint64_t n
   // one chunk per internal batch of the fused formats; everything at once when a separate unpack
   // pass reads the whole block first
   const int fmt = p->desc.unpack.format;
-  const bool chunked = (fmt == B200_FMT_CASPSR8);
+  // formats K1 unpacks itself read their parts straight from the staged bytes: transfer and compute pipeline per batch
+  const bool chunked = fmt == B200_FMT_CASPSR8 ||
+                       (!fb->fast_k1 && (fmt == B200_FMT_MEERKAT8 || fmt == B200_FMT_UWB16 || fmt == B200_FMT_GENERIC8));
   // The bin plan uploads a few KiB of phase segments on the pipeline's stream.  Host-to-device copies of all
   // streams share one copy engine and run in submission order, so that small copy must be SUBMITTED BEFORE
   // the bulk chunks -- queued behind them it would hold the first kernels back until the whole block had
@@ -484,7 +501,9 @@ int b200_pipeline_execute_host(b200_pipeline* p, const void* h_input, uint64_t n
   for (uint64_t c = 0; c < nchunk; c++) {
     uint64_t end = nbytes;
     if (c + 1 < nchunk) {
-      const uint64_t last_sample = first_sample + (c + 1) * batch * fb->nsamp_step + fb->nsamp_overlap;
+      // whole resolution units (a MeerKAT heap / UWB block interleaves its polarisations and channels)
+      const unsigned res = fmt_resolution(fmt);
+      const uint64_t last_sample = (first_sample + (c + 1) * batch * fb->nsamp_step + fb->nsamp_overlap + res - 1) / res * res;
       end = std::min<uint64_t>(nbytes, (last_sample * bits_per_sample / 8 + 4095) / 4096 * 4096);
     }
     if (end > done)
