@@ -657,36 +657,59 @@ __global__ void __launch_bounds__(1024, 1) k_cols_inv_fold(ColsInvArgs a) {
   const unsigned nbin = a.sink.nbin, dndim = a.sink.dndim;
   const unsigned* plan = a.sink.bins + partl * uint64_t(nkeep);
   float* prof = a.sink.profile + uint64_t(ic) * nbin * NPROD;      // per channel [npol'][nbin][ndim']
-  for (unsigned g = threadIdx.x; g < a.P; g += blockDim.x) {
-    const unsigned mbase = g * a.Q + blockIdx.x * B;
-    const float* s = stage + uint64_t(g * B + g) * NPROD;
+  // Groups of neighbouring lanes are Q samples apart in time: when a phase bin is wider than that (cfg4: 35 thousand
+  // samples per bin) many groups end in the same bin, so the last run of every lane is first combined over
+  // neighbouring lanes with equal bin (segmented scan over maximal runs of equal keys: every value is added exactly
+  // once whatever the key pattern) and only the tail of each run of lanes issues the REDs.
+  const unsigned lane = threadIdx.x & 31u;
+  for (unsigned g0 = threadIdx.x - lane; g0 < a.P; g0 += blockDim.x) {       // warp-uniform trip count
+    const unsigned g = g0 + lane;
     float acc[NPROD];
+#pragma unroll
+    for (unsigned pr = 0; pr < NPROD; pr++) acc[pr] = 0.f;
     unsigned cur = 0xffffffffu;
-    for (unsigned bb = 0; bb < B; bb++) {
-      const unsigned m = mbase + bb;
-      const unsigned bin = (m >= np0 && m < np0 + nkeep) ? __ldg(plan + (m - np0)) : 0xffffffffu;
-      float v[NPROD];
-      if (NPROD == 4) {
-        const float4 x = *reinterpret_cast<const float4*>(s + bb * NPROD);
-        v[0] = x.x; v[1 % NPROD] = x.y; v[2 % NPROD] = x.z; v[3 % NPROD] = x.w;
-      } else if (NPROD == 2) {
-        const float2 x = *reinterpret_cast<const float2*>(s + bb * NPROD);
-        v[0] = x.x; v[1 % NPROD] = x.y;
-      } else v[0] = s[bb];
-      if (bin != cur) {
-        if (cur < nbin)                                      // nbin: flagged window; 0xffffffff: discarded sample
+    if (g < a.P) {
+      const unsigned mbase = g * a.Q + blockIdx.x * B;
+      const float* s = stage + uint64_t(g * B + g) * NPROD;
+      for (unsigned bb = 0; bb < B; bb++) {
+        const unsigned m = mbase + bb;
+        const unsigned bin = (m >= np0 && m < np0 + nkeep) ? __ldg(plan + (m - np0)) : 0xffffffffu;
+        float v[NPROD];
+        if (NPROD == 4) {
+          const float4 x = *reinterpret_cast<const float4*>(s + bb * NPROD);
+          v[0] = x.x; v[1 % NPROD] = x.y; v[2 % NPROD] = x.z; v[3 % NPROD] = x.w;
+        } else if (NPROD == 2) {
+          const float2 x = *reinterpret_cast<const float2*>(s + bb * NPROD);
+          v[0] = x.x; v[1 % NPROD] = x.y;
+        } else v[0] = s[bb];
+        if (bin != cur) {
+          if (cur < nbin)                                      // nbin: flagged window; 0xffffffff: discarded sample
 #pragma unroll
-          for (unsigned pr = 0; pr < NPROD; pr++)
-            atomicAdd(prof + (uint64_t(pr / dndim) * nbin + cur) * dndim + pr % dndim, acc[pr]);
-        cur = bin;
+            for (unsigned pr = 0; pr < NPROD; pr++)
+              atomicAdd(prof + (uint64_t(pr / dndim) * nbin + cur) * dndim + pr % dndim, acc[pr]);
+          cur = bin;
 #pragma unroll
-        for (unsigned pr = 0; pr < NPROD; pr++) acc[pr] = v[pr];
-      } else {
+          for (unsigned pr = 0; pr < NPROD; pr++) acc[pr] = v[pr];
+        } else {
 #pragma unroll
-        for (unsigned pr = 0; pr < NPROD; pr++) acc[pr] += v[pr];
+          for (unsigned pr = 0; pr < NPROD; pr++) acc[pr] += v[pr];
+        }
       }
     }
-    if (cur < nbin)
+    // the lane's last run (cur, acc): combine over neighbouring lanes
+    const unsigned prev = __shfl_up_sync(0xffffffffu, cur, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != cur);
+    const unsigned h = 31u - __clz(heads & (0xffffffffu >> (31u - lane)));    // first lane of this lane's run
+#pragma unroll
+    for (unsigned o = 1; o < 32; o <<= 1) {
+#pragma unroll
+      for (unsigned pr = 0; pr < NPROD; pr++) {
+        const float up = __shfl_up_sync(0xffffffffu, acc[pr], o);
+        if (lane >= h + o) acc[pr] += up;
+      }
+    }
+    const bool tail = lane == 31u || ((heads >> (lane + 1u)) & 1u);
+    if (tail && cur < nbin)
 #pragma unroll
       for (unsigned pr = 0; pr < NPROD; pr++)
         atomicAdd(prof + (uint64_t(pr / dndim) * nbin + cur) * dndim + pr % dndim, acc[pr]);
@@ -829,8 +852,10 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
       dim3 grid(pl->Q / Bi, nb * nchan_in);
       dim3 block(npol * (pl->P / 16) * Bi);
       size_t smem = size_t(npol) * pl->P * Bi * sizeof(float2);
-      if (sk.kind == EPI_FOLD)   // the detected products are staged over the transforms, one padding sample per group
+      if (sk.kind == EPI_FOLD) { // the detected products are staged over the transforms, one padding sample per group
         smem = std::max(smem, (size_t(pl->P) * Bi + pl->P) * nprod * sizeof(float));
+        B200_REQUIRE(block.x % 32 == 0, "convolution fold epilogue: %u threads per block are not whole warps", block.x);
+      }
       LaunchScope ls(ctx, KC_INV);
       if (sk.kind == EPI_VOLT) k_cols_inv<EPI_VOLT><<<grid, block, smem, st>>>(a);
       else if (sk.kind == EPI_DETECT) k_cols_inv<EPI_DETECT><<<grid, block, smem, st>>>(a);
