@@ -60,6 +60,8 @@ struct ColsArgs {
   uint64_t first;           // raw formats: first sample of part 0 within the stream at src
   float scale;
   unsigned sample_swap, ndim;
+  const float2* H;          // Q == 1, complex input: the column pass IS the whole transform -- the response is
+                            // applied here and the result goes straight to Z (no row pass)
 };
 
 template <int SRC, int EPT, unsigned PCT>
@@ -143,8 +145,10 @@ __global__ void __launch_bounds__((PCT && EPT == 32) ? 512 : 1024, 1) k_cols_fwd
   };
   float2* dst = a.dst + uint64_t(blk) * a.Nc + n2;
   const float2 wbase = a.Q > 1 ? big_twiddle<false>(a.blo, a.bhi, n2 * j) : make_float2(1.f, 0.f);
+  const float2* Hc = a.H ? a.H + uint64_t(ic) * a.Nc : nullptr;
   auto store = [&](unsigned k1, float2 v, int e) {
     if (a.Q > 1) v = cmul(cmul(v, wbase), s_h[(e << a.lb) + b]);
+    else if (Hc) v = cmul(v, __ldg(Hc + k1));
     dst[uint64_t(k1) * a.Q] = v;
   };
   fft_any<EPT, false, PCT>(P, j, T, map, smem, a.twP, a.twPs, load, store);
@@ -752,6 +756,9 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
   for (uint64_t part0 = 0; part0 < npart; part0 += batch) {
     const unsigned nb = (unsigned)std::min<uint64_t>(batch, npart - part0);
     if (src.batch_ready) B200_CUDA(cudaStreamWaitEvent(st, src.batch_ready[part0 / batch], 0));
+    // a transform that fits one column pass (Q == 1) of complex input needs no row pass: K1 multiplies by the response
+    // and writes Z (the row kernel would be P blocks of a handful of threads: 2.8 of 3.6 ms on the top UWL sub-bands)
+    const bool skip_k2 = pl->Q == 1 && !pl->desc.input_real && !pl->conv_path;
     // ---- K1 ----
     const bool k1_fast = pl->fast_k1 && src.kind <= SRC_CASPSR8 && (src.kind == SRC_F32 || (src.step % 4 == 0 && (reinterpret_cast<uintptr_t>(src.ptr) & 3) == 0));
     if (k1_fast) {
@@ -760,7 +767,8 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
     } else {
       ColsArgs a;
       a.src = src.ptr; a.span = src.span; a.step = src.step; a.lut = src.d_lut;
-      a.dst = pl->scratchA; a.twP = pl->twP.tw; a.twPs = pl->twP.stage; a.blo = pl->bigN.lo; a.bhi = pl->bigN.hi;
+      a.dst = skip_k2 ? pl->scratchZ : pl->scratchA; a.H = skip_k2 ? pl->d_response : nullptr;
+      a.twP = pl->twP.tw; a.twPs = pl->twP.stage; a.blo = pl->bigN.lo; a.bhi = pl->bigN.hi;
       a.P = pl->P; a.Q = pl->Q; a.lb = pl->lbB; a.npol = npol; a.nchan_in = nchan_in; a.Nc = pl->Nc;
       a.part0 = part0;
       a.first = src.first; a.scale = src.scale; a.sample_swap = src.sample_swap; a.ndim = src.ndim;
@@ -793,7 +801,8 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
       }
     }
     // ---- K2 ----
-    if (pl->fast_k2) {
+    if (skip_k2) {
+    } else if (pl->fast_k2) {
       int rc = fast_k2(pl, nb);
       if (rc != B200_OK) return rc;
     } else {
@@ -1026,9 +1035,9 @@ int b200_fb_plan_create(b200_context* cctx, const b200_fb_desc* d, b200_fb_plan*
     const uint64_t cap = std::max<uint64_t>(1, (2ull << 30) / per_part);
     uint64_t b = std::min<uint64_t>(cap, 16);
     // short transforms (cfg2: 512 KiB per part; the upper UWL sub-bands): 16 parts would be a few hundred CTAs of a few
-    // microseconds each.  Take as many parts as keep one spectrum buffer near 32 MiB -- A and Z then stay in the
-    // 126 MB L2 between the kernels of a batch
-    if (per_part * 16 < (32ull << 20)) b = std::min<uint64_t>(std::min<uint64_t>(cap, 4096), (32ull << 20) / per_part);
+    // microseconds each.  Take as many parts as fill a spectrum buffer of 256 MiB (cfg2, 2048-part blocks: 30.7 GS/s
+    // with 37 parts per batch, 36.2 with 64, 43.8 with 256, 47.3 with 1024: launch count and tails beat L2 residency)
+    if (per_part * 16 < (256ull << 20)) b = std::min<uint64_t>(std::min<uint64_t>(cap, 4096), (256ull << 20) / per_part);
     if (!pl->conv_path && pl->Q >= 8 && pl->P >= 16) {
       auto gcd = [](uint64_t x, uint64_t y) { while (y) { const uint64_t t = x % y; x = y; y = t; } return x; };
       const uint64_t sm = uint64_t(std::max(1, ctx->sm_count)), blk = uint64_t(d->input_nchan) * d->npol;
@@ -1041,7 +1050,8 @@ int b200_fb_plan_create(b200_context* cctx, const b200_fb_desc* d, b200_fb_plan*
         if (need > 64) break;
       }
       // ... as long as one spectrum buffer stays below 1.25 GiB (cfg1: 37 x 32 MiB = 1.16 GiB)
-      if (need > 1 && need <= 64 && need <= cap && need * per_part <= (5ull << 28)) b = need;
+      // whole multiples of that count near the size chosen above
+      if (need > 1 && need <= 64 && need <= cap && need * per_part <= (5ull << 28)) b = std::max<uint64_t>(1, b / need) * need;
     }
     pl->batch = d->max_npart ? d->max_npart : unsigned(b);
     // the generic kernels index (part, input channel, polarisation) blocks through grid.y (limit 65535): a

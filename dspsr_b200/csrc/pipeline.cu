@@ -485,9 +485,11 @@ int b200_pipeline_execute_host(b200_pipeline* p, const void* h_input, uint64_t n
     if (rc0 != B200_OK) return rc0;
     p->bins_preset = true;
   }
-  // host-fed blocks are PCIe-bound: chunks (= kernel batches) of 8 parts keep the pipeline fine-grained
-  // (first kernels start after 1/4 of a 32-part block instead of 1/2) at a small cost in kernel efficiency
-  static const unsigned host_batch = getenv("B200_HOST_BATCH") ? (unsigned)atoi(getenv("B200_HOST_BATCH")) : 8u;
+  // host-fed blocks are PCIe-bound: chunks (= kernel batches) of about 64 MB keep the pipeline fine-grained (cfg1: 8
+  // parts, first kernels start after 1/4 of a 32-part block instead of 1/2) at a small cost in kernel efficiency
+  const uint64_t bytes_per_part = std::max<uint64_t>(1, uint64_t(fb->nsamp_step) * p->desc.unpack.nchan * p->desc.unpack.npol *
+                                                            p->desc.unpack.ndim * fmt_nbit(p->desc.unpack.format) / 8);
+  const uint64_t host_batch = std::max<uint64_t>(1, (64ull << 20) / bytes_per_part);
   const uint64_t batch = chunked ? std::max<uint64_t>(1, std::min<uint64_t>(fb->batch, host_batch)) : fb->batch;
   const uint64_t nchunk = chunked ? (npart + batch - 1) / batch : 1;
   while (p->chunk_ready->size() < nchunk) {
