@@ -11,6 +11,22 @@
 
 namespace b200 {
 
+// Tuning switches.  The product build (libb200dsp.so) has NONE: tune_flag / tune_int are constexpr and return the
+// built-in choice, so every variant test below folds away at compile time and the library never reads the environment.
+// `make dev` builds libb200dsp_dev.so with -DB200_TUNING, in which the same calls read B200_* variables once: that build
+// serves the A/B measurements behind DESIGN.md section 6 (scratch/) and tests/test_gpu_variants.py.
+#ifdef B200_TUNING
+#include <cstdlib>
+inline int tune_int(const char* name, int def) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : def;
+}
+inline bool tune_flag(const char* name, bool def) { return tune_int(name, def ? 1 : 0) != 0; }
+#else
+constexpr int tune_int(const char*, int def) { return def; }
+constexpr bool tune_flag(const char*, bool def) { return def; }
+#endif
+
 // ---- host-side error handling: no exceptions cross the C ABI --------------------------------
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);

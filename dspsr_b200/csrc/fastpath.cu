@@ -1188,12 +1188,11 @@ template <typename K> static int opt_in_smem(K kernel, size_t dyn_bytes) {
 }
 
 static unsigned dbg_flags(int k) {
-  const char* e = getenv(k == 1 ? "B200_DBG1" : k == 2 ? "B200_DBG2" : "B200_DBG3");
-  return e ? (unsigned)atoi(e) : 0u;
+  return (unsigned)tune_int(k == 1 ? "B200_DBG1" : k == 2 ? "B200_DBG2" : "B200_DBG3", 0);
 }
 
 static bool fast_enabled() {
-  static const bool on = !(getenv("B200_FAST") && atoi(getenv("B200_FAST")) == 0);
+  static const bool on = tune_flag("B200_FAST", true);
   return on;
 }
 
@@ -1206,7 +1205,7 @@ template <unsigned F> static size_t k3_smem() { return size_t(512 / (F / 16)) * 
 static size_t k3_tma_smem() { return k3_smem<8192>() + 65536; }   // + landing zone of the TMA half tile
 
 static bool k3_r32_enabled() {
-  static const bool on = !(getenv("B200_K3_R32") && atoi(getenv("B200_K3_R32")) == 0);
+  static const bool on = tune_flag("B200_K3_R32", true);
   return on;
 }
 
@@ -1281,8 +1280,8 @@ template <unsigned F> static void k3_launch(b200_fb_plan* pl, const K3Args& a, c
 // Z travels from K2 to K3 in K2's tile-major order when both ends are the kernels that implement it:
 // k2_r32 with the real-input split and the 32.16.16 K3, i.e. P = 2048, Q = 1024, freq_res = 8192 (cfg1).
 static bool z_tiled(const b200_fb_plan* pl) {
-  static const bool want = !(getenv("B200_Z_TILED") && atoi(getenv("B200_Z_TILED")) == 0);
-  static const bool k2r32 = !(getenv("B200_K2_R32") && atoi(getenv("B200_K2_R32")) == 0);
+  static const bool want = tune_flag("B200_Z_TILED", true);
+  static const bool k2r32 = tune_flag("B200_K2_R32", true);
   return want && k2r32 && k3_r32_enabled() && pl->fast_k2 && pl->fast_k3 && pl->c2Q32 && pl->c2F32 &&
          pl->desc.input_real && pl->P == 2048 && pl->Q == 1024 && pl->F == 8192;
 }
@@ -1314,13 +1313,13 @@ int fast_plan_init(b200_fb_plan* pl) {
     // TMA tensor store of the K1 tile: correct (parity-tested) but measured 3.6 % SLOWER than plain 128-bit
     // global stores on B200 (0.278 vs 0.269 ms per 16 parts: two more CTA barriers, one issuing thread), so
     // it is opt-in (B200_K1_TMA=1) until tiles shrink enough to double-buffer the staging area.
-    static const bool want_tma = getenv("B200_K1_TMA") && atoi(getenv("B200_K1_TMA")) == 1;
+    static const bool want_tma = tune_flag("B200_K1_TMA", false);
     pl->k1_tma = false;
     if (want_tma && rows_fit_tma(pl)) {
       pl->tmapA = new CUtensorMap();
       const int trc = make_a_tensor_map(pl, static_cast<CUtensorMap*>(pl->tmapA));
       if (trc == B200_OK) pl->k1_tma = true;
-      if (getenv("B200_DEBUG")) fprintf(stderr, "[b200] K1 TMA store: tensor map rc=%d enabled=%d\n", trc, int(pl->k1_tma));
+      if (tune_flag("B200_DEBUG", false)) fprintf(stderr, "[b200] K1 TMA store: tensor map rc=%d enabled=%d\n", trc, int(pl->k1_tma));
     }
   }
   if (pl->Q == FP_Q && pl->P == FP_P) {
@@ -1362,7 +1361,7 @@ int fast_plan_init(b200_fb_plan* pl) {
   }
   // K3's TMA half-tile loads from the tile-major Z: correct (parity-tested) but measured no faster than the
   // all-register prefetch on B200 (0.248 vs 0.246 ms per 16 parts), so it is opt-in (B200_K3_TMA=1)
-  static const bool want_ztma = getenv("B200_K3_TMA") && atoi(getenv("B200_K3_TMA")) == 1;
+  static const bool want_ztma = tune_flag("B200_K3_TMA", false);
   if (z_tiled(pl) && want_ztma) {
     pl->tmapZ = new CUtensorMap();
     if (make_z_tensor_map(pl, static_cast<CUtensorMap*>(pl->tmapZ)) != B200_OK) {
@@ -1467,11 +1466,11 @@ int fast_k1(b200_fb_plan* pl, const FbSource& src, uint64_t part0, unsigned nb) 
   const unsigned ntiles = pl->Q / (2 * FP_NP) * a.nblk;
   const unsigned cta_per_sm = 512 / (FP_NP * (FP_P / 16));
   a.nsm = (unsigned)ctx->sm_count;
-  a.skew_ns = cta_per_sm > 1 ? (getenv("B200_K1_SKEW") ? (unsigned)atoi(getenv("B200_K1_SKEW")) : 3000u) : 0u;
+  a.skew_ns = cta_per_sm > 1 ? (unsigned)tune_int("B200_K1_SKEW", 3000) : 0u;
   dim3 grid(std::min(ntiles, cta_per_sm * (unsigned)ctx->sm_count));
   dim3 block(FP_NP * (FP_P / 16));
   a.use_tma = pl->k1_tma ? 1 : 0;
-  static const bool l2pf = !(getenv("B200_K1_L2PF") && atoi(getenv("B200_K1_L2PF")) == 0);
+  static const bool l2pf = tune_flag("B200_K1_L2PF", true);
   a.l2_prefetch = l2pf ? 1 : 0;
   a.overlap = pl->nsamp_overlap;
   CUtensorMap tm;
@@ -1504,13 +1503,13 @@ int fast_k2(b200_fb_plan* pl, unsigned nb) {
   const unsigned ntiles = (split ? (FP_P / 2) / G : FP_P / (2 * G)) * a.nblk;
   dim3 grid(persistent_grid(ctx, ntiles));
   LaunchScope ls(ctx, KC_ROWS);
-  static const bool r32 = !(getenv("B200_K2_R32") && atoi(getenv("B200_K2_R32")) == 0);
+  static const bool r32 = tune_flag("B200_K2_R32", true);
   a.tw32 = pl->c2Q32;
   a.z_tiled = z_tiled(pl) ? 1 : 0;
 #ifdef B200_ABLATION
-  if (getenv("B200_K2_NOH")) a.H = nullptr;   // timing experiment only (cost of the response stream): results are wrong
+  if (tune_flag("B200_K2_NOH", false)) a.H = nullptr;   // timing experiment only (cost of the response stream): results are wrong
 #endif
-  static const bool g2 = !(getenv("B200_K2_G2") && atoi(getenv("B200_K2_G2")) == 0);
+  static const bool g2 = tune_flag("B200_K2_G2", true);
   if (r32 && pl->c2Q32 && split && a.z_tiled && g2) {
     k2_g2<FP_P><<<grid, 512, k2r32_smem(), ctx->stream>>>(a);
     return B200_OK;

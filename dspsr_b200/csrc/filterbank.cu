@@ -774,12 +774,12 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
       a.first = src.first; a.scale = src.scale; a.sample_swap = src.sample_swap; a.ndim = src.ndim;
       dim3 grid(pl->Q / B, nb * nblk1);
       const bool ct = (pl->P == 2048) && src.kind <= SRC_CASPSR8;   // compile-time-sized fast path (float / CASPSR sources)
-      static const int k1_ept = getenv("B200_K1_EPT") ? atoi(getenv("B200_K1_EPT")) : 32;
+      static const int k1_ept = tune_int("B200_K1_EPT", 32);
       const bool ct16 = ct && k1_ept == 16;
       if (ct16) a.twPs = pl->twP.stage16;
       dim3 block((pl->P / ((ct && !ct16) ? 32 : 16)) * B);
       size_t smem = size_t(pl->P) * B * sizeof(float2);
-      if (getenv("B200_DEBUG") && part0 == 0) {
+      if (tune_flag("B200_DEBUG", false) && part0 == 0) {
         int nb1 = 0, nb2 = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb1, k_cols_fwd<SRC_CASPSR8, 32, 2048>, block.x, smem);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_cols_fwd<SRC_CASPSR8, 16, 0>, block.x, smem);
@@ -896,7 +896,7 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
       size_t smem = size_t(CB) * npol_cta * F * sizeof(float2);
       dim3 grid(pl->nchan_out / CB, nb, npol / npol_cta);
       const bool ct = (F == 8192 && npol_cta == npol && CB == 1);   // compile-time-sized fast path
-      static const int k3_ept = getenv("B200_K3_EPT") ? atoi(getenv("B200_K3_EPT")) : 32;
+      static const int k3_ept = tune_int("B200_K3_EPT", 32);
       const bool ct16 = ct && k3_ept == 16;
       if (ct16) a.twFs = pl->twF.stage16;
       dim3 block(CB * npol_cta * ((ct && !ct16) ? F / 32 : T));
@@ -1007,8 +1007,8 @@ int b200_fb_plan_create(b200_context* cctx, const b200_fb_desc* d, b200_fb_plan*
   // column tile: B columns, P*B elements <= 16384, (P/16)*B threads <= 1024
   // (tuning overrides: B200_TILE_KB_COLS / B200_TILE_KB_ROWS = tile budget in KiB)
   size_t tile_cols = SMEM_TILE, tile_rows = SMEM_TILE;
-  if (const char* e = getenv("B200_TILE_KB_COLS")) tile_cols = size_t(atoi(e)) * 1024;
-  if (const char* e = getenv("B200_TILE_KB_ROWS")) tile_rows = size_t(atoi(e)) * 1024;
+  tile_cols = size_t(tune_int("B200_TILE_KB_COLS", int(SMEM_TILE / 1024))) * 1024;
+  tile_rows = size_t(tune_int("B200_TILE_KB_ROWS", int(SMEM_TILE / 1024))) * 1024;
   {
     unsigned lb = 0;
     while ((2u << lb) <= pl->Q && size_t(pl->P) * (2u << lb) * sizeof(float2) <= tile_cols &&

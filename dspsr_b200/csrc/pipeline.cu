@@ -160,7 +160,7 @@ int b200_pipeline_create(b200_context* cctx, const b200_pipeline_desc* d, b200_p
     if (rc != B200_OK) { b200_pipeline_destroy(p); return rc; }
   }
   if (fmt == B200_FMT_CASPSR8 || fmt == B200_FMT_GENERIC8) {
-    static const bool arith = !(getenv("B200_LUT_ARITH") && atoi(getenv("B200_LUT_ARITH")) == 0);
+    static const bool arith = tune_flag("B200_LUT_ARITH", true);
     p->conv_ok = arith ? lut_as_arithmetic(d->unpack.lut, &p->conv_hi, &p->conv_lo) : 0;
     cudaError_t e = cudaMalloc(&p->d_lut, 256 * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_lut, d->unpack.lut, 256 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
@@ -416,7 +416,7 @@ static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t inpu
     sink.nbin = p->desc.nbin;
     // one-bin-per-chunk shortcut of the fold epilogue: measured SLOWER than the per-sample walk on
     // B200 (0.83 vs 0.76 ms per 32 parts of cfg1), so it is opt-in for experiments only
-    static const bool fold_fast = getenv("B200_FOLD_FAST") && atoi(getenv("B200_FOLD_FAST")) == 1;
+    static const bool fold_fast = tune_flag("B200_FOLD_FAST", false);
     sink.phase_per_sample = (fold_fast && !wt.d) ? pps : 0.0;      // flagged samples break the one-bin-per-chunk shortcut
     sink.profile = b200_fold_device_profile(p->fold);
   } else {
