@@ -312,6 +312,8 @@ def run_ours(args):
             fd, keep = E.make_fb_desc(cfg["input_real"], S["nin"], cfg["npol"], S["C"], S["F"], S["npos"], S["nneg"],
                                       st["H"], args.batch)
             st["pipe"] = pipe = E.Pipeline(ctx, ud, fd, keep, st["state"], st["dndim"], st["nbin"])
+            if args.deterministic and st["nbin"]:
+                pipe.set_deterministic()
             st["h_raw"] = torch.from_numpy(st["raw"]).pin_memory()
             st["d_raw"] = st["h_raw"].to("cuda", non_blocking=True)
             st["H"] = None                                    # the plan holds its own copy
@@ -528,6 +530,7 @@ def run_ours(args):
                    "parts_per_block": [s["parts"] for s in streams] if len(streams) > 1 else s0["parts"],
                    "samples_per_pol_per_step": samples_step_all, "batch_parts": s0["pipe"].info.batch_npart,
                    "sharding": meta["sharding"], "combine": combine, "numa_bound_cores": numa_cores,
+                   "fold_accumulation": "fixed point (reproducible)" if args.deterministic else "float RED (default)",
                    "l2": "inputs larger than L2: %d MB raw per block, %d MB of spectrum scratch per batch"
                          % (sum(s["raw"].nbytes for s in streams) // 1000000, s0["pipe"].info.scratch_bytes // 1000000)},
         "real_time_factor": value / rt,
@@ -577,6 +580,8 @@ def main():
     ap.add_argument("--step-ms", type=float, default=100.0, help="target device time of one step")
     ap.add_argument("--batch", type=int, default=0, help="parts per internal kernel batch (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--deterministic", action="store_true",
+                    help="fold with the reproducible fixed-point accumulator (b200_pipeline_set_deterministic)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -213,6 +213,8 @@ SIGNATURES = {
     "b200_fold_set_bins": (_i, [_vp, _d, _d, _u64, _u64, C.POINTER(_u64)]),
     "b200_fold_set_bins_weighted": (_i, [_vp, _d, _d, _u64, _u64, _vp, _u64, _u, _u64]),
     "b200_fold_weighted": (_i, [_vp]),
+    "b200_fold_set_deterministic": (_i, [_vp, C.c_float]),
+    "b200_pipeline_set_deterministic": (_i, [_vp, C.c_float]),
     "b200_fold_get_bin_hits": (_i, [_vp, _vp]),
     "b200_fold_fold": (_i, [_vp, _vp, _u64]),
     "b200_fold_fold_into": (_i, [_vp, _vp, _u64, _vp, _u64]),

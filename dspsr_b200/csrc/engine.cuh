@@ -52,6 +52,11 @@ struct FbSink {
   double phase_per_sample;  // of the block's fold call (0 = unknown): enables the one-bin-per-chunk path
   unsigned nbin;
   float* profile;           // [chan][npol'][nbin][dndim]
+  // reproducible accumulation (b200_fold_set_deterministic): run sums are converted to fixed point (units of lsb)
+  // and added to 64-bit integers -- integer addition is associative, so the result no longer depends on the order
+  // in which the CTAs' reductions arrive
+  long long* fix;           // same layout as profile, or null
+  float inv_lsb;
 };
 
 #ifdef __CUDACC__
@@ -79,6 +84,12 @@ __device__ __forceinline__ int detect_products(int state, float2 p, float2 q, fl
     r[0] = __fadd_rn(pp, qq); r[1] = __fsub_rn(pp, qq); r[2] = __fmul_rn(2.f, re); r[3] = __fmul_rn(2.f, im);
   }
   return 4;
+}
+
+// one run sum into the PhaseSeries: RED.ADD.F32, or RED.ADD.64 of the fixed-point value in deterministic mode
+__device__ __forceinline__ void profile_add(float* profile, long long* fix, float inv_lsb, uint64_t idx, float v) {
+  if (fix) atomicAdd(reinterpret_cast<unsigned long long*>(fix + idx), (unsigned long long)__float2ll_rn(v * inv_lsb));
+  else atomicAdd(profile + idx, v);
 }
 
 __host__ __device__ inline unsigned state_nprod(int state, unsigned npol) {

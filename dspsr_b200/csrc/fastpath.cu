@@ -1123,7 +1123,7 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a, const __grid_constant_
     if (tn < ntiles) issue_loads(tn);
     {
       const unsigned nbin = a.sink.nbin;
-      float* prof0 = a.sink.profile + uint64_t(ch0) * nbin * nprod;     // per channel [npol'][nbin][ndim']
+      const uint64_t prof0 = uint64_t(ch0) * nbin * nprod;              // per channel [npol'][nbin][ndim']
       for (unsigned it = threadIdx.x; it < total; it += 512u) {
         const unsigned c = (CB == 1) ? 0 : it / nrun;
         if (it >= 1024u) run_of(it, rt0, rt1, rbin);
@@ -1147,10 +1147,11 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a, const __grid_constant_
             if (unsigned(8 + i) < n) { acc[0] += x[i].x; acc[1] += x[i].y; acc[2] += x[i].z; acc[3] += x[i].w; }
           }
         }
-        float* base = prof0 + uint64_t(c) * nbin * nprod;
+        const uint64_t base = prof0 + uint64_t(c) * nbin * nprod;
         if (rbin < nbin)                                    // bin == nbin: samples of a flagged window (weights.cu)
           for (unsigned pr = 0; pr < nprod; pr++)
-            atomicAdd(base + (uint64_t(pr / dndim) * nbin + rbin) * dndim + pr % dndim, acc[pr]);
+            profile_add(a.sink.profile, a.sink.fix, a.sink.inv_lsb, base + (uint64_t(pr / dndim) * nbin + rbin) * dndim + pr % dndim,
+                        acc[pr]);
       }
     }
     __syncthreads();       // fold readers are done before the next tile's first scatter

@@ -437,15 +437,15 @@ __global__ void __launch_bounds__((FCT && EPT == 32) ? 512 : 1024, 1) k_chan_inv
     const unsigned nchunk = (nkeep + L - 1) / L;
     const unsigned total = a.CB * nchunk;
     const unsigned* plan = a.sink.bins + partl * uint64_t(nkeep);
-    float* prof0 = a.sink.profile + uint64_t(ch0) * nbin * nprod;
+    const uint64_t prof0 = uint64_t(ch0) * nbin * nprod;
     auto red_add = [&](unsigned key, const float* acc) {
       // key = c*(nbin+1) + bin; profile layout per channel [npol'][nbin][ndim'];  bin == nbin marks the samples of
       // a flagged window (weights.cu): dropped
       const unsigned c = key / (nbin + 1u), bin = key - c * (nbin + 1u);
       if (bin == nbin) return;
-      float* base = prof0 + uint64_t(c) * nbin * nprod;
+      const uint64_t base = prof0 + uint64_t(c) * nbin * nprod;
       for (unsigned pr = 0; pr < nprod; pr++)
-        atomicAdd(base + (uint64_t(pr / dndim) * nbin + bin) * dndim + pr % dndim, acc[pr]);
+        profile_add(a.sink.profile, a.sink.fix, a.sink.inv_lsb, base + (uint64_t(pr / dndim) * nbin + bin) * dndim + pr % dndim, acc[pr]);
     };
     const bool chunk_monotonic = a.sink.phase_per_sample > 0.0 && a.sink.phase_per_sample * double(L) < 0.25;
     const unsigned niter = (total + nthreads - 1) / nthreads;
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(1024, 1) k_cols_inv_fold(ColsInvArgs a) {
   __syncthreads();
   const unsigned nbin = a.sink.nbin, dndim = a.sink.dndim;
   const unsigned* plan = a.sink.bins + partl * uint64_t(nkeep);
-  float* prof = a.sink.profile + uint64_t(ic) * nbin * NPROD;      // per channel [npol'][nbin][ndim']
+  const uint64_t prof = uint64_t(ic) * nbin * NPROD;               // per channel [npol'][nbin][ndim']
   // Groups of neighbouring lanes are Q samples apart in time: when a phase bin is wider than that (cfg4: 35 thousand
   // samples per bin) many groups end in the same bin, so the last run of every lane is first combined over
   // neighbouring lanes with equal bin (segmented scan over maximal runs of equal keys: every value is added exactly
@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(1024, 1) k_cols_inv_fold(ColsInvArgs a) {
           if (cur < nbin)                                      // nbin: flagged window; 0xffffffff: discarded sample
 #pragma unroll
             for (unsigned pr = 0; pr < NPROD; pr++)
-              atomicAdd(prof + (uint64_t(pr / dndim) * nbin + cur) * dndim + pr % dndim, acc[pr]);
+              profile_add(a.sink.profile, a.sink.fix, a.sink.inv_lsb, prof + (uint64_t(pr / dndim) * nbin + cur) * dndim + pr % dndim, acc[pr]);
           cur = bin;
 #pragma unroll
           for (unsigned pr = 0; pr < NPROD; pr++) acc[pr] = v[pr];
@@ -716,7 +716,7 @@ __global__ void __launch_bounds__(1024, 1) k_cols_inv_fold(ColsInvArgs a) {
     if (tail && cur < nbin)
 #pragma unroll
       for (unsigned pr = 0; pr < NPROD; pr++)
-        atomicAdd(prof + (uint64_t(pr / dndim) * nbin + cur) * dndim + pr % dndim, acc[pr]);
+        profile_add(a.sink.profile, a.sink.fix, a.sink.inv_lsb, prof + (uint64_t(pr / dndim) * nbin + cur) * dndim + pr % dndim, acc[pr]);
   }
 }
 

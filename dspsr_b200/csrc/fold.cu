@@ -308,6 +308,8 @@ struct FoldArgs {
   uint64_t prof_span;            // floats between the planes of the profile (nbin*ndim when the handle owns it)
   unsigned nchan, npol, ndim, nbin, slab;
   unsigned smem_bins;
+  long long* fix;                // deterministic mode: fixed-point accumulator (engine.cuh profile_add), else null
+  float inv_lsb;
 };
 
 template <int NDIM>
@@ -318,11 +320,16 @@ __global__ void k_fold(FoldArgs a) {
   const uint64_t s1 = min(a.ndat, s0 + a.slab);
   const float* tp = a.in + uint64_t(plane) * a.in_span + a.idat_start * NDIM;
   float* prof = a.profile + uint64_t(plane) * a.prof_span;
+  long long* fixp = a.fix ? a.fix + uint64_t(plane) * a.prof_span : nullptr;
   if (a.smem_bins) {
     for (unsigned i = threadIdx.x; i < a.nbin * NDIM; i += blockDim.x) sbins[i] = 0.f;
     __syncthreads();
   }
   float* dst = a.smem_bins ? sbins : prof;
+  auto add = [&](uint64_t idx, float v) {
+    if (fixp) profile_add(prof, fixp, a.inv_lsb, idx, v);     // straight to the fixed-point accumulator
+    else atomicAdd(dst + idx, v);
+  };
   const unsigned L = 16;
   for (uint64_t c0 = s0 + uint64_t(threadIdx.x) * L; c0 < s1; c0 += uint64_t(blockDim.x) * L) {
     const uint64_t c1 = min(s1, c0 + L);
@@ -342,7 +349,7 @@ __global__ void k_fold(FoldArgs a) {
       }
       if (bin != cur) {
         if (cur < a.nbin)                                    // cur == nbin: samples of a flagged window, dropped
-          for (int d = 0; d < NDIM; d++) atomicAdd(dst + uint64_t(cur) * NDIM + d, acc[d]);
+          for (int d = 0; d < NDIM; d++) add(uint64_t(cur) * NDIM + d, acc[d]);
         cur = bin;
         for (int d = 0; d < NDIM; d++) acc[d] = v[d];
       } else {
@@ -350,7 +357,7 @@ __global__ void k_fold(FoldArgs a) {
       }
     }
     if (cur < a.nbin)
-      for (int d = 0; d < NDIM; d++) atomicAdd(dst + uint64_t(cur) * NDIM + d, acc[d]);
+      for (int d = 0; d < NDIM; d++) add(uint64_t(cur) * NDIM + d, acc[d]);
   }
   if (a.smem_bins) {
     __syncthreads();
@@ -365,9 +372,17 @@ __global__ void k_fold(FoldArgs a) {
 
 using namespace b200;
 
+// fixed-point accumulator -> float profile (deterministic mode)
+__global__ void k_fix_to_float(const long long* __restrict__ fix, float lsb, uint64_t n, float* __restrict__ out) {
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x)
+    out[i] = float(double(fix[i]) * double(lsb));
+}
+
 struct b200_fold {
   Context* ctx;
   unsigned nchan, npol, ndim, nbin;
+  long long* d_fix;              // deterministic mode (b200_fold_set_deterministic): the accumulator; d_profile is
+  float lsb;                     // refreshed from it whenever it is read
   float* d_profile;
   unsigned* d_hits_total;
   unsigned* d_hits_last;
@@ -553,6 +568,7 @@ int b200_fold_create(b200_context* cctx, unsigned nchan, unsigned npol, unsigned
 int b200_fold_destroy(b200_fold* f) {
   if (!f) return B200_OK;
   if (f->d_profile) cudaFree(f->d_profile);
+  if (f->d_fix) cudaFree(f->d_fix);
   if (f->d_hits_total) cudaFree(f->d_hits_total);
   if (f->d_hits_last) cudaFree(f->d_hits_last);
   if (f->d_bins) cudaFree(f->d_bins);
@@ -666,6 +682,9 @@ static int fold_into(b200_fold* f, const float* d_in, uint64_t in_span, float* d
   a.in = d_in; a.in_span = in_span; a.idat_start = f->idat_start; a.ndat = f->ndat; a.bins = f->d_bins;
   a.profile = d_out; a.prof_span = out_span;
   a.nchan = f->nchan; a.npol = f->npol; a.ndim = f->ndim; a.nbin = f->nbin;
+  // deterministic mode accumulates in the handle's fixed-point array (only when folding into the handle's own profile)
+  a.fix = (f->d_fix && d_out == f->d_profile) ? f->d_fix : nullptr;
+  a.inv_lsb = f->d_fix ? 1.0f / f->lsb : 0.f;
   const unsigned threads = 256;
   const unsigned nplane = f->nchan * f->npol;
   // slabs so that the grid fills the machine a few times over
@@ -674,7 +693,7 @@ static int fold_into(b200_fold* f, const float* d_in, uint64_t in_span, float* d
   a.slab = (unsigned)std::min<uint64_t>(slab, 1u << 30);
   unsigned gx = (unsigned)((f->ndat + a.slab - 1) / a.slab);
   size_t smem = size_t(f->nbin) * f->ndim * sizeof(float);
-  a.smem_bins = smem <= 48 * 1024 ? 1 : 0;
+  a.smem_bins = (smem <= 48 * 1024 && !a.fix) ? 1 : 0;
   if (!a.smem_bins) smem = 0;
   LaunchScope ls(ctx, KC_OTHER);
   // planes beyond the 65535 limit of grid.y go in further launches
@@ -683,6 +702,7 @@ static int fold_into(b200_fold* f, const float* d_in, uint64_t in_span, float* d
     FoldArgs b = a;
     b.in = a.in + uint64_t(p0) * in_span;
     b.profile = a.profile + uint64_t(p0) * out_span;
+    if (a.fix) b.fix = a.fix + uint64_t(p0) * out_span;
     dim3 grid(gx, np);
     if (f->ndim == 4) k_fold<4><<<grid, threads, smem, ctx->stream>>>(b);
     else if (f->ndim == 2) k_fold<2><<<grid, threads, smem, ctx->stream>>>(b);
@@ -703,9 +723,42 @@ int b200_fold_fold_into(b200_fold* f, const float* d_in, uint64_t in_span, float
   return fold_into(f, d_in, in_span, d_out, out_span);
 }
 
+// deterministic mode: bring the float view of the accumulator up to date
+static int fold_refresh(b200_fold* f) {
+  if (!f->d_fix) return B200_OK;
+  const uint64_t nfloat = uint64_t(f->nchan) * f->npol * f->ndim * f->nbin;
+  LaunchScope ls(f->ctx, KC_OTHER);
+  const unsigned grid = unsigned(std::min<uint64_t>((nfloat + 255) / 256, uint64_t(f->ctx->sm_count) * 8));
+  k_fix_to_float<<<grid, 256, 0, f->ctx->stream>>>(f->d_fix, f->lsb, nfloat, f->d_profile);
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_fold_set_deterministic(b200_fold* f, float lsb) {
+  B200_REQUIRE(f, "b200_fold_set_deterministic: null fold");
+  const uint64_t nfloat = uint64_t(f->nchan) * f->npol * f->ndim * f->nbin;
+  if (!(lsb > 0.f)) {                      // back to floating-point accumulation (from the current float view)
+    if (f->d_fix) {
+      int rc = fold_refresh(f);
+      if (rc != B200_OK) return rc;
+      B200_CUDA(cudaStreamSynchronize(f->ctx->stream));
+      cudaFree(f->d_fix);
+      f->d_fix = nullptr;
+    }
+    return B200_OK;
+  }
+  B200_REQUIRE(f->ndat_total == 0, "b200_fold_set_deterministic: switch modes on an empty (zeroed) PhaseSeries");
+  if (!f->d_fix) B200_CUDA(cudaMalloc(&f->d_fix, nfloat * sizeof(long long)));
+  B200_CUDA(cudaMemsetAsync(f->d_fix, 0, nfloat * sizeof(long long), f->ctx->stream));
+  f->lsb = lsb;
+  return B200_OK;
+}
+
 int b200_fold_synch(b200_fold* f, float* h_profile) {
   B200_REQUIRE(f && h_profile, "b200_fold_synch: null argument");
   const uint64_t nfloat = uint64_t(f->nchan) * f->npol * f->ndim * f->nbin;
+  int rcr = fold_refresh(f);
+  if (rcr != B200_OK) return rcr;
   B200_CUDA(cudaMemcpyAsync(h_profile, f->d_profile, nfloat * sizeof(float), cudaMemcpyDeviceToHost, f->ctx->stream));
   B200_CUDA(cudaStreamSynchronize(f->ctx->stream));
   return B200_OK;
@@ -725,6 +778,7 @@ int b200_fold_zero(b200_fold* f) {
   B200_REQUIRE(f, "b200_fold_zero: null fold");
   const uint64_t nfloat = uint64_t(f->nchan) * f->npol * f->ndim * f->nbin;
   B200_CUDA(cudaMemsetAsync(f->d_profile, 0, nfloat * sizeof(float), f->ctx->stream));
+  if (f->d_fix) B200_CUDA(cudaMemsetAsync(f->d_fix, 0, nfloat * sizeof(long long), f->ctx->stream));
   B200_CUDA(cudaMemsetAsync(f->d_hits_total, 0, f->nbin * sizeof(unsigned), f->ctx->stream));
   B200_CUDA(cudaMemsetAsync(f->d_hits_last, 0, f->nbin * sizeof(unsigned), f->ctx->stream));
   f->ndat_total = 0;
@@ -734,7 +788,12 @@ int b200_fold_zero(b200_fold* f) {
 
 int b200_fold_weighted(const b200_fold* f) { return f && f->weighted ? 1 : 0; }
 
-float* b200_fold_device_profile(b200_fold* f) { return f ? f->d_profile : nullptr; }
+// deterministic mode: the float view is refreshed (stream ordered) before the pointer is handed out
+float* b200_fold_device_profile(b200_fold* f) {
+  if (!f) return nullptr;
+  fold_refresh(f);
+  return f->d_profile;
+}
 unsigned* b200_fold_device_hits(b200_fold* f) { return f ? f->d_hits_total : nullptr; }
 
 }  // extern "C"
@@ -742,6 +801,8 @@ unsigned* b200_fold_device_hits(b200_fold* f) { return f ? f->d_hits_total : nul
 // internal accessors for pipeline.cu
 namespace b200 {
 const unsigned* fold_bins(b200_fold* f) { return f->d_bins; }
+long long* fold_fix(b200_fold* f) { return f->d_fix; }
+float fold_lsb(b200_fold* f) { return f->lsb; }
 const uint2* fold_runs(b200_fold* f) { return f->d_runs; }
 const unsigned* fold_nruns(b200_fold* f) { return f->d_nruns; }
 

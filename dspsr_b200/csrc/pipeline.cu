@@ -16,6 +16,8 @@ const unsigned* fold_bins(b200_fold* f);
 const uint2* fold_runs(b200_fold* f);
 const unsigned* fold_nruns(b200_fold* f);
 int fold_build_runs(b200_fold* f, unsigned nkeep, unsigned align);
+long long* fold_fix(b200_fold* f);
+float fold_lsb(b200_fold* f);
 int fold_reserve(b200_fold* f, uint64_t ndat, unsigned nkeep);
 }
 using namespace b200;
@@ -418,7 +420,9 @@ static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t inpu
     // B200 (0.83 vs 0.76 ms per 32 parts of cfg1), so it is opt-in for experiments only
     static const bool fold_fast = tune_flag("B200_FOLD_FAST", false);
     sink.phase_per_sample = (fold_fast && !wt.d) ? pps : 0.0;      // flagged samples break the one-bin-per-chunk shortcut
-    sink.profile = b200_fold_device_profile(p->fold);
+    sink.fix = fold_fix(p->fold);
+    sink.inv_lsb = sink.fix ? 1.0f / fold_lsb(p->fold) : 0.f;
+    sink.profile = sink.fix ? nullptr : b200_fold_device_profile(p->fold);
   } else {
     B200_REQUIRE(d_detected, "b200_pipeline_execute: nbin == 0 needs an output buffer for the detected series");
     sink.kind = EPI_DETECT;
@@ -691,6 +695,14 @@ int b200_pipeline_get_phase_series(b200_pipeline* p, b200_phase_series* out) {
     if (rc == B200_OK) out->integration_length = double(folded) / out->obs.rate;
   }
   return rc;
+}
+
+int b200_pipeline_set_deterministic(b200_pipeline* p, float lsb) {
+  B200_REQUIRE(p && p->fold, "b200_pipeline_set_deterministic: pipeline has no fold stage");
+  // lsb < 0: a unit suited to input of unit variance (the 8-bit tables are scaled to it, BitTable.C:182-194): the
+  // un-normalised transforms give detected samples of the order of n_fft * freq_res; 2^-20 of that per unit
+  if (lsb < 0.f) lsb = float(double(p->fb->Nc) * double(p->fb->F) * std::ldexp(1.0, -20));
+  return b200_fold_set_deterministic(p->fold, lsb);
 }
 
 int b200_pipeline_reset(b200_pipeline* p) {

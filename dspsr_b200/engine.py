@@ -367,6 +367,10 @@ class Pipeline:
             L.check(self.ctx.lib.b200_pipeline_feed_host(self.h, C.c_void_p(ptr), nsamples, dptr, dspan, C.byref(n)))
         return n.value
 
+    def set_deterministic(self, lsb=-1.0):
+        """Reproducible fixed-point accumulation of the PhaseSeries (b200_fold_set_deterministic); lsb < 0: automatic."""
+        L.check(self.ctx.lib.b200_pipeline_set_deterministic(self.h, lsb))
+
     def reserve(self, max_npart):
         L.check(self.ctx.lib.b200_pipeline_reserve(self.h, max_npart))
 

@@ -215,6 +215,14 @@ int b200_fold_synch(b200_fold* fold, float* h_profile);
 /* accumulated hits of every set_bins since the last zero (PhaseSeries::get_hits) */
 int b200_fold_get_hits(b200_fold* fold, unsigned* h_hits, uint64_t* ndat_total);
 int b200_fold_zero(b200_fold* fold);
+/* Reproducible accumulation.  By default run sums reach the PhaseSeries as float reductions (RED.ADD.F32) from many
+ * CTAs: the result depends on their arrival order in the last bits (the reference's own multi-threaded result
+ * depends on the thread count in the same way).  With lsb > 0 every run sum is rounded to a multiple of lsb and
+ * added to a 64-bit integer accumulator instead: integer addition is associative, so the profile is bit-identical
+ * from run to run and independent of the launch order.  lsb must be far below the size of a sample (2^-20 of a
+ * typical detected sample keeps the rounding below that of the float path) and large enough that the total stays
+ * below 2^63 * lsb.  lsb <= 0 returns to float accumulation.  Only on a zeroed PhaseSeries. */
+int b200_fold_set_deterministic(b200_fold* fold, float lsb);
 /* device pointer of the accumulating profile (for NCCL reductions at sub-integration ends) */
 float* b200_fold_device_profile(b200_fold* fold);
 unsigned* b200_fold_device_hits(b200_fold* fold);
@@ -476,6 +484,9 @@ int b200_pipeline_feed(b200_pipeline* pipe, const void* d_bytes, uint64_t nsampl
 /* Fold::Engine::synch + the attributes: fills *ps; when ps->data / ps->hits are non-NULL they receive the
  * accumulated sums [nchan][npol][nbin][ndim] and hits [nbin] (synchronises the stream). */
 int b200_pipeline_get_phase_series(b200_pipeline* pipe, b200_phase_series* ps);
+/* b200_fold_set_deterministic on the pipeline's fold stage; lsb < 0 picks a unit from the transform sizes for input
+ * of unit variance (n_fft * freq_res * 2^-20). */
+int b200_pipeline_set_deterministic(b200_pipeline* pipe, float lsb);
 /* Fold::reset -> Engine::zero + PhaseSeries::zero: clears the sums, the hits and integration_length / ndat_total */
 int b200_pipeline_reset(b200_pipeline* pipe);
 

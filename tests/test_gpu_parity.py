@@ -958,3 +958,110 @@ def test_stream_feed_twobit_filterbank_detected_and_fil(ctx, oracle, tmp_path):
     L.check(ctx.lib.b200_sigproc_file_write(str(path).encode(), C.byref(h), got.ctypes.data, got.size, 0))
     blob = open(path, "rb").read()
     assert blob.endswith(got.tobytes()) and b"HEADER_END" in blob and h.nchans == C_ and h.foff == -2.0
+
+
+# ------------------------------------------------------------------------------------ science known answer
+@pytest.mark.parametrize("F,dm", [(8192, 1.0), (65536, 6.0)])
+def test_injected_dispersed_pulsar_folds_to_a_spike(ctx, oracle, F, dm):
+    """A known answer that does not come from the oracle's arithmetic: a train of one-sample pulses (period 1777.25
+    samples) is dispersed with the ANALYTIC cold-plasma chirp evaluated on the full-length frequency grid (what the
+    interstellar medium does), quantised to 8-bit complex samples and sent through unpack -> coherent dedispersion ->
+    detection -> fold on the GPU with the reference's Dedispersion response.  The folded profile must be a spike in
+    the phase bin the construction predicts, holding nearly all of the pulsed power."""
+    torch, E, L = _torch(), _E(), _L()
+    from dspsr_b200 import hostmath as HM
+    bw, cf, nbin, npart = 16.0, 1400.0, 256, 6
+    d, H = HM.dedispersion(cf, bw, dm, 1, 1, False, frequency_resolution=F)
+    npos, nneg = d.impulse_pos, d.impulse_neg
+    step, overlap = F - npos - nneg, npos + nneg
+    n = npart * step + overlap
+    period = 1777.25
+    t0 = npos + 40.0
+    pulse = np.zeros(n, np.complex128)
+    k = 0
+    while t0 + k * period < n - nneg - 2:
+        pulse[int(round(t0 + k * period))] = 1.0
+        k += 1
+    assert k >= 20
+    kk = np.arange(n)
+    f = np.where(kk < n // 2, kk / n, kk / n - 1.0) * bw                     # baseband frequency of FFT bin (MHz)
+    phase = -2 * np.pi * (1e6 * dm / 2.41e-4) / cf ** 2 * f * f / (cf + f)   # Dedispersion.C:534-545, bw > 0
+    disp = np.fft.ifft(np.fft.fft(pulse) * np.exp(-1j * phase))              # the ISM applies the inverse filter
+    amp = 100.0 / np.abs(np.concatenate([disp.real, disp.imag])).max()
+    raw = np.zeros((n, 1, 2, 2), np.int8)                                    # generic TFP bytes [t][chan][pol][re,im]
+    raw[:, 0, 0, 0] = np.clip(np.rint(disp.real * amp - 0.5), -128, 127)     # the table adds 0.5 (BitTable.C:176)
+    raw[:, 0, 0, 1] = np.clip(np.rint(disp.imag * amp - 0.5), -128, 127)
+    raw = raw.reshape(-1).view(np.uint8)
+    lut, _ = HM.bittable8()
+    ud = E.make_unpack_desc(L.FMT_GENERIC8, 1, 2, 2, lut)
+    fd, keep = E.make_fb_desc(False, 1, 2, 1, F, npos, nneg, H)
+    pipe = E.Pipeline(ctx, ud, fd, keep, "PPQQ", 1, nbin)
+    # output sample m is input sample m + nfilt_pos; fold with the train's own period, phase 0 at output sample 0
+    pipe.execute(torch.from_numpy(raw).cuda(), npart, 0.0, 1.0 / period, first_sample=0)
+    prof, hits, ntot = pipe.synch()
+    assert ntot == npart * step and hits.sum() == ntot
+    pp = prof[0, 0] / np.maximum(hits, 1)
+    want_bin = int(((t0 - npos) / period % 1.0) * nbin)
+    assert int(pp.argmax()) == want_bin
+    on = pp[want_bin] + pp[(want_bin + 1) % nbin] + pp[(want_bin - 1) % nbin]
+    off = np.median(pp)
+    assert (on - 3 * off) / max(pp.sum() - nbin * off, 1e-30) > 0.9
+    # recovered pulse energy: each unit pulse was scaled by amp and by the table's gain; the unnormalised FFT pair
+    # multiplies amplitudes by F (Convolution.C:303-305), so a dedispersed pulse carries (amp * g * F)^2
+    g = float(lut[129] - lut[128])                                           # table units per count
+    per_pulse = (amp * g * F) ** 2
+    pulses_kept = sum(1 for i in range(k) if npos <= int(round(t0 + i * period)) < npos + npart * step)
+    got = (prof[0, 0, want_bin] + prof[0, 0, (want_bin + 1) % nbin] + prof[0, 0, (want_bin - 1) % nbin])
+    assert got == pytest.approx(pulses_kept * per_pulse, rel=0.08)
+
+
+# ------------------------------------------------------------------------------------ reproducible fold (SURVEY 7, hard part 3)
+def test_deterministic_fold_is_bit_reproducible(ctx, oracle):
+    """b200_pipeline_set_deterministic: fixed-point accumulation makes the folded profile bit-identical from run to run
+    (cfg1 shape: 148 persistent CTAs add their run sums in whatever order they finish), still within the parity
+    tolerance of the oracle; the same for the convolution path and the stand-alone fold engine."""
+    torch, E, L = _torch(), _E(), _L()
+    from dspsr_b200 import hostmath as HM
+    C_, npart, nbin = 256, 3, 1024
+    d, H = HM.dedispersion(1382.0, -400.0, 67.99, 1, C_, True)
+    lut, _ = HM.bittable8()
+    f = oracle.fb_sizes(1, 1, 2, C_, d.ndat, d.impulse_pos, d.impulse_neg)
+    ndat = (npart * f.nsamp_step + f.nsamp_overlap + 3) // 4 * 4
+    raw = synth.caspsr_bytes(ndat, seed=111)
+    phi, pps = 0.25, 1.0 / (0.37 * npart * f.nkeep)
+    d_raw = torch.from_numpy(raw).cuda()
+
+    def run(det):
+        ud = E.make_unpack_desc(L.FMT_CASPSR8, 1, 2, 1, lut)
+        fd, keep = E.make_fb_desc(1, 1, 2, C_, d.ndat, d.impulse_pos, d.impulse_neg, H)
+        pipe = E.Pipeline(ctx, ud, fd, keep, "Coherence", 4, nbin)
+        if det:
+            pipe.set_deterministic()
+        out = []
+        for _ in range(3):
+            pipe.zero()
+            pipe.execute(d_raw, npart, phi, pps)
+            out.append(pipe.synch()[0].copy())
+        return out
+    a = run(True)
+    assert np.array_equal(a[0], a[1]) and np.array_equal(a[0], a[2])
+    lo, _ = oracle.bittable8()
+    _, Ho = oracle.dedispersion(1382.0, -400.0, 67.99, 1, C_, True)
+    op = oracle.make_pipe(0, 1, 2, 1, lo, 0.0, f, None, Ho, "Coherence", 4, nbin)
+    ref, _ = oracle.pipe_run(op, raw, 1, npart, [phi], [pps], 1)
+    assert synth.relerr(a[0], ref) <= TOL
+    b = run(False)
+    assert synth.relerr(b[0], ref) <= TOL
+    # stand-alone fold engine
+    rng = np.random.default_rng(112)
+    x = torch.from_numpy(rng.standard_normal((8, 2, 50000 * 2)).astype(np.float32) * 1e3).cuda()
+    res = []
+    for _ in range(2):
+        fe = E.FoldEngine(ctx, 8, 2, 2, 64)
+        L.check(ctx.lib.b200_fold_set_deterministic(fe.h, 2.0 ** -12))
+        fe.set_bins(0.1, 1.0 / 977.0, 50000)
+        fe.fold(x)
+        res.append(fe.synch())
+    assert np.array_equal(res[0], res[1])
+    bp, hh, _, _ = oracle.fold_plan(0.1, 1.0 / 977.0, 64, 50000)
+    assert synth.relerr(res[0], oracle.fold(x.cpu().numpy(), 2, bp, 64)) <= TOL
