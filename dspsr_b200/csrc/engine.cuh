@@ -120,10 +120,7 @@ struct b200_fb_plan {
   // second-generation kernels (fastpath.cu): which passes they cover for this plan + their stage tables
   bool fast_k1, fast_k2, fast_k3;
   float2 *c2P, *c2Q, *c2F, *c2F32, *c2Q32;
-  float2* d_response_tiled;   // the response in K2's tile-major Z order (fastpath.cu, z_tiled), or null
-  void* tmapA;              // CUtensorMap of scratchA for K1's TMA store (heap copy), or null
-  void* tmapZ;              // CUtensorMap of the tile-major scratchZ for K3's TMA half-tile loads, or null
-  bool k1_tma;
+  float2* d_response_tiled;   // the response in the tile-image order of Z (fastpath.cu zi_pos), or null
 };
 
 namespace b200 {

@@ -17,12 +17,11 @@
 // fills the SM's registers and most of its shared memory: there is no second CTA to overlap with).
 // fb_run (filterbank.cu) dispatches here when the plan's sizes are instantiated below; every other
 // shape keeps the generic kernels.  B200_FAST=0 disables the dispatch (A/B measurements).
-#include <cuda.h>
-
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "engine.cuh"
@@ -53,10 +52,21 @@ __device__ __forceinline__ void ldg_nc_f2x4(const float2* p, float2& a, float2& 
   asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=f"(a.x), "=f"(a.y), "=f"(b.x), "=f"(b.y), "=f"(c.x), "=f"(c.y), "=f"(d.x), "=f"(d.y) : "l"(p));
 }
-// Tile-major Z (see k2_r32): float2 offset of element k2 of tile row g inside one (tile, side) region of Q*8
-// elements.  Four consecutive k2 of a row are contiguous (32 bytes: one sector, one 256-bit load in K3), the
-// eight rows of the tile follow each other, then the next group of four k2.
-__device__ __forceinline__ unsigned zt_pos(unsigned k2, unsigned g) { return ((k2 >> 2) << 5) + (g << 2) + (k2 & 3u); }
+// Tile-image Z (see k2_g2): a K2 tile (8 mirror row pairs x Q = 1024 bins = 16384 float2 = 128 KiB) travels to K3 as
+// the verbatim image of K2's shared-memory arrays, written by two 64 KiB bulk copies (one per half-CTA group).
+// Offset, inside the tile, of element k2 of pair g (0..7), row `which` (0: row low, 1: its mirror row):
+//   [g / 4][k2 / 4][which][ ((g % 4) * 4 + k2 % 4) ^ h(k2 / 4) ],   h(m) = ((m >> 3) ^ (m << 2)) & 15
+// * the four k2 of one K3 channel and row stay one aligned 32-byte group (the XOR permutes them inside the group by
+//   h & 3 and moves the group inside its 128-byte line by h >> 2): K3 fetches them with one 256-bit load;
+// * the four rows g % 4 of a group fill a whole 128-byte line;
+// * as a SHARED-MEMORY layout it is conflict free for every access pattern of K2 (64-bit accesses, 16 lanes per
+//   wavefront): the radix-32 scatter (lane j writes element 32 j + r: bank pair = const ^ j), the gather (lane j
+//   reads j + 32 e) and the split walk (4 consecutive k2 x 4 pairs per half warp).
+__host__ __device__ __forceinline__ unsigned zi_h(unsigned m) { return ((m >> 3) ^ (m << 2)) & 15u; }
+__host__ __device__ __forceinline__ unsigned zi_pos(unsigned g, unsigned which, unsigned k2) {
+  const unsigned m = k2 >> 2;
+  return (g >> 2) * 8192u + m * 32u + which * 16u + ((((g & 3u) << 2) | (k2 & 3u)) ^ zi_h(m));
+}
 
 // Cache policy of the once-written / once-read streams (spectrum scratch A and Z).  st.global.cs (evict
 // first) for the Z stores of K2 measured -7.7 % on that kernel; B200_NO_STREAMING restores default policies.
@@ -103,15 +113,14 @@ struct K1Args {
   unsigned skew_ns, nsm;
   int conv_ok;               // 8-bit table is RN(x*(conv_hi+conv_lo)): convert arithmetically, no gathers
   float conv_hi, conv_lo;
-  int use_tma;               // store the tile with cp.async.bulk.tensor (tensor map over the A buffer)
   int l2_prefetch;           // prefetch the next part's raw bytes into L2 as contiguous slices
   unsigned overlap;          // nsamp_overlap (samples)
 };
 
 // QC: row length Q fixed at compile time (0 = run-time a.Q): all row strides become immediates
-template <int SRC, unsigned P, int NP, bool TMA, unsigned QC = 0>
+template <int SRC, unsigned P, int NP, unsigned QC = 0>
 __global__ void __launch_bounds__(NP*(P / 16), 512 / (NP * (P / 16)))
-k1_c2(K1Args a, const __grid_constant__ CUtensorMap tmapA) {
+k1_c2(K1Args a) {
   extern __shared__ __align__(128) float4 smem4[];
   __shared__ float s_lut[256];
   __shared__ float4 s_h[16 * NP];   // [e][pair] = (W_N^(n2a*T*e), W_N^(n2b*T*e))
@@ -233,8 +242,6 @@ k1_c2(K1Args a, const __grid_constant__ CUtensorMap tmapA) {
         vb[e] = ldg_nc_f2(f + uint64_t(Q) * T * e + 1);
       }
     }
-    // the exchange buffer is scattered into again after this barrier: TMA must have finished reading it
-    if (TMA && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();     // the previous tile's readers of s_h and of the exchange buffer are done
     if (threadIdx.x < 16 * NP * 2) reinterpret_cast<float2*>(s_h)[threadIdx.x] = shv;
 
@@ -249,34 +256,7 @@ k1_c2(K1Args a, const __grid_constant__ CUtensorMap tmapA) {
       for (int e = 0; e < 16; e++) w[e] = __ldg(reinterpret_cast<const unsigned*>(raw + 4ull * Q * T * e));
     }
 
-    if (TMA) {
-      // TMA store: the exchange buffer is free once every thread has gathered its last-stage inputs, so the
-      // twiddled tile is laid out there as [k1][2*NP columns] (dense 16*NP-byte rows) and handed to the TMA
-      // unit as P/256 boxes of 256 rows -- 128-bit shared-memory stores (128 B per cycle) instead of global
-      // stores through the LSU data pipe (32 B per cycle), and no store instructions left to drain.
-      __syncthreads();
-      float4* stage = smem4 + j * NP + pair;                          // row k1 = j + e*T, NP float4 per row
-#pragma unroll
-      for (int e = 0; e < 16; e++) {
-        const float4 h = s_h[e * NP + pair];
-        const float2 xa = cmul(cmul(va[e], wa), make_float2(h.x, h.y));
-        const float2 xb = cmul(cmul(vb[e], wb), make_float2(h.z, h.w));
-        stage[e * int(T * NP)] = make_float4(xa.x, xa.y, xb.x, xb.y);
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem4);
-#pragma unroll
-        for (unsigned box = 0; box < P / 256; box++) {
-          const int c0 = int(col0 * 2);                               // inner coordinate in floats
-          const int c1 = int(blk * P + box * 256);                    // row of the [nblk*P][2Q] float tensor
-          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                       :: "l"(&tmapA), "r"(c0), "r"(c1), "r"(smem_base + box * 256u * 16u * NP) : "memory");
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-    } else {
+    {
       float2* dst = a.dst + uint64_t(blk) * a.Nc + uint64_t(j) * Q + n2;
 #pragma unroll
       for (int e = 0; e < 16; e++) {
@@ -288,7 +268,6 @@ k1_c2(K1Args a, const __grid_constant__ CUtensorMap tmapA) {
       }
     }
   }
-  if (TMA && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -298,7 +277,7 @@ struct K2Args {
   const float2* A;
   float2* Z;
   const float2* H;
-  const float2* Ht;        // H in the tile-major order of Z (same offsets as the Z stores), used when z_tiled
+  const float2* Ht;        // H in the tile-image order of Z (zi_pos), used when z_tiled
   const float2* tw;        // c2 stage tables of Q
   const float2* tw2Q;      // exp(-2 pi i m / (2Q))
   const float2* tw32;      // 32.32 plan: W_1024^(s j), s = 1..7, then W_1024^(8 m j), m = 1..3  ([10][32])
@@ -306,7 +285,7 @@ struct K2Args {
   const float2* b2hi;
   unsigned Nc, npol, nchan_in, nblk;
   unsigned dbg;
-  int z_tiled;             // write Z in the tile-major order (k2_r32 + the 32.16.16 K3 only)
+  int z_tiled;             // Z leaves as the tile image (k2_g2 + the 32.16.16 K3 only)
 };
 
 template <unsigned P, unsigned Q, bool SPLIT>
@@ -475,18 +454,14 @@ __global__ void __launch_bounds__(512, 1) k2_c2(K2Args a) {
 // radix-32 stages -- so the single exchange of the transform is warp-local (__syncwarp, stride-33 padded
 // 64-bit accesses) and the whole tile needs just two CTA barriers (before and after the split phase)
 // instead of six.  Rows a / b of a mirror pair sit in separate float2 arrays (a at sequence 2g, b at 2g+1);
-// the array stride (1057 or 1058, see RSQ) makes the lane-by-pair walk of the split phase conflict free.
+// the array stride 1057 makes the lane-by-pair walk of the split phase conflict free.  Writes Z in natural
+// order (complex input, or real input when the tile-image path k2_g2 is not in use).
 // ------------------------------------------------------------------------------------------
 template <unsigned P, bool SPLIT>
 __global__ void __launch_bounds__(512, 1) k2_r32(K2Args a) {
   extern __shared__ float4 smem4[];
   float2* sm2 = reinterpret_cast<float2*>(smem4);
-  constexpr unsigned Q = 1024, G = 8;
-  // row stride of the shared arrays (float2): the split phase reads element kk of 8 pair rows per warp.  Natural Z
-  // order walks the rows fastest (half-warp = 8 rows x 2 kk: 2 RSQ = 2 mod 16 is conflict free); the tiled order
-  // walks kk fastest so that lanes are in address order (half-warp = 4 kk x 4 rows: 2 RSQ = 4 mod 16).
-  const bool kfast = a.z_tiled != 0;
-  const unsigned RSQ = kfast ? 1058u : 1057u;
+  constexpr unsigned Q = 1024, G = 8, RSQ = 1057u;
   constexpr unsigned TPB = SPLIT ? (P / 2) / G : P / (2 * G);
   __shared__ float2 s_rowtw[G + 1];
   const unsigned seq = threadIdx.x >> 5, j = threadIdx.x & 31u;
@@ -550,9 +525,7 @@ __global__ void __launch_bounds__(512, 1) k2_r32(K2Args a) {
     {
       const float2* H = a.H ? a.H + uint64_t(ic) * Nc : nullptr;
       float2* Zblk = a.Z + uint64_t(blk) * Nc;
-      // kk < 64.  Tiled: lane = (kk & 3) + 4 g2 is the address order inside the warp's 256-byte block (zt_pos)
-      const unsigned g2 = kfast ? (threadIdx.x >> 2) & 7u : threadIdx.x % G;
-      const unsigned kk = kfast ? (threadIdx.x & 3u) + 4u * (threadIdx.x >> 5) : threadIdx.x / G;
+      const unsigned g2 = threadIdx.x % G, kk = threadIdx.x / G;   // kk < 64; lanes walk the pairs first
       const float2* SA = sm2 + (2 * g2) * RSQ;                     // row a of pair g2
       const float2* SB = SA + RSQ;                                 // row b
       auto p33 = [](unsigned i) { return i + (i >> 5); };
@@ -593,34 +566,10 @@ __global__ void __launch_bounds__(512, 1) k2_r32(K2Args a) {
           const float2* HAm = H ? H + (Nc - k0) : nullptr;
           const float2* HB = H ? H + k1b : nullptr;
           const float2* HBm = H ? H + (Nc - k1b) : nullptr;
-          int hstep = KSTEP;
-          // natural order: bin k at Z[k].  Tiled order (a.z_tiled): element k2 of row r sits at
-          // Z'[tile][side][k2/4][g][k2%4] (zt_pos; r < P/2: tile = r/8, side 0, g = r%8; r > P/2: m = P-r, tile = m/8, side 1,
-          // g = m%8), so a K2 tile writes two contiguous 64 KiB regions -- sequential stores -- and a warp's
-          // store covers 256 contiguous bytes.  K3 (32.16.16 plan) reads the same layout.
-          float2 *ZA, *ZAm, *ZB, *ZBm;
-          int zstep, zstepm;
-          if (a.z_tiled) {
-            float2* zt = Zblk + uint64_t(tile) * (2 * Q * G);
-            ZA = zt + zt_pos(kk, g2);                        // (side 0, k2)
-            ZBm = zt + Q * G + zt_pos(kk, g2);               // (side 1, k2)
-            ZB = zt + zt_pos(Q - 1 - kk, g2);                // (side 0, Q-1-k2)
-            ZAm = zt + Q * G + zt_pos(Q - 1 - kk, g2);       // (side 1, Q-1-k2)
-            zstep = 64 * G;                                  // k2 += 64 keeps k2 & 3: the group index moves by 16
-            zstepm = 64 * G;
-            if (H) {                                         // the response sits in the same order (Ht)
-              const float2* Htc = a.Ht + uint64_t(ic) * Nc;
-              HA = Htc + (ZA - Zblk); HAm = Htc + (ZAm - Zblk); HB = Htc + (ZB - Zblk); HBm = Htc + (ZBm - Zblk);
-              hstep = 64 * G;
-            }
-          } else {
-            ZA = Zblk + k0;
-            ZAm = Zblk + (Nc - k0);
-            ZB = Zblk + k1b;
-            ZBm = Zblk + (Nc - k1b);
-            zstep = KSTEP;
-            zstepm = KSTEP;
-          }
+          float2* ZA = Zblk + k0;
+          float2* ZAm = Zblk + (Nc - k0);
+          float2* ZB = Zblk + k1b;
+          float2* ZBm = Zblk + (Nc - k1b);
 #pragma unroll 2
           for (int it = 0; it < 8; it++) {
             const float2 ua = SA[sa + SSTEP * it], ub = SB[sa + SSTEP * it];      // a[k2], b[k2]
@@ -631,15 +580,15 @@ __global__ void __launch_bounds__(512, 1) k2_r32(K2Args a) {
             split(ua, make_float2(vb2.x, -vb2.y), wA, xk, xm);
             split(va2, make_float2(ub.x, -ub.y), wB, yk, ym);
             if (H) {
-              xk = cmul(xk, __ldg(HA + it * hstep));
-              xm = cmul(xm, __ldg(HAm - it * hstep));
-              yk = cmul(yk, __ldg(HB - it * hstep));
-              ym = cmul(ym, __ldg(HBm + it * hstep));
+              xk = cmul(xk, __ldg(HA + it * KSTEP));
+              xm = cmul(xm, __ldg(HAm - it * KSTEP));
+              yk = cmul(yk, __ldg(HB - it * KSTEP));
+              ym = cmul(ym, __ldg(HBm + it * KSTEP));
             }
-            B200_ZST(ZA + it * zstep, xk);
-            B200_ZST(ZAm - it * zstepm, xm);
-            B200_ZST(ZB - it * zstep, yk);
-            B200_ZST(ZBm + it * zstepm, ym);
+            B200_ZST(ZA + it * KSTEP, xk);
+            B200_ZST(ZAm - it * KSTEP, xm);
+            B200_ZST(ZB - it * KSTEP, yk);
+            B200_ZST(ZBm + it * KSTEP, ym);
           }
         } else {
           // rows 0 (array a) and P/2 (array b) mirror onto themselves
@@ -653,13 +602,8 @@ __global__ void __launch_bounds__(512, 1) k2_r32(K2Args a) {
               split(xa, make_float2(xm2.x, -xm2.y), __ldg(a.tw2Q + k2), xk, xm);
               const unsigned k = P * k2, km = (Nc - k) & (Nc - 1);
               if (H) { xk = cmul(xk, __ldg(H + k)); xm = cmul(xm, __ldg(H + km)); }
-              if (a.z_tiled) {                       // row 0: tile 0, side 0, g 0
-                Zblk[zt_pos(k2, 0)] = xk;
-                if (km2 != k2) Zblk[zt_pos(km2, 0)] = xm;
-              } else {
-                Zblk[k] = xk;
-                if (km2 != k2) Zblk[km] = xm;
-              }
+              Zblk[k] = xk;
+              if (km2 != k2) Zblk[km] = xm;
             }
             if (k2 < Q / 2) {
               const float2 xb = SB[p33(k2)], xm2 = SB[p33(Q - 1 - k2)];
@@ -667,13 +611,8 @@ __global__ void __launch_bounds__(512, 1) k2_r32(K2Args a) {
               split(xb, make_float2(xm2.x, -xm2.y), cmul(rwh, __ldg(a.tw2Q + k2)), xk, xm);
               const unsigned k = P / 2 + P * k2, km = Nc - k;
               if (H) { xk = cmul(xk, __ldg(H + k)); xm = cmul(xm, __ldg(H + km)); }
-              if (a.z_tiled) {                       // row P/2: tile 0, side 1, g 0
-                Zblk[Q * G + zt_pos(k2, 0)] = xk;
-                Zblk[Q * G + zt_pos(Q - 1 - k2, 0)] = xm;
-              } else {
-                Zblk[k] = xk;
-                Zblk[km] = xm;
-              }
+              Zblk[k] = xk;
+              Zblk[km] = xm;
             }
           }
         }
@@ -684,22 +623,27 @@ __global__ void __launch_bounds__(512, 1) k2_r32(K2Args a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K2, two half-CTA groups (real input, tile-major Z).  Same arithmetic and the same Z' / H' layout as k2_r32, but
-// the 512 threads work as TWO independent 256-thread groups, each on four of the tile's eight mirror-row pairs,
-// synchronised by their own named barriers (bar.sync 1 + grp, 256) instead of CTA-wide barriers.  A tile has two
-// phases of about equal length that stress different units -- the row transforms (FP32 pipe + warp-local exchanges)
-// and the split / response / store phase (L1TEX + global stores).  One lock-stepped group of 16 warps runs them one
-// after the other; two groups drift apart and one's split phase runs under the other's transforms: K2 -5 %
-// (0.576 -> 0.548 ms per 37 parts, profiles/r2_*).  Measured and rejected: a token (bar.arrive / bar.sync pair) that
-// lets only one group transform at a time, +2.5 % -- eight warps alone do not fill the FP32 pipe.
+// K2, two half-CTA groups, in-place split, bulk stores (real input; the default for cfg1).  Same arithmetic as
+// k2_r32, but
+// * the 512 threads work as TWO independent 256-thread groups, each on four of the tile's eight mirror-row pairs,
+//   synchronised by their own named barriers (bar.sync 1 + grp, 256): the groups drift apart and one's split phase
+//   (L1TEX) runs under the other's row transforms (FP32 pipe);
+// * the shared-memory arrays use the dense, XOR-swizzled tile-image layout zi_pos() -- conflict free for the
+//   radix-32 scatter, the gather and the split walk -- and the split + response results are written back IN PLACE:
+//   X[k] of row `low` replaces element k2 of that row, X[N-k] replaces element Q-1-k2 of the mirror row;
+// * the finished 64 KiB image of a group then leaves the SM as cp.async.bulk (TMA) copies straight from shared
+//   memory.  Global stores through the LSU pass the L1TEX data pipe at 32 bytes per cycle -- 4096 cycles per tile,
+//   the longest single item of the old split phase -- the in-place 64-bit shared stores cost a quarter of that and
+//   the copy itself runs under the next tile's first butterflies.  K3 reads the image as it is (Z travels as the
+//   verbatim picture of K2's shared memory), the response is pre-permuted into the same order (k_tile_response).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void named_sync(unsigned id, unsigned n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 
 template <unsigned P>
 __global__ void __launch_bounds__(512, 1) k2_g2(K2Args a) {
-  extern __shared__ float4 smem4[];
+  extern __shared__ __align__(128) float4 smem4[];
   float2* sm2 = reinterpret_cast<float2*>(smem4);
-  constexpr unsigned Q = 1024, G = 8, RSQ = 1058u;
+  constexpr unsigned Q = 1024, G = 8;
   constexpr unsigned TPB = (P / 2) / G;
   __shared__ float2 s_rowtw[G + 1];
   const unsigned grp = threadIdx.x >> 8, tl = threadIdx.x & 255u;
@@ -707,15 +651,29 @@ __global__ void __launch_bounds__(512, 1) k2_g2(K2Args a) {
   const unsigned g = seq >> 1, which = seq & 1u;            // pair g (0..7; group grp owns 4 grp .. 4 grp + 3)
   const unsigned Nc = a.Nc;
   const unsigned ntiles = TPB * a.nblk;
+  float2* sgrp = sm2 + grp * 8192u;                         // this group's half of the tile image (64 KiB)
+  float2* s_tw2Q = sm2 + 16384u;                            // W_2Q^k2, k2 < Q, behind the image: read in the split walk
+  for (unsigned i = threadIdx.x; i < Q; i += 512u) s_tw2Q[i] = a.tw2Q[i];
+  __syncthreads();
+  const float2 one = make_float2(1.f, 0.f);
+  // zi_pos for this warp's row: element 32 j + r sits at s1[32 (r >> 2) + (jx ^ (r & 15))] (scatter of stage 0),
+  // element j + 32 e at s2[256 e + (jx ^ (e & 15))] (gather, natural order)
+  const unsigned jx = ((g & 3u) << 2) ^ (j & 15u);
+  float2* s1 = sgrp + which * 16u + 256u * j;
+  float2* s2 = sgrp + which * 16u + 32u * (j >> 2);
+  unsigned long long zpolicy;                               // Z is written once and read once: evict first
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(zpolicy));
 
   float2 v[32];
   auto issue_loads = [&](unsigned tt) {
     const unsigned tile = tt % TPB, blk = tt / TPB;
     const unsigned low = tile * G + g;
     const unsigned row = which ? (low == 0 ? P / 2 : P - low) : low;
-    const float2* src = a.A + uint64_t(blk) * Nc + uint64_t(row) * Q + j;
+    {
+      const float2* src = a.A + uint64_t(blk) * Nc + uint64_t(row) * Q + j;
 #pragma unroll
-    for (int e = 0; e < 32; e++) v[e] = B200_LDS1(src + 32 * e);
+      for (int e = 0; e < 32; e++) v[e] = B200_LDS1(src + 32 * e);
+    }
   };
 
   unsigned t = blockIdx.x;
@@ -726,42 +684,40 @@ __global__ void __launch_bounds__(512, 1) k2_g2(K2Args a) {
     // W_2N^row of this group's four pairs (+ row P/2, needed by pair 0 of tile 0 only: group 0)
     if (tl < 4) s_rowtw[4 * grp + tl] = big_twiddle<false>(a.b2lo, a.b2hi, tile * G + 4 * grp + tl);
     if (threadIdx.x == 4) s_rowtw[G] = big_twiddle<false>(a.b2lo, a.b2hi, P / 2);
-    float2* sq = sm2 + seq * RSQ;
     dft32<false>(v);
+    // the bulk copy of the previous tile has finished reading this group's image
+    if (tl == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    named_sync(1 + grp, 256);
 #pragma unroll
-    for (int r = 0; r < 32; r++) sq[33u * j + r] = v[r];
+    for (int r = 0; r < 32; r++) s1[32 * (r >> 2) + (jx ^ unsigned(r & 15))] = v[r];
     float2 ws[8], wm[4];
 #pragma unroll
-    for (int s1 = 1; s1 < 8; s1++) ws[s1] = __ldg(a.tw32 + (s1 - 1) * 32 + j);
+    for (int s1i = 1; s1i < 8; s1i++) ws[s1i] = __ldg(a.tw32 + (s1i - 1) * 32 + j);
 #pragma unroll
     for (int m = 1; m < 4; m++) wm[m] = __ldg(a.tw32 + (6 + m) * 32 + j);
     __syncwarp();
 #pragma unroll
-    for (int e = 0; e < 32; e++) v[e] = sq[j + 33u * e];
+    for (int e = 0; e < 32; e++) v[e] = s2[256 * e + (jx ^ unsigned(e & 15))];
 #pragma unroll
     for (int r = 1; r < 32; r++) {
-      const int s1 = r & 7, m = r >> 3;
-      const float2 w = m == 0 ? ws[s1] : (s1 == 0 ? wm[m] : cmul(wm[m], ws[s1]));
+      const int s1i = r & 7, m = r >> 3;
+      const float2 w = m == 0 ? ws[s1i] : (s1i == 0 ? wm[m] : cmul(wm[m], ws[s1i]));
       v[r] = cmul(v[r], w);
     }
     dft32<false>(v);
     __syncwarp();
 #pragma unroll
-    for (int e = 0; e < 32; e++) sq[j + 33u * e] = v[e];
+    for (int e = 0; e < 32; e++) s2[256 * e + (jx ^ unsigned(e & 15))] = v[e];
     named_sync(1 + grp, 256);
 
     if (t + gridDim.x < ntiles) issue_loads(t + gridDim.x);
 
     {
-      const float2* H = a.H ? a.H + uint64_t(ic) * Nc : nullptr;
-      float2* Zblk = a.Z + uint64_t(blk) * Nc;
-      // 64 kk x 4 pairs per group; lane = (kk & 3) + 4 g2l: 16 lanes cover 128 contiguous bytes of Z'
-      const unsigned g2 = 4u * grp + ((tl >> 2) & 3u);
-      const unsigned kk = (tl & 3u) + 4u * (tl >> 4);
-      const float2* SA = sm2 + (2 * g2) * RSQ;
-      const float2* SB = SA + RSQ;
-      auto p33 = [](unsigned i) { return i + (i >> 5); };
-      constexpr int SSTEP = 66;
+      // 64 kk x 4 pairs per group; a half warp = 4 consecutive k2 of 4 pairs = 16 distinct bank pairs
+      const unsigned gl = (tl >> 2) & 3u, q = tl & 3u, m0 = tl >> 4;     // k2 = q + 4 (m0 + 16 it)
+      const unsigned g2 = 4u * grp + gl, kk = q + 4u * m0;
+      const unsigned tile_off = tile * (2 * Q * G) + grp * 8192u;        // of this group's image inside the block
+      const float2* Hg = a.Ht ? a.Ht + uint64_t(ic) * Nc + tile_off : nullptr;
       auto split = [&](float2 zk, float2 zmc, float2 w, float2& xk, float2& xm) {
         const float2 e = make_float2(0.5f * (zk.x + zmc.x), 0.5f * (zk.y + zmc.y));
         const float2 d = make_float2(0.5f * (zk.x - zmc.x), 0.5f * (zk.y - zmc.y));
@@ -772,69 +728,85 @@ __global__ void __launch_bounds__(512, 1) k2_g2(K2Args a) {
       const unsigned low = tile * G + g2;
       if (low != 0) {
         const float2 rw = s_rowtw[g2];
-        const unsigned sa = p33(kk), sb = p33(Q - 1 - kk);
-        const float2* t2a = a.tw2Q + kk;
-        const float2* t2b = a.tw2Q + (Q - 1 - kk);
-        float2* zt = Zblk + uint64_t(tile) * (2 * Q * G);
-        float2* ZA = zt + zt_pos(kk, g2);
-        float2* ZBm = zt + Q * G + zt_pos(kk, g2);
-        float2* ZB = zt + zt_pos(Q - 1 - kk, g2);
-        float2* ZAm = zt + Q * G + zt_pos(Q - 1 - kk, g2);
-        constexpr int zstep = 64 * G;
-        const float2 *HA = nullptr, *HAm = nullptr, *HB = nullptr, *HBm = nullptr;
-        if (H) {
-          const float2* Htc = a.Ht + uint64_t(ic) * Nc;
-          HA = Htc + (ZA - Zblk); HAm = Htc + (ZAm - Zblk); HB = Htc + (ZB - Zblk); HBm = Htc + (ZBm - Zblk);
-        }
+        const float2* t2a = s_tw2Q + kk;
+        const float2* t2b = s_tw2Q + (Q - 1 - kk);
+        const unsigned lq = (gl << 2) | q;
+        // element k2 of rows a, b at sa, sa + 16; element Q-1-k2 (m -> 255 - m, q -> 3 - q: same swizzled low part)
+        auto slots = [&](int it, unsigned& sa, unsigned& sb) {
+          const unsigned m = m0 + 16u * it;
+          const unsigned lo = lq ^ zi_h(m);
+          sa = m * 32u + lo;
+          sb = (255u - m) * 32u + lo;
+        };
+        // the response values of iteration it + 1 are requested before iteration it is computed (L2 latency)
+        unsigned sa, sb;
+        slots(0, sa, sb);
+        float2 h0 = one, h1 = one, h2 = one, h3 = one;
+        if (Hg) { h0 = __ldg(Hg + sa); h1 = __ldg(Hg + sb + 16); h2 = __ldg(Hg + sb); h3 = __ldg(Hg + sa + 16); }
 #pragma unroll 2
         for (int it = 0; it < 8; it++) {
-          const float2 ua = SA[sa + SSTEP * it], ub = SB[sa + SSTEP * it];
-          const float2 va2 = SA[sb - SSTEP * it], vb2 = SB[sb - SSTEP * it];
-          const float2 wA = cmul(rw, __ldg(t2a + it * 64));
-          const float2 wB = cmul(rw, __ldg(t2b - it * 64));
+          unsigned san = 0, sbn = 0;
+          float2 n0 = one, n1 = one, n2 = one, n3 = one;
+          if (it < 7) {
+            slots(it + 1, san, sbn);
+            if (Hg) { n0 = __ldg(Hg + san); n1 = __ldg(Hg + sbn + 16); n2 = __ldg(Hg + sbn); n3 = __ldg(Hg + san + 16); }
+          }
+          const float2 ua = sgrp[sa], ub = sgrp[sa + 16];
+          const float2 va2 = sgrp[sb], vb2 = sgrp[sb + 16];
+          const float2 wA = cmul(rw, t2a[it * 64]);
+          const float2 wB = cmul(rw, t2b[-it * 64]);
           float2 xk, xm, yk, ym;
           split(ua, make_float2(vb2.x, -vb2.y), wA, xk, xm);
           split(va2, make_float2(ub.x, -ub.y), wB, yk, ym);
-          if (H) {
-            xk = cmul(xk, __ldg(HA + it * zstep));
-            xm = cmul(xm, __ldg(HAm - it * zstep));
-            yk = cmul(yk, __ldg(HB - it * zstep));
-            ym = cmul(ym, __ldg(HBm + it * zstep));
-          }
-          B200_ZST(ZA + it * zstep, xk);
-          B200_ZST(ZAm - it * zstep, xm);
-          B200_ZST(ZB - it * zstep, yk);
-          B200_ZST(ZBm + it * zstep, ym);
+          if (Hg) { xk = cmul(xk, h0); xm = cmul(xm, h1); yk = cmul(yk, h2); ym = cmul(ym, h3); }
+          sgrp[sa] = xk;            // X[k],   k = low + P k2        (row low,     element k2)
+          sgrp[sb + 16] = xm;       // X[N-k]                        (row P - low, element Q-1-k2)
+          sgrp[sb] = yk;            // X[k'],  k' = low + P (Q-1-k2) (row low,     element Q-1-k2)
+          sgrp[sa + 16] = ym;       // X[N-k']                       (row P - low, element k2)
+          sa = san; sb = sbn; h0 = n0; h1 = n1; h2 = n2; h3 = n3;
         }
       } else {
-        // rows 0 (array a) and P/2 (array b) mirror onto themselves
+        // rows 0 (array a) and P/2 (array b) mirror onto themselves (pair 0 of tile 0: group 0, gl = 0)
         const float2 rwh = s_rowtw[G];
+        auto pa = [](unsigned k2) { return (k2 >> 2) * 32u + ((k2 & 3u) ^ zi_h(k2 >> 2)); };
         for (unsigned it = 0; it < 16; it++) {
           const unsigned k2 = kk + it * 64;
           if (k2 <= Q / 2) {
             const unsigned km2 = (Q - k2) % Q;
-            const float2 xa = SA[p33(k2)], xm2 = SA[p33(km2)];
+            const unsigned s0 = pa(k2), sm_ = pa(km2);
+            const float2 xa = sgrp[s0], xm2 = sgrp[sm_];
             float2 xk, xm;
-            split(xa, make_float2(xm2.x, -xm2.y), __ldg(a.tw2Q + k2), xk, xm);
-            const unsigned k = P * k2, km = (Nc - k) & (Nc - 1);
-            if (H) { xk = cmul(xk, __ldg(H + k)); xm = cmul(xm, __ldg(H + km)); }
-            Zblk[zt_pos(k2, 0)] = xk;
-            if (km2 != k2) Zblk[zt_pos(km2, 0)] = xm;
+            split(xa, make_float2(xm2.x, -xm2.y), s_tw2Q[k2], xk, xm);
+            if (Hg) { xk = cmul(xk, __ldg(Hg + s0)); xm = cmul(xm, __ldg(Hg + sm_)); }
+            sgrp[s0] = xk;
+            if (km2 != k2) sgrp[sm_] = xm;
           }
           if (k2 < Q / 2) {
-            const float2 xb = SB[p33(k2)], xm2 = SB[p33(Q - 1 - k2)];
+            const unsigned s0 = pa(k2) + 16u, sm_ = pa(Q - 1 - k2) + 16u;
+            const float2 xb = sgrp[s0], xm2 = sgrp[sm_];
             float2 xk, xm;
-            split(xb, make_float2(xm2.x, -xm2.y), cmul(rwh, __ldg(a.tw2Q + k2)), xk, xm);
-            const unsigned k = P / 2 + P * k2, km = Nc - k;
-            if (H) { xk = cmul(xk, __ldg(H + k)); xm = cmul(xm, __ldg(H + km)); }
-            Zblk[Q * G + zt_pos(k2, 0)] = xk;
-            Zblk[Q * G + zt_pos(Q - 1 - k2, 0)] = xm;
+            split(xb, make_float2(xm2.x, -xm2.y), cmul(rwh, s_tw2Q[k2]), xk, xm);
+            if (Hg) { xk = cmul(xk, __ldg(Hg + s0)); xm = cmul(xm, __ldg(Hg + sm_)); }
+            sgrp[s0] = xk;
+            sgrp[sm_] = xm;
           }
         }
       }
+      // generic-proxy writes -> visible to the async proxy, then one thread hands the image to the TMA unit
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      named_sync(1 + grp, 256);
+      if (tl == 0) {
+        float2* dst = a.Z + uint64_t(blk) * Nc + tile_off;
+        const unsigned src = (unsigned)__cvta_generic_to_shared(sgrp);
+#pragma unroll
+        for (unsigned c = 0; c < 4; c++)
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                       :: "l"(dst + c * 2048u), "r"(src + c * 16384u), "r"(16384u), "l"(zpolicy) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
     }
-    named_sync(1 + grp, 256);     // this group's split readers are done before its next scatter
   }
+  if (tl == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -850,7 +822,7 @@ struct K3Args {
   uint64_t part0;
   FbSink sink;
   unsigned dbg;
-  int z_tiled;             // Z is in K2's tile-major order (see k2_r32)
+  int z_tiled;             // Z is the tile image of k2_g2 (zi_pos)
 };
 
 // STATE >= 0: detection state fixed at compile time (no per-sample branches); -1: run-time state
@@ -871,18 +843,10 @@ __device__ __forceinline__ void detect4(int state, float2 p, float2 q, float* r)
 // stage runs as ONE 32-point butterfly per thread (threads 0-255 polarisation p, 256-511 polarisation q),
 // which removes one of the three shared-memory exchanges and two of the six barriers.  The exchanges are
 // 64-bit (one float2 array per polarisation, one pad slot after every 32: stride 33 is conflict free).
-//
-// ZTMA (R32 with the tile-major Z only): the side-0 half of the next tile (rows < P/2: 64 KiB) is fetched by the
-// TMA unit into a landing zone behind the exchange buffer WHILE the current tile is transformed -- a 3-D box of
-// the tensor [tile][side][8192 float2] -- and only the side-1 half still travels through registers during the fold
-// phase.  With one 128 KiB tile filling the register file, the register prefetch alone confines all HBM reads of
-// the kernel to the short fold phase of 148 SMs running in lock step.
-template <unsigned F, int EPI, int STATE, bool R32 = false, bool ZTMA = false>
-__global__ void __launch_bounds__(512, 1) k3_c2(K3Args a, const __grid_constant__ CUtensorMap tmapZ) {
+template <unsigned F, int EPI, int STATE, bool R32 = false>
+__global__ void __launch_bounds__(512, 1) k3_c2(K3Args a) {
   static_assert(!R32 || F == 8192, "the 32.16.16 plan is built for 8192 points");
-  static_assert(!ZTMA || R32, "the TMA landing zone belongs to the 32.16.16 plan");
   extern __shared__ __align__(128) float4 smem4[];
-  __shared__ __align__(8) unsigned long long s_mbar;
   constexpr unsigned T = F / 16;
   constexpr unsigned CB = 512 / T;                     // channels per CTA
   constexpr unsigned RS = c2::pair_slots<F>();
@@ -904,24 +868,35 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a, const __grid_constant_
       // stage-0 ownership: thread (pol, j0) holds x_pol[j0 + 256 e], e < 32, in vp[0..15], vq[0..15]
       const unsigned pol = threadIdx.x >> 8, j0 = threadIdx.x & 255u;
       if (a.z_tiled) {
-        // bin f = j0 + 256 e of channel csub is element k2 = 4 csub + (e >> 3) of row r = j0 + 256 (e & 7):
-        // the four k2 of a row are one 32-byte group of the tiled layout -> one 256-bit load
-        const float2* zb = a.Z + (blk + pol) * a.Nc + 32u * csub;     // zt_pos(4 csub, 0)
+        // bin f = j0 + 256 e of channel csub is element k2 = 4 csub + (e >> 3) of row r = j0 + 256 (e & 7): the four
+        // k2 of a row are one aligned 32-byte group of the tile image (zi_pos) -> one 256-bit load; inside the group
+        // they are permuted by XOR with hq = zi_h(csub) & 3, the same for every thread of the tile (one channel)
+        const unsigned h = zi_h(csub), hq = h & 3u;
+        const float2* zb = a.Z + (blk + pol) * a.Nc + 32u * csub;
+        auto load_perm = [&](auto HQ) {
+          constexpr unsigned hqc = decltype(HQ)::value;
 #pragma unroll
-        for (int i = ZTMA ? 4 : 0; i < 8; i++) {
-          const unsigned r = j0 + 256u * i;
-          unsigned tile, side, g8;
-          if (r < 1024u) { tile = r >> 3; side = 0; g8 = r & 7u; }
-          else if (r == 1024u) { tile = 0; side = 1; g8 = 0; }
-          else { const unsigned m = 2048u - r; tile = m >> 3; side = 1; g8 = m & 7u; }
-          const float2* p = zb + (uint64_t(tile) * 2 + side) * 8192u + 4u * g8;
-          float2 x[4];
-          ldg_nc_f2x4(p, x[0], x[1], x[2], x[3]);
+          for (int i = 0; i < 8; i++) {
+            const unsigned r = j0 + 256u * i;
+            unsigned tile, which, g8;
+            if (r < 1024u) { tile = r >> 3; which = 0; g8 = r & 7u; }
+            else if (r == 1024u) { tile = 0; which = 1; g8 = 0; }
+            else { const unsigned m = 2048u - r; tile = m >> 3; which = 1; g8 = m & 7u; }
+            const float2* p = zb + tile * 16384u + (g8 >> 2) * 8192u + which * 16u + (((g8 & 3u) << 2) ^ (h & 12u));
+            float2 x[4];
+            ldg_nc_f2x4(p, x[0], x[1], x[2], x[3]);
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const int e = i + 8 * q;
-            if (e < 16) vp[e] = x[q]; else vq[e - 16] = x[q];
+            for (int q = 0; q < 4; q++) {
+              const int e = i + 8 * q;                       // element k2 = 4 csub + q sits at slot q ^ hq
+              if (e < 16) vp[e] = x[q ^ hqc]; else vq[e - 16] = x[q ^ hqc];
+            }
           }
+        };
+        switch (hq) {
+          case 0: load_perm(std::integral_constant<unsigned, 0>()); break;
+          case 1: load_perm(std::integral_constant<unsigned, 1>()); break;
+          case 2: load_perm(std::integral_constant<unsigned, 2>()); break;
+          default: load_perm(std::integral_constant<unsigned, 3>()); break;
         }
         return;
       }
@@ -943,33 +918,6 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a, const __grid_constant_
     }
   };
 
-  // landing zone of the TMA half: [pol][tile 0..127][8 rows][4 k2] float2 = 2 x 32 KiB behind the exchange buffer
-  constexpr unsigned LAND_OFF = RS * CB * sizeof(float4);
-  static_assert(!ZTMA || LAND_OFF % 128 == 0, "TMA destination alignment");
-  unsigned char* land = reinterpret_cast<unsigned char*>(smem4) + LAND_OFF;
-  const unsigned mbar = (unsigned)__cvta_generic_to_shared(&s_mbar);
-  unsigned mbar_parity = 0;
-  auto issue_tma = [&](unsigned tt) {       // one thread: both polarisations of tile tt, side 0
-    const unsigned ch = tt % tiles_per_part, partl = tt / tiles_per_part;
-    const unsigned ic = ch / a.C, csub = ch % a.C;
-    const unsigned blk = (partl * a.nchan_in + ic) * 2;
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(land);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(65536u) : "memory");
-#pragma unroll
-    for (unsigned pol = 0; pol < 2; pol++)
-      asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                   :: "r"(dst + pol * 32768u), "l"(&tmapZ), "r"(int(csub * 64u)), "r"(0), "r"(int((blk + pol) * 128u)), "r"(mbar)
-                   : "memory");
-  };
-  if (ZTMA) {
-    if (threadIdx.x == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar) : "memory");
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && blockIdx.x < ntiles) issue_tma(blockIdx.x);
-  }
-
   unsigned t = blockIdx.x;
   if (t < ntiles) issue_loads(t);
   for (; t < ntiles; t += gridDim.x) {
@@ -986,27 +934,6 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a, const __grid_constant_
         float2 u[32];
 #pragma unroll
         for (int e = 0; e < 16; e++) { u[e] = vp[e]; u[16 + e] = vq[e]; }
-        if (ZTMA) {
-          // wait for the TMA half of this tile, then rows j0 + 256 i, i < 4 (tile = (j0 >> 3) + 32 i, g = j0 & 7):
-          // 32 bytes per row, read as two 16-byte halves in a lane-dependent order so that a quarter warp covers
-          // all banks (lanes are 32 bytes apart)
-          asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-                       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-                       "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" :: "r"(mbar), "r"(mbar_parity) : "memory");
-          mbar_parity ^= 1u;
-          const unsigned g8 = j0 & 7u, hsel = (g8 >> 2) & 1u;
-          const unsigned char* lp = land + pol * 32768u + (j0 >> 3) * 256u + g8 * 32u;
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const float4 fa = *reinterpret_cast<const float4*>(lp + i * 8192 + hsel * 16u);
-            const float4 fb = *reinterpret_cast<const float4*>(lp + i * 8192 + (hsel ^ 1u) * 16u);
-            const float4 lo = hsel ? fb : fa, hi = hsel ? fa : fb;
-            u[i] = make_float2(lo.x, lo.y);
-            u[i + 8] = make_float2(lo.z, lo.w);
-            u[i + 16] = make_float2(hi.x, hi.y);
-            u[i + 24] = make_float2(hi.z, hi.w);
-          }
-        }
         dft32<true>(u);
         float2* dst = (pol ? arrQ : arrP) + 33u * j0;           // pad33(32 j0 + r) = 33 j0 + r
 #pragma unroll
@@ -1017,8 +944,6 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a, const __grid_constant_
 #pragma unroll
       for (int r = 1; r < 16; r++) w[r - 1] = tw_get<true>(a.tw32, (unsigned)(r - 1) * 32u + k1);
       __syncthreads();
-      // every thread has read the landing zone: the TMA unit may refill it with the next tile's half
-      if (ZTMA && threadIdx.x == 0 && tn < ntiles) issue_tma(tn);
       const unsigned pj = j + (j >> 5);                           // pad33(j + 512 e) = pj + 528 e
 #pragma unroll
       for (int e = 0; e < 16; e++) { vp[e] = arrP[pj + 528u * e]; vq[e] = arrQ[pj + 528u * e]; }
@@ -1158,17 +1083,17 @@ __global__ void __launch_bounds__(512, 1) k3_c2(K3Args a, const __grid_constant_
   }
 }
 
-// Response in the tile-major order of Z: bin k = r + P k2 (row r, element k2) goes where k2_r32 stores that bin.
+// Response in the tile-image order of Z: bin k = r + P k2 (row r, element k2) goes where k2_g2 leaves that bin.
 __global__ void k_tile_response(const float2* __restrict__ H, float2* __restrict__ Ht, unsigned nchan_in) {
   constexpr unsigned P = 2048, Q = 1024, Nc = P * Q;
   const uint64_t n = uint64_t(nchan_in) * Nc;
   for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
     const unsigned k = unsigned(i % Nc), r = k % P, k2 = k / P;
-    unsigned tile, side, g;
-    if (r < P / 2) { tile = r >> 3; side = 0; g = r & 7u; }
-    else if (r == P / 2) { tile = 0; side = 1; g = 0; }
-    else { const unsigned m = P - r; tile = m >> 3; side = 1; g = m & 7u; }
-    Ht[(i - k) + (uint64_t(tile) * 2 + side) * (Q * 8) + zt_pos(k2, g)] = H[i];
+    unsigned tile, which, g;
+    if (r < P / 2) { tile = r >> 3; which = 0; g = r & 7u; }
+    else if (r == P / 2) { tile = 0; which = 1; g = 0; }
+    else { const unsigned m = P - r; tile = m >> 3; which = 1; g = m & 7u; }
+    Ht[(i - k) + uint64_t(tile) * (Q * 16) + zi_pos(g, which, k2)] = H[i];
   }
 }
 
@@ -1201,9 +1126,9 @@ static constexpr unsigned FP_P = 2048, FP_Q = 1024;
 static constexpr int FP_NP = B200_K1_NP;
 static size_t k1_smem() { return size_t(FP_NP) * (c2::pair_slots<FP_P>() + 8 / FP_NP) * sizeof(float4); }
 static size_t k2_smem() { return size_t(512 / (FP_Q / 16)) * (c2::pair_slots<FP_Q>() | 1u) * sizeof(float4); }
-static size_t k2r32_smem() { return size_t(16) * 1058 * sizeof(float2); }
+static size_t k2r32_smem() { return size_t(16) * 1057 * sizeof(float2); }
+static size_t k2g2_smem() { return size_t(17) * 1024 * sizeof(float2); }   // the tile image, dense, + W_2Q^k2
 template <unsigned F> static size_t k3_smem() { return size_t(512 / (F / 16)) * c2::pair_slots<F>() * sizeof(float4); }
-static size_t k3_tma_smem() { return k3_smem<8192>() + 65536; }   // + landing zone of the TMA half tile
 
 static bool k3_r32_enabled() {
   static const bool on = tune_flag("B200_K3_R32", true);
@@ -1234,10 +1159,6 @@ template <unsigned F> static int k3_init(b200_fb_plan* pl) {
     if ((rc = opt_in_smem(k3_c2<8192, EPI_DETECT, -1, true>, k3_smem<8192>())) != B200_OK) return rc;
     if ((rc = opt_in_smem(k3_c2<8192, EPI_FOLD, -1, true>, k3_smem<8192>())) != B200_OK) return rc;
     if ((rc = opt_in_smem(k3_c2<8192, EPI_FOLD, B200_COHERENCE, true>, k3_smem<8192>())) != B200_OK) return rc;
-    if ((rc = opt_in_smem(k3_c2<8192, EPI_VOLT, -1, true, true>, k3_tma_smem())) != B200_OK) return rc;
-    if ((rc = opt_in_smem(k3_c2<8192, EPI_DETECT, -1, true, true>, k3_tma_smem())) != B200_OK) return rc;
-    if ((rc = opt_in_smem(k3_c2<8192, EPI_FOLD, -1, true, true>, k3_tma_smem())) != B200_OK) return rc;
-    if ((rc = opt_in_smem(k3_c2<8192, EPI_FOLD, B200_COHERENCE, true, true>, k3_tma_smem())) != B200_OK) return rc;
   }
   if ((rc = opt_in_smem(k3_c2<F, EPI_VOLT, -1>, k3_smem<F>())) != B200_OK) return rc;
   if ((rc = opt_in_smem(k3_c2<F, EPI_DETECT, -1>, k3_smem<F>())) != B200_OK) return rc;
@@ -1252,44 +1173,31 @@ template <unsigned F> static void k3_launch(b200_fb_plan* pl, const K3Args& a, c
   constexpr unsigned CB = 512 / (F / 16);
   const unsigned ntiles = pl->nchan_out / CB * nb;
   dim3 grid(ntiles < (unsigned)ctx->sm_count ? ntiles : (unsigned)ctx->sm_count);
-  CUtensorMap tm;
-  memset(&tm, 0, sizeof(tm));
   if constexpr (F == 8192) {
-    if (a.z_tiled && pl->tmapZ) {
-      tm = *static_cast<CUtensorMap*>(pl->tmapZ);
-      const size_t sm = k3_tma_smem();
-      if (sk.kind == EPI_VOLT) k3_c2<8192, EPI_VOLT, -1, true, true><<<grid, 512, sm, ctx->stream>>>(a, tm);
-      else if (sk.kind == EPI_DETECT) k3_c2<8192, EPI_DETECT, -1, true, true><<<grid, 512, sm, ctx->stream>>>(a, tm);
-      else if (sk.state == B200_COHERENCE) k3_c2<8192, EPI_FOLD, B200_COHERENCE, true, true><<<grid, 512, sm, ctx->stream>>>(a, tm);
-      else k3_c2<8192, EPI_FOLD, -1, true, true><<<grid, 512, sm, ctx->stream>>>(a, tm);
-      return;
-    }
     if (k3_r32_enabled() && pl->c2F32) {
-      if (sk.kind == EPI_VOLT) k3_c2<8192, EPI_VOLT, -1, true><<<grid, 512, k3_smem<8192>(), ctx->stream>>>(a, tm);
-      else if (sk.kind == EPI_DETECT) k3_c2<8192, EPI_DETECT, -1, true><<<grid, 512, k3_smem<8192>(), ctx->stream>>>(a, tm);
-      else if (sk.state == B200_COHERENCE) k3_c2<8192, EPI_FOLD, B200_COHERENCE, true><<<grid, 512, k3_smem<8192>(), ctx->stream>>>(a, tm);
-      else k3_c2<8192, EPI_FOLD, -1, true><<<grid, 512, k3_smem<8192>(), ctx->stream>>>(a, tm);
+      if (sk.kind == EPI_VOLT) k3_c2<8192, EPI_VOLT, -1, true><<<grid, 512, k3_smem<8192>(), ctx->stream>>>(a);
+      else if (sk.kind == EPI_DETECT) k3_c2<8192, EPI_DETECT, -1, true><<<grid, 512, k3_smem<8192>(), ctx->stream>>>(a);
+      else if (sk.state == B200_COHERENCE) k3_c2<8192, EPI_FOLD, B200_COHERENCE, true><<<grid, 512, k3_smem<8192>(), ctx->stream>>>(a);
+      else k3_c2<8192, EPI_FOLD, -1, true><<<grid, 512, k3_smem<8192>(), ctx->stream>>>(a);
       return;
     }
   }
-  if (sk.kind == EPI_VOLT) k3_c2<F, EPI_VOLT, -1><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a, tm);
-  else if (sk.kind == EPI_DETECT) k3_c2<F, EPI_DETECT, -1><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a, tm);
-  else if (sk.state == B200_COHERENCE) k3_c2<F, EPI_FOLD, B200_COHERENCE><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a, tm);
-  else k3_c2<F, EPI_FOLD, -1><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a, tm);
+  if (sk.kind == EPI_VOLT) k3_c2<F, EPI_VOLT, -1><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a);
+  else if (sk.kind == EPI_DETECT) k3_c2<F, EPI_DETECT, -1><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a);
+  else if (sk.state == B200_COHERENCE) k3_c2<F, EPI_FOLD, B200_COHERENCE><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a);
+  else k3_c2<F, EPI_FOLD, -1><<<grid, 512, k3_smem<F>(), ctx->stream>>>(a);
 }
 
-// Z travels from K2 to K3 in K2's tile-major order when both ends are the kernels that implement it:
-// k2_r32 with the real-input split and the 32.16.16 K3, i.e. P = 2048, Q = 1024, freq_res = 8192 (cfg1).
+// Z travels from K2 to K3 as the image of K2's shared memory (zi_pos) when both ends are the kernels that implement
+// it: k2_g2 (real-input split) and the 32.16.16 K3, i.e. P = 2048, Q = 1024, freq_res = 8192 (cfg1).
 static bool z_tiled(const b200_fb_plan* pl) {
   static const bool want = tune_flag("B200_Z_TILED", true);
   static const bool k2r32 = tune_flag("B200_K2_R32", true);
-  return want && k2r32 && k3_r32_enabled() && pl->fast_k2 && pl->fast_k3 && pl->c2Q32 && pl->c2F32 &&
+  static const bool g2 = tune_flag("B200_K2_G2", true);
+  return want && k2r32 && g2 && k3_r32_enabled() && pl->fast_k2 && pl->fast_k3 && pl->c2Q32 && pl->c2F32 &&
          pl->desc.input_real && pl->P == 2048 && pl->Q == 1024 && pl->F == 8192;
 }
 
-static bool rows_fit_tma(const b200_fb_plan* pl);
-static int make_a_tensor_map(b200_fb_plan* pl, CUtensorMap* tm);
-static int make_z_tensor_map(b200_fb_plan* pl, CUtensorMap* tm);
 
 int fast_plan_init(b200_fb_plan* pl) {
   pl->fast_k1 = pl->fast_k2 = pl->fast_k3 = false;
@@ -1297,31 +1205,15 @@ int fast_plan_init(b200_fb_plan* pl) {
   pl->c2F32 = nullptr;
   pl->c2Q32 = nullptr;
   pl->d_response_tiled = nullptr;
-  pl->tmapA = nullptr;
-  pl->tmapZ = nullptr;
-  pl->k1_tma = false;
   if (!fast_enabled() || pl->conv_path) return B200_OK;
   int rc = B200_OK;
   if (pl->P == FP_P && pl->Q >= 2 * FP_NP && pl->Q % (2 * FP_NP) == 0) {
     if ((rc = make_c2_table<FP_P>(&pl->c2P)) != B200_OK) return rc;
-    if ((rc = opt_in_smem(k1_c2<SRC_F32, FP_P, FP_NP, false>, k1_smem())) != B200_OK) return rc;
-    if ((rc = opt_in_smem(k1_c2<SRC_CASPSR8, FP_P, FP_NP, false>, k1_smem())) != B200_OK) return rc;
-    if ((rc = opt_in_smem(k1_c2<SRC_F32, FP_P, FP_NP, false, FP_Q>, k1_smem())) != B200_OK) return rc;
-    if ((rc = opt_in_smem(k1_c2<SRC_CASPSR8, FP_P, FP_NP, false, FP_Q>, k1_smem())) != B200_OK) return rc;
-    if ((rc = opt_in_smem(k1_c2<SRC_F32, FP_P, FP_NP, true>, k1_smem())) != B200_OK) return rc;
-    if ((rc = opt_in_smem(k1_c2<SRC_CASPSR8, FP_P, FP_NP, true>, k1_smem())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k1_c2<SRC_F32, FP_P, FP_NP>, k1_smem())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k1_c2<SRC_CASPSR8, FP_P, FP_NP>, k1_smem())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k1_c2<SRC_F32, FP_P, FP_NP, FP_Q>, k1_smem())) != B200_OK) return rc;
+    if ((rc = opt_in_smem(k1_c2<SRC_CASPSR8, FP_P, FP_NP, FP_Q>, k1_smem())) != B200_OK) return rc;
     pl->fast_k1 = true;
-    // TMA tensor store of the K1 tile: correct (parity-tested) but measured 3.6 % SLOWER than plain 128-bit
-    // global stores on B200 (0.278 vs 0.269 ms per 16 parts: two more CTA barriers, one issuing thread), so
-    // it is opt-in (B200_K1_TMA=1) until tiles shrink enough to double-buffer the staging area.
-    static const bool want_tma = tune_flag("B200_K1_TMA", false);
-    pl->k1_tma = false;
-    if (want_tma && rows_fit_tma(pl)) {
-      pl->tmapA = new CUtensorMap();
-      const int trc = make_a_tensor_map(pl, static_cast<CUtensorMap*>(pl->tmapA));
-      if (trc == B200_OK) pl->k1_tma = true;
-      if (tune_flag("B200_DEBUG", false)) fprintf(stderr, "[b200] K1 TMA store: tensor map rc=%d enabled=%d\n", trc, int(pl->k1_tma));
-    }
   }
   if (pl->Q == FP_Q && pl->P == FP_P) {
     if ((rc = make_c2_table<FP_Q>(&pl->c2Q)) != B200_OK) return rc;
@@ -1343,7 +1235,7 @@ int fast_plan_init(b200_fb_plan* pl) {
       B200_CUDA(cudaMemcpy(pl->c2Q32, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice));
       if ((rc = opt_in_smem(k2_r32<FP_P, true>, k2r32_smem())) != B200_OK) return rc;
       if ((rc = opt_in_smem(k2_r32<FP_P, false>, k2r32_smem())) != B200_OK) return rc;
-      if ((rc = opt_in_smem(k2_g2<FP_P>, k2r32_smem())) != B200_OK) return rc;
+      if ((rc = opt_in_smem(k2_g2<FP_P>, k2g2_smem())) != B200_OK) return rc;
     }
     pl->fast_k2 = true;
   }
@@ -1360,16 +1252,6 @@ int fast_plan_init(b200_fb_plan* pl) {
     }
     if (rc != B200_OK) return rc;
   }
-  // K3's TMA half-tile loads from the tile-major Z: correct (parity-tested) but measured no faster than the
-  // all-register prefetch on B200 (0.248 vs 0.246 ms per 16 parts), so it is opt-in (B200_K3_TMA=1)
-  static const bool want_ztma = tune_flag("B200_K3_TMA", false);
-  if (z_tiled(pl) && want_ztma) {
-    pl->tmapZ = new CUtensorMap();
-    if (make_z_tensor_map(pl, static_cast<CUtensorMap*>(pl->tmapZ)) != B200_OK) {
-      delete static_cast<CUtensorMap*>(pl->tmapZ);
-      pl->tmapZ = nullptr;
-    }
-  }
   if (z_tiled(pl) && pl->d_response) {
     const uint64_t n = uint64_t(pl->desc.input_nchan) * pl->Nc;
     B200_CUDA(cudaMalloc(&pl->d_response_tiled, n * sizeof(float2)));
@@ -1383,10 +1265,6 @@ int fast_plan_init(b200_fb_plan* pl) {
 void fast_plan_free(b200_fb_plan* pl) {
   if (pl->d_response_tiled) cudaFree(pl->d_response_tiled);
   pl->d_response_tiled = nullptr;
-  if (pl->tmapA) delete static_cast<CUtensorMap*>(pl->tmapA);
-  pl->tmapA = nullptr;
-  if (pl->tmapZ) delete static_cast<CUtensorMap*>(pl->tmapZ);
-  pl->tmapZ = nullptr;
   if (pl->c2P) cudaFree(pl->c2P);
   if (pl->c2Q) cudaFree(pl->c2Q);
   if (pl->c2F) cudaFree(pl->c2F);
@@ -1395,60 +1273,6 @@ void fast_plan_free(b200_fb_plan* pl) {
   pl->c2Q32 = nullptr;
   pl->c2P = pl->c2Q = pl->c2F = nullptr;
   pl->c2F32 = nullptr;
-}
-
-static bool rows_fit_tma(const b200_fb_plan* pl) {
-  return uint64_t(pl->batch) * pl->desc.input_nchan * pl->desc.npol * pl->P < (1ull << 31) && pl->P % 256 == 0;
-}
-
-// Tensor map of the A buffer seen as a 2-D float array [batch*nblk*P rows][2*Q floats], box = 256 rows x
-// 2*NP columns (16*NP bytes).  cuTensorMapEncodeTiled is fetched through the runtime so that the library
-// does not link against libcuda.
-static int make_a_tensor_map(b200_fb_plan* pl, CUtensorMap* tm) {
-  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
-      qres != cudaDriverEntryPointSuccess) {
-    cudaGetLastError();
-    return B200_ERR_UNSUPPORTED;
-  }
-  const uint64_t rows = uint64_t(pl->batch) * pl->desc.input_nchan * pl->desc.npol * pl->P;
-  const cuuint64_t gdim[2] = {cuuint64_t(pl->Q) * 2, rows};
-  const cuuint64_t gstride[1] = {cuuint64_t(pl->Q) * 2 * sizeof(float)};
-  const cuuint32_t box[2] = {4u * FP_NP, 256u};
-  const cuuint32_t estride[2] = {1u, 1u};
-  CUresult r = reinterpret_cast<encode_fn>(fn)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, pl->scratchA, gdim, gstride, box, estride,
-                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? B200_OK : B200_ERR_UNSUPPORTED;
-}
-
-// Tensor map of the tile-major Z scratch: [blocks * 128 tiles][2 sides][8192 float2] seen as floats; box = one
-// 256-byte k2 group of 128 tiles of one side (32 KiB): the side-0 half of one polarisation of a K3 tile.
-static int make_z_tensor_map(b200_fb_plan* pl, CUtensorMap* tm) {
-  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
-      qres != cudaDriverEntryPointSuccess) {
-    cudaGetLastError();
-    return B200_ERR_UNSUPPORTED;
-  }
-  const uint64_t nblk = uint64_t(pl->batch) * pl->desc.input_nchan * pl->desc.npol;
-  if (nblk * 128 >= (1ull << 31)) return B200_ERR_UNSUPPORTED;
-  const cuuint64_t gdim[3] = {16384, 2, nblk * 128};
-  const cuuint64_t gstride[2] = {16384 * sizeof(float), 2 * 16384 * sizeof(float)};
-  const cuuint32_t box[3] = {64u, 1u, 128u};
-  const cuuint32_t estride[3] = {1u, 1u, 1u};
-  CUresult r = reinterpret_cast<encode_fn>(fn)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, pl->scratchZ, gdim, gstride, box, estride,
-                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? B200_OK : B200_ERR_UNSUPPORTED;
 }
 
 static unsigned persistent_grid(Context* ctx, unsigned ntiles) {
@@ -1470,23 +1294,16 @@ int fast_k1(b200_fb_plan* pl, const FbSource& src, uint64_t part0, unsigned nb) 
   a.skew_ns = cta_per_sm > 1 ? (unsigned)tune_int("B200_K1_SKEW", 3000) : 0u;
   dim3 grid(std::min(ntiles, cta_per_sm * (unsigned)ctx->sm_count));
   dim3 block(FP_NP * (FP_P / 16));
-  a.use_tma = pl->k1_tma ? 1 : 0;
   static const bool l2pf = tune_flag("B200_K1_L2PF", true);
   a.l2_prefetch = l2pf ? 1 : 0;
   a.overlap = pl->nsamp_overlap;
-  CUtensorMap tm;
-  if (pl->k1_tma) tm = *static_cast<CUtensorMap*>(pl->tmapA);
-  else memset(&tm, 0, sizeof(tm));
   LaunchScope ls(ctx, KC_COLS_FWD);
-  if (pl->k1_tma) {
-    if (src.kind == SRC_F32) k1_c2<SRC_F32, FP_P, FP_NP, true><<<grid, block, k1_smem(), ctx->stream>>>(a, tm);
-    else k1_c2<SRC_CASPSR8, FP_P, FP_NP, true><<<grid, block, k1_smem(), ctx->stream>>>(a, tm);
-  } else {
+  {
     if (pl->Q == FP_Q) {
-      if (src.kind == SRC_F32) k1_c2<SRC_F32, FP_P, FP_NP, false, FP_Q><<<grid, block, k1_smem(), ctx->stream>>>(a, tm);
-      else k1_c2<SRC_CASPSR8, FP_P, FP_NP, false, FP_Q><<<grid, block, k1_smem(), ctx->stream>>>(a, tm);
-    } else if (src.kind == SRC_F32) k1_c2<SRC_F32, FP_P, FP_NP, false><<<grid, block, k1_smem(), ctx->stream>>>(a, tm);
-    else k1_c2<SRC_CASPSR8, FP_P, FP_NP, false><<<grid, block, k1_smem(), ctx->stream>>>(a, tm);
+      if (src.kind == SRC_F32) k1_c2<SRC_F32, FP_P, FP_NP, FP_Q><<<grid, block, k1_smem(), ctx->stream>>>(a);
+      else k1_c2<SRC_CASPSR8, FP_P, FP_NP, FP_Q><<<grid, block, k1_smem(), ctx->stream>>>(a);
+    } else if (src.kind == SRC_F32) k1_c2<SRC_F32, FP_P, FP_NP><<<grid, block, k1_smem(), ctx->stream>>>(a);
+    else k1_c2<SRC_CASPSR8, FP_P, FP_NP><<<grid, block, k1_smem(), ctx->stream>>>(a);
   }
   return B200_OK;
 }
@@ -1510,9 +1327,8 @@ int fast_k2(b200_fb_plan* pl, unsigned nb) {
 #ifdef B200_ABLATION
   if (tune_flag("B200_K2_NOH", false)) a.H = nullptr;   // timing experiment only (cost of the response stream): results are wrong
 #endif
-  static const bool g2 = tune_flag("B200_K2_G2", true);
-  if (r32 && pl->c2Q32 && split && a.z_tiled && g2) {
-    k2_g2<FP_P><<<grid, 512, k2r32_smem(), ctx->stream>>>(a);
+  if (r32 && pl->c2Q32 && split && a.z_tiled) {
+    k2_g2<FP_P><<<grid, 512, k2g2_smem(), ctx->stream>>>(a);
     return B200_OK;
   }
   if (r32 && pl->c2Q32) {

@@ -14,8 +14,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DEVLIB = os.path.join(ROOT, "dspsr_b200", "libb200dsp_dev.so")
 
 VARIANTS = {
-    "k3_tma_half_tile": {"B200_K3_TMA": "1"},
-    "k1_tma_store": {"B200_K1_TMA": "1"},
     "z_natural_order": {"B200_Z_TILED": "0"},
     "k2_single_group": {"B200_K2_G2": "0"},
     "first_generation_plans": {"B200_K2_R32": "0", "B200_K3_R32": "0"},

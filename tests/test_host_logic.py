@@ -304,29 +304,62 @@ def test_bind_cpu_affinity_is_harmless_without_gpu():
         assert os.sched_getaffinity(0) == before
 
 
-def test_tile_major_spectrum_layout_spec():
-    """Executable statement of the tile-major order of Z between K2 and K3 (fastpath.cu zt_pos /
-    k_tile_response): bin k = r + P*k2 -> Z'[tile][side][k2/4][row%8][k2%4].  The map is a bijection onto [0, Nc); a K2
-    tile owns two contiguous 64 KiB regions; the four k2 of one K3 channel and row are one 32-byte group and the 32
-    points of a K3 thread are eight such groups."""
+def test_tile_image_spectrum_layout_spec():
+    """Executable statement of the order of Z between K2 and K3 on the cfg1 fast path (fastpath.cu
+    zi_pos / k_tile_response): a K2 tile (8 mirror row pairs) leaves the SM as the verbatim image of K2's shared memory,
+    bin k = r + P*k2 -> Z'[tile][g/4][k2/4][which][((g%4)*4 + k2%4) ^ h(k2/4)], h(m) = ((m>>3) ^ (m<<2)) & 15.
+    The map is a bijection onto [0, Nc); a K2 tile owns one contiguous 128 KiB region and each half-CTA group one
+    contiguous 64 KiB half of it; the four k2 of one K3 channel and row are one aligned 32-byte group (permuted inside
+    by h & 3); the layout is bank-conflict free for K2's three shared-memory access patterns."""
     P, Q = 2048, 1024
     r = np.arange(P, dtype=np.int64)[:, None]
     k2 = np.arange(Q, dtype=np.int64)[None, :]
     m = np.where(r > P // 2, P - r, r)
     tile = np.where(r == P // 2, 0, m >> 3)
-    side = np.where(r >= P // 2, 1, 0)
+    which = np.where(r >= P // 2, 1, 0)
     g = np.where(r == P // 2, 0, m & 7)
-    pos = (tile * 2 + side) * (Q * 8) + ((k2 >> 2) << 5) + (g << 2) + (k2 & 3)
+
+    def h(mm):
+        return ((mm >> 3) ^ (mm << 2)) & 15
+
+    def zi(g, which, k2):
+        return (g >> 2) * 8192 + (k2 >> 2) * 32 + which * 16 + ((((g & 3) << 2) | (k2 & 3)) ^ h(k2 >> 2))
+
+    pos = tile * (Q * 16) + zi(g, which, k2)
     flat = pos.ravel()
     assert flat.min() == 0 and flat.max() == P * Q - 1 and np.unique(flat).size == P * Q
-    # a K2 tile (rows 8t..8t+7 and their mirrors) = regions [2t, 2t+2) of Q*8 elements = 2 x 64 KiB of float2
+    # a K2 tile (rows 8t..8t+7 and their mirrors) = one region of 16 Q elements; pairs 0-3 / 4-7 = its two halves
     t = 5
-    rows = np.concatenate([np.arange(8 * t, 8 * t + 8), P - np.arange(8 * t, 8 * t + 8)])
-    got = np.sort(pos[rows].ravel())
-    assert np.array_equal(got, np.arange(2 * t * Q * 8, (2 * t + 2) * Q * 8))
+    lo = np.arange(8 * t, 8 * t + 8)
+    assert np.array_equal(np.sort(pos[np.concatenate([lo, P - lo])].ravel()), np.arange(t * Q * 16, (t + 1) * Q * 16))
+    assert np.array_equal(np.sort(pos[np.concatenate([lo[:4], P - lo[:4]])].ravel()),
+                          np.arange(t * Q * 16, t * Q * 16 + Q * 8))
     # K3: thread (pol, j0) of channel csub holds bins f = j0 + 256 e, e < 32: rows j0 + 256 i (i < 8), k2 = 4 csub + q
-    csub, j0 = 77, 201
-    for i in range(8):
-        row = j0 + 256 * i
-        offs = pos[row, 4 * csub: 4 * csub + 4]
-        assert np.array_equal(offs, offs[0] + np.arange(4)) and offs[0] % 4 == 0      # one aligned 32-byte group
+    for csub, j0 in ((77, 201), (8, 0), (255, 255), (130, 1)):
+        hq = h(np.int64(csub)) & 3
+        for i in range(8):
+            row = j0 + 256 * i
+            offs = pos[row, 4 * csub: 4 * csub + 4]
+            base = offs.min()
+            assert base % 4 == 0 and np.array_equal(offs, base + (np.arange(4) ^ hq))    # one aligned 32-byte group
+    # the four rows g % 4 of a group fill one 128-byte line (16 float2)
+    line = pos[8 * t: 8 * t + 4, 4 * 77: 4 * 77 + 4].ravel()
+    assert line.max() - line.min() == 15 and line.min() % 16 == 0
+    # shared-memory bank pairs (64-bit accesses: 16 lanes per wavefront, 16 pairs of banks)
+    j = np.arange(16)
+    for gg in range(8):
+        for rr in range(32):                                   # scatter of stage 0: lane j writes element 32 j + r
+            assert np.unique(zi(np.int64(gg), 0, 32 * j + rr) & 15).size == 16
+            assert np.unique(zi(np.int64(gg), 1, 32 * (j + 16) + rr) & 15).size == 16
+        for e in range(32):                                    # gather / natural store: lane j holds element j + 32 e
+            assert np.unique(zi(np.int64(gg), 0, j + 32 * e) & 15).size == 16
+            assert np.unique(zi(np.int64(gg), 0, j + 16 + 32 * e) & 15).size == 16
+    lane = np.arange(16)                                       # split walk: 4 consecutive k2 x 4 pairs per half warp
+    for m0 in range(16):
+        for it in range(8):
+            kk = (lane & 3) + 4 * (m0 + 16 * it)
+            gl = (lane >> 2) & 3
+            assert np.unique(zi(gl, 0, kk) & 15).size == 16
+            assert np.unique(zi(gl, 1, Q - 1 - kk) & 15).size == 16
+            # the mirror element Q-1-k2 shares the swizzled low part: slot = (255 - m) * 32 + same low bits
+            assert np.array_equal(zi(gl, 0, Q - 1 - kk) - (255 - (kk >> 2)) * 32, zi(gl, 0, kk) - (kk >> 2) * 32)
