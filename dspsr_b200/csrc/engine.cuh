@@ -121,6 +121,9 @@ struct b200_fb_plan {
   bool fast_k1, fast_k2, fast_k3;
   float2 *c2P, *c2Q, *c2F, *c2F32, *c2Q32;
   float2* d_response_tiled;   // the response in the tile-image order of Z (fastpath.cu zi_pos), or null
+  // one-kernel cluster path of 65536-point convolutions (clusterconv.cu)
+  float2* c2cc;               // stage tables of its 4096-point row transforms, or null
+  int cc_clusters;            // clusters of 8 CTAs the device keeps resident (0 = path not available)
 };
 
 namespace b200 {
@@ -132,4 +135,9 @@ void fast_plan_free(b200_fb_plan* plan);
 int fast_k1(b200_fb_plan* plan, const FbSource& src, uint64_t part0, unsigned nb);
 int fast_k2(b200_fb_plan* plan, unsigned nb);
 int fast_k3(b200_fb_plan* plan, const FbSink& sink, uint64_t part0, unsigned nb);
+// clusterconv.cu
+int cc_plan_init(b200_fb_plan* plan);
+void cc_plan_free(b200_fb_plan* plan);
+bool cc_applies(const b200_fb_plan* plan, const FbSource& src, const FbSink& sink);
+int cc_run(b200_fb_plan* plan, const FbSource& src, const FbSink& sink, uint64_t part0, unsigned nb);
 }

@@ -113,6 +113,7 @@ struct K1Args {
   unsigned skew_ns, nsm;
   int conv_ok;               // 8-bit table is RN(x*(conv_hi+conv_lo)): convert arithmetically, no gathers
   float conv_hi, conv_lo;
+  int pad_;                  // keeps the fields below where ptxas allocates K1 without a spill (16 bytes of stack otherwise)
   int l2_prefetch;           // prefetch the next part's raw bytes into L2 as contiguous slices
   unsigned overlap;          // nsamp_overlap (samples)
 };

@@ -756,6 +756,14 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
   for (uint64_t part0 = 0; part0 < npart; part0 += batch) {
     const unsigned nb = (unsigned)std::min<uint64_t>(batch, npart - part0);
     if (src.batch_ready) B200_CUDA(cudaStreamWaitEvent(st, src.batch_ready[part0 / batch], 0));
+    // 65536-point convolutions folded on the fly: one cluster kernel, no spectrum scratch (clusterconv.cu)
+    if (cc_applies(pl, src, sink)) {
+      FbSink sk = sink;
+      sk.bins = sink.bins + part0 * pl->nkeep;
+      int rc = cc_run(pl, src, sk, part0, nb);
+      if (rc != B200_OK) return rc;
+      continue;
+    }
     // a transform that fits one column pass (Q == 1) of complex input needs no row pass: K1 multiplies by the response
     // and writes Z (the row kernel would be P blocks of a handful of threads: 2.8 of 3.6 ms on the top UWL sub-bands)
     const bool skip_k2 = pl->Q == 1 && !pl->desc.input_real && !pl->conv_path;
@@ -1090,6 +1098,7 @@ int b200_fb_plan_create(b200_context* cctx, const b200_fb_desc* d, b200_fb_plan*
   }
   pl->scratch_bytes = sbytes * (pl->conv_path ? 1 : 2);
   rc = fast_plan_init(pl);
+  if (rc == B200_OK) rc = cc_plan_init(pl);
   if (rc != B200_OK) { b200_fb_plan_destroy(pl); return rc; }
   *out = pl;
   return B200_OK;
@@ -1118,6 +1127,7 @@ int b200_fb_plan_destroy(b200_fb_plan* pl) {
   free_big_twiddle(pl->bigN);
   free_big_twiddle(pl->big2N);
   fast_plan_free(pl);
+  cc_plan_free(pl);
   if (pl->d_response) cudaFree(pl->d_response);
   if (pl->scratchA) cudaFree(pl->scratchA);
   if (pl->scratchZ) cudaFree(pl->scratchZ);

@@ -460,6 +460,42 @@ def test_pipeline_cfg3_meerkat_convolution_fold(ctx, oracle):
     assert err <= TOL, err
 
 
+@pytest.mark.parametrize("fmt,nchan,npart,nblock,state,dndim,nbin", [
+    ("meerkat", 5, 7, 1, "Stokes", 4, 257),       # 35 tiles: several per cluster, the channel changes inside a cluster's range
+    ("meerkat", 3, 2, 2, "PPQQ", 1, 1024),        # two blocks into one PhaseSeries
+    ("uwb", 1, 3, 1, "Intensity", 1, 64),         # 16-bit blocks of 2048 samples
+    ("generic8", 2, 3, 1, "Coherence", 2, 128),   # TFP bytes through the 8-bit table, Coherence with ndim 2
+])
+def test_cluster_convolution_kernel(ctx, oracle, fmt, nchan, npart, nblock, state, dndim, nbin):
+    """clusterconv.cu: 65536-point convolutions folded on the fly run as ONE kernel on clusters of 16 CTAs (distributed
+    shared memory exchanges).  Every source format it unpacks itself, every detection state, tile counts that do not
+    divide into the clusters, several blocks into one PhaseSeries -- against the oracle pipeline."""
+    L = _L()
+    F, npos, nneg = 65536, 2536, 2543
+    c = oracle.conv_sizes(0, nchan, 2, F, npos, nneg)
+    rng = np.random.default_rng(77)
+    H = np.exp(1j * rng.uniform(-np.pi, np.pi, (nchan, F))).astype(np.complex64)
+    nsamp = nblock * npart * c.nsamp_step + c.nsamp_overlap
+    if fmt == "meerkat":
+        ndat = (nsamp + 255) // 256 * 256
+        raw = synth.meerkat_bytes(ndat, nchan, 2, seed=78)
+        _, scale = oracle.bittable8()
+        err = _pipe_generic(ctx, oracle, L.FMT_MEERKAT8, nchan, 2, 2, raw, ndat, None, c, H, 1, F, npos, nneg, npart,
+                            state, dndim, nbin, scale=np.float32(scale), nblock=nblock)
+    elif fmt == "uwb":
+        ndat = (nsamp + 2047) // 2048 * 2048
+        raw = synth.uwb_bytes(ndat, 2, seed=79)
+        err = _pipe_generic(ctx, oracle, L.FMT_UWB16, 1, 2, 2, raw, ndat, None, c, H, 1, F, npos, nneg, npart,
+                            state, dndim, nbin, nblock=nblock)
+    else:
+        ndat = nsamp
+        raw = synth.generic8_bytes(ndat, nchan, 2, 2, seed=80)
+        lut, _ = oracle.bittable8()
+        err = _pipe_generic(ctx, oracle, L.FMT_GENERIC8, nchan, 2, 2, raw, ndat, None, c, H, 1, F, npos, nneg, npart,
+                            state, dndim, nbin, lut=lut, nblock=nblock)
+    assert err <= TOL, err
+
+
 def test_pipeline_4096_input_channels_grid_limit(ctx, oracle):
     """4096 input channels x 2 polarisations = 8192 (channel, pol) blocks per part; with the default
     16 parts per launch the generic kernels' grid.y would be 131072 (> 65535).  The plan caps the batch; 20 parts
