@@ -58,3 +58,32 @@ all: $(OUT)/libdspsr_refsigproc.so
 $(OUT)/libdspsr_refsigproc.so: $(SIGSRCS) ref_shim/ref_sigproc.c
 	@mkdir -p $(OUT)
 	$(CC) -std=gnu99 -O2 -fPIC -w -shared -I$(SIGPROC) -o $@ $(SIGSRCS) ref_shim/ref_sigproc.c -lm
+
+# libdspsr_reffold.so: the loops of dsp::Fold::fold (row a13) compiled from the reference's own text.  Fold.C as a whole
+# needs PSRCHIVE's predictor / ephemeris classes; its three self-contained statement blocks do not: sed cuts them, where
+# the file lies, into _ref/gen/*.inc (build products, git-ignored) and ref_shim/ref_fold.cpp supplies the variables
+# around them.  The grep lines make the build fail if the reference text is not the one the line numbers were read from.
+FOLDC = $(REF)/Signal/Pulsar/Fold.C
+all: $(OUT)/libdspsr_reffold.so
+$(OUT)/gen/fold_binplan.inc: $(FOLDC)
+	@mkdir -p $(OUT)/gen
+	sed -n '687,716p' $(FOLDC) > $(OUT)/gen/fold_weights.inc
+	sed -n '744,787p' $(FOLDC) > $(OUT)/gen/fold_binplan.inc
+	sed -n '835,873p' $(FOLDC) > $(OUT)/gen/fold_accum.inc
+	grep -q 'iweight = (idat_start + weight_idat) / ndatperweight;' $(OUT)/gen/fold_weights.inc
+	head -1 $(OUT)/gen/fold_binplan.inc | grep -q 'for (uint64_t idat=idat_start; idat < idat_end; idat++)'
+	grep -q 'phi -= floor(phi);' $(OUT)/gen/fold_binplan.inc
+	grep -q 'hits\[ibin\]++;' $(OUT)/gen/fold_binplan.inc
+	head -1 $(OUT)/gen/fold_accum.inc | grep -q 'if (in->get_order() == TimeSeries::OrderFPT)'
+	grep -q 'phdimp\[idim\] += timep\[idim\];' $(OUT)/gen/fold_accum.inc
+$(OUT)/libdspsr_reffold.so: $(OUT)/gen/fold_binplan.inc ref_shim/ref_fold.cpp ref_shim/Error.h
+	$(CXX) -std=gnu++98 -O2 -fPIC -ffp-contract=off -w -shared -Iref_shim -I$(OUT) -o $@ ref_shim/ref_fold.cpp -lm
+
+# libdspsr_refbit.so: the generic 8-bit unpacker (row a3): BitUnpacker.C + EightBitUnpacker.C + BitTable.C with their own
+# headers; ref_shim/bit comes first so that only dsp/HistUnpacker.h (the PSRCHIVE-dependent base) is a stand-in
+BITSRCS = $(REF)/Kernel/Classes/BitUnpacker.C $(REF)/Kernel/Classes/EightBitUnpacker.C $(REF)/Kernel/Classes/BitTable.C
+all: $(OUT)/libdspsr_refbit.so
+$(OUT)/libdspsr_refbit.so: $(BITSRCS) ref_shim/bit/ref_bitunpack.cpp $(wildcard ref_shim/*.h ref_shim/dsp/*.h ref_shim/bit/dsp/*.h) _build/liboracle.so
+	@mkdir -p $(OUT)
+	$(CXX) -std=gnu++98 -O2 -fPIC -ffp-contract=off -w -shared -Iref_shim/bit -I$(REF)/Kernel/Classes -Iref_shim \
+	    -o $@ $(BITSRCS) ref_shim/bit/ref_bitunpack.cpp -L_build -loracle -Wl,-rpath,'$$ORIGIN/../_build' -lm -lpthread

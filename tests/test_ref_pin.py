@@ -476,3 +476,116 @@ def test_sigproc_header_bytes_equal_reference_writer(tmp_path, bw, nchan, npol, 
     L.check(lib.b200_sigproc_file_write(str(fil).encode(), None, data.ctypes.data, data.size, 1))
     blob = open(fil, "rb").read()
     assert blob[:n] == ref and blob[n:] == data.tobytes() * 2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Fold (row a13; oracle/_ref/libdspsr_reffold.so): the statement blocks of dsp::Fold::fold -- weight set-up
+# (Fold.C:687-716), the per-sample phase recurrence / bin plan / hits loop (:744-787) and the OrderFPT accumulation
+# (:835-873) -- compiled from the reference's own text (oracle/ref.mk cuts them out of the file in place) inside
+# oracle/ref_shim/ref_fold.cpp.  The oracle's orc_fold_plan / orc_fold_plan_weighted / orc_fold must agree bit for bit.
+# ---------------------------------------------------------------------------------------------------------------
+REFFOLD = os.path.join(ROOT, "oracle", "_ref", "libdspsr_reffold.so")
+needs_fold = pytest.mark.skipif(not os.path.exists(REFFOLD), reason="oracle/_ref fold pin library not built")
+
+
+@pytest.fixture(scope="module")
+def reffold():
+    L = C.CDLL(REFFOLD)
+    L.ref_fold.restype = C.c_uint64
+    L.ref_fold.argtypes = [C.c_double, C.c_double, C.c_uint, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint,
+                           C.c_uint, C.c_int, C.c_void_p, C.c_uint64, C.c_uint, C.c_uint, C.c_uint, C.c_void_p,
+                           C.c_void_p, C.c_void_p, C.c_void_p]
+    return L
+
+
+def _ref_fold(L, phi, pps, nbin, idat_start, ndat, weights, ndpw, widat, x=None, ndim=1):
+    binplan = np.zeros(ndat, np.uint32)
+    hits = np.zeros(nbin, np.uint32)
+    disc = np.zeros(1, np.uint32)
+    prof = None
+    args = [None, 0, 0, 0, 0]
+    if x is not None:
+        x = np.ascontiguousarray(x, np.float32)
+        nchan, npol, n = x.shape
+        prof = np.zeros((nchan, npol, nbin * ndim), np.float32)
+        args = [_vp(x), n, nchan, npol, ndim]
+    w = np.ascontiguousarray(weights if weights is not None else [], np.uint32)
+    n = L.ref_fold(phi, pps, nbin, idat_start, ndat, _vp(w) if w.size else None, w.size, ndpw if w.size else 0, widat,
+                   0, *args, _vp(binplan), _vp(hits), _vp(prof) if prof is not None else None, _vp(disc))
+    return binplan, hits, n, prof, int(disc[0])
+
+
+@needs_fold
+@pytest.mark.parametrize("nbin,pps,phi,ndat", [
+    (1024, 1.0 / 71492.5, 0.123456789, 300000),        # cfg1-like: many samples per bin
+    (1024, 1.0 / 4000.37, 0.999999, 200000),           # cfg3-like: ~4 samples per bin, start next to a wrap
+    (37, 0.0173, 0.0, 5000),                           # a period of a few dozen samples
+    (2, 0.61803398875, 0.5, 1000),                     # period shorter than two samples
+    (8192, 1e-9, 0.75, 100000),                        # a whole block inside one bin
+])
+def test_fold_bin_plan_matches_reference_loop(reffold, oracle, nbin, pps, phi, ndat):
+    """The sequential double-precision recurrence of Fold.C:765-768 and its hit counting, from the reference's text,
+    against the oracle (and through it against the GPU's segment expansion, tests/test_host_logic.py)."""
+    rb, rh, rn, _, _ = _ref_fold(reffold, phi, pps, nbin, 0, ndat, None, 0, 0)
+    ob, oh, on, _ = oracle.fold_plan(phi, pps, nbin, ndat)
+    assert rn == on == ndat
+    assert np.array_equal(rb, ob) and np.array_equal(rh, oh)
+
+
+@needs_fold
+@pytest.mark.parametrize("seed", range(6))
+def test_fold_weighted_plan_and_accumulation_match_reference_loop(reffold, oracle, seed):
+    """Weighted input (WeightedTimeSeries windows with zero weight are not folded and get bin = nbin, Fold.C:687-716,
+    746-763, 777-786) and the OrderFPT accumulation loop (Fold.C:835-873) for every detected layout: bin plan, hits,
+    ndat_folded and the float profile sums are bit-identical."""
+    rng = np.random.default_rng(100 + seed)
+    nbin = int(rng.choice([16, 128, 1024]))
+    ndpw = int(rng.choice([64, 512, 1000]))
+    idat_start = int(rng.integers(0, 3 * ndpw))
+    widat = int(rng.integers(0, ndpw))
+    ndat = int(rng.integers(2000, 20000))
+    nweights = (idat_start + ndat + widat) // ndpw + 2
+    weights = (rng.random(nweights) > 0.3).astype(np.uint32) * rng.integers(1, 9, nweights).astype(np.uint32)
+    phi, pps = float(rng.random()), float(1.0 / rng.uniform(3.0, 5000.0))
+    nchan, npol, ndim = int(rng.integers(1, 4)), int(rng.choice([1, 2, 4])), int(rng.choice([1, 2, 4]))
+    x = rng.standard_normal((nchan, npol, (idat_start + ndat) * ndim)).astype(np.float32)
+    rb, rh, rn, rprof, rdisc = _ref_fold(reffold, phi, pps, nbin, idat_start, ndat, weights, ndpw, widat, x, ndim)
+    ob, oh, on = oracle.fold_plan_weighted(phi, pps, nbin, idat_start, ndat, weights, ndpw, widat)
+    assert rn == on and np.array_equal(rb, ob) and np.array_equal(rh, oh)
+    assert rdisc == int(np.count_nonzero(weights[(idat_start + widat) // ndpw:(idat_start + ndat - 1 + widat) // ndpw + 1] == 0))
+    oprof = oracle.fold(x, ndim, ob, nbin, idat_start=idat_start)
+    assert np.array_equal(rprof.view(np.uint32), oprof.view(np.uint32))
+    assert (rb == nbin).any() and (rb != nbin).any()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Generic 8-bit unpacker (row a3; oracle/_ref/libdspsr_refbit.so): BitUnpacker.C + EightBitUnpacker.C + BitTable.C
+# compiled in place with their own headers (only dsp/HistUnpacker.h, the PSRCHIVE-dependent base, is a stand-in).
+# ---------------------------------------------------------------------------------------------------------------
+REFBIT = os.path.join(ROOT, "oracle", "_ref", "libdspsr_refbit.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REFBIT), reason="oracle/_ref/libdspsr_refbit.so not built")
+@pytest.mark.parametrize("nchan,npol,ndim,twos", [(1, 2, 1, 1), (3, 2, 2, 1), (4, 1, 2, 0), (2, 2, 1, 0)])
+def test_generic8_unpack_and_histogram_match_reference(oracle, nchan, npol, ndim, twos):
+    """BitUnpacker.C:48-80 (the digitizer walk over TFP bytes) and EightBitUnpacker.C:25-49 (hist[*from]++,
+    *into = lookup[*from]): floats and the per-digitizer histograms are bit-identical with the oracle."""
+    oracle.lib()
+    L = C.CDLL(REFBIT)
+    L.ref_unpack_generic8.restype = C.c_int
+    L.ref_unpack_generic8.argtypes = [C.c_void_p, C.c_uint64, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_void_p, C.c_uint64,
+                                      C.c_void_p]
+    rng = np.random.default_rng(55)
+    ndat = 3001
+    raw = rng.integers(0, 256, ndat * nchan * npol * ndim, dtype=np.uint8)
+    raw[:6] = [0, 1, 127, 128, 129, 255]
+    want = np.zeros((nchan, npol, ndat * ndim), np.float32)
+    whist = np.zeros((nchan * npol * ndim, 256), np.uint64)
+    assert L.ref_unpack_generic8(_vp(raw), ndat, nchan, npol, ndim, twos, _vp(want), ndat * ndim, _vp(whist)) == 0
+    lut, _ = oracle.bittable8(twos_complement=bool(twos))
+    got = np.zeros_like(want)
+    ghist = np.zeros_like(whist)
+    oracle.lib().orc_unpack_generic8(_vp(raw), C.c_uint64(ndat), nchan, npol, ndim, _vp(lut), _vp(got),
+                                     C.c_uint64(ndat * ndim), _vp(ghist))
+    assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
+    assert np.array_equal(whist, ghist) and int(whist.sum()) == raw.size
