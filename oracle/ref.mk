@@ -33,9 +33,22 @@ $(OUT)/libdspsr_refc.so: $(SRCS) ref_shim/config.h
 	$(CC) -std=gnu99 -O2 -fPIC -ffp-contract=off -w -shared $(INCS) -o $@ $(SRCS) -lm
 
 # links against the oracle library for the restated JenetAnderson98 numbers only (ref_shim/JenetAnderson98.h)
-$(OUT)/libdspsr_refcxx.so: $(CXXSRCS) ref_shim/ref_cxx.cpp $(wildcard ref_shim/*.h ref_shim/dsp/*.h) $(OUT)/libdspsr_refc.so _build/liboracle.so
+# the overlap-save loop nests of Filterbank.C / Convolution.C (rows a10, a11), cut out of the files in place into
+# _ref/gen/*.inc and compiled inside ref_shim/ref_fbconv.cpp (response multiply = the reference's Response::operate,
+# FFT calls = the oracle's restatement of the FFTW conventions).  The greps pin the text to the line numbers.
+$(OUT)/gen/filterbank_loop.inc: $(REF)/Signal/General/Filterbank.C $(REF)/Signal/General/Convolution.C
+	@mkdir -p $(OUT)/gen
+	sed -n '563,660p' $(REF)/Signal/General/Filterbank.C > $(OUT)/gen/filterbank_loop.inc
+	sed -n '389,458p' $(REF)/Signal/General/Convolution.C > $(OUT)/gen/convolution_loop.inc
+	head -1 $(OUT)/gen/filterbank_loop.inc | grep -q 'for (unsigned input_ichan=0; input_ichan<input->get_nchan(); input_ichan++)'
+	grep -q 'backward->bcc1d (freq_res, c_time, freq_dom_ptr);' $(OUT)/gen/filterbank_loop.inc
+	grep -q 'data_from = (uint64_t\*)( c_time + nfilt_pos\*2 );' $(OUT)/gen/filterbank_loop.inc
+	head -1 $(OUT)/gen/convolution_loop.inc | grep -q 'for (unsigned ichan=0; ichan < nchan; ichan++)'
+	grep -q 'memcpy (ptr, complex_time + nfilt_pos\*2, nbytes_step);' $(OUT)/gen/convolution_loop.inc
+
+$(OUT)/libdspsr_refcxx.so: $(CXXSRCS) ref_shim/ref_cxx.cpp ref_shim/ref_fbconv.cpp $(OUT)/gen/filterbank_loop.inc $(wildcard ref_shim/*.h ref_shim/dsp/*.h) $(OUT)/libdspsr_refc.so _build/liboracle.so
 	@mkdir -p $(OUT)
-	$(CXX) -std=gnu++98 -O2 -fPIC -ffp-contract=off -w -shared $(INCS) -o $@ $(CXXSRCS) ref_shim/ref_cxx.cpp \
+	$(CXX) -std=gnu++98 -O2 -fPIC -ffp-contract=off -w -shared $(INCS) -I$(OUT) -o $@ $(CXXSRCS) ref_shim/ref_cxx.cpp ref_shim/ref_fbconv.cpp \
 	    -L$(OUT) -ldspsr_refc -L_build -loracle -Wl,-rpath,'$$ORIGIN' -Wl,-rpath,'$$ORIGIN/../_build' -lm
 
 # libdspsr_reffmt.so: the format unpackers (rows a2, a4, a5).  Their own first-level headers are the reference's;

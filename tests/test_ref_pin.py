@@ -1,10 +1,19 @@
-"""Pins the parts of the oracle that CAN be checked against the real reference: the four plain-C files of
-the hot path compiled in place from /root/reference by oracle/ref.mk into oracle/_ref/libdspsr_refc.so
-(optimize_fft.c, cross_detect.c, stokes_detect.c, ascii_header.c).  Everything else on the path is C++
-against PSRCHIVE/FFTW and cannot be built here (DESIGN.md "Oracle"), so those rows stay "parity unpinned".
+"""Pins the oracle to the real reference wherever reference code can be compiled here (oracle/ref.mk, outputs in
+oracle/_ref/, sources read where they lie under /root/reference):
+  libdspsr_refc.so       optimize_fft.c, cross_detect.c, stokes_detect.c, ascii_header.c            (rows a9, a12, header)
+  libdspsr_refcxx.so     BitTable.C, TwoBitTable.C, TwoBitLookup.C, TwoBitFour.C, excision_unpack.h,
+                         Dedispersion.C, Response.C, Shape.C                                        (a1, a6, a7, a8)
+                         + the overlap-save loop nests of Filterbank.C:563-660 / Convolution.C:389-458 compiled from
+                           the reference's text around the reference's Response::operate              (a10, a11)
+  libdspsr_reffmt.so     CASPSRUnpacker.C, MeerKATUnpacker.C, UWBUnpacker.C                          (a2, a4, a5)
+  libdspsr_refbit.so     BitUnpacker.C, EightBitUnpacker.C                                           (a3)
+  libdspsr_reffold.so    the weight / bin-plan / accumulation loops of Fold.C:687-716,744-787,835-873 (a13)
+  libdspsr_refsigproc.so filterbank_header.c, send_stuff.c                                           (f1)
+What stays restated: the FFT primitive (FFTW inside PSRCHIVE) and the TEMPO polyco evaluation (PSRCHIVE) -- third-party
+code that is not in the reference tree.
 
-The library is built by __graft_entry__.build() whenever /root/reference exists and travels to the GPU
-box with the snapshot; nothing here reads /root/reference at run time."""
+The libraries are built by __graft_entry__.build() whenever /root/reference exists and travel to the GPU box with the
+snapshot; nothing here reads /root/reference at run time."""
 import ctypes as C
 import os
 
@@ -589,3 +598,59 @@ def test_generic8_unpack_and_histogram_match_reference(oracle, nchan, npol, ndim
                                      C.c_uint64(ndat * ndim), _vp(ghist))
     assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
     assert np.array_equal(whist, ghist) and int(whist.sum()) == raw.size
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Filterbank / Convolution (rows a10, a11): the overlap-save loop nests of Filterbank.C:563-660 and
+# Convolution.C:389-458 compiled from the reference's own text (oracle/ref_shim/ref_fbconv.cpp) with the reference's
+# own Response::operate; only the three FFT calls go to the oracle's restatement of the FFTW conventions (FFTW lives in
+# PSRCHIVE, which is not in the tree).  The oracle's loops must reproduce the output bit for bit.
+# ---------------------------------------------------------------------------------------------------------------
+@needs_cxx
+@pytest.mark.parametrize("real,input_nchan,npol,nchan,F,npos,nneg,with_H", [
+    (1, 1, 2, 16, 128, 11, 13, True),       # cfg1-shaped: real input, one input channel, -F 16:D
+    (1, 1, 1, 8, 1, 0, 0, False),           # freq_res 1: the 64-bit copy branch, no response
+    (0, 3, 2, 12, 64, 5, 6, True),          # complex multi-channel input, 4 sub-channels each
+    (0, 2, 2, 2, 256, 20, 21, True),        # nchan_subband 1 through the filterbank
+])
+def test_filterbank_loop_matches_reference_text(refcxx, oracle, real, input_nchan, npol, nchan, F, npos, nneg, with_H):
+    f = oracle.fb_sizes(bool(real), input_nchan, npol, nchan, F, npos, nneg)
+    ndim = 1 if real else 2
+    npart = 3
+    ndat = npart * f.nsamp_step + f.nsamp_overlap
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((input_nchan, npol, ndat * ndim)).astype(np.float32)
+    H = np.exp(1j * rng.uniform(-np.pi, np.pi, (nchan, F))).astype(np.complex64) if with_H else None
+    got = oracle.filterbank(f, x, H)
+    assert got.shape == (nchan, npol, npart * f.nkeep)
+    want = np.zeros_like(got)
+    refcxx.ref_filterbank.restype = C.c_int
+    refcxx.ref_filterbank.argtypes = [C.c_void_p, C.c_uint64, C.c_uint, C.c_uint, C.c_int, C.c_uint, C.c_uint, C.c_uint,
+                                      C.c_uint, C.c_uint, C.c_uint, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64]
+    assert refcxx.ref_filterbank(_vp(x), x.shape[2], input_nchan, npol, real, f.nchan_subband, F, npos, nneg, f.nsamp_fft,
+                                 f.nsamp_step, npart, _vp(H) if with_H else None, _vp(want), 2 * npart * f.nkeep) == 0
+    assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
+    assert np.abs(want).max() > 0
+
+
+@needs_cxx
+@pytest.mark.parametrize("real,nchan,npol,n_fft,npos,nneg", [(0, 3, 2, 512, 40, 45), (1, 1, 2, 1024, 100, 101), (0, 1, 1, 64, 0, 7)])
+def test_convolution_loop_matches_reference_text(refcxx, oracle, real, nchan, npol, n_fft, npos, nneg):
+    c = oracle.conv_sizes(bool(real), nchan, npol, n_fft, npos, nneg)
+    ndim = 1 if real else 2
+    npart = 3
+    ndat = npart * c.nsamp_step + c.nsamp_overlap
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((nchan, npol, ndat * ndim)).astype(np.float32)
+    H = np.exp(1j * rng.uniform(-np.pi, np.pi, (nchan, n_fft))).astype(np.complex64)
+    got = oracle.convolution(c, x, H)
+    nkeep = n_fft - npos - nneg
+    assert got.shape == (nchan, npol, npart * nkeep)
+    want = np.zeros_like(got)
+    refcxx.ref_convolution.restype = C.c_int
+    refcxx.ref_convolution.argtypes = [C.c_void_p, C.c_uint64, C.c_uint, C.c_uint, C.c_int, C.c_uint, C.c_uint, C.c_uint,
+                                       C.c_uint, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64]
+    assert refcxx.ref_convolution(_vp(x), x.shape[2], nchan, npol, real, n_fft, npos, c.nsamp_fft, c.nsamp_step, npart,
+                                  _vp(H), _vp(want), 2 * npart * nkeep) == 0
+    assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
+    assert np.abs(want).max() > 0
