@@ -78,7 +78,7 @@ $(OUT)/libdspsr_refsigproc.so: $(SIGSRCS) ref_shim/ref_sigproc.c
 # around them.  The grep lines make the build fail if the reference text is not the one the line numbers were read from.
 FOLDC = $(REF)/Signal/Pulsar/Fold.C
 all: $(OUT)/libdspsr_reffold.so
-$(OUT)/gen/fold_binplan.inc: $(FOLDC)
+$(OUT)/gen/fold_binplan.inc: $(FOLDC) $(REF)/Kernel/Classes/WeightedTimeSeries.C
 	@mkdir -p $(OUT)/gen
 	sed -n '687,716p' $(FOLDC) > $(OUT)/gen/fold_weights.inc
 	sed -n '744,787p' $(FOLDC) > $(OUT)/gen/fold_binplan.inc
@@ -89,6 +89,12 @@ $(OUT)/gen/fold_binplan.inc: $(FOLDC)
 	grep -q 'hits\[ibin\]++;' $(OUT)/gen/fold_binplan.inc
 	head -1 $(OUT)/gen/fold_accum.inc | grep -q 'if (in->get_order() == TimeSeries::OrderFPT)'
 	grep -q 'phdimp\[idim\] += timep\[idim\];' $(OUT)/gen/fold_accum.inc
+	sed -n '584,696p' $(REF)/Kernel/Classes/WeightedTimeSeries.C > $(OUT)/gen/wts_convolve.inc
+	sed -n '705,774p' $(REF)/Kernel/Classes/WeightedTimeSeries.C > $(OUT)/gen/wts_scrunch.inc
+	head -1 $(OUT)/gen/wts_convolve.inc | grep -q 'if (ndat_per_weight >= nfft)'
+	grep -q 'zero_end = uint64_t( ceil((start_idat+nkeep) \* weights_per_dat) );' $(OUT)/gen/wts_convolve.inc
+	head -1 $(OUT)/gen/wts_scrunch.inc | grep -q 'uint64_t nweights_tot = get_nweights();'
+	grep -q 'weights\[iwt\] /= nscrunch;' $(OUT)/gen/wts_scrunch.inc
 $(OUT)/libdspsr_reffold.so: $(OUT)/gen/fold_binplan.inc ref_shim/ref_fold.cpp ref_shim/Error.h
 	$(CXX) -std=gnu++98 -O2 -fPIC -ffp-contract=off -w -shared -Iref_shim -I$(OUT) -o $@ ref_shim/ref_fold.cpp -lm
 

@@ -3,7 +3,9 @@
 //   Fold.C:687-716   weight set-up            (iweight, idat_nextweight, first bad window)
 //   Fold.C:744-788   per-sample loop          (weight walk, phase recurrence, bin plan, hits, ndat_folded)
 //   Fold.C:835-873   OrderFPT accumulation    (phdimp[idim] += timep[idim], zeroed-sample hit counting)
-// out of the file where it lies under /root/reference into oracle/_ref/gen/*.inc (git-ignored build products; no
+// and the bodies of dsp::WeightedTimeSeries::convolve_weights / scrunch_weights (Kernel/Classes/WeightedTimeSeries.C:584-696,
+// 705-774)
+// out of the files where they lie under /root/reference into oracle/_ref/gen/*.inc (git-ignored build products; no
 // reference text enters this repository) and this harness supplies the member variables and the two accessors the
 // blocks touch.  Fold.C as a whole needs the PSRCHIVE predictor / ephemeris class trees and cannot be compiled here.
 #include <assert.h>
@@ -76,4 +78,49 @@ extern "C" uint64_t ref_fold(double phi, double phase_per_sample, unsigned foldi
   }
   (void)ndat_not_folded; (void)bad_weights; (void)tot_weights;
   return ndat_folded;
+}
+
+// ---- WeightedTimeSeries::convolve_weights / scrunch_weights: the reference's function bodies inside a holder of the
+//      members they touch ----
+#ifndef DEBUG
+#define DEBUG(x)
+#endif
+#define UI64 "%lu"
+namespace {
+struct WeightsHolder {
+  unsigned* weights;
+  uint64_t nweights_, ndat_;
+  unsigned ndat_per_weight;
+  uint64_t weight_idat;
+  static const bool verbose = false;
+  uint64_t get_ndat() const { return ndat_; }
+  uint64_t get_nweights() const { return nweights_; }
+  uint64_t get_nzero() const { return 0; }
+  void convolve_weights(unsigned nfft, unsigned nkeep) {
+#include "gen/wts_convolve.inc"
+  }
+  void scrunch_weights(unsigned nscrunch) {
+#include "gen/wts_scrunch.inc"
+  }
+};
+}  // namespace
+
+extern "C" int ref_convolve_weights(unsigned* weights, uint64_t nweights_tot, unsigned ndat_per_weight, uint64_t weight_idat,
+                                    uint64_t ndat, unsigned nfft, unsigned nkeep) {
+  WeightsHolder h = {weights, nweights_tot, ndat, ndat_per_weight, weight_idat};
+  try {
+    h.convolve_weights(nfft, nkeep);
+  } catch (Error&) {
+    return -1;
+  }
+  return 0;
+}
+
+// the reference updates ndat_per_weight and weight_idat; the new weight count follows from them (get_nweights)
+extern "C" void ref_scrunch_weights(unsigned* weights, uint64_t nweights_tot, unsigned* ndat_per_weight, uint64_t* weight_idat,
+                                    unsigned nscrunch) {
+  WeightsHolder h = {weights, nweights_tot, 0, *ndat_per_weight, *weight_idat};
+  h.scrunch_weights(nscrunch);
+  *ndat_per_weight = h.ndat_per_weight;
+  *weight_idat = h.weight_idat;
 }

@@ -7,7 +7,8 @@ oracle/_ref/, sources read where they lie under /root/reference):
                            the reference's text around the reference's Response::operate              (a10, a11)
   libdspsr_reffmt.so     CASPSRUnpacker.C, MeerKATUnpacker.C, UWBUnpacker.C                          (a2, a4, a5)
   libdspsr_refbit.so     BitUnpacker.C, EightBitUnpacker.C                                           (a3)
-  libdspsr_reffold.so    the weight / bin-plan / accumulation loops of Fold.C:687-716,744-787,835-873 (a13)
+  libdspsr_reffold.so    the weight / bin-plan / accumulation loops of Fold.C:687-716,744-787,835-873 (a13) and the bodies of
+                         WeightedTimeSeries::convolve_weights / scrunch_weights (WeightedTimeSeries.C:584-696,705-774; f4)
   libdspsr_refsigproc.so filterbank_header.c, send_stuff.c                                           (f1)
 What stays restated: the FFT primitive (FFTW inside PSRCHIVE) and the TEMPO polyco evaluation (PSRCHIVE) -- third-party
 code that is not in the reference tree.
@@ -654,3 +655,36 @@ def test_convolution_loop_matches_reference_text(refcxx, oracle, real, nchan, np
                                   _vp(H), _vp(want), 2 * npart * nkeep) == 0
     assert np.array_equal(want.view(np.uint32), got.view(np.uint32))
     assert np.abs(want).max() > 0
+
+
+@needs_fold
+@pytest.mark.parametrize("seed", range(8))
+def test_weights_convolve_and_scrunch_match_reference_text(reffold, oracle, seed):
+    """SURVEY 8f row f4: the bodies of WeightedTimeSeries::convolve_weights (WeightedTimeSeries.C:584-696: a transform
+    holding a bad window is flagged as a whole, one transform late) and scrunch_weights (:705-774), compiled from the
+    reference's text, against the oracle -- random bad windows, both scrunch regimes."""
+    rng = np.random.default_rng(300 + seed)
+    ndpw = int(rng.choice([16, 64, 512]))
+    nfft = int(rng.choice([128, 1024, 4096]))
+    nkeep = int(nfft - rng.integers(1, nfft // 2))
+    weight_idat = int(rng.integers(0, ndpw))
+    ndat = int(nfft + nkeep * rng.integers(2, 12) + rng.integers(0, nkeep))
+    nweights = (ndat + weight_idat + ndpw - 1) // ndpw + 1
+    w0 = (rng.random(nweights) > 0.15).astype(np.uint32) * rng.integers(1, 5, nweights).astype(np.uint32)
+    reffold.ref_convolve_weights.restype = C.c_int
+    reffold.ref_convolve_weights.argtypes = [C.c_void_p, C.c_uint64, C.c_uint, C.c_uint64, C.c_uint64, C.c_uint, C.c_uint]
+    want = w0.copy()
+    assert reffold.ref_convolve_weights(_vp(want), want.size, ndpw, weight_idat, ndat, nfft, nkeep) == 0
+    got = oracle.convolve_weights(w0, ndpw, weight_idat, ndat, nfft, nkeep)
+    assert np.array_equal(want, got)
+    if ndpw < nfft:
+        assert (want == 0).sum() >= (w0 == 0).sum()
+    reffold.ref_scrunch_weights.restype = None
+    reffold.ref_scrunch_weights.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint), C.POINTER(C.c_uint64), C.c_uint]
+    for nscrunch in (2, ndpw // 4, ndpw, 3 * ndpw):
+        wref = want.copy()
+        npw, wi = C.c_uint(ndpw), C.c_uint64(weight_idat)
+        reffold.ref_scrunch_weights(_vp(wref), wref.size, C.byref(npw), C.byref(wi), nscrunch)
+        ow, onpw, owi = oracle.scrunch_weights(want, ndpw, weight_idat, nscrunch)
+        assert (npw.value, wi.value) == (onpw, owi)
+        assert np.array_equal(wref[:ow.size], ow)
