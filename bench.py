@@ -506,6 +506,14 @@ def run_ours(args):
             traffic = sum(per_part.values()) * streams[0]["parts"]
         if dom in per_part:
             traffic_dom = per_part[dom] * streams[0]["parts"] / kinfo[dom]["launches_per_block"]
+    if args.workload == "cfg3" and os.path.exists(tp) and set(kinfo) <= {"inverse", "bins"}:
+        # the one-kernel cluster path (clusterconv.cu): all DRAM traffic of a block is that kernel's
+        with open(tp) as f:
+            tc = json.load(f).get("cfg3_cluster")
+        if tc:
+            per_tile = tc["dram_bytes_per_launch"] / (tc["parts_per_launch"] * tc["channels"])
+            traffic = per_tile * streams[0]["parts"] * streams[0]["S"]["nin"]
+            traffic_dom = traffic / kinfo[dom]["launches_per_block"]
     roof = {"bound": "hbm", "achieved": path_gbs, "peak": peak, "unit": "GB/s", "frac": path_gbs / peak,
             "what": "whole path, SURVEY 8(d): algorithmic bytes (one spectrum round trip) per block / block time",
             "alg_bytes_per_block": alg_block,

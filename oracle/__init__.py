@@ -2,7 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs.  The product (dspsr_b200/) never imports this.
-Parity is UNPINNED: the reference ships no golden vectors for the path.
+Parity status: pinned bit for bit to reference code compiled in place (oracle/ref.mk -> oracle/_ref/, checked by
+tests/test_ref_pin.py) for every stage; UNPINNED only for the third-party primitives that live in PSRCHIVE (FFTW
+transforms, TEMPO polyco evaluation, JA98 / normal-distribution numbers) -- see the header of dspsr_oracle.cpp.
 """
 import ctypes as C
 import os

@@ -7,15 +7,23 @@
 // bench.py's cpu_baseline / --impl reference legs).  Nothing in dspsr_b200/ links,
 // imports or executes it.
 //
-// PARITY UNPINNED: the reference holds no golden vectors for this path (its test_*.C
-// are file-driven smoke/timing drivers) and cannot be built here (needs PSRCHIVE, FFTW,
-// autotools).  Third-party arithmetic that lives in PSRCHIVE (version un-pinned by
-// configure.ac:73) is restated from its published definition:
+// PARITY STATUS: PINNED to reference code, stage by stage, by tests/test_ref_pin.py -- oracle/ref.mk compiles the
+// reference's sources where they lie under /root/reference into oracle/_ref/*.so (whole files: BitTable.C, the format
+// and 8-bit / 2-bit unpackers, Dedispersion.C, Response.C, Shape.C, optimize_fft.c, cross_detect.c, stokes_detect.c,
+// filterbank_header.c, ascii_header.c; statement blocks cut from the text: the overlap-save loop nests of
+// Filterbank.C:563-660 and Convolution.C:389-458, the loops of Fold.C:687-716,744-787,835-873, the bodies of
+// WeightedTimeSeries::convolve_weights / scrunch_weights) and every function below that restates one of them must
+// agree with it bit for bit.  The reference holds no golden vectors for this path (its test_*.C are file-driven
+// smoke/timing drivers) and cannot be built as a whole here (needs PSRCHIVE, autotools).
+// PARITY UNPINNED for the third-party arithmetic that lives in PSRCHIVE (version un-pinned by configure.ac:73, source
+// not in the tree); it is restated from its published definition:
 //   * FTransform frc1d/fcc1d/bcc1d  -> orc_fft.cpp (FFTW conventions, unnormalised)
 //   * JenetAnderson98::get_optimal_spacing -> Table of optimal n-bit thresholds (JA98)
 //   * NormalDistribution::cumulative_distribution -> 0.5*(1+erf(x/sqrt 2))
-//   * Pulsar::Predictor (TEMPO polyco) phase/frequency -> TEMPO polyco definition
+//   * Pulsar::Predictor (TEMPO polyco) phase/frequency -> TEMPO polyco definition (checked on Benchmark/vela.polyco)
 //   * MJD -> (day, second, fraction) triple
+// and for the size bookkeeping of Filterbank.C:68-155 / Convolution.C:105-221 and TimeDivide.C (restated; values of
+// SURVEY App. B asserted).
 // Compiled with -ffp-contract=off so double-precision results are reproducible.
 #include <algorithm>
 #include <cassert>
