@@ -2,7 +2,8 @@
 """SASS census of the product library: per kernel, how many of the instructions that carry the design are there.
   python profiles/sass_census.py [lib.so] > profiles/rN_sass_census.txt
 Packed FP32 (FFMA2 / FADD2 / FMUL2: Blackwell's two-lane FP32 issue), 128/256-bit global and shared accesses, the
-fire-and-forget reductions of the fold (RED), TMA (UTMALDG / UTMASTG), named barriers (BAR with an id), and what is
+fire-and-forget reductions of the fold (RED), TMA (UTMALDG / UTMASTG tensor, UBLKCP bulk), distributed-shared-memory
+stores and cluster barriers of the cluster kernel, named barriers (BAR with an id), and what is
 NOT there (no HMMA / tcgen05: FFT butterflies are not a dense contraction)."""
 import collections
 import re
@@ -35,6 +36,9 @@ keys = [("FFMA2", lambda o: o.startswith("FFMA2")), ("FADD2", lambda o: o.starts
         ("RED", lambda o: o.startswith("RED")), ("ATOM", lambda o: o.startswith("ATOM")),
         ("BAR", lambda o: o.startswith("BAR")), ("SHFL", lambda o: o.startswith("SHFL")),
         ("UTMALDG", lambda o: o.startswith("UTMALDG")), ("UTMASTG", lambda o: o.startswith("UTMASTG")),
+        ("UBLKCP", lambda o: o.startswith("UBLKCP")),            # cp.async.bulk: K2's 64 KiB image stores
+        ("ST.dsmem", lambda o: o.startswith("ST.E")),            # st.shared::cluster through a mapa address (cluster kernel)
+        ("UCGABAR", lambda o: o.startswith("UCGABAR")),          # barrier.cluster arrive / wait
         ("HMMA/tcgen05", lambda o: o.startswith("HMMA") or o.startswith("UTC") or "MMA" in o)]
 import subprocess as sp
 def demangle(n):
