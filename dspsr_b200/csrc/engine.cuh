@@ -123,7 +123,9 @@ struct b200_fb_plan {
   float2* d_response_tiled;   // the response in the tile-image order of Z (fastpath.cu zi_pos), or null
   // one-kernel cluster path of 65536-point convolutions (clusterconv.cu)
   float2* c2cc;               // stage tables of its 4096-point row transforms, or null
-  int cc_clusters;            // clusters of 8 CTAs the device keeps resident (0 = path not available)
+  int cc_clusters;            // clusters of 16 CTAs the device keeps resident (0 = path not available)
+  void* cc_xch;               // exchange matrices of the global-memory variant of its two transposes, or null
+  void* cc_bar;               // arrival counters of the counter-barrier variant, or null
 };
 
 namespace b200 {
@@ -139,5 +141,7 @@ int fast_k3(b200_fb_plan* plan, const FbSink& sink, uint64_t part0, unsigned nb)
 int cc_plan_init(b200_fb_plan* plan);
 void cc_plan_free(b200_fb_plan* plan);
 bool cc_applies(const b200_fb_plan* plan, const FbSource& src, const FbSink& sink);
+// B200_OK, an error, or CC_NOT_RUN: the launch was refused for lack of residency and the path is now disabled
+enum { CC_NOT_RUN = 1000 };
 int cc_run(b200_fb_plan* plan, const FbSource& src, const FbSink& sink, uint64_t part0, unsigned nb);
 }

@@ -761,8 +761,8 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
       FbSink sk = sink;
       sk.bins = sink.bins + part0 * pl->nkeep;
       int rc = cc_run(pl, src, sk, part0, nb);
-      if (rc != B200_OK) return rc;
-      continue;
+      if (rc == B200_OK) continue;
+      if (rc != CC_NOT_RUN) return rc;
     }
     // a transform that fits one column pass (Q == 1) of complex input needs no row pass: K1 multiplies by the response
     // and writes Z (the row kernel would be P blocks of a handful of threads: 2.8 of 3.6 ms on the top UWL sub-bands)

@@ -463,13 +463,15 @@ def test_pipeline_cfg3_meerkat_convolution_fold(ctx, oracle):
 @pytest.mark.parametrize("fmt,nchan,npart,nblock,state,dndim,nbin", [
     ("meerkat", 5, 7, 1, "Stokes", 4, 257),       # 35 tiles: several per cluster, the channel changes inside a cluster's range
     ("meerkat", 3, 2, 2, "PPQQ", 1, 1024),        # two blocks into one PhaseSeries
+    ("meerkat", 4, 19, 1, "Intensity", 1, 64),    # 76 tiles: five per group, the software pipeline in steady state
     ("uwb", 1, 3, 1, "Intensity", 1, 64),         # 16-bit blocks of 2048 samples
     ("generic8", 2, 3, 1, "Coherence", 2, 128),   # TFP bytes through the 8-bit table, Coherence with ndim 2
 ])
 def test_cluster_convolution_kernel(ctx, oracle, fmt, nchan, npart, nblock, state, dndim, nbin):
-    """clusterconv.cu: 65536-point convolutions folded on the fly run as ONE kernel on clusters of 16 CTAs (distributed
-    shared memory exchanges).  Every source format it unpacks itself, every detection state, tile counts that do not
-    divide into the clusters, several blocks into one PhaseSeries -- against the oracle pipeline."""
+    """clusterconv.cu: 65536-point convolutions folded on the fly run as ONE kernel on groups of 16 co-resident CTAs
+    (exchanges through L2-resident matrices, counter barriers; -DCC_GROUP=0: hardware clusters + distributed shared
+    memory).  Every source format it unpacks itself, every detection state, tile counts that do not divide into the
+    groups, several tiles per group, several blocks into one PhaseSeries -- against the oracle pipeline."""
     L = _L()
     F, npos, nneg = 65536, 2536, 2543
     c = oracle.conv_sizes(0, nchan, 2, F, npos, nneg)
