@@ -1,5 +1,5 @@
-// clusterconv.cu -- the convolution path of 65536-point transforms (cfg3: MeerKAT, one coherent-dedispersion
-// transform per input channel) as ONE kernel: unpack -> forward FFT -> response -> inverse FFT -> discard -> detect ->
+// clusterconv.cu -- the convolution path of 16384- to 131072-point transforms (cfg3: 65536 points, MeerKAT, one
+// coherent-dedispersion transform per input channel) as ONE kernel: unpack -> forward FFT -> response -> inverse FFT -> discard -> detect ->
 // fold without a single spectrum round trip through HBM.
 //
 // dsp::Convolution::transformation (Convolution.C:389-458) per (channel, part): both polarisations, N = 65536
@@ -50,13 +50,16 @@
 
 namespace b200 {
 
-namespace cc {
-constexpr unsigned N = 65536, P = 16, Q = 4096, CL = 16, COLS = Q / CL, NT = 256;
-constexpr unsigned T = Q / 16;                       // threads per row pair
-constexpr unsigned PS = c2::pair_slots<Q>();         // float4 slots of one pair buffer (4352)
-constexpr size_t SMEM = size_t(PS) * sizeof(float4) + size_t(Q) * sizeof(float2);
-static_assert(PS == COLS * 16 + COLS, "the receive buffer of phase D (16 x 256 padded) is the pair buffer");
-}  // namespace cc
+// sizes of one transform length N = 16 Q (Q = 1024 ... 8192: N = 16384 ... 131072; cfg3: Q = 4096)
+template <unsigned QQ>
+struct Cc {
+  static constexpr unsigned Q = QQ, N = 16 * QQ, P = 16, CL = 16;
+  static constexpr unsigned NT = QQ / 16;              // threads per CTA = threads of the row pair = columns per CTA
+  static constexpr unsigned COLS = NT, T = NT;
+  static constexpr unsigned PS = c2::pair_slots<QQ>(); // float4 slots of the pair buffer
+  static constexpr size_t SMEM = size_t(PS) * sizeof(float4) + size_t(QQ) * sizeof(float2);
+  static_assert(PS == COLS * 16 + COLS, "the staging area of phase D (16 x NT padded) is the pair buffer");
+};
 
 struct CcArgs {
   const void* src;
@@ -149,14 +152,16 @@ __device__ __forceinline__ float2 cc_load(const CcArgs& a, const float* s_lut, u
   }
 }
 
-template <int SRC>
-__global__ void __launch_bounds__(256, 2) k_conv64k(CcArgs a) {
-  using namespace cc;
+template <int SRC, unsigned QQ>
+__global__ void __launch_bounds__(QQ / 16, 512 / (QQ / 16)) k_conv64k(CcArgs a) {
+  using C = Cc<QQ>;
+  constexpr unsigned Q = C::Q, N = C::N, CL = C::CL, NT = C::NT, COLS = C::COLS, T = C::T, PS = C::PS;
   extern __shared__ __align__(16) float4 buf[];                    // the pair buffer of the row transforms; phase D staging
   float2* Hs = reinterpret_cast<float2*>(buf + PS);                // response row k1 = rank: [Q]
-  __shared__ float2 s_tw[16];                                      // W_N^(-k1 256 e) of the CTA's row
+  __shared__ float2 s_tw[16];                                      // W_N^(-k1 NT e) of the CTA's row
   __shared__ float s_lut[SRC == SRC_GENERIC8 ? 256 : 1];
-  if (SRC == SRC_GENERIC8) s_lut[threadIdx.x] = a.lut[threadIdx.x];
+  if (SRC == SRC_GENERIC8)
+    for (unsigned i = threadIdx.x; i < 256; i += NT) s_lut[i] = a.lut[i];
   const unsigned tid = threadIdx.x;
 #if CC_GROUP
   const unsigned rank = blockIdx.x % CL, group = blockIdx.x / CL;  // rank = the row k1 this CTA owns
@@ -188,7 +193,7 @@ __global__ void __launch_bounds__(256, 2) k_conv64k(CcArgs a) {
   const unsigned rank = cluster_ctarank(), group = cluster_id_x(); // rank = the row k1 this CTA owns
   const unsigned sbuf = (unsigned)__cvta_generic_to_shared(buf);
 #endif
-  if (tid < 16) s_tw[tid] = big_twiddle<true>(a.blo, a.bhi, (rank * 256u * tid) & (N - 1));
+  if (tid < 16) s_tw[tid] = big_twiddle<true>(a.blo, a.bhi, (rank * NT * tid) & (N - 1));
   const float2 wown = big_twiddle<true>(a.blo, a.bhi, rank * tid); // W_N^(-k1 j)
   const unsigned n2 = COLS * rank + tid;                           // phases A / D: this thread's column
   const unsigned np0 = a.nfilt_pos, nkeep = a.nkeep;
@@ -251,13 +256,13 @@ __global__ void __launch_bounds__(256, 2) k_conv64k(CcArgs a) {
     }
   };
 
-  // ---- phase B: forward row, response, inverse row, times W_N^(-m2 k1); register e = element m2 = tid + 256 e ----
+  // ---- phase B: forward row, response, inverse row, times W_N^(-m2 k1); register e = element m2 = tid + NT e ----
   auto phase_b = [&](unsigned t, float2* va, float2* vb) {
 #if CC_GROUP
     const float4* X = XY + ((t - t_begin) & 1u) * (16u * Q) + rank * Q + tid;
 #pragma unroll
     for (int e = 0; e < 16; e++) {
-      const float4 x = ld_cg_f4(X + 256 * e);
+      const float4 x = ld_cg_f4(X + NT * e);
       va[e] = make_float2(x.x, x.y);
       vb[e] = make_float2(x.z, x.w);
     }
@@ -288,12 +293,12 @@ __global__ void __launch_bounds__(256, 2) k_conv64k(CcArgs a) {
   };
 
   // ---- phase D: inverse 16-point column transforms, detection, fold ----
-  // thread = 16 consecutive samples of segment m1 = tid / 16: transform index Q m1 + 256 rank + 16 (tid % 16) + i.
+  // thread = 16 consecutive samples of segment m1 = tid / (NT / 16): transform index Q m1 + NT rank + 16 (tid % (NT / 16)) + i.
   // `columns_ready` runs after the phase bins have been requested and before the columns are read; `reads_done` after
   // the last shared-memory read
   auto phase_d = [&](unsigned t, auto columns_ready, auto reads_done) {
     const unsigned ic = t / a.nb, partl = t % a.nb;
-    const unsigned seg = tid >> 4, b16 = tid & 15u;
+    const unsigned seg = tid / (NT / 16u), b16 = tid % (NT / 16u);
     const unsigned t0 = Q * seg + COLS * rank + 16u * b16;
     const unsigned* plan = a.sink.bins + uint64_t(partl) * nkeep;
     unsigned bins16[16];
@@ -376,7 +381,7 @@ __global__ void __launch_bounds__(256, 2) k_conv64k(CcArgs a) {
     {
       float4* Y = XY + (2u + ((t - t_begin) & 1u)) * (16u * Q) + rank * Q + tid;
 #pragma unroll
-      for (int e = 0; e < 16; e++) Y[256 * e] = make_float4(va[e].x, va[e].y, vb[e].x, vb[e].y);
+      for (int e = 0; e < 16; e++) Y[NT * e] = make_float4(va[e].x, va[e].y, vb[e].x, vb[e].y);
     }
     arrive(1);
     if (t + 1 < t_end) {
@@ -398,7 +403,7 @@ __global__ void __launch_bounds__(256, 2) k_conv64k(CcArgs a) {
     twiddle_back(va, vb);
     cluster_wait();                         // ... nor does any other: the pair buffers become receive buffers
     {
-      // element (k1, m2 = tid + 256 e) to the owner of column m2 (rank e)
+      // element (k1, m2 = tid + NT e) to the owner of column m2 (rank e)
       const unsigned slot = sbuf + c2::pad16(rank * COLS + tid) * 16u;
 #pragma unroll
       for (int e = 0; e < 16; e++)
@@ -414,32 +419,55 @@ __global__ void __launch_bounds__(256, 2) k_conv64k(CcArgs a) {
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-template <int SRC>
-static int cc_prepare(int* max_clusters) {
-  B200_CUDA(cudaFuncSetAttribute(k_conv64k<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cc::SMEM));
-  B200_CUDA(cudaFuncSetAttribute(k_conv64k<SRC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));   // clusters of 16
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cc::CL * 64);
-  cfg.blockDim = dim3(cc::NT);
-  cfg.dynamicSmemBytes = cc::SMEM;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = cc::CL;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
+template <int SRC, unsigned Q>
+static int cc_prepare(int* max_groups) {
+  using C = Cc<Q>;
+  B200_CUDA(cudaFuncSetAttribute(k_conv64k<SRC, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
   int n = 0;
 #if CC_GROUP
   int dev = 0, sms = 0, per_sm = 0;
   B200_CUDA(cudaGetDevice(&dev));
   B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_conv64k<SRC>, cc::NT, cc::SMEM));
-  n = per_sm * sms / int(cc::CL);
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_conv64k<SRC, Q>, C::NT, C::SMEM));
+  n = per_sm * sms / int(C::CL);
 #else
-  B200_CUDA(cudaOccupancyMaxActiveClusters(&n, k_conv64k<SRC>, &cfg));
+  B200_CUDA(cudaFuncSetAttribute(k_conv64k<SRC, Q>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));   // clusters of 16
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(C::CL * 64);
+  cfg.blockDim = dim3(C::NT);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = C::CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  B200_CUDA(cudaOccupancyMaxActiveClusters(&n, k_conv64k<SRC, Q>, &cfg));
 #endif
-  *max_clusters = n;
+  *max_groups = n;
+  return B200_OK;
+}
+
+template <unsigned Q>
+static int cc_init_q(b200_fb_plan* pl) {
+  using C = Cc<Q>;
+  if (size_t(pl->ctx->max_smem_optin) < C::SMEM + 1024) return B200_OK;
+  std::vector<float2> h(c2::twiddle_count<Q>(), make_float2(1.f, 0.f));
+  c2::fill_twiddles<Q>(h.data());
+  B200_CUDA(cudaMalloc(&pl->c2cc, sizeof(float2) * h.size()));
+  B200_CUDA(cudaMemcpy(pl->c2cc, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice));
+  int n0 = 0, n1 = 0, n2 = 0, n3 = 0, rc;
+  if ((rc = cc_prepare<SRC_F32, Q>(&n0)) != B200_OK) return rc;
+  if ((rc = cc_prepare<SRC_MEERKAT8, Q>(&n1)) != B200_OK) return rc;
+  if ((rc = cc_prepare<SRC_UWB16, Q>(&n2)) != B200_OK) return rc;
+  if ((rc = cc_prepare<SRC_GENERIC8, Q>(&n3)) != B200_OK) return rc;
+  pl->cc_clusters = std::min(std::min(n0, n1), std::min(n2, n3));
+  if (CC_GROUP && pl->cc_clusters > 0) {
+    // four exchange matrices of 16 Q float4 and two arrival counters (each on its own 128-byte line) per group
+    B200_CUDA(cudaMalloc(&pl->cc_xch, size_t(pl->cc_clusters) * 4 * 16 * Q * sizeof(float4)));
+    B200_CUDA(cudaMalloc(&pl->cc_bar, size_t(pl->cc_clusters) * 64 * sizeof(unsigned)));
+  }
   return B200_OK;
 }
 
@@ -449,26 +477,14 @@ int cc_plan_init(b200_fb_plan* pl) {
   pl->cc_bar = nullptr;
   pl->cc_clusters = 0;
   static const bool want = tune_flag("B200_CLUSTER_CONV", true);
-  if (!want || !pl->conv_path || pl->Nc != cc::N || pl->desc.input_real || pl->desc.npol != 2) return B200_OK;
-  if (size_t(pl->ctx->max_smem_optin) < 2 * (cc::SMEM + 1024)) return B200_OK;
-  std::vector<float2> h(c2::twiddle_count<cc::Q>(), make_float2(1.f, 0.f));
-  c2::fill_twiddles<cc::Q>(h.data());
-  B200_CUDA(cudaMalloc(&pl->c2cc, sizeof(float2) * h.size()));
-  B200_CUDA(cudaMemcpy(pl->c2cc, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice));
-  int n0 = 0, n1 = 0, n2 = 0, n3 = 0, rc;
-  if ((rc = cc_prepare<SRC_F32>(&n0)) != B200_OK) return rc;
-  if ((rc = cc_prepare<SRC_MEERKAT8>(&n1)) != B200_OK) return rc;
-  if ((rc = cc_prepare<SRC_UWB16>(&n2)) != B200_OK) return rc;
-  if ((rc = cc_prepare<SRC_GENERIC8>(&n3)) != B200_OK) return rc;
-  pl->cc_clusters = std::min(std::min(n0, n1), std::min(n2, n3));
-  pl->cc_xch = nullptr;
-  pl->cc_bar = nullptr;
-  if (CC_GROUP && pl->cc_clusters > 0) {
-    // four 1 MiB exchange matrices and two arrival counters (each on its own 128-byte line) per group
-    B200_CUDA(cudaMalloc(&pl->cc_xch, size_t(pl->cc_clusters) * 4 * 16 * cc::Q * sizeof(float4)));
-    B200_CUDA(cudaMalloc(&pl->cc_bar, size_t(pl->cc_clusters) * 64 * sizeof(unsigned)));
+  if (!want || !pl->conv_path || pl->desc.input_real || pl->desc.npol != 2) return B200_OK;
+  switch (pl->Nc) {
+    case 16 * 1024: return cc_init_q<1024>(pl);
+    case 16 * 2048: return cc_init_q<2048>(pl);
+    case 16 * 4096: return cc_init_q<4096>(pl);
+    case 16 * 8192: return cc_init_q<8192>(pl);
+    default: return B200_OK;
   }
-  return B200_OK;
 }
 
 void cc_plan_free(b200_fb_plan* pl) {
@@ -486,23 +502,17 @@ bool cc_applies(const b200_fb_plan* pl, const FbSource& src, const FbSink& sink)
           (src.kind == SRC_GENERIC8 && src.ndim == 2));
 }
 
-int cc_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sk, uint64_t part0, unsigned nb) {
+template <unsigned Q>
+static int cc_launch(b200_fb_plan* pl, const FbSource& src, CcArgs& a) {
+  using C = Cc<Q>;
   Context* ctx = pl->ctx;
-  CcArgs a;
-  a.src = src.ptr; a.span = src.span; a.step = src.step; a.first = src.first; a.scale = src.scale; a.sample_swap = src.sample_swap;
-  a.lut = src.d_lut;
-  a.H = pl->d_response; a.tw = pl->c2cc; a.blo = pl->bigN.lo; a.bhi = pl->bigN.hi;
-  a.nchan_in = pl->desc.input_nchan; a.nb = nb; a.ntiles = nb * pl->desc.input_nchan;
-  a.xch = static_cast<float4*>(pl->cc_xch);
-  a.bar = static_cast<unsigned*>(pl->cc_bar);
-  a.part0 = part0; a.nfilt_pos = pl->desc.nfilt_pos; a.nkeep = pl->nkeep; a.sink = sk;
   const unsigned ncl = std::min<unsigned>(a.ntiles, (unsigned)pl->cc_clusters);
   a.tiles_per_cluster = (a.ntiles + ncl - 1) / ncl;
   const unsigned used = (a.ntiles + a.tiles_per_cluster - 1) / a.tiles_per_cluster;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cc::CL * used);
-  cfg.blockDim = dim3(cc::NT);
-  cfg.dynamicSmemBytes = cc::SMEM;
+  cfg.gridDim = dim3(C::CL * used);
+  cfg.blockDim = dim3(C::NT);
+  cfg.dynamicSmemBytes = C::SMEM;
   cfg.stream = ctx->stream;
   cudaLaunchAttribute at[1];
 #if CC_GROUP
@@ -511,7 +521,7 @@ int cc_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sk, uint64_t par
   B200_CUDA(cudaMemsetAsync(pl->cc_bar, 0, size_t(pl->cc_clusters) * 64 * sizeof(unsigned), ctx->stream));
 #else
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = cc::CL;
+  at[0].val.clusterDim.x = C::CL;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
 #endif
@@ -520,10 +530,10 @@ int cc_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sk, uint64_t par
   cudaError_t e;
   {
     LaunchScope ls(ctx, KC_INV);
-    if (src.kind == SRC_F32) e = cudaLaunchKernelEx(&cfg, k_conv64k<SRC_F32>, a);
-    else if (src.kind == SRC_MEERKAT8) e = cudaLaunchKernelEx(&cfg, k_conv64k<SRC_MEERKAT8>, a);
-    else if (src.kind == SRC_GENERIC8) e = cudaLaunchKernelEx(&cfg, k_conv64k<SRC_GENERIC8>, a);
-    else e = cudaLaunchKernelEx(&cfg, k_conv64k<SRC_UWB16>, a);
+    if (src.kind == SRC_F32) e = cudaLaunchKernelEx(&cfg, k_conv64k<SRC_F32, Q>, a);
+    else if (src.kind == SRC_MEERKAT8) e = cudaLaunchKernelEx(&cfg, k_conv64k<SRC_MEERKAT8, Q>, a);
+    else if (src.kind == SRC_GENERIC8) e = cudaLaunchKernelEx(&cfg, k_conv64k<SRC_GENERIC8, Q>, a);
+    else e = cudaLaunchKernelEx(&cfg, k_conv64k<SRC_UWB16, Q>, a);
   }
   if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
     // the device cannot keep the whole grid resident right now (shared with another context): nothing was launched;
@@ -534,6 +544,23 @@ int cc_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sk, uint64_t par
   }
   B200_CUDA(e);
   return B200_OK;
+}
+
+int cc_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sk, uint64_t part0, unsigned nb) {
+  CcArgs a;
+  a.src = src.ptr; a.span = src.span; a.step = src.step; a.first = src.first; a.scale = src.scale; a.sample_swap = src.sample_swap;
+  a.lut = src.d_lut;
+  a.H = pl->d_response; a.tw = pl->c2cc; a.blo = pl->bigN.lo; a.bhi = pl->bigN.hi;
+  a.nchan_in = pl->desc.input_nchan; a.nb = nb; a.ntiles = nb * pl->desc.input_nchan;
+  a.xch = static_cast<float4*>(pl->cc_xch);
+  a.bar = static_cast<unsigned*>(pl->cc_bar);
+  a.part0 = part0; a.nfilt_pos = pl->desc.nfilt_pos; a.nkeep = pl->nkeep; a.sink = sk;
+  switch (pl->Nc) {
+    case 16 * 1024: return cc_launch<1024>(pl, src, a);
+    case 16 * 2048: return cc_launch<2048>(pl, src, a);
+    case 16 * 4096: return cc_launch<4096>(pl, src, a);
+    default: return cc_launch<8192>(pl, src, a);
+  }
 }
 
 }  // namespace b200

@@ -498,6 +498,23 @@ def test_cluster_convolution_kernel(ctx, oracle, fmt, nchan, npart, nblock, stat
     assert err <= TOL, err
 
 
+@pytest.mark.parametrize("F,npos,nneg,nchan,npart", [(16384, 700, 650, 3, 30), (32768, 1200, 1300, 2, 21),
+                                                       (131072, 5000, 5100, 2, 3), (131072, 0, 9000, 1, 41)])
+def test_one_kernel_convolution_other_lengths(ctx, oracle, F, npos, nneg, nchan, npart):
+    """clusterconv.cu is instantiated for N = 16 Q, Q = 1024 ... 8192: every length, with tile counts that leave one
+    (131072: 18 groups) or several tiles per group, MeerKAT input, Coherence, against the oracle pipeline."""
+    L = _L()
+    c = oracle.conv_sizes(0, nchan, 2, F, npos, nneg)
+    ndat = (npart * c.nsamp_step + c.nsamp_overlap + 255) // 256 * 256
+    raw = synth.meerkat_bytes(ndat, nchan, 2, seed=90 + nchan)
+    _, scale = oracle.bittable8()
+    rng = np.random.default_rng(F)
+    H = np.exp(1j * rng.uniform(-np.pi, np.pi, (nchan, F))).astype(np.complex64)
+    err = _pipe_generic(ctx, oracle, L.FMT_MEERKAT8, nchan, 2, 2, raw, ndat, None, c, H, 1, F, npos, nneg, npart,
+                        "Coherence", 4, 512, scale=np.float32(scale))
+    assert err <= TOL, err
+
+
 def test_pipeline_4096_input_channels_grid_limit(ctx, oracle):
     """4096 input channels x 2 polarisations = 8192 (channel, pol) blocks per part; with the default
     16 parts per launch the generic kernels' grid.y would be 131072 (> 65535).  The plan caps the batch; 20 parts
