@@ -115,6 +115,12 @@ __device__ __forceinline__ float4 ld_cg_f4(const float4* p) {
   return r;
 }
 
+// The 128-byte line at p is dead: drop it from L2 without writing it back (the exchange matrices are rewritten every
+// other tile; without this their dirty lines are evicted to DRAM by the raw-data stream long before that)
+__device__ __forceinline__ void l2_discard(const void* p) {
+  asm volatile("discard.global.L2 [%0], 128;" :: "l"(p) : "memory");
+}
+
 struct CcSync {
   __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
@@ -271,6 +277,14 @@ __global__ void __launch_bounds__(QQ / 16, 512 / (QQ / 16)) k_conv64k(CcArgs a) 
     __syncthreads();
 #endif
     if (!(CC_DBG & 2)) c2::fft_pair<Q, false>(va, vb, tid, buf, a.tw, CcSync());
+#if CC_GROUP
+    // the row has been read (every lane's loads were consumed before the barriers of the transform): its lines are
+    // dead -- a line is the 8 consecutive float4 of 8 consecutive threads, read by nobody else
+    if ((tid & 7u) == 0) {
+#pragma unroll
+      for (int e = 0; e < 16; e++) l2_discard(X + NT * e);
+    }
+#endif
     if (a.H) {
       const float2* h = Hs + tid;
 #pragma unroll
@@ -325,6 +339,13 @@ __global__ void __launch_bounds__(QQ / 16, 512 / (QQ / 16)) k_conv64k(CcArgs a) 
       }
       dft16<true>(yp);
       dft16<true>(yq);
+#if CC_GROUP
+      __syncwarp();                         // every lane's column loads have been consumed
+      if ((tid & 7u) == 0) {
+#pragma unroll
+        for (int k1 = 0; k1 < 16; k1++) l2_discard(Y + unsigned(k1) * Q);
+      }
+#endif
 #pragma unroll
       for (int m1 = 0; m1 < 16; m1++) {
         float r[4] = {0.f, 0.f, 0.f, 0.f};

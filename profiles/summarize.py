@@ -50,8 +50,10 @@ def main():
             if k in d and d[k] != "":
                 print("  %-34s %14s %s" % (label, d[k], u[k]))
         try:
-            tr = float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"])
-            print("  %-34s %14.3f %s" % ("DRAM traffic (read+write)", tr, u["dram__bytes_read.sum"]))
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+            tr = (float(d["dram__bytes_read.sum"]) * scale[u["dram__bytes_read.sum"]] +
+                  float(d["dram__bytes_write.sum"]) * scale[u["dram__bytes_write.sum"]])
+            print("  %-34s %14.3f %s" % ("DRAM traffic (read+write)", tr / 1e9, "Gbyte"))
         except (KeyError, ValueError):
             pass
 
