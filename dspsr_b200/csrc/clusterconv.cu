@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(QQ / 16, 512 / (QQ / 16)) k_conv64k(CcArgs a) 
   const unsigned n2 = COLS * rank + tid;                           // phases A / D: this thread's column
   const unsigned np0 = a.nfilt_pos, nkeep = a.nkeep;
   const int state = a.sink.state;
-  const unsigned nprod = state_nprod(state, 2), dndim = a.sink.dndim, nbin = a.sink.nbin;
+  const unsigned nprod = a.sink.kind == EPI_VOLT ? 1 : state_nprod(state, 2), dndim = a.sink.kind == EPI_VOLT ? 1 : a.sink.dndim;
+  const unsigned nbin = a.sink.nbin;
   const unsigned t_begin = group * a.tiles_per_cluster;
   const unsigned t_end = min(a.ntiles, t_begin + a.tiles_per_cluster);
   unsigned cur_ic = 0xffffffffu;
@@ -314,12 +315,13 @@ __global__ void __launch_bounds__(QQ / 16, 512 / (QQ / 16)) k_conv64k(CcArgs a) 
     const unsigned ic = t / a.nb, partl = t % a.nb;
     const unsigned seg = tid / (NT / 16u), b16 = tid % (NT / 16u);
     const unsigned t0 = Q * seg + COLS * rank + 16u * b16;
+    const bool folding = a.sink.kind == EPI_FOLD;         // uniform over the grid
     const unsigned* plan = a.sink.bins + uint64_t(partl) * nkeep;
     unsigned bins16[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) {
       const unsigned u = t0 + unsigned(i) - np0;          // unsigned: samples before nfilt_pos wrap to huge values
-      bins16[i] = u < nkeep ? __ldg(plan + u) : 0xfffffffeu;
+      bins16[i] = (folding && u < nkeep) ? __ldg(plan + u) : 0xfffffffeu;
     }
     columns_ready();
     {
@@ -346,6 +348,38 @@ __global__ void __launch_bounds__(QQ / 16, 512 / (QQ / 16)) k_conv64k(CcArgs a) 
         for (int k1 = 0; k1 < 16; k1++) l2_discard(Y + unsigned(k1) * Q);
       }
 #endif
+      if (!folding) {
+        // voltages (Convolution::Engine::perform) or the detected series: this thread's 16 samples are Q apart, the
+        // threads of a warp write 32 consecutive samples of a plane
+        const uint64_t part = a.part0 + partl;
+        if (a.sink.kind == EPI_VOLT) {
+          float2* outp = reinterpret_cast<float2*>(a.sink.volt + (uint64_t(ic) * 2) * a.sink.volt_span + part * a.sink.volt_step);
+          float2* outq = reinterpret_cast<float2*>(a.sink.volt + (uint64_t(ic) * 2 + 1) * a.sink.volt_span + part * a.sink.volt_step);
+#pragma unroll
+          for (int m1 = 0; m1 < 16; m1++) {
+            const unsigned u = Q * unsigned(m1) + n2 - np0;
+            if (u < nkeep) {
+              outp[u] = yp[m1];
+              outq[u] = yq[m1];
+            }
+          }
+        } else {
+          const unsigned dnpol = nprod / dndim;
+#pragma unroll
+          for (int m1 = 0; m1 < 16; m1++) {
+            const unsigned u = Q * unsigned(m1) + n2 - np0;
+            if (u < nkeep) {
+              float r[4] = {0.f, 0.f, 0.f, 0.f};
+              detect_products(state, yp[m1], yq[m1], r);
+              const uint64_t osamp = part * nkeep + u;
+              for (unsigned pr = 0; pr < nprod; pr++)
+                a.sink.det[(uint64_t(ic) * dnpol + pr / dndim) * a.sink.det_span + osamp * dndim + pr % dndim] = r[pr];
+            }
+          }
+        }
+        reads_done();
+        return;
+      }
 #pragma unroll
       for (int m1 = 0; m1 < 16; m1++) {
         float r[4] = {0.f, 0.f, 0.f, 0.f};
@@ -518,7 +552,7 @@ void cc_plan_free(b200_fb_plan* pl) {
 }
 
 bool cc_applies(const b200_fb_plan* pl, const FbSource& src, const FbSink& sink) {
-  return pl->cc_clusters > 0 && pl->c2cc && sink.kind == EPI_FOLD &&
+  return pl->cc_clusters > 0 && pl->c2cc &&
          (src.kind == SRC_F32 || src.kind == SRC_MEERKAT8 || src.kind == SRC_UWB16 ||
           (src.kind == SRC_GENERIC8 && src.ndim == 2));
 }

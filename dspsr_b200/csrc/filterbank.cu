@@ -756,10 +756,10 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
   for (uint64_t part0 = 0; part0 < npart; part0 += batch) {
     const unsigned nb = (unsigned)std::min<uint64_t>(batch, npart - part0);
     if (src.batch_ready) B200_CUDA(cudaStreamWaitEvent(st, src.batch_ready[part0 / batch], 0));
-    // 65536-point convolutions folded on the fly: one cluster kernel, no spectrum scratch (clusterconv.cu)
+    // 16384- to 131072-point convolutions: one kernel for the whole transform pair and its epilogue (clusterconv.cu)
     if (cc_applies(pl, src, sink)) {
       FbSink sk = sink;
-      sk.bins = sink.bins + part0 * pl->nkeep;
+      if (sk.kind == EPI_FOLD) sk.bins = sink.bins + part0 * pl->nkeep;
       int rc = cc_run(pl, src, sk, part0, nb);
       if (rc == B200_OK) continue;
       if (rc != CC_NOT_RUN) return rc;

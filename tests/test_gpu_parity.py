@@ -144,7 +144,9 @@ def test_filterbank_cfg1_shape(ctx, oracle):
     (0, 4, 2, 1, 4096, 100, 101, 3),     # complex multi-channel (cfg3-like, small)
     (0, 1, 2, 1, 16384, 500, 501, 3),    # two-pass inverse (convolution path)
     (1, 1, 2, 1, 32768, 900, 901, 2),    # real + two-pass inverse
-    (0, 2, 2, 1, 65536, 2536, 2543, 2),  # cfg3's per-channel transform
+    (0, 2, 2, 1, 65536, 2536, 2543, 2),  # cfg3's per-channel transform (one-kernel path, voltage sink)
+    (0, 3, 2, 1, 32768, 1000, 1001, 9),  # one-kernel path, several tiles per group
+    (0, 1, 2, 1, 131072, 4000, 4001, 2), # one-kernel path, 8192-point rows
 ])
 def test_convolution_voltages(ctx, oracle, case):
     torch, E = _torch(), _E()
@@ -513,6 +515,29 @@ def test_one_kernel_convolution_other_lengths(ctx, oracle, F, npos, nneg, nchan,
     err = _pipe_generic(ctx, oracle, L.FMT_MEERKAT8, nchan, 2, 2, raw, ndat, None, c, H, 1, F, npos, nneg, npart,
                         "Coherence", 4, 512, scale=np.float32(scale))
     assert err <= TOL, err
+
+
+@pytest.mark.parametrize("state,dndim,F", [("Stokes", 4, 65536), ("Intensity", 1, 16384), ("Coherence", 2, 32768)])
+def test_one_kernel_convolution_detected_series(ctx, oracle, state, dndim, F):
+    """The detected-series sink (no fold: digifil with coherent dedispersion) of the one-kernel convolution path: UWB /
+    MeerKAT bytes in, detected planes out, against the oracle chain."""
+    torch, E, L = _torch(), _E(), _L()
+    nchan, npart = 2, 5
+    npos, nneg = F // 30, F // 29
+    c = oracle.conv_sizes(0, nchan, 2, F, npos, nneg)
+    ndat = (npart * c.nsamp_step + c.nsamp_overlap + 255) // 256 * 256
+    raw = synth.meerkat_bytes(ndat, nchan, 2, seed=95)
+    _, scale = oracle.bittable8()
+    rng = np.random.default_rng(96)
+    H = np.exp(1j * rng.uniform(-np.pi, np.pi, (nchan, F))).astype(np.complex64)
+    op = oracle.make_pipe(L.FMT_MEERKAT8, nchan, 2, 2, None, np.float32(scale), None, c, H, state, dndim, 0)
+    ref = oracle.pipe_block_detected(op, raw, 0, npart)
+    ud = E.make_unpack_desc(L.FMT_MEERKAT8, nchan, 2, 2, None, np.float32(scale), 1)
+    fd, keep = E.make_fb_desc(False, nchan, 2, 1, F, npos, nneg, H)
+    pipe = E.Pipeline(ctx, ud, fd, keep, state, dndim, 0)
+    det = pipe.execute(torch.from_numpy(raw).cuda(), npart, 0.0, 0.0, first_sample=0).cpu().numpy()
+    assert det.shape == ref.shape
+    assert np.array_equal(det, ref) or synth.relerr(det, ref) <= TOL
 
 
 def test_pipeline_4096_input_channels_grid_limit(ctx, oracle):
