@@ -217,10 +217,27 @@ __global__ void __launch_bounds__(QQ / 16, 512 / (QQ / 16)) k_conv64k(CcArgs a) 
     const unsigned ic = t / a.nb;
     const uint64_t part = a.part0 + t % a.nb;
     float2 xp[16], xq[16];
+    if (SRC == SRC_MEERKAT8) {
+      // heaps of 256 samples, [heap][pol][chan][256 x (re, im) int8] (MeerKATUnpacker.C:196-229): the 16 samples of a
+      // column are Q = (Q / 256) heaps apart, so one address computation serves all of them
+      uint64_t i = a.first + part * a.step + n2;
+      if (a.sample_swap == 2) i ^= 1ull;
+      const unsigned short* w0 = static_cast<const unsigned short*>(a.src) + ((i >> 8) * 2 * a.nchan_in + ic) * 256ull + (i & 255ull);
+      const uint64_t dheap = uint64_t(Q / 256u) * 2u * a.nchan_in * 256u, dpol = uint64_t(a.nchan_in) * 256u;
 #pragma unroll
-    for (int n1 = 0; n1 < 16; n1++) {
-      xp[n1] = cc_load<SRC>(a, s_lut, ic, 0, part, n2 + Q * n1);
-      xq[n1] = cc_load<SRC>(a, s_lut, ic, 1, part, n2 + Q * n1);
+      for (int n1 = 0; n1 < 16; n1++) {
+        const unsigned short wp = __ldg(w0 + n1 * dheap), wq = __ldg(w0 + n1 * dheap + dpol);
+        xp[n1] = make_float2(__fmul_rn(float(int(int8_t(wp & 255u))) + 0.5f, a.scale),
+                             __fmul_rn(float(int(int8_t(wp >> 8))) + 0.5f, a.scale));
+        xq[n1] = make_float2(__fmul_rn(float(int(int8_t(wq & 255u))) + 0.5f, a.scale),
+                             __fmul_rn(float(int(int8_t(wq >> 8))) + 0.5f, a.scale));
+      }
+    } else {
+#pragma unroll
+      for (int n1 = 0; n1 < 16; n1++) {
+        xp[n1] = cc_load<SRC>(a, s_lut, ic, 0, part, n2 + Q * n1);
+        xq[n1] = cc_load<SRC>(a, s_lut, ic, 1, part, n2 + Q * n1);
+      }
     }
     // W_N^(n2 k1), k1 < 16: four table values (k1 = 1, 2, 4, 8), the others as products over the bits of k1
     float2 w[4];
@@ -277,26 +294,43 @@ __global__ void __launch_bounds__(QQ / 16, 512 / (QQ / 16)) k_conv64k(CcArgs a) 
     c2::gather<Q>(buf, va, vb, tid);
     __syncthreads();
 #endif
-    if (!(CC_DBG & 2)) c2::fft_pair<Q, false>(va, vb, tid, buf, a.tw, CcSync());
-#if CC_GROUP
-    // the row has been read (every lane's loads were consumed before the barriers of the transform): its lines are
-    // dead -- a line is the 8 consecutive float4 of 8 consecutive threads, read by nobody else
-    if ((tid & 7u) == 0) {
+    // Both row transforms run through ONE copy of the forward code (the kernel is instruction-cache bound: two CTAs in
+    // different phases share an SM): the inverse is conj(FFT(conj z)), which is the same IEEE operations as the
+    // conjugate-twiddle inverse with the signs of the imaginary parts flipped -- bit-identical results.
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+      if (pass) {
+        if (a.H) {
+          const float2* h = Hs + tid;
 #pragma unroll
-      for (int e = 0; e < 16; e++) l2_discard(X + NT * e);
-    }
-#endif
-    if (a.H) {
-      const float2* h = Hs + tid;
+          for (int e = 0; e < 16; e++) {
+            const float2 hv = h[e * int(T)];
+            va[e] = cmul(va[e], hv);
+            vb[e] = cmul(vb[e], hv);
+          }
+        }
 #pragma unroll
-      for (int e = 0; e < 16; e++) {
-        const float2 hv = h[e * int(T)];
-        va[e] = cmul(va[e], hv);
-        vb[e] = cmul(vb[e], hv);
+        for (int e = 0; e < 16; e++) {
+          va[e].y = -va[e].y;
+          vb[e].y = -vb[e].y;
+        }
+        __syncthreads();                    // every thread has gathered the last stage of the forward transform
       }
+      if (!(CC_DBG & 2)) c2::fft_pair<Q, false>(va, vb, tid, buf, a.tw, CcSync());
+#if CC_GROUP
+      // the row has been read (every lane's loads were consumed before the barriers of the transform): its lines are
+      // dead -- a line is the 8 consecutive float4 of 8 consecutive threads, read by nobody else
+      if (!pass && (tid & 7u) == 0) {
+#pragma unroll
+        for (int e = 0; e < 16; e++) l2_discard(X + NT * e);
+      }
+#endif
     }
-    __syncthreads();                        // every thread has gathered the last stage of the forward transform
-    if (!(CC_DBG & 2)) c2::fft_pair<Q, true>(va, vb, tid, buf, a.tw, CcSync());
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+      va[e].y = -va[e].y;
+      vb[e].y = -vb[e].y;
+    }
   };
   auto twiddle_back = [&](float2* va, float2* vb) {
 #pragma unroll
@@ -317,12 +351,6 @@ __global__ void __launch_bounds__(QQ / 16, 512 / (QQ / 16)) k_conv64k(CcArgs a) 
     const unsigned t0 = Q * seg + COLS * rank + 16u * b16;
     const bool folding = a.sink.kind == EPI_FOLD;         // uniform over the grid
     const unsigned* plan = a.sink.bins + uint64_t(partl) * nkeep;
-    unsigned bins16[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-      const unsigned u = t0 + unsigned(i) - np0;          // unsigned: samples before nfilt_pos wrap to huge values
-      bins16[i] = (folding && u < nkeep) ? __ldg(plan + u) : 0xfffffffeu;
-    }
     columns_ready();
     {
       float2 yp[16], yq[16];
@@ -388,34 +416,39 @@ __global__ void __launch_bounds__(QQ / 16, 512 / (QQ / 16)) k_conv64k(CcArgs a) 
       }
     }
     __syncthreads();
+    // one rolled loop (the kernel is instruction-cache bound): this thread's 16 samples are consecutive slots of the
+    // padded staging area, their phase bins 64 consecutive bytes of the bin plan (L1 after the first look)
     const float4* d = buf + c2::pad16(seg * COLS + 16u * b16);
-    float4 x[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) x[i] = d[i];
-    reads_done();
+    // profile element of product pr and bin b: prof0 + (pr / dndim * nbin + b) * dndim + pr % dndim = off[pr] + b * dndim
     const uint64_t prof0 = uint64_t(ic) * nbin * nprod;
+    uint64_t off[4];
+#pragma unroll
+    for (unsigned pr = 0; pr < 4; pr++) off[pr] = prof0 + uint64_t(pr / dndim) * nbin * dndim + pr % dndim;
     unsigned cur = 0xffffffffu;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    auto flush = [&]() {
-      if (cur < nbin)                                     // nbin: samples of a flagged window; 0xffffffff: nothing yet
-        for (unsigned pr = 0; pr < nprod; pr++)
-          profile_add(a.sink.profile, a.sink.fix, a.sink.inv_lsb, prof0 + (uint64_t(pr / dndim) * nbin + cur) * dndim + pr % dndim,
-                      acc[pr]);
-    };
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-      const unsigned bin = bins16[i];
-      if ((CC_DBG & 1) && x[i].x != 12345.678f) continue;
-      if (bin == 0xfffffffeu) continue;                   // discarded by overlap-save
+#pragma unroll 1
+    for (unsigned i = 0; i <= 16u; i++) {
+      const unsigned u = t0 + i - np0;                    // unsigned: samples before nfilt_pos wrap to huge values
+      // i = 16: flush the last run;  nbin: samples of a flagged window;  0xfffffffe: discarded by overlap-save
+      const unsigned bin = i == 16u ? 0xffffffffu : (u < nkeep ? __ldg(plan + u) : 0xfffffffeu);
+      if ((CC_DBG & 1) && bin != 12345678u) continue;
+      if (bin == 0xfffffffeu) continue;
       if (bin != cur) {
-        flush();
+        if (cur < nbin) {
+#pragma unroll
+          for (unsigned pr = 0; pr < 4; pr++)
+            if (pr < nprod) profile_add(a.sink.profile, a.sink.fix, a.sink.inv_lsb, off[pr] + uint64_t(cur) * dndim, acc[pr]);
+        }
+        if (i == 16u) break;
         cur = bin;
-        acc[0] = x[i].x; acc[1] = x[i].y; acc[2] = x[i].z; acc[3] = x[i].w;
+        const float4 x = d[i];
+        acc[0] = x.x; acc[1] = x.y; acc[2] = x.z; acc[3] = x.w;
       } else {
-        acc[0] += x[i].x; acc[1] += x[i].y; acc[2] += x[i].z; acc[3] += x[i].w;
+        const float4 x = d[i];
+        acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
       }
     }
-    flush();
+    reads_done();
   };
   auto nothing = [] {};
 
