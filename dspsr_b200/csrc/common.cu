@@ -128,6 +128,8 @@ int b200_context_create(int device, void* cuda_stream, b200_context** out) {
   }
   B200_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
   B200_CUDA(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  c->d_tables = nullptr;
+  B200_CUDA(cudaMalloc(&c->d_tables, 8192));
   *out = c;
   return B200_OK;
 }
@@ -137,6 +139,7 @@ int b200_context_destroy(b200_context* c) {
   if (c->own_stream) cudaStreamDestroy(c->stream);
   for (auto& t : *c->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
   delete c->timed;
+  if (c->d_tables) cudaFree(c->d_tables);
   delete c;
   return B200_OK;
 }

@@ -60,6 +60,9 @@ struct Context {
   unsigned long long launches;   // kernels launched through this context (bench's gpu_launches)
   bool timing;
   std::vector<TimedLaunch>* timed;
+  // 8 KiB of device memory owned by the context for the small tables that travel with stand-alone calls (the 256-entry
+  // table of b200_unpack, the 2 x 513 levels of b200_unpack_twobit): execute-type calls never allocate
+  float* d_tables;
 };
 
 // RAII helper: brackets one kernel launch with events when timing is on, and counts it

@@ -5,7 +5,7 @@
 
 namespace b200 {
 
-enum SrcKind { SRC_F32 = 0, SRC_CASPSR8 = 1, SRC_MEERKAT8 = 2, SRC_UWB16 = 3, SRC_GENERIC8 = 4 };
+enum SrcKind { SRC_F32 = 0, SRC_CASPSR8 = 1, SRC_MEERKAT8 = 2, SRC_UWB16 = 3, SRC_GENERIC8 = 4, SRC_TWOBIT = 5 };
 enum Epilogue { EPI_VOLT = 0, EPI_DETECT = 1, EPI_FOLD = 2 };
 
 // where the forward transform reads its samples
@@ -27,6 +27,10 @@ struct FbSource {
   float scale;              // MeerKAT: (float(x) + 0.5) * scale
   unsigned sample_swap;     // MeerKAT: 2 = odd/even samples exchanged (MKBFRo)
   unsigned ndim;            // generic 8-bit: 1 real, 2 complex
+  // two-bit (CPSR2 convention, real input) unpacked inside the generic K1: per-window level pairs (fold.cu
+  // k_twobit_windows), [window][npol] from the 512-sample boundary at ptr; which codes are low / negative
+  const float2* win;
+  unsigned lowsel, negsel;
 };
 
 // Tries to express a 256-entry 8-bit table as the float evaluation fmaf(x, hi, x*lo); returns 1 and the
@@ -131,6 +135,9 @@ struct b200_fb_plan {
 namespace b200 {
 // Runs the engine over npart parts: source -> (K1, K2, K3) -> sink.
 int fb_run(b200_fb_plan* plan, const FbSource& src, const FbSink& sink, uint64_t npart);
+// fold.cu
+int twobit_windows(Context* ctx, const b200_twobit_desc* d, const void* d_raw, uint64_t nwindow, float2* d_win,
+                   unsigned* d_weights, unsigned* lowsel, unsigned* negsel);
 // fastpath.cu
 int fast_plan_init(b200_fb_plan* plan);
 void fast_plan_free(b200_fb_plan* plan);

@@ -62,6 +62,8 @@ struct ColsArgs {
   unsigned sample_swap, ndim;
   const float2* H;          // Q == 1, complex input: the column pass IS the whole transform -- the response is
                             // applied here and the result goes straight to Z (no row pass)
+  const float2* win;        // SRC_TWOBIT: (lo, hi) of every 512-sample window and digitizer
+  unsigned lowsel, negsel;
 };
 
 template <int SRC, int EPT, unsigned PCT>
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__((PCT && EPT == 32) ? 512 : 1024, 1) k_cols_fwd
   else {
     raw = static_cast<const unsigned char*>(a.src);
     // element n = Q*n1 + n2 of the part is the sample pair (2n, 2n+1) of a real stream, sample n of a complex one
-    const bool real_in = (SRC == SRC_CASPSR8) || (SRC == SRC_GENERIC8 && a.ndim == 1);
+    const bool real_in = (SRC == SRC_CASPSR8) || (SRC == SRC_TWOBIT) || (SRC == SRC_GENERIC8 && a.ndim == 1);
     samp0 = a.first + part * a.step + (real_in ? 2ull * n2 : uint64_t(n2));
   }
   MapCols map{b, a.lb, SwzShift<EPT>::value};
@@ -123,6 +125,17 @@ __global__ void __launch_bounds__((PCT && EPT == 32) ? 512 : 1024, 1) k_cols_fwd
       const uint64_t word = ((i >> 11) * a.npol + pol) * 2048ull + (i & 2047ull);
       const unsigned w = __ldg(reinterpret_cast<const unsigned*>(raw) + word);
       return make_float2(float(short((w & 0xffffu) ^ 0x8000u)), float(short((w >> 16) ^ 0x8000u)));
+    } else if (SRC == SRC_TWOBIT) {
+      // CPSR2 convention: four samples per byte, most significant first, digitizers interleaved byte by byte
+      // (ExcisionUnpacker.C:258-266, BitTable.C:154-163); samples 2n, 2n+1 share a byte; the output levels of the
+      // 512-sample window come from k_twobit_windows (0, 0 for an excised window) -- bit-identical to b200_unpack_twobit
+      const uint64_t i0 = samp0 + 2ull * uint64_t(n1) * a.Q;
+      const unsigned byte = __ldg(raw + (i0 >> 2) * a.npol + pol);
+      const float2 lv = __ldg(a.win + (i0 >> 9) * a.npol + pol);
+      const unsigned sh = 6u - 2u * unsigned(i0 & 3ull);
+      const unsigned c0 = (byte >> sh) & 3u, c1 = (byte >> (sh - 2u)) & 3u;
+      const float m0 = ((a.lowsel >> c0) & 1u) ? lv.x : lv.y, m1 = ((a.lowsel >> c1) & 1u) ? lv.x : lv.y;
+      return make_float2(((a.negsel >> c0) & 1u) ? -m0 : m0, ((a.negsel >> c1) & 1u) ? -m1 : m1);
     } else if (SRC == SRC_GENERIC8) {
       // TFP bytes: i*(nchan*npol*ndim) + ndim*(npol*c + p) + d (BitUnpacker.C:56-75)
       if (a.ndim == 2) {
@@ -780,6 +793,7 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
       a.P = pl->P; a.Q = pl->Q; a.lb = pl->lbB; a.npol = npol; a.nchan_in = nchan_in; a.Nc = pl->Nc;
       a.part0 = part0;
       a.first = src.first; a.scale = src.scale; a.sample_swap = src.sample_swap; a.ndim = src.ndim;
+      a.win = src.win; a.lowsel = src.lowsel; a.negsel = src.negsel;
       dim3 grid(pl->Q / B, nb * nblk1);
       const bool ct = (pl->P == 2048) && src.kind <= SRC_CASPSR8;   // compile-time-sized fast path (float / CASPSR sources)
       static const int k1_ept = tune_int("B200_K1_EPT", 32);
@@ -805,6 +819,7 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
         else if (src.kind == SRC_MEERKAT8) k_cols_fwd<SRC_MEERKAT8, 16, 0><<<grid, block, smem, st>>>(a);
         else if (src.kind == SRC_UWB16) k_cols_fwd<SRC_UWB16, 16, 0><<<grid, block, smem, st>>>(a);
         else if (src.kind == SRC_GENERIC8) k_cols_fwd<SRC_GENERIC8, 16, 0><<<grid, block, smem, st>>>(a);
+        else if (src.kind == SRC_TWOBIT) k_cols_fwd<SRC_TWOBIT, 16, 0><<<grid, block, smem, st>>>(a);
         else k_cols_fwd<SRC_CASPSR8, 16, 0><<<grid, block, smem, st>>>(a);
       }
     }
@@ -935,7 +950,7 @@ static int plan_set_attributes(size_t maxs) {
   int rc;
 #define SET(k) if ((rc = set_smem(k, maxs)) != B200_OK) return rc;
   SET((k_cols_fwd<SRC_F32, 16, 0>)) SET((k_cols_fwd<SRC_CASPSR8, 16, 0>))
-  SET((k_cols_fwd<SRC_MEERKAT8, 16, 0>)) SET((k_cols_fwd<SRC_UWB16, 16, 0>)) SET((k_cols_fwd<SRC_GENERIC8, 16, 0>))
+  SET((k_cols_fwd<SRC_MEERKAT8, 16, 0>)) SET((k_cols_fwd<SRC_UWB16, 16, 0>)) SET((k_cols_fwd<SRC_GENERIC8, 16, 0>)) SET((k_cols_fwd<SRC_TWOBIT, 16, 0>))
   SET((k_cols_fwd<SRC_F32, 32, 2048>)) SET((k_cols_fwd<SRC_CASPSR8, 32, 2048>))
   SET((k_cols_fwd<SRC_F32, 16, 2048>)) SET((k_cols_fwd<SRC_CASPSR8, 16, 2048>))
   SET((k_chan_inv<16, EPI_VOLT, 8192>)) SET((k_chan_inv<16, EPI_DETECT, 8192>)) SET((k_chan_inv<16, EPI_FOLD, 8192>))

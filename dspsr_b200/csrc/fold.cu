@@ -163,6 +163,43 @@ __global__ void k_unpack_twobit(TwoBitArgs a) {
   }
 }
 
+// The per-window half of the two-bit unpacker alone: for every 512-sample window and digitizer the pair of output
+// levels (lo, hi) the reference would use (0, 0 for an excised window) and the window's weight.  The filterbank's
+// column kernel then converts the 2-bit codes itself (filterbank.cu, SRC_TWOBIT): no float time series is written.
+template <unsigned NPOL>
+__global__ void k_twobit_windows(TwoBitArgs a, float2* __restrict__ win) {
+  const unsigned lane = threadIdx.x & 31u;
+  const uint64_t warp0 = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5;
+  const uint64_t nwarp = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+  for (uint64_t w = warp0; w < a.nwindow; w += nwarp) {
+    unsigned words[NPOL];
+    const unsigned* src = reinterpret_cast<const unsigned*>(a.raw + (w * 128 + 4 * lane) * NPOL);
+#pragma unroll
+    for (unsigned i = 0; i < NPOL; i++) words[i] = __ldg(src + i);
+    bool zero_any = false;
+#pragma unroll
+    for (unsigned p = 0; p < NPOL; p++) {
+      unsigned nlow = 0, any = 0;
+#pragma unroll
+      for (unsigned k = 0; k < 4; k++) {
+        const unsigned b = k * NPOL + p;                                  // byte b of the group belongs to digitizer b % NPOL
+        const unsigned byte = (words[b / 4] >> (8 * (b % 4))) & 255u;
+        any |= byte;
+#pragma unroll
+        for (unsigned s4 = 0; s4 < 4; s4++) nlow += (a.lowsel >> ((byte >> (6 - 2 * s4)) & 3u)) & 1u;
+      }
+      nlow = __reduce_add_sync(0xffffffffu, nlow);
+      any = __reduce_or_sync(0xffffffffu, any);
+      const bool bad = (any == 0) || nlow < a.nlow_min || nlow > a.nlow_max;   // excision_unpack.h:79-97
+      zero_any |= bad;
+      const unsigned row = min(max(nlow, a.nlow_min), a.nlow_max) - a.nlow_min;   // TwoBitFour.h:68-75
+      if (lane == 0)
+        win[w * NPOL + p] = bad ? make_float2(0.f, 0.f) : make_float2(__ldg(a.levels + row), __ldg(a.levels + 513 + row));
+    }
+    if (a.weights && lane == 0) a.weights[w] = zero_any ? 0u : 1u;     // WeightedTimeSeries::mask_weights
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // stand-alone detection (Detection.C:218-320,322-421)
 // ------------------------------------------------------------------------------------------
@@ -423,8 +460,9 @@ int b200_unpack(b200_context* cctx, const b200_unpack_desc* d, const void* d_raw
   const unsigned maxgrid = ctx->sm_count * 16;
   float* d_lut = nullptr;
   if (d->format == B200_FMT_CASPSR8 || d->format == B200_FMT_GENERIC8) {
-    // the table travels with the call; 1 KiB async copy from a staging copy owned by the stream order
-    B200_CUDA(cudaMallocAsync(&d_lut, 256 * sizeof(float), ctx->stream));
+    // the table travels with the call: a stream-ordered 1 KiB copy into the context's table area (no allocation; the
+    // copy of the next call is ordered behind this call's kernel)
+    d_lut = ctx->d_tables;
     B200_CUDA(cudaMemcpyAsync(d_lut, d->lut, 256 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   }
   LaunchScope ls(ctx, KC_OTHER);
@@ -463,7 +501,6 @@ int b200_unpack(b200_context* cctx, const b200_unpack_desc* d, const void* d_raw
       set_error("b200_unpack: unknown format %d", d->format);
       return B200_ERR_INVALID;
   }
-  if (d_lut) B200_CUDA(cudaFreeAsync(d_lut, ctx->stream));
   B200_CUDA(cudaGetLastError());
   return B200_OK;
 }
@@ -484,8 +521,7 @@ int b200_unpack_twobit(b200_context* cctx, const b200_twobit_desc* d, const void
                (reinterpret_cast<uintptr_t>(d_raw) & 3) == 0, "two-bit unpacker: unaligned buffers");
   B200_REQUIRE(d->nlow_min <= d->nlow_max && d->nlow_max <= 512, "two-bit unpacker: invalid nlow limits");
   if (ndat == 0) return B200_OK;
-  float* d_levels = nullptr;
-  B200_CUDA(cudaMallocAsync(&d_levels, 2 * 513 * sizeof(float), ctx->stream));
+  float* d_levels = ctx->d_tables + 256;           // behind the 8-bit table; 2 x 513 floats (no allocation)
   B200_CUDA(cudaMemcpyAsync(d_levels, d->lo, 513 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   B200_CUDA(cudaMemcpyAsync(d_levels + 513, d->hi, 513 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   TwoBitArgs a;
@@ -504,10 +540,43 @@ int b200_unpack_twobit(b200_context* cctx, const b200_twobit_desc* d, const void
     if (d->npol == 1) k_unpack_twobit<1><<<grid, threads, 0, ctx->stream>>>(a);
     else k_unpack_twobit<2><<<grid, threads, 0, ctx->stream>>>(a);
   }
-  B200_CUDA(cudaFreeAsync(d_levels, ctx->stream));
   B200_CUDA(cudaGetLastError());
   return B200_OK;
 }
+
+}  // extern "C"
+
+namespace b200 {
+// level pairs + weights of `nwindow` windows starting at d_raw (a 512-sample boundary); tables go through the
+// context's table area like b200_unpack_twobit
+int twobit_windows(Context* ctx, const b200_twobit_desc* d, const void* d_raw, uint64_t nwindow, float2* d_win,
+                   unsigned* d_weights, unsigned* lowsel_out, unsigned* negsel_out) {
+  static const unsigned lowsel[3] = {0x6u, 0x5u, 0x9u};
+  static const unsigned negsel[3] = {0x3u, 0xcu, 0xcu};
+  B200_REQUIRE(d->table_type >= 0 && d->table_type <= 2, "two-bit unpacker: unknown table type %d", d->table_type);
+  *lowsel_out = lowsel[d->table_type];
+  *negsel_out = negsel[d->table_type];
+  if (nwindow == 0) return B200_OK;
+  float* d_levels = ctx->d_tables + 256;
+  B200_CUDA(cudaMemcpyAsync(d_levels, d->lo, 513 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  B200_CUDA(cudaMemcpyAsync(d_levels + 513, d->hi, 513 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  TwoBitArgs a;
+  a.raw = static_cast<const unsigned char*>(d_raw);
+  a.out = nullptr; a.span = 0; a.nwindow = nwindow; a.npol = d->npol;
+  a.nlow_min = d->nlow_min; a.nlow_max = d->nlow_max; a.levels = d_levels; a.weights = d_weights;
+  a.lowsel = *lowsel_out;
+  a.negsel = *negsel_out;
+  const unsigned threads = 256;
+  unsigned grid = (unsigned)std::min<uint64_t>((nwindow * 32 + threads - 1) / threads, uint64_t(ctx->sm_count) * 16);
+  LaunchScope ls(ctx, KC_OTHER);
+  if (d->npol == 1) k_twobit_windows<1><<<grid, threads, 0, ctx->stream>>>(a, d_win);
+  else k_twobit_windows<2><<<grid, threads, 0, ctx->stream>>>(a, d_win);
+  B200_CUDA(cudaGetLastError());
+  return B200_OK;
+}
+}  // namespace b200
+
+extern "C" {
 
 int b200_detect(b200_context* cctx, int state, unsigned ndim_out, const float* d_in, uint64_t in_span, unsigned nchan,
                 unsigned npol, uint64_t ndat, float* d_out, uint64_t out_span) {

@@ -40,6 +40,8 @@ struct b200_pipeline {
   // unpacked float series for formats whose unpack is not fused into K1
   float* d_unpacked;
   uint64_t unpacked_floats;
+  float2* d_win;             // fused two-bit path: (lo, hi) per 512-sample window and digitizer
+  uint64_t win_capacity;
   unsigned nprod, dnpol, dndim;
   int conv_ok;
   float conv_hi, conv_lo;
@@ -188,6 +190,7 @@ int b200_pipeline_destroy(b200_pipeline* p) {
   }
   if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
   if (p->d_unpacked) cudaFree(p->d_unpacked);
+  if (p->d_win) cudaFree(p->d_win);
   if (p->d_volt) cudaFree(p->d_volt);
   if (p->d_det) cudaFree(p->d_det);
   for (int i = 0; i < 2; i++) {
@@ -228,6 +231,14 @@ static int grow(Context* ctx, T** ptr, uint64_t* capacity, uint64_t need) {
   return B200_OK;
 }
 
+// Two-bit input is unpacked inside the generic K1 (no float time series) whenever that kernel runs the column pass:
+// real input (the CPSR2 convention), and no second-generation K1 for the plan's shape
+static bool twobit_fused(const b200_pipeline* p) {
+  static const bool want = b200::tune_flag("B200_TWOBIT_FUSED", true);
+  return want && p->desc.unpack.format == B200_FMT_TWOBIT && p->desc.unpack.ndim == 1 && p->desc.unpack.nchan == 1 &&
+         p->desc.fb.input_real && !p->fb->fast_k1 && p->twobit.ndat_per_weight == 512;
+}
+
 // scratch of a block of npart parts for everything execute needs besides the plan's own buffers
 static int pipeline_scratch(b200_pipeline* p, uint64_t npart) {
   Context* ctx = p->ctx;
@@ -236,12 +247,16 @@ static int pipeline_scratch(b200_pipeline* p, uint64_t npart) {
   const unsigned ndim = p->desc.unpack.ndim;
   const uint64_t ndat_out = npart * fb->nkeep;
   int rc = B200_OK;
+  const bool fused_twobit = twobit_fused(p);
   const bool fused_unpack = fmt == B200_FMT_CASPSR8 ||
                             (!fb->fast_k1 && (fmt == B200_FMT_MEERKAT8 || fmt == B200_FMT_UWB16 || fmt == B200_FMT_GENERIC8));
   if (!fused_unpack && fmt != B200_FMT_FLOAT32) {
     const unsigned res = fmt_resolution(fmt);
     const uint64_t ndat_in = npart * fb->nsamp_step + fb->nsamp_overlap + 2 * res;
-    rc = grow(ctx, &p->d_unpacked, &p->unpacked_floats, ndat_in * ndim * p->desc.unpack.nchan * p->desc.unpack.npol);
+    if (fused_twobit)
+      rc = grow(ctx, &p->d_win, &p->win_capacity, (ndat_in / p->twobit.ndat_per_weight + 2) * p->desc.unpack.npol);
+    else
+      rc = grow(ctx, &p->d_unpacked, &p->unpacked_floats, ndat_in * ndim * p->desc.unpack.nchan * p->desc.unpack.npol);
     if (rc == B200_OK && fmt == B200_FMT_TWOBIT) {
       const uint64_t nw = ndat_in / p->twobit.ndat_per_weight + 2;
       uint64_t cap2 = p->weights_capacity;
@@ -331,9 +346,13 @@ static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t inpu
     if (rc != B200_OK) return rc;
     const uint64_t bits_per_sample = uint64_t(p->desc.unpack.nchan) * p->desc.unpack.npol * ndim * fmt_nbit(fmt);
     const unsigned char* raw0 = static_cast<const unsigned char*>(d_input) + a0 * bits_per_sample / 8;
+    const bool fused_twobit = twobit_fused(p);
     if (fmt == B200_FMT_TWOBIT) {
       // a WeightedTimeSeries: the flags of the windows travel with the data (weights.cu)
-      rc = b200_unpack_twobit(reinterpret_cast<b200_context*>(ctx), &p->twobit, raw0, a1 - a0, p->d_unpacked, span, p->d_weights);
+      if (fused_twobit)
+        rc = twobit_windows(ctx, &p->twobit, raw0, (a1 - a0) / 512, p->d_win, p->d_weights, &src.lowsel, &src.negsel);
+      else
+        rc = b200_unpack_twobit(reinterpret_cast<b200_context*>(ctx), &p->twobit, raw0, a1 - a0, p->d_unpacked, span, p->d_weights);
       if (rc != B200_OK) return rc;
       wt.nweights = (a1 - a0) / p->twobit.ndat_per_weight;
       wt.ndat_per_weight = p->twobit.ndat_per_weight;
@@ -361,11 +380,22 @@ static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t inpu
       rc = b200_unpack(reinterpret_cast<b200_context*>(ctx), &p->desc.unpack, raw0, a1 - a0, p->d_unpacked, span);
       if (rc != B200_OK) return rc;
     }
-    src.kind = SRC_F32;
-    src.ptr = p->d_unpacked + (first_sample - a0) * ndim;
-    src.span = span;
-    src.step = uint64_t(fb->nsamp_step) * ndim;
-    B200_REQUIRE(((first_sample - a0) * ndim) % 2 == 0, "unaligned block start");
+    if (fused_twobit) {
+      // K1 converts the codes itself from the window levels: ptr is the 512-sample boundary a0, first the offset into it
+      src.kind = SRC_TWOBIT;
+      src.ptr = raw0;
+      src.first = first_sample - a0;
+      src.step = fb->nsamp_step;
+      src.win = p->d_win;
+      src.ndim = 1;
+      B200_REQUIRE((first_sample - a0) % 2 == 0, "two-bit input must start on an even sample");
+    } else {
+      src.kind = SRC_F32;
+      src.ptr = p->d_unpacked + (first_sample - a0) * ndim;
+      src.span = span;
+      src.step = uint64_t(fb->nsamp_step) * ndim;
+      B200_REQUIRE(((first_sample - a0) * ndim) % 2 == 0, "unaligned block start");
+    }
   }
 
   FbSink sink;
