@@ -360,6 +360,64 @@ struct ChanArgs {
   FbSink sink;
 };
 
+// K3 for short per-channel transforms (freq_res = 2 ... 16: cfg2's -F 4096:D has 8), voltage and detected-series sinks:
+// ONE THREAD per output channel does the inverse transform of both polarisations in registers and walks PG consecutive
+// parts, so that what it writes per plane is one contiguous run (PG * nkeep samples) instead of nkeep samples per part,
+// and what a warp reads per part is one contiguous stretch of the spectrum (32 channels x F bins).
+template <unsigned F, int EPI>
+__global__ void __launch_bounds__(128) k_chan_inv_small(ChanArgs a, unsigned npart, unsigned PG) {
+  const unsigned ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= a.nchan_in * a.C) return;
+  const unsigned ic = ch / a.C, csub = ch % a.C;
+  const unsigned np0 = a.nfilt_pos, nkeep = a.nkeep;
+  const int state = a.sink.state;
+  const unsigned nprod = EPI == EPI_VOLT ? 0 : state_nprod(state, a.npol);
+  const unsigned dndim = a.sink.dndim, dnpol = EPI == EPI_VOLT ? 1 : nprod / dndim;
+  const unsigned p_end = min(npart, (blockIdx.y + 1) * PG);
+  for (unsigned partl = blockIdx.y * PG; partl < p_end; partl++) {
+    const uint64_t part = a.part0 + partl;
+    float2 v[2][F];
+#pragma unroll
+    for (unsigned pol = 0; pol < 2; pol++) {
+      if (pol < a.npol) {
+        const float2* src = a.Z + (uint64_t(partl) * a.nchan_in + ic) * a.npol * a.Nc + uint64_t(pol) * a.Nc + uint64_t(csub) * F;
+        if (F >= 2) {
+#pragma unroll
+          for (unsigned i = 0; i < F; i += 2) {
+            const float4 x = __ldcs(reinterpret_cast<const float4*>(src + i));      // read once: evict first
+            v[pol][i] = make_float2(x.x, x.y);
+            v[pol][i + 1] = make_float2(x.z, x.w);
+          }
+        }
+        dftR<F, true>(v[pol]);
+      } else {
+#pragma unroll
+        for (unsigned i = 0; i < F; i++) v[pol][i] = make_float2(0.f, 0.f);
+      }
+    }
+    if (EPI == EPI_VOLT) {
+#pragma unroll
+      for (unsigned pol = 0; pol < 2; pol++) {
+        if (pol >= a.npol) continue;
+        float2* out = reinterpret_cast<float2*>(a.sink.volt + (uint64_t(ch) * a.npol + pol) * a.sink.volt_span + part * a.sink.volt_step);
+#pragma unroll
+        for (unsigned i = 0; i < F; i++)
+          if (i - np0 < nkeep) out[i - np0] = v[pol][i];
+      }
+    } else {
+      const uint64_t osamp0 = part * nkeep;
+#pragma unroll
+      for (unsigned i = 0; i < F; i++) {
+        if (i - np0 >= nkeep) continue;                     // unsigned: samples before nfilt_pos wrap to huge values
+        float r[4] = {0.f, 0.f, 0.f, 0.f};
+        detect_products(state, v[0][i], v[1][i], r);
+        for (unsigned pr = 0; pr < nprod; pr++)
+          a.sink.det[(uint64_t(ch) * dnpol + pr / dndim) * a.sink.det_span + (osamp0 + (i - np0)) * dndim + pr % dndim] = r[pr];
+      }
+    }
+  }
+}
+
 template <int EPT, int EPI, unsigned FCT>
 __global__ void __launch_bounds__((FCT && EPT == 32) ? 512 : 1024, 1) k_chan_inv(ChanArgs a) {
   extern __shared__ float2 smem[];
@@ -901,6 +959,28 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
       a.F = pl->F; a.C = pl->C; a.Nc = pl->Nc; a.npol = npol; a.nchan_in = nchan_in;
       a.nfilt_pos = pl->desc.nfilt_pos; a.nkeep = pl->nkeep; a.part0 = part0; a.sink = sk;
       const unsigned F = pl->F;
+      static const bool small_k3 = tune_flag("B200_K3_SMALL", true);
+      if (small_k3 && F >= 2 && F <= 16 && sk.kind != EPI_FOLD && npol <= 2 && (sk.kind == EPI_VOLT || state_nprod(sk.state, npol) <= 4)) {
+        // one thread per channel, PG parts per thread: enough thread blocks to fill the machine a few times over
+        const unsigned nch = pl->nchan_out;
+        const unsigned gx = (nch + 127) / 128;
+        unsigned PG = 16;
+        while (PG > 1 && uint64_t(gx) * ((nb + PG - 1) / PG) < 4ull * ctx->sm_count) PG /= 2;
+        dim3 grid(gx, (nb + PG - 1) / PG);
+        LaunchScope ls(ctx, KC_INV);
+#define B200_K3S(FF)                                                                               \
+  if (sk.kind == EPI_VOLT) k_chan_inv_small<FF, EPI_VOLT><<<grid, 128, 0, st>>>(a, nb, PG);           \
+  else k_chan_inv_small<FF, EPI_DETECT><<<grid, 128, 0, st>>>(a, nb, PG);
+        switch (F) {
+          case 2: B200_K3S(2) break;
+          case 4: B200_K3S(4) break;
+          case 8: B200_K3S(8) break;
+          default: B200_K3S(16) break;
+        }
+#undef B200_K3S
+        B200_CUDA(cudaGetLastError());
+        continue;
+      }
       const unsigned ept = F >= 16 ? 16 : F;       // 16, 8, 4, 2, 1
       const unsigned T = F >= 16 ? F / 16 : 1;
       // transforms per CTA: both polarisations of CB channels

@@ -710,6 +710,29 @@ def test_fast_k3_all_epilogues(ctx, oracle, state, dndim, nbin):
     assert np.array_equal(det, ref) or synth.relerr(det, ref) <= TOL
 
 
+@pytest.mark.parametrize("C,F,npos,nneg,state,dndim", [(64, 4, 1, 0, "Stokes", 4), (32, 16, 2, 3, "Coherence", 2),
+                                                         (128, 2, 0, 1, "PPQQ", 1), (4096, 8, 1, 1, "Intensity", 1)])
+def test_short_channel_transforms_detected_series(ctx, oracle, C, F, npos, nneg, state, dndim):
+    """k_chan_inv_small: freq_res 2 ... 16 (cfg2: 8) with the detected-series sink -- one thread per channel, several
+    parts per thread -- for every detection state, with a part count that does not divide into the part groups."""
+    torch, E, L = _torch(), _E(), _L()
+    npart = 37
+    lut, _ = oracle.bittable8()
+    f = oracle.fb_sizes(1, 1, 2, C, F, npos, nneg)
+    ndat = (npart * f.nsamp_step + f.nsamp_overlap + 3) // 4 * 4
+    raw = synth.caspsr_bytes(ndat, seed=71)
+    H = np.exp(1j * np.random.default_rng(72).uniform(-np.pi, np.pi, (C, F))).astype(np.complex64)
+    x = oracle.unpack_caspsr(raw, ndat, lut)
+    volt = oracle.filterbank(f, x[:, :, : npart * f.nsamp_step + f.nsamp_overlap], H)
+    ref = oracle.detect(state, dndim, volt)
+    ud = E.make_unpack_desc(L.FMT_CASPSR8, 1, 2, 1, lut)
+    fd, keep = E.make_fb_desc(1, 1, 2, C, F, npos, nneg, H)
+    pipe = E.Pipeline(ctx, ud, fd, keep, state, dndim, 0)
+    det = pipe.execute(torch.from_numpy(raw).cuda(), npart, 0.0, 0.0, first_sample=0).cpu().numpy()
+    assert det.shape == ref.shape
+    assert np.array_equal(det, ref) or synth.relerr(det, ref) <= TOL
+
+
 @pytest.mark.parametrize("C,F,npos,nneg", [(32, 256, 20, 21), (16, 512, 30, 31), (8, 1024, 60, 61), (4, 2048, 98, 98),
                                            (2, 4096, 200, 201)])
 def test_fast_k3_every_planned_length(ctx, oracle, C, F, npos, nneg):
