@@ -362,59 +362,74 @@ struct ChanArgs {
 
 // K3 for short per-channel transforms (freq_res = 2 ... 16: cfg2's -F 4096:D has 8), voltage and detected-series sinks:
 // ONE THREAD per output channel does the inverse transform of both polarisations in registers and walks PG consecutive
-// parts, so that what it writes per plane is one contiguous run (PG * nkeep samples) instead of nkeep samples per part,
-// and what a warp reads per part is one contiguous stretch of the spectrum (32 channels x F bins).
+// parts.  What a warp reads per part is one contiguous stretch of the spectrum (32 channels x F bins); what the CTA
+// writes is staged in shared memory as one row per (channel, output plane) -- PG parts = PG * nkeep consecutive
+// samples -- and leaves as coalesced runs (scattered 4-byte stores cost eight times the L2 sector writes).
+// Output planes: voltages (channel, pol) of 2 floats per sample; detected (channel, pr / dndim) of dndim floats.
 template <unsigned F, int EPI>
 __global__ void __launch_bounds__(128) k_chan_inv_small(ChanArgs a, unsigned npart, unsigned PG) {
-  const unsigned ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= a.nchan_in * a.C) return;
-  const unsigned ic = ch / a.C, csub = ch % a.C;
+  extern __shared__ float stage[];
+  const unsigned cl = threadIdx.x, ch0 = blockIdx.x * 128u, ch = ch0 + cl;
+  const unsigned nch = a.nchan_in * a.C;
   const unsigned np0 = a.nfilt_pos, nkeep = a.nkeep;
   const int state = a.sink.state;
   const unsigned nprod = EPI == EPI_VOLT ? 0 : state_nprod(state, a.npol);
-  const unsigned dndim = a.sink.dndim, dnpol = EPI == EPI_VOLT ? 1 : nprod / dndim;
-  const unsigned p_end = min(npart, (blockIdx.y + 1) * PG);
-  for (unsigned partl = blockIdx.y * PG; partl < p_end; partl++) {
-    const uint64_t part = a.part0 + partl;
-    float2 v[2][F];
-#pragma unroll
-    for (unsigned pol = 0; pol < 2; pol++) {
-      if (pol < a.npol) {
-        const float2* src = a.Z + (uint64_t(partl) * a.nchan_in + ic) * a.npol * a.Nc + uint64_t(pol) * a.Nc + uint64_t(csub) * F;
-        if (F >= 2) {
-#pragma unroll
-          for (unsigned i = 0; i < F; i += 2) {
-            const float4 x = __ldcs(reinterpret_cast<const float4*>(src + i));      // read once: evict first
-            v[pol][i] = make_float2(x.x, x.y);
-            v[pol][i + 1] = make_float2(x.z, x.w);
-          }
-        }
-        dftR<F, true>(v[pol]);
-      } else {
-#pragma unroll
-        for (unsigned i = 0; i < F; i++) v[pol][i] = make_float2(0.f, 0.f);
-      }
-    }
-    if (EPI == EPI_VOLT) {
+  const unsigned edim = EPI == EPI_VOLT ? 2u : a.sink.dndim;               // floats per sample of a plane
+  const unsigned nplane = EPI == EPI_VOLT ? a.npol : nprod / edim;         // planes per channel
+  const unsigned RL = PG * nkeep * edim, RS = RL + 1u;                     // row length, odd-ish stride: no bank conflicts
+  const unsigned p_begin = blockIdx.y * PG, p_end = min(npart, p_begin + PG);
+  if (ch < nch) {
+    const unsigned ic = ch / a.C, csub = ch % a.C;
+    for (unsigned partl = p_begin; partl < p_end; partl++) {
+      float2 v[2][F];
 #pragma unroll
       for (unsigned pol = 0; pol < 2; pol++) {
-        if (pol >= a.npol) continue;
-        float2* out = reinterpret_cast<float2*>(a.sink.volt + (uint64_t(ch) * a.npol + pol) * a.sink.volt_span + part * a.sink.volt_step);
+        if (pol < a.npol) {
+          const float2* src = a.Z + ((uint64_t(partl) * a.nchan_in + ic) * a.npol + pol) * a.Nc + uint64_t(csub) * F;
 #pragma unroll
-        for (unsigned i = 0; i < F; i++)
-          if (i - np0 < nkeep) out[i - np0] = v[pol][i];
+          for (unsigned i = 0; i < F; i += 2) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(src + i));   // L1: a lane's 8 F bytes span sectors
+            v[pol][i] = make_float2(x.x, x.y);                                  // that its next load touches again
+            v[pol][i + 1] = make_float2(x.z, x.w);
+          }
+          dftR<F, true>(v[pol]);
+        } else {
+#pragma unroll
+          for (unsigned i = 0; i < F; i++) v[pol][i] = make_float2(0.f, 0.f);
+        }
       }
-    } else {
-      const uint64_t osamp0 = part * nkeep;
+      const unsigned s0 = (partl - p_begin) * nkeep;                           // first sample of this part in the row
 #pragma unroll
       for (unsigned i = 0; i < F; i++) {
-        if (i - np0 >= nkeep) continue;                     // unsigned: samples before nfilt_pos wrap to huge values
-        float r[4] = {0.f, 0.f, 0.f, 0.f};
-        detect_products(state, v[0][i], v[1][i], r);
-        for (unsigned pr = 0; pr < nprod; pr++)
-          a.sink.det[(uint64_t(ch) * dnpol + pr / dndim) * a.sink.det_span + (osamp0 + (i - np0)) * dndim + pr % dndim] = r[pr];
+        if (i - np0 >= nkeep) continue;                   // unsigned: samples before nfilt_pos wrap to huge values
+        const unsigned so = (s0 + (i - np0)) * edim;
+        if (EPI == EPI_VOLT) {
+#pragma unroll
+          for (unsigned pol = 0; pol < 2; pol++)
+            if (pol < a.npol) {
+              float* row = stage + (cl * nplane + pol) * RS + so;
+              row[0] = v[pol][i].x;
+              row[1] = v[pol][i].y;
+            }
+        } else {
+          float r[4] = {0.f, 0.f, 0.f, 0.f};
+          detect_products(state, v[0][i], v[1][i], r);
+          for (unsigned pr = 0; pr < nprod; pr++) stage[(cl * nplane + pr / edim) * RS + so + pr % edim] = r[pr];
+        }
       }
     }
+  }
+  __syncthreads();
+  // coalesced write-out: one warp per row, lanes along the row
+  const unsigned nrow = min(128u, nch - ch0) * nplane, len = (p_end - p_begin) * nkeep * edim;
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  for (unsigned row = warp; row < nrow; row += 4u) {
+    const unsigned c = ch0 + row / nplane, pl = row % nplane;
+    float* out;
+    if (EPI == EPI_VOLT) out = a.sink.volt + (uint64_t(c) * a.npol + pl) * a.sink.volt_span + (a.part0 + p_begin) * a.sink.volt_step;
+    else out = a.sink.det + (uint64_t(c) * nplane + pl) * a.sink.det_span + (a.part0 + p_begin) * uint64_t(nkeep) * edim;
+    const float* srow = stage + row * RS;
+    for (unsigned i = lane; i < len; i += 32u) out[i] = srow[i];
   }
 }
 
@@ -960,17 +975,25 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
       a.nfilt_pos = pl->desc.nfilt_pos; a.nkeep = pl->nkeep; a.part0 = part0; a.sink = sk;
       const unsigned F = pl->F;
       static const bool small_k3 = tune_flag("B200_K3_SMALL", true);
-      if (small_k3 && F >= 2 && F <= 16 && sk.kind != EPI_FOLD && npol <= 2 && (sk.kind == EPI_VOLT || state_nprod(sk.state, npol) <= 4)) {
-        // one thread per channel, PG parts per thread: enough thread blocks to fill the machine a few times over
+      const unsigned s_edim = sk.kind == EPI_VOLT ? 2u : sk.dndim;
+      const unsigned s_nplane = sk.kind == EPI_VOLT ? npol : (sk.kind == EPI_DETECT ? state_nprod(sk.state, npol) / s_edim : 1u);
+      if (small_k3 && F >= 2 && F <= 16 && sk.kind != EPI_FOLD && npol <= 2 && pl->nkeep > 0 &&
+          size_t(128) * s_nplane * (pl->nkeep * s_edim + 1) * sizeof(float) <= 48 * 1024) {
+        // one thread per channel, PG parts per thread: as many as the 48 KiB staging tile holds (rows of PG * nkeep
+        // samples per output plane), fewer if the grid would not fill the machine a few times over
         const unsigned nch = pl->nchan_out;
         const unsigned gx = (nch + 127) / 128;
+        const unsigned edim = sk.kind == EPI_VOLT ? 2u : sk.dndim;
+        const unsigned nplane = sk.kind == EPI_VOLT ? npol : state_nprod(sk.state, npol) / edim;
         unsigned PG = 16;
+        while (PG > 1 && size_t(128) * nplane * (PG * pl->nkeep * edim + 1) * sizeof(float) > 48 * 1024) PG /= 2;
         while (PG > 1 && uint64_t(gx) * ((nb + PG - 1) / PG) < 4ull * ctx->sm_count) PG /= 2;
+        const size_t ssm = size_t(128) * nplane * (PG * pl->nkeep * edim + 1) * sizeof(float);
         dim3 grid(gx, (nb + PG - 1) / PG);
         LaunchScope ls(ctx, KC_INV);
 #define B200_K3S(FF)                                                                               \
-  if (sk.kind == EPI_VOLT) k_chan_inv_small<FF, EPI_VOLT><<<grid, 128, 0, st>>>(a, nb, PG);           \
-  else k_chan_inv_small<FF, EPI_DETECT><<<grid, 128, 0, st>>>(a, nb, PG);
+  if (sk.kind == EPI_VOLT) k_chan_inv_small<FF, EPI_VOLT><<<grid, 128, ssm, st>>>(a, nb, PG);         \
+  else k_chan_inv_small<FF, EPI_DETECT><<<grid, 128, ssm, st>>>(a, nb, PG);
         switch (F) {
           case 2: B200_K3S(2) break;
           case 4: B200_K3S(4) break;
