@@ -188,6 +188,8 @@ template <bool SPLIT, bool CONV, int EPT, unsigned QCT>
 __global__ void __launch_bounds__(QCT ? 512 : 1024, 1) k_rows(RowsArgs a) {
   extern __shared__ float2 smem[];
   __shared__ float2 s_rowtw[32];   // W_2N^(row) of every slot: row factor of the real-split twiddle
+  __shared__ float2 s_wt[512];     // convolution path: W_N^-(row*T*e) of every slot, the part of the output
+                                   // twiddle W_N^-(row*m2), m2 = j + T*e, that does not depend on the thread
   const unsigned Q = QCT ? QCT : a.Q;
   const unsigned T = EPT ? Q / (EPT ? EPT : 1) : 1;
   constexpr unsigned SH = SwzShift<EPT>::value;
@@ -217,6 +219,17 @@ __global__ void __launch_bounds__(QCT ? 512 : 1024, 1) k_rows(RowsArgs a) {
     unsigned r = slot_row(threadIdx.x);
     if (threadIdx.x == 0 && tile == 0) r = 0;
     s_rowtw[threadIdx.x] = big_twiddle<false>(a.b2lo, a.b2hi, r);
+  }
+
+  const unsigned nslots = blockDim.x / T;
+  const bool wt_fact = CONV && EPT && nslots * (EPT ? EPT : 1) <= 512;
+  float2 wj = make_float2(1.f, 0.f);
+  if (wt_fact) {
+    for (unsigned i = threadIdx.x; i < nslots * (EPT ? EPT : 1); i += blockDim.x) {
+      const unsigned s = i / (EPT ? EPT : 1), e = i % (EPT ? EPT : 1);
+      s_wt[i] = big_twiddle<true>(a.blo, a.bhi, slot_row(s) * T * e);
+    }
+    wj = big_twiddle<true>(a.blo, a.bhi, row * j);
   }
 
   // ---- phase 1: forward row FFT into shared memory (natural order) ----
@@ -337,8 +350,9 @@ __global__ void __launch_bounds__(QCT ? 512 : 1024, 1) k_rows(RowsArgs a) {
     if (EPT) {
       MapRows map{slot * Q, SH, ((slot % G) * 2u) & 15u};
       auto load = [&](unsigned idx) -> float2 { return smem[map(idx)]; };
-      auto store = [&](unsigned m2, float2 v, int) {
-        dst[m2] = cmul(v, big_twiddle<true>(a.blo, a.bhi, row * m2));
+      const float2* wt = s_wt + slot * (EPT ? EPT : 1);
+      auto store = [&](unsigned m2, float2 v, int e) {
+        dst[m2] = wt_fact ? cmul(cmul(v, wj), wt[e]) : cmul(v, big_twiddle<true>(a.blo, a.bhi, row * m2));
       };
       fft_any<(EPT ? EPT : 2), true, QCT>(Q, j, T, map, smem, a.twQ, a.twQs, load, store);
     } else {
@@ -855,8 +869,15 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
     const bool skip_k2 = pl->Q == 1 && !pl->desc.input_real && !pl->conv_path;
     // ---- K1 ----
     const bool k1_fast = pl->fast_k1 && src.kind <= SRC_CASPSR8 && (src.kind == SRC_F32 || (src.step % 4 == 0 && (reinterpret_cast<uintptr_t>(src.ptr) & 3) == 0));
+    // long convolutions (N > 131072): c2 kernels of clusterconv.cu; all three -> polarisations interleaved in the scratch
+    const bool bc1 = bc_k1_applies(pl, src), bc2 = bc_k2_applies(pl), bc3 = bc_k3_applies(pl);
+    const bool bc_il = bc1 && bc2 && bc3;
+    B200_REQUIRE(bc_il || pl->Nc <= (1u << 22), "transforms of more than 2^22 points: source format %d is not built", src.kind);
     if (k1_fast) {
       int rc = fast_k1(pl, src, part0, nb);
+      if (rc != B200_OK) return rc;
+    } else if (bc1) {
+      int rc = bc_k1(pl, src, part0, nb, bc_il);
       if (rc != B200_OK) return rc;
     } else {
       ColsArgs a;
@@ -901,6 +922,9 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
     } else if (pl->fast_k2) {
       int rc = fast_k2(pl, nb);
       if (rc != B200_OK) return rc;
+    } else if (bc2) {
+      int rc = bc_k2(pl, nb, bc_il);
+      if (rc != B200_OK) return rc;
     } else {
       RowsArgs a;
       a.A = pl->scratchA; a.Z = pl->scratchZ; a.H = pl->d_response; a.twQ = pl->twQ.tw; a.twQs = pl->twQ.stage;
@@ -942,6 +966,9 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
     }
     if (pl->fast_k3) {
       int rc = fast_k3(pl, sk, part0, nb);
+      if (rc != B200_OK) return rc;
+    } else if (pl->conv_path && bc3) {
+      int rc = bc_k3(pl, sk, part0, nb, bc_il);
       if (rc != B200_OK) return rc;
     } else if (pl->conv_path) {
       ColsInvArgs a;
@@ -1086,7 +1113,7 @@ int b200_fb_plan_create(b200_context* cctx, const b200_fb_desc* d, b200_fb_plan*
   B200_REQUIRE(is_pow2(d->nchan_subband) && is_pow2(d->freq_res),
                "nchan_subband=%u and freq_res=%u must be powers of two", d->nchan_subband, d->freq_res);
   const uint64_t Nc64 = uint64_t(d->nchan_subband) * d->freq_res;
-  B200_REQUIRE(Nc64 >= 16 && Nc64 <= (1ull << 22), "forward transform of %llu complex points unsupported (16..2^22)",
+  B200_REQUIRE(Nc64 >= 16 && Nc64 <= (1ull << 24), "forward transform of %llu complex points unsupported (16..2^24)",
                (unsigned long long)Nc64);
   B200_REQUIRE(d->nfilt_pos + d->nfilt_neg < d->freq_res || (d->freq_res == 1 && d->nfilt_pos + d->nfilt_neg == 0),
                "nfilt_pos+nfilt_neg=%u must be smaller than freq_res=%u", d->nfilt_pos + d->nfilt_neg, d->freq_res);
@@ -1217,6 +1244,13 @@ int b200_fb_plan_create(b200_context* cctx, const b200_fb_desc* d, b200_fb_plan*
   pl->scratch_bytes = sbytes * (pl->conv_path ? 1 : 2);
   rc = fast_plan_init(pl);
   if (rc == B200_OK) rc = cc_plan_init(pl);
+  if (rc == B200_OK) rc = bc_plan_init(pl);
+  if (rc == B200_OK && pl->Nc > (1u << 22) && !pl->bc_ok) {
+    // 2^23 and 2^24 points exist only as the long-transform kernels of clusterconv.cu (rows of 4096 / 8192 points)
+    set_error("transforms of more than 2^22 complex points are built for single-channel convolution of complex "
+              "dual-polarisation input only (got %u points)", pl->Nc);
+    rc = B200_ERR_UNSUPPORTED;
+  }
   if (rc != B200_OK) { b200_fb_plan_destroy(pl); return rc; }
   *out = pl;
   return B200_OK;
@@ -1246,6 +1280,7 @@ int b200_fb_plan_destroy(b200_fb_plan* pl) {
   free_big_twiddle(pl->big2N);
   fast_plan_free(pl);
   cc_plan_free(pl);
+  bc_plan_free(pl);
   if (pl->d_response) cudaFree(pl->d_response);
   if (pl->scratchA) cudaFree(pl->scratchA);
   if (pl->scratchZ) cudaFree(pl->scratchZ);

@@ -147,6 +147,8 @@ def test_filterbank_cfg1_shape(ctx, oracle):
     (0, 2, 2, 1, 65536, 2536, 2543, 2),  # cfg3's per-channel transform (one-kernel path, voltage sink)
     (0, 3, 2, 1, 32768, 1000, 1001, 9),  # one-kernel path, several tiles per group
     (0, 1, 2, 1, 131072, 4000, 4001, 2), # one-kernel path, 8192-point rows
+    (0, 1, 2, 1, 262144, 8000, 8001, 2), # long-transform kernels (512 x 512), float input, voltage sink
+    (0, 2, 2, 1, 1 << 20, 30000, 30001, 2),  # long-transform kernels (1024 x 1024), two channels
 ])
 def test_convolution_voltages(ctx, oracle, case):
     torch, E = _torch(), _E()
@@ -555,6 +557,67 @@ def test_pipeline_4096_input_channels_grid_limit(ctx, oracle):
     err = _pipe_generic(ctx, oracle, L.FMT_MEERKAT8, nchan, 2, 2, raw, ndat, None, c, H, 1, F, npos, nneg, npart,
                         "Coherence", 4, 64, scale=np.float32(scale))
     assert err <= TOL, err
+
+
+@pytest.mark.parametrize("fmt,F,nchan,npart,state,dndim,nbin", [
+    ("meerkat", 1 << 18, 2, 3, "Stokes", 4, 257),       # 512 x 512
+    ("uwb", 1 << 19, 1, 2, "Intensity", 1, 64),         # 1024 x 512
+    ("generic8", 1 << 20, 2, 2, "Coherence", 2, 1024),  # 1024 x 1024, two channels
+    ("meerkat", 1 << 21, 1, 2, "PPQQ", 1, 1024),        # 2048 x 1024
+    ("meerkat", 1 << 22, 1, 1, "Stokes", 4, 512),       # 2048 x 2048 (cfg4's shape, another source and state)
+    ("generic8", 1 << 23, 1, 1, "Coherence", 4, 2048),  # 2048 x 4096: above 2^22 only these kernels exist
+    ("uwb", 1 << 24, 1, 1, "Intensity", 1, 4096),       # 2048 x 8192, the longest transform
+])
+def test_long_convolution_kernels(ctx, oracle, fmt, F, nchan, npart, state, dndim, nbin):
+    """clusterconv.cu "long transforms": convolutions of more than 131072 points (N = P Q, P = 512 ... 2048, Q = 512 ...
+    8192) run as three c2-core kernels with both polarisations of a bin side by side in the spectrum scratch.  Every
+    source format, detection state and factorisation against the oracle pipeline (cfg4, 2048 x 2048, has its own test;
+    tests/test_gpu_variants.py isolates each of the three kernels between the generic ones)."""
+    L = _L()
+    npos, nneg = F // 9, F // 11
+    c = oracle.conv_sizes(0, nchan, 2, F, npos, nneg)
+    rng = np.random.default_rng(F % 1000 + nchan)
+    H = np.exp(1j * rng.uniform(-np.pi, np.pi, (nchan, F))).astype(np.complex64)
+    nsamp = npart * c.nsamp_step + c.nsamp_overlap
+    if fmt == "meerkat":
+        ndat = (nsamp + 255) // 256 * 256
+        raw = synth.meerkat_bytes(ndat, nchan, 2, seed=178)
+        _, scale = oracle.bittable8()
+        err = _pipe_generic(ctx, oracle, L.FMT_MEERKAT8, nchan, 2, 2, raw, ndat, None, c, H, 1, F, npos, nneg, npart,
+                            state, dndim, nbin, scale=np.float32(scale))
+    elif fmt == "uwb":
+        ndat = (nsamp + 2047) // 2048 * 2048
+        raw = synth.uwb_bytes(ndat, 2, seed=179)
+        err = _pipe_generic(ctx, oracle, L.FMT_UWB16, 1, 2, 2, raw, ndat, None, c, H, 1, F, npos, nneg, npart,
+                            state, dndim, nbin)
+    else:
+        ndat = nsamp
+        raw = synth.generic8_bytes(ndat, nchan, 2, 2, seed=180)
+        lut, _ = oracle.bittable8()
+        err = _pipe_generic(ctx, oracle, L.FMT_GENERIC8, nchan, 2, 2, raw, ndat, None, c, H, 1, F, npos, nneg, npart,
+                            state, dndim, nbin, lut=lut)
+    assert err <= TOL, err
+
+
+def test_long_convolution_detected_series(ctx, oracle):
+    """The detected-series sink of the long-transform kernels (digifil with coherent dedispersion of one wide channel)."""
+    torch, E, L = _torch(), _E(), _L()
+    nchan, npart, F, state, dndim = 1, 3, 1 << 18, "Stokes", 4
+    npos, nneg = F // 30, F // 29
+    c = oracle.conv_sizes(0, nchan, 2, F, npos, nneg)
+    ndat = (npart * c.nsamp_step + c.nsamp_overlap + 255) // 256 * 256
+    raw = synth.meerkat_bytes(ndat, nchan, 2, seed=195)
+    _, scale = oracle.bittable8()
+    rng = np.random.default_rng(196)
+    H = np.exp(1j * rng.uniform(-np.pi, np.pi, (nchan, F))).astype(np.complex64)
+    op = oracle.make_pipe(L.FMT_MEERKAT8, nchan, 2, 2, None, np.float32(scale), None, c, H, state, dndim, 0)
+    ref = oracle.pipe_block_detected(op, raw, 0, npart)
+    ud = E.make_unpack_desc(L.FMT_MEERKAT8, nchan, 2, 2, None, np.float32(scale), 1)
+    fd, keep = E.make_fb_desc(False, nchan, 2, 1, F, npos, nneg, H)
+    pipe = E.Pipeline(ctx, ud, fd, keep, state, dndim, 0)
+    det = pipe.execute(torch.from_numpy(raw).cuda(), npart, 0.0, 0.0, first_sample=0).cpu().numpy()
+    assert det.shape == ref.shape
+    assert np.array_equal(det, ref) or synth.relerr(det, ref) <= TOL
 
 
 def test_pipeline_cfg4_single_channel_4m_convolution(ctx, oracle):

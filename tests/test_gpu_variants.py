@@ -21,6 +21,31 @@ VARIANTS = {
 }
 
 
+# clusterconv.cu "long transforms": each of the three c2 kernels alone between the generic kernels (plane-per-polarisation
+# scratch), and the generic three-kernel path the product falls back to for real input
+LONG_VARIANTS = {
+    "long_only_k1": {"B200_BC_K2": "0", "B200_BC_K3": "0"},
+    "long_only_k2": {"B200_BC_K1": "0", "B200_BC_K3": "0"},
+    "long_only_k3": {"B200_BC_K1": "0", "B200_BC_K2": "0"},
+    "long_generic": {"B200_BIG_CONV": "0"},
+}
+
+
+@pytest.mark.parametrize("name", sorted(LONG_VARIANTS))
+def test_long_convolution_variant_matches_oracle(name):
+    if not os.path.exists(DEVLIB):
+        pytest.skip("developer build libb200dsp_dev.so not present")
+    env = dict(os.environ)
+    env.update(LONG_VARIANTS[name])
+    env["B200_LIB"] = DEVLIB
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-x",
+                        "-m", "gpu", "-k", "test_long_convolution_kernels and (262144 or 1048576 or 2097152)",
+                        "-p", "no:cacheprovider"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (name, r.stdout[-2000:], r.stderr[-2000:])
+    assert "3 passed" in r.stdout, r.stdout[-500:]
+
+
 @pytest.mark.parametrize("name", sorted(VARIANTS))
 def test_variant_matches_oracle(name):
     if not os.path.exists(DEVLIB):
