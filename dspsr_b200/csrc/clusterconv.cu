@@ -717,11 +717,25 @@ __global__ void __launch_bounds__(Bc<P>::NT, 512 / Bc<P>::NT) k_bc_cols_fwd(BcAr
   if (tid < 16 * NC) s_h[tid] = big_twiddle<false>(c.blo, c.bhi, (cb * NC + tid % NC) * T * (tid / NC));
   const float2 wbase = big_twiddle<false>(c.blo, c.bhi, n2 * j);
   float2 va[16], vb[16];
+  if (SRC == SRC_GENERIC8 && (reinterpret_cast<uintptr_t>(c.src) & 3u) == 0) {
+    // TFP bytes: the two polarisations of a complex sample are one aligned 32-bit word (BitUnpacker.C:56-75 with
+    // npol = ndim = 2): one load per point instead of two (the kernel's loads are 16-byte granules a row apart: the
+    // number of requests, not of bytes, is what L1TEX pays for)
+    const unsigned* words = static_cast<const unsigned*>(c.src) + (c.first + part * c.step) * c.nchan_in + ic;
 #pragma unroll
-  for (int e = 0; e < 16; e++) {
-    const unsigned n = Q * (j + T * unsigned(e)) + n2;
-    va[e] = cc_load<SRC>(c, s_lut, ic, 0, part, n);
-    vb[e] = cc_load<SRC>(c, s_lut, ic, 1, part, n);
+    for (int e = 0; e < 16; e++) {
+      const unsigned n = Q * (j + T * unsigned(e)) + n2;
+      const unsigned w = __ldg(words + uint64_t(n) * c.nchan_in);
+      va[e] = make_float2(s_lut[w & 255u], s_lut[(w >> 8) & 255u]);
+      vb[e] = make_float2(s_lut[(w >> 16) & 255u], s_lut[w >> 24]);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+      const unsigned n = Q * (j + T * unsigned(e)) + n2;
+      va[e] = cc_load<SRC>(c, s_lut, ic, 0, part, n);
+      vb[e] = cc_load<SRC>(c, s_lut, ic, 1, part, n);
+    }
   }
   c2::fft_pair<P, false>(va, vb, j, buf + col * B::RS, a.twP, CcSync());
   const uint64_t N = uint64_t(P) * Q;

@@ -1153,7 +1153,8 @@ int b200_fb_plan_create(b200_context* cctx, const b200_fb_desc* d, b200_fb_plan*
     pl->Q = 1;
   } else {
     unsigned lgP = (lgN + 1) / 2;
-    if (lgP > 11) lgP = 11;
+    const unsigned lgp_cap = (unsigned)tune_int("B200_LGP_CAP", 11);
+    if (lgP > lgp_cap) lgP = lgp_cap;
     pl->P = 1u << lgP;
     pl->Q = pl->Nc / pl->P;
   }

@@ -260,30 +260,55 @@ __global__ void k_expand_bins(const b200_phase_segment* __restrict__ seg, unsign
                               unsigned* __restrict__ bins, unsigned* __restrict__ hits_last,
                               unsigned* __restrict__ hits_total, BinWeights bw) {
   const double double_nbin = double(nbin);
-  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < ndat; i += uint64_t(gridDim.x) * blockDim.x) {
-    // binary search for the segment containing sample i
-    unsigned lo = 0, hi = nseg - 1;
-    while (lo < hi) {
-      unsigned mid = (lo + hi + 1) >> 1;
-      if (seg[mid].start <= i) lo = mid;
-      else hi = mid - 1;
+  // A warp takes chunks of 32 x 32 consecutive samples, 32 at a time (coalesced stores).  Hits: the lowest lane holding
+  // a bin in an iteration counts its peers, and keeps counting for as long as it leads the same bin -- one pair of
+  // atomics per bin and chunk when bins are wide (cfg4: 35 thousand samples per bin; one pair per warp and iteration
+  // made the kernel atomic-bound), at worst one pair per distinct bin of an iteration as before.
+  constexpr unsigned CHUNK = 32u * 32u;
+  const unsigned lane = threadIdx.x & 31u;
+  const uint64_t warp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5, nwarp = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+  for (uint64_t c0 = warp * CHUNK; c0 < ndat; c0 += nwarp * CHUNK) {           // warp-uniform trip count
+    unsigned my_bin = 0xffffffffu, my_n = 0;
+    for (unsigned it = 0; it < 32u; it++) {
+      const uint64_t i = c0 + it * 32u + lane;
+      unsigned ibin = 0xfffffffeu;                                              // beyond the end: counted by nobody
+      if (i < ndat) {
+        // binary search for the segment containing sample i
+        unsigned lo = 0, hi = nseg - 1;
+        while (lo < hi) {
+          unsigned mid = (lo + hi + 1) >> 1;
+          if (seg[mid].start <= i) lo = mid;
+          else hi = mid - 1;
+        }
+        const b200_phase_segment s = seg[lo];
+        const uint64_t a = s.a0 + (i - s.start) * s.step;            // < 2^53: exact in double
+        const double phi = ldexp(double(a), s.scale_exp);            // exact scaling
+        const double double_ibin = __dmul_rn(phi, double_nbin);      // Fold.C:766
+        ibin = unsigned(double_ibin);                                // Fold.C:767 (truncation)
+        if (bw.w) {
+          const uint64_t iw = (bw.idat_start + i + bw.weight_idat) / bw.ndatperweight;
+          if (iw >= bw.nweights || bw.w[iw] == 0u) ibin = nbin;      // bad_data: binplan = folding_nbin (Fold.C:773-774)
+        }
+        bins[i] = ibin;
+      }
+      const unsigned peers = __match_any_sync(0xffffffffu, ibin);
+      if (ibin < nbin && lane == unsigned(__ffs(peers) - 1)) {
+        const unsigned n = __popc(peers);
+        if (ibin == my_bin) my_n += n;
+        else {
+          if (my_n) {
+            atomicAdd(hits_last + my_bin, my_n);
+            atomicAdd(hits_total + my_bin, my_n);
+          }
+          my_bin = ibin;
+          my_n = n;
+        }
+      }
+      if (c0 + (it + 1u) * 32u >= ndat) break;                                  // warp-uniform
     }
-    const b200_phase_segment s = seg[lo];
-    const uint64_t a = s.a0 + (i - s.start) * s.step;            // < 2^53: exact in double
-    const double phi = ldexp(double(a), s.scale_exp);            // exact scaling
-    const double double_ibin = __dmul_rn(phi, double_nbin);      // Fold.C:766
-    unsigned ibin = unsigned(double_ibin);                       // Fold.C:767 (truncation)
-    if (bw.w) {
-      const uint64_t iw = (bw.idat_start + i + bw.weight_idat) / bw.ndatperweight;
-      if (iw >= bw.nweights || bw.w[iw] == 0u) ibin = nbin;      // bad_data: binplan = folding_nbin (Fold.C:773-774)
-    }
-    bins[i] = ibin;
-    // neighbouring samples mostly share a bin: one atomic per distinct bin of the warp instead of one per lane
-    const unsigned peers = __match_any_sync(__activemask(), ibin);
-    if (ibin < nbin && (threadIdx.x & 31u) == unsigned(__ffs(peers) - 1)) {
-      const unsigned n = __popc(peers);
-      atomicAdd(hits_last + ibin, n);
-      atomicAdd(hits_total + ibin, n);
+    if (my_n) {
+      atomicAdd(hits_last + my_bin, my_n);
+      atomicAdd(hits_total + my_bin, my_n);
     }
   }
 }
@@ -725,7 +750,8 @@ static int fold_set_bins(b200_fold* f, double phi, double pps, uint64_t ndat, ui
   f->seg_pending = true;
   B200_CUDA(cudaMemsetAsync(f->d_hits_last, 0, f->nbin * sizeof(unsigned), ctx->stream));
   const unsigned threads = 256;
-  unsigned grid = (unsigned)std::min<uint64_t>((ndat + threads - 1) / threads, ctx->sm_count * 8);
+  // a warp takes 1024 consecutive samples at a time
+  unsigned grid = (unsigned)std::min<uint64_t>((ndat + threads * 32 - 1) / (threads * 32), ctx->sm_count * 8);
   {
     LaunchScope ls(ctx, KC_BINS);
     k_expand_bins<<<grid, threads, 0, ctx->stream>>>(f->d_seg, (unsigned)nseg, ndat, f->nbin, f->d_bins, f->d_hits_last,

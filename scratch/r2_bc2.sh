@@ -1,3 +1,2 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short -k "long_convolution or convolution_voltages" 2>&1 | grep -v "^$" | tail -30
-timeout 900 python -m pytest tests/test_gpu_variants.py -m gpu -q --tb=short -k "long_" 2>&1 | grep -v "^$" | tail -12
+for i in 1 2 3; do timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=line -k "long_conv or cfg4" 2>&1 | grep -v "^$" | tail -6; done

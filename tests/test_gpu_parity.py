@@ -564,7 +564,7 @@ def test_pipeline_4096_input_channels_grid_limit(ctx, oracle):
     ("uwb", 1 << 19, 1, 2, "Intensity", 1, 64),         # 1024 x 512
     ("generic8", 1 << 20, 2, 2, "Coherence", 2, 1024),  # 1024 x 1024, two channels
     ("meerkat", 1 << 21, 1, 2, "PPQQ", 1, 1024),        # 2048 x 1024
-    ("meerkat", 1 << 22, 1, 1, "Stokes", 4, 512),       # 2048 x 2048 (cfg4's shape, another source and state)
+    ("meerkat", 1 << 22, 1, 1, "Stokes", 4, 4096),      # 2048 x 2048 (cfg4's shape, another source and state)
     ("generic8", 1 << 23, 1, 1, "Coherence", 4, 2048),  # 2048 x 4096: above 2^22 only these kernels exist
     ("uwb", 1 << 24, 1, 1, "Intensity", 1, 4096),       # 2048 x 8192, the longest transform
 ])
