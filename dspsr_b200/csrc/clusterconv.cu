@@ -893,7 +893,31 @@ __global__ void __launch_bounds__(Bc<P>::NT, 512 / Bc<P>::NT) k_bc_cols_inv(BcAr
     }
     return;
   }
-  // fold: the CTA's samples are P groups (one per m1, Q samples apart) of NC consecutive samples
+  // fold: the CTA's samples are P groups (one per m1, Q samples apart) of NC consecutive samples; thread t walks the
+  // groups t, t + NT, ... (16 / NC of them).  Their phase bins are requested now, all at once, and arrive while the
+  // products are detected and staged
+  constexpr unsigned NG = 16 / NC;
+  static_assert(NG * Bc<P>::NT == P, "every thread walks 16 / NC groups");
+  const unsigned* plan = c.sink.bins + uint64_t(partl) * nkeep;
+  unsigned wb[NG][NC];
+  // a group's first sample is a multiple of NC = 4 past -nfilt_pos: when that falls on a 16-byte boundary of the plan
+  // (cfg4 does), one 128-bit load per group instead of four requests that touch 32 lines each
+  static_assert(NC == 4, "vector bin loads assume four samples per group");
+  const bool vec = ((reinterpret_cast<uintptr_t>(plan) >> 2) - np0) % 4u == 0;
+#pragma unroll
+  for (unsigned k = 0; k < NG; k++) {
+    const unsigned u0 = (tid + k * B::NT) * Q + cb * NC - np0;           // unsigned: samples before nfilt_pos wrap to huge values
+    if (vec && u0 < nkeep && u0 + 3u < nkeep) {
+      const uint4 x = __ldg(reinterpret_cast<const uint4*>(plan + u0));
+      wb[k][0] = x.x; wb[k][1] = x.y; wb[k][2] = x.z; wb[k][3] = x.w;
+    } else {
+#pragma unroll
+      for (unsigned bb = 0; bb < NC; bb++) {
+        const unsigned u = u0 + bb;
+        wb[k][bb] = u < nkeep ? __ldg(plan + u) : 0xffffffffu;
+      }
+    }
+  }
   __syncthreads();                       // every thread has gathered the last stage: the pair buffers are free
 #pragma unroll
   for (int e = 0; e < 16; e++) {
@@ -903,7 +927,6 @@ __global__ void __launch_bounds__(Bc<P>::NT, 512 / Bc<P>::NT) k_bc_cols_inv(BcAr
     buf[g * (NC + 1) + col] = make_float4(r[0], r[1], r[2], r[3]);
   }
   __syncthreads();
-  const unsigned* plan = c.sink.bins + uint64_t(partl) * nkeep;
   const uint64_t prof0 = uint64_t(ic) * nbin * nprod;
   uint64_t off[4];
 #pragma unroll
@@ -913,16 +936,14 @@ __global__ void __launch_bounds__(Bc<P>::NT, 512 / Bc<P>::NT) k_bc_cols_inv(BcAr
   // equal bin (segmented scan, as in k_cols_inv_fold) and only the tail lane of each run of lanes issues the REDs
   const unsigned lane = tid & 31u;
   static_assert(P % Bc<P>::NT == 0 && Bc<P>::NT % 32 == 0, "whole warps walk whole groups");
-#pragma unroll 1
-  for (unsigned g = tid; g < P; g += B::NT) {
+#pragma unroll
+  for (unsigned k = 0; k < NG; k++) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     unsigned cur = 0xffffffffu;
-    const unsigned mbase = g * Q + cb * NC - np0;            // unsigned: samples before nfilt_pos wrap to huge values
-    const float4* sgrp = buf + g * (NC + 1);
+    const float4* sgrp = buf + (tid + k * B::NT) * (NC + 1);
 #pragma unroll
     for (unsigned bb = 0; bb < NC; bb++) {
-      const unsigned u = mbase + bb;
-      const unsigned bin = u < nkeep ? __ldg(plan + u) : 0xffffffffu;
+      const unsigned bin = wb[k][bb];
       const float4 x = sgrp[bb];
       if (bin != cur) {
         if (cur < nbin) {                                       // nbin: flagged window; 0xffffffff: discarded sample
@@ -936,6 +957,7 @@ __global__ void __launch_bounds__(Bc<P>::NT, 512 / Bc<P>::NT) k_bc_cols_inv(BcAr
         acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
       }
     }
+    // (combining the NG scans step by step -- 16 independent shuffle chains -- measured the same 0.77 ms at cfg4)
     const unsigned prev = __shfl_up_sync(0xffffffffu, cur, 1);
     const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != cur);
     const unsigned h = 31u - __clz(heads & (0xffffffffu >> (31u - lane)));    // first lane of this lane's run
