@@ -41,6 +41,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 UNIT = "MSamples/s"
+# developer build only: cfg4 on the generic three-kernel path (A/B runs); the traffic figures of the long-transform kernels do not apply
+W_GENERIC_LONG = os.environ.get("B200_BIG_CONV") == "0"
 
 
 def metric_name(rate_in):
@@ -514,6 +516,15 @@ def run_ours(args):
             per_tile = tc["dram_bytes_per_launch"] / (tc["parts_per_launch"] * tc["channels"])
             traffic = per_tile * streams[0]["parts"] * streams[0]["S"]["nin"]
             traffic_dom = traffic / kinfo[dom]["launches_per_block"]
+    if args.workload == "cfg4" and os.path.exists(tp) and not W_GENERIC_LONG:
+        # the long-transform kernels (clusterconv.cu k_bc_*): one launch of each per block of 16 parts
+        with open(tp) as f:
+            tl = json.load(f).get("cfg4_long")
+        if tl:
+            per_part = {k: v / tl["parts_per_launch"] for k, v in tl["dram_bytes_per_launch"].items()}
+            traffic = sum(per_part.values()) * streams[0]["parts"]
+            if dom in per_part:
+                traffic_dom = per_part[dom] * streams[0]["parts"] / kinfo[dom]["launches_per_block"]
     roof = {"bound": "hbm", "achieved": path_gbs, "peak": peak, "unit": "GB/s", "frac": path_gbs / peak,
             "what": "whole path, SURVEY 8(d): algorithmic bytes (one spectrum round trip) per block / block time",
             "alg_bytes_per_block": alg_block,

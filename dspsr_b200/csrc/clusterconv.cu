@@ -676,6 +676,8 @@ struct BcArgs {
   const float2* twQ;    // c2 stage tables
   unsigned P, Q;
   unsigned il;          // 1: float4 (pol 0, pol 1) per bin; 0: planes of N float2 per polarisation
+  int conv_ok;          // generic 8-bit: the table is RN(x (conv_hi + conv_lo)), x = int8(b) + 0.5 (FbSource::conv_ok)
+  float conv_hi, conv_lo;
 };
 
 constexpr unsigned BC_NC = 4;   // columns per CTA of the column kernels
@@ -722,12 +724,34 @@ __global__ void __launch_bounds__(Bc<P>::NT, 512 / Bc<P>::NT) k_bc_cols_fwd(BcAr
     // npol = ndim = 2): one load per point instead of two (the kernel's loads are 16-byte granules a row apart: the
     // number of requests, not of bytes, is what L1TEX pays for)
     const unsigned* words = static_cast<const unsigned*>(c.src) + (c.first + part * c.step) * c.nchan_in + ic;
+    unsigned w[16];
 #pragma unroll
-    for (int e = 0; e < 16; e++) {
-      const unsigned n = Q * (j + T * unsigned(e)) + n2;
-      const unsigned w = __ldg(words + uint64_t(n) * c.nchan_in);
-      va[e] = make_float2(s_lut[w & 255u], s_lut[(w >> 8) & 255u]);
-      vb[e] = make_float2(s_lut[(w >> 16) & 255u], s_lut[w >> 24]);
+    for (int e = 0; e < 16; e++) w[e] = __ldg(words + uint64_t(Q * (j + T * unsigned(e)) + n2) * c.nchan_in);
+    if (a.conv_ok) {
+      // two's-complement table that is RN(x (hi + lo)), x = int8(b) + 0.5, entry by entry (lut_as_arithmetic on the host):
+      // converted arithmetically, bit for bit the table's values, instead of 64 shared-memory gathers per thread
+      // (k1_c2's conversion: the byte, sign bit flipped, dropped into bits 8..15 of the float 32768 reads 32768 + 128 + int8(b))
+#ifdef __CUDA_ARCH__
+      const unsigned long long off2 = pk2(-32895.5f, -32895.5f);
+      const unsigned long long lo2 = pk2(a.conv_lo, a.conv_lo), hi2 = pk2(a.conv_hi, a.conv_hi);
+      auto cv2 = [&](unsigned word, unsigned sel0, unsigned sel1) -> float2 {
+        const unsigned long long x = add2(pk2(__uint_as_float(__byte_perm(word, 0x47000000u, sel0)),
+                                              __uint_as_float(__byte_perm(word, 0x47000000u, sel1))), off2);
+        return up2(fma2(x, hi2, mul2(x, lo2)));
+      };
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        const unsigned x = w[e] ^ 0x80808080u;
+        va[e] = cv2(x, 0x7604, 0x7614);
+        vb[e] = cv2(x, 0x7624, 0x7634);
+      }
+#endif
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        va[e] = make_float2(s_lut[w[e] & 255u], s_lut[(w[e] >> 8) & 255u]);
+        vb[e] = make_float2(s_lut[(w[e] >> 16) & 255u], s_lut[w[e] >> 24]);
+      }
     }
   } else {
 #pragma unroll
@@ -1081,6 +1105,7 @@ static void bc_args(const b200_fb_plan* pl, BcArgs& a, uint64_t part0, unsigned 
   a.c.nfilt_pos = pl->desc.nfilt_pos; a.c.nkeep = pl->nkeep;
   a.A = pl->scratchA; a.Ht = pl->bc_Ht; a.twP = pl->bc_twP; a.twQ = pl->bc_twQ;
   a.P = pl->P; a.Q = pl->Q; a.il = il ? 1u : 0u;
+  a.conv_ok = 0; a.conv_hi = a.conv_lo = 0.f;
 }
 
 template <unsigned P> static void bc_k1_launch(b200_fb_plan* pl, const FbSource& src, const BcArgs& a, unsigned nb) {
@@ -1097,6 +1122,7 @@ int bc_k1(b200_fb_plan* pl, const FbSource& src, uint64_t part0, unsigned nb, bo
   bc_args(pl, a, part0, nb, il);
   a.c.src = src.ptr; a.c.span = src.span; a.c.step = src.step; a.c.first = src.first; a.c.scale = src.scale;
   a.c.sample_swap = src.sample_swap; a.c.lut = src.d_lut;
+  a.conv_ok = src.kind == SRC_GENERIC8 ? src.conv_ok : 0; a.conv_hi = src.conv_hi; a.conv_lo = src.conv_lo;
   LaunchScope ls(pl->ctx, KC_COLS_FWD);
   switch (pl->P) {
     case 512: bc_k1_launch<512>(pl, src, a, nb); break;

@@ -333,6 +333,7 @@ static int pipeline_execute(b200_pipeline* p, const void* d_input, uint64_t inpu
     src.scale = p->desc.unpack.scale;
     src.sample_swap = p->desc.unpack.sample_swap ? p->desc.unpack.sample_swap : 1;
     src.ndim = ndim;
+    if (fmt == B200_FMT_GENERIC8) { src.conv_ok = p->conv_ok; src.conv_hi = p->conv_hi; src.conv_lo = p->conv_lo; }
     if (fmt == B200_FMT_GENERIC8 && ndim == 1)
       B200_REQUIRE(first_sample % 2 == 0, "real 8-bit input must start on an even sample");
   } else {
