@@ -269,20 +269,33 @@ __global__ void k_expand_bins(const b200_phase_segment* __restrict__ seg, unsign
   const uint64_t warp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5, nwarp = (uint64_t(gridDim.x) * blockDim.x) >> 5;
   for (uint64_t c0 = warp * CHUNK; c0 < ndat; c0 += nwarp * CHUNK) {           // warp-uniform trip count
     unsigned my_bin = 0xffffffffu, my_n = 0;
+    // the lane's samples are 32 apart: inside a segment its phase numerator advances by 32 steps per iteration, and the
+    // segment is looked up again only when the lane leaves it (142 warp instructions per 32 samples before, mostly the
+    // search and ldexp)
+    uint64_t seg_end = 0, a = 0, a_step = 0;
+    double scale = 0.0;
+    int sexp = 0;
     for (unsigned it = 0; it < 32u; it++) {
       const uint64_t i = c0 + it * 32u + lane;
       unsigned ibin = 0xfffffffeu;                                              // beyond the end: counted by nobody
       if (i < ndat) {
-        // binary search for the segment containing sample i
-        unsigned lo = 0, hi = nseg - 1;
-        while (lo < hi) {
-          unsigned mid = (lo + hi + 1) >> 1;
-          if (seg[mid].start <= i) lo = mid;
-          else hi = mid - 1;
-        }
-        const b200_phase_segment s = seg[lo];
-        const uint64_t a = s.a0 + (i - s.start) * s.step;            // < 2^53: exact in double
-        const double phi = ldexp(double(a), s.scale_exp);            // exact scaling
+        if (i >= seg_end) {
+          // binary search for the segment containing sample i
+          unsigned lo = 0, hi = nseg - 1;
+          while (lo < hi) {
+            unsigned mid = (lo + hi + 1) >> 1;
+            if (seg[mid].start <= i) lo = mid;
+            else hi = mid - 1;
+          }
+          const b200_phase_segment s = seg[lo];
+          a = s.a0 + (i - s.start) * s.step;                         // < 2^53: exact in double
+          a_step = 32u * s.step;
+          seg_end = s.start + s.count;
+          sexp = s.scale_exp;
+          scale = sexp >= -1000 ? ldexp(1.0, sexp) : 0.0;            // 0: phases below 2^-900, scaled by ldexp itself
+        } else a += a_step;
+        // exact scaling by a power of two (the product of a 53-bit integer and 2^sexp is a normal double)
+        const double phi = scale != 0.0 ? __dmul_rn(double(a), scale) : ldexp(double(a), sexp);
         const double double_ibin = __dmul_rn(phi, double_nbin);      // Fold.C:766
         ibin = unsigned(double_ibin);                                // Fold.C:767 (truncation)
         if (bw.w) {
