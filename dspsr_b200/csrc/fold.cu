@@ -258,13 +258,14 @@ struct BinWeights {
 
 __global__ void k_expand_bins(const b200_phase_segment* __restrict__ seg, unsigned nseg, uint64_t ndat, unsigned nbin,
                               unsigned* __restrict__ bins, unsigned* __restrict__ hits_last,
-                              unsigned* __restrict__ hits_total, BinWeights bw) {
+                              unsigned* __restrict__ hits_total, BinWeights bw, unsigned iters) {
   const double double_nbin = double(nbin);
-  // A warp takes chunks of 32 x 32 consecutive samples, 32 at a time (coalesced stores).  Hits: the lowest lane holding
+  // A warp takes chunks of 32 x iters consecutive samples, 32 at a time (coalesced stores; iters = 32 for long blocks,
+  // fewer when the block would not fill the machine: cfg5's sub-bands).  Hits: the lowest lane holding
   // a bin in an iteration counts its peers, and keeps counting for as long as it leads the same bin -- one pair of
   // atomics per bin and chunk when bins are wide (cfg4: 35 thousand samples per bin; one pair per warp and iteration
   // made the kernel atomic-bound), at worst one pair per distinct bin of an iteration as before.
-  constexpr unsigned CHUNK = 32u * 32u;
+  const unsigned CHUNK = 32u * iters;
   const unsigned lane = threadIdx.x & 31u;
   const uint64_t warp = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5, nwarp = (uint64_t(gridDim.x) * blockDim.x) >> 5;
   for (uint64_t c0 = warp * CHUNK; c0 < ndat; c0 += nwarp * CHUNK) {           // warp-uniform trip count
@@ -275,7 +276,7 @@ __global__ void k_expand_bins(const b200_phase_segment* __restrict__ seg, unsign
     uint64_t seg_end = 0, a = 0, a_step = 0;
     double scale = 0.0;
     int sexp = 0;
-    for (unsigned it = 0; it < 32u; it++) {
+    for (unsigned it = 0; it < iters; it++) {
       const uint64_t i = c0 + it * 32u + lane;
       unsigned ibin = 0xfffffffeu;                                              // beyond the end: counted by nobody
       if (i < ndat) {
@@ -763,12 +764,15 @@ static int fold_set_bins(b200_fold* f, double phi, double pps, uint64_t ndat, ui
   f->seg_pending = true;
   B200_CUDA(cudaMemsetAsync(f->d_hits_last, 0, f->nbin * sizeof(unsigned), ctx->stream));
   const unsigned threads = 256;
-  // a warp takes 1024 consecutive samples at a time
-  unsigned grid = (unsigned)std::min<uint64_t>((ndat + threads * 32 - 1) / (threads * 32), ctx->sm_count * 8);
+  // a warp takes 32 x iters consecutive samples at a time: 1024 when that still leaves four warps' worth of chunks for
+  // every warp slot of the machine, fewer for short blocks
+  const uint64_t slots = uint64_t(ctx->sm_count) * 8 * (threads / 32) * 4;
+  const unsigned iters = (unsigned)std::min<uint64_t>(32, std::max<uint64_t>(1, ndat / (32 * slots)));
+  unsigned grid = (unsigned)std::min<uint64_t>((ndat + uint64_t(threads) * iters - 1) / (uint64_t(threads) * iters), ctx->sm_count * 8);
   {
     LaunchScope ls(ctx, KC_BINS);
     k_expand_bins<<<grid, threads, 0, ctx->stream>>>(f->d_seg, (unsigned)nseg, ndat, f->nbin, f->d_bins, f->d_hits_last,
-                                                    f->d_hits_total, bw);
+                                                    f->d_hits_total, bw, iters);
   }
   f->ndat_total += ndat;
   B200_CUDA(cudaGetLastError());
