@@ -439,7 +439,12 @@ def expand_segments_numpy(segs, nbin, ndat):
     for s in segs:
         t = np.arange(s.count, dtype=np.uint64)
         a = np.uint64(s.a0) + t * np.uint64(s.step)
-        phi = np.ldexp(a.astype(np.float64), s.scale_exp)
+        # k_expand_bins scales by multiplying with the power of two (exact: the product is a normal double) and keeps
+        # ldexp for phases below 2^-900
+        if s.scale_exp >= -1000:
+            phi = a.astype(np.float64) * np.ldexp(1.0, s.scale_exp)
+        else:
+            phi = np.ldexp(a.astype(np.float64), s.scale_exp)
         bins[s.start:s.start + s.count] = (phi * float(nbin)).astype(np.uint32)
     return bins
 

@@ -84,6 +84,10 @@ def test_phase_segments_equal_sequential_recurrence(oracle):
             assert np.array_equal(ref, orc) and np.array_equal(got, ref), (phi, pps, n, nbin)
             assert phi_end == phi_end_ref == phi_end_orc
             assert sum(s.count for s in segs) == n
+            for s in segs:   # the device scales by a multiplication with 2^scale_exp: the same double as ldexp
+                a = np.uint64(s.a0) + np.arange(min(s.count, 64), dtype=np.uint64) * np.uint64(s.step)
+                if s.scale_exp >= -1000:
+                    assert np.array_equal(a.astype(np.float64) * np.ldexp(1.0, s.scale_exp), np.ldexp(a.astype(np.float64), s.scale_exp))
     segs, _ = E.phase_segments(0.3, 7.16e-6, 466000)     # a cfg1 block of 64 parts: a handful of segments
     assert len(segs) < 100
     assert E.phase_segments(0.3, 1e-3, 0)[0] == []        # empty input
@@ -363,3 +367,55 @@ def test_tile_image_spectrum_layout_spec():
             assert np.unique(zi(gl, 1, Q - 1 - kk) & 15).size == 16
             # the mirror element Q-1-k2 shares the swizzled low part: slot = (255 - m) * 32 + same low bits
             assert np.array_equal(zi(gl, 0, Q - 1 - kk) - (255 - (kk >> 2)) * 32, zi(gl, 0, kk) - (kk >> 2) * 32)
+
+
+def test_long_transform_factorisation_spec():
+    """Executable statement of the arithmetic of the long-transform kernels (clusterconv.cu k_bc_cols_fwd / k_bc_rows /
+    k_bc_cols_inv): N = P Q, n = Q n1 + n2, k = k1 + P k2.  Thread j of a column (T = P/16 threads)
+    or of a row (NT = Q/16) holds elements j + T e, e < 16, and builds its twiddles from ONE table value per thread times a
+    16-entry table per tile; the row pass reads the response from the transposed copy Ht[k1][k2] = H[k1 + P k2] and runs
+    its inverse transform as conj(FFT(conj .)); the scratch holds both polarisations of a bin side by side.  The chain
+    must equal the plain overlap-save convolution N * ifft(fft(x) * H) of both polarisations."""
+    rng = np.random.default_rng(5)
+    P, Q = 64, 32
+    N, T, NT = P * Q, P // 16, Q // 16
+    x = (rng.standard_normal((2, N)) + 1j * rng.standard_normal((2, N)))
+    H = np.exp(1j * rng.uniform(-np.pi, np.pi, N))
+    W = lambda m: np.exp(-2j * np.pi * (np.asarray(m) % N) / N)          # the two-level table of W_N (big_twiddle)
+
+    # K1: columns n2; register e of thread j = row k1 = j + T e; twiddle W_N^(n2 k1) = W_N^(n2 j) * W_N^(n2 T e)
+    A = np.zeros((P, Q, 2), dtype=complex)                               # [k1][n2][pol]: one float4 per bin
+    for n2 in range(Q):
+        col = np.fft.fft(x[:, n2::Q], axis=1)                            # over n1, both polarisations
+        for j in range(T):
+            wbase = W(n2 * j)
+            for e in range(16):
+                k1 = j + T * e
+                A[k1, n2, :] = col[:, k1] * (wbase * W(n2 * T * e))
+    # K2: one row k1 per CTA; response row from the transposed copy; inverse = conj(FFT(conj)); W_N^-(k1 m2) factorised
+    Ht = H.reshape(Q, P).T.copy()                                        # Ht[k1][k2] = H[k1 + P k2]
+    assert all(Ht[k1, k2] == H[k1 + P * k2] for k1 in (0, 1, P - 1) for k2 in (0, 3, Q - 1))
+    for k1 in range(P):
+        row = np.fft.fft(A[k1], axis=0) * Ht[k1][:, None]                # over n2 -> k2
+        inv = np.conj(np.fft.fft(np.conj(row), axis=0))                  # over k2 -> m2 (unnormalised inverse)
+        assert np.allclose(inv, np.fft.ifft(row, axis=0) * Q)
+        for tid in range(NT):
+            wown = np.conj(W(k1 * tid))
+            for e in range(16):
+                m2 = tid + NT * e
+                A[k1, m2, :] = inv[m2] * (wown * np.conj(W(k1 * NT * e)))
+    # K3: columns m2; register e of thread j = segment m1 = j + T e: sample Q m1 + m2
+    y = np.zeros((2, N), dtype=complex)
+    for m2 in range(Q):
+        col = np.conj(np.fft.fft(np.conj(A[:, m2, :]), axis=0))          # inverse over k1 -> m1
+        for m1 in range(P):
+            y[:, Q * m1 + m2] = col[m1]
+    ref = np.fft.ifft(np.fft.fft(x, axis=1) * H[None, :], axis=1) * N
+    assert np.allclose(y, ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    # K3's fold walk: thread t owns the groups t, t + NT3, ... of NC = 4 consecutive samples; group g starts at sample
+    # g Q + 4 cb - nfilt_pos of the part's bin plan: a 16-byte boundary of the plan exactly when (plan/4 - nfilt_pos) % 4 == 0
+    for npos in (0, 3, 4, 534848):
+        for base_words in (0, 1, 4):
+            vec = (base_words - npos) % 4 == 0
+            starts = [(base_words + g * Q + 4 * cb - npos) % 4 for g in (0, 5) for cb in (0, 7)]
+            assert all((s == 0) == vec for s in starts)
