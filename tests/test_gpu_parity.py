@@ -561,7 +561,7 @@ def test_pipeline_4096_input_channels_grid_limit(ctx, oracle):
 
 @pytest.mark.parametrize("fmt,F,nchan,npart,state,dndim,nbin", [
     ("meerkat", 1 << 18, 2, 3, "Stokes", 4, 257),       # 512 x 512
-    ("uwb", 1 << 19, 1, 2, "Intensity", 1, 64),         # 1024 x 512
+    ("uwb", 1 << 19, 1, 2, "Intensity", 1, 256),        # 1024 x 512
     ("generic8", 1 << 20, 2, 2, "Coherence", 2, 1024),  # 1024 x 1024, two channels
     ("meerkat", 1 << 21, 1, 2, "PPQQ", 1, 1024),        # 2048 x 1024
     ("meerkat", 1 << 22, 1, 1, "Stokes", 4, 4096),      # 2048 x 2048 (cfg4's shape, another source and state)
