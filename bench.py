@@ -517,7 +517,7 @@ def run_ours(args):
             traffic = per_tile * streams[0]["parts"] * streams[0]["S"]["nin"]
             traffic_dom = traffic / kinfo[dom]["launches_per_block"]
     if args.workload == "cfg4" and os.path.exists(tp) and not W_GENERIC_LONG:
-        # the long-transform kernels (clusterconv.cu k_bc_*): one launch of each per block of 16 parts
+        # the long-transform kernels (longconv.cu k_bc_*): one launch of each per block of 16 parts
         with open(tp) as f:
             tl = json.load(f).get("cfg4_long")
         if tl:

@@ -130,7 +130,7 @@ struct b200_fb_plan {
   int cc_clusters;            // clusters of 16 CTAs the device keeps resident (0 = path not available)
   void* cc_xch;               // exchange matrices of the global-memory variant of its two transposes, or null
   void* cc_bar;               // arrival counters of the counter-barrier variant, or null
-  // longer convolutions (N = P Q > 131072, clusterconv.cu "long transforms"): three kernels on the c2 core
+  // longer convolutions (N = P Q > 131072, longconv.cu): three kernels on the c2 core
   bool bc_ok;                 // the plan's P and Q are planned for and the kernels fit the device
   float2 *bc_twP, *bc_twQ;    // c2 stage tables of P and Q
   float2* bc_Ht;              // the response transposed to [channel][P][Q] (rows of the row pass contiguous), or null
@@ -155,7 +155,7 @@ bool cc_applies(const b200_fb_plan* plan, const FbSource& src, const FbSink& sin
 // B200_OK, an error, or CC_NOT_RUN: the launch was refused for lack of residency and the path is now disabled
 enum { CC_NOT_RUN = 1000 };
 int cc_run(b200_fb_plan* plan, const FbSource& src, const FbSink& sink, uint64_t part0, unsigned nb);
-// clusterconv.cu, long transforms: which of the three passes the c2 kernels take over (all three -> the spectrum
+// longconv.cu: which of the three passes the c2 kernels take over (all three -> the spectrum
 // scratch holds both polarisations of a bin side by side, otherwise the generic kernels' plane per polarisation)
 int bc_plan_init(b200_fb_plan* plan);
 void bc_plan_free(b200_fb_plan* plan);

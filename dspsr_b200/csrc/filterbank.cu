@@ -869,7 +869,7 @@ int fb_run(b200_fb_plan* pl, const FbSource& src, const FbSink& sink, uint64_t n
     const bool skip_k2 = pl->Q == 1 && !pl->desc.input_real && !pl->conv_path;
     // ---- K1 ----
     const bool k1_fast = pl->fast_k1 && src.kind <= SRC_CASPSR8 && (src.kind == SRC_F32 || (src.step % 4 == 0 && (reinterpret_cast<uintptr_t>(src.ptr) & 3) == 0));
-    // long convolutions (N > 131072): c2 kernels of clusterconv.cu; all three -> polarisations interleaved in the scratch
+    // long convolutions (N > 131072): c2 kernels of longconv.cu; all three -> polarisations interleaved in the scratch
     const bool bc1 = bc_k1_applies(pl, src), bc2 = bc_k2_applies(pl), bc3 = bc_k3_applies(pl);
     const bool bc_il = bc1 && bc2 && bc3;
     B200_REQUIRE(bc_il || pl->Nc <= (1u << 22), "transforms of more than 2^22 points: source format %d is not built", src.kind);
@@ -1247,7 +1247,7 @@ int b200_fb_plan_create(b200_context* cctx, const b200_fb_desc* d, b200_fb_plan*
   if (rc == B200_OK) rc = cc_plan_init(pl);
   if (rc == B200_OK) rc = bc_plan_init(pl);
   if (rc == B200_OK && pl->Nc > (1u << 22) && !pl->bc_ok) {
-    // 2^23 and 2^24 points exist only as the long-transform kernels of clusterconv.cu (rows of 4096 / 8192 points)
+    // 2^23 and 2^24 points exist only as the long-transform kernels of longconv.cu (rows of 4096 / 8192 points)
     set_error("transforms of more than 2^22 complex points are built for single-channel convolution of complex "
               "dual-polarisation input only (got %u points)", pl->Nc);
     rc = B200_ERR_UNSUPPORTED;

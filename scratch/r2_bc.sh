@@ -1,5 +1,5 @@
 #!/bin/bash
-# long-transform kernels (clusterconv.cu k_bc_*): parity (new tests, every convolution test, the isolating variants),
+# long-transform kernels (longconv.cu k_bc_*): parity (new tests, every convolution test, the isolating variants),
 # then cfg4 A/B: generic three-kernel path against the c2 kernels, each alone and together
 mkdir -p gpurun_out/r2s
 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "long_convolution or convolution_voltages or cfg4 or one_kernel" 2>&1 | tail -4

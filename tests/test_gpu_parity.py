@@ -569,7 +569,7 @@ def test_pipeline_4096_input_channels_grid_limit(ctx, oracle):
     ("uwb", 1 << 24, 1, 1, "Intensity", 1, 4096),       # 2048 x 8192, the longest transform
 ])
 def test_long_convolution_kernels(ctx, oracle, fmt, F, nchan, npart, state, dndim, nbin):
-    """clusterconv.cu "long transforms": convolutions of more than 131072 points (N = P Q, P = 512 ... 2048, Q = 512 ...
+    """longconv.cu: convolutions of more than 131072 points (N = P Q, P = 512 ... 2048, Q = 512 ...
     8192) run as three c2-core kernels with both polarisations of a bin side by side in the spectrum scratch.  Every
     source format, detection state and factorisation against the oracle pipeline (cfg4, 2048 x 2048, has its own test;
     tests/test_gpu_variants.py isolates each of the three kernels between the generic ones)."""

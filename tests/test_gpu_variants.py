@@ -21,7 +21,7 @@ VARIANTS = {
 }
 
 
-# clusterconv.cu "long transforms": each of the three c2 kernels alone between the generic kernels (plane-per-polarisation
+# longconv.cu: each of the three c2 kernels alone between the generic kernels (plane-per-polarisation
 # scratch), and the generic three-kernel path the product falls back to for real input
 LONG_VARIANTS = {
     "long_only_k1": {"B200_BC_K2": "0", "B200_BC_K3": "0"},

@@ -370,7 +370,7 @@ def test_tile_image_spectrum_layout_spec():
 
 
 def test_long_transform_factorisation_spec():
-    """Executable statement of the arithmetic of the long-transform kernels (clusterconv.cu k_bc_cols_fwd / k_bc_rows /
+    """Executable statement of the arithmetic of the long-transform kernels (longconv.cu k_bc_cols_fwd / k_bc_rows /
     k_bc_cols_inv): N = P Q, n = Q n1 + n2, k = k1 + P k2.  Thread j of a column (T = P/16 threads)
     or of a row (NT = Q/16) holds elements j + T e, e < 16, and builds its twiddles from ONE table value per thread times a
     16-entry table per tile; the row pass reads the response from the transposed copy Ht[k1][k2] = H[k1 + P k2] and runs
